@@ -1,0 +1,103 @@
+"""ctypes binding of libdqomap_b200.so (include/dqo_b200.h).
+
+The library is the product: there is no CPU or PyTorch fallback.  `lib()` raises if the shared object is
+missing or its ABI version does not match this file.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdqomap_b200.so")
+ABI_VERSION = 1
+
+ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_WORDS = 0, 1, 2, 3, 8
+ADAM_MAX_TENSORS = 16
+
+c_p = C.c_void_p
+
+
+class RastSettings(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("D", C.c_int32), ("M", C.c_int32), ("W", C.c_int32), ("H", C.c_int32),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("scale_modifier", C.c_float), ("color_sigma", C.c_float), ("opaque_threshold", C.c_float),
+        ("depth_threshold", C.c_float), ("normal_threshold", C.c_float), ("T_threshold", C.c_float),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("need_n_touched", C.c_int32),
+    ]
+
+
+class AdamTensor(C.Structure):
+    _fields_ = [
+        ("param", c_p), ("grad", c_p), ("exp_avg", c_p), ("exp_avg_sq", c_p),
+        ("numel", C.c_int64), ("lr", C.c_float), ("row_width", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/dqo_b200.h declaration by declaration
+PROTOTYPES = {
+    "dqo_abi_version": (C.c_int, []),
+    "dqo_last_error": (C.c_char_p, []),
+    "dqo_rast_geom_bytes": (C.c_size_t, [C.c_int32]),
+    "dqo_rast_binning_bytes": (C.c_size_t, [C.c_int64]),
+    "dqo_rast_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "dqo_rast_forward": (C.c_int, [C.POINTER(RastSettings)] + [c_p] * 12 + [c_p, c_p, C.c_int64, c_p] + [c_p] * 12),
+    "dqo_rast_backward": (C.c_int, [C.POINTER(RastSettings)] + [c_p] * 11 + [c_p, c_p, C.c_int64, c_p, c_p]
+                          + [c_p] * 3 + [c_p] * 9 + [c_p]),
+    "dqo_mark_visible": (C.c_int, [C.c_int32, c_p, c_p, c_p, c_p, c_p]),
+    "dqo_rast_export_state": (C.c_int, [C.POINTER(RastSettings), c_p, c_p, C.c_int64, c_p, c_p] + [c_p] * 10 + [c_p]),
+    "dqo_knn_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "dqo_knn3": (C.c_int, [C.c_int32, c_p, c_p, c_p, c_p, C.c_size_t, c_p]),
+    "dqo_accumulate_error": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [c_p] * 5
+                             + [C.c_float, C.c_float, C.c_float, C.c_int32] + [c_p] * 7 + [c_p]),
+    "dqo_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "dqo_masked_l1_loss": (C.c_int, [C.c_int32, C.c_int32] + [c_p] * 6 + [C.c_float, C.c_float, C.c_float]
+                           + [c_p] * 5 + [c_p]),
+    "dqo_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float,
+                                c_p, C.c_int32, c_p]),
+    "dqo_quadric_init": (C.c_int, [C.c_int32] + [c_p] * 7 + [c_p]),
+    "dqo_quadric_project": (C.c_int, [C.c_int32] + [c_p] * 6 + [c_p]),
+    "dqo_quadric_refine": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [c_p] * 4
+                           + [C.c_float, C.c_float, C.c_float] + [c_p] * 4 + [c_p]),
+}
+
+_lib = None
+
+
+class DqoError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the C-ABI library; fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DqoError(
+            "libdqomap_b200.so not found at %s: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    handle = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(handle, name)  # AttributeError if the export is missing
+        fn.restype = res
+        fn.argtypes = args
+    if handle.dqo_abi_version() != ABI_VERSION:
+        raise DqoError("libdqomap_b200.so ABI %d != binding ABI %d; rebuild" % (handle.dqo_abi_version(), ABI_VERSION))
+    _lib = handle
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().dqo_last_error().decode("utf-8", "replace")
+        raise DqoError("%s failed (code %d): %s" % (what, code, msg))
+
+
+def ptr(t):
+    """Device/host pointer of a tensor as an int (None -> NULL; empty tensors -> NULL like the reference's
+    null data_ptr convention)."""
+    if t is None:
+        return None
+    if t.numel() == 0:
+        return None
+    return t.data_ptr()

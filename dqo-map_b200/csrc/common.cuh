@@ -1,0 +1,188 @@
+// Shared declarations for the B200-native DQO-MAP hot path (sm_100a only).
+//
+// Arithmetic policy: every value that feeds an integer decision of the reference (depth sort key, pixel
+// centre, radius, tile rectangle, alpha / transmittance thresholds) is computed with explicit
+// __fmul_rn/__fadd_rn/__fmaf_rn in the exact operation order that nvcc 12.9 emits for the reference
+// sources on sm_100a (decoded from SASS, see DESIGN.md "Bit-exactness").  The compiler is therefore not
+// free to re-contract them and oracle/ can restate them with fmaf() on the CPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/dqo_b200.h"
+
+#define DQO_TILE 16
+#define DQO_TILE_PIX 256
+#define DQO_ABI_VERSION 1
+
+namespace dqo {
+
+void set_error(const char *fmt, ...);
+
+#define DQO_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            dqo::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return (int)_e;                                                                   \
+        }                                                                                     \
+    } while (0)
+
+#define DQO_LAUNCH_CHECK(name, debug, stream)                                                 \
+    do {                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e == cudaSuccess && (debug)) _e = cudaStreamSynchronize(stream);                 \
+        if (_e != cudaSuccess) {                                                              \
+            dqo::set_error("kernel %s failed: %s", name, cudaGetErrorString(_e));             \
+            return (int)_e;                                                                   \
+        }                                                                                     \
+    } while (0)
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- exact-op helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fadd_rn(a, -b); }
+__device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float frcp(float a) { return __frcp_rn(a); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+
+// row `c` of a column-major 4x4 applied to (x,y,z,1): m[c]*x + m[c+4]*y + m[c+8]*z (+ m[c+12])
+// reference order (auxiliary.h:59-77 as compiled): FMUL(y), FFMA(x), FFMA(z), FADD(w)
+__device__ __forceinline__ float xform_row(const float *__restrict__ m, int c, float x, float y, float z) {
+    float t = fmul(y, m[c + 4]);
+    t = ffma(x, m[c], t);
+    t = ffma(z, m[c + 8], t);
+    return fadd(t, m[c + 12]);
+}
+__device__ __forceinline__ float xform_row3(const float *__restrict__ m, int c, float x, float y, float z) {
+    float t = fmul(y, m[c + 4]);
+    t = ffma(x, m[c], t);
+    return ffma(z, m[c + 8], t);
+}
+
+// a0*b0 + a1*b1 + a2*b2 as the reference compiles it: FMUL(term1), FFMA(term0), FFMA(term2)
+__device__ __forceinline__ float dot3_ref(float a0, float b0, float a1, float b1, float a2, float b2) {
+    float t = fmul(a1, b1);
+    t = ffma(a0, b0, t);
+    return ffma(a2, b2, t);
+}
+
+// Quaternion (r,x,y,z), NOT normalised (forward.cu:211).  Entries of the GLM matrix
+// R = mat3(col0 | col1 | col2) of forward.cu:218-221, rounded exactly as compiled.
+struct QuatMat {
+    float c0[3], c1[3], c2[3]; // GLM columns: R[col][row]
+};
+__device__ __forceinline__ QuatMat quat_to_glm(float r, float x, float y, float z) {
+    const float xz = fmul(x, z), rx = fmul(r, x), rz = fmul(r, z);
+    const float yy = fmul(y, y), zz = fmul(z, z);
+    const float xz_p_ry = ffma(r, y, xz), xz_m_ry = ffma(-r, y, xz);
+    const float yz_m_rx = ffma(y, z, -rx), yz_p_rx = ffma(y, z, rx);
+    const float xy_m_rz = ffma(x, y, -rz), xy_p_rz = ffma(x, y, rz);
+    float s0 = fadd(yy, zz), s1 = ffma(x, x, zz), s2 = ffma(x, x, yy);
+    QuatMat q;
+    q.c0[0] = fadd(-fadd(s0, s0), 1.f);
+    q.c0[1] = fadd(xy_m_rz, xy_m_rz);
+    q.c0[2] = fadd(xz_p_ry, xz_p_ry);
+    q.c1[0] = fadd(xy_p_rz, xy_p_rz);
+    q.c1[1] = fadd(-fadd(s1, s1), 1.f);
+    q.c1[2] = fadd(yz_m_rx, yz_m_rx);
+    q.c2[0] = fadd(xz_m_ry, xz_m_ry);
+    q.c2[1] = fadd(yz_p_rx, yz_p_rx);
+    q.c2[2] = fadd(-fadd(s2, s2), 1.f);
+    return q;
+}
+
+// 3D covariance (forward.cu:202-235): M = S*R, Sigma = M^T M, upper triangle.
+__device__ __forceinline__ void cov3d_from_scale_rot(float sx, float sy, float sz, float mod, float r, float x,
+                                                     float y, float z, float *cov) {
+    const QuatMat q = quat_to_glm(r, x, y, z);
+    const float s[3] = {fmul(mod, sx), fmul(mod, sy), fmul(mod, sz)};
+    float M0[3], M1[3], M2[3]; // M[col][row] = s[row] * R[col][row]
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        M0[k] = fmul(s[k], q.c0[k]);
+        M1[k] = fmul(s[k], q.c1[k]);
+        M2[k] = fmul(s[k], q.c2[k]);
+    }
+    cov[0] = dot3_ref(M0[0], M0[0], M0[1], M0[1], M0[2], M0[2]);
+    cov[1] = dot3_ref(M1[0], M0[0], M1[1], M0[1], M1[2], M0[2]);
+    cov[2] = dot3_ref(M2[0], M0[0], M2[1], M0[1], M2[2], M0[2]);
+    cov[3] = dot3_ref(M1[0], M1[0], M1[1], M1[1], M1[2], M1[2]);
+    cov[4] = dot3_ref(M2[0], M1[0], M2[1], M1[1], M2[2], M1[2]);
+    cov[5] = dot3_ref(M2[0], M2[0], M2[1], M2[1], M2[2], M2[2]);
+}
+
+// argMin / argMax with the reference's tie rules (forward.cu:20-52)
+__device__ __forceinline__ int arg_min3(float a, float b, float c) {
+    if (a <= b && a <= c) return 0;
+    if (b <= a && b <= c) return 1;
+    return 2;
+}
+__device__ __forceinline__ int arg_max3(float a, float b, float c) {
+    if (a >= b && a >= c) return 0;
+    if (b >= a && b >= c) return 1;
+    return 2;
+}
+
+// Pixel ray (forward.cu:92-100)
+__device__ __forceinline__ float3 pixel_ray(uint32_t px, uint32_t py, float fx, float fy, float cx, float cy) {
+    float rx = fdiv(fsub((float)px, cx), fx);
+    float ry = fdiv(fsub((float)py, cy), fy);
+    float n2 = fadd(ffma(rx, rx, fmul(ry, ry)), 1.0f);
+    float inv = frcp(fsqrt(n2));
+    return make_float3(fmul(rx, inv), fmul(ry, inv), inv); // 1.0 * inv is exact
+}
+
+__host__ __device__ inline uint32_t higher_msb(uint32_t n) { // rasterizer_impl.cu:35-50 == bit length
+    uint32_t b = 0;
+    while (n >> b && b < 32) b++;
+    return b;
+}
+
+// ---- private workspace layouts ------------------------------------------------------------------
+// geometry buffer: per-Gaussian splat records + depth-sort scratch
+struct GeomLayout {
+    size_t rec;        // float4[3P]: {x,y,conic.x,conic.y} {conic.z,opacity,power_reject,depth} {r,g,b,0}
+    size_t depth_key;  // u32[P] float bits of view depth, 0xFFFFFFFF when the Gaussian emits no instance
+    size_t depth_key2; // u32[P] sorted keys (scratch)
+    size_t ids;        // u32[P] iota
+    size_t order;      // u32[P] Gaussian ids in (depth, id) order
+    size_t tiles;      // u32[P] tiles_touched
+    size_t offsets;    // u32[P] inclusive scan of tiles_touched in depth-rank order
+    size_t rect;       // uint2[P] {min.x | max.x<<16, min.y | max.y<<16}
+    size_t clamped;    // u8[P] bit c = colour channel c clamped (forward.cu:151-153)
+    size_t gacc;       // f32[16P] gradient accumulators of the backward blend (see DQO_GACC_FLOATS)
+    size_t cub;        // CUB temp storage
+    size_t cub_bytes;
+    size_t total;
+};
+// binning buffer: instance lists
+struct BinLayout {
+    size_t keys_in, keys_out; // u32[C] tile id per instance (unsorted / sorted)
+    size_t vals_in, vals_out; // u32[C] Gaussian id per instance; vals_out == reference point_list
+    size_t cub;
+    size_t cub_bytes;
+    size_t total;
+};
+// image buffer: per-tile ranges and tile-major per-pixel state for the backward pass
+struct ImgLayout {
+    size_t ranges;     // uint2[T]
+    size_t n_contrib;  // u32[T*256]
+    size_t final_T;    // f32[T*256]
+    size_t hit_geo;    // f32[6][T*256]: hit_normal_c.xyz, hit_point_c.xyz (forward.cu:807-808)
+    size_t total;
+    int tiles_x, tiles_y, T;
+};
+
+int make_geom_layout(int P, GeomLayout *L);
+int make_bin_layout(int64_t C, BinLayout *L);
+void make_img_layout(int W, int H, ImgLayout *L);
+
+// per-Gaussian gradient accumulator written by the backward blend (16 floats = 64 B)
+// {dmean2D.x, dmean2D.y, dconic.x, dconic.y | dconic.w, dopacity, dcolor.r, dcolor.g | dcolor.b, dmean3D.xyz | drot.rxyz}
+#define DQO_GACC_FLOATS 16
+
+} // namespace dqo

@@ -1,0 +1,614 @@
+// Backward rasterization: reverse blend with warp-level pre-reduction, then one fused per-Gaussian kernel.
+//
+// Replaces CudaRasterizer::Rasterizer::backward (reference RAST/cuda_rasterizer/rasterizer_impl.cu:445-564):
+//   BACKWARD::renderCUDA_flat  backward.cu:808-1066  -> render_backward_kernel
+//   computeCov2DCUDA           backward.cu:273-422   \
+//   BACKWARD::preprocessCUDA   backward.cu:492-548    > gaussian_backward_kernel (one pass, no dL_dcov3D round trip)
+//   computeColorFromSH (bwd)   backward.cu:152-268   /
+//   computeCov3D (bwd)         backward.cu:426-487  /
+// The reference issues 9 global float atomics per contributing (pixel, Gaussian) pair.  Here the 9 partial
+// gradients of a warp are summed with a 12-shuffle recursive-halving reduction and written with one
+// 9-lane RED into a 64-byte per-Gaussian accumulator record; the per-Gaussian kernel then produces every
+// output tensor densely (zeros included), so no gradient tensor has to be pre-zeroed by the caller.
+#include "common.cuh"
+
+namespace dqo {
+
+struct RenderBwdArgs {
+    int W, H, grid_x;
+    float fx, fy, cx, cy;
+    float depth_thr, normal_thr;
+    const uint2 *ranges;
+    const uint32_t *point_list;
+    const float4 *rec;
+    const float *view, *means3D, *scales, *rotations, *bg;
+    const uint32_t *n_contrib;
+    const float *final_T;
+    const float *hit_geo;
+    size_t plane;
+    const float *dL_dpix, *dL_ddepth;
+    const int *hit_image;
+    float *gacc;
+};
+
+// Sum 9 per-lane values over the warp; on return lanes with (lane & 1) == 0 whose slot index < 9 hold the
+// total of value `slot` (see slot_of_lane).  12 shuffles instead of 45.
+__device__ __forceinline__ float warp_reduce9(const float v[9], int lane) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    float w[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const float lo = v[k], hi = (k + 5 < 9) ? v[k + 5] : 0.f;
+        const float send = b4 ? lo : hi;
+        const float keep = b4 ? hi : lo;
+        w[k] = keep + __shfl_xor_sync(FULL, send, 16);
+    }
+    float u[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float lo = w[k], hi = (k + 3 < 5) ? w[k + 3] : 0.f;
+        const float send = b3 ? lo : hi;
+        const float keep = b3 ? hi : lo;
+        u[k] = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+    float t[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const float lo = u[k], hi = (k + 2 < 3) ? u[k + 2] : 0.f;
+        const float send = b2 ? lo : hi;
+        const float keep = b2 ? hi : lo;
+        t[k] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+    float r = (b1 ? t[1] : t[0]) + __shfl_xor_sync(FULL, b1 ? t[0] : t[1], 2);
+    r += __shfl_xor_sync(FULL, r, 1);
+    return r;
+}
+__device__ __forceinline__ int slot_of_lane(int lane) {
+    // five-slot index after the first round, three-slot after the second, two-slot after the third
+    const int s2 = (lane & 2) ? 1 : 0;
+    const int s3 = ((lane & 4) ? 2 : 0) + s2;       // valid if < 3
+    const int s5 = ((lane & 8) ? 3 : 0) + s3;       // valid if < 5
+    const int s9 = ((lane & 16) ? 5 : 0) + s5;      // valid if < 9
+    const bool ok = (s3 < 3) && (s5 < 5) && (s9 < 9) && !((lane & 4) && s2) && ((lane & 1) == 0);
+    return ok ? s9 : -1;
+}
+
+__global__ void __launch_bounds__(256) render_backward_kernel(RenderBwdArgs a) {
+    __shared__ float4 s_r0[256];
+    __shared__ float4 s_r1[256];
+    __shared__ float4 s_r2[256];
+    __shared__ int s_id[256];
+    __shared__ int s_max;
+
+    const int tile = blockIdx.x;
+    const uint2 range = a.ranges[tile];
+    if (range.x == range.y) return;
+    const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t pix_x = tile_x * DQO_TILE + lx, pix_y = tile_y * DQO_TILE + ly;
+    const bool inside = pix_x < (uint32_t)a.W && pix_y < (uint32_t)a.H;
+    const size_t pix_id = (size_t)a.W * pix_y + pix_x;
+    const size_t HW = (size_t)a.W * a.H;
+    const size_t sp = (size_t)tile * 256 + tid;
+    const float pixfx = (float)pix_x, pixfy = (float)pix_y;
+
+    const float T_final = inside ? a.final_T[sp] : 0.f;
+    float T = T_final;
+    const int last_contributor = inside ? (int)a.n_contrib[sp] : 0;
+    if (tid == 0) s_max = 0;
+    __syncthreads();
+    {
+        int m = last_contributor;
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        if (lane == 0) atomicMax(&s_max, m);
+    }
+    __syncthreads();
+    const int max_c = s_max; // entries at list positions >= max_c contribute to no pixel of this tile
+
+    float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
+    if (inside) {
+        dLp0 = a.dL_dpix[pix_id];
+        dLp1 = a.dL_dpix[HW + pix_id];
+        dLp2 = a.dL_dpix[2 * HW + pix_id];
+    }
+    const float bg_dot = a.bg[0] * dLp0 + a.bg[1] * dLp1 + a.bg[2] * dLp2;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
+    const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+    const int my_slot = slot_of_lane(lane);
+
+    const int rounds = (max_c + 255) / 256;
+    for (int i = 0; i < rounds; i++) {
+        __syncthreads();
+        const int pos = max_c - 1 - (i * 256 + tid);
+        if (pos >= 0) {
+            const int id = (int)a.point_list[range.x + pos];
+            s_id[tid] = id;
+            s_r0[tid] = __ldg(&a.rec[3 * (size_t)id]);
+            s_r1[tid] = __ldg(&a.rec[3 * (size_t)id + 1]);
+            s_r2[tid] = __ldg(&a.rec[3 * (size_t)id + 2]);
+        }
+        __syncthreads();
+        const int n = min(256, max_c - i * 256);
+        for (int j = 0; j < n; j++) {
+            const int posj = max_c - 1 - (i * 256 + j);
+            const float4 r0 = s_r0[j];
+            const float4 r1 = s_r1[j];
+            const float dx = fsub(r0.x, pixfx), dy = fsub(r0.y, pixfy);
+            const float power = ffma(ffma(dx, fmul(dx, r0.z), fmul(dy, fmul(dy, r1.x))), -0.5f, -fmul(dy, fmul(dx, r0.w)));
+            bool contrib = (posj < last_contributor) && !(power > 0.0f) && !(power < r1.z);
+            float G = 0.f, alpha = 0.f;
+            if (contrib) {
+                G = expf(power);
+                alpha = fminf(0.99f, fmul(r1.y, G));
+                contrib = !(alpha < 1.0f / 255.0f);
+            }
+            if (!__any_sync(0xFFFFFFFFu, contrib)) continue;
+            float v[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) v[k] = 0.f;
+            if (contrib) {
+                const float4 r2 = s_r2[j];
+                T = T / (1.f - alpha);
+                const float dchannel_dcolor = alpha * T;
+                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
+                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
+                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
+                lc0 = r2.x;
+                lc1 = r2.y;
+                lc2 = r2.z;
+                float dL_dalpha = (r2.x - acc0) * dLp0 + (r2.y - acc1) * dLp1 + (r2.z - acc2) * dLp2;
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                const float dL_dG = r1.y * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
+                const float dG_ddely = -gdy * r1.x - gdx * r0.w;
+                v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                v[1] = dL_dG * dG_ddely * ddely_dy;
+                v[2] = -0.5f * gdx * dx * dL_dG;
+                v[3] = -0.5f * gdx * dy * dL_dG;
+                v[4] = -0.5f * gdy * dy * dL_dG;
+                v[5] = G * dL_dalpha;
+                v[6] = dchannel_dcolor * dLp0;
+                v[7] = dchannel_dcolor * dLp1;
+                v[8] = dchannel_dcolor * dLp2;
+            }
+            const float total = warp_reduce9(v, lane);
+            if (my_slot >= 0) atomicAdd(&a.gacc[(size_t)s_id[j] * DQO_GACC_FLOATS + my_slot], total);
+        }
+    }
+
+    // depth gradient to the single hit Gaussian (backward.cu:998-1065)
+    if (inside) {
+        const int gid = a.hit_image[pix_id];
+        if (gid >= 0) {
+            const float3 ray = pixel_ray(pix_x, pix_y, a.fx, a.fy, a.cx, a.cy);
+            const float sx = a.scales[3 * gid], sy = a.scales[3 * gid + 1], sz = a.scales[3 * gid + 2];
+            const float scale_max = fmaxf(fmaxf(sx, sy), sz);
+            const float ncx = a.hit_geo[sp], ncy = a.hit_geo[a.plane + sp], ncz = a.hit_geo[2 * a.plane + sp];
+            const float hz = a.hit_geo[5 * a.plane + sp];
+            const float *v = a.view;
+            const float wx = a.means3D[3 * gid], wy = a.means3D[3 * gid + 1], wz = a.means3D[3 * gid + 2];
+            const float pcx = xform_row(v, 0, wx, wy, wz), pcy = xform_row(v, 1, wx, wy, wz),
+                        pcz = xform_row(v, 2, wx, wy, wz);
+            const float ndotr = dot3_ref(ncx, ray.x, ncy, ray.y, ncz, ray.z);
+            const float angle_distance = fabsf(ndotr);
+            const float depth_distance = fabsf(fsub(hz, pcz));
+            const float g = a.dL_ddepth[pix_id];
+            float *acc = a.gacc + (size_t)gid * DQO_GACC_FLOATS;
+            if (depth_distance <= fmul(a.depth_thr, scale_max) && angle_distance >= a.normal_thr) {
+                const float nr = (float)((double)ndotr + 1e-8);
+                const float inv_nr = 1.f / nr;
+                const float inv_nr2 = inv_nr * inv_nr;
+                const float np = ncx * pcx + ncy * pcy + ncz * pcz;
+                const float dpx = ray.z * ncx * inv_nr, dpy = ray.z * ncy * inv_nr, dpz = ray.z * ncz * inv_nr;
+                atomicAdd(&acc[9], g * (dpx * v[0] + dpy * v[1] + dpz * v[2]));
+                atomicAdd(&acc[10], g * (dpx * v[4] + dpy * v[5] + dpz * v[6]));
+                atomicAdd(&acc[11], g * (dpx * v[8] + dpy * v[9] + dpz * v[10]));
+                const int axis = arg_min3(sx, sy, sz);
+                const float n1c = ray.z * (nr * pcx - np * ray.x) * inv_nr2;
+                const float n2c = ray.z * (nr * pcy - np * ray.y) * inv_nr2;
+                const float n3c = ray.z * (nr * pcz - np * ray.z) * inv_nr2;
+                const float n1w = n1c * v[0] + n2c * v[1] + n3c * v[2];
+                const float n2w = n1c * v[4] + n2c * v[5] + n3c * v[6];
+                const float n3w = n1c * v[8] + n2c * v[9] + n3c * v[10];
+                const float4 q = reinterpret_cast<const float4 *>(a.rotations)[gid];
+                const float q0 = q.x, q1 = q.y, q2 = q.z, q3 = q.w;
+                float d0[3], d1[3], d2[3], d3[3]; // d normal / d q_k (backward.cu:100-148)
+                if (axis == 0) {
+                    d0[0] = 0; d0[1] = 2 * q3; d0[2] = -2 * q2;
+                    d1[0] = 0; d1[1] = 2 * q2; d1[2] = 2 * q3;
+                    d2[0] = -4 * q2; d2[1] = 2 * q1; d2[2] = -2 * q0;
+                    d3[0] = -4 * q3; d3[1] = 2 * q0; d3[2] = 2 * q1;
+                } else if (axis == 1) {
+                    d0[0] = -2 * q3; d0[1] = 0; d0[2] = 2 * q1;
+                    d1[0] = 2 * q2; d1[1] = -4 * q1; d1[2] = 2 * q0;
+                    d2[0] = 2 * q1; d2[1] = 0; d2[2] = 2 * q3;
+                    d3[0] = -2 * q0; d3[1] = -4 * q3; d3[2] = 2 * q2;
+                } else {
+                    d0[0] = 2 * q2; d0[1] = -2 * q1; d0[2] = 0;
+                    d1[0] = 2 * q3; d1[1] = -2 * q0; d1[2] = -4 * q1;
+                    d2[0] = 2 * q0; d2[1] = 2 * q3; d2[2] = -4 * q2;
+                    d3[0] = 2 * q1; d3[1] = 2 * q2; d3[2] = 0;
+                }
+                atomicAdd(&acc[12], g * (n1w * d0[0] + n2w * d0[1] + n3w * d0[2]));
+                atomicAdd(&acc[13], g * (n1w * d1[0] + n2w * d1[1] + n3w * d1[2]));
+                atomicAdd(&acc[14], g * (n1w * d2[0] + n2w * d2[1] + n3w * d2[2]));
+                atomicAdd(&acc[15], g * (n1w * d3[0] + n2w * d3[1] + n3w * d3[2]));
+            } else {
+                atomicAdd(&acc[9], g * v[2]);
+                atomicAdd(&acc[10], g * v[6]);
+                atomicAdd(&acc[11], g * v[10]);
+            }
+        }
+    }
+}
+
+struct GaussBwdArgs {
+    int P, D, M;
+    float scale_modifier, tanfovx, tanfovy, focal_x, focal_y;
+    const float *means3D, *scales, *rotations, *shs, *cov3D_precomp;
+    const float *view, *proj, *campos;
+    const int *radii;
+    const uint8_t *clamped;
+    const float *gacc;
+    float *dL_dmeans2D, *dL_dconic, *dL_dopacity, *dL_dcolors, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drot;
+};
+
+__device__ __constant__ float B_SH_C0 = 0.28209479177387814f;
+__device__ __constant__ float B_SH_C1 = 0.4886025119029199f;
+__device__ __constant__ float B_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                            -1.0925484305920792f, 0.5462742152960396f};
+__device__ __constant__ float B_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                            0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                            -0.5900435899266435f};
+
+__global__ void __launch_bounds__(256) gaussian_backward_kernel(GaussBwdArgs a) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.P) return;
+    const bool active = a.radii[idx] > 0;
+    const int M = a.M;
+    float g[DQO_GACC_FLOATS];
+    if (active) {
+        const float4 *gp = reinterpret_cast<const float4 *>(a.gacc + (size_t)idx * DQO_GACC_FLOATS);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float4 t = gp[k];
+            g[4 * k] = t.x; g[4 * k + 1] = t.y; g[4 * k + 2] = t.z; g[4 * k + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < DQO_GACC_FLOATS; k++) g[k] = 0.f;
+    }
+    float dmean[3] = {g[9], g[10], g[11]};
+    float drot[4] = {g[12], g[13], g[14], g[15]};
+    float dscale[3] = {0.f, 0.f, 0.f};
+    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float *dsh = a.dL_dsh ? a.dL_dsh + (size_t)idx * M * 3 : nullptr;
+
+    if (active) {
+        const float mx = a.means3D[3 * idx], my = a.means3D[3 * idx + 1], mz = a.means3D[3 * idx + 2];
+        const float *v = a.view;
+        float cov3[6];
+        float sx = 0, sy = 0, sz = 0;
+        float4 q = make_float4(0, 0, 0, 0);
+        if (a.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) cov3[k] = a.cov3D_precomp[6 * idx + k];
+        } else {
+            sx = a.scales[3 * idx]; sy = a.scales[3 * idx + 1]; sz = a.scales[3 * idx + 2];
+            q = reinterpret_cast<const float4 *>(a.rotations)[idx];
+            cov3d_from_scale_rot(sx, sy, sz, a.scale_modifier, q.x, q.y, q.z, q.w, cov3);
+        }
+        // ---- conic -> cov2D -> cov3D, mean (backward.cu:273-422) ----
+        // This chain is ill-conditioned in fp32 (denom = a*c - b*b and the dL_da/db/dc sums cancel for
+        // edge-on surfels), so it is written in the exact operation order of the reference's compiled
+        // computeCov2DCUDA; any other association differs from the reference by up to ~1e-3 relative.
+        {
+            const float dcx = g[2], dcy = g[3], dcz = g[4];
+            float tx = xform_row(v, 0, mx, my, mz), ty = xform_row(v, 1, mx, my, mz);
+            const float tz = xform_row(v, 2, mx, my, mz);
+            const float limx = fmul(1.3f, a.tanfovx), limy = fmul(1.3f, a.tanfovy);
+            const float txtz = fdiv(tx, tz), tytz = fdiv(ty, tz);
+            tx = fmul(fminf(limx, fmaxf(-limx, txtz)), tz);
+            ty = fmul(fminf(limy, fmaxf(-limy, tytz)), tz);
+            const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+            const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+            const float hx = a.focal_x, hy = a.focal_y;
+            const float tzz = fmul(tz, tz);
+            const float J00 = fdiv(hx, tz), J11 = fdiv(hy, tz);
+            const float J02 = fdiv(fmul(tx, -hx), tzz), J12 = fdiv(fmul(ty, -hy), tzz);
+            float T0[3], T1[3]; // T[0][r], T[1][r]
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                T0[r] = ffma(J02, v[4 * r + 2], fmul(v[4 * r], J00));
+                T1[r] = ffma(J12, v[4 * r + 2], fmul(v[4 * r + 1], J11));
+            }
+            const float V[3][3] = {{cov3[0], cov3[1], cov3[2]}, {cov3[1], cov3[3], cov3[4]}, {cov3[2], cov3[4], cov3[5]}};
+            float TV0[3], TV1[3]; // (T0 . V[k]), (T1 . V[k])
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                TV0[k] = dot3_ref(T0[0], V[k][0], T0[1], V[k][1], T0[2], V[k][2]);
+                TV1[k] = dot3_ref(T1[0], V[k][0], T1[1], V[k][1], T1[2], V[k][2]);
+            }
+            // here the compiled reference multiplies the FIRST term and fuses the other two
+            const float ca = fadd(ffma(T0[2], TV0[2], ffma(T0[1], TV0[1], fmul(T0[0], TV0[0]))), 0.3f);
+            const float cb = ffma(T0[2], TV1[2], ffma(T0[1], TV1[1], fmul(T0[0], TV1[0])));
+            const float cc = fadd(ffma(T1[2], TV1[2], ffma(T1[1], TV1[1], fmul(T1[0], TV1[0]))), 0.3f);
+            const float ac = fmul(ca, cc);
+            const float denom = ffma(-cb, cb, ac);
+            float dL_da = 0, dL_db = 0, dL_dc = 0;
+            const float denom2inv = frcp(ffma(denom, denom, 0.0000001f));
+            if (denom2inv != 0) {
+                const float b2 = fadd(cb, cb), a2 = fadd(ca, ca);
+                const float dmac = fadd(denom, -ac);
+                dL_da = fmul(ffma(dcz, dmac, ffma(dcy, fmul(cc, b2), -fmul(dcx, fmul(cc, cc)))), denom2inv);
+                dL_dc = fmul(ffma(dcx, dmac, ffma(dcy, fmul(cb, a2), -fmul(dcz, fmul(ca, ca)))), denom2inv);
+                dL_db = fmul(fadd(denom2inv, denom2inv),
+                             ffma(dcz, fmul(cb, ca), ffma(dcx, fmul(cb, cc), -fmul(dcy, ffma(cb, b2, denom)))));
+                dcov[0] = ffma(dL_dc, fmul(T1[0], T1[0]), ffma(dL_da, fmul(T0[0], T0[0]), fmul(dL_db, fmul(T0[0], T1[0]))));
+                dcov[3] = ffma(dL_dc, fmul(T1[1], T1[1]), ffma(dL_da, fmul(T0[1], T0[1]), fmul(dL_db, fmul(T0[1], T1[1]))));
+                dcov[5] = ffma(dL_dc, fmul(T1[2], T1[2]), ffma(dL_da, fmul(T0[2], T0[2]), fmul(dL_db, fmul(T0[2], T1[2]))));
+                const float T00x2 = fadd(T0[0], T0[0]), T10x2 = fadd(T1[0], T1[0]);
+                const float T02x2 = fadd(T0[2], T0[2]), T11x2 = fadd(T1[1], T1[1]);
+                dcov[1] = ffma(dL_dc, fmul(T1[1], T10x2),
+                               ffma(dL_da, fmul(T0[1], T00x2), fmul(dL_db, ffma(T0[0], T1[1], fmul(T0[1], T1[0])))));
+                dcov[2] = ffma(dL_dc, fmul(T1[2], T10x2),
+                               ffma(dL_da, fmul(T0[2], T00x2), fmul(dL_db, ffma(T0[0], T1[2], fmul(T0[2], T1[0])))));
+                dcov[4] = ffma(dL_dc, fmul(T1[2], T11x2),
+                               ffma(dL_da, fmul(T0[1], T02x2), fmul(dL_db, ffma(T0[1], T1[2], fmul(T0[2], T1[1])))));
+            }
+            float dT0[3], dT1[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                dT0[k] = ffma(fadd(TV0[k], TV0[k]), dL_da, fmul(TV1[k], dL_db));
+                dT1[k] = ffma(TV0[k], dL_db, fmul(fadd(TV1[k], TV1[k]), dL_dc));
+            }
+            const float dJ00 = dot3_ref(v[0], dT0[0], v[4], dT0[1], v[8], dT0[2]);
+            const float dJ02 = dot3_ref(v[2], dT0[0], v[6], dT0[1], v[10], dT0[2]);
+            const float dJ11 = dot3_ref(v[1], dT1[0], v[5], dT1[1], v[9], dT1[2]);
+            const float dJ12 = dot3_ref(v[2], dT1[0], v[6], dT1[1], v[10], dT1[2]);
+            const float itz = frcp(tz), itz2 = fmul(itz, itz), itz3 = fmul(itz2, itz);
+            const float dtx = fmul(dJ02, fmul(itz2, fmul(x_grad_mul, -hx)));
+            const float dty = fmul(dJ12, fmul(itz2, fmul(y_grad_mul, -hy)));
+            float dtz = ffma(dJ00, fmul(itz2, -hx), -fmul(dJ11, fmul(itz2, hy)));
+            dtz = ffma(dJ02, fmul(itz3, fmul(tx, fadd(hx, hx))), dtz);
+            dtz = ffma(dJ12, fmul(itz3, fmul(ty, fadd(hy, hy))), dtz);
+            dmean[0] = fadd(dot3_ref(dtx, v[0], dty, v[1], dtz, v[2]), dmean[0]);
+            dmean[1] = fadd(dot3_ref(dtx, v[4], dty, v[5], dtz, v[6]), dmean[1]);
+            dmean[2] = fadd(dot3_ref(dtx, v[8], dty, v[9], dtz, v[10]), dmean[2]);
+        }
+        // ---- mean2D -> mean3D through the projection (backward.cu:516-533) ----
+        {
+            const float *p = a.proj;
+            const float hw = p[3] * mx + p[7] * my + p[11] * mz + p[15];
+            const float m_w = 1.0f / (hw + 0.0000001f);
+            const float mul1 = (p[0] * mx + p[4] * my + p[8] * mz + p[12]) * m_w * m_w;
+            const float mul2 = (p[1] * mx + p[5] * my + p[9] * mz + p[13]) * m_w * m_w;
+            const float d2x = g[0], d2y = g[1];
+            dmean[0] += (p[0] * m_w - p[3] * mul1) * d2x + (p[1] * m_w - p[3] * mul2) * d2y;
+            dmean[1] += (p[4] * m_w - p[7] * mul1) * d2x + (p[5] * m_w - p[7] * mul2) * d2y;
+            dmean[2] += (p[8] * m_w - p[11] * mul1) * d2x + (p[9] * m_w - p[11] * mul2) * d2y;
+        }
+        // ---- colour -> SH (+ view direction -> mean) (backward.cu:152-268) ----
+        if (a.shs) {
+            const float *sh = a.shs + (size_t)idx * M * 3;
+            const uint8_t cl = a.clamped[idx];
+            const float dRGB[3] = {(cl & 1) ? 0.f : g[6], (cl & 2) ? 0.f : g[7], (cl & 4) ? 0.f : g[8]};
+            const float ox = mx - a.campos[0], oy = my - a.campos[1], oz = mz - a.campos[2];
+            const float inv_len = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
+            const float x = ox * inv_len, y = oy * inv_len, z = oz * inv_len;
+            float w[16]; // dRGB / dsh_k
+            float dx_[3] = {0, 0, 0}, dy_[3] = {0, 0, 0}, dz_[3] = {0, 0, 0}; // dRGB/d dir per channel
+            w[0] = B_SH_C0;
+            const int deg = a.D;
+            if (deg > 0) {
+                w[1] = -B_SH_C1 * y; w[2] = B_SH_C1 * z; w[3] = -B_SH_C1 * x;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    dx_[c] = -B_SH_C1 * sh[9 + c];
+                    dy_[c] = -B_SH_C1 * sh[3 + c];
+                    dz_[c] = B_SH_C1 * sh[6 + c];
+                }
+                if (deg > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    w[4] = B_SH_C2[0] * xy; w[5] = B_SH_C2[1] * yz; w[6] = B_SH_C2[2] * (2.f * zz - xx - yy);
+                    w[7] = B_SH_C2[3] * xz; w[8] = B_SH_C2[4] * (xx - yy);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        dx_[c] += B_SH_C2[0] * y * sh[12 + c] + B_SH_C2[2] * 2.f * -x * sh[18 + c] + B_SH_C2[3] * z * sh[21 + c] +
+                                  B_SH_C2[4] * 2.f * x * sh[24 + c];
+                        dy_[c] += B_SH_C2[0] * x * sh[12 + c] + B_SH_C2[1] * z * sh[15 + c] + B_SH_C2[2] * 2.f * -y * sh[18 + c] +
+                                  B_SH_C2[4] * 2.f * -y * sh[24 + c];
+                        dz_[c] += B_SH_C2[1] * y * sh[15 + c] + B_SH_C2[2] * 2.f * 2.f * z * sh[18 + c] + B_SH_C2[3] * x * sh[21 + c];
+                    }
+                    if (deg > 2) {
+                        w[9] = B_SH_C3[0] * y * (3.f * xx - yy); w[10] = B_SH_C3[1] * xy * z;
+                        w[11] = B_SH_C3[2] * y * (4.f * zz - xx - yy);
+                        w[12] = B_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                        w[13] = B_SH_C3[4] * x * (4.f * zz - xx - yy); w[14] = B_SH_C3[5] * z * (xx - yy);
+                        w[15] = B_SH_C3[6] * x * (xx - 3.f * yy);
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            dx_[c] += B_SH_C3[0] * sh[27 + c] * 3.f * 2.f * xy + B_SH_C3[1] * sh[30 + c] * yz +
+                                      B_SH_C3[2] * sh[33 + c] * -2.f * xy + B_SH_C3[3] * sh[36 + c] * -3.f * 2.f * xz +
+                                      B_SH_C3[4] * sh[39 + c] * (-3.f * xx + 4.f * zz - yy) + B_SH_C3[5] * sh[42 + c] * 2.f * xz +
+                                      B_SH_C3[6] * sh[45 + c] * 3.f * (xx - yy);
+                            dy_[c] += B_SH_C3[0] * sh[27 + c] * 3.f * (xx - yy) + B_SH_C3[1] * sh[30 + c] * xz +
+                                      B_SH_C3[2] * sh[33 + c] * (-3.f * yy + 4.f * zz - xx) +
+                                      B_SH_C3[3] * sh[36 + c] * -3.f * 2.f * yz + B_SH_C3[4] * sh[39 + c] * -2.f * xy +
+                                      B_SH_C3[5] * sh[42 + c] * -2.f * yz + B_SH_C3[6] * sh[45 + c] * -3.f * 2.f * xy;
+                            dz_[c] += B_SH_C3[1] * sh[30 + c] * xy + B_SH_C3[2] * sh[33 + c] * 4.f * 2.f * yz +
+                                      B_SH_C3[3] * sh[36 + c] * 3.f * (2.f * zz - xx - yy) +
+                                      B_SH_C3[4] * sh[39 + c] * 4.f * 2.f * xz + B_SH_C3[5] * sh[42 + c] * (xx - yy);
+                        }
+                    }
+                }
+            }
+            const int ncoef = (deg + 1) * (deg + 1);
+            for (int k = 0; k < M; k++) {
+                const float wk = (k < ncoef) ? w[k < 16 ? k : 15] : 0.f;
+                dsh[3 * k] = (k < ncoef) ? wk * dRGB[0] : 0.f;
+                dsh[3 * k + 1] = (k < ncoef) ? wk * dRGB[1] : 0.f;
+                dsh[3 * k + 2] = (k < ncoef) ? wk * dRGB[2] : 0.f;
+            }
+            const float ddx = dx_[0] * dRGB[0] + dx_[1] * dRGB[1] + dx_[2] * dRGB[2];
+            const float ddy = dy_[0] * dRGB[0] + dy_[1] * dRGB[1] + dy_[2] * dRGB[2];
+            const float ddz = dz_[0] * dRGB[0] + dz_[1] * dRGB[1] + dz_[2] * dRGB[2];
+            // dnormvdv (auxiliary.h:107-117)
+            const float sum2 = ox * ox + oy * oy + oz * oz;
+            const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+            dmean[0] += ((+sum2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * invsum32;
+            dmean[1] += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * invsum32;
+            dmean[2] += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * invsum32;
+        }
+        // ---- cov3D -> scale, rotation (backward.cu:426-487) ----
+        if (!a.cov3D_precomp) {
+            const QuatMat R = quat_to_glm(q.x, q.y, q.z, q.w);
+            const float s[3] = {a.scale_modifier * sx, a.scale_modifier * sy, a.scale_modifier * sz};
+            const float Rc[3][3] = {{R.c0[0], R.c0[1], R.c0[2]}, {R.c1[0], R.c1[1], R.c1[2]}, {R.c2[0], R.c2[1], R.c2[2]}};
+            float Mm[3][3]; // M[c][r] = s[r] * R[c][r]
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int r = 0; r < 3; r++) Mm[c][r] = s[r] * Rc[c][r];
+            const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
+                                    {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
+                                    {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+            float dM[3][3]; // dL_dM[c][r] = 2 * sum_k M[k][r] * dS[c][k]
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+                    dM[c][r] = 2.0f * (Mm[0][r] * dS[c][0] + Mm[1][r] * dS[c][1] + Mm[2][r] * dS[c][2]);
+#pragma unroll
+            for (int r = 0; r < 3; r++) dscale[r] = Rc[0][r] * dM[0][r] + Rc[1][r] * dM[1][r] + Rc[2][r] * dM[2][r];
+            float Mt[3][3]; // dL_dMt[r][c] = s[r] * dM[c][r]
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) Mt[r][c] = s[r] * dM[c][r];
+            const float r_ = q.x, x = q.y, y = q.z, z = q.w;
+            drot[0] += 2 * z * (Mt[0][1] - Mt[1][0]) + 2 * y * (Mt[2][0] - Mt[0][2]) + 2 * x * (Mt[1][2] - Mt[2][1]);
+            drot[1] += 2 * y * (Mt[1][0] + Mt[0][1]) + 2 * z * (Mt[2][0] + Mt[0][2]) + 2 * r_ * (Mt[1][2] - Mt[2][1]) -
+                       4 * x * (Mt[2][2] + Mt[1][1]);
+            drot[2] += 2 * x * (Mt[1][0] + Mt[0][1]) + 2 * r_ * (Mt[2][0] - Mt[0][2]) + 2 * z * (Mt[1][2] + Mt[2][1]) -
+                       4 * y * (Mt[2][2] + Mt[0][0]);
+            drot[3] += 2 * r_ * (Mt[0][1] - Mt[1][0]) + 2 * x * (Mt[2][0] + Mt[0][2]) + 2 * y * (Mt[1][2] + Mt[2][1]) -
+                       4 * z * (Mt[1][1] + Mt[0][0]);
+        }
+    } else if (dsh) {
+        for (int k = 0; k < 3 * M; k++) dsh[k] = 0.f;
+    }
+    if (active && !a.shs && dsh) {
+        for (int k = 0; k < 3 * M; k++) dsh[k] = 0.f;
+    }
+
+    if (a.dL_dmeans2D) {
+        a.dL_dmeans2D[3 * idx] = g[0];
+        a.dL_dmeans2D[3 * idx + 1] = g[1];
+        a.dL_dmeans2D[3 * idx + 2] = 0.f;
+    }
+    if (a.dL_dconic) reinterpret_cast<float4 *>(a.dL_dconic)[idx] = make_float4(g[2], g[3], 0.f, g[4]);
+    if (a.dL_dopacity) a.dL_dopacity[idx] = g[5];
+    if (a.dL_dcolors) {
+        a.dL_dcolors[3 * idx] = g[6];
+        a.dL_dcolors[3 * idx + 1] = g[7];
+        a.dL_dcolors[3 * idx + 2] = g[8];
+    }
+    a.dL_dmeans3D[3 * idx] = dmean[0];
+    a.dL_dmeans3D[3 * idx + 1] = dmean[1];
+    a.dL_dmeans3D[3 * idx + 2] = dmean[2];
+    if (a.dL_dcov3D) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * idx + k] = dcov[k];
+    }
+    if (a.dL_dscales) {
+        a.dL_dscales[3 * idx] = dscale[0];
+        a.dL_dscales[3 * idx + 1] = dscale[1];
+        a.dL_dscales[3 * idx + 2] = dscale[2];
+    }
+    if (a.dL_drot) reinterpret_cast<float4 *>(a.dL_drot)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+}
+
+} // namespace dqo
+
+using namespace dqo;
+
+extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *background, const float *means3D,
+                                 const float *shs, const float *colors_precomp, const float *scales,
+                                 const float *rotations, const float *cov3D_precomp, const float *viewmatrix,
+                                 const float *projmatrix, const float *campos, const int32_t *radii,
+                                 void *geom_buffer, const void *binning_buffer, int64_t capacity,
+                                 const void *image_buffer, const int32_t *status, const float *dL_dout_color,
+                                 const float *dL_dout_depth, const int32_t *hit_image, float *dL_dmeans2D,
+                                 float *dL_dconic, float *dL_dopacity, float *dL_dcolors, float *dL_dmeans3D,
+                                 float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
+                                 void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!s || s->P < 0) {
+        set_error("dqo_rast_backward: invalid settings");
+        return DQO_ERR_INVALID_ARG;
+    }
+    const int P = s->P;
+    if (P == 0) return DQO_OK;
+    if (!background || !means3D || !scales || !rotations || !viewmatrix || !projmatrix || !campos || !radii ||
+        !geom_buffer || !binning_buffer || !image_buffer || !status || !dL_dout_color || !dL_dout_depth || !hit_image ||
+        !dL_dmeans3D) {
+        set_error("dqo_rast_backward: null pointer argument");
+        return DQO_ERR_INVALID_ARG;
+    }
+    if (s->M > 0 && shs && !dL_dsh) {
+        set_error("dqo_rast_backward: dL_dsh is required when SH coefficients are given");
+        return DQO_ERR_INVALID_ARG;
+    }
+    (void)colors_precomp;
+    GeomLayout GL;
+    BinLayout BL;
+    ImgLayout IL;
+    if (make_geom_layout(P, &GL) || make_bin_layout(capacity, &BL)) return DQO_ERR_WORKSPACE;
+    make_img_layout(s->W, s->H, &IL);
+    char *geom = (char *)geom_buffer;
+    const char *bin = (const char *)binning_buffer;
+    const char *img = (const char *)image_buffer;
+    float *gacc = (float *)(geom + GL.gacc);
+    DQO_CUDA_CHECK(cudaMemsetAsync(gacc, 0, (size_t)P * DQO_GACC_FLOATS * sizeof(float), stream));
+
+    const float focal_y = s->H / (2.0f * s->tanfovy);
+    const float focal_x = s->W / (2.0f * s->tanfovx);
+    RenderBwdArgs ra;
+    ra.W = s->W; ra.H = s->H; ra.grid_x = IL.tiles_x;
+    ra.fx = focal_x; ra.fy = focal_y; ra.cx = s->cx; ra.cy = s->cy;
+    ra.depth_thr = s->depth_threshold; ra.normal_thr = s->normal_threshold;
+    ra.ranges = (const uint2 *)(img + IL.ranges);
+    ra.point_list = (const uint32_t *)(bin + BL.vals_out);
+    ra.rec = (const float4 *)(geom + GL.rec);
+    ra.view = viewmatrix; ra.means3D = means3D; ra.scales = scales; ra.rotations = rotations; ra.bg = background;
+    ra.n_contrib = (const uint32_t *)(img + IL.n_contrib);
+    ra.final_T = (const float *)(img + IL.final_T);
+    ra.hit_geo = (const float *)(img + IL.hit_geo);
+    ra.plane = (size_t)IL.T * 256;
+    ra.dL_dpix = dL_dout_color; ra.dL_ddepth = dL_dout_depth; ra.hit_image = hit_image; ra.gacc = gacc;
+    render_backward_kernel<<<IL.T, 256, 0, stream>>>(ra);
+    DQO_LAUNCH_CHECK("render backward", s->debug, stream);
+
+    GaussBwdArgs ga;
+    ga.P = P; ga.D = s->D; ga.M = s->M;
+    ga.scale_modifier = s->scale_modifier; ga.tanfovx = s->tanfovx; ga.tanfovy = s->tanfovy;
+    ga.focal_x = focal_x; ga.focal_y = focal_y;
+    ga.means3D = means3D; ga.scales = scales; ga.rotations = rotations; ga.shs = shs; ga.cov3D_precomp = cov3D_precomp;
+    ga.view = viewmatrix; ga.proj = projmatrix; ga.campos = campos; ga.radii = radii;
+    ga.clamped = (const uint8_t *)(geom + GL.clamped);
+    ga.gacc = gacc;
+    ga.dL_dmeans2D = dL_dmeans2D; ga.dL_dconic = dL_dconic; ga.dL_dopacity = dL_dopacity; ga.dL_dcolors = dL_dcolors;
+    ga.dL_dmeans3D = dL_dmeans3D; ga.dL_dcov3D = dL_dcov3D; ga.dL_dsh = (s->M > 0) ? dL_dsh : nullptr;
+    ga.dL_dscales = dL_dscales; ga.dL_drot = dL_drotations;
+    gaussian_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(ga);
+    DQO_LAUNCH_CHECK("gaussian backward", s->debug, stream);
+    return DQO_OK;
+}

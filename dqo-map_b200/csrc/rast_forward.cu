@@ -1,0 +1,841 @@
+// Forward rasterization: preprocess -> depth-rank sort -> instance emission -> tile sort -> ranges -> blend.
+//
+// Replaces CudaRasterizer::Rasterizer::forward (reference RAST/cuda_rasterizer/rasterizer_impl.cu:205-441,
+// forward.cu:238-354 and 636-866).  Design differences (results identical):
+//   * no host synchronisation: R and the compact tile list stay on the device (reference syncs twice,
+//     rasterizer_impl.cu:307,349-364);
+//   * the 64-bit (tile|depth) sort of R instances is split into a 32-bit depth sort of the P Gaussians
+//     followed by a stable tile-id sort of the instances emitted in depth-rank order.  The resulting
+//     point_list is identical (stable LSD sort, ties in Gaussian-index order) at ~1/5 of the traffic;
+//   * per-Gaussian splat data is packed in one 48-byte record gathered once per (tile, Gaussian);
+//   * the plane / normal math of forward.cu:779-791 is evaluated only at the single "first opaque hit"
+//     event per pixel (N3 in SURVEY.md);
+//   * an exact-safe early reject (power < ln(1/(255 o)) - margin) skips expf for pairs that cannot pass
+//     the alpha >= 1/255 test;
+//   * fill values for non-rendered tiles are written by the blend kernel itself.
+#include "common.cuh"
+#include <cub/cub.cuh>
+#include <math.h>
+
+namespace dqo {
+
+// ------------------------------------------------------------------------------------------------
+// layouts
+// ------------------------------------------------------------------------------------------------
+struct GatherTiles {
+    const uint32_t *tiles;
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t &id) const { return tiles[id]; }
+};
+typedef cub::TransformInputIterator<uint32_t, GatherTiles, const uint32_t *> TilesInRankOrder;
+
+static size_t bump(size_t &cur, size_t bytes) {
+    size_t off = align_up(cur, 256);
+    cur = off + bytes;
+    return off;
+}
+
+int make_geom_layout(int P, GeomLayout *L) {
+    size_t cur = 0;
+    size_t n = (size_t)(P > 0 ? P : 1);
+    L->rec = bump(cur, n * 48);
+    L->depth_key = bump(cur, n * 4);
+    L->depth_key2 = bump(cur, n * 4);
+    L->ids = bump(cur, n * 4);
+    L->order = bump(cur, n * 4);
+    L->tiles = bump(cur, n * 4);
+    L->offsets = bump(cur, n * 4);
+    L->rect = bump(cur, n * 8);
+    L->clamped = bump(cur, n);
+    L->gacc = bump(cur, n * DQO_GACC_FLOATS * 4);
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 32);
+    if (e != cudaSuccess) {
+        set_error("cub sort size query failed: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    TilesInRankOrder it((const uint32_t *)nullptr, GatherTiles{nullptr});
+    e = cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, it, (uint32_t *)nullptr, (int)n);
+    if (e != cudaSuccess) {
+        set_error("cub scan size query failed: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    L->cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+    L->cub = bump(cur, L->cub_bytes);
+    L->total = align_up(cur, 256);
+    return 0;
+}
+
+int make_bin_layout(int64_t C, BinLayout *L) {
+    size_t cur = 0;
+    size_t n = (size_t)(C > 0 ? C : 1);
+    L->keys_in = bump(cur, n * 4);
+    L->keys_out = bump(cur, n * 4);
+    L->vals_in = bump(cur, n * 4);
+    L->vals_out = bump(cur, n * 4);
+    size_t sort_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 16);
+    if (e != cudaSuccess) {
+        set_error("cub sort size query failed: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    L->cub_bytes = sort_bytes;
+    L->cub = bump(cur, sort_bytes);
+    L->total = align_up(cur, 256);
+    return 0;
+}
+
+void make_img_layout(int W, int H, ImgLayout *L) {
+    L->tiles_x = (W + DQO_TILE - 1) / DQO_TILE;
+    L->tiles_y = (H + DQO_TILE - 1) / DQO_TILE;
+    L->T = L->tiles_x * L->tiles_y;
+    size_t cur = 0;
+    size_t T = (size_t)(L->T > 0 ? L->T : 1);
+    L->ranges = bump(cur, T * 8);
+    L->n_contrib = bump(cur, T * DQO_TILE_PIX * 4);
+    L->final_T = bump(cur, T * DQO_TILE_PIX * 4);
+    L->hit_geo = bump(cur, T * DQO_TILE_PIX * 4 * 6);
+    L->total = align_up(cur, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+struct PreArgs {
+    int P, D, M, W, H;
+    float color_sigma, scale_modifier;
+    float tanfovx, tanfovy, focal_x, focal_y, cx, cy;
+    int grid_x, grid_y;
+    int prefiltered;
+    const float *means3D, *scales, *rotations, *opacities, *shs, *cov3D_precomp, *colors_precomp;
+    const float *view, *proj, *campos;
+    const int *tile_mask;
+    int *radii;
+    int *n_touched;
+    float4 *rec;
+    uint32_t *depth_key, *ids, *tiles;
+    uint2 *rect;
+    uint8_t *clamped;
+    int *status;
+};
+
+__device__ __constant__ float SH_C0 = 0.28209479177387814f;
+__device__ __constant__ float SH_C1 = 0.4886025119029199f;
+__device__ __constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                          -1.0925484305920792f, 0.5462742152960396f};
+__device__ __constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                          0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                          -0.5900435899266435f};
+
+// SH -> RGB (forward.cu:104-155).  `sh` points at this Gaussian's [M][3] block.
+__device__ __forceinline__ float3 sh_to_rgb(int deg, const float *__restrict__ sh, float3 pos, float3 campos,
+                                            uint8_t *clamp_bits) {
+    float dx = fsub(pos.x, campos.x), dy = fsub(pos.y, campos.y), dz = fsub(pos.z, campos.z);
+    float len = fsqrt(dot3_ref(dx, dx, dy, dy, dz, dz));
+    float x = fdiv(dx, len), y = fdiv(dy, len), z = fdiv(dz, len);
+    float res[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) res[c] = fmul(SH_C0, sh[c]);
+    if (deg > 0) {
+        const float c1y = fmul(SH_C1, y), c1z = fmul(SH_C1, z), c1x = fmul(SH_C1, x);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float r = ffma(-c1y, sh[3 + c], res[c]);
+            r = ffma(c1z, sh[6 + c], r);
+            res[c] = ffma(-c1x, sh[9 + c], r);
+        }
+        if (deg > 1) {
+            float xx = x * x, yy = y * y, zz = z * z;
+            float xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                res[c] = res[c] + SH_C2[0] * xy * sh[12 + c] + SH_C2[1] * yz * sh[15 + c] +
+                         SH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + c] + SH_C2[3] * xz * sh[21 + c] +
+                         SH_C2[4] * (xx - yy) * sh[24 + c];
+            }
+            if (deg > 2) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    res[c] = res[c] + SH_C3[0] * y * (3.0f * xx - yy) * sh[27 + c] + SH_C3[1] * xy * z * sh[30 + c] +
+                             SH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + c] +
+                             SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
+                             SH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + c] + SH_C3[5] * z * (xx - yy) * sh[42 + c] +
+                             SH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + c];
+                }
+            }
+        }
+    }
+    uint8_t bits = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        res[c] = fadd(res[c], 0.5f);
+        if (res[c] < 0.f) bits |= (1u << c);
+        res[c] = fmaxf(res[c], 0.0f);
+    }
+    *clamp_bits = bits;
+    return make_float3(res[0], res[1], res[2]);
+}
+
+// frustum test shared with mark_visible (auxiliary.h:139-165)
+__device__ __forceinline__ bool frustum_test(float px, float py, float pz, const float *__restrict__ view,
+                                             const float *__restrict__ proj, float *pview_z, float *projx,
+                                             float *projy) {
+    float hx = xform_row(proj, 0, px, py, pz);
+    float hy = xform_row(proj, 1, px, py, pz);
+    float hw = xform_row(proj, 3, px, py, pz);
+    float p_w = frcp(fadd(hw, 0.0000001f));
+    float ppx = fmul(hx, p_w), ppy = fmul(hy, p_w);
+    float vz = xform_row(view, 2, px, py, pz);
+    *pview_z = vz;
+    *projx = ppx;
+    *projy = ppy;
+    // the reference compares against the double literals -1.3 / 1.3
+    if (vz <= 0.2f || (double)ppx < -1.3 || (double)ppx > 1.3 || (double)ppy < -1.3 || (double)ppy > 1.3) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.P) return;
+    int radius_out = 0;
+    uint32_t tiles_out = 0;
+    uint32_t key_out = 0xFFFFFFFFu;
+    uint8_t flags_out = 0; // bits 0-2: clamped channels, bit 7: splat record valid
+    a.ids[idx] = (uint32_t)idx;
+    if (a.n_touched) a.n_touched[idx] = 0;
+
+    const float px = a.means3D[3 * idx], py = a.means3D[3 * idx + 1], pz = a.means3D[3 * idx + 2];
+    float vz, ppx, ppy;
+    bool ok = frustum_test(px, py, pz, a.view, a.proj, &vz, &ppx, &ppy);
+    if (!ok && a.prefiltered) {
+        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+        __trap();
+    }
+    if (ok) {
+        float cov3[6];
+        if (a.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) cov3[k] = a.cov3D_precomp[6 * idx + k];
+        } else {
+            const float4 q = reinterpret_cast<const float4 *>(a.rotations)[idx];
+            cov3d_from_scale_rot(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2], a.scale_modifier, q.x,
+                                 q.y, q.z, q.w, cov3);
+        }
+        // EWA 2D covariance (forward.cu:158-197)
+        const float *v = a.view;
+        float tx = xform_row(v, 0, px, py, pz), ty = xform_row(v, 1, px, py, pz);
+        const float tz = vz;
+        const float limx = fmul(1.3f, a.tanfovx), limy = fmul(1.3f, a.tanfovy);
+        const float txtz = fdiv(tx, tz), tytz = fdiv(ty, tz);
+        tx = fmul(fminf(limx, fmaxf(-limx, txtz)), tz);
+        ty = fmul(fminf(limy, fmaxf(-limy, tytz)), tz);
+        const float tz2 = fmul(tz, tz);
+        const float J00 = fdiv(a.focal_x, tz), J11 = fdiv(a.focal_y, tz);
+        const float J02 = fdiv(fmul(-tx, a.focal_x), tz2), J12 = fdiv(fmul(-ty, a.focal_y), tz2);
+        // T = W * J ; W[0][r] = v[4r], W[1][r] = v[4r+1], W[2][r] = v[4r+2]
+        float T0[3], T1[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            T0[r] = ffma(J02, v[4 * r + 2], fmul(v[4 * r], J00));
+            T1[r] = ffma(J12, v[4 * r + 2], fmul(v[4 * r + 1], J11));
+        }
+        const float V0[3] = {cov3[0], cov3[1], cov3[2]}, V1[3] = {cov3[1], cov3[3], cov3[4]},
+                    V2[3] = {cov3[2], cov3[4], cov3[5]};
+        // A[c][r] = T[r] . V[c]
+        const float A00 = dot3_ref(T0[0], V0[0], T0[1], V0[1], T0[2], V0[2]);
+        const float A01 = dot3_ref(T1[0], V0[0], T1[1], V0[1], T1[2], V0[2]);
+        const float A10 = dot3_ref(T0[0], V1[0], T0[1], V1[1], T0[2], V1[2]);
+        const float A11 = dot3_ref(T1[0], V1[0], T1[1], V1[1], T1[2], V1[2]);
+        const float A20 = dot3_ref(T0[0], V2[0], T0[1], V2[1], T0[2], V2[2]);
+        const float A21 = dot3_ref(T1[0], V2[0], T1[1], V2[1], T1[2], V2[2]);
+        // cov[c][r] = A[0][r]*T[c][0] + A[1][r]*T[c][1] + A[2][r]*T[c][2]
+        const float cov_x = fadd(dot3_ref(T0[0], A00, T0[1], A10, T0[2], A20), 0.3f);
+        const float cov_y = dot3_ref(T0[0], A01, T0[1], A11, T0[2], A21);
+        const float cov_z = fadd(dot3_ref(T1[0], A01, T1[1], A11, T1[2], A21), 0.3f);
+
+        const float det = ffma(cov_x, cov_z, -fmul(cov_y, cov_y));
+        if (det != 0.0f) {
+            const float det_inv = frcp(det);
+            const float conic_x = fmul(cov_z, det_inv), conic_y = fmul(cov_y, -det_inv), conic_z = fmul(cov_x, det_inv);
+            const float mid = fmul(fadd(cov_x, cov_z), 0.5f);
+            const float sq = fsqrt(fmaxf(0.1f, ffma(mid, mid, -det)));
+            const float lam = fmaxf(fadd(mid, sq), fsub(mid, sq));
+            const float rad_f = ceilf(fmul(a.color_sigma, fsqrt(lam)));
+            const int my_radius = (int)rad_f;
+            // ndc2Pix(v, S, c) = v * S * 0.5 + c evaluated in double (auxiliary.h:44-47)
+            const float pix_x = (float)fma((double)fmul(ppx, (float)a.W), 0.5, (double)a.cx);
+            const float pix_y = (float)fma((double)fmul(ppy, (float)a.H), 0.5, (double)a.cy);
+            // getRect (auxiliary.h:49-57)
+            const float rf = (float)my_radius;
+            int rx0 = (int)fmul(fsub(pix_x, rf), 0.0625f), ry0 = (int)fmul(fsub(pix_y, rf), 0.0625f);
+            int rx1 = (int)fmul(fadd(fadd(fadd(pix_x, rf), 16.0f), -1.0f), 0.0625f);
+            int ry1 = (int)fmul(fadd(fadd(fadd(pix_y, rf), 16.0f), -1.0f), 0.0625f);
+            const uint32_t minx = min((uint32_t)a.grid_x, (uint32_t)max(0, rx0));
+            const uint32_t miny = min((uint32_t)a.grid_y, (uint32_t)max(0, ry0));
+            const uint32_t maxx = min((uint32_t)a.grid_x, (uint32_t)max(0, rx1));
+            const uint32_t maxy = min((uint32_t)a.grid_y, (uint32_t)max(0, ry1));
+            if ((maxx - minx) * (maxy - miny) != 0) {
+                float3 rgb;
+                uint8_t cl = 0;
+                if (a.colors_precomp == nullptr) {
+                    const float3 cam = make_float3(a.campos[0], a.campos[1], a.campos[2]);
+                    rgb = sh_to_rgb(a.D, a.shs + (size_t)idx * a.M * 3, make_float3(px, py, pz), cam, &cl);
+                } else {
+                    rgb = make_float3(a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1],
+                                      a.colors_precomp[3 * idx + 2]);
+                }
+                const float opacity = a.opacities[idx];
+                // conservative reject bound: alpha = o*exp(power) < 1/255 whenever power < ln(1/(255 o)) - margin
+                float thr = logf(1.0f / (255.0f * opacity));
+                thr = thr - (1e-4f + 1e-5f * fabsf(thr));
+                if (!(thr == thr)) thr = -INFINITY; // NaN (negative / NaN opacity): never early-reject
+                a.rec[3 * idx + 0] = make_float4(pix_x, pix_y, conic_x, conic_y);
+                a.rec[3 * idx + 1] = make_float4(conic_z, opacity, thr, vz);
+                a.rec[3 * idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
+                a.rect[idx] = make_uint2(minx | (maxx << 16), miny | (maxy << 16));
+                flags_out = cl | 0x80;
+                radius_out = my_radius;
+                for (uint32_t x = minx; x < maxx; x++)
+                    for (uint32_t y = miny; y < maxy; y++)
+                        if (a.tile_mask[y * a.grid_x + x]) tiles_out++;
+                if (tiles_out > 0) key_out = __float_as_uint(vz);
+            }
+        }
+    }
+    a.radii[idx] = radius_out;
+    a.tiles[idx] = tiles_out;
+    a.depth_key[idx] = key_out;
+    a.clamped[idx] = flags_out;
+    const unsigned vis = __ballot_sync(__activemask(), radius_out > 0);
+    if ((threadIdx.x & 31) == 0 && vis) atomicAdd(&a.status[DQO_ST_NUM_VISIBLE], __popc(vis));
+}
+
+__global__ void mark_visible_kernel(int P, const float *__restrict__ means, const float *__restrict__ view,
+                                    const float *__restrict__ proj, uint8_t *present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    float vz, ppx, ppy;
+    present[idx] = frustum_test(means[3 * idx], means[3 * idx + 1], means[3 * idx + 2], view, proj, &vz, &ppx, &ppy) ? 1 : 0;
+}
+
+// Emits one (tile, gaussian) pair per masked tile of the rectangle (rasterizer_impl.cu:70-115), walking the
+// Gaussians in depth-rank order so that a stable sort by tile id alone reproduces the reference order.
+// Threads beyond P pad the unused tail of the instance buffer with the sentinel tile id.
+__global__ void __launch_bounds__(256)
+    duplicate_kernel(int P, int64_t capacity, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
+                     const uint32_t *__restrict__ offsets, const uint2 *__restrict__ rect,
+                     const int *__restrict__ tile_mask, int grid_x, uint32_t *__restrict__ keys,
+                     uint32_t *__restrict__ vals, int *status) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t R = offsets[P - 1];
+    const bool overflow = (int64_t)R > capacity;
+    if (i == 0) {
+        status[DQO_ST_NUM_RENDERED] = (int)R;
+        status[DQO_ST_OVERFLOW] = overflow ? 1 : 0;
+    }
+    const int64_t R_eff = overflow ? 0 : (int64_t)R;
+    if (i >= R_eff && i < capacity) keys[i] = 0xFFFFFFFFu;
+    if (i >= P || overflow) return;
+    const uint32_t id = order[i];
+    const uint32_t n = tiles[id];
+    if (n == 0) return;
+    uint32_t off = offsets[i] - n;
+    const uint2 rc = rect[id];
+    const uint32_t minx = rc.x & 0xFFFF, maxx = rc.x >> 16, miny = rc.y & 0xFFFF, maxy = rc.y >> 16;
+    for (uint32_t y = miny; y < maxy; y++)
+        for (uint32_t x = minx; x < maxx; x++) {
+            const uint32_t t = y * grid_x + x;
+            if (tile_mask[t]) {
+                keys[off] = t;
+                vals[off] = id;
+                off++;
+            }
+        }
+}
+
+// per-tile [start, end) in the sorted list (rasterizer_impl.cu:120-142)
+__global__ void __launch_bounds__(256)
+    tile_ranges_kernel(int64_t capacity, const uint32_t *__restrict__ keys, const int *__restrict__ status,
+                       uint2 *ranges) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t L = status[DQO_ST_OVERFLOW] ? 0 : status[DQO_ST_NUM_RENDERED];
+    if (i >= L) return;
+    const uint32_t cur = keys[i];
+    if (i == 0)
+        ranges[cur].x = 0;
+    else {
+        const uint32_t prev = keys[i - 1];
+        if (cur != prev) {
+            ranges[prev].y = (uint32_t)i;
+            ranges[cur].x = (uint32_t)i;
+        }
+    }
+    if (i == L - 1) ranges[cur].y = (uint32_t)L;
+}
+
+// compact list of non-empty tiles in row-major order (rasterizer_impl.cu:348-365 on the host in the reference)
+__global__ void __launch_bounds__(1024) compact_tiles_kernel(int T, const uint2 *__restrict__ ranges, int *tile_indices,
+                                                             int *status) {
+    __shared__ int warp_sums[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int start = 0; start < T; start += 1024) {
+        const int t = start + threadIdx.x;
+        int flag = 0;
+        if (t < T) {
+            const uint2 r = ranges[t];
+            flag = (r.x != r.y) ? 1 : 0;
+        }
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, flag);
+        const int within = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) warp_sums[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, total = 0;
+        for (int w = 0; w < 32; w++) {
+            const int c = warp_sums[w];
+            if (w < warp) woff += c;
+            total += c;
+        }
+        if (flag) tile_indices[base + woff + within] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) base += total;
+        __syncthreads();
+    }
+    for (int t = base + threadIdx.x; t < T; t += 1024) tile_indices[t] = -1;
+    if (threadIdx.x == 0) status[DQO_ST_TILE_NUM] = base;
+}
+
+struct RenderArgs {
+    int W, H, grid_x;
+    float fx, fy, cx, cy, scale_mod;
+    float opaque_thr, depth_thr, normal_thr, T_thr;
+    const uint2 *ranges;
+    const uint32_t *point_list;
+    const float4 *rec;
+    const float *view, *means3D, *scales, *rotations, *bg;
+    uint32_t *n_contrib;
+    float *final_T;
+    float *hit_geo;
+    size_t plane; // T*256
+    float *out_color, *out_depth, *out_hit_cw, *out_hit_dw, *out_T;
+    int *out_hit_depth, *out_hit_color, *n_touched;
+};
+
+// Front-to-back blend of one 16x16 tile (forward.cu:636-866).  Warp w covers an 8x4 pixel block.
+__global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
+    __shared__ float4 s_r0[256];
+    __shared__ float4 s_r1[256];
+    __shared__ float4 s_r2[256];
+    __shared__ int s_id[256];
+
+    const int tile = blockIdx.x;
+    const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t pix_x = tile_x * DQO_TILE + lx, pix_y = tile_y * DQO_TILE + ly;
+    const bool inside = pix_x < (uint32_t)a.W && pix_y < (uint32_t)a.H;
+    const size_t pix_id = (size_t)a.W * pix_y + pix_x;
+    const size_t HW = (size_t)a.W * a.H;
+    const uint2 range = a.ranges[tile];
+
+    if (range.x == range.y) { // tile not rendered: reference fill values (rasterize_points.cu:79-86)
+        if (inside) {
+            a.out_color[pix_id] = 0.f;
+            a.out_color[HW + pix_id] = 0.f;
+            a.out_color[2 * HW + pix_id] = 0.f;
+            a.out_depth[pix_id] = 0.f;
+            a.out_hit_depth[pix_id] = 0;
+            a.out_hit_color[pix_id] = 0;
+            a.out_hit_cw[pix_id] = 0.f;
+            a.out_hit_dw[pix_id] = 0.f;
+            a.out_T[pix_id] = 1.f;
+        }
+        return;
+    }
+    const float pixfx = (float)pix_x, pixfy = (float)pix_y;
+    const int total = (int)(range.y - range.x);
+    const int rounds = (total + 255) / 256;
+    int toDo = total;
+
+    bool done = !inside;
+    float T = 1.0f, end_T = 1.0f;
+    uint32_t contributor = 0, last_contributor = 0;
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    float depth_ = 0.f;
+    bool hit = false;
+    int hit_id = -1, hit_color_id = -1;
+    float cw_max = -1.f, hit_cw = 0.f, hit_dw = 0.f;
+
+    for (int i = 0; i < rounds; i++, toDo -= 256) {
+        if (__syncthreads_count(done) == 256) break;
+        const int progress = i * 256 + tid;
+        if (progress < total) {
+            const int id = (int)a.point_list[range.x + progress];
+            s_id[tid] = id;
+            s_r0[tid] = __ldg(&a.rec[3 * (size_t)id]);
+            s_r1[tid] = __ldg(&a.rec[3 * (size_t)id + 1]);
+            s_r2[tid] = __ldg(&a.rec[3 * (size_t)id + 2]);
+        }
+        __syncthreads();
+        const int n = min(256, toDo);
+        for (int j = 0; !done && j < n; j++) {
+            contributor++;
+            const float4 r0 = s_r0[j];
+            const float4 r1 = s_r1[j];
+            const float dx = fsub(r0.x, pixfx), dy = fsub(r0.y, pixfy);
+            const float power = ffma(ffma(dx, fmul(dx, r0.z), fmul(dy, fmul(dy, r1.x))), -0.5f, -fmul(dy, fmul(dx, r0.w)));
+            if (power > 0.0f || power < r1.z) continue;
+            const float alpha = fminf(0.99f, fmul(r1.y, expf(power)));
+            if (alpha < 1.0f / 255.0f) continue;
+
+            if (!hit && alpha >= a.opaque_thr) {
+                const int id = s_id[j];
+                const float sx = a.scales[3 * id], sy = a.scales[3 * id + 1], sz = a.scales[3 * id + 2];
+                const float4 q = reinterpret_cast<const float4 *>(a.rotations)[id];
+                const QuatMat R = quat_to_glm(q.x, q.y, q.z, q.w);
+                const int ax = arg_min3(sx, sy, sz);
+                const float nx = R.c0[ax], ny = R.c1[ax], nz = R.c2[ax];
+                const float smax = fmul(fmaxf(fmaxf(sx, sy), sz), a.scale_mod);
+                const float *v = a.view;
+                const float ncx = xform_row3(v, 0, nx, ny, nz), ncy = xform_row3(v, 1, nx, ny, nz),
+                            ncz = xform_row3(v, 2, nx, ny, nz);
+                const float wx = a.means3D[3 * id], wy = a.means3D[3 * id + 1], wz = a.means3D[3 * id + 2];
+                const float pcx = xform_row(v, 0, wx, wy, wz), pcy = xform_row(v, 1, wx, wy, wz),
+                            pcz = xform_row(v, 2, wx, wy, wz);
+                const float3 ray = pixel_ray(pix_x, pix_y, a.fx, a.fy, a.cx, a.cy);
+                const float num = dot3_ref(pcx, ncx, pcy, ncy, pcz, ncz);
+                const float den = dot3_ref(ray.x, ncx, ray.y, ncy, ray.z, ncz);
+                const float t = (float)((double)num / ((double)den + 1e-8));
+                const float hx = fmul(t, ray.x), hy = fmul(t, ray.y), hz = fmul(t, ray.z);
+                const float depth_distance = fabsf(fsub(hz, pcz));
+                const float angle_distance = fabsf(den);
+                hit_id = id;
+                hit_dw = fmul(alpha, T);
+                if (depth_distance <= fmul(smax, a.depth_thr) && angle_distance >= a.normal_thr)
+                    depth_ = hz;
+                else
+                    depth_ = r1.w;
+                const size_t sp = (size_t)tile * 256 + tid;
+                a.hit_geo[sp] = ncx;
+                a.hit_geo[a.plane + sp] = ncy;
+                a.hit_geo[2 * a.plane + sp] = ncz;
+                a.hit_geo[3 * a.plane + sp] = hx;
+                a.hit_geo[4 * a.plane + sp] = hy;
+                a.hit_geo[5 * a.plane + sp] = hz;
+                hit = true;
+            }
+            const float test_T = fmul(T, fsub(1.0f, alpha));
+            if (test_T < a.T_thr && hit) {
+                done = true;
+                continue;
+            }
+            if (test_T >= a.T_thr) {
+                const float w = fmul(alpha, T);
+                const float4 r2 = s_r2[j];
+                C0 = ffma(r2.x, w, C0);
+                C1 = ffma(r2.y, w, C1);
+                C2 = ffma(r2.z, w, C2);
+                if (w > cw_max) {
+                    cw_max = w;
+                    hit_color_id = s_id[j];
+                    hit_cw = w;
+                }
+                if (a.n_touched && test_T > 0.5f) {
+                    const int id = s_id[j];
+                    const unsigned m = __match_any_sync(__activemask(), id);
+                    if (lane == __ffs(m) - 1) atomicAdd(&a.n_touched[id], __popc(m));
+                }
+                last_contributor = contributor;
+                end_T = test_T;
+            }
+            T = test_T;
+        }
+    }
+    if (inside) {
+        const size_t sp = (size_t)tile * 256 + tid;
+        a.final_T[sp] = end_T;
+        a.n_contrib[sp] = last_contributor;
+        a.out_color[pix_id] = ffma(T, a.bg[0], C0);
+        a.out_color[HW + pix_id] = ffma(T, a.bg[1], C1);
+        a.out_color[2 * HW + pix_id] = ffma(T, a.bg[2], C2);
+        a.out_depth[pix_id] = depth_;
+        a.out_hit_depth[pix_id] = hit_id;
+        a.out_hit_color[pix_id] = hit_color_id;
+        a.out_hit_cw[pix_id] = hit_cw;
+        a.out_hit_dw[pix_id] = hit_dw;
+        a.out_T[pix_id] = end_T;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// state export for parity tests
+// ------------------------------------------------------------------------------------------------
+__global__ void export_instances_kernel(int64_t capacity, const int *__restrict__ status,
+                                        const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                        const float4 *__restrict__ rec, uint64_t *out_keys, uint32_t *out_list) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= capacity) return;
+    const int64_t L = status[DQO_ST_OVERFLOW] ? 0 : status[DQO_ST_NUM_RENDERED];
+    if (i < L) {
+        const uint32_t id = vals[i];
+        const uint32_t dbits = __float_as_uint(rec[3 * (size_t)id + 1].w);
+        if (out_keys) out_keys[i] = ((uint64_t)keys[i] << 32) | dbits;
+        if (out_list) out_list[i] = id;
+    } else {
+        if (out_keys) out_keys[i] = 0;
+        if (out_list) out_list[i] = 0;
+    }
+}
+__global__ void export_pixels_kernel(int W, int H, int grid_x, const uint32_t *__restrict__ n_contrib,
+                                     const float *__restrict__ final_T, const uint2 *__restrict__ ranges,
+                                     uint32_t *out_nc, float *out_T) {
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+    const int px = (tile % grid_x) * 16 + lx, py = (tile / grid_x) * 16 + ly;
+    if (px >= W || py >= H) return;
+    const uint2 r = ranges[tile];
+    const bool rendered = r.x != r.y;
+    const size_t sp = (size_t)tile * 256 + tid;
+    if (out_nc) out_nc[(size_t)py * W + px] = rendered ? n_contrib[sp] : 0u;
+    if (out_T) out_T[(size_t)py * W + px] = rendered ? final_T[sp] : 1.0f;
+}
+__global__ void export_gauss_kernel(int P, const float4 *__restrict__ rec, const uint32_t *__restrict__ tiles,
+                                    const uint8_t *__restrict__ flags, float *means2D, float *depths, float *conic_o,
+                                    float *rgb, uint32_t *tiles_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const bool valid = (flags[i] & 0x80) != 0;
+    float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0;
+    if (valid) {
+        r0 = rec[3 * (size_t)i];
+        r1 = rec[3 * (size_t)i + 1];
+        r2 = rec[3 * (size_t)i + 2];
+    }
+    if (means2D) {
+        means2D[2 * i] = r0.x;
+        means2D[2 * i + 1] = r0.y;
+    }
+    if (depths) depths[i] = r1.w;
+    if (conic_o) {
+        conic_o[4 * i] = r0.z;
+        conic_o[4 * i + 1] = r0.w;
+        conic_o[4 * i + 2] = r1.x;
+        conic_o[4 * i + 3] = r1.y;
+    }
+    if (rgb) {
+        rgb[3 * i] = r2.x;
+        rgb[3 * i + 1] = r2.y;
+        rgb[3 * i + 2] = r2.z;
+    }
+    if (tiles_out) tiles_out[i] = tiles[i];
+}
+} // namespace dqo
+
+using namespace dqo;
+
+extern "C" size_t dqo_rast_geom_bytes(int32_t P) {
+    GeomLayout L;
+    if (make_geom_layout(P, &L)) return 0;
+    return L.total;
+}
+extern "C" size_t dqo_rast_binning_bytes(int64_t C) {
+    BinLayout L;
+    if (make_bin_layout(C, &L)) return 0;
+    return L.total;
+}
+extern "C" size_t dqo_rast_image_bytes(int32_t W, int32_t H) {
+    ImgLayout L;
+    make_img_layout(W, H, &L);
+    return L.total;
+}
+
+extern "C" int dqo_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                                uint8_t *present, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !projmatrix || !present))) {
+        set_error("dqo_mark_visible: invalid argument");
+        return DQO_ERR_INVALID_ARG;
+    }
+    if (P == 0) return DQO_OK;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, projmatrix, present);
+    DQO_LAUNCH_CHECK("mark_visible", 0, stream);
+    return DQO_OK;
+}
+
+extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *background, const float *means3D,
+                                const float *shs, const float *colors_precomp, const float *opacities,
+                                const float *scales, const float *rotations, const float *cov3D_precomp,
+                                const float *viewmatrix, const float *projmatrix, const float *campos,
+                                const int32_t *tile_mask, void *geom_buffer, void *binning_buffer,
+                                int64_t capacity, void *image_buffer, int32_t *tile_indices, float *out_color,
+                                float *out_depth, int32_t *out_hit_depth, int32_t *out_hit_color,
+                                float *out_hit_color_weight, float *out_hit_depth_weight, float *out_T, int32_t *radii,
+                                int32_t *n_touched, int32_t *status, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!s || s->P < 0 || s->W <= 0 || s->H <= 0 || !status) {
+        set_error("dqo_rast_forward: invalid settings");
+        return DQO_ERR_INVALID_ARG;
+    }
+    if (!background || !viewmatrix || !projmatrix || !campos || !tile_mask || !image_buffer || !tile_indices ||
+        !out_color || !out_depth || !out_hit_depth || !out_hit_color || !out_hit_color_weight ||
+        !out_hit_depth_weight || !out_T) {
+        set_error("dqo_rast_forward: null pointer argument");
+        return DQO_ERR_INVALID_ARG;
+    }
+    const int P = s->P;
+    if (P > 0) {
+        if (!means3D || !opacities || !geom_buffer || !binning_buffer || !radii || capacity <= 0) {
+            set_error("dqo_rast_forward: null pointer argument");
+            return DQO_ERR_INVALID_ARG;
+        }
+        if ((shs == nullptr) == (colors_precomp == nullptr)) {
+            set_error("Please provide excatly one of either SHs or precomputed colors!");
+            return DQO_ERR_INVALID_ARG;
+        }
+        if (!scales || !rotations) {
+            // the reference blend dereferences scales/rotations unconditionally (forward.cu:780)
+            set_error("scale/rotation pair is required by the depth rasterizer (cov3D_precomp alone is not supported)");
+            return DQO_ERR_INVALID_ARG;
+        }
+        if (shs && (s->M <= 0 || (s->D + 1) * (s->D + 1) > s->M || s->D > 3 || s->D < 0)) {
+            set_error("dqo_rast_forward: SH degree %d incompatible with %d coefficients", s->D, s->M);
+            return DQO_ERR_INVALID_ARG;
+        }
+    }
+    const int debug = s->debug;
+    ImgLayout IL;
+    make_img_layout(s->W, s->H, &IL);
+    char *img = (char *)image_buffer;
+    uint2 *ranges = (uint2 *)(img + IL.ranges);
+    const int T = IL.T;
+    if ((int64_t)T >= (1ll << 31)) {
+        set_error("image too large");
+        return DQO_ERR_INVALID_ARG;
+    }
+    DQO_CUDA_CHECK(cudaMemsetAsync(ranges, 0, (size_t)T * sizeof(uint2), stream));
+    DQO_CUDA_CHECK(cudaMemsetAsync(status, 0, DQO_ST_WORDS * sizeof(int), stream));
+
+    const float focal_y = s->H / (2.0f * s->tanfovy);
+    const float focal_x = s->W / (2.0f * s->tanfovx);
+    GeomLayout GL;
+    BinLayout BL;
+    const uint32_t *point_list = nullptr;
+    const float4 *rec = nullptr;
+    if (P > 0) {
+        if (make_geom_layout(P, &GL)) return DQO_ERR_WORKSPACE;
+        if (make_bin_layout(capacity, &BL)) return DQO_ERR_WORKSPACE;
+        char *geom = (char *)geom_buffer;
+        char *bin = (char *)binning_buffer;
+        PreArgs pa;
+        pa.P = P; pa.D = s->D; pa.M = s->M; pa.W = s->W; pa.H = s->H;
+        pa.color_sigma = s->color_sigma; pa.scale_modifier = s->scale_modifier;
+        pa.tanfovx = s->tanfovx; pa.tanfovy = s->tanfovy; pa.focal_x = focal_x; pa.focal_y = focal_y;
+        pa.cx = s->cx; pa.cy = s->cy; pa.grid_x = IL.tiles_x; pa.grid_y = IL.tiles_y;
+        pa.prefiltered = s->prefiltered;
+        pa.means3D = means3D; pa.scales = scales; pa.rotations = rotations; pa.opacities = opacities;
+        pa.shs = shs; pa.cov3D_precomp = cov3D_precomp; pa.colors_precomp = colors_precomp;
+        pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos; pa.tile_mask = tile_mask;
+        pa.radii = radii; pa.n_touched = n_touched;
+        pa.rec = (float4 *)(geom + GL.rec);
+        pa.depth_key = (uint32_t *)(geom + GL.depth_key);
+        pa.ids = (uint32_t *)(geom + GL.ids);
+        pa.tiles = (uint32_t *)(geom + GL.tiles);
+        pa.rect = (uint2 *)(geom + GL.rect);
+        pa.clamped = (uint8_t *)(geom + GL.clamped);
+        pa.status = status;
+        rec = pa.rec;
+        preprocess_kernel<<<(P + 255) / 256, 256, 0, stream>>>(pa);
+        DQO_LAUNCH_CHECK("preprocess", debug, stream);
+
+        // (depth, id) order of the Gaussians: stable LSD sort on the depth bits
+        uint32_t *order = (uint32_t *)(geom + GL.order);
+        size_t cub_bytes = GL.cub_bytes;
+        DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(geom + GL.cub, cub_bytes, (const uint32_t *)pa.depth_key,
+                                                       (uint32_t *)(geom + GL.depth_key2), (const uint32_t *)pa.ids,
+                                                       order, P, 0, 32, stream));
+        DQO_LAUNCH_CHECK("depth sort", debug, stream);
+        uint32_t *offsets = (uint32_t *)(geom + GL.offsets);
+        TilesInRankOrder it((const uint32_t *)order, GatherTiles{pa.tiles});
+        cub_bytes = GL.cub_bytes;
+        DQO_CUDA_CHECK(cub::DeviceScan::InclusiveSum(geom + GL.cub, cub_bytes, it, offsets, P, stream));
+        DQO_LAUNCH_CHECK("scan", debug, stream);
+
+        uint32_t *keys_in = (uint32_t *)(bin + BL.keys_in), *keys_out = (uint32_t *)(bin + BL.keys_out);
+        uint32_t *vals_in = (uint32_t *)(bin + BL.vals_in), *vals_out = (uint32_t *)(bin + BL.vals_out);
+        const int64_t nthreads = capacity > P ? capacity : P;
+        duplicate_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, stream>>>(
+            P, capacity, order, pa.tiles, offsets, pa.rect, tile_mask, IL.tiles_x, keys_in, vals_in, status);
+        DQO_LAUNCH_CHECK("duplicate", debug, stream);
+        const int bit = (int)higher_msb((uint32_t)T);
+        cub_bytes = BL.cub_bytes;
+        DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(bin + BL.cub, cub_bytes, (const uint32_t *)keys_in, keys_out,
+                                                       (const uint32_t *)vals_in, vals_out, (int)capacity, 0, bit,
+                                                       stream));
+        DQO_LAUNCH_CHECK("tile sort", debug, stream);
+        tile_ranges_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(capacity, keys_out, status, ranges);
+        DQO_LAUNCH_CHECK("tile ranges", debug, stream);
+        point_list = vals_out;
+    }
+    compact_tiles_kernel<<<1, 1024, 0, stream>>>(T, ranges, tile_indices, status);
+    DQO_LAUNCH_CHECK("compact tiles", debug, stream);
+
+    RenderArgs ra;
+    ra.W = s->W; ra.H = s->H; ra.grid_x = IL.tiles_x;
+    ra.fx = focal_x; ra.fy = focal_y; ra.cx = s->cx; ra.cy = s->cy; ra.scale_mod = s->scale_modifier;
+    ra.opaque_thr = s->opaque_threshold; ra.depth_thr = s->depth_threshold; ra.normal_thr = s->normal_threshold;
+    ra.T_thr = s->T_threshold;
+    ra.ranges = ranges; ra.point_list = point_list; ra.rec = rec;
+    ra.view = viewmatrix; ra.means3D = means3D; ra.scales = scales; ra.rotations = rotations; ra.bg = background;
+    ra.n_contrib = (uint32_t *)(img + IL.n_contrib);
+    ra.final_T = (float *)(img + IL.final_T);
+    ra.hit_geo = (float *)(img + IL.hit_geo);
+    ra.plane = (size_t)T * 256;
+    ra.out_color = out_color; ra.out_depth = out_depth; ra.out_hit_cw = out_hit_color_weight;
+    ra.out_hit_dw = out_hit_depth_weight; ra.out_T = out_T; ra.out_hit_depth = out_hit_depth;
+    ra.out_hit_color = out_hit_color; ra.n_touched = s->need_n_touched ? n_touched : nullptr;
+    render_forward_kernel<<<T, 256, 0, stream>>>(ra);
+    DQO_LAUNCH_CHECK("render forward", debug, stream);
+    return DQO_OK;
+}
+
+extern "C" int dqo_rast_export_state(const dqo_rast_settings *s, const void *geom_buffer, const void *binning_buffer,
+                                     int64_t capacity, const void *image_buffer, const int32_t *status,
+                                     uint64_t *sorted_keys, uint32_t *point_list, uint32_t *ranges_out,
+                                     uint32_t *n_contrib, float *final_T, float *means2D, float *depths,
+                                     float *conic_opacity, float *rgb, uint32_t *tiles_touched, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!s || !image_buffer || !status) return DQO_ERR_INVALID_ARG;
+    ImgLayout IL;
+    make_img_layout(s->W, s->H, &IL);
+    const char *img = (const char *)image_buffer;
+    const int P = s->P;
+    if (ranges_out)
+        DQO_CUDA_CHECK(cudaMemcpyAsync(ranges_out, img + IL.ranges, (size_t)IL.T * 8, cudaMemcpyDeviceToDevice, stream));
+    if (n_contrib || final_T)
+        export_pixels_kernel<<<IL.T, 256, 0, stream>>>(s->W, s->H, IL.tiles_x, (const uint32_t *)(img + IL.n_contrib),
+                                                       (const float *)(img + IL.final_T),
+                                                       (const uint2 *)(img + IL.ranges), n_contrib, final_T);
+    if (P > 0) {
+        GeomLayout GL;
+        BinLayout BL;
+        if (make_geom_layout(P, &GL) || make_bin_layout(capacity, &BL)) return DQO_ERR_WORKSPACE;
+        const char *geom = (const char *)geom_buffer;
+        const char *bin = (const char *)binning_buffer;
+        if (sorted_keys || point_list)
+            export_instances_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(
+                capacity, status, (const uint32_t *)(bin + BL.keys_out), (const uint32_t *)(bin + BL.vals_out),
+                (const float4 *)(geom + GL.rec), sorted_keys, point_list);
+        if (means2D || depths || conic_opacity || rgb || tiles_touched) {
+            export_gauss_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
+                P, (const float4 *)(geom + GL.rec), (const uint32_t *)(geom + GL.tiles),
+                (const uint8_t *)(geom + GL.clamped), means2D, depths, conic_opacity, rgb, tiles_touched);
+        }
+    }
+    DQO_LAUNCH_CHECK("export", 0, stream);
+    return DQO_OK;
+}

@@ -1,0 +1,302 @@
+"""Host-side mirror of the reference rasterizer binding.
+
+Same names, argument meaning and error behaviour as
+`submodules/diff-gaussian-rasterizer-depth/diff_gaussian_rasterization_depth/__init__.py`
+(GaussianRasterizationSettings :288-307, GaussianRasterizer :310-376, _RasterizeGaussians :53-285) and as the
+pybind functions of `rasterize_points.cu` (rasterize_gaussians :37-155, rasterize_gaussians_backward :157-249,
+mark_visible :251-270), implemented over the C-ABI of include/dqo_b200.h.  PyTorch only owns memory and streams.
+"""
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import RastSettings, check, lib, ptr
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    opaque_threshold: float
+    normal_threshold: float
+    depth_threshold: float
+    prefiltered: bool
+    debug: bool
+    cx: float
+    cy: float
+    color_sigma: float = 3.0
+    T_threshold: float = 0.0001
+
+
+# ---------------------------------------------------------------------------------------------------
+# workspace policy: the instance capacity is remembered per device and grows geometrically.  The forward
+# never synchronises in the middle of the pipeline; one status read-back at the end tells whether the
+# capacity was sufficient (otherwise the pass is re-run with a larger buffer).
+# ---------------------------------------------------------------------------------------------------
+_capacity_hint = {}
+NEED_N_TOUCHED = True  # reference behaviour (forward.cu:833-835); set False to skip the per-pair counter
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t):
+    if t is None or t.numel() == 0:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError("expected float32 tensor, got %s" % t.dtype)
+    return t.contiguous()
+
+
+def _make_settings(P, D, M, W, H, tanfovx, tanfovy, cx, cy, scale_modifier, color_sigma, opaque_threshold,
+                   depth_threshold, normal_threshold, T_threshold, prefiltered, debug, need_n_touched=True):
+    return RastSettings(P, D, M, W, H, tanfovx, tanfovy, cx, cy, scale_modifier, color_sigma, opaque_threshold,
+                        depth_threshold, normal_threshold, T_threshold, int(bool(prefiltered)), int(bool(debug)),
+                        int(bool(need_n_touched)))
+
+
+class ForwardState:
+    """Everything the backward needs; plays the role of (geomBuffer, binningBuffer, imgBuffer, tile_indices,
+    num_rendered, num_tile) in the reference."""
+    __slots__ = ("settings", "geom", "binning", "image", "tile_indices", "status", "capacity", "status_host")
+
+
+def _forward_impl(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                  projmatrix, render_mask, tan_fovx, tan_fovy, image_height, image_width, cx, cy, sh, degree,
+                  color_sigma, campos, opaque_threshold, hit_depth_threshold, hit_normal_threshold, T_threshold,
+                  prefiltered, debug, sync=True, tile_indices_len=None):
+    L = lib()
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:67-70
+    if not means3D.is_cuda:
+        raise RuntimeError("means3D must be a CUDA tensor (there is no CPU path)")
+    dev = means3D.device
+    P, H, W = means3D.size(0), int(image_height), int(image_width)
+    sh_c, colors_c = _f32c(sh), _f32c(colors)
+    M = sh_c.size(1) if sh_c is not None else 0
+    means_c, opac_c = _f32c(means3D), _f32c(opacity)
+    scales_c, rot_c, cov_c = _f32c(scales), _f32c(rotations), _f32c(cov3D_precomp)
+    bg_c, view_c, proj_c, campos_c = _f32c(background), _f32c(viewmatrix), _f32c(projmatrix), _f32c(campos)
+    if render_mask is None:
+        raise TypeError("tile_mask must be an int32 CUDA tensor of shape [ceil(H/16), ceil(W/16)]")
+    mask_c = render_mask.contiguous()
+    tiles = ((H + 15) // 16) * ((W + 15) // 16)
+    if mask_c.dtype != torch.int32 or mask_c.numel() != tiles:
+        raise TypeError("tile_mask must be an int32 tensor with %d elements" % tiles)
+
+    f32 = dict(dtype=torch.float32, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    out_color = torch.empty((3, H, W), **f32)
+    out_depth = torch.empty((1, H, W), **f32)
+    out_hit_depth = torch.empty((1, H, W), **i32)
+    out_hit_color = torch.empty((1, H, W), **i32)
+    out_hit_cw = torch.empty((1, H, W), **f32)
+    out_hit_dw = torch.empty((1, H, W), **f32)
+    out_T = torch.empty((1, H, W), **f32)
+    radii = torch.empty((P,), **i32)
+    n_touched = torch.empty((P,), **i32)
+    tile_indices = torch.empty((tile_indices_len or tiles,), **i32)
+    if tile_indices.numel() > tiles:
+        tile_indices[tiles:] = -1
+    status = torch.empty((_lib.ST_WORDS,), **i32)
+
+    st = ForwardState()
+    st.settings = _make_settings(P, int(degree), M, W, H, tan_fovx, tan_fovy, cx, cy, scale_modifier, color_sigma,
+                                 opaque_threshold, hit_depth_threshold, hit_normal_threshold, T_threshold, prefiltered,
+                                 debug, NEED_N_TOUCHED)
+    st.image = torch.empty((L.dqo_rast_image_bytes(W, H),), dtype=torch.uint8, device=dev)
+    st.tile_indices, st.status = tile_indices, status
+    st.geom = torch.empty((L.dqo_rast_geom_bytes(P) if P > 0 else 0,), dtype=torch.uint8, device=dev)
+    key = (dev.index, )
+    capacity = max(_capacity_hint.get(key, 0), 4 * P, 1 << 16) if P > 0 else 0
+    while True:
+        st.capacity = capacity
+        st.binning = torch.empty((L.dqo_rast_binning_bytes(capacity) if P > 0 else 0,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            code = L.dqo_rast_forward(
+                st.settings, ptr(bg_c), ptr(means_c), ptr(sh_c), ptr(colors_c), ptr(opac_c), ptr(scales_c), ptr(rot_c),
+                ptr(cov_c), ptr(view_c), ptr(proj_c), ptr(campos_c), ptr(mask_c), ptr(st.geom), ptr(st.binning),
+                capacity, ptr(st.image), ptr(tile_indices), ptr(out_color), ptr(out_depth), ptr(out_hit_depth),
+                ptr(out_hit_color), ptr(out_hit_cw), ptr(out_hit_dw), ptr(out_T), ptr(radii), ptr(n_touched),
+                ptr(status), _stream())
+        check(code, "dqo_rast_forward")
+        if not sync:
+            st.status_host = None
+            break
+        host = status.tolist()  # the single host synchronisation of the forward, after all launches
+        st.status_host = host
+        if not host[_lib.ST_OVERFLOW]:
+            _capacity_hint[key] = max(_capacity_hint.get(key, 0), int(host[_lib.ST_NUM_RENDERED] * 1.25) + 1024)
+            break
+        capacity = int(host[_lib.ST_NUM_RENDERED] * 1.25) + 1024
+        _capacity_hint[key] = capacity
+    outs = (out_color, out_depth, out_hit_color, out_hit_depth, out_hit_cw, out_hit_dw, out_T, radii, n_touched)
+    return st, outs
+
+
+def _backward_impl(st, background, means3D, radii, colors, scales, rotations, cov3D_precomp, viewmatrix, projmatrix,
+                   dL_dout_color, dL_dout_depth, sh, campos, hit_image):
+    L = lib()
+    dev = means3D.device
+    s = st.settings
+    P, M = s.P, s.M
+    f32 = dict(dtype=torch.float32, device=dev)
+    dL_dmeans3D = torch.empty((P, 3), **f32)
+    dL_dmeans2D = torch.empty((P, 3), **f32)
+    dL_dcolors = torch.empty((P, 3), **f32)
+    dL_dconic = torch.empty((P, 2, 2), **f32)
+    dL_dopacity = torch.empty((P, 1), **f32)
+    dL_dcov3D = torch.empty((P, 6), **f32)
+    dL_dsh = torch.empty((P, M, 3), **f32)
+    dL_dscales = torch.empty((P, 3), **f32)
+    dL_drotations = torch.empty((P, 4), **f32)
+    if P != 0:
+        g_color, g_depth = _f32c(dL_dout_color), _f32c(dL_dout_depth)
+        with torch.cuda.device(dev):
+            code = L.dqo_rast_backward(
+                s, ptr(_f32c(background)), ptr(_f32c(means3D)), ptr(_f32c(sh)), ptr(_f32c(colors)),
+                ptr(_f32c(scales)), ptr(_f32c(rotations)), ptr(_f32c(cov3D_precomp)), ptr(_f32c(viewmatrix)),
+                ptr(_f32c(projmatrix)), ptr(_f32c(campos)), ptr(radii), ptr(st.geom), ptr(st.binning), st.capacity,
+                ptr(st.image), ptr(st.status), ptr(g_color), ptr(g_depth), ptr(hit_image.contiguous()),
+                ptr(dL_dmeans2D), ptr(dL_dconic), ptr(dL_dopacity), ptr(dL_dcolors), ptr(dL_dmeans3D), ptr(dL_dcov3D),
+                ptr(dL_dsh), ptr(dL_dscales), ptr(dL_drotations), _stream())
+        check(code, "dqo_rast_backward")
+    return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+# ---------------------------------------------------------------------------------------------------
+# pybind-level compatibility functions (`_C_depth.*`, RAST/ext.cpp:15-19)
+# ---------------------------------------------------------------------------------------------------
+def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                        viewmatrix, projmatrix, render_mask, tan_fovx, tan_fovy, image_height, image_width, cx, cy,
+                        sh, degree, color_sigma, campos, opaque_threshold, hit_depth_threshold, hit_normal_threshold,
+                        T_threshold, prefiltered, debug):
+    """Same 27 arguments and 15-tuple as the reference's `rasterize_gaussians`.  `geomBuffer` carries the
+    private forward state object (callers only pass it back to `rasterize_gaussians_backward`)."""
+    st, outs = _forward_impl(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                             viewmatrix, projmatrix, render_mask, tan_fovx, tan_fovy, image_height, image_width, cx,
+                             cy, sh, degree, color_sigma, campos, opaque_threshold, hit_depth_threshold,
+                             hit_normal_threshold, T_threshold, prefiltered, debug, sync=True,
+                             tile_indices_len=int(image_height) * int(image_width))
+    (color, depth, hit_color, hit_depth, hit_cw, hit_dw, T_map, radii, n_touched) = outs
+    rendered = st.status_host[_lib.ST_NUM_RENDERED]
+    tile_num = st.status_host[_lib.ST_TILE_NUM]
+    st.geom._dqo_state = st  # keep the state reachable from the returned buffer
+    return (rendered, tile_num, color, depth, hit_color, hit_depth, hit_cw, hit_dw, T_map, radii, st.geom, st.binning,
+            st.image, st.tile_indices, n_touched)
+
+
+def rasterize_gaussians_backward(tile_indices, tile_num, background, means3D, radii, colors, scales, rotations,
+                                 scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, cx, cy,
+                                 depth_threshold, normal_threshold, dL_dout_color, dL_dout_depth, sh, degree, campos,
+                                 geomBuffer, R, binningBuffer, imageBuffer, hit_image, debug):
+    """Same 29 arguments and 8-tuple as the reference's `rasterize_gaussians_backward`."""
+    st = getattr(geomBuffer, "_dqo_state", None)
+    if st is None:
+        raise RuntimeError("geomBuffer was not produced by this library's rasterize_gaussians")
+    return _backward_impl(st, background, means3D, radii, colors, scales, rotations, cov3D_precomp, viewmatrix,
+                          projmatrix, dL_dout_color, dL_dout_depth, sh, campos, hit_image)
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    P = means3D.size(0)
+    present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
+    if P != 0:
+        with torch.cuda.device(means3D.device):
+            check(lib().dqo_mark_visible(P, ptr(_f32c(means3D)), ptr(_f32c(viewmatrix)), ptr(_f32c(projmatrix)),
+                                         ptr(present), _stream()), "dqo_mark_visible")
+    return present
+
+
+# ---------------------------------------------------------------------------------------------------
+# autograd wrapper (same structure as the reference's _RasterizeGaussians)
+# ---------------------------------------------------------------------------------------------------
+def rasterize_gaussians_fn(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, tile_mask,
+                           raster_settings):
+    return _RasterizeGaussians.apply(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                     tile_mask, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, tile_mask,
+                raster_settings):
+        rs = raster_settings
+        st, outs = _forward_impl(rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
+                                 cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, tile_mask, rs.tanfovx, rs.tanfovy,
+                                 rs.image_height, rs.image_width, rs.cx, rs.cy, sh, rs.sh_degree, rs.color_sigma,
+                                 rs.campos, rs.opaque_threshold, rs.depth_threshold, rs.normal_threshold,
+                                 rs.T_threshold, rs.prefiltered, rs.debug, sync=True)
+        (color, depth, hit_color, hit_depth, hit_cw, hit_dw, T_map, radii, n_touched) = outs
+        ctx.raster_settings = rs
+        ctx.state = st
+        ctx.num_rendered = st.status_host[_lib.ST_NUM_RENDERED]
+        ctx.num_tile = st.status_host[_lib.ST_TILE_NUM]
+        ctx.save_for_backward(colors_precomp, hit_depth, means3D, scales, rotations, cov3Ds_precomp, radii, sh)
+        ctx.mark_non_differentiable(hit_color, hit_depth, n_touched, radii)
+        return color, depth, hit_color, hit_depth, hit_cw, hit_dw, T_map, n_touched, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_out_depth, grad_hit_color, grad_hit_depth, grad_hit_color_weight,
+                 grad_hit_depth_weight, grad_T_map, grad_n_touched, _):
+        # only colour and depth gradients are consumed, like the reference (__init__.py:176-187, N5)
+        rs = ctx.raster_settings
+        colors_precomp, hit_depth, means3D, scales, rotations, cov3Ds_precomp, radii, sh = ctx.saved_tensors
+        H, W = int(rs.image_height), int(rs.image_width)
+        if grad_out_color is None:
+            grad_out_color = torch.zeros((3, H, W), dtype=torch.float32, device=means3D.device)
+        if grad_out_depth is None:
+            grad_out_depth = torch.zeros((1, H, W), dtype=torch.float32, device=means3D.device)
+        (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
+         grad_rotations) = _backward_impl(ctx.state, rs.bg, means3D, radii, colors_precomp, scales, rotations,
+                                          cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, grad_out_color,
+                                          grad_out_depth, sh, rs.campos, hit_depth)
+
+        def _opt(g, x):  # gradients for absent (empty) inputs are dropped
+            return g if (x is not None and x.numel() != 0) else None
+
+        return (grad_means3D, _opt(grad_sh, sh), _opt(grad_colors_precomp, colors_precomp), grad_opacities,
+                _opt(grad_scales, scales), _opt(grad_rotations, rotations), _opt(grad_cov3Ds_precomp, cov3Ds_precomp),
+                None, None)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            return mark_visible(positions, rs.viewmatrix, rs.projmatrix)
+
+    def forward(self, means3D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None, tile_mask=None, normal_w=None):
+        raster_settings = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+                (scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+        return rasterize_gaussians_fn(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                      tile_mask, raster_settings)

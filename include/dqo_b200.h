@@ -1,0 +1,218 @@
+/*
+ * dqo_b200.h — C-ABI of the B200-native DQO-MAP hot path (libdqomap_b200.so).
+ *
+ * Every entry point takes only POD: device pointers, sizes, floats and a CUDA stream handle
+ * (cudaStream_t passed as void*).  No torch types, no C++ exceptions, no std::function.
+ * All functions are asynchronous with respect to the host (they only enqueue work on `stream`)
+ * and return 0 on success or a negative DQO_ERR_* / positive cudaError_t code.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the reference
+ * repository root; RAST = submodules/diff-gaussian-rasterizer-depth, KNN = submodules/simple-knn,
+ * CU = submodules/cuda_utils).
+ */
+#ifndef DQO_B200_H_
+#define DQO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DQO_OK 0
+#define DQO_ERR_INVALID_ARG (-1)
+#define DQO_ERR_NO_DEVICE (-2)
+#define DQO_ERR_WORKSPACE (-3)
+
+/* ABI version; bumped whenever a signature or struct layout changes. */
+int dqo_abi_version(void);
+/* Human-readable description of the last error on this thread (never NULL). */
+const char *dqo_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rasterizer settings.  Mirrors GaussianRasterizationSettings
+ * (RAST/diff_gaussian_rasterization_depth/__init__.py:288-307) minus the tensors, plus the sizes
+ * the pybind layer derives from tensor shapes (RAST/rasterize_points.cu:72-109).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dqo_rast_settings {
+    int32_t P;          /* number of Gaussians (means3D.size(0)) */
+    int32_t D;          /* active SH degree (sh_degree) */
+    int32_t M;          /* SH coefficients per channel stored in `shs` (0 when colors are precomputed) */
+    int32_t W, H;       /* image_width, image_height */
+    float tanfovx, tanfovy;
+    float cx, cy;
+    float scale_modifier;
+    float color_sigma;        /* default 3.0 */
+    float opaque_threshold;
+    float depth_threshold;    /* "hit_depth_threshold" of the kernels */
+    float normal_threshold;   /* cos of the angle */
+    float T_threshold;        /* default 1e-4 */
+    int32_t prefiltered;
+    int32_t debug;            /* nonzero: synchronise after every stage and report the failing one */
+    int32_t need_n_touched;   /* 1 = reference behaviour (count per-Gaussian touches, forward.cu:833-835) */
+} dqo_rast_settings;
+
+/* status words written on the device by the forward pass (int32[8]) */
+#define DQO_ST_NUM_RENDERED 0 /* R: number of (Gaussian, tile) instances (rasterizer_impl.cu:307) */
+#define DQO_ST_TILE_NUM 1     /* number of non-empty tiles (rasterizer_impl.cu:365) */
+#define DQO_ST_OVERFLOW 2     /* 1 if R exceeded the instance capacity: outputs are invalid, re-run larger */
+#define DQO_ST_NUM_VISIBLE 3  /* Gaussians with radii > 0 */
+#define DQO_ST_WORDS 8
+
+/* Workspace sizing (replaces the three resize callbacks of CudaRasterizer::Rasterizer::forward,
+ * RAST/cuda_rasterizer/rasterizer.h:31-33 and rasterizer_impl.h:68-74 `required<T>`). */
+size_t dqo_rast_geom_bytes(int32_t P);
+size_t dqo_rast_binning_bytes(int64_t instance_capacity);
+size_t dqo_rast_image_bytes(int32_t W, int32_t H);
+
+/* Forward pass.  Replaces CudaRasterizer::Rasterizer::forward (RAST/cuda_rasterizer/rasterizer.h:30-76,
+ * rasterizer_impl.cu:205-441) as called by RasterizeGaussiansCUDA (RAST/rasterize_points.cu:37-155).
+ * Optional inputs are NULL when absent (the reference detects empty tensors via null data_ptr).
+ * Every output image is fully written by the call (including the fill values of
+ * rasterize_points.cu:79-89 for tiles that are not rendered), so callers may pass uninitialised memory.
+ * `status` is device int32[DQO_ST_WORDS].  No host synchronisation is performed. */
+int dqo_rast_forward(const dqo_rast_settings *s,
+                     const float *background,     /* [3] */
+                     const float *means3D,        /* [P,3] */
+                     const float *shs,            /* [P,M,3] or NULL */
+                     const float *colors_precomp, /* [P,3] or NULL */
+                     const float *opacities,      /* [P] */
+                     const float *scales,         /* [P,3] or NULL */
+                     const float *rotations,      /* [P,4] or NULL */
+                     const float *cov3D_precomp,  /* [P,6] or NULL */
+                     const float *viewmatrix,     /* [16] column-major (transposed W2C) */
+                     const float *projmatrix,     /* [16] column-major */
+                     const float *campos,         /* [3] */
+                     const int32_t *tile_mask,    /* [ceil(H/16), ceil(W/16)] */
+                     void *geom_buffer, void *binning_buffer, int64_t instance_capacity, void *image_buffer,
+                     int32_t *tile_indices,       /* [>= tiles] compact list of non-empty tiles, rest -1 */
+                     float *out_color,            /* [3,H,W] */
+                     float *out_depth,            /* [H,W] */
+                     int32_t *out_hit_depth,      /* [H,W] index of the Gaussian fixing depth, -1 none */
+                     int32_t *out_hit_color,      /* [H,W] index of the max-weight Gaussian, -1 none */
+                     float *out_hit_color_weight, /* [H,W] */
+                     float *out_hit_depth_weight, /* [H,W] */
+                     float *out_T,                /* [H,W] */
+                     int32_t *radii,              /* [P] */
+                     int32_t *n_touched,          /* [P] */
+                     int32_t *status, void *stream);
+
+/* Backward pass.  Replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:78-105,
+ * rasterizer_impl.cu:445-564) as called by RasterizeGaussiansBackwardCUDA (rasterize_points.cu:157-249).
+ * All nine gradient outputs are fully written (no pre-zeroing needed, cf. rasterize_points.cu:198-206).
+ * dL_dconic is [P,4] (x, y, unused, w) exactly as the reference's [P,2,2] tensor is used. */
+int dqo_rast_backward(const dqo_rast_settings *s, const float *background, const float *means3D, const float *shs,
+                      const float *colors_precomp, const float *scales, const float *rotations,
+                      const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix,
+                      const float *campos, const int32_t *radii, void *geom_buffer /* holds the gradient accumulators */,
+                      const void *binning_buffer, int64_t instance_capacity, const void *image_buffer,
+                      const int32_t *status,
+                      const float *dL_dout_color,   /* [3,H,W] */
+                      const float *dL_dout_depth,   /* [H,W] */
+                      const int32_t *hit_image,     /* [H,W] = out_hit_depth of the forward */
+                      float *dL_dmeans2D,           /* [P,3] */
+                      float *dL_dconic,             /* [P,4] */
+                      float *dL_dopacity,           /* [P] */
+                      float *dL_dcolors,            /* [P,3] */
+                      float *dL_dmeans3D,           /* [P,3] */
+                      float *dL_dcov3D,             /* [P,6] */
+                      float *dL_dsh,                /* [P,M,3] or NULL when M == 0 */
+                      float *dL_dscales,            /* [P,3] */
+                      float *dL_drotations,         /* [P,4] */
+                      void *stream);
+
+/* Frustum test.  Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:23-28,
+ * rasterizer_impl.cu:145-157; pybind `mark_visible`, rasterize_points.cu:251-270). */
+int dqo_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                     uint8_t *present, void *stream);
+
+/* Introspection for parity tests: re-materialises the reference's binning artefacts from the
+ * private workspace in the reference's own formats (rasterizer_impl.h:29-66): 64-bit sorted keys
+ * (tile<<32 | depth bits), sorted Gaussian ids, per-tile ranges, and row-major per-pixel / per-Gaussian state.
+ * Any output pointer may be NULL.  keys/point_list must hold instance_capacity entries. */
+int dqo_rast_export_state(const dqo_rast_settings *s, const void *geom_buffer, const void *binning_buffer,
+                          int64_t instance_capacity, const void *image_buffer, const int32_t *status,
+                          uint64_t *sorted_keys, uint32_t *point_list, uint32_t *ranges /* [tiles,2] */,
+                          uint32_t *n_contrib /* [H,W] */, float *final_T /* [H,W] */,
+                          float *means2D /* [P,2] */, float *depths /* [P] */, float *conic_opacity /* [P,4] */,
+                          float *rgb /* [P,3] */, uint32_t *tiles_touched /* [P] */, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * simple-knn.  Replaces SimpleKNN::knn (KNN/simple_knn.cu:216-252) behind distCUDA2 (KNN/spatial.cu:15-28):
+ * mean squared distance to the 3 nearest neighbours and their original indices (ascending distance,
+ * ties resolved by Morton-sorted position, INT_MAX / FLT_MAX when fewer than 3 neighbours exist).
+ * ---------------------------------------------------------------------------------------------- */
+size_t dqo_knn_workspace_bytes(int32_t P);
+int dqo_knn3(int32_t P, const float *points /* [P,3] */, float *mean_dist2 /* [P] */, int32_t *knn_idx /* [P,3] */,
+             void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * cuda_utils.  Replaces accumulate_gaussian_error_impl (CU/map_process.cu:194-245) behind
+ * accumulate_gaussian_error (CU/cuda_utils.cu:17-60).  All seven [P] outputs are fully written.
+ * ---------------------------------------------------------------------------------------------- */
+int dqo_accumulate_error(int32_t W, int32_t H, int32_t P, const float *color_err, const float *depth_err,
+                         const float *normal_err, const int32_t *color_index, const int32_t *depth_index,
+                         float color_thr, float depth_thr, float normal_thr, int32_t check_max,
+                         float *gs_color_error, float *gs_depth_error, float *gs_normal_error,
+                         int32_t *color_counter, int32_t *depth_counter, int32_t *normal_counter,
+                         float *rescale_counter, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mapping step (no native boundary exists in the reference: SLAM/multiprocess/mapper.py:799-928 is
+ * inline PyTorch).  Masked L1 colour + depth loss and its image gradients in two launches.
+ *   colour: mean |img - gt| over render_mask pixels x 3 channels          (mapper.py:847, loss_utils.py:27-31)
+ *   depth : mean |d - gt_d| over hit != -1 & gt_d > 0 & (d-gt_d) < depth_err_thres & render_mask (mapper.py:849-857)
+ *   total = depth_weight * depth + color_weight * colour
+ * `loss_out` is device float[4] = {total, colour, depth, unused}; `counts_out` device int32[2].
+ * Empty selections give NaN means exactly like torch (0/0) and zero gradients.
+ * ---------------------------------------------------------------------------------------------- */
+size_t dqo_loss_workspace_bytes(int32_t W, int32_t H);
+int dqo_masked_l1_loss(int32_t W, int32_t H, const float *image /* [3,H,W] */, const float *depth /* [H,W] */,
+                       const int32_t *hit_depth /* [H,W] */, const float *gt_color /* [H,W,3] */,
+                       const float *gt_depth /* [H,W] */, const uint8_t *render_mask /* [H,W] or NULL */,
+                       float color_weight, float depth_weight, float depth_err_thres,
+                       float *dL_dimage /* [3,H,W] */, float *dL_ddepth /* [H,W] */, float *loss_out,
+                       int32_t *counts_out, void *workspace, void *stream);
+
+/* Fused multi-tensor Adam.  Replaces torch.optim.Adam(l, lr=0.0, eps=1e-15).step() over the parameter groups
+ * of GaussianPointCloud.parametrize (SLAM/gaussian_pointcloud.py:331-378; mapper.py:548,906) with one
+ * launch, plus the confidence bump of mapper.py:909-910 when `confidence`/`conf_tensor` are given.
+ * Semantics: torch Adam, amsgrad=False, weight_decay=0, maximize=False. */
+typedef struct dqo_adam_tensor {
+    float *param;
+    const float *grad;
+    float *exp_avg;
+    float *exp_avg_sq;
+    int64_t numel;
+    float lr;
+    int32_t row_width; /* trailing elements per Gaussian (for the confidence bump), 0 = n/a */
+} dqo_adam_tensor;
+#define DQO_ADAM_MAX_TENSORS 16
+int dqo_adam_step(const dqo_adam_tensor *tensors /* host array */, int32_t n_tensors, int32_t step, float beta1,
+                  float beta2, float eps, float *confidence /* [P] or NULL */, int32_t conf_tensor, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dual quadrics (SLAM/multiprocess/quadrics.py).  Batched over objects.
+ *   dqo_quadric_init   : Object.__init__ single-view construction (quadrics.py:451-487)
+ *   dqo_quadric_project: Ellipsoid.project + Ellipse.ComputeBbox (quadrics.py:388-425,148-248) in fp64
+ *   dqo_quadric_refine : Object_Optimize_only's 20-iteration IoU-Adam loop (quadrics.py:2234-2298) with
+ *                        Ellipsoid_tensor.forward / Ellipse_tensor (quadrics.py:2018-2225) in fp32,
+ *                        analytic gradients; the per-iteration view choice is supplied by the caller.
+ * ---------------------------------------------------------------------------------------------- */
+int dqo_quadric_init(int32_t n, const double *bboxes /* [n,4] */, const double *depth_stats /* [n,2] avg,diff */,
+                     const double *K /* [3,3] */, const double *Rts /* [n,3,4] */, double *axes /* [n,3] */,
+                     double *R /* [n,3,3] */, double *center /* [n,3] */, void *stream);
+int dqo_quadric_project(int32_t n, const double *axes, const double *R, const double *center,
+                        const double *P /* [n,3,4] */, double *bbox /* [n,4] */, double *ellipse /* [n,5] ax0,ax1,angle,cx,cy */,
+                        void *stream);
+int dqo_quadric_refine(int32_t n, int32_t iters, int32_t max_views, const int32_t *n_views /* [n] */,
+                       const float *obs_bboxes /* [n,max_views,4] */, const float *Ps /* [n,max_views,3,4] */,
+                       const int32_t *view_choice /* [n,iters] */, float lr_axes, float lr_center, float lr_R,
+                       float *axes /* [n,3] in/out */, float *R /* [n,9] in/out */, float *center /* [n,3] in/out */,
+                       float *last_loss /* [n] or NULL */, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DQO_B200_H_ */
