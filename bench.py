@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the DQO-MAP hot path on B200 (contract: one JSON line on rank 0).
+
+  python bench.py --gpus N --steps K --warmup W            this repository's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...   the unmodified reference CUDA extension (oracle/_ref) on the
+                                                            same workload; falls back to the CPU oracle port if the
+                                                            reference .so did not travel to the box
+
+metric  : fwd+bwd render iterations/s at BASELINE config 2 (1M Gaussians, SH degree 3, 1200x680), whole job.
+value   : device-timed (CUDA events) rate of rasterizer forward+backward with every input resident in HBM.
+e2e     : the same iteration inside the mapping step a user runs (public API): per step the keyframe (colour, depth,
+          render mask) is copied from pinned host memory, activations -> rasterize -> masked L1 loss -> backward ->
+          Adam run, and the loss scalar is read back to the host.
+N > 1   : one process per GPU; the objects are sharded (each rank maps its own shard of the scene, no gradient
+          exchange) and the per-object table is all-gathered over NCCL every step: weak scaling.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+LRS = dict(xyz=1e-3, f_dc=5e-4, f_rest=2.5e-5, opacity=0.0, scaling=4e-3, rotation=1e-3)  # configs/replica_base.yaml:17-23
+METRIC = "fwd+bwd render iters/s"
+UNIT = "iters/s"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def inverse_sigmoid(x):
+    return torch.log(x / (1 - x))
+
+
+def build_workload(cfg, dev, rank):
+    import refharness as rh
+    from dqo_map_b200 import synthetic
+    inp = rh.make_inputs(cfg, dev, seed=2024 + rank)
+    cam = inp["cam"]
+    rd = synthetic.RENDER_DEFAULTS
+
+    def settings(Sett):
+        return Sett(image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                    bg=inp["bg"], scale_modifier=1.0, viewmatrix=cam.world_view_transform,
+                    projmatrix=cam.full_proj_transform, sh_degree=inp["sh_degree"], campos=cam.camera_center,
+                    opaque_threshold=rd["opaque_threshold"], normal_threshold=rd["normal_threshold"],
+                    depth_threshold=rd["depth_threshold"], prefiltered=False, debug=False, cx=cam.cx, cy=cam.cy)
+
+    return inp, cam, settings
+
+
+def make_keyframe(inp, cam, settings, rasterizer_mod):
+    """GT keyframe = render of a perturbed copy (positions +N(0,5mm), colours +N(0,0.05)), SURVEY.md §8d."""
+    P = inp["xyz"].shape[0]
+    g = torch.Generator(device="cpu").manual_seed(99)
+    xyz = inp["xyz"] + (0.005 * torch.randn(P, 3, generator=g)).to(inp["xyz"].device)
+    shs = inp["shs"].clone()
+    shs[:, 0] += (0.05 / 0.28209479177387814 * torch.randn(P, 3, generator=g)).to(shs.device)
+    with torch.no_grad():
+        out = rasterizer_mod.GaussianRasterizer(settings(rasterizer_mod.GaussianRasterizationSettings))(
+            means3D=xyz, opacities=inp["opacity"], shs=shs, scales=inp["scales"], rotations=inp["rotations"],
+            tile_mask=inp["tile_mask"])
+    gt_color = out[0].permute(1, 2, 0).contiguous()
+    gt_depth = out[1].permute(1, 2, 0).contiguous()
+    mask = (out[6][0] != 1).contiguous()
+    return gt_color, gt_depth, mask
+
+
+def raw_params(inp):
+    return dict(xyz=inp["xyz"].clone(), f_dc=inp["shs"][:, :1].clone(), f_rest=inp["shs"][:, 1:].clone(),
+                opacity=inverse_sigmoid(inp["opacity"].clamp(0.01, 0.995)), scaling=torch.log(inp["scales"]),
+                rotation=inp["rotations"].clone())
+
+
+def torch_mapping_iteration(params, opt, conf, Rast, rs, tile_mask, gt_color, gt_depth, render_mask):
+    """The reference's iteration with stock ops: SLAM/multiprocess/mapper.py:578-599 + loss_update :799-928."""
+    out = Rast(rs)(means3D=params["xyz"], opacities=torch.sigmoid(params["opacity"]),
+                   shs=torch.cat((params["f_dc"], params["f_rest"]), dim=1), scales=torch.exp(params["scaling"]),
+                   rotations=torch.nn.functional.normalize(params["rotation"]), tile_mask=tile_mask)
+    image, depth, depth_index = out[0].permute(1, 2, 0), out[1].permute(1, 2, 0), out[3].permute(1, 2, 0)
+    color_loss = torch.abs(image[render_mask] - gt_color[render_mask]).mean()
+    depth_error = depth - gt_depth
+    valid = (depth_index != -1).squeeze() & (gt_depth > 0).squeeze() & (depth_error < 0.1).squeeze() & render_mask
+    depth_loss = torch.abs(depth_error[valid]).mean()
+    total = 1.0 * depth_loss + 0.8 * color_loss
+    total.backward()
+    opt.step()
+    grad_mask = (params["f_dc"].grad.abs() != 0).any(dim=-1)
+    conf[grad_mask.view(-1)] += 1
+    opt.zero_grad(set_to_none=True)
+    return total
+
+
+def timed(fn, steps, warmup, dist_on):
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def cpu_port_rate(cfg, iters=2):
+    """CPU oracle port (all host threads) on the same workload: fwd+bwd iterations/s."""
+    import refharness as rh
+    from dqo_map_b200 import synthetic
+    from oracle import oracle
+    inp = rh.make_inputs(cfg, torch.device("cpu"))
+    cam = inp["cam"]
+    n = lambda t: t.numpy()
+    sc = oracle.Scene(n(inp["xyz"]), n(inp["scales"]), n(inp["rotations"]), n(inp["opacity"]), n(cam.world_view_transform),
+                      n(cam.full_proj_transform), n(cam.camera_center), cam.image_width, cam.image_height, cam.tanfovx,
+                      cam.tanfovy, cam.cx, cam.cy, n(inp["bg"]), n(inp["tile_mask"]), shs=n(inp["shs"]),
+                      sh_degree=inp["sh_degree"], normal_threshold=synthetic.RENDER_DEFAULTS["normal_threshold"])
+    cores = os.cpu_count() or 1
+    oracle.set_threads(cores)
+    gc, gd = rh.make_pixel_grads(cam.image_height, cam.image_width, "cpu")
+    t0 = time.time()
+    for _ in range(iters):
+        pre, bn, img = oracle.forward(sc)
+        oracle.backward(sc, pre, bn, img, gc.numpy(), gd.numpy())
+    dt = time.time() - t0
+    return iters / dt, cores, "%d full fwd+bwd iterations of the %s workload (%d Gaussians, %dx%d), oracle C port" % (
+        iters, cfg, sc.P, cam.image_width, cam.image_height)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import refharness as rh
+    ref_ok = rh.reference_available()
+    if a.impl == "reference" and not ref_ok:
+        # no reference .so on this box: time the CPU oracle port instead (rank 0 only)
+        if rank == 0:
+            rate, cores, sample = cpu_port_rate(a.config, iters=max(1, min(a.steps, 3)))
+            print(json.dumps({
+                "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": 1000.0 / rate, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": a.config},
+                "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from dqo_map_b200 import _lib, mapping, rasterizer, sharding
+    inp, cam, settings = build_workload(a.config, dev, rank)
+    P, H, W = inp["xyz"].shape[0], cam.image_height, cam.image_width
+    M = inp["shs"].shape[1]
+    gc, gd = rh.make_pixel_grads(H, W, dev)
+    gt_color, gt_depth, render_mask = make_keyframe(inp, cam, settings, rasterizer)
+    host_kf = [t.cpu().pin_memory() for t in (gt_color, gt_depth, render_mask)]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_kf)
+    dev_kf = [torch.empty_like(t, device=dev) for t in host_kf]
+    obj_table = torch.zeros((1, 12), device=dev)
+    obj_table[0, 0] = rank
+
+    sampler = ClockSampler(local_rank)
+    roofline, stage_ms, stats = None, None, {}
+    launches0 = 0
+
+    if a.impl == "ours":
+        L = _lib.lib()
+        rs = settings(rasterizer.GaussianRasterizationSettings)
+        # capacity from one synchronous probe; the timed loop never synchronises
+        probe = rasterizer.rasterize_gaussians(*rh.raster_args(inp))
+        R = probe[0]
+        pipe = rasterizer.RasterPipeline(P, M, W, H, int(R * 1.05) + 4096, dev)
+        del probe
+
+        def kernel_step():
+            pipe.forward(rs, inp["xyz"], inp["opacity"], inp["scales"], inp["rotations"], inp["tile_mask"], shs=inp["shs"])
+            pipe.backward(gc, gd)
+            if dist_on:
+                sharding.gather_object_table(obj_table)
+
+        params = {k: torch.nn.Parameter(v) for k, v in raw_params(inp).items()}
+        conf = torch.zeros(P, 1, device=dev)
+        step_obj = mapping.MappingStep(params, LRS, lambda _f: rs, 0.8, 1.0, 0.1, confidence=conf, optimizer="fused")
+
+        def e2e_step():
+            for d, h in zip(dev_kf, host_kf):
+                d.copy_(h, non_blocking=True)
+            total, _, _ = step_obj(None, inp["tile_mask"], dev_kf[0], dev_kf[1], dev_kf[2])
+            if dist_on:
+                sharding.gather_object_table(obj_table)
+            return float(total)  # D2H read of the loss
+
+        launch_fn = L.dqo_launch_count
+    else:
+        rast_pkg, C, _, _ = rh.load_reference()
+        rs = settings(rast_pkg.GaussianRasterizationSettings)
+        args = rh.raster_args(inp)
+
+        def kernel_step():
+            fwd = C.rasterize_gaussians(*args)
+            C.rasterize_gaussians_backward(*rh.backward_args(inp, fwd, gc, gd))
+            if dist_on:
+                sharding.gather_object_table(obj_table)
+
+        params = {k: torch.nn.Parameter(v) for k, v in raw_params(inp).items()}
+        conf = torch.zeros(P, 1, device=dev)
+        groups = [{"params": [params[k]], "lr": LRS[k], "name": k} for k in ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")]
+        opt = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+
+        def e2e_step():
+            for d, h in zip(dev_kf, host_kf):
+                d.copy_(h, non_blocking=True)
+            total = torch_mapping_iteration(params, opt, conf, rast_pkg.GaussianRasterizer, rs, inp["tile_mask"], dev_kf[0],
+                                            dev_kf[1], dev_kf[2])
+            if dist_on:
+                sharding.gather_object_table(obj_table)
+            return float(total)
+
+        launch_fn = lambda: 0
+
+    sampler.start()
+    launches0 = launch_fn()
+    ms = timed(kernel_step, a.steps, a.warmup, dist_on)
+    launches = launch_fn() - launches0 - 0
+    ms_e2e = timed(e2e_step, a.steps, a.warmup, dist_on)
+    sampler.stop_flag = True
+    value = world * a.steps / (ms / 1000.0)
+    e2e_value = world * a.steps / (ms_e2e / 1000.0)
+
+    if a.impl == "ours":
+        # per-stage CUDA-event timing on the launching stream (separate short run, not part of `value`)
+        L.dqo_profile_enable(1)
+        acc = np.zeros(16)
+        reps = 5
+        for _ in range(reps):
+            pipe.forward(rs, inp["xyz"], inp["opacity"], inp["scales"], inp["rotations"], inp["tile_mask"], shs=inp["shs"])
+            pipe.backward(gc, gd)
+            buf = (ctypes.c_float * 16)()
+            L.dqo_profile_read(buf, 16)
+            acc += np.array(list(buf))
+        L.dqo_profile_enable(0)
+        acc /= reps
+        names = ["", "preprocess", "depth_sort", "scan", "duplicate", "tile_sort", "ranges", "compact", "render_fwd", "",
+                 "render_bwd", "gaussian_bwd"]
+        stage_ms = {n: float(acc[i]) for i, n in enumerate(names) if n}
+        host = pipe.check()
+        R, V = host[_lib.ST_NUM_RENDERED], host[_lib.ST_NUM_VISIBLE]
+        st = type("S", (), {})()
+        st.settings, st.geom, st.binning, st.image, st.status, st.capacity = pipe.settings, pipe.geom, pipe.binning, pipe.image, pipe.status, pipe.capacity
+        ex = rh.export_ours(st, P, W, H)
+        th, tw = (H + 15) // 16, (W + 15) // 16
+        nc = np.zeros((th * 16, tw * 16), np.int64)
+        nc[:H, :W] = ex["n_contrib"]
+        max_c = nc.reshape(th, 16, tw, 16).max(axis=(1, 3)).reshape(-1)
+        rg = ex["ranges"].astype(np.int64)
+        length = rg[:, 1] - rg[:, 0]
+        Rt = int(np.minimum(length, ((max_c + 255) // 256) * 256).sum())
+        Npx = int((length > 0).sum()) * 256
+        bit = max(1, int(th * tw).bit_length())
+        D_t = (bit + 7) // 8
+        # algorithmic (compulsory) bytes per launch, byte model of SURVEY.md §8d adapted to this design
+        alg = {
+            "preprocess": P * (44 + 12 * M) + V * 64 + P * 17,
+            "depth_sort": P * 8 * (1 + 2 * 4),
+            "scan": P * 12,
+            "duplicate": P * 16 + R * 8,
+            "tile_sort": R * 8 * (1 + 2 * D_t),
+            "ranges": R * 4 + th * tw * 8,
+            "render_fwd": 52 * Rt + (40 + 32) * Npx,
+            "render_bwd": 52 * Rt + 72 * Npx + 36 * R,
+            "gaussian_bwd": V * (100 + 12 * M) + P * (76 + 12 * M),
+        }
+        dom = max((k for k in alg), key=lambda k: stage_ms.get(k, 0.0))
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = alg[dom] / (stage_ms[dom] / 1000.0) / 1e9 if stage_ms[dom] > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                    "algorithmic_bytes": int(alg[dom]), "kernel_ms": stage_ms[dom],
+                    "per_stage": {k: {"ms": stage_ms.get(k, 0.0), "alg_bytes": int(v),
+                                      "gbps": (v / (stage_ms[k] / 1000.0) / 1e9) if stage_ms.get(k, 0) > 0 else None}
+                                  for k, v in alg.items()}}
+        stats = {"P": P, "V": V, "R": R, "Rt": Rt, "Npx": Npx, "tile_num": host[_lib.ST_TILE_NUM]}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: %d Gaussians, SH degree %d, %dx%d RGB-D keyframe, dense tile mask, per-rank shard" % (
+                a.config, P, inp["sh_degree"], W, H), "l2_policy": "working set (>=600 MB per iteration) exceeds the 126 MB L2",
+                "parallelism": "object-sharded x%d" % world, **stats},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": 4,
+                    "what": "mapping iteration through the public API: H2D keyframe, activations, fwd, masked L1, bwd, Adam, D2H loss"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+        }
+        if a.impl == "reference":
+            out["impl"] = "reference"
+            out["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                                   "sample": "the reference's path is CUDA-only: unmodified extension (oracle/_ref) timed on the same B200"}
+        else:
+            out["roofline"] = roofline
+            out["stage_ms"] = stage_ms
+            if world == 1 and not a.no_cpu_baseline:
+                rate, cores, sample = cpu_port_rate(a.config, iters=2)
+                out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(out))
+    if dist_on:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

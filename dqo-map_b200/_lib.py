@@ -37,6 +37,9 @@ class AdamTensor(C.Structure):
 PROTOTYPES = {
     "dqo_abi_version": (C.c_int, []),
     "dqo_last_error": (C.c_char_p, []),
+    "dqo_launch_count": (C.c_longlong, []),
+    "dqo_profile_enable": (None, [C.c_int]),
+    "dqo_profile_read": (C.c_int, [C.POINTER(C.c_float), C.c_int]),
     "dqo_rast_geom_bytes": (C.c_size_t, [C.c_int32]),
     "dqo_rast_binning_bytes": (C.c_size_t, [C.c_int64]),
     "dqo_rast_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),

@@ -11,7 +11,42 @@ void set_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static long long g_launches = 0;
+void note_launch(int n) { g_launches += n; }
+
+static int g_profile = 0;
+static cudaEvent_t g_ev[ST_COUNT];
+static bool g_ev_made = false, g_ev_set[ST_COUNT];
+void stage_mark(cudaStream_t stream, int stage) {
+    if (!g_profile) return;
+    if (!g_ev_made) {
+        for (int i = 0; i < ST_COUNT; i++) cudaEventCreate(&g_ev[i]);
+        g_ev_made = true;
+    }
+    cudaEventRecord(g_ev[stage], stream);
+    g_ev_set[stage] = true;
+}
 } // namespace dqo
+
+extern "C" long long dqo_launch_count(void) { return dqo::g_launches; }
+extern "C" void dqo_profile_enable(int on) {
+    dqo::g_profile = on;
+    for (int i = 0; i < dqo::ST_COUNT; i++) dqo::g_ev_set[i] = false;
+}
+// ms_out[i] = time between stage mark i-1 and i (0 for the two BEGIN marks / missing marks); returns ST_COUNT
+extern "C" int dqo_profile_read(float *ms_out, int n) {
+    using namespace dqo;
+    for (int i = 0; i < n; i++) ms_out[i] = 0.f;
+    if (!g_ev_made) return ST_COUNT;
+    for (int i = 1; i < ST_COUNT && i < n; i++) {
+        if (i == ST_BEGIN_BWD || !g_ev_set[i] || !g_ev_set[i - 1]) continue;
+        cudaEventSynchronize(g_ev[i]);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_ev[i - 1], g_ev[i]) == cudaSuccess) ms_out[i] = ms;
+    }
+    return ST_COUNT;
+}
 
 extern "C" int dqo_abi_version(void) { return DQO_ABI_VERSION; }
 extern "C" const char *dqo_last_error(void) { return dqo::g_err; }

@@ -18,6 +18,14 @@
 namespace dqo {
 
 void set_error(const char *fmt, ...);
+void note_launch(int n = 1);                      // counts this library's own kernel launches (dqo_launch_count)
+void stage_mark(cudaStream_t stream, int stage);  // records a CUDA event when stage profiling is enabled
+
+// stage ids of dqo_profile_read()
+enum {
+    ST_BEGIN_FWD = 0, ST_PREPROCESS, ST_DEPTH_SORT, ST_SCAN, ST_DUPLICATE, ST_TILE_SORT, ST_RANGES, ST_COMPACT,
+    ST_RENDER_FWD, ST_BEGIN_BWD, ST_RENDER_BWD, ST_GAUSS_BWD, ST_COUNT
+};
 
 #define DQO_CUDA_CHECK(expr)                                                                  \
     do {                                                                                      \
@@ -31,6 +39,7 @@ void set_error(const char *fmt, ...);
 #define DQO_LAUNCH_CHECK(name, debug, stream)                                                 \
     do {                                                                                      \
         cudaError_t _e = cudaGetLastError();                                                  \
+        dqo::note_launch();                                                                   \
         if (_e == cudaSuccess && (debug)) _e = cudaStreamSynchronize(stream);                 \
         if (_e != cudaSuccess) {                                                              \
             dqo::set_error("kernel %s failed: %s", name, cudaGetErrorString(_e));             \

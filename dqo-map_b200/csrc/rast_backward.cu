@@ -577,6 +577,7 @@ extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *backgr
     const char *bin = (const char *)binning_buffer;
     const char *img = (const char *)image_buffer;
     float *gacc = (float *)(geom + GL.gacc);
+    stage_mark(stream, ST_BEGIN_BWD);
     DQO_CUDA_CHECK(cudaMemsetAsync(gacc, 0, (size_t)P * DQO_GACC_FLOATS * sizeof(float), stream));
 
     const float focal_y = s->H / (2.0f * s->tanfovy);
@@ -596,6 +597,7 @@ extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *backgr
     ra.dL_dpix = dL_dout_color; ra.dL_ddepth = dL_dout_depth; ra.hit_image = hit_image; ra.gacc = gacc;
     render_backward_kernel<<<IL.T, 256, 0, stream>>>(ra);
     DQO_LAUNCH_CHECK("render backward", s->debug, stream);
+    stage_mark(stream, ST_RENDER_BWD);
 
     GaussBwdArgs ga;
     ga.P = P; ga.D = s->D; ga.M = s->M;
@@ -610,5 +612,6 @@ extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *backgr
     ga.dL_dscales = dL_dscales; ga.dL_drot = dL_drotations;
     gaussian_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(ga);
     DQO_LAUNCH_CHECK("gaussian backward", s->debug, stream);
+    stage_mark(stream, ST_GAUSS_BWD);
     return DQO_OK;
 }

@@ -717,6 +717,7 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
         set_error("image too large");
         return DQO_ERR_INVALID_ARG;
     }
+    stage_mark(stream, ST_BEGIN_FWD);
     DQO_CUDA_CHECK(cudaMemsetAsync(ranges, 0, (size_t)T * sizeof(uint2), stream));
     DQO_CUDA_CHECK(cudaMemsetAsync(status, 0, DQO_ST_WORDS * sizeof(int), stream));
 
@@ -751,6 +752,7 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
         rec = pa.rec;
         preprocess_kernel<<<(P + 255) / 256, 256, 0, stream>>>(pa);
         DQO_LAUNCH_CHECK("preprocess", debug, stream);
+    stage_mark(stream, ST_PREPROCESS);
 
         // (depth, id) order of the Gaussians: stable LSD sort on the depth bits
         uint32_t *order = (uint32_t *)(geom + GL.order);
@@ -759,11 +761,13 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
                                                        (uint32_t *)(geom + GL.depth_key2), (const uint32_t *)pa.ids,
                                                        order, P, 0, 32, stream));
         DQO_LAUNCH_CHECK("depth sort", debug, stream);
+    stage_mark(stream, ST_DEPTH_SORT);
         uint32_t *offsets = (uint32_t *)(geom + GL.offsets);
         TilesInRankOrder it((const uint32_t *)order, GatherTiles{pa.tiles});
         cub_bytes = GL.cub_bytes;
         DQO_CUDA_CHECK(cub::DeviceScan::InclusiveSum(geom + GL.cub, cub_bytes, it, offsets, P, stream));
         DQO_LAUNCH_CHECK("scan", debug, stream);
+    stage_mark(stream, ST_SCAN);
 
         uint32_t *keys_in = (uint32_t *)(bin + BL.keys_in), *keys_out = (uint32_t *)(bin + BL.keys_out);
         uint32_t *vals_in = (uint32_t *)(bin + BL.vals_in), *vals_out = (uint32_t *)(bin + BL.vals_out);
@@ -771,18 +775,22 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
         duplicate_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, stream>>>(
             P, capacity, order, pa.tiles, offsets, pa.rect, tile_mask, IL.tiles_x, keys_in, vals_in, status);
         DQO_LAUNCH_CHECK("duplicate", debug, stream);
+    stage_mark(stream, ST_DUPLICATE);
         const int bit = (int)higher_msb((uint32_t)T);
         cub_bytes = BL.cub_bytes;
         DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(bin + BL.cub, cub_bytes, (const uint32_t *)keys_in, keys_out,
                                                        (const uint32_t *)vals_in, vals_out, (int)capacity, 0, bit,
                                                        stream));
         DQO_LAUNCH_CHECK("tile sort", debug, stream);
+    stage_mark(stream, ST_TILE_SORT);
         tile_ranges_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(capacity, keys_out, status, ranges);
         DQO_LAUNCH_CHECK("tile ranges", debug, stream);
+    stage_mark(stream, ST_RANGES);
         point_list = vals_out;
     }
     compact_tiles_kernel<<<1, 1024, 0, stream>>>(T, ranges, tile_indices, status);
     DQO_LAUNCH_CHECK("compact tiles", debug, stream);
+    stage_mark(stream, ST_COMPACT);
 
     RenderArgs ra;
     ra.W = s->W; ra.H = s->H; ra.grid_x = IL.tiles_x;
@@ -800,6 +808,7 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
     ra.out_hit_color = out_hit_color; ra.n_touched = s->need_n_touched ? n_touched : nullptr;
     render_forward_kernel<<<T, 256, 0, stream>>>(ra);
     DQO_LAUNCH_CHECK("render forward", debug, stream);
+    stage_mark(stream, ST_RENDER_FWD);
     return DQO_OK;
 }
 

@@ -1,0 +1,5 @@
+import os
+import sys
+
+sys.path.insert(0, os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")))
+import _bootstrap  # noqa: F401,E402

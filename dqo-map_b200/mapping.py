@@ -1,0 +1,158 @@
+"""Mapping-step operators: masked L1 colour/depth loss, fused multi-tensor Adam, and the iteration that
+`Mapping.local_optimize` / `loss_update` run (reference SLAM/multiprocess/mapper.py:531-605, 799-928).
+
+The reference has no native boundary here (inline PyTorch); these are opt-in replacements with the same
+semantics: `FusedAdam` accepts the param-group dicts of `GaussianPointCloud.parametrize`
+(SLAM/gaussian_pointcloud.py:331-378) and behaves like `torch.optim.Adam(l, lr=0.0, eps=1e-15)`.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import AdamTensor, check, lib, ptr
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _MaskedL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, depth, hit_depth, gt_color, gt_depth, render_mask, color_weight, depth_weight,
+                depth_err_thres):
+        L = lib()
+        dev = image.device
+        H, W = image.shape[1], image.shape[2]
+        image_c, depth_c = image.contiguous(), depth.contiguous()
+        mask_c = None
+        if render_mask is not None:
+            mask_c = render_mask.contiguous()
+            if mask_c.dtype == torch.bool:
+                mask_c = mask_c.view(torch.uint8)
+            elif mask_c.dtype != torch.uint8:
+                mask_c = (mask_c != 0).view(torch.uint8)
+        d_img = torch.empty_like(image_c)
+        d_depth = torch.empty_like(depth_c)
+        out = torch.empty((4,), dtype=torch.float32, device=dev)
+        counts = torch.empty((2,), dtype=torch.int32, device=dev)
+        ws = torch.empty((L.dqo_loss_workspace_bytes(W, H),), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(L.dqo_masked_l1_loss(W, H, ptr(image_c), ptr(depth_c), ptr(hit_depth.contiguous()),
+                                       ptr(gt_color.contiguous()), ptr(gt_depth.contiguous()), ptr(mask_c),
+                                       float(color_weight), float(depth_weight), float(depth_err_thres), ptr(d_img),
+                                       ptr(d_depth), ptr(out), ptr(counts), ptr(ws), _stream()), "dqo_masked_l1_loss")
+        ctx.save_for_backward(d_img, d_depth)
+        ctx.mark_non_differentiable(counts)
+        return out[0], out[1], out[2], counts
+
+    @staticmethod
+    def backward(ctx, g_total, g_color, g_depth, _):
+        d_img, d_depth = ctx.saved_tensors
+        # the component losses are reported only (detached), like the `.item()` reports of the reference
+        return d_img * g_total, d_depth * g_total, None, None, None, None, None, None, None
+
+
+def masked_l1_loss(image, depth, hit_depth, gt_color, gt_depth, render_mask=None, color_weight=0.8, depth_weight=1.0,
+                   depth_err_thres=0.1):
+    """total = depth_weight * mean|d - gt_d|[valid] + color_weight * mean|img - gt|[mask]  (mapper.py:847-875).
+
+    image [3,H,W], depth [1,H,W], hit_depth [1,H,W] int32 (the rasterizer's depth index map), gt_color [H,W,3],
+    gt_depth [H,W,1] or [H,W], render_mask [H,W] bool or None.  Returns (total, colour, depth, counts[2])."""
+    return _MaskedL1.apply(image, depth, hit_depth, gt_color, gt_depth, render_mask, color_weight, depth_weight,
+                           depth_err_thres)
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (amsgrad=False, weight_decay=0, maximize=False) in ONE launch over all groups."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, confidence=None, confidence_param=None):
+        defaults = dict(lr=lr, betas=betas, eps=eps)
+        super().__init__(params, defaults)
+        self.confidence = confidence          # [P] or [P,1] float tensor bumped where grad(confidence_param) != 0
+        self.confidence_param = confidence_param
+        self._step = 0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        arr = (AdamTensor * _lib.ADAM_MAX_TENSORS)()
+        n, conf_idx, keep = 0, -1, []
+        betas, eps = None, None
+        for group in self.param_groups:
+            if betas is None:
+                betas, eps = group["betas"], group["eps"]
+            elif betas != group["betas"] or eps != group["eps"]:
+                raise ValueError("FusedAdam requires identical betas/eps across param groups")
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if n >= _lib.ADAM_MAX_TENSORS:
+                    raise ValueError("FusedAdam supports at most %d tensors" % _lib.ADAM_MAX_TENSORS)
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise ValueError("FusedAdam expects contiguous float32 CUDA parameters")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                g = p.grad.contiguous()
+                keep.append(g)
+                width = int(p.numel() // p.shape[0]) if p.dim() > 0 and p.shape[0] > 0 else 0
+                arr[n] = AdamTensor(ptr(p), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(),
+                                    float(group["lr"]), width)
+                if self.confidence_param is not None and p is self.confidence_param:
+                    conf_idx = n
+                n += 1
+        if n == 0:
+            return loss
+        self._step += 1
+        dev = keep[0].device
+        conf = self.confidence if conf_idx >= 0 else None
+        with torch.cuda.device(dev):
+            check(lib().dqo_adam_step(arr, n, self._step, float(betas[0]), float(betas[1]), float(eps), ptr(conf),
+                                      conf_idx, _stream()), "dqo_adam_step")
+        return loss
+
+
+class MappingStep:
+    """One iteration of the reference's mapping hot loop (mapper.py:568-599 + loss_update :799-928) with the
+    B200 operators plugged in: activations (torch) -> rasterize (C-ABI) -> masked L1 loss (C-ABI) -> backward
+    (C-ABI + torch activations) -> fused Adam (C-ABI) with the confidence bump."""
+
+    def __init__(self, params, lrs, settings_fn, color_weight=0.8, depth_weight=1.0, depth_err_thres=0.1,
+                 confidence=None, optimizer="fused"):
+        # params: dict with raw leaf tensors xyz[P,3], f_dc[P,1,3], f_rest[P,M-1,3], opacity[P,1], scaling[P,3], rotation[P,4]
+        self.p = params
+        groups = [{"params": [params[k]], "lr": lrs[k], "name": k}
+                  for k in ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")]
+        if optimizer == "fused":
+            self.opt = FusedAdam(groups, lr=0.0, eps=1e-15, confidence=confidence, confidence_param=params["f_dc"])
+        else:
+            self.opt = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+        self.confidence = confidence
+        self.fused = optimizer == "fused"
+        self.settings_fn = settings_fn
+        self.cw, self.dw, self.thr = color_weight, depth_weight, depth_err_thres
+
+    def activated(self):
+        p = self.p
+        return dict(xyz=p["xyz"], opacity=torch.sigmoid(p["opacity"]), scales=torch.exp(p["scaling"]),
+                    rotations=torch.nn.functional.normalize(p["rotation"]),
+                    shs=torch.cat((p["f_dc"], p["f_rest"]), dim=1))
+
+    def __call__(self, frame, tile_mask, gt_color, gt_depth, render_mask):
+        from .rasterizer import GaussianRasterizer
+        a = self.activated()
+        rast = GaussianRasterizer(self.settings_fn(frame))
+        color, depth, hit_color, hit_depth, hcw, hdw, T_map, n_touched, radii = rast(
+            means3D=a["xyz"], opacities=a["opacity"], shs=a["shs"], scales=a["scales"], rotations=a["rotations"],
+            tile_mask=tile_mask)
+        total, lc, ld, counts = masked_l1_loss(color, depth, hit_depth, gt_color, gt_depth, render_mask, self.cw,
+                                               self.dw, self.thr)
+        total.backward()
+        self.opt.step()
+        if not self.fused and self.confidence is not None:
+            grad_mask = (self.p["f_dc"].grad.abs() != 0).any(dim=-1)
+            self.confidence[grad_mask.view(-1)] += 1
+        self.opt.zero_grad(set_to_none=True)
+        return total.detach(), lc.detach(), ld.detach()

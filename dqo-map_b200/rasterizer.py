@@ -174,6 +174,66 @@ def _backward_impl(st, background, means3D, radii, colors, scales, rotations, co
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 
 
+class RasterPipeline:
+    """Pre-allocated, synchronisation-free forward+backward for hot loops (bench.py, fused mapping step).
+
+    All buffers (outputs, workspaces, gradients) are allocated once for a fixed (P, M, W, H, capacity); `forward()` and
+    `backward()` only enqueue kernels.  `check()` reads the device status words (one host sync) and raises if the
+    instance capacity was exceeded — call it whenever convenient, e.g. together with the loss read-back."""
+
+    def __init__(self, P, M, W, H, capacity, device):
+        L = lib()
+        dev = torch.device(device)
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        self.P, self.M, self.W, self.H, self.capacity, self.dev = P, M, W, H, int(capacity), dev
+        tiles = ((H + 15) // 16) * ((W + 15) // 16)
+        self.color, self.depth = torch.empty((3, H, W), **f32), torch.empty((1, H, W), **f32)
+        self.hit_depth, self.hit_color = torch.empty((1, H, W), **i32), torch.empty((1, H, W), **i32)
+        self.hit_cw, self.hit_dw, self.T = (torch.empty((1, H, W), **f32) for _ in range(3))
+        self.radii, self.n_touched = torch.empty((P,), **i32), torch.empty((P,), **i32)
+        self.tile_indices, self.status = torch.empty((tiles,), **i32), torch.zeros((_lib.ST_WORDS,), **i32)
+        self.geom = torch.empty((L.dqo_rast_geom_bytes(P),), **u8)
+        self.binning = torch.empty((L.dqo_rast_binning_bytes(self.capacity),), **u8)
+        self.image = torch.empty((L.dqo_rast_image_bytes(W, H),), **u8)
+        self.g_means2D, self.g_conic = torch.empty((P, 3), **f32), torch.empty((P, 4), **f32)
+        self.g_opacity, self.g_colors = torch.empty((P, 1), **f32), torch.empty((P, 3), **f32)
+        self.g_means3D, self.g_cov3D = torch.empty((P, 3), **f32), torch.empty((P, 6), **f32)
+        self.g_sh = torch.empty((P, max(M, 0), 3), **f32)
+        self.g_scales, self.g_rot = torch.empty((P, 3), **f32), torch.empty((P, 4), **f32)
+        self.settings = None
+
+    def forward(self, rs, means3D, opacities, scales, rotations, tile_mask, shs=None, colors_precomp=None,
+                need_n_touched=True):
+        self.settings = _make_settings(self.P, int(rs.sh_degree), self.M, self.W, self.H, rs.tanfovx, rs.tanfovy, rs.cx,
+                                       rs.cy, rs.scale_modifier, rs.color_sigma, rs.opaque_threshold, rs.depth_threshold,
+                                       rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, need_n_touched)
+        self._in = (rs, means3D, shs, colors_precomp, scales, rotations)
+        check(lib().dqo_rast_forward(
+            self.settings, ptr(rs.bg), ptr(means3D), ptr(shs), ptr(colors_precomp), ptr(opacities), ptr(scales),
+            ptr(rotations), None, ptr(rs.viewmatrix), ptr(rs.projmatrix), ptr(rs.campos), ptr(tile_mask), ptr(self.geom),
+            ptr(self.binning), self.capacity, ptr(self.image), ptr(self.tile_indices), ptr(self.color), ptr(self.depth),
+            ptr(self.hit_depth), ptr(self.hit_color), ptr(self.hit_cw), ptr(self.hit_dw), ptr(self.T), ptr(self.radii),
+            ptr(self.n_touched), ptr(self.status), _stream()), "dqo_rast_forward")
+
+    def backward(self, dL_dcolor, dL_ddepth):
+        rs, means3D, shs, colors_precomp, scales, rotations = self._in
+        check(lib().dqo_rast_backward(
+            self.settings, ptr(rs.bg), ptr(means3D), ptr(shs), ptr(colors_precomp), ptr(scales), ptr(rotations), None,
+            ptr(rs.viewmatrix), ptr(rs.projmatrix), ptr(rs.campos), ptr(self.radii), ptr(self.geom), ptr(self.binning),
+            self.capacity, ptr(self.image), ptr(self.status), ptr(dL_dcolor), ptr(dL_ddepth), ptr(self.hit_depth),
+            ptr(self.g_means2D), ptr(self.g_conic), ptr(self.g_opacity), ptr(self.g_colors), ptr(self.g_means3D),
+            ptr(self.g_cov3D), ptr(self.g_sh), ptr(self.g_scales), ptr(self.g_rot), _stream()), "dqo_rast_backward")
+
+    def check(self):
+        host = self.status.tolist()
+        if host[_lib.ST_OVERFLOW]:
+            raise _lib.DqoError("instance capacity %d exceeded (R = %d): results invalid, re-create the pipeline larger"
+                                % (self.capacity, host[_lib.ST_NUM_RENDERED]))
+        return host
+
+
 # ---------------------------------------------------------------------------------------------------
 # pybind-level compatibility functions (`_C_depth.*`, RAST/ext.cpp:15-19)
 # ---------------------------------------------------------------------------------------------------

@@ -29,6 +29,13 @@ extern "C" {
 int dqo_abi_version(void);
 /* Human-readable description of the last error on this thread (never NULL). */
 const char *dqo_last_error(void);
+/* Instrumentation (bench.py): number of this library's own kernel launches so far (CUB library calls count as one),
+ * and optional per-stage CUDA-event timing of the rasterizer on the launching stream.  Stage order:
+ * 0 begin-fwd, 1 preprocess, 2 depth sort, 3 scan, 4 duplicate, 5 tile sort, 6 ranges, 7 compact, 8 render-fwd,
+ * 9 begin-bwd, 10 render-bwd, 11 gaussian-bwd.  dqo_profile_read synchronises on the recorded events. */
+long long dqo_launch_count(void);
+void dqo_profile_enable(int on);
+int dqo_profile_read(float *ms_out, int n);
 
 /* ------------------------------------------------------------------------------------------------
  * Rasterizer settings.  Mirrors GaussianRasterizationSettings

@@ -1,0 +1,56 @@
+"""CPU: the C-ABI library loads and exports exactly what include/dqo_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from dqo_map_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "dqo_b200.h")
+
+
+def _declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dqo_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    declared = _declared_functions()
+    assert declared, "no functions parsed from the header"
+    assert sorted(_lib.PROTOTYPES) == declared
+
+
+def test_library_exports_every_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _declared_functions():
+        assert hasattr(h, name), name
+    L = _lib.lib()
+    assert L.dqo_abi_version() == _lib.ABI_VERSION
+    assert L.dqo_last_error() is not None
+
+
+def test_struct_layouts():
+    assert ctypes.sizeof(_lib.RastSettings) == 18 * 4
+    assert ctypes.sizeof(_lib.AdamTensor) == 4 * 8 + 8 + 4 + 4
+
+
+def test_invalid_arguments_are_reported_without_a_gpu():
+    L = _lib.lib()
+    assert L.dqo_mark_visible(-1, None, None, None, None, None) == -1
+    assert b"invalid" in L.dqo_last_error()
+    assert L.dqo_knn3(-5, None, None, None, None, 0, None) == -1
+    assert L.dqo_adam_step(None, 0, 1, 0.9, 0.999, 1e-15, None, -1, None) == -1
+    # P == 0 short-circuits like the reference (rasterize_points.cu:103,208)
+    assert L.dqo_knn3(0, None, None, None, None, 0, None) == 0
+    assert L.dqo_quadric_refine(0, 20, 1, None, None, None, None, 0.01, 0.001, 0.01, None, None, None, None, None) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libdqomap_b200.so")
+    with pytest.raises(_lib.DqoError, match="no CPU fallback"):
+        _lib.lib()

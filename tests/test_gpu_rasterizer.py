@@ -1,0 +1,304 @@
+"""GPU parity tests of the rasterizer hot path, all through the C-ABI (dqo_rast_forward / dqo_rast_backward).
+
+Gates (BASELINE.json north_star): sort keys, sorted ids, tile ranges, tile list, per-pixel contributor counts, radii and
+index maps bit-exact; colour / depth / T within max-abs 1e-4; gradients within 1e-3 relative.
+Three arbiters: (1) golden fixtures produced by the reference on a B200, (2) the CPU oracle on fresh seeded inputs,
+(3) the live reference extension (oracle/_ref) when its .so travelled to the box.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import refharness as rh
+from dqo_map_b200 import _lib, rasterizer, synthetic
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GRADS = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"]
+
+
+def t2n(t):
+    return t.detach().cpu().numpy()
+
+
+def _inputs_from_golden(g):
+    dev = torch.device(DEV)
+    d = {k: torch.tensor(g[k]).to(dev) for k in ["xyz", "scales", "rotations", "opacity", "shs", "bg", "tile_mask"]}
+    d["rgb"] = torch.tensor(g["rgb_in"]).to(dev)
+    d["sh_degree"] = int(g["sh_degree"])
+    d["precomp"] = bool(int(g["precomp"]))
+    cam = synthetic.make_camera("tiny").to(dev)
+    assert np.array_equal(t2n(cam.world_view_transform), g["viewmatrix"])
+    assert np.array_equal(t2n(cam.full_proj_transform), g["projmatrix"])
+    d["cam"] = cam
+    return d
+
+
+def _run_ours(inp, gc=None, gd=None):
+    o = rasterizer.rasterize_gaussians(*rh.raster_args(inp))
+    cam = inp["cam"]
+    st = o[10]._dqo_state
+    ex = rh.export_ours(st, inp["xyz"].shape[0], cam.image_width, cam.image_height)
+    bw = None
+    if gc is not None:
+        bw = rasterizer.rasterize_gaussians_backward(*rh.backward_args(inp, o, gc, gd))
+        torch.cuda.synchronize()
+    return o, ex, bw
+
+
+def _check_forward_exact(o, ex, ref, P):
+    """ref: dict in golden-fixture format."""
+    (rendered, tile_num, color, depth, hit_color, hit_depth, hcw, hdw, T_map, radii, *_rest) = o
+    tile_indices, n_touched = o[13], o[14]
+    assert rendered == int(ref["num_rendered"]) and tile_num == int(ref["tile_num"])
+    assert np.array_equal(t2n(radii), ref["radii"])
+    assert np.array_equal(ex["tiles_touched"], ref["tiles_touched"])
+    assert np.array_equal(ex["keys_sorted"], ref["keys_sorted"])
+    assert np.array_equal(ex["point_list"], ref["point_list"])
+    assert np.array_equal(ex["ranges"], ref["ranges"])
+    assert np.array_equal(t2n(tile_indices)[:tile_num], ref["tile_indices"][:tile_num])
+    rendered_px = ref["T_map"][0] != 1.0
+    assert np.array_equal(np.where(rendered_px, ex["n_contrib"], 0), np.where(rendered_px, ref["n_contrib"], 0))
+    assert np.array_equal(t2n(hit_depth), ref["hit_depth"])
+    assert np.array_equal(t2n(hit_color), ref["hit_color"])
+    assert np.array_equal(t2n(n_touched), ref["n_touched"])
+    vis = ref["radii"] > 0
+    for k in ["means2D", "depths", "conic_opacity"]:
+        assert np.array_equal(ex[k][vis].view(np.uint32), np.ascontiguousarray(ref[k][vis]).view(np.uint32)), k
+    for name, t in [("color", color), ("depth", depth), ("T_map", T_map), ("hit_color_weight", hcw),
+                    ("hit_depth_weight", hdw)]:
+        assert np.abs(t2n(t) - ref[name]).max() <= 1e-4, name
+
+
+def _check_grads(bw, ref, tol=1e-3, ref2=None):
+    """Norm-wise relative gate of 1e-3 (north_star).  `ref2` = a second run of the same reference: its float atomics
+    land in unspecified order and the conic->cov3D chain amplifies the last-bit differences, so at 1M Gaussians two
+    reference runs differ from EACH OTHER by up to ~7e-4 in dL_drotations (profiles/r01_gradient_parity_vs_reference.log).
+    Where that floor is known the gate is max(1e-3, 2.5 x floor)."""
+    for i, (name, t) in enumerate(zip(GRADS, bw)):
+        b = np.asarray(ref[name], dtype=np.float64)
+        if b.size == 0:
+            continue
+        a = t2n(t).astype(np.float64).reshape(b.shape)
+        rel = np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+        gate = tol
+        if ref2 is not None:
+            floor = np.linalg.norm(np.asarray(ref2[name], dtype=np.float64) - b) / (np.linalg.norm(b) + 1e-30)
+            gate = max(tol, 2.5 * floor)
+        assert rel <= gate, (name, rel, gate)
+
+
+@pytest.mark.parametrize("case", ["tiny_sh0_full", "tiny_sh3_half", "tiny_precomp"])
+def test_against_reference_golden(case, golden_dir):
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    inp = _inputs_from_golden(g)
+    gc, gd = torch.tensor(g["grad_color"]).to(DEV), torch.tensor(g["grad_depth"]).to(DEV)
+    o, ex, bw = _run_ours(inp, gc, gd)
+    _check_forward_exact(o, ex, g, inp["xyz"].shape[0])
+    # against the reference on the GPU the images are in fact bit-identical (same expf)
+    for name, idx in [("color", 2), ("depth", 3), ("T_map", 8)]:
+        assert np.array_equal(t2n(o[idx]).view(np.uint32), g[name].view(np.uint32)), name
+    _check_grads(bw, g)
+
+
+def _oracle_as_ref(inp):
+    cam = inp["cam"]
+    sc = oracle.Scene(t2n(inp["xyz"]), t2n(inp["scales"]), t2n(inp["rotations"]), t2n(inp["opacity"]),
+                      t2n(cam.world_view_transform), t2n(cam.full_proj_transform), t2n(cam.camera_center),
+                      cam.image_width, cam.image_height, cam.tanfovx, cam.tanfovy, cam.cx, cam.cy, t2n(inp["bg"]),
+                      t2n(inp["tile_mask"]), shs=None if inp["precomp"] else t2n(inp["shs"]),
+                      sh_degree=0 if inp["precomp"] else inp["sh_degree"],
+                      colors_precomp=t2n(inp["rgb"]) if inp["precomp"] else None,
+                      normal_threshold=synthetic.RENDER_DEFAULTS["normal_threshold"])
+    oracle.set_threads(os.cpu_count() or 1)
+    pre, bn, img = oracle.forward(sc)
+    ref = dict(num_rendered=bn["num_rendered"], tile_num=bn["tile_num"], radii=pre["radii"],
+               tiles_touched=pre["tiles_touched"], keys_sorted=bn["keys_sorted"], point_list=bn["point_list"],
+               ranges=bn["ranges"], tile_indices=bn["tile_indices"], n_contrib=img["n_contrib"], T_map=img["T_map"],
+               hit_depth=img["hit_depth"], hit_color=img["hit_color"], n_touched=img["n_touched"],
+               means2D=pre["means2D"], depths=pre["depths"], conic_opacity=pre["conic_opacity"], color=img["color"],
+               depth=img["depth"], hit_color_weight=img["hit_color_weight"], hit_depth_weight=img["hit_depth_weight"])
+    return sc, pre, bn, img, ref
+
+
+@pytest.mark.parametrize("cfg,P,deg,mask", [("small", 20000, 3, "ones"), ("small", 12000, 1, "half"), ("c1", 30000, 0, "ones")])
+def test_against_cpu_oracle(cfg, P, deg, mask):
+    inp = rh.make_inputs(cfg, torch.device(DEV), seed=77, P=P, sh_degree=deg, mask=mask)
+    cam = inp["cam"]
+    gc, gd = rh.make_pixel_grads(cam.image_height, cam.image_width, DEV, seed=5)
+    o, ex, bw = _run_ours(inp, gc, gd)
+    sc, pre, bn, img, ref = _oracle_as_ref(inp)
+    # the CPU cannot reproduce MUFU.EX2 bit-exactly: allow the (unobserved so far) alpha-threshold flips on a
+    # vanishing fraction of pixels for the quantities downstream of expf; everything upstream must be exact
+    assert o[0] == ref["num_rendered"] and o[1] == ref["tile_num"]
+    assert np.array_equal(t2n(o[9]), ref["radii"])
+    assert np.array_equal(ex["keys_sorted"], ref["keys_sorted"])
+    assert np.array_equal(ex["point_list"], ref["point_list"])
+    assert np.array_equal(ex["ranges"], ref["ranges"])
+    rendered_px = img["T_map"][0] != 1.0
+    mism = (np.where(rendered_px, ex["n_contrib"], 0) != np.where(rendered_px, img["n_contrib"], 0)).mean()
+    assert mism <= 1e-4
+    assert (t2n(o[5]) != img["hit_depth"]).mean() <= 1e-4
+    good = (t2n(o[5]) == img["hit_depth"])[0] & (np.where(rendered_px, ex["n_contrib"], 0) == np.where(rendered_px, img["n_contrib"], 0))
+    assert np.abs(t2n(o[2]) - img["color"])[:, good].max() <= 1e-4
+    assert np.abs(t2n(o[3]) - img["depth"])[:, good].max() <= 1e-4
+    assert np.abs(t2n(o[8]) - img["T_map"])[:, good].max() <= 1e-4
+    gr = oracle.backward(sc, pre, bn, img, t2n(gc), t2n(gd))
+    _check_grads(bw, gr)
+
+
+@pytest.mark.skipif(not rh.reference_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("cfg,mask,precomp", [("c1", "ones", False), ("c1", "half", True), ("c2", "ones", False)])
+def test_against_live_reference(cfg, mask, precomp):
+    """Full BASELINE sizes against the unmodified reference extension on the same GPU."""
+    _, C, _, _ = rh.load_reference()
+    inp = rh.make_inputs(cfg, torch.device(DEV), mask=mask, precomp=precomp)
+    cam = inp["cam"]
+    H, W, P = cam.image_height, cam.image_width, inp["xyz"].shape[0]
+    gc, gd = rh.make_pixel_grads(H, W, DEV)
+    fwd = C.rasterize_gaussians(*rh.raster_args(inp))
+    bwd = C.rasterize_gaussians_backward(*rh.backward_args(inp, fwd, gc, gd))
+    torch.cuda.synchronize()
+    dec = rh.decode_ref_buffers(fwd[10], fwd[11], fwd[12], P, fwd[0], W, H)
+    ref = dict(num_rendered=fwd[0], tile_num=fwd[1], radii=t2n(fwd[9]), tile_indices=t2n(fwd[13]), color=t2n(fwd[2]),
+               depth=t2n(fwd[3]), hit_color=t2n(fwd[4]), hit_depth=t2n(fwd[5]), hit_color_weight=t2n(fwd[6]),
+               hit_depth_weight=t2n(fwd[7]), T_map=t2n(fwd[8]), n_touched=t2n(fwd[14]), **dec)
+    for n, t in zip(GRADS, bwd):
+        ref[n] = t2n(t)
+    bwd2 = C.rasterize_gaussians_backward(*rh.backward_args(inp, fwd, gc, gd))
+    ref2 = {n: t2n(t) for n, t in zip(GRADS, bwd2)}
+    o, ex, bw = _run_ours(inp, gc, gd)
+    _check_forward_exact(o, ex, ref, P)
+    assert np.array_equal(t2n(o[2]).view(np.uint32), ref["color"].view(np.uint32))
+    _check_grads(bw, ref, ref2=ref2)
+
+
+def test_full_size_properties():
+    """Size-independent properties at BASELINE config 2 (1M Gaussians, 1200x680)."""
+    inp = rh.make_inputs("c2", torch.device(DEV))
+    cam = inp["cam"]
+    H, W, P = cam.image_height, cam.image_width, inp["xyz"].shape[0]
+    o1, ex1, _ = _run_ours(inp)
+    o2, ex2, _ = _run_ours(inp)
+    R = o1[0]
+    assert R == int(ex1["tiles_touched"].sum())                       # every counted tile emits exactly one instance
+    k = ex1["keys_sorted"]
+    assert np.all(k[1:] >= k[:-1])                                     # sortedness
+    same = k[1:] == k[:-1]
+    assert np.all(ex1["point_list"][1:][same] > ex1["point_list"][:-1][same])  # stability (ties in index order)
+    rg = ex1["ranges"].astype(np.int64)
+    ne = rg[:, 0] != rg[:, 1]
+    assert int((rg[ne, 1] - rg[ne, 0]).sum()) == R                     # ranges partition the list
+    assert np.array_equal((k >> np.uint64(32)).astype(np.int64)[rg[ne, 0]], np.nonzero(ne)[0])
+    assert o1[1] == int(ne.sum())
+    # idempotence / determinism of everything but float atomics
+    for i in (2, 3, 4, 5, 6, 7, 8, 9, 14):
+        assert torch.equal(o1[i], o2[i])
+    assert np.array_equal(ex1["point_list"], ex2["point_list"])
+    # transmittance stays in (0, 1]; pixels outside rendered tiles keep the fill values (N1)
+    T = t2n(o1[8])
+    assert T.max() <= 1.0 and T.min() > 0.0
+    hit = t2n(o1[5])
+    assert hit.max() < P and hit.min() >= -1
+
+
+def test_edge_cases():
+    dev = torch.device(DEV)
+    cam = synthetic.make_camera("tiny").to(dev)
+    H, W = cam.image_height, cam.image_width
+    th, tw = (H + 15) // 16, (W + 15) // 16
+
+    def settings(deg=0):
+        return rasterizer.GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=torch.zeros(3, device=dev),
+            scale_modifier=1.0, viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, sh_degree=deg,
+            campos=cam.camera_center, opaque_threshold=0.6, normal_threshold=0.5, depth_threshold=1.0,
+            prefiltered=False, debug=True, cx=cam.cx, cy=cam.cy)
+
+    ones = torch.ones(th, tw, dtype=torch.int32, device=dev)
+    # P == 0 (rasterize_points.cu:103): pre-filled outputs
+    r = rasterizer.GaussianRasterizer(settings())
+    out = r(means3D=torch.zeros(0, 3, device=dev), opacities=torch.zeros(0, 1, device=dev),
+            colors_precomp=torch.zeros(0, 3, device=dev), scales=torch.zeros(0, 3, device=dev),
+            rotations=torch.zeros(0, 4, device=dev), tile_mask=ones)
+    assert out[0].shape == (3, H, W) and float(out[0].abs().max()) == 0 and float(out[6].min()) == 1.0
+    assert int(out[3].abs().max()) == 0 and out[8].numel() == 0
+    # all Gaussians culled
+    g = synthetic.make_gaussians("tiny", P=500)
+    xyz = g["xyz"].to(dev).clone()
+    far = xyz + 1000.0
+    out = r(means3D=far, opacities=g["opacity"].to(dev), colors_precomp=g["rgb"].to(dev), scales=g["scales"].to(dev),
+            rotations=g["rotations"].to(dev), tile_mask=ones)
+    assert int(out[8].max()) == 0 and float(out[6].min()) == 1.0
+    # tile mask all zeros: radii are still reported (N7) but nothing is rendered
+    out = r(means3D=xyz, opacities=g["opacity"].to(dev), colors_precomp=g["rgb"].to(dev), scales=g["scales"].to(dev),
+            rotations=g["rotations"].to(dev), tile_mask=torch.zeros_like(ones))
+    assert int(out[8].max()) > 0 and float(out[6].min()) == 1.0 and float(out[0].abs().max()) == 0
+
+
+def test_capacity_overflow_is_detected_and_recovered():
+    dev = torch.device(DEV)
+    L = _lib.lib()
+    inp = rh.make_inputs("small", dev, P=16000, sh_degree=0)
+    inp["scales"] = inp["scales"] * 4.0
+    ref = rasterizer.rasterize_gaussians(*rh.raster_args(inp))
+    R = ref[0]
+    assert R > 70000, R  # larger than the wrapper's minimum capacity so that the first attempt overflows
+    rasterizer._capacity_hint.clear()
+    again = rasterizer.rasterize_gaussians(*rh.raster_args(inp))
+    assert again[0] == R and torch.equal(again[2], ref[2]) and torch.equal(again[5], ref[5])
+    # raw C-ABI call with a too-small capacity: overflow flag set, nothing rendered, no crash
+    st = ref[10]._dqo_state
+    cap = 1024
+    binning = torch.empty((L.dqo_rast_binning_bytes(cap),), dtype=torch.uint8, device=dev)
+    status = torch.zeros(8, dtype=torch.int32, device=dev)
+    args = rh.raster_args(inp)
+    p = _lib.ptr
+    cam = inp["cam"]
+    H, W, P = cam.image_height, cam.image_width, inp["xyz"].shape[0]
+    f = lambda *s: torch.empty(s, device=dev)
+    i = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
+    color, depth, hd, hc, hcw, hdw, T = f(3, H, W), f(H, W), i(H, W), i(H, W), f(H, W), f(H, W), f(H, W)
+    radii, nt, tidx = i(P), i(P), i(((H + 15) // 16) * ((W + 15) // 16))
+    code = L.dqo_rast_forward(st.settings, p(inp["bg"]), p(inp["xyz"]), p(inp["shs"]), None, p(inp["opacity"]),
+                              p(inp["scales"]), p(inp["rotations"]), None, p(cam.world_view_transform),
+                              p(cam.full_proj_transform), p(cam.camera_center), p(inp["tile_mask"]), p(st.geom),
+                              p(binning), cap, p(st.image), p(tidx), p(color), p(depth), p(hd), p(hc), p(hcw), p(hdw),
+                              p(T), p(radii), p(nt), p(status), torch.cuda.current_stream().cuda_stream)
+    assert code == 0
+    s = status.tolist()
+    assert s[_lib.ST_OVERFLOW] == 1 and s[_lib.ST_NUM_RENDERED] == R and s[_lib.ST_TILE_NUM] == 0
+    assert float(T.min()) == 1.0
+
+
+def test_autograd_api_matches_pybind_path():
+    dev = torch.device(DEV)
+    inp = rh.make_inputs("tiny", dev, P=2500, sh_degree=3)
+    cam = inp["cam"]
+    rd = synthetic.RENDER_DEFAULTS
+    s = rasterizer.GaussianRasterizationSettings(
+        image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        bg=inp["bg"], scale_modifier=1.0, viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform,
+        sh_degree=3, campos=cam.camera_center, opaque_threshold=rd["opaque_threshold"],
+        normal_threshold=rd["normal_threshold"], depth_threshold=rd["depth_threshold"], prefiltered=False, debug=False,
+        cx=cam.cx, cy=cam.cy)
+    leaves = {k: inp[k].clone().requires_grad_(True) for k in ["xyz", "shs", "opacity", "scales", "rotations"]}
+    out = rasterizer.GaussianRasterizer(s)(means3D=leaves["xyz"], opacities=leaves["opacity"], shs=leaves["shs"],
+                                           scales=leaves["scales"], rotations=leaves["rotations"],
+                                           tile_mask=inp["tile_mask"], normal_w=None)
+    assert len(out) == 9
+    gc, gd = rh.make_pixel_grads(cam.image_height, cam.image_width, DEV)
+    (out[0] * gc).sum().add((out[1] * gd).sum()).backward()
+    o = rasterizer.rasterize_gaussians(*rh.raster_args(inp))
+    bw = rasterizer.rasterize_gaussians_backward(*rh.backward_args(inp, o, gc, gd))
+    assert torch.equal(out[0], o[2]) and torch.equal(out[3], o[5]) and torch.equal(out[8], o[9])
+    for name, g in [("xyz", bw[3]), ("shs", bw[5]), ("opacity", bw[2]), ("scales", bw[6]), ("rotations", bw[7])]:
+        a, b = leaves[name].grad, g.reshape(leaves[name].shape)
+        assert float((a - b).norm() / (b.norm() + 1e-30)) <= 1e-4, name
+    vis = rasterizer.GaussianRasterizer(s).markVisible(inp["xyz"])
+    assert vis.dtype == torch.bool and bool(vis[o[9] > 0].all())
+    assert np.array_equal(t2n(vis), oracle.mark_visible(t2n(inp["xyz"]), t2n(cam.world_view_transform),
+                                                        t2n(cam.full_proj_transform)))
