@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdqomap_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_WORDS = 0, 1, 2, 3, 8
 ADAM_MAX_TENSORS = 16
@@ -29,7 +29,7 @@ class RastSettings(C.Structure):
 class AdamTensor(C.Structure):
     _fields_ = [
         ("param", c_p), ("grad", c_p), ("exp_avg", c_p), ("exp_avg_sq", c_p),
-        ("numel", C.c_int64), ("lr", C.c_float), ("row_width", C.c_int32),
+        ("numel", C.c_int64), ("lr", C.c_double), ("row_width", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -55,7 +55,7 @@ PROTOTYPES = {
     "dqo_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "dqo_masked_l1_loss": (C.c_int, [C.c_int32, C.c_int32] + [c_p] * 6 + [C.c_float, C.c_float, C.c_float]
                            + [c_p] * 5 + [c_p]),
-    "dqo_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float,
+    "dqo_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                                 c_p, C.c_int32, c_p]),
     "dqo_quadric_init": (C.c_int, [C.c_int32] + [c_p] * 7 + [c_p]),
     "dqo_quadric_project": (C.c_int, [C.c_int32] + [c_p] * 6 + [c_p]),

@@ -13,7 +13,7 @@
 
 #define DQO_TILE 16
 #define DQO_TILE_PIX 256
-#define DQO_ABI_VERSION 1
+#define DQO_ABI_VERSION 2
 
 namespace dqo {
 
@@ -154,7 +154,8 @@ __host__ __device__ inline uint32_t higher_msb(uint32_t n) { // rasterizer_impl.
 // ---- private workspace layouts ------------------------------------------------------------------
 // geometry buffer: per-Gaussian splat records + depth-sort scratch
 struct GeomLayout {
-    size_t rec;        // float4[3P]: {x,y,conic.x,conic.y} {conic.z,opacity,power_reject,depth} {r,g,b,0}
+    size_t rec;        // float4[3P]: {x,y,conic.x,conic.y} {conic.z,opacity,power_reject,extent.y} {r,g,b,extent.x}
+    size_t depth;      // f32[P] view-space depth (forward.cu:339)
     size_t depth_key;  // u32[P] float bits of view depth, 0xFFFFFFFF when the Gaussian emits no instance
     size_t depth_key2; // u32[P] sorted keys (scratch)
     size_t ids;        // u32[P] iota
@@ -170,7 +171,7 @@ struct GeomLayout {
 };
 // binning buffer: instance lists
 struct BinLayout {
-    size_t keys_in, keys_out; // u32[C] tile id per instance (unsorted / sorted)
+    size_t keys_in, keys_out; // tile id per instance (unsorted / sorted): u16[C] when the image has < 65535 tiles, else u32[C]
     size_t vals_in, vals_out; // u32[C] Gaussian id per instance; vals_out == reference point_list
     size_t cub;
     size_t cub_bytes;
@@ -182,9 +183,27 @@ struct ImgLayout {
     size_t n_contrib;  // u32[T*256]
     size_t final_T;    // f32[T*256]
     size_t hit_geo;    // f32[6][T*256]: hit_normal_c.xyz, hit_point_c.xyz (forward.cu:807-808)
+    size_t mask_bits;  // u32[tiles_y][mask_words]: tile_mask != 0 as a bitmap
+    int mask_words;
     size_t total;
     int tiles_x, tiles_y, T;
 };
+
+// the 8 sub-blocks (8x4 pixels, one per warp) of a 16x16 tile that a splat can reach, from its conservative
+// contribution extent (ex, ey): bit b set <=> sub-block b = (bx = (b&1)*8, by = (b>>1)*4) intersects
+__device__ __forceinline__ unsigned subblock_mask(float mx, float my, float ex, float ey, float tile_px, float tile_py) {
+    unsigned m = 0;
+    const bool x0 = (mx + ex >= tile_px) && (mx - ex <= tile_px + 7.f);
+    const bool x1 = (mx + ex >= tile_px + 8.f) && (mx - ex <= tile_px + 15.f);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const float y0 = tile_py + 4.f * r;
+        const bool yr = (my + ey >= y0) && (my - ey <= y0 + 3.f);
+        if (yr && x0) m |= 1u << (2 * r);
+        if (yr && x1) m |= 1u << (2 * r + 1);
+    }
+    return m;
+}
 
 int make_geom_layout(int P, GeomLayout *L);
 int make_bin_layout(int64_t C, BinLayout *L);

@@ -128,14 +128,14 @@ struct AdamPack {
     int chunk_start[DQO_ADAM_MAX_TENSORS + 1];
     float step_size[DQO_ADAM_MAX_TENSORS]; // lr / bias_correction1
     int n;
-    float beta1, beta2, one_minus_beta1, one_minus_beta2, inv_bc2_sqrt, eps;
+    float beta1, beta2, one_minus_beta1, one_minus_beta2, bc2_sqrt, eps;
 };
 
 __device__ __forceinline__ void adam_elem(float &p, float g, float &m, float &v, const AdamPack &k, float step_size) {
     // torch/optim/adam.py _single_tensor_adam: lerp_, mul_/addcmul_, sqrt/div/add_, addcdiv_
     m = m + k.one_minus_beta1 * (g - m);
     v = v * k.beta2 + k.one_minus_beta2 * g * g;
-    const float denom = sqrtf(v) * k.inv_bc2_sqrt + k.eps;
+    const float denom = sqrtf(v) / k.bc2_sqrt + k.eps;
     p = p - step_size * (m / denom);
 }
 
@@ -276,21 +276,21 @@ extern "C" int dqo_masked_l1_loss(int32_t W, int32_t H, const float *image, cons
     return DQO_OK;
 }
 
-extern "C" int dqo_adam_step(const dqo_adam_tensor *tensors, int32_t n_tensors, int32_t step, float beta1, float beta2,
-                             float eps, float *confidence, int32_t conf_tensor, void *stream_) {
+extern "C" int dqo_adam_step(const dqo_adam_tensor *tensors, int32_t n_tensors, int32_t step, double beta1, double beta2,
+                             double eps, float *confidence, int32_t conf_tensor, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!tensors || n_tensors < 0 || n_tensors > DQO_ADAM_MAX_TENSORS || step < 1) {
         set_error("dqo_adam_step: invalid argument (n_tensors=%d, step=%d)", n_tensors, step);
         return DQO_ERR_INVALID_ARG;
     }
     AdamPack k;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)beta2, (double)step);
-    k.beta1 = beta1; k.beta2 = beta2;
-    k.one_minus_beta1 = (float)(1.0 - (double)beta1);
-    k.one_minus_beta2 = (float)(1.0 - (double)beta2);
-    k.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-    k.eps = eps;
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    k.beta1 = (float)beta1; k.beta2 = (float)beta2;
+    k.one_minus_beta1 = (float)(1.0 - beta1);
+    k.one_minus_beta2 = (float)(1.0 - beta2);
+    k.bc2_sqrt = (float)sqrt(bc2);
+    k.eps = (float)eps;
     int n = 0, chunks = 0;
     for (int i = 0; i < n_tensors; i++) {
         const dqo_adam_tensor &t = tensors[i];
@@ -301,7 +301,7 @@ extern "C" int dqo_adam_step(const dqo_adam_tensor *tensors, int32_t n_tensors, 
         }
         k.param[n] = t.param; k.grad[n] = t.grad; k.m[n] = t.exp_avg; k.v[n] = t.exp_avg_sq;
         k.numel[n] = t.numel;
-        k.step_size[n] = (float)((double)t.lr / bc1);
+        k.step_size[n] = (float)(t.lr / bc1);
         k.chunk_start[n] = chunks;
         chunks += (int)((t.numel + ADAM_CHUNK - 1) / ADAM_CHUNK);
         n++;

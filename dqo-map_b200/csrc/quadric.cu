@@ -198,7 +198,7 @@ struct RefineArgs {
     const int *n_views;
     const float *obs, *Ps;
     const int *choice;
-    float lr[3]; // axes, center, R
+    double lr[3]; // axes, center, R
     float *axes, *R, *center, *last_loss;
 };
 
@@ -214,7 +214,8 @@ __global__ void quadric_refine_kernel(RefineArgs A) {
     int step = 0;
     float loss_v = 0.f;
     const int nv = A.n_views[o];
-    const float beta1 = 0.9f, beta2 = 0.999f, eps = 1e-15f;
+    const double beta1 = 0.9, beta2 = 0.999;
+    const float b2f = (float)beta2, omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2), eps = 1e-15f;
     for (int it = 0; it < A.iters; it++) {
         int k = A.choice[(size_t)o * A.iters + it];
         if (k < 0) k += nv; // python negative index: -1 = latest observation
@@ -310,15 +311,16 @@ __global__ void quadric_refine_kernel(RefineArgs A) {
             for (int kk = 0; kk < 3; kk++) grad[6 + 3 * i + kk] = 2.f * HR[i][kk] * ax[kk] * ax[kk];
         // ---------------- Adam (torch semantics, eps = 1e-15) ----------------
         step++;
-        const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-        const float bc2s = sqrtf(bc2);
+        const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+        const float bc2s = (float)sqrt(bc2);
         for (int q = 0; q < 15; q++) {
-            const float lr = (q < 3) ? A.lr[0] : ((q < 6) ? A.lr[1] : A.lr[2]);
+            const double lr = (q < 3) ? A.lr[0] : ((q < 6) ? A.lr[1] : A.lr[2]);
+            const float step_size = (float)(lr / bc1);
             const float g = grad[q];
-            mom[q] = mom[q] + (1.f - beta1) * (g - mom[q]);
-            var[q] = var[q] * beta2 + (1.f - beta2) * g * g;
+            mom[q] = mom[q] + omb1 * (g - mom[q]);
+            var[q] = var[q] * b2f + omb2 * g * g;
             const float denom = sqrtf(var[q]) / bc2s + eps;
-            p[q] = p[q] - (lr / bc1) * (mom[q] / denom);
+            p[q] = p[q] - step_size * (mom[q] / denom);
         }
     }
     for (int k = 0; k < 3; k++) A.axes[3 * o + k] = p[k];

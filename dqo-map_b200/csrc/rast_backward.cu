@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(256) render_backward_kernel(RenderBwdArgs a) {
     __shared__ float4 s_r1[256];
     __shared__ float4 s_r2[256];
     __shared__ int s_id[256];
+    __shared__ uint8_t s_mask[256];
+    __shared__ uint8_t s_list[8][256];
     __shared__ int s_max;
 
     const int tile = blockIdx.x;
@@ -94,17 +96,16 @@ __global__ void __launch_bounds__(256) render_backward_kernel(RenderBwdArgs a) {
     const size_t HW = (size_t)a.W * a.H;
     const size_t sp = (size_t)tile * 256 + tid;
     const float pixfx = (float)pix_x, pixfy = (float)pix_y;
+    const float tile_px = (float)(tile_x * DQO_TILE), tile_py = (float)(tile_y * DQO_TILE);
 
     const float T_final = inside ? a.final_T[sp] : 0.f;
     float T = T_final;
     const int last_contributor = inside ? (int)a.n_contrib[sp] : 0;
     if (tid == 0) s_max = 0;
     __syncthreads();
-    {
-        int m = last_contributor;
-        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-        if (lane == 0) atomicMax(&s_max, m);
-    }
+    int warp_max = last_contributor; // entries at positions >= warp_max contribute to no pixel of this warp
+    for (int o = 16; o > 0; o >>= 1) warp_max = max(warp_max, __shfl_xor_sync(0xFFFFFFFFu, warp_max, o));
+    if (lane == 0) atomicMax(&s_max, warp_max);
     __syncthreads();
     const int max_c = s_max; // entries at list positions >= max_c contribute to no pixel of this tile
 
@@ -124,16 +125,32 @@ __global__ void __launch_bounds__(256) render_backward_kernel(RenderBwdArgs a) {
     for (int i = 0; i < rounds; i++) {
         __syncthreads();
         const int pos = max_c - 1 - (i * 256 + tid);
+        const int n = min(256, max_c - i * 256);
         if (pos >= 0) {
             const int id = (int)a.point_list[range.x + pos];
+            const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
+            const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
+            const float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
             s_id[tid] = id;
-            s_r0[tid] = __ldg(&a.rec[3 * (size_t)id]);
-            s_r1[tid] = __ldg(&a.rec[3 * (size_t)id + 1]);
-            s_r2[tid] = __ldg(&a.rec[3 * (size_t)id + 2]);
+            s_r0[tid] = r0;
+            s_r1[tid] = r1;
+            s_r2[tid] = r2;
+            s_mask[tid] = (uint8_t)subblock_mask(r0.x, r0.y, r2.w, r1.w, tile_px, tile_py);
         }
         __syncthreads();
-        const int n = min(256, max_c - i * 256);
-        for (int j = 0; j < n; j++) {
+        // this warp's entries of the batch, in processing (back-to-front) order
+        int cnt = 0;
+        for (int b = 0; b < n; b += 32) {
+            const int j = b + lane;
+            const int posj = max_c - 1 - (i * 256 + j);
+            const bool m = (j < n) && (posj < warp_max) && ((s_mask[j] >> warp) & 1);
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, m);
+            if (m) s_list[warp][cnt + __popc(bal & ((1u << lane) - 1))] = (uint8_t)j;
+            cnt += __popc(bal);
+        }
+        __syncwarp();
+        for (int k = 0; k < cnt; k++) {
+            const int j = s_list[warp][k];
             const int posj = max_c - 1 - (i * 256 + j);
             const float4 r0 = s_r0[j];
             const float4 r1 = s_r1[j];
@@ -149,7 +166,7 @@ __global__ void __launch_bounds__(256) render_backward_kernel(RenderBwdArgs a) {
             if (!__any_sync(0xFFFFFFFFu, contrib)) continue;
             float v[9];
 #pragma unroll
-            for (int k = 0; k < 9; k++) v[k] = 0.f;
+            for (int q = 0; q < 9; q++) v[q] = 0.f;
             if (contrib) {
                 const float4 r2 = s_r2[j];
                 T = T / (1.f - alpha);
@@ -268,10 +285,31 @@ __device__ __constant__ float B_SH_C3[7] = {-0.5900435899266435f, 2.890611442640
                                             0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
                                             -0.5900435899266435f};
 
-__global__ void __launch_bounds__(256) gaussian_backward_kernel(GaussBwdArgs a) {
+#define GB_THREADS 128
+#define GB_ROW_Q 13 // float4 per staged SH row (12 used + 1 pad)
+
+// STAGED (M == 16, 16-byte aligned shs / dL_dsh): each warp moves its 32 x 192 B of SH coefficients in and its
+// 32 x 192 B of SH gradients out with coalesced 128-bit accesses through a padded shared-memory tile.
+template <bool STAGED>
+__global__ void __launch_bounds__(GB_THREADS) gaussian_backward_kernel(GaussBwdArgs a) {
+    extern __shared__ float4 s_row[];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.P) return;
-    const bool active = a.radii[idx] > 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 *wbuf = s_row + warp * 32 * GB_ROW_Q;
+    const int base_g = blockIdx.x * blockDim.x + warp * 32;
+    const int nrow = min(32, a.P - base_g);
+    if (STAGED && nrow > 0) {
+        const float4 *gsh = reinterpret_cast<const float4 *>(a.shs) + (size_t)base_g * 12;
+        const int nq = nrow * 12;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            const int q = i * 32 + lane;
+            if (q < nq) wbuf[(q / 12) * GB_ROW_Q + (q % 12)] = __ldg(gsh + q);
+        }
+        __syncwarp();
+    }
+    const bool live = idx < a.P;
+    const bool active = live && a.radii[idx] > 0;
     const int M = a.M;
     float g[DQO_GACC_FLOATS];
     if (active) {
@@ -289,7 +327,12 @@ __global__ void __launch_bounds__(256) gaussian_backward_kernel(GaussBwdArgs a) 
     float drot[4] = {g[12], g[13], g[14], g[15]};
     float dscale[3] = {0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float *dsh = a.dL_dsh ? a.dL_dsh + (size_t)idx * M * 3 : nullptr;
+    float *dsh = (a.dL_dsh && live) ? a.dL_dsh + (size_t)idx * M * 3 : nullptr;
+    float shg[48]; // staged path: this Gaussian's SH gradients (flat [k][c])
+    if (STAGED) {
+#pragma unroll
+        for (int k = 0; k < 48; k++) shg[k] = 0.f;
+    }
 
     if (active) {
         const float mx = a.means3D[3 * idx], my = a.means3D[3 * idx + 1], mz = a.means3D[3 * idx + 2];
@@ -397,13 +440,27 @@ __global__ void __launch_bounds__(256) gaussian_backward_kernel(GaussBwdArgs a) 
         }
         // ---- colour -> SH (+ view direction -> mean) (backward.cu:152-268) ----
         if (a.shs) {
-            const float *sh = a.shs + (size_t)idx * M * 3;
+            float sh[48];
+            if (STAGED) {
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    const float4 t = wbuf[lane * GB_ROW_Q + i];
+                    sh[4 * i] = t.x; sh[4 * i + 1] = t.y; sh[4 * i + 2] = t.z; sh[4 * i + 3] = t.w;
+                }
+            } else {
+                const float *gp = a.shs + (size_t)idx * M * 3;
+                const int nload = (a.D + 1) * (a.D + 1) * 3;
+#pragma unroll
+                for (int k = 0; k < 48; k++) sh[k] = (k < nload) ? gp[k] : 0.f;
+            }
             const uint8_t cl = a.clamped[idx];
             const float dRGB[3] = {(cl & 1) ? 0.f : g[6], (cl & 2) ? 0.f : g[7], (cl & 4) ? 0.f : g[8]};
             const float ox = mx - a.campos[0], oy = my - a.campos[1], oz = mz - a.campos[2];
             const float inv_len = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
             const float x = ox * inv_len, y = oy * inv_len, z = oz * inv_len;
             float w[16]; // dRGB / dsh_k
+#pragma unroll
+            for (int k = 0; k < 16; k++) w[k] = 0.f;
             float dx_[3] = {0, 0, 0}, dy_[3] = {0, 0, 0}, dz_[3] = {0, 0, 0}; // dRGB/d dir per channel
             w[0] = B_SH_C0;
             const int deg = a.D;
@@ -450,12 +507,23 @@ __global__ void __launch_bounds__(256) gaussian_backward_kernel(GaussBwdArgs a) 
                     }
                 }
             }
-            const int ncoef = (deg + 1) * (deg + 1);
-            for (int k = 0; k < M; k++) {
-                const float wk = (k < ncoef) ? w[k < 16 ? k : 15] : 0.f;
-                dsh[3 * k] = (k < ncoef) ? wk * dRGB[0] : 0.f;
-                dsh[3 * k + 1] = (k < ncoef) ? wk * dRGB[1] : 0.f;
-                dsh[3 * k + 2] = (k < ncoef) ? wk * dRGB[2] : 0.f;
+            if (STAGED) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    shg[3 * k] = w[k] * dRGB[0];
+                    shg[3 * k + 1] = w[k] * dRGB[1];
+                    shg[3 * k + 2] = w[k] * dRGB[2];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    if (k < M) {
+                        dsh[3 * k] = w[k] * dRGB[0];
+                        dsh[3 * k + 1] = w[k] * dRGB[1];
+                        dsh[3 * k + 2] = w[k] * dRGB[2];
+                    }
+                }
+                for (int k = 48; k < 3 * M; k++) dsh[k] = 0.f;
             }
             const float ddx = dx_[0] * dRGB[0] + dx_[1] * dRGB[1] + dx_[2] * dRGB[2];
             const float ddy = dy_[0] * dRGB[0] + dy_[1] * dRGB[1] + dy_[2] * dRGB[2];
@@ -502,12 +570,29 @@ __global__ void __launch_bounds__(256) gaussian_backward_kernel(GaussBwdArgs a) 
             drot[3] += 2 * r_ * (Mt[0][1] - Mt[1][0]) + 2 * x * (Mt[2][0] + Mt[0][2]) + 2 * y * (Mt[1][2] + Mt[2][1]) -
                        4 * z * (Mt[1][1] + Mt[0][0]);
         }
-    } else if (dsh) {
+    } else if (!STAGED && dsh) {
         for (int k = 0; k < 3 * M; k++) dsh[k] = 0.f;
     }
-    if (active && !a.shs && dsh) {
+    if (!STAGED && active && !a.shs && dsh) {
         for (int k = 0; k < 3 * M; k++) dsh[k] = 0.f;
     }
+    if (STAGED) { // own row -> shared -> coalesced 128-bit stores of the warp's contiguous 32 x 192 B block
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 12; i++)
+            wbuf[lane * GB_ROW_Q + i] = make_float4(shg[4 * i], shg[4 * i + 1], shg[4 * i + 2], shg[4 * i + 3]);
+        __syncwarp();
+        if (nrow > 0) {
+            float4 *gd = reinterpret_cast<float4 *>(a.dL_dsh) + (size_t)base_g * 12;
+            const int nq = nrow * 12;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const int q = i * 32 + lane;
+                if (q < nq) gd[q] = wbuf[(q / 12) * GB_ROW_Q + (q % 12)];
+            }
+        }
+    }
+    if (!live) return;
 
     if (a.dL_dmeans2D) {
         a.dL_dmeans2D[3 * idx] = g[0];
@@ -610,7 +695,12 @@ extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *backgr
     ga.dL_dmeans2D = dL_dmeans2D; ga.dL_dconic = dL_dconic; ga.dL_dopacity = dL_dopacity; ga.dL_dcolors = dL_dcolors;
     ga.dL_dmeans3D = dL_dmeans3D; ga.dL_dcov3D = dL_dcov3D; ga.dL_dsh = (s->M > 0) ? dL_dsh : nullptr;
     ga.dL_dscales = dL_dscales; ga.dL_drot = dL_drotations;
-    gaussian_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(ga);
+    const bool staged = shs && dL_dsh && s->M == 16 && ((uintptr_t)shs % 16 == 0) && ((uintptr_t)dL_dsh % 16 == 0);
+    const int gb_blocks = (P + GB_THREADS - 1) / GB_THREADS;
+    if (staged)
+        gaussian_backward_kernel<true><<<gb_blocks, GB_THREADS, (size_t)(GB_THREADS / 32) * 32 * GB_ROW_Q * sizeof(float4), stream>>>(ga);
+    else
+        gaussian_backward_kernel<false><<<gb_blocks, GB_THREADS, 0, stream>>>(ga);
     DQO_LAUNCH_CHECK("gaussian backward", s->debug, stream);
     stage_mark(stream, ST_GAUSS_BWD);
     return DQO_OK;

@@ -38,6 +38,7 @@ int make_geom_layout(int P, GeomLayout *L) {
     size_t cur = 0;
     size_t n = (size_t)(P > 0 ? P : 1);
     L->rec = bump(cur, n * 48);
+    L->depth = bump(cur, n * 4);
     L->depth_key = bump(cur, n * 4);
     L->depth_key2 = bump(cur, n * 4);
     L->ids = bump(cur, n * 4);
@@ -73,13 +74,17 @@ int make_bin_layout(int64_t C, BinLayout *L) {
     L->keys_out = bump(cur, n * 4);
     L->vals_in = bump(cur, n * 4);
     L->vals_out = bump(cur, n * 4);
-    size_t sort_bytes = 0;
+    size_t sort_bytes = 0, sort16_bytes = 0;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 16);
+                                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 32);
+    if (e == cudaSuccess)
+        e = cub::DeviceRadixSort::SortPairs(nullptr, sort16_bytes, (const uint16_t *)nullptr, (uint16_t *)nullptr,
+                                            (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 16);
     if (e != cudaSuccess) {
         set_error("cub sort size query failed: %s", cudaGetErrorString(e));
         return (int)e;
     }
+    if (sort16_bytes > sort_bytes) sort_bytes = sort16_bytes;
     L->cub_bytes = sort_bytes;
     L->cub = bump(cur, sort_bytes);
     L->total = align_up(cur, 256);
@@ -96,6 +101,8 @@ void make_img_layout(int W, int H, ImgLayout *L) {
     L->n_contrib = bump(cur, T * DQO_TILE_PIX * 4);
     L->final_T = bump(cur, T * DQO_TILE_PIX * 4);
     L->hit_geo = bump(cur, T * DQO_TILE_PIX * 4 * 6);
+    L->mask_words = (L->tiles_x + 31) / 32;
+    L->mask_bits = bump(cur, (size_t)(L->tiles_y > 0 ? L->tiles_y : 1) * L->mask_words * 4);
     L->total = align_up(cur, 256);
 }
 
@@ -110,10 +117,12 @@ struct PreArgs {
     int prefiltered;
     const float *means3D, *scales, *rotations, *opacities, *shs, *cov3D_precomp, *colors_precomp;
     const float *view, *proj, *campos;
-    const int *tile_mask;
+    const uint32_t *mask_bits;
+    int mask_words;
     int *radii;
     int *n_touched;
     float4 *rec;
+    float *depth;
     uint32_t *depth_key, *ids, *tiles;
     uint2 *rect;
     uint8_t *clamped;
@@ -129,8 +138,8 @@ __device__ __constant__ float SH_C3[7] = {-0.5900435899266435f, 2.89061144264055
                                           -0.5900435899266435f};
 
 // SH -> RGB (forward.cu:104-155).  `sh` points at this Gaussian's [M][3] block.
-__device__ __forceinline__ float3 sh_to_rgb(int deg, const float *__restrict__ sh, float3 pos, float3 campos,
-                                            uint8_t *clamp_bits) {
+template <typename SH>
+__device__ __forceinline__ float3 sh_to_rgb(int deg, const SH sh, float3 pos, float3 campos, uint8_t *clamp_bits) {
     float dx = fsub(pos.x, campos.x), dy = fsub(pos.y, campos.y), dz = fsub(pos.z, campos.z);
     float len = fsqrt(dot3_ref(dx, dx, dy, dy, dz, dz));
     float x = fdiv(dx, len), y = fdiv(dy, len), z = fdiv(dz, len);
@@ -195,8 +204,65 @@ __device__ __forceinline__ bool frustum_test(float px, float py, float pz, const
     return true;
 }
 
-__global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
+// tile_mask != 0 as one bitmap row per tile row: the per-Gaussian tile count and the instance emission then cost
+// O(rows x words) instead of one global load per tile of the rectangle
+__global__ void mask_bits_kernel(int gx, int gy, int words, const int *__restrict__ tile_mask, uint32_t *bits) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= gy * words) return;
+    const int y = w / words, word = w % words, x = word * 32 + (threadIdx.x & 31);
+    const bool on = (x < gx) && (tile_mask[y * gx + x] != 0);
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, on);
+    if ((threadIdx.x & 31) == 0) bits[w] = b;
+}
+
+// number of set mask bits in columns [minx, maxx) of tile row y
+__device__ __forceinline__ uint32_t mask_row_count(const uint32_t *__restrict__ bits, int words, uint32_t y, uint32_t minx,
+                                                   uint32_t maxx) {
+    uint32_t c = 0;
+    for (uint32_t w = minx >> 5; w <= (maxx - 1) >> 5; w++) {
+        uint32_t m = __ldg(&bits[y * words + w]);
+        const uint32_t lo = (w == (minx >> 5)) ? (minx & 31) : 0;
+        const uint32_t hi = (w == ((maxx - 1) >> 5)) ? ((maxx - 1) & 31) : 31;
+        m &= (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi));
+        c += __popc(m);
+    }
+    return c;
+}
+
+struct ShRegs { // 48 SH floats of one Gaussian held in registers (flat [k][c] order)
+    float v[48];
+    __device__ __forceinline__ float operator[](int i) const { return v[i]; }
+};
+struct ShPtr {
+    const float *p;
+    __device__ __forceinline__ float operator[](int i) const { return p[i]; }
+};
+
+#define PRE_THREADS 128
+#define SH_ROW_Q 13 // float4 per staged SH row (12 used + 1 pad: conflict-free for both access patterns)
+
+// STAGED: M == 16 and 16-byte aligned SH — each warp pulls its 32 x 192 B of coefficients with coalesced 128-bit
+// loads through shared memory instead of 32 strided streams.
+template <bool STAGED>
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
+    extern __shared__ float4 s_sh[];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 *wbuf = s_sh + warp * 32 * SH_ROW_Q;
+    if (STAGED) {
+        const int base_g = blockIdx.x * blockDim.x + warp * 32;
+        const int nrow = min(32, a.P - base_g);
+        if (nrow > 0) {
+            const float4 *g = reinterpret_cast<const float4 *>(a.shs) + (size_t)base_g * 12;
+            const int nq = nrow * 12;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const int q = i * 32 + lane;
+                if (q < nq) wbuf[(q / 12) * SH_ROW_Q + (q % 12)] = __ldg(g + q);
+            }
+        }
+        __syncwarp();
+    }
     if (idx >= a.P) return;
     int radius_out = 0;
     uint32_t tiles_out = 0;
@@ -280,7 +346,17 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
                 uint8_t cl = 0;
                 if (a.colors_precomp == nullptr) {
                     const float3 cam = make_float3(a.campos[0], a.campos[1], a.campos[2]);
-                    rgb = sh_to_rgb(a.D, a.shs + (size_t)idx * a.M * 3, make_float3(px, py, pz), cam, &cl);
+                    if (STAGED) {
+                        ShRegs sh;
+#pragma unroll
+                        for (int i = 0; i < 12; i++) {
+                            const float4 t = wbuf[lane * SH_ROW_Q + i];
+                            sh.v[4 * i] = t.x; sh.v[4 * i + 1] = t.y; sh.v[4 * i + 2] = t.z; sh.v[4 * i + 3] = t.w;
+                        }
+                        rgb = sh_to_rgb(a.D, sh, make_float3(px, py, pz), cam, &cl);
+                    } else {
+                        rgb = sh_to_rgb(a.D, ShPtr{a.shs + (size_t)idx * a.M * 3}, make_float3(px, py, pz), cam, &cl);
+                    }
                 } else {
                     rgb = make_float3(a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1],
                                       a.colors_precomp[3 * idx + 2]);
@@ -290,15 +366,34 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
                 float thr = logf(1.0f / (255.0f * opacity));
                 thr = thr - (1e-4f + 1e-5f * fabsf(thr));
                 if (!(thr == thr)) thr = -INFINITY; // NaN (negative / NaN opacity): never early-reject
+                // conservative extent of {pixels whose float-evaluated power can reach thr}: bounding box of the ellipse
+                // d^T Q d <= tau' of the conic actually used, tau' inflated for the rounding noise of the fp32 power
+                // (noise <= delta * (A dx^2 + C dy^2) <= delta * kappa * d^T Q d, kappa = 1 / (1 - |rho|))
+                float ex = INFINITY, ey = INFINITY;
+                {
+                    const double A = conic_x, B = conic_y, C = conic_z;
+                    const double detq = A * C - B * B;
+                    const double rho = fabs(B) / sqrt(A * C);
+                    const double shrink = 1.0 - 2.0 * 2e-6 / (1.0 - rho);
+                    if (detq > 0.0 && A > 0.0 && C > 0.0 && rho < 1.0 && shrink > 0.5) {
+                        const double tau = -2.0 * (double)thr / shrink;
+                        if (tau < 0.0) {
+                            ex = ey = -1.0f; // no pixel can pass the alpha test (opacity < 1/255)
+                        } else {
+                            ex = (float)(sqrt(tau * C / detq) * 1.001 + 0.05);
+                            ey = (float)(sqrt(tau * A / detq) * 1.001 + 0.05);
+                        }
+                    }
+                    if (!(ex == ex) || !(ey == ey)) ex = ey = INFINITY;
+                }
                 a.rec[3 * idx + 0] = make_float4(pix_x, pix_y, conic_x, conic_y);
-                a.rec[3 * idx + 1] = make_float4(conic_z, opacity, thr, vz);
-                a.rec[3 * idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
+                a.rec[3 * idx + 1] = make_float4(conic_z, opacity, thr, ey);
+                a.rec[3 * idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, ex);
+                a.depth[idx] = vz;
                 a.rect[idx] = make_uint2(minx | (maxx << 16), miny | (maxy << 16));
                 flags_out = cl | 0x80;
                 radius_out = my_radius;
-                for (uint32_t x = minx; x < maxx; x++)
-                    for (uint32_t y = miny; y < maxy; y++)
-                        if (a.tile_mask[y * a.grid_x + x]) tiles_out++;
+                for (uint32_t y = miny; y < maxy; y++) tiles_out += mask_row_count(a.mask_bits, a.mask_words, y, minx, maxx);
                 if (tiles_out > 0) key_out = __float_as_uint(vz);
             }
         }
@@ -321,13 +416,17 @@ __global__ void mark_visible_kernel(int P, const float *__restrict__ means, cons
 
 // Emits one (tile, gaussian) pair per masked tile of the rectangle (rasterizer_impl.cu:70-115), walking the
 // Gaussians in depth-rank order so that a stable sort by tile id alone reproduces the reference order.
-// Threads beyond P pad the unused tail of the instance buffer with the sentinel tile id.
+// One warp serves 32 consecutive ranks: the run of each Gaussian is written by all lanes together (coalesced)
+// when no tile of its rectangle is masked out, otherwise by its owner lane walking the mask bitmap.
+// Threads also pad the unused tail [R, capacity) of the key buffer with the sentinel tile id.
+template <typename KeyT>
 __global__ void __launch_bounds__(256)
     duplicate_kernel(int P, int64_t capacity, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
                      const uint32_t *__restrict__ offsets, const uint2 *__restrict__ rect,
-                     const int *__restrict__ tile_mask, int grid_x, uint32_t *__restrict__ keys,
+                     const uint32_t *__restrict__ mask_bits, int mask_words, int grid_x, KeyT *__restrict__ keys,
                      uint32_t *__restrict__ vals, int *status) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const uint32_t R = offsets[P - 1];
     const bool overflow = (int64_t)R > capacity;
     if (i == 0) {
@@ -335,29 +434,57 @@ __global__ void __launch_bounds__(256)
         status[DQO_ST_OVERFLOW] = overflow ? 1 : 0;
     }
     const int64_t R_eff = overflow ? 0 : (int64_t)R;
-    if (i >= R_eff && i < capacity) keys[i] = 0xFFFFFFFFu;
-    if (i >= P || overflow) return;
-    const uint32_t id = order[i];
-    const uint32_t n = tiles[id];
-    if (n == 0) return;
-    uint32_t off = offsets[i] - n;
-    const uint2 rc = rect[id];
-    const uint32_t minx = rc.x & 0xFFFF, maxx = rc.x >> 16, miny = rc.y & 0xFFFF, maxy = rc.y >> 16;
-    for (uint32_t y = miny; y < maxy; y++)
-        for (uint32_t x = minx; x < maxx; x++) {
-            const uint32_t t = y * grid_x + x;
-            if (tile_mask[t]) {
-                keys[off] = t;
-                vals[off] = id;
-                off++;
-            }
+    if (i >= R_eff && i < capacity) keys[i] = (KeyT)~(KeyT)0;
+    if (overflow) return;
+    uint32_t id = 0, n = 0, off = 0;
+    uint2 rc = make_uint2(0, 0);
+    if (i < P) {
+        id = order[i];
+        n = tiles[id];
+        if (n) {
+            off = offsets[i] - n;
+            rc = rect[id];
         }
+    }
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, n != 0);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t s_id = __shfl_sync(0xFFFFFFFFu, id, src), s_n = __shfl_sync(0xFFFFFFFFu, n, src);
+        const uint32_t s_off = __shfl_sync(0xFFFFFFFFu, off, src);
+        const uint32_t rx = __shfl_sync(0xFFFFFFFFu, rc.x, src), ry = __shfl_sync(0xFFFFFFFFu, rc.y, src);
+        const uint32_t minx = rx & 0xFFFF, maxx = rx >> 16, miny = ry & 0xFFFF, maxy = ry >> 16;
+        const uint32_t w = maxx - minx;
+        if (s_n == w * (maxy - miny)) { // nothing masked inside the rectangle
+            for (uint32_t k = lane; k < s_n; k += 32) {
+                const uint32_t dy = k / w, dx = k - dy * w;
+                keys[s_off + k] = (KeyT)((miny + dy) * grid_x + minx + dx);
+                vals[s_off + k] = s_id;
+            }
+        } else if (lane == src) {
+            uint32_t o = s_off;
+            for (uint32_t y = miny; y < maxy; y++)
+                for (uint32_t wd = minx >> 5; wd <= (maxx - 1) >> 5; wd++) {
+                    uint32_t m = __ldg(&mask_bits[y * mask_words + wd]);
+                    const uint32_t lo = (wd == (minx >> 5)) ? (minx & 31) : 0;
+                    const uint32_t hi = (wd == ((maxx - 1) >> 5)) ? ((maxx - 1) & 31) : 31;
+                    m &= (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi));
+                    while (m) {
+                        const uint32_t x = wd * 32 + (__ffs(m) - 1);
+                        m &= m - 1;
+                        keys[o] = (KeyT)(y * grid_x + x);
+                        vals[o] = s_id;
+                        o++;
+                    }
+                }
+        }
+    }
 }
 
 // per-tile [start, end) in the sorted list (rasterizer_impl.cu:120-142)
+template <typename KeyT>
 __global__ void __launch_bounds__(256)
-    tile_ranges_kernel(int64_t capacity, const uint32_t *__restrict__ keys, const int *__restrict__ status,
-                       uint2 *ranges) {
+    tile_ranges_kernel(int64_t capacity, const KeyT *__restrict__ keys, const int *__restrict__ status, uint2 *ranges) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t L = status[DQO_ST_OVERFLOW] ? 0 : status[DQO_ST_NUM_RENDERED];
     if (i >= L) return;
@@ -415,6 +542,7 @@ struct RenderArgs {
     const uint2 *ranges;
     const uint32_t *point_list;
     const float4 *rec;
+    const float *depth;
     const float *view, *means3D, *scales, *rotations, *bg;
     uint32_t *n_contrib;
     float *final_T;
@@ -424,12 +552,19 @@ struct RenderArgs {
     int *out_hit_depth, *out_hit_color, *n_touched;
 };
 
-// Front-to-back blend of one 16x16 tile (forward.cu:636-866).  Warp w covers an 8x4 pixel block.
+// Front-to-back blend of one 16x16 tile (forward.cu:636-866).  Warp w owns the 8x4 pixel sub-block
+// (bx = (w&1)*8, by = (w>>1)*4).  Every 256-entry batch of the tile's list is staged in shared memory together
+// with an 8-bit mask of the sub-blocks each splat can reach; each warp then compacts the batch into its own
+// index list and only walks the splats that can contribute to its pixels.  Skipped splats are exactly those the
+// reference rejects for all 32 pixels (alpha < 1/255), so every output is unchanged; `contributor` is the list
+// position, recovered from the batch index instead of being counted.
 __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
     __shared__ float4 s_r0[256];
     __shared__ float4 s_r1[256];
     __shared__ float4 s_r2[256];
     __shared__ int s_id[256];
+    __shared__ uint8_t s_mask[256];
+    __shared__ uint8_t s_list[8][256];
 
     const int tile = blockIdx.x;
     const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
@@ -457,33 +592,49 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
         return;
     }
     const float pixfx = (float)pix_x, pixfy = (float)pix_y;
+    const float tile_px = (float)(tile_x * DQO_TILE), tile_py = (float)(tile_y * DQO_TILE);
     const int total = (int)(range.y - range.x);
     const int rounds = (total + 255) / 256;
-    int toDo = total;
 
     bool done = !inside;
     float T = 1.0f, end_T = 1.0f;
-    uint32_t contributor = 0, last_contributor = 0;
+    uint32_t last_contributor = 0;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f;
     float depth_ = 0.f;
     bool hit = false;
     int hit_id = -1, hit_color_id = -1;
     float cw_max = -1.f, hit_cw = 0.f, hit_dw = 0.f;
 
-    for (int i = 0; i < rounds; i++, toDo -= 256) {
+    for (int i = 0; i < rounds; i++) {
         if (__syncthreads_count(done) == 256) break;
         const int progress = i * 256 + tid;
+        const int n = min(256, total - i * 256);
         if (progress < total) {
             const int id = (int)a.point_list[range.x + progress];
+            const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
+            const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
+            const float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
             s_id[tid] = id;
-            s_r0[tid] = __ldg(&a.rec[3 * (size_t)id]);
-            s_r1[tid] = __ldg(&a.rec[3 * (size_t)id + 1]);
-            s_r2[tid] = __ldg(&a.rec[3 * (size_t)id + 2]);
+            s_r0[tid] = r0;
+            s_r1[tid] = r1;
+            s_r2[tid] = r2;
+            s_mask[tid] = (uint8_t)subblock_mask(r0.x, r0.y, r2.w, r1.w, tile_px, tile_py);
         }
         __syncthreads();
-        const int n = min(256, toDo);
-        for (int j = 0; !done && j < n; j++) {
-            contributor++;
+        // per-warp compaction of the batch (order preserved)
+        int cnt = 0;
+        if (!__all_sync(0xFFFFFFFFu, done)) {
+            for (int b = 0; b < n; b += 32) {
+                const int j = b + lane;
+                const bool m = (j < n) && ((s_mask[j] >> warp) & 1);
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, m);
+                if (m) s_list[warp][cnt + __popc(bal & ((1u << lane) - 1))] = (uint8_t)j;
+                cnt += __popc(bal);
+            }
+            __syncwarp();
+        }
+        for (int k = 0; !done && k < cnt; k++) {
+            const int j = s_list[warp][k];
             const float4 r0 = s_r0[j];
             const float4 r1 = s_r1[j];
             const float dx = fsub(r0.x, pixfx), dy = fsub(r0.y, pixfy);
@@ -518,7 +669,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
                 if (depth_distance <= fmul(smax, a.depth_thr) && angle_distance >= a.normal_thr)
                     depth_ = hz;
                 else
-                    depth_ = r1.w;
+                    depth_ = a.depth[id];
                 const size_t sp = (size_t)tile * 256 + tid;
                 a.hit_geo[sp] = ncx;
                 a.hit_geo[a.plane + sp] = ncy;
@@ -549,7 +700,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
                     const unsigned m = __match_any_sync(__activemask(), id);
                     if (lane == __ffs(m) - 1) atomicAdd(&a.n_touched[id], __popc(m));
                 }
-                last_contributor = contributor;
+                last_contributor = (uint32_t)(i * 256 + j + 1);
                 end_T = test_T;
             }
             T = test_T;
@@ -574,15 +725,16 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
 // ------------------------------------------------------------------------------------------------
 // state export for parity tests
 // ------------------------------------------------------------------------------------------------
+template <typename KeyT>
 __global__ void export_instances_kernel(int64_t capacity, const int *__restrict__ status,
-                                        const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                        const float4 *__restrict__ rec, uint64_t *out_keys, uint32_t *out_list) {
+                                        const KeyT *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                        const float *__restrict__ depth, uint64_t *out_keys, uint32_t *out_list) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= capacity) return;
     const int64_t L = status[DQO_ST_OVERFLOW] ? 0 : status[DQO_ST_NUM_RENDERED];
     if (i < L) {
         const uint32_t id = vals[i];
-        const uint32_t dbits = __float_as_uint(rec[3 * (size_t)id + 1].w);
+        const uint32_t dbits = __float_as_uint(depth[id]);
         if (out_keys) out_keys[i] = ((uint64_t)keys[i] << 32) | dbits;
         if (out_list) out_list[i] = id;
     } else {
@@ -605,8 +757,8 @@ __global__ void export_pixels_kernel(int W, int H, int grid_x, const uint32_t *_
     if (out_T) out_T[(size_t)py * W + px] = rendered ? final_T[sp] : 1.0f;
 }
 __global__ void export_gauss_kernel(int P, const float4 *__restrict__ rec, const uint32_t *__restrict__ tiles,
-                                    const uint8_t *__restrict__ flags, float *means2D, float *depths, float *conic_o,
-                                    float *rgb, uint32_t *tiles_out) {
+                                    const uint8_t *__restrict__ flags, const float *__restrict__ depth_in, float *means2D,
+                                    float *depths, float *conic_o, float *rgb, uint32_t *tiles_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const bool valid = (flags[i] & 0x80) != 0;
@@ -620,7 +772,7 @@ __global__ void export_gauss_kernel(int P, const float4 *__restrict__ rec, const
         means2D[2 * i] = r0.x;
         means2D[2 * i + 1] = r0.y;
     }
-    if (depths) depths[i] = r1.w;
+    if (depths) depths[i] = valid ? depth_in[i] : 0.f;
     if (conic_o) {
         conic_o[4 * i] = r0.z;
         conic_o[4 * i + 1] = r0.w;
@@ -727,11 +879,19 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
     BinLayout BL;
     const uint32_t *point_list = nullptr;
     const float4 *rec = nullptr;
+    const float *depth = nullptr;
+    const bool keys16 = T < 65535;
     if (P > 0) {
         if (make_geom_layout(P, &GL)) return DQO_ERR_WORKSPACE;
         if (make_bin_layout(capacity, &BL)) return DQO_ERR_WORKSPACE;
         char *geom = (char *)geom_buffer;
         char *bin = (char *)binning_buffer;
+        uint32_t *mask_bits = (uint32_t *)(img + IL.mask_bits);
+        {
+            const int nw = IL.tiles_y * IL.mask_words;
+            mask_bits_kernel<<<(nw + 7) / 8, 256, 0, stream>>>(IL.tiles_x, IL.tiles_y, IL.mask_words, tile_mask, mask_bits);
+            DQO_LAUNCH_CHECK("mask bits", debug, stream);
+        }
         PreArgs pa;
         pa.P = P; pa.D = s->D; pa.M = s->M; pa.W = s->W; pa.H = s->H;
         pa.color_sigma = s->color_sigma; pa.scale_modifier = s->scale_modifier;
@@ -740,9 +900,11 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
         pa.prefiltered = s->prefiltered;
         pa.means3D = means3D; pa.scales = scales; pa.rotations = rotations; pa.opacities = opacities;
         pa.shs = shs; pa.cov3D_precomp = cov3D_precomp; pa.colors_precomp = colors_precomp;
-        pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos; pa.tile_mask = tile_mask;
+        pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
+        pa.mask_bits = mask_bits; pa.mask_words = IL.mask_words;
         pa.radii = radii; pa.n_touched = n_touched;
         pa.rec = (float4 *)(geom + GL.rec);
+        pa.depth = (float *)(geom + GL.depth);
         pa.depth_key = (uint32_t *)(geom + GL.depth_key);
         pa.ids = (uint32_t *)(geom + GL.ids);
         pa.tiles = (uint32_t *)(geom + GL.tiles);
@@ -750,9 +912,17 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
         pa.clamped = (uint8_t *)(geom + GL.clamped);
         pa.status = status;
         rec = pa.rec;
-        preprocess_kernel<<<(P + 255) / 256, 256, 0, stream>>>(pa);
+        depth = pa.depth;
+        const bool staged = shs && s->M == 16 && ((uintptr_t)shs % 16 == 0);
+        const int pre_blocks = (P + PRE_THREADS - 1) / PRE_THREADS;
+        if (staged) {
+            const size_t smem = (size_t)(PRE_THREADS / 32) * 32 * SH_ROW_Q * sizeof(float4);
+            preprocess_kernel<true><<<pre_blocks, PRE_THREADS, smem, stream>>>(pa);
+        } else {
+            preprocess_kernel<false><<<pre_blocks, PRE_THREADS, 0, stream>>>(pa);
+        }
         DQO_LAUNCH_CHECK("preprocess", debug, stream);
-    stage_mark(stream, ST_PREPROCESS);
+        stage_mark(stream, ST_PREPROCESS);
 
         // (depth, id) order of the Gaussians: stable LSD sort on the depth bits
         uint32_t *order = (uint32_t *)(geom + GL.order);
@@ -761,31 +931,45 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
                                                        (uint32_t *)(geom + GL.depth_key2), (const uint32_t *)pa.ids,
                                                        order, P, 0, 32, stream));
         DQO_LAUNCH_CHECK("depth sort", debug, stream);
-    stage_mark(stream, ST_DEPTH_SORT);
+        stage_mark(stream, ST_DEPTH_SORT);
         uint32_t *offsets = (uint32_t *)(geom + GL.offsets);
         TilesInRankOrder it((const uint32_t *)order, GatherTiles{pa.tiles});
         cub_bytes = GL.cub_bytes;
         DQO_CUDA_CHECK(cub::DeviceScan::InclusiveSum(geom + GL.cub, cub_bytes, it, offsets, P, stream));
         DQO_LAUNCH_CHECK("scan", debug, stream);
-    stage_mark(stream, ST_SCAN);
+        stage_mark(stream, ST_SCAN);
 
-        uint32_t *keys_in = (uint32_t *)(bin + BL.keys_in), *keys_out = (uint32_t *)(bin + BL.keys_out);
         uint32_t *vals_in = (uint32_t *)(bin + BL.vals_in), *vals_out = (uint32_t *)(bin + BL.vals_out);
         const int64_t nthreads = capacity > P ? capacity : P;
-        duplicate_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, stream>>>(
-            P, capacity, order, pa.tiles, offsets, pa.rect, tile_mask, IL.tiles_x, keys_in, vals_in, status);
-        DQO_LAUNCH_CHECK("duplicate", debug, stream);
-    stage_mark(stream, ST_DUPLICATE);
+        const unsigned dup_blocks = (unsigned)((nthreads + 255) / 256);
         const int bit = (int)higher_msb((uint32_t)T);
         cub_bytes = BL.cub_bytes;
-        DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(bin + BL.cub, cub_bytes, (const uint32_t *)keys_in, keys_out,
-                                                       (const uint32_t *)vals_in, vals_out, (int)capacity, 0, bit,
-                                                       stream));
-        DQO_LAUNCH_CHECK("tile sort", debug, stream);
-    stage_mark(stream, ST_TILE_SORT);
-        tile_ranges_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(capacity, keys_out, status, ranges);
+        if (keys16) {
+            uint16_t *keys_in = (uint16_t *)(bin + BL.keys_in), *keys_out = (uint16_t *)(bin + BL.keys_out);
+            duplicate_kernel<uint16_t><<<dup_blocks, 256, 0, stream>>>(P, capacity, order, pa.tiles, offsets, pa.rect, mask_bits,
+                                                                      IL.mask_words, IL.tiles_x, keys_in, vals_in, status);
+            DQO_LAUNCH_CHECK("duplicate", debug, stream);
+            stage_mark(stream, ST_DUPLICATE);
+            DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(bin + BL.cub, cub_bytes, (const uint16_t *)keys_in, keys_out,
+                                                           (const uint32_t *)vals_in, vals_out, (int)capacity, 0,
+                                                           bit < 16 ? bit : 16, stream));
+            DQO_LAUNCH_CHECK("tile sort", debug, stream);
+            stage_mark(stream, ST_TILE_SORT);
+            tile_ranges_kernel<uint16_t><<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(capacity, keys_out, status, ranges);
+        } else {
+            uint32_t *keys_in = (uint32_t *)(bin + BL.keys_in), *keys_out = (uint32_t *)(bin + BL.keys_out);
+            duplicate_kernel<uint32_t><<<dup_blocks, 256, 0, stream>>>(P, capacity, order, pa.tiles, offsets, pa.rect, mask_bits,
+                                                                      IL.mask_words, IL.tiles_x, keys_in, vals_in, status);
+            DQO_LAUNCH_CHECK("duplicate", debug, stream);
+            stage_mark(stream, ST_DUPLICATE);
+            DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(bin + BL.cub, cub_bytes, (const uint32_t *)keys_in, keys_out,
+                                                           (const uint32_t *)vals_in, vals_out, (int)capacity, 0, bit, stream));
+            DQO_LAUNCH_CHECK("tile sort", debug, stream);
+            stage_mark(stream, ST_TILE_SORT);
+            tile_ranges_kernel<uint32_t><<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(capacity, keys_out, status, ranges);
+        }
         DQO_LAUNCH_CHECK("tile ranges", debug, stream);
-    stage_mark(stream, ST_RANGES);
+        stage_mark(stream, ST_RANGES);
         point_list = vals_out;
     }
     compact_tiles_kernel<<<1, 1024, 0, stream>>>(T, ranges, tile_indices, status);
@@ -797,7 +981,7 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
     ra.fx = focal_x; ra.fy = focal_y; ra.cx = s->cx; ra.cy = s->cy; ra.scale_mod = s->scale_modifier;
     ra.opaque_thr = s->opaque_threshold; ra.depth_thr = s->depth_threshold; ra.normal_thr = s->normal_threshold;
     ra.T_thr = s->T_threshold;
-    ra.ranges = ranges; ra.point_list = point_list; ra.rec = rec;
+    ra.ranges = ranges; ra.point_list = point_list; ra.rec = rec; ra.depth = depth;
     ra.view = viewmatrix; ra.means3D = means3D; ra.scales = scales; ra.rotations = rotations; ra.bg = background;
     ra.n_contrib = (uint32_t *)(img + IL.n_contrib);
     ra.final_T = (float *)(img + IL.final_T);
@@ -835,14 +1019,22 @@ extern "C" int dqo_rast_export_state(const dqo_rast_settings *s, const void *geo
         if (make_geom_layout(P, &GL) || make_bin_layout(capacity, &BL)) return DQO_ERR_WORKSPACE;
         const char *geom = (const char *)geom_buffer;
         const char *bin = (const char *)binning_buffer;
-        if (sorted_keys || point_list)
-            export_instances_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(
-                capacity, status, (const uint32_t *)(bin + BL.keys_out), (const uint32_t *)(bin + BL.vals_out),
-                (const float4 *)(geom + GL.rec), sorted_keys, point_list);
+        if (sorted_keys || point_list) {
+            const unsigned nb = (unsigned)((capacity + 255) / 256);
+            if (IL.T < 65535)
+                export_instances_kernel<uint16_t><<<nb, 256, 0, stream>>>(
+                    capacity, status, (const uint16_t *)(bin + BL.keys_out), (const uint32_t *)(bin + BL.vals_out),
+                    (const float *)(geom + GL.depth), sorted_keys, point_list);
+            else
+                export_instances_kernel<uint32_t><<<nb, 256, 0, stream>>>(
+                    capacity, status, (const uint32_t *)(bin + BL.keys_out), (const uint32_t *)(bin + BL.vals_out),
+                    (const float *)(geom + GL.depth), sorted_keys, point_list);
+        }
         if (means2D || depths || conic_opacity || rgb || tiles_touched) {
             export_gauss_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
                 P, (const float4 *)(geom + GL.rec), (const uint32_t *)(geom + GL.tiles),
-                (const uint8_t *)(geom + GL.clamped), means2D, depths, conic_opacity, rgb, tiles_touched);
+                (const uint8_t *)(geom + GL.clamped), (const float *)(geom + GL.depth), means2D, depths, conic_opacity, rgb,
+                tiles_touched);
         }
     }
     DQO_LAUNCH_CHECK("export", 0, stream);

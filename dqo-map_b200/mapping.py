@@ -99,7 +99,7 @@ class FusedAdam(torch.optim.Optimizer):
                 keep.append(g)
                 width = int(p.numel() // p.shape[0]) if p.dim() > 0 and p.shape[0] > 0 else 0
                 arr[n] = AdamTensor(ptr(p), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(),
-                                    float(group["lr"]), width)
+                                    float(group["lr"]), width, 0)
                 if self.confidence_param is not None and p is self.confidence_param:
                     conf_idx = n
                 n += 1

@@ -192,12 +192,14 @@ typedef struct dqo_adam_tensor {
     float *exp_avg;
     float *exp_avg_sq;
     int64_t numel;
-    float lr;
+    double lr;
     int32_t row_width; /* trailing elements per Gaussian (for the confidence bump), 0 = n/a */
+    int32_t reserved;
 } dqo_adam_tensor;
 #define DQO_ADAM_MAX_TENSORS 16
-int dqo_adam_step(const dqo_adam_tensor *tensors /* host array */, int32_t n_tensors, int32_t step, float beta1,
-                  float beta2, float eps, float *confidence /* [P] or NULL */, int32_t conf_tensor, void *stream);
+/* betas / eps / lr are doubles like the Python floats torch receives ((float)(1 - beta2) != 1 - (float)beta2). */
+int dqo_adam_step(const dqo_adam_tensor *tensors /* host array */, int32_t n_tensors, int32_t step, double beta1,
+                  double beta2, double eps, float *confidence /* [P] or NULL */, int32_t conf_tensor, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Dual quadrics (SLAM/multiprocess/quadrics.py).  Batched over objects.

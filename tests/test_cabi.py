@@ -35,7 +35,7 @@ def test_library_exports_every_symbol():
 
 def test_struct_layouts():
     assert ctypes.sizeof(_lib.RastSettings) == 18 * 4
-    assert ctypes.sizeof(_lib.AdamTensor) == 4 * 8 + 8 + 4 + 4
+    assert ctypes.sizeof(_lib.AdamTensor) == 4 * 8 + 8 + 8 + 4 + 4
 
 
 def test_invalid_arguments_are_reported_without_a_gpu():
