@@ -189,9 +189,19 @@ struct ImgLayout {
     int tiles_x, tiles_y, T;
 };
 
-// the 8 sub-blocks (8x4 pixels, one per warp) of a 16x16 tile that a splat can reach, from its conservative
-// contribution extent (ex, ey): bit b set <=> sub-block b = (bx = (b&1)*8, by = (b>>1)*4) intersects
-__device__ __forceinline__ unsigned subblock_mask(float mx, float my, float ex, float ey, float tile_px, float tile_py) {
+// The 8 sub-blocks (8x4 pixels, one per warp) of a 16x16 tile that a splat can reach.  Bit b set <=> some pixel
+// centre of sub-block b = (bx = (b&1)*8, by = (b>>1)*4) may satisfy power >= power_reject, i.e. lies inside the
+// ellipse d^T Q d <= tau (Q = conic).  Two conservative tests: the ellipse's axis-aligned extent (ex, ey), then the
+// exact minimum of the quadratic form over the sub-block rectangle (interior, else the best point of the 4 edges).
+// tau is recovered from ex (which already carries the rounding-noise inflation and margins of the preprocess);
+// any NaN / inf in the chain keeps the sub-block.
+__device__ __forceinline__ float edge_min_qf(float A, float B, float C, float u, float vlo, float vhi, float invC) {
+    // min over v in [vlo, vhi] of A u^2 + 2 B u v + C v^2
+    const float v = fminf(fmaxf(-B * u * invC, vlo), vhi);
+    return A * u * u + 2.f * B * u * v + C * v * v;
+}
+__device__ __forceinline__ unsigned subblock_mask(float mx, float my, float A, float B, float C, float ex, float ey,
+                                                  float tile_px, float tile_py) {
     unsigned m = 0;
     const bool x0 = (mx + ex >= tile_px) && (mx - ex <= tile_px + 7.f);
     const bool x1 = (mx + ex >= tile_px + 8.f) && (mx - ex <= tile_px + 15.f);
@@ -202,7 +212,27 @@ __device__ __forceinline__ unsigned subblock_mask(float mx, float my, float ex, 
         if (yr && x0) m |= 1u << (2 * r);
         if (yr && x1) m |= 1u << (2 * r + 1);
     }
-    return m;
+    if (m == 0) return 0;
+    const float tau = ex * ex * (A * C - B * B) / C * 1.0001f;
+    if (!(tau < 3.0e38f)) return m; // inf / NaN: extent test only
+    const float invA = 1.f / A, invC = 1.f / C;
+    unsigned keep = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        if (!((m >> b) & 1)) continue;
+        const float dxl = tile_px + 8.f * (b & 1) - mx, dxh = dxl + 7.f;
+        const float dyl = tile_py + 4.f * (b >> 1) - my, dyh = dyl + 3.f;
+        if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) {
+            keep |= 1u << b;
+            continue;
+        }
+        float f = edge_min_qf(A, B, C, dxl, dyl, dyh, invC);
+        f = fminf(f, edge_min_qf(A, B, C, dxh, dyl, dyh, invC));
+        f = fminf(f, edge_min_qf(C, B, A, dyl, dxl, dxh, invA));
+        f = fminf(f, edge_min_qf(C, B, A, dyh, dxl, dxh, invA));
+        if (!(f > tau)) keep |= 1u << b;
+    }
+    return keep;
 }
 
 int make_geom_layout(int P, GeomLayout *L);

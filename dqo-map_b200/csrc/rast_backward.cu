@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) render_backward_kernel(RenderBwdArgs a) {
             s_r0[tid] = r0;
             s_r1[tid] = r1;
             s_r2[tid] = r2;
-            s_mask[tid] = (uint8_t)subblock_mask(r0.x, r0.y, r2.w, r1.w, tile_px, tile_py);
+            s_mask[tid] = (uint8_t)subblock_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, r1.w, tile_px, tile_py);
         }
         __syncthreads();
         // this warp's entries of the batch, in processing (back-to-front) order

@@ -481,24 +481,41 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// per-tile [start, end) in the sorted list (rasterizer_impl.cu:120-142)
+// per-tile [start, end) in the sorted list (rasterizer_impl.cu:120-142); each thread checks 8 consecutive keys
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
     tile_ranges_kernel(int64_t capacity, const KeyT *__restrict__ keys, const int *__restrict__ status, uint2 *ranges) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
     const int64_t L = status[DQO_ST_OVERFLOW] ? 0 : status[DQO_ST_NUM_RENDERED];
-    if (i >= L) return;
-    const uint32_t cur = keys[i];
-    if (i == 0)
-        ranges[cur].x = 0;
-    else {
-        const uint32_t prev = keys[i - 1];
-        if (cur != prev) {
+    if (base >= L) return;
+    uint32_t prev = (base > 0) ? (uint32_t)keys[base - 1] : 0xFFFFFFFFu;
+    KeyT k[8];
+    if (base + 8 <= L && sizeof(KeyT) == 2) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(keys + base); // capacity-sized arrays are 256-byte aligned
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            k[2 * q] = (KeyT)(w[q] & 0xFFFF);
+            k[2 * q + 1] = (KeyT)(w[q] >> 16);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) k[q] = (base + q < L) ? keys[base + q] : (KeyT)0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int64_t i = base + q;
+        if (i >= L) break;
+        const uint32_t cur = k[q];
+        if (i == 0)
+            ranges[cur].x = 0;
+        else if (cur != prev) {
             ranges[prev].y = (uint32_t)i;
             ranges[cur].x = (uint32_t)i;
         }
+        if (i == L - 1) ranges[cur].y = (uint32_t)L;
+        prev = cur;
     }
-    if (i == L - 1) ranges[cur].y = (uint32_t)L;
 }
 
 // compact list of non-empty tiles in row-major order (rasterizer_impl.cu:348-365 on the host in the reference)
@@ -598,7 +615,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
 
     bool done = !inside;
     float T = 1.0f, end_T = 1.0f;
-    uint32_t last_contributor = 0;
+    int last_j = -1, last_i = 0;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f;
     float depth_ = 0.f;
     bool hit = false;
@@ -618,7 +635,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
             s_r0[tid] = r0;
             s_r1[tid] = r1;
             s_r2[tid] = r2;
-            s_mask[tid] = (uint8_t)subblock_mask(r0.x, r0.y, r2.w, r1.w, tile_px, tile_py);
+            s_mask[tid] = (uint8_t)subblock_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, r1.w, tile_px, tile_py);
         }
         __syncthreads();
         // per-warp compaction of the batch (order preserved)
@@ -700,7 +717,8 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
                     const unsigned m = __match_any_sync(__activemask(), id);
                     if (lane == __ffs(m) - 1) atomicAdd(&a.n_touched[id], __popc(m));
                 }
-                last_contributor = (uint32_t)(i * 256 + j + 1);
+                last_j = j;
+                last_i = i;
                 end_T = test_T;
             }
             T = test_T;
@@ -709,7 +727,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
     if (inside) {
         const size_t sp = (size_t)tile * 256 + tid;
         a.final_T[sp] = end_T;
-        a.n_contrib[sp] = last_contributor;
+        a.n_contrib[sp] = (uint32_t)(last_i * 256 + last_j + 1);
         a.out_color[pix_id] = ffma(T, a.bg[0], C0);
         a.out_color[HW + pix_id] = ffma(T, a.bg[1], C1);
         a.out_color[2 * HW + pix_id] = ffma(T, a.bg[2], C2);
@@ -955,7 +973,7 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
                                                            bit < 16 ? bit : 16, stream));
             DQO_LAUNCH_CHECK("tile sort", debug, stream);
             stage_mark(stream, ST_TILE_SORT);
-            tile_ranges_kernel<uint16_t><<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(capacity, keys_out, status, ranges);
+            tile_ranges_kernel<uint16_t><<<(unsigned)((capacity + 2047) / 2048), 256, 0, stream>>>(capacity, keys_out, status, ranges);
         } else {
             uint32_t *keys_in = (uint32_t *)(bin + BL.keys_in), *keys_out = (uint32_t *)(bin + BL.keys_out);
             duplicate_kernel<uint32_t><<<dup_blocks, 256, 0, stream>>>(P, capacity, order, pa.tiles, offsets, pa.rect, mask_bits,
@@ -966,7 +984,7 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
                                                            (const uint32_t *)vals_in, vals_out, (int)capacity, 0, bit, stream));
             DQO_LAUNCH_CHECK("tile sort", debug, stream);
             stage_mark(stream, ST_TILE_SORT);
-            tile_ranges_kernel<uint32_t><<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(capacity, keys_out, status, ranges);
+            tile_ranges_kernel<uint32_t><<<(unsigned)((capacity + 2047) / 2048), 256, 0, stream>>>(capacity, keys_out, status, ranges);
         }
         DQO_LAUNCH_CHECK("tile ranges", debug, stream);
         stage_mark(stream, ST_RANGES);
