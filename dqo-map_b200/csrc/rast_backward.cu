@@ -74,13 +74,124 @@ __device__ __forceinline__ int slot_of_lane(int lane) {
     return ok ? s9 : -1;
 }
 
-__global__ void __launch_bounds__(256) render_backward_kernel(RenderBwdArgs a) {
+#define RB_THREADS 128 // 4 warps x (8x8 pixels); every thread owns the pixels (x, y) and (x, y + 4)
+
+// per-pixel state of the reverse traversal (backward.cu:881-900)
+struct BwdPix {
+    float T, T_final, acc0, acc1, acc2, last_alpha, lc0, lc1, lc2, dLp0, dLp1, dLp2, bg_dot, pixfy;
+    int last_contributor;
+};
+
+// One (splat, pixel) pair of the reverse blend (backward.cu:926-995): adds this pixel's 9 partial gradients to v.
+__device__ __forceinline__ bool bwd_pair(BwdPix &p, const float4 r0, const float4 r1, const float4 r2, int posj, float pixfx,
+                                         float ddelx_dx, float ddely_dy, float v[9]) {
+    if (!(posj < p.last_contributor)) return false;
+    const float dx = fsub(r0.x, pixfx), dy = fsub(r0.y, p.pixfy);
+    const float power = ffma(ffma(dx, fmul(dx, r0.z), fmul(dy, fmul(dy, r1.x))), -0.5f, -fmul(dy, fmul(dx, r0.w)));
+    if (power > 0.0f || power < r1.z) return false;
+    const float G = expf(power);
+    const float alpha = fminf(0.99f, fmul(r1.y, G));
+    if (alpha < 1.0f / 255.0f) return false;
+    p.T = p.T / (1.f - alpha);
+    const float dchannel_dcolor = alpha * p.T;
+    p.acc0 = p.last_alpha * p.lc0 + (1.f - p.last_alpha) * p.acc0;
+    p.acc1 = p.last_alpha * p.lc1 + (1.f - p.last_alpha) * p.acc1;
+    p.acc2 = p.last_alpha * p.lc2 + (1.f - p.last_alpha) * p.acc2;
+    p.lc0 = r2.x;
+    p.lc1 = r2.y;
+    p.lc2 = r2.z;
+    float dL_dalpha = (r2.x - p.acc0) * p.dLp0 + (r2.y - p.acc1) * p.dLp1 + (r2.z - p.acc2) * p.dLp2;
+    dL_dalpha *= p.T;
+    p.last_alpha = alpha;
+    dL_dalpha += (-p.T_final / (1.f - alpha)) * p.bg_dot;
+    const float dL_dG = r1.y * dL_dalpha;
+    const float gdx = G * dx, gdy = G * dy;
+    const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
+    const float dG_ddely = -gdy * r1.x - gdx * r0.w;
+    v[0] += dL_dG * dG_ddelx * ddelx_dx;
+    v[1] += dL_dG * dG_ddely * ddely_dy;
+    v[2] += -0.5f * gdx * dx * dL_dG;
+    v[3] += -0.5f * gdx * dy * dL_dG;
+    v[4] += -0.5f * gdy * dy * dL_dG;
+    v[5] += G * dL_dalpha;
+    v[6] += dchannel_dcolor * p.dLp0;
+    v[7] += dchannel_dcolor * p.dLp1;
+    v[8] += dchannel_dcolor * p.dLp2;
+    return true;
+}
+
+// depth gradient to the single hit Gaussian of a pixel (backward.cu:998-1065)
+__device__ __noinline__ void bwd_depth_path(const float *scales, const float *rotations, const float *means3D,
+                                            const float *view, const float *hit_geo, size_t plane, size_t sp, float *gacc,
+                                            int gid, float g, uint32_t pix_x, uint32_t pix_y, float fx, float fy, float cx,
+                                            float cy, float depth_thr, float normal_thr) {
+    const float3 ray = pixel_ray(pix_x, pix_y, fx, fy, cx, cy);
+    const float sx = scales[3 * gid], sy = scales[3 * gid + 1], sz = scales[3 * gid + 2];
+    const float scale_max = fmaxf(fmaxf(sx, sy), sz);
+    const float ncx = hit_geo[sp], ncy = hit_geo[plane + sp], ncz = hit_geo[2 * plane + sp];
+    const float hz = hit_geo[5 * plane + sp];
+    const float *v = view;
+    const float wx = means3D[3 * gid], wy = means3D[3 * gid + 1], wz = means3D[3 * gid + 2];
+    const float pcx = xform_row(v, 0, wx, wy, wz), pcy = xform_row(v, 1, wx, wy, wz), pcz = xform_row(v, 2, wx, wy, wz);
+    const float ndotr = dot3_ref(ncx, ray.x, ncy, ray.y, ncz, ray.z);
+    const float angle_distance = fabsf(ndotr);
+    const float depth_distance = fabsf(fsub(hz, pcz));
+    float *acc = gacc + (size_t)gid * DQO_GACC_FLOATS;
+    if (depth_distance <= fmul(depth_thr, scale_max) && angle_distance >= normal_thr) {
+        const float nr = (float)((double)ndotr + 1e-8);
+        const float inv_nr = 1.f / nr;
+        const float inv_nr2 = inv_nr * inv_nr;
+        const float np = ncx * pcx + ncy * pcy + ncz * pcz;
+        const float dpx = ray.z * ncx * inv_nr, dpy = ray.z * ncy * inv_nr, dpz = ray.z * ncz * inv_nr;
+        atomicAdd(&acc[9], g * (dpx * v[0] + dpy * v[1] + dpz * v[2]));
+        atomicAdd(&acc[10], g * (dpx * v[4] + dpy * v[5] + dpz * v[6]));
+        atomicAdd(&acc[11], g * (dpx * v[8] + dpy * v[9] + dpz * v[10]));
+        const int axis = arg_min3(sx, sy, sz);
+        const float n1c = ray.z * (nr * pcx - np * ray.x) * inv_nr2;
+        const float n2c = ray.z * (nr * pcy - np * ray.y) * inv_nr2;
+        const float n3c = ray.z * (nr * pcz - np * ray.z) * inv_nr2;
+        const float n1w = n1c * v[0] + n2c * v[1] + n3c * v[2];
+        const float n2w = n1c * v[4] + n2c * v[5] + n3c * v[6];
+        const float n3w = n1c * v[8] + n2c * v[9] + n3c * v[10];
+        const float4 q = reinterpret_cast<const float4 *>(rotations)[gid];
+        const float q0 = q.x, q1 = q.y, q2 = q.z, q3 = q.w;
+        float d0[3], d1[3], d2[3], d3[3]; // d normal / d q_k (backward.cu:100-148)
+        if (axis == 0) {
+            d0[0] = 0; d0[1] = 2 * q3; d0[2] = -2 * q2;
+            d1[0] = 0; d1[1] = 2 * q2; d1[2] = 2 * q3;
+            d2[0] = -4 * q2; d2[1] = 2 * q1; d2[2] = -2 * q0;
+            d3[0] = -4 * q3; d3[1] = 2 * q0; d3[2] = 2 * q1;
+        } else if (axis == 1) {
+            d0[0] = -2 * q3; d0[1] = 0; d0[2] = 2 * q1;
+            d1[0] = 2 * q2; d1[1] = -4 * q1; d1[2] = 2 * q0;
+            d2[0] = 2 * q1; d2[1] = 0; d2[2] = 2 * q3;
+            d3[0] = -2 * q0; d3[1] = -4 * q3; d3[2] = 2 * q2;
+        } else {
+            d0[0] = 2 * q2; d0[1] = -2 * q1; d0[2] = 0;
+            d1[0] = 2 * q3; d1[1] = -2 * q0; d1[2] = -4 * q1;
+            d2[0] = 2 * q0; d2[1] = 2 * q3; d2[2] = -4 * q2;
+            d3[0] = 2 * q1; d3[1] = 2 * q2; d3[2] = 0;
+        }
+        atomicAdd(&acc[12], g * (n1w * d0[0] + n2w * d0[1] + n3w * d0[2]));
+        atomicAdd(&acc[13], g * (n1w * d1[0] + n2w * d1[1] + n3w * d1[2]));
+        atomicAdd(&acc[14], g * (n1w * d2[0] + n2w * d2[1] + n3w * d2[2]));
+        atomicAdd(&acc[15], g * (n1w * d3[0] + n2w * d3[1] + n3w * d3[2]));
+    } else {
+        atomicAdd(&acc[9], g * v[2]);
+        atomicAdd(&acc[10], g * v[6]);
+        atomicAdd(&acc[11], g * v[10]);
+    }
+}
+
+// Reverse blend of one 16x16 tile.  Same thread / warp layout and per-warp culled lists as the forward kernel; the
+// two pixels of a thread add into the same 9 partial sums before the single warp reduction per splat.
+__global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(RenderBwdArgs a) {
     __shared__ float4 s_r0[256];
     __shared__ float4 s_r1[256];
     __shared__ float4 s_r2[256];
     __shared__ int s_id[256];
     __shared__ uint8_t s_mask[256];
-    __shared__ uint8_t s_list[8][256];
+    __shared__ uint8_t s_list[RB_THREADS / 32][256];
     __shared__ int s_max;
 
     const int tile = blockIdx.x;
@@ -89,53 +200,72 @@ __global__ void __launch_bounds__(256) render_backward_kernel(RenderBwdArgs a) {
     const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
-    const uint32_t pix_x = tile_x * DQO_TILE + lx, pix_y = tile_y * DQO_TILE + ly;
-    const bool inside = pix_x < (uint32_t)a.W && pix_y < (uint32_t)a.H;
-    const size_t pix_id = (size_t)a.W * pix_y + pix_x;
+    const int lx = (warp & 1) * 8 + (lane & 7), ly0 = (warp >> 1) * 8 + (lane >> 3);
+    const uint32_t pix_x = tile_x * DQO_TILE + lx;
     const size_t HW = (size_t)a.W * a.H;
-    const size_t sp = (size_t)tile * 256 + tid;
-    const float pixfx = (float)pix_x, pixfy = (float)pix_y;
+    const float pixfx = (float)pix_x;
     const float tile_px = (float)(tile_x * DQO_TILE), tile_py = (float)(tile_y * DQO_TILE);
+    const int b_lo = 2 * (2 * (warp >> 1)) + (warp & 1), b_hi = b_lo + 2;
+    const unsigned warp_bits = (1u << b_lo) | (1u << b_hi);
 
-    const float T_final = inside ? a.final_T[sp] : 0.f;
-    float T = T_final;
-    const int last_contributor = inside ? (int)a.n_contrib[sp] : 0;
+    BwdPix px[2];
+    uint32_t pix_y[2];
+    bool inside[2];
+    size_t pix_id[2], sp[2];
+    int warp_max = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int ly = ly0 + 4 * h;
+        pix_y[h] = tile_y * DQO_TILE + ly;
+        inside[h] = pix_x < (uint32_t)a.W && pix_y[h] < (uint32_t)a.H;
+        pix_id[h] = (size_t)a.W * pix_y[h] + pix_x;
+        sp[h] = (size_t)tile * 256 + ly * 16 + lx;
+        BwdPix &p = px[h];
+        p.pixfy = (float)pix_y[h];
+        p.T_final = inside[h] ? a.final_T[sp[h]] : 0.f;
+        p.T = p.T_final;
+        p.last_contributor = inside[h] ? (int)a.n_contrib[sp[h]] : 0;
+        p.dLp0 = p.dLp1 = p.dLp2 = 0.f;
+        if (inside[h]) {
+            p.dLp0 = a.dL_dpix[pix_id[h]];
+            p.dLp1 = a.dL_dpix[HW + pix_id[h]];
+            p.dLp2 = a.dL_dpix[2 * HW + pix_id[h]];
+        }
+        p.bg_dot = a.bg[0] * p.dLp0 + a.bg[1] * p.dLp1 + a.bg[2] * p.dLp2;
+        p.acc0 = p.acc1 = p.acc2 = 0.f;
+        p.last_alpha = 0.f;
+        p.lc0 = p.lc1 = p.lc2 = 0.f;
+        warp_max = max(warp_max, p.last_contributor);
+    }
     if (tid == 0) s_max = 0;
     __syncthreads();
-    int warp_max = last_contributor; // entries at positions >= warp_max contribute to no pixel of this warp
+    // entries at positions >= warp_max contribute to no pixel of this warp, >= max_c to no pixel of the tile
     for (int o = 16; o > 0; o >>= 1) warp_max = max(warp_max, __shfl_xor_sync(0xFFFFFFFFu, warp_max, o));
     if (lane == 0) atomicMax(&s_max, warp_max);
     __syncthreads();
-    const int max_c = s_max; // entries at list positions >= max_c contribute to no pixel of this tile
-
-    float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
-    if (inside) {
-        dLp0 = a.dL_dpix[pix_id];
-        dLp1 = a.dL_dpix[HW + pix_id];
-        dLp2 = a.dL_dpix[2 * HW + pix_id];
-    }
-    const float bg_dot = a.bg[0] * dLp0 + a.bg[1] * dLp1 + a.bg[2] * dLp2;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
+    const int max_c = s_max;
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
     const int my_slot = slot_of_lane(lane);
 
     const int rounds = (max_c + 255) / 256;
     for (int i = 0; i < rounds; i++) {
         __syncthreads();
-        const int pos = max_c - 1 - (i * 256 + tid);
         const int n = min(256, max_c - i * 256);
-        if (pos >= 0) {
-            const int id = (int)a.point_list[range.x + pos];
-            const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
-            const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
-            const float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
-            s_id[tid] = id;
-            s_r0[tid] = r0;
-            s_r1[tid] = r1;
-            s_r2[tid] = r2;
-            s_mask[tid] = (uint8_t)subblock_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, r1.w, tile_px, tile_py);
+#pragma unroll
+        for (int e = 0; e < 256 / RB_THREADS; e++) {
+            const int slot = e * RB_THREADS + tid;
+            if (slot < n) {
+                const int pos = max_c - 1 - (i * 256 + slot);
+                const int id = (int)a.point_list[range.x + pos];
+                const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
+                const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
+                const float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
+                s_id[slot] = id;
+                s_r0[slot] = r0;
+                s_r1[slot] = r1;
+                s_r2[slot] = r2;
+                s_mask[slot] = (uint8_t)subblock_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, r1.w, tile_px, tile_py);
+            }
         }
         __syncthreads();
         // this warp's entries of the batch, in processing (back-to-front) order
@@ -143,7 +273,7 @@ __global__ void __launch_bounds__(256) render_backward_kernel(RenderBwdArgs a) {
         for (int b = 0; b < n; b += 32) {
             const int j = b + lane;
             const int posj = max_c - 1 - (i * 256 + j);
-            const bool m = (j < n) && (posj < warp_max) && ((s_mask[j] >> warp) & 1);
+            const bool m = (j < n) && (posj < warp_max) && (s_mask[j] & warp_bits);
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, m);
             if (m) s_list[warp][cnt + __popc(bal & ((1u << lane) - 1))] = (uint8_t)j;
             cnt += __popc(bal);
@@ -152,117 +282,28 @@ __global__ void __launch_bounds__(256) render_backward_kernel(RenderBwdArgs a) {
         for (int k = 0; k < cnt; k++) {
             const int j = s_list[warp][k];
             const int posj = max_c - 1 - (i * 256 + j);
+            const unsigned mk = s_mask[j];
             const float4 r0 = s_r0[j];
             const float4 r1 = s_r1[j];
-            const float dx = fsub(r0.x, pixfx), dy = fsub(r0.y, pixfy);
-            const float power = ffma(ffma(dx, fmul(dx, r0.z), fmul(dy, fmul(dy, r1.x))), -0.5f, -fmul(dy, fmul(dx, r0.w)));
-            bool contrib = (posj < last_contributor) && !(power > 0.0f) && !(power < r1.z);
-            float G = 0.f, alpha = 0.f;
-            if (contrib) {
-                G = expf(power);
-                alpha = fminf(0.99f, fmul(r1.y, G));
-                contrib = !(alpha < 1.0f / 255.0f);
-            }
-            if (!__any_sync(0xFFFFFFFFu, contrib)) continue;
+            const float4 r2 = s_r2[j];
             float v[9];
 #pragma unroll
             for (int q = 0; q < 9; q++) v[q] = 0.f;
-            if (contrib) {
-                const float4 r2 = s_r2[j];
-                T = T / (1.f - alpha);
-                const float dchannel_dcolor = alpha * T;
-                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-                lc0 = r2.x;
-                lc1 = r2.y;
-                lc2 = r2.z;
-                float dL_dalpha = (r2.x - acc0) * dLp0 + (r2.y - acc1) * dLp1 + (r2.z - acc2) * dLp2;
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                const float dL_dG = r1.y * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
-                const float dG_ddely = -gdy * r1.x - gdx * r0.w;
-                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                v[1] = dL_dG * dG_ddely * ddely_dy;
-                v[2] = -0.5f * gdx * dx * dL_dG;
-                v[3] = -0.5f * gdx * dy * dL_dG;
-                v[4] = -0.5f * gdy * dy * dL_dG;
-                v[5] = G * dL_dalpha;
-                v[6] = dchannel_dcolor * dLp0;
-                v[7] = dchannel_dcolor * dLp1;
-                v[8] = dchannel_dcolor * dLp2;
-            }
+            bool contrib = false;
+            if ((mk >> b_lo) & 1) contrib |= bwd_pair(px[0], r0, r1, r2, posj, pixfx, ddelx_dx, ddely_dy, v);
+            if ((mk >> b_hi) & 1) contrib |= bwd_pair(px[1], r0, r1, r2, posj, pixfx, ddelx_dx, ddely_dy, v);
+            if (!__any_sync(0xFFFFFFFFu, contrib)) continue;
             const float total = warp_reduce9(v, lane);
             if (my_slot >= 0) atomicAdd(&a.gacc[(size_t)s_id[j] * DQO_GACC_FLOATS + my_slot], total);
         }
     }
-
-    // depth gradient to the single hit Gaussian (backward.cu:998-1065)
-    if (inside) {
-        const int gid = a.hit_image[pix_id];
-        if (gid >= 0) {
-            const float3 ray = pixel_ray(pix_x, pix_y, a.fx, a.fy, a.cx, a.cy);
-            const float sx = a.scales[3 * gid], sy = a.scales[3 * gid + 1], sz = a.scales[3 * gid + 2];
-            const float scale_max = fmaxf(fmaxf(sx, sy), sz);
-            const float ncx = a.hit_geo[sp], ncy = a.hit_geo[a.plane + sp], ncz = a.hit_geo[2 * a.plane + sp];
-            const float hz = a.hit_geo[5 * a.plane + sp];
-            const float *v = a.view;
-            const float wx = a.means3D[3 * gid], wy = a.means3D[3 * gid + 1], wz = a.means3D[3 * gid + 2];
-            const float pcx = xform_row(v, 0, wx, wy, wz), pcy = xform_row(v, 1, wx, wy, wz),
-                        pcz = xform_row(v, 2, wx, wy, wz);
-            const float ndotr = dot3_ref(ncx, ray.x, ncy, ray.y, ncz, ray.z);
-            const float angle_distance = fabsf(ndotr);
-            const float depth_distance = fabsf(fsub(hz, pcz));
-            const float g = a.dL_ddepth[pix_id];
-            float *acc = a.gacc + (size_t)gid * DQO_GACC_FLOATS;
-            if (depth_distance <= fmul(a.depth_thr, scale_max) && angle_distance >= a.normal_thr) {
-                const float nr = (float)((double)ndotr + 1e-8);
-                const float inv_nr = 1.f / nr;
-                const float inv_nr2 = inv_nr * inv_nr;
-                const float np = ncx * pcx + ncy * pcy + ncz * pcz;
-                const float dpx = ray.z * ncx * inv_nr, dpy = ray.z * ncy * inv_nr, dpz = ray.z * ncz * inv_nr;
-                atomicAdd(&acc[9], g * (dpx * v[0] + dpy * v[1] + dpz * v[2]));
-                atomicAdd(&acc[10], g * (dpx * v[4] + dpy * v[5] + dpz * v[6]));
-                atomicAdd(&acc[11], g * (dpx * v[8] + dpy * v[9] + dpz * v[10]));
-                const int axis = arg_min3(sx, sy, sz);
-                const float n1c = ray.z * (nr * pcx - np * ray.x) * inv_nr2;
-                const float n2c = ray.z * (nr * pcy - np * ray.y) * inv_nr2;
-                const float n3c = ray.z * (nr * pcz - np * ray.z) * inv_nr2;
-                const float n1w = n1c * v[0] + n2c * v[1] + n3c * v[2];
-                const float n2w = n1c * v[4] + n2c * v[5] + n3c * v[6];
-                const float n3w = n1c * v[8] + n2c * v[9] + n3c * v[10];
-                const float4 q = reinterpret_cast<const float4 *>(a.rotations)[gid];
-                const float q0 = q.x, q1 = q.y, q2 = q.z, q3 = q.w;
-                float d0[3], d1[3], d2[3], d3[3]; // d normal / d q_k (backward.cu:100-148)
-                if (axis == 0) {
-                    d0[0] = 0; d0[1] = 2 * q3; d0[2] = -2 * q2;
-                    d1[0] = 0; d1[1] = 2 * q2; d1[2] = 2 * q3;
-                    d2[0] = -4 * q2; d2[1] = 2 * q1; d2[2] = -2 * q0;
-                    d3[0] = -4 * q3; d3[1] = 2 * q0; d3[2] = 2 * q1;
-                } else if (axis == 1) {
-                    d0[0] = -2 * q3; d0[1] = 0; d0[2] = 2 * q1;
-                    d1[0] = 2 * q2; d1[1] = -4 * q1; d1[2] = 2 * q0;
-                    d2[0] = 2 * q1; d2[1] = 0; d2[2] = 2 * q3;
-                    d3[0] = -2 * q0; d3[1] = -4 * q3; d3[2] = 2 * q2;
-                } else {
-                    d0[0] = 2 * q2; d0[1] = -2 * q1; d0[2] = 0;
-                    d1[0] = 2 * q3; d1[1] = -2 * q0; d1[2] = -4 * q1;
-                    d2[0] = 2 * q0; d2[1] = 2 * q3; d2[2] = -4 * q2;
-                    d3[0] = 2 * q1; d3[1] = 2 * q2; d3[2] = 0;
-                }
-                atomicAdd(&acc[12], g * (n1w * d0[0] + n2w * d0[1] + n3w * d0[2]));
-                atomicAdd(&acc[13], g * (n1w * d1[0] + n2w * d1[1] + n3w * d1[2]));
-                atomicAdd(&acc[14], g * (n1w * d2[0] + n2w * d2[1] + n3w * d2[2]));
-                atomicAdd(&acc[15], g * (n1w * d3[0] + n2w * d3[1] + n3w * d3[2]));
-            } else {
-                atomicAdd(&acc[9], g * v[2]);
-                atomicAdd(&acc[10], g * v[6]);
-                atomicAdd(&acc[11], g * v[10]);
-            }
-        }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        if (!inside[h]) continue;
+        const int gid = a.hit_image[pix_id[h]];
+        if (gid >= 0)
+            bwd_depth_path(a.scales, a.rotations, a.means3D, a.view, a.hit_geo, a.plane, sp[h], a.gacc, gid,
+                           a.dL_ddepth[pix_id[h]], pix_x, pix_y[h], a.fx, a.fy, a.cx, a.cy, a.depth_thr, a.normal_thr);
     }
 }
 
@@ -680,7 +721,7 @@ extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *backgr
     ra.hit_geo = (const float *)(img + IL.hit_geo);
     ra.plane = (size_t)IL.T * 256;
     ra.dL_dpix = dL_dout_color; ra.dL_ddepth = dL_dout_depth; ra.hit_image = hit_image; ra.gacc = gacc;
-    render_backward_kernel<<<IL.T, 256, 0, stream>>>(ra);
+    render_backward_kernel<<<IL.T, RB_THREADS, 0, stream>>>(ra);
     DQO_LAUNCH_CHECK("render backward", s->debug, stream);
     stage_mark(stream, ST_RENDER_BWD);
 

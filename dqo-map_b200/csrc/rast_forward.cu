@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
                     depth_ = hz;
                 else
                     depth_ = a.depth[id];
-                const size_t sp = (size_t)tile * 256 + tid;
+                const size_t sp = (size_t)tile * 256 + ly * 16 + lx;
                 a.hit_geo[sp] = ncx;
                 a.hit_geo[a.plane + sp] = ncy;
                 a.hit_geo[2 * a.plane + sp] = ncz;
@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
         }
     }
     if (inside) {
-        const size_t sp = (size_t)tile * 256 + tid;
+        const size_t sp = (size_t)tile * 256 + ly * 16 + lx;
         a.final_T[sp] = end_T;
         a.n_contrib[sp] = (uint32_t)(last_i * 256 + last_j + 1);
         a.out_color[pix_id] = ffma(T, a.bg[0], C0);
@@ -764,8 +764,7 @@ __global__ void export_pixels_kernel(int W, int H, int grid_x, const uint32_t *_
                                      const float *__restrict__ final_T, const uint2 *__restrict__ ranges,
                                      uint32_t *out_nc, float *out_T) {
     const int tile = blockIdx.x, tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+    const int lx = tid & 15, ly = tid >> 4;
     const int px = (tile % grid_x) * 16 + lx, py = (tile / grid_x) * 16 + ly;
     if (px >= W || py >= H) return;
     const uint2 r = ranges[tile];
