@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdqomap_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_WORDS = 0, 1, 2, 3, 8
 ADAM_MAX_TENSORS = 16
@@ -31,6 +31,17 @@ class AdamTensor(C.Structure):
         ("param", c_p), ("grad", c_p), ("exp_avg", c_p), ("exp_avg_sq", c_p),
         ("numel", C.c_int64), ("lr", C.c_double), ("row_width", C.c_int32), ("reserved", C.c_int32),
     ]
+
+
+class MapParams(C.Structure):
+    _fields_ = [("param", c_p * 6), ("exp_avg", c_p * 6), ("exp_avg_sq", c_p * 6), ("lr", C.c_double * 6),
+                ("confidence", c_p)]
+
+
+class Keyframe(C.Structure):
+    _fields_ = [("gt_color", c_p), ("gt_depth", c_p), ("render_mask", c_p), ("tile_mask", c_p), ("viewmatrix", c_p),
+                ("projmatrix", c_p), ("campos", c_p), ("background", c_p), ("color_weight", C.c_float),
+                ("depth_weight", C.c_float), ("depth_err_thres", C.c_float)]
 
 
 # name -> (restype, argtypes); mirrors include/dqo_b200.h declaration by declaration
@@ -57,6 +68,11 @@ PROTOTYPES = {
                            + [c_p] * 5 + [c_p]),
     "dqo_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                                 c_p, C.c_int32, c_p]),
+    "dqo_mapping_step_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
+    "dqo_mapping_step": (C.c_int, [C.POINTER(RastSettings), C.POINTER(MapParams), C.POINTER(Keyframe), C.c_int32,
+                                   C.c_double, C.c_double, C.c_double, c_p, C.c_int64, c_p, c_p, c_p, c_p]),
+    "dqo_mapping_step_outputs": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, c_p]
+                                 + [C.POINTER(c_p)] * 4),
     "dqo_quadric_init": (C.c_int, [C.c_int32] + [c_p] * 7 + [c_p]),
     "dqo_quadric_project": (C.c_int, [C.c_int32] + [c_p] * 6 + [c_p]),
     "dqo_quadric_refine": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [c_p] * 4

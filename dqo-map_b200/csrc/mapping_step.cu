@@ -1,0 +1,291 @@
+// Fused mapping iteration: one C-ABI call enqueues the whole step of the reference's hot loop
+// (SLAM/multiprocess/mapper.py:568-599 + loss_update :799-928, without the attach term) on one stream, with no host
+// synchronisation and no intermediate tensor owned by the host:
+//
+//   raw parameters --activate--> rasterize forward --> masked L1 colour/depth loss + image gradients
+//                  <-- Adam on the raw parameters <-- activation backward <-- rasterize backward
+//
+// This is SURVEY.md §8f row 1 ("activation + concat fusion") built on top of the parity-checked kernels: the
+// reference's exp / sigmoid / normalize / torch.cat graph (mapper.py:1810-1840, gaussian_pointcloud.py:724-826) and
+// the autograd nodes behind it are replaced by two small kernels, the spherical-harmonics tensors f_dc / f_rest are
+// read in place by the staged loaders (SHMODE 2) and updated in place by an Adam kernel that walks the merged
+// gradient.  The plain operator path (dqo_rast_forward / dqo_rast_backward / dqo_adam_step) stays the parity baseline.
+#include "common.cuh"
+#include <math.h>
+
+namespace dqo {
+int rast_forward_impl(const dqo_rast_settings *s, const float *background, const float *means3D, const float *shs,
+                      const float *f_rest, const float *colors_precomp, const float *opacities, const float *scales,
+                      const float *rotations, const float *cov3D_precomp, const float *viewmatrix,
+                      const float *projmatrix, const float *campos, const int32_t *tile_mask, void *geom_buffer,
+                      void *binning_buffer, int64_t capacity, void *image_buffer, int32_t *tile_indices, float *out_color,
+                      float *out_depth, int32_t *out_hit_depth, int32_t *out_hit_color, float *out_hit_color_weight,
+                      float *out_hit_depth_weight, float *out_T, int32_t *radii, int32_t *n_touched, int32_t *status,
+                      void *stream_);
+int rast_backward_impl(const dqo_rast_settings *s, const float *background, const float *means3D, const float *shs,
+                       const float *f_rest, const float *colors_precomp, const float *scales, const float *rotations,
+                       const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix, const float *campos,
+                       const int32_t *radii, void *geom_buffer, const void *binning_buffer, int64_t capacity,
+                       const void *image_buffer, const int32_t *status, const float *dL_dout_color,
+                       const float *dL_dout_depth, const int32_t *hit_image, float *dL_dmeans2D, float *dL_dconic,
+                       float *dL_dopacity, float *dL_dcolors, float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh,
+                       float *dL_dscales, float *dL_drotations, void *stream_);
+
+struct StepLayout {
+    size_t act_opacity, act_scales, act_rot;                    // activated copies [P], [P,3], [P,4]
+    size_t geom, binning, image;                                // rasterizer workspaces
+    size_t color, depth, hit_depth, hit_color, hit_cw, hit_dw, T, radii, n_touched, tile_indices;
+    size_t g_img, g_depth, loss_ws;                             // loss gradients + reduction scratch
+    size_t g_means3D, g_sh, g_opacity, g_scales, g_rot;         // activated-space parameter gradients
+    size_t total;
+};
+static size_t sbump(size_t &cur, size_t bytes) {
+    size_t off = align_up(cur, 256);
+    cur = off + bytes;
+    return off;
+}
+static int make_step_layout(int P, int M, int W, int H, int64_t capacity, StepLayout *L) {
+    const size_t n = (size_t)(P > 0 ? P : 1), N = (size_t)W * H;
+    const size_t tiles = (size_t)((W + 15) / 16) * ((H + 15) / 16);
+    size_t cur = 0;
+    L->act_opacity = sbump(cur, n * 4);
+    L->act_scales = sbump(cur, n * 12);
+    L->act_rot = sbump(cur, n * 16);
+    const size_t gb = dqo_rast_geom_bytes(P), bb = dqo_rast_binning_bytes(capacity), ib = dqo_rast_image_bytes(W, H);
+    if (!gb || !bb || !ib) return -1;
+    L->geom = sbump(cur, gb);
+    L->binning = sbump(cur, bb);
+    L->image = sbump(cur, ib);
+    L->color = sbump(cur, N * 12);
+    L->depth = sbump(cur, N * 4);
+    L->hit_depth = sbump(cur, N * 4);
+    L->hit_color = sbump(cur, N * 4);
+    L->hit_cw = sbump(cur, N * 4);
+    L->hit_dw = sbump(cur, N * 4);
+    L->T = sbump(cur, N * 4);
+    L->radii = sbump(cur, n * 4);
+    L->n_touched = sbump(cur, n * 4);
+    L->tile_indices = sbump(cur, tiles * 4);
+    L->g_img = sbump(cur, N * 12);
+    L->g_depth = sbump(cur, N * 4);
+    L->loss_ws = sbump(cur, dqo_loss_workspace_bytes(W, H));
+    L->g_means3D = sbump(cur, n * 12);
+    L->g_sh = sbump(cur, n * (size_t)(M > 0 ? M : 1) * 12);
+    L->g_opacity = sbump(cur, n * 4);
+    L->g_scales = sbump(cur, n * 12);
+    L->g_rot = sbump(cur, n * 16);
+    L->total = align_up(cur, 256);
+    return 0;
+}
+
+// exp / sigmoid / normalize of the raw parameters (gaussian_pointcloud.py:20-30: torch.exp, torch.sigmoid,
+// torch.nn.functional.normalize with eps = 1e-12)
+__global__ void __launch_bounds__(256) activate_kernel(int P, const float *__restrict__ opacity_raw,
+                                                       const float *__restrict__ scaling_log,
+                                                       const float *__restrict__ rotation_raw, float *opacity, float *scales,
+                                                       float *rot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    opacity[i] = 1.0f / (1.0f + expf(-opacity_raw[i]));
+#pragma unroll
+    for (int c = 0; c < 3; c++) scales[3 * i + c] = expf(scaling_log[3 * i + c]);
+    const float4 r = reinterpret_cast<const float4 *>(rotation_raw)[i];
+    const float nrm = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
+    const float d = fmaxf(nrm, 1e-12f);
+    reinterpret_cast<float4 *>(rot)[i] = make_float4(r.x / d, r.y / d, r.z / d, r.w / d);
+}
+
+struct AdamScalars {
+    float beta1, beta2, omb1, omb2, bc2_sqrt, eps;
+    float step_size[6]; // xyz, f_dc, f_rest, opacity, scaling, rotation
+};
+__device__ __forceinline__ void adam_update(float &p, float g, float &m, float &v, const AdamScalars &k, float step_size) {
+    m = m + k.omb1 * (g - m);
+    v = v * k.beta2 + k.omb2 * g * g;
+    const float denom = sqrtf(v) / k.bc2_sqrt + k.eps;
+    p = p - step_size * (m / denom);
+}
+
+// Activation backward + Adam for the 11 geometric parameters of a Gaussian, plus the confidence bump
+// (mapper.py:909-910: confidence += 1 where any f_dc gradient is non-zero).
+struct SmallArgs {
+    int P, M;
+    float *xyz, *opacity, *scaling, *rotation;
+    float *m_xyz, *v_xyz, *m_op, *v_op, *m_sc, *v_sc, *m_rot, *v_rot;
+    const float *act_opacity, *act_scales;
+    const float *g_means3D, *g_opacity, *g_scales, *g_rot, *g_sh;
+    float *confidence;
+    AdamScalars k;
+};
+__global__ void __launch_bounds__(256) adam_geometry_kernel(SmallArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.P) return;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int e = 3 * i + c;
+        float p = a.xyz[e], m = a.m_xyz[e], v = a.v_xyz[e];
+        adam_update(p, a.g_means3D[e], m, v, a.k, a.k.step_size[0]);
+        a.xyz[e] = p; a.m_xyz[e] = m; a.v_xyz[e] = v;
+    }
+    { // opacity: o = sigmoid(x), dL/dx = g * o * (1 - o)
+        const float o = a.act_opacity[i];
+        const float g = a.g_opacity[i] * (o * (1.0f - o));
+        float p = a.opacity[i], m = a.m_op[i], v = a.v_op[i];
+        adam_update(p, g, m, v, a.k, a.k.step_size[3]);
+        a.opacity[i] = p; a.m_op[i] = m; a.v_op[i] = v;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) { // scale: s = exp(x), dL/dx = g * s
+        const int e = 3 * i + c;
+        const float g = a.g_scales[e] * a.act_scales[e];
+        float p = a.scaling[e], m = a.m_sc[e], v = a.v_sc[e];
+        adam_update(p, g, m, v, a.k, a.k.step_size[4]);
+        a.scaling[e] = p; a.m_sc[e] = m; a.v_sc[e] = v;
+    }
+    { // rotation: q = r / max(|r|, eps); dL/dr = (g - q (q . g)) / max(|r|, eps)
+        float4 r = reinterpret_cast<float4 *>(a.rotation)[i];
+        const float4 g = reinterpret_cast<const float4 *>(a.g_rot)[i];
+        const float nrm = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
+        const float d = fmaxf(nrm, 1e-12f);
+        const float qx = r.x / d, qy = r.y / d, qz = r.z / d, qw = r.w / d;
+        const float qg = qx * g.x + qy * g.y + qz * g.z + qw * g.w;
+        const float inv = (nrm > 1e-12f) ? 1.0f / d : 0.0f;
+        const float gr[4] = {(g.x - qx * qg) * inv, (g.y - qy * qg) * inv, (g.z - qz * qg) * inv, (g.w - qw * qg) * inv};
+        float pr[4] = {r.x, r.y, r.z, r.w};
+        float4 m4 = reinterpret_cast<float4 *>(a.m_rot)[i], v4 = reinterpret_cast<float4 *>(a.v_rot)[i];
+        float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int c = 0; c < 4; c++) adam_update(pr[c], gr[c], mm[c], vv[c], a.k, a.k.step_size[5]);
+        reinterpret_cast<float4 *>(a.rotation)[i] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+        reinterpret_cast<float4 *>(a.m_rot)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+        reinterpret_cast<float4 *>(a.v_rot)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+    if (a.confidence) {
+        const float *gs = a.g_sh + (size_t)i * a.M * 3;
+        if (fabsf(gs[0]) != 0.f || fabsf(gs[1]) != 0.f || fabsf(gs[2]) != 0.f) a.confidence[i] += 1.0f;
+    }
+}
+
+// Adam for the split SH parameters f_dc [P,3] / f_rest [P,3(M-1)] walking the merged gradient [P,M,3]
+struct ShAdamArgs {
+    long long total; // P * M * 3
+    int row; // M * 3
+    float *f_dc, *f_rest, *m_dc, *v_dc, *m_rest, *v_rest;
+    const float *g_sh;
+    AdamScalars k;
+};
+template <int ROW>
+__global__ void __launch_bounds__(256) adam_sh_kernel(ShAdamArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.total) return;
+    const long long g_idx = i / ROW;
+    const int col = (int)(i - g_idx * ROW);
+    const float g = a.g_sh[i];
+    if (col < 3) {
+        const long long e = g_idx * 3 + col;
+        float p = a.f_dc[e], m = a.m_dc[e], v = a.v_dc[e];
+        adam_update(p, g, m, v, a.k, a.k.step_size[1]);
+        a.f_dc[e] = p; a.m_dc[e] = m; a.v_dc[e] = v;
+    } else {
+        const long long e = g_idx * (ROW - 3) + (col - 3);
+        float p = a.f_rest[e], m = a.m_rest[e], v = a.v_rest[e];
+        adam_update(p, g, m, v, a.k, a.k.step_size[2]);
+        a.f_rest[e] = p; a.m_rest[e] = m; a.v_rest[e] = v;
+    }
+}
+
+} // namespace dqo
+
+using namespace dqo;
+
+extern "C" size_t dqo_mapping_step_workspace_bytes(int32_t P, int32_t M, int32_t W, int32_t H, int64_t capacity) {
+    StepLayout L;
+    if (make_step_layout(P, M, W, H, capacity, &L)) return 0;
+    return L.total;
+}
+
+extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params *p, const dqo_keyframe *kf, int32_t step,
+                                double beta1, double beta2, double eps, void *workspace, int64_t capacity,
+                                float *loss_out, int32_t *counts_out, int32_t *status, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!s || !p || !kf || !workspace || !loss_out || !counts_out || !status || step < 1 || s->P <= 0) {
+        set_error("dqo_mapping_step: invalid argument");
+        return DQO_ERR_INVALID_ARG;
+    }
+    if (!(s->M == 16 || s->M == 1)) {
+        set_error("dqo_mapping_step supports M == 16 (SH degree 3 storage) or M == 1");
+        return DQO_ERR_INVALID_ARG;
+    }
+    for (int t = 0; t < 6; t++)
+        if (!p->param[t] || !p->exp_avg[t] || !p->exp_avg_sq[t]) {
+            if (t == 2 && s->M == 1) continue; // no f_rest at degree 0
+            set_error("dqo_mapping_step: parameter tensor %d or its Adam state is NULL", t);
+            return DQO_ERR_INVALID_ARG;
+        }
+    const int P = s->P, M = s->M, W = s->W, H = s->H;
+    StepLayout L;
+    if (make_step_layout(P, M, W, H, capacity, &L)) return DQO_ERR_WORKSPACE;
+    char *ws = (char *)workspace;
+    float *act_op = (float *)(ws + L.act_opacity), *act_sc = (float *)(ws + L.act_scales), *act_rot = (float *)(ws + L.act_rot);
+    float *xyz = p->param[0], *f_dc = p->param[1], *f_rest = (M == 16) ? p->param[2] : nullptr;
+    const int nb = (P + 255) / 256;
+    activate_kernel<<<nb, 256, 0, stream>>>(P, p->param[3], p->param[4], p->param[5], act_op, act_sc, act_rot);
+    DQO_LAUNCH_CHECK("activate", s->debug, stream);
+
+    float *color = (float *)(ws + L.color), *depth = (float *)(ws + L.depth);
+    int32_t *hit_depth = (int32_t *)(ws + L.hit_depth), *radii = (int32_t *)(ws + L.radii);
+    int rc = rast_forward_impl(s, kf->background, xyz, f_dc, f_rest, nullptr, act_op, act_sc, act_rot, nullptr, kf->viewmatrix,
+                               kf->projmatrix, kf->campos, kf->tile_mask, ws + L.geom, ws + L.binning, capacity,
+                               ws + L.image, (int32_t *)(ws + L.tile_indices), color, depth, hit_depth,
+                               (int32_t *)(ws + L.hit_color), (float *)(ws + L.hit_cw), (float *)(ws + L.hit_dw),
+                               (float *)(ws + L.T), radii, (int32_t *)(ws + L.n_touched), status, stream_);
+    if (rc) return rc;
+    float *g_img = (float *)(ws + L.g_img), *g_depth = (float *)(ws + L.g_depth);
+    rc = dqo_masked_l1_loss(W, H, color, depth, hit_depth, kf->gt_color, kf->gt_depth, kf->render_mask, kf->color_weight,
+                            kf->depth_weight, kf->depth_err_thres, g_img, g_depth, loss_out, counts_out, ws + L.loss_ws,
+                            stream_);
+    if (rc) return rc;
+    float *g_means3D = (float *)(ws + L.g_means3D), *g_sh = (float *)(ws + L.g_sh), *g_op = (float *)(ws + L.g_opacity);
+    float *g_sc = (float *)(ws + L.g_scales), *g_rot = (float *)(ws + L.g_rot);
+    rc = rast_backward_impl(s, kf->background, xyz, f_dc, f_rest, nullptr, act_sc, act_rot, nullptr, kf->viewmatrix,
+                            kf->projmatrix, kf->campos, radii, ws + L.geom, ws + L.binning, capacity, ws + L.image, status,
+                            g_img, g_depth, hit_depth, nullptr, nullptr, g_op, nullptr, g_means3D, nullptr, g_sh, g_sc,
+                            g_rot, stream_);
+    if (rc) return rc;
+
+    AdamScalars k;
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    k.beta1 = (float)beta1; k.beta2 = (float)beta2; k.omb1 = (float)(1.0 - beta1); k.omb2 = (float)(1.0 - beta2);
+    k.bc2_sqrt = (float)sqrt(bc2); k.eps = (float)eps;
+    for (int t = 0; t < 6; t++) k.step_size[t] = (float)(p->lr[t] / bc1);
+    SmallArgs sa;
+    sa.P = P; sa.M = M; sa.xyz = xyz; sa.opacity = p->param[3]; sa.scaling = p->param[4]; sa.rotation = p->param[5];
+    sa.m_xyz = p->exp_avg[0]; sa.v_xyz = p->exp_avg_sq[0]; sa.m_op = p->exp_avg[3]; sa.v_op = p->exp_avg_sq[3];
+    sa.m_sc = p->exp_avg[4]; sa.v_sc = p->exp_avg_sq[4]; sa.m_rot = p->exp_avg[5]; sa.v_rot = p->exp_avg_sq[5];
+    sa.act_opacity = act_op; sa.act_scales = act_sc; sa.g_means3D = g_means3D; sa.g_opacity = g_op; sa.g_scales = g_sc;
+    sa.g_rot = g_rot; sa.g_sh = g_sh; sa.confidence = p->confidence; sa.k = k;
+    adam_geometry_kernel<<<nb, 256, 0, stream>>>(sa);
+    DQO_LAUNCH_CHECK("adam geometry", s->debug, stream);
+    ShAdamArgs sh;
+    sh.total = (long long)P * M * 3; sh.row = M * 3; sh.f_dc = f_dc; sh.f_rest = f_rest; sh.m_dc = p->exp_avg[1];
+    sh.v_dc = p->exp_avg_sq[1]; sh.m_rest = p->exp_avg[2]; sh.v_rest = p->exp_avg_sq[2]; sh.g_sh = g_sh; sh.k = k;
+    if (M == 16)
+        adam_sh_kernel<48><<<(unsigned)((sh.total + 255) / 256), 256, 0, stream>>>(sh);
+    else
+        adam_sh_kernel<3><<<(unsigned)((sh.total + 255) / 256), 256, 0, stream>>>(sh);
+    DQO_LAUNCH_CHECK("adam sh", s->debug, stream);
+    return DQO_OK;
+}
+
+// Read-only views into the step workspace for callers that want the rendered images of the last step
+extern "C" int dqo_mapping_step_outputs(int32_t P, int32_t M, int32_t W, int32_t H, int64_t capacity, void *workspace,
+                                        float **color, float **depth, int32_t **hit_depth, float **T_map) {
+    StepLayout L;
+    if (!workspace || make_step_layout(P, M, W, H, capacity, &L)) return DQO_ERR_WORKSPACE;
+    char *ws = (char *)workspace;
+    if (color) *color = (float *)(ws + L.color);
+    if (depth) *depth = (float *)(ws + L.depth);
+    if (hit_depth) *hit_depth = (int32_t *)(ws + L.hit_depth);
+    if (T_map) *T_map = (float *)(ws + L.T);
+    return DQO_OK;
+}

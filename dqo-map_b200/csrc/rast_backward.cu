@@ -311,6 +311,7 @@ struct GaussBwdArgs {
     int P, D, M;
     float scale_modifier, tanfovx, tanfovy, focal_x, focal_y;
     const float *means3D, *scales, *rotations, *shs, *cov3D_precomp;
+    const float *f_rest; // split-SH mode: shs = f_dc [P,3], f_rest [P,45]
     const float *view, *proj, *campos;
     const int *radii;
     const uint8_t *clamped;
@@ -331,15 +332,34 @@ __device__ __constant__ float B_SH_C3[7] = {-0.5900435899266435f, 2.890611442640
 
 // STAGED (M == 16, 16-byte aligned shs / dL_dsh): each warp moves its 32 x 192 B of SH coefficients in and its
 // 32 x 192 B of SH gradients out with coalesced 128-bit accesses through a padded shared-memory tile.
-template <bool STAGED>
+// SHMODE 1: staged merged SH, 2: staged split f_dc / f_rest inputs (gradients are still written merged), 0: plain.
+template <int SHMODE>
 __global__ void __launch_bounds__(GB_THREADS) gaussian_backward_kernel(GaussBwdArgs a) {
     extern __shared__ float4 s_row[];
+    constexpr bool STAGED = SHMODE != 0;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 *wbuf = s_row + warp * 32 * GB_ROW_Q;
+    float *wrest = reinterpret_cast<float *>(wbuf), *wdc = wrest + 1440;
     const int base_g = blockIdx.x * blockDim.x + warp * 32;
     const int nrow = min(32, a.P - base_g);
-    if (STAGED && nrow > 0) {
+    if (SHMODE == 2 && nrow > 0) {
+        if (nrow == 32) {
+            const float4 *g4 = reinterpret_cast<const float4 *>(a.f_rest + (size_t)base_g * 45);
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const int q = i * 32 + lane;
+                if (q < 360) wbuf[q] = __ldg(g4 + q);
+            }
+            const float4 *gd4 = reinterpret_cast<const float4 *>(a.shs + (size_t)base_g * 3);
+            if (lane < 24) reinterpret_cast<float4 *>(wdc)[lane] = __ldg(gd4 + lane);
+        } else {
+            for (int q = lane; q < nrow * 45; q += 32) wrest[q] = a.f_rest[(size_t)base_g * 45 + q];
+            for (int q = lane; q < nrow * 3; q += 32) wdc[q] = a.shs[(size_t)base_g * 3 + q];
+        }
+        __syncwarp();
+    }
+    if (SHMODE == 1 && nrow > 0) {
         const float4 *gsh = reinterpret_cast<const float4 *>(a.shs) + (size_t)base_g * 12;
         const int nq = nrow * 12;
 #pragma unroll
@@ -482,12 +502,17 @@ __global__ void __launch_bounds__(GB_THREADS) gaussian_backward_kernel(GaussBwdA
         // ---- colour -> SH (+ view direction -> mean) (backward.cu:152-268) ----
         if (a.shs) {
             float sh[48];
-            if (STAGED) {
+            if (SHMODE == 1) {
 #pragma unroll
                 for (int i = 0; i < 12; i++) {
                     const float4 t = wbuf[lane * GB_ROW_Q + i];
                     sh[4 * i] = t.x; sh[4 * i + 1] = t.y; sh[4 * i + 2] = t.z; sh[4 * i + 3] = t.w;
                 }
+            } else if (SHMODE == 2) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) sh[c] = wdc[lane * 3 + c];
+#pragma unroll
+                for (int k = 0; k < 45; k++) sh[3 + k] = wrest[lane * 45 + k];
             } else {
                 const float *gp = a.shs + (size_t)idx * M * 3;
                 const int nload = (a.D + 1) * (a.D + 1) * 3;
@@ -666,8 +691,35 @@ __global__ void __launch_bounds__(GB_THREADS) gaussian_backward_kernel(GaussBwdA
 
 using namespace dqo;
 
+namespace dqo {
+int rast_backward_impl(const dqo_rast_settings *s, const float *background, const float *means3D, const float *shs,
+                       const float *f_rest, const float *colors_precomp, const float *scales, const float *rotations,
+                       const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix, const float *campos,
+                       const int32_t *radii, void *geom_buffer, const void *binning_buffer, int64_t capacity,
+                       const void *image_buffer, const int32_t *status, const float *dL_dout_color,
+                       const float *dL_dout_depth, const int32_t *hit_image, float *dL_dmeans2D, float *dL_dconic,
+                       float *dL_dopacity, float *dL_dcolors, float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh,
+                       float *dL_dscales, float *dL_drotations, void *stream_);
+}
+
 extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *background, const float *means3D,
                                  const float *shs, const float *colors_precomp, const float *scales,
+                                 const float *rotations, const float *cov3D_precomp, const float *viewmatrix,
+                                 const float *projmatrix, const float *campos, const int32_t *radii,
+                                 void *geom_buffer, const void *binning_buffer, int64_t capacity,
+                                 const void *image_buffer, const int32_t *status, const float *dL_dout_color,
+                                 const float *dL_dout_depth, const int32_t *hit_image, float *dL_dmeans2D,
+                                 float *dL_dconic, float *dL_dopacity, float *dL_dcolors, float *dL_dmeans3D,
+                                 float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
+                                 void *stream_) {
+    return rast_backward_impl(s, background, means3D, shs, nullptr, colors_precomp, scales, rotations, cov3D_precomp,
+                              viewmatrix, projmatrix, campos, radii, geom_buffer, binning_buffer, capacity, image_buffer,
+                              status, dL_dout_color, dL_dout_depth, hit_image, dL_dmeans2D, dL_dconic, dL_dopacity,
+                              dL_dcolors, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, stream_);
+}
+
+int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background, const float *means3D,
+                                 const float *shs, const float *f_rest, const float *colors_precomp, const float *scales,
                                  const float *rotations, const float *cov3D_precomp, const float *viewmatrix,
                                  const float *projmatrix, const float *campos, const int32_t *radii,
                                  void *geom_buffer, const void *binning_buffer, int64_t capacity,
@@ -729,19 +781,26 @@ extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *backgr
     ga.P = P; ga.D = s->D; ga.M = s->M;
     ga.scale_modifier = s->scale_modifier; ga.tanfovx = s->tanfovx; ga.tanfovy = s->tanfovy;
     ga.focal_x = focal_x; ga.focal_y = focal_y;
-    ga.means3D = means3D; ga.scales = scales; ga.rotations = rotations; ga.shs = shs; ga.cov3D_precomp = cov3D_precomp;
+    ga.means3D = means3D; ga.scales = scales; ga.rotations = rotations; ga.shs = shs; ga.f_rest = f_rest; ga.cov3D_precomp = cov3D_precomp;
     ga.view = viewmatrix; ga.proj = projmatrix; ga.campos = campos; ga.radii = radii;
     ga.clamped = (const uint8_t *)(geom + GL.clamped);
     ga.gacc = gacc;
     ga.dL_dmeans2D = dL_dmeans2D; ga.dL_dconic = dL_dconic; ga.dL_dopacity = dL_dopacity; ga.dL_dcolors = dL_dcolors;
     ga.dL_dmeans3D = dL_dmeans3D; ga.dL_dcov3D = dL_dcov3D; ga.dL_dsh = (s->M > 0) ? dL_dsh : nullptr;
     ga.dL_dscales = dL_dscales; ga.dL_drot = dL_drotations;
-    const bool staged = shs && dL_dsh && s->M == 16 && ((uintptr_t)shs % 16 == 0) && ((uintptr_t)dL_dsh % 16 == 0);
+    const bool staged = shs && !f_rest && dL_dsh && s->M == 16 && ((uintptr_t)shs % 16 == 0) && ((uintptr_t)dL_dsh % 16 == 0);
     const int gb_blocks = (P + GB_THREADS - 1) / GB_THREADS;
-    if (staged)
-        gaussian_backward_kernel<true><<<gb_blocks, GB_THREADS, (size_t)(GB_THREADS / 32) * 32 * GB_ROW_Q * sizeof(float4), stream>>>(ga);
+    const size_t gb_smem = (size_t)(GB_THREADS / 32) * 32 * GB_ROW_Q * sizeof(float4);
+    if (f_rest) {
+        if (s->M != 16 || !dL_dsh || (uintptr_t)shs % 16 || (uintptr_t)f_rest % 16 || (uintptr_t)dL_dsh % 16) {
+            set_error("split SH input requires M == 16 and 16-byte aligned f_dc / f_rest / dL_dsh");
+            return DQO_ERR_INVALID_ARG;
+        }
+        gaussian_backward_kernel<2><<<gb_blocks, GB_THREADS, gb_smem, stream>>>(ga);
+    } else if (staged)
+        gaussian_backward_kernel<1><<<gb_blocks, GB_THREADS, gb_smem, stream>>>(ga);
     else
-        gaussian_backward_kernel<false><<<gb_blocks, GB_THREADS, 0, stream>>>(ga);
+        gaussian_backward_kernel<0><<<gb_blocks, GB_THREADS, 0, stream>>>(ga);
     DQO_LAUNCH_CHECK("gaussian backward", s->debug, stream);
     stage_mark(stream, ST_GAUSS_BWD);
     return DQO_OK;

@@ -116,6 +116,7 @@ struct PreArgs {
     int grid_x, grid_y;
     int prefiltered;
     const float *means3D, *scales, *rotations, *opacities, *shs, *cov3D_precomp, *colors_precomp;
+    const float *f_rest; // split-SH mode: shs = f_dc [P,3], f_rest [P,45]
     const float *view, *proj, *campos;
     const uint32_t *mask_bits;
     int mask_words;
@@ -241,14 +242,36 @@ struct ShPtr {
 #define PRE_THREADS 128
 #define SH_ROW_Q 13 // float4 per staged SH row (12 used + 1 pad: conflict-free for both access patterns)
 
-// STAGED: M == 16 and 16-byte aligned SH — each warp pulls its 32 x 192 B of coefficients with coalesced 128-bit
-// loads through shared memory instead of 32 strided streams.
-template <bool STAGED>
+// SHMODE 1 (M == 16, 16-byte aligned SH): each warp pulls its 32 x 192 B of coefficients with coalesced 128-bit loads
+// through shared memory instead of 32 strided streams.  SHMODE 2: the same for the reference's split parameter
+// tensors f_dc [P,1,3] / f_rest [P,15,3] (GaussianPointCloud.get_features' torch.cat is never materialised); the
+// 45-float rows of f_rest are conflict-free for per-thread scalar reads as they lie.  SHMODE 0: plain pointer.
+template <int SHMODE>
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
     extern __shared__ float4 s_sh[];
+    constexpr bool STAGED = SHMODE == 1;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 *wbuf = s_sh + warp * 32 * SH_ROW_Q;
+    float *wrest = reinterpret_cast<float *>(wbuf), *wdc = wrest + 1440;
+    if (SHMODE == 2) {
+        const int base_g = blockIdx.x * blockDim.x + warp * 32;
+        const int nrow = min(32, a.P - base_g);
+        if (nrow == 32) {
+            const float4 *g = reinterpret_cast<const float4 *>(a.f_rest + (size_t)base_g * 45);
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const int q = i * 32 + lane;
+                if (q < 360) wbuf[q] = __ldg(g + q);
+            }
+            const float4 *gd = reinterpret_cast<const float4 *>(a.shs + (size_t)base_g * 3);
+            if (lane < 24) reinterpret_cast<float4 *>(wdc)[lane] = __ldg(gd + lane);
+        } else if (nrow > 0) {
+            for (int q = lane; q < nrow * 45; q += 32) wrest[q] = a.f_rest[(size_t)base_g * 45 + q];
+            for (int q = lane; q < nrow * 3; q += 32) wdc[q] = a.shs[(size_t)base_g * 3 + q];
+        }
+        __syncwarp();
+    }
     if (STAGED) {
         const int base_g = blockIdx.x * blockDim.x + warp * 32;
         const int nrow = min(32, a.P - base_g);
@@ -353,6 +376,13 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
                             const float4 t = wbuf[lane * SH_ROW_Q + i];
                             sh.v[4 * i] = t.x; sh.v[4 * i + 1] = t.y; sh.v[4 * i + 2] = t.z; sh.v[4 * i + 3] = t.w;
                         }
+                        rgb = sh_to_rgb(a.D, sh, make_float3(px, py, pz), cam, &cl);
+                    } else if (SHMODE == 2) {
+                        ShRegs sh;
+#pragma unroll
+                        for (int c = 0; c < 3; c++) sh.v[c] = wdc[lane * 3 + c];
+#pragma unroll
+                        for (int k = 0; k < 45; k++) sh.v[3 + k] = wrest[lane * 45 + k];
                         rgb = sh_to_rgb(a.D, sh, make_float3(px, py, pz), cam, &cl);
                     } else {
                         rgb = sh_to_rgb(a.D, ShPtr{a.shs + (size_t)idx * a.M * 3}, make_float3(px, py, pz), cam, &cl);
@@ -836,8 +866,34 @@ extern "C" int dqo_mark_visible(int32_t P, const float *means3D, const float *vi
     return DQO_OK;
 }
 
+namespace dqo {
+int rast_forward_impl(const dqo_rast_settings *s, const float *background, const float *means3D, const float *shs,
+                      const float *f_rest, const float *colors_precomp, const float *opacities, const float *scales,
+                      const float *rotations, const float *cov3D_precomp, const float *viewmatrix,
+                      const float *projmatrix, const float *campos, const int32_t *tile_mask, void *geom_buffer,
+                      void *binning_buffer, int64_t capacity, void *image_buffer, int32_t *tile_indices, float *out_color,
+                      float *out_depth, int32_t *out_hit_depth, int32_t *out_hit_color, float *out_hit_color_weight,
+                      float *out_hit_depth_weight, float *out_T, int32_t *radii, int32_t *n_touched, int32_t *status,
+                      void *stream_);
+}
+
 extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *background, const float *means3D,
                                 const float *shs, const float *colors_precomp, const float *opacities,
+                                const float *scales, const float *rotations, const float *cov3D_precomp,
+                                const float *viewmatrix, const float *projmatrix, const float *campos,
+                                const int32_t *tile_mask, void *geom_buffer, void *binning_buffer,
+                                int64_t capacity, void *image_buffer, int32_t *tile_indices, float *out_color,
+                                float *out_depth, int32_t *out_hit_depth, int32_t *out_hit_color,
+                                float *out_hit_color_weight, float *out_hit_depth_weight, float *out_T, int32_t *radii,
+                                int32_t *n_touched, int32_t *status, void *stream_) {
+    return rast_forward_impl(s, background, means3D, shs, nullptr, colors_precomp, opacities, scales, rotations,
+                             cov3D_precomp, viewmatrix, projmatrix, campos, tile_mask, geom_buffer, binning_buffer,
+                             capacity, image_buffer, tile_indices, out_color, out_depth, out_hit_depth, out_hit_color,
+                             out_hit_color_weight, out_hit_depth_weight, out_T, radii, n_touched, status, stream_);
+}
+
+int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, const float *means3D,
+                                const float *shs, const float *f_rest, const float *colors_precomp, const float *opacities,
                                 const float *scales, const float *rotations, const float *cov3D_precomp,
                                 const float *viewmatrix, const float *projmatrix, const float *campos,
                                 const int32_t *tile_mask, void *geom_buffer, void *binning_buffer,
@@ -916,7 +972,7 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
         pa.cx = s->cx; pa.cy = s->cy; pa.grid_x = IL.tiles_x; pa.grid_y = IL.tiles_y;
         pa.prefiltered = s->prefiltered;
         pa.means3D = means3D; pa.scales = scales; pa.rotations = rotations; pa.opacities = opacities;
-        pa.shs = shs; pa.cov3D_precomp = cov3D_precomp; pa.colors_precomp = colors_precomp;
+        pa.shs = shs; pa.f_rest = f_rest; pa.cov3D_precomp = cov3D_precomp; pa.colors_precomp = colors_precomp;
         pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
         pa.mask_bits = mask_bits; pa.mask_words = IL.mask_words;
         pa.radii = radii; pa.n_touched = n_touched;
@@ -930,13 +986,19 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
         pa.status = status;
         rec = pa.rec;
         depth = pa.depth;
-        const bool staged = shs && s->M == 16 && ((uintptr_t)shs % 16 == 0);
+        const bool staged = shs && !f_rest && s->M == 16 && ((uintptr_t)shs % 16 == 0);
         const int pre_blocks = (P + PRE_THREADS - 1) / PRE_THREADS;
-        if (staged) {
-            const size_t smem = (size_t)(PRE_THREADS / 32) * 32 * SH_ROW_Q * sizeof(float4);
-            preprocess_kernel<true><<<pre_blocks, PRE_THREADS, smem, stream>>>(pa);
+        const size_t smem = (size_t)(PRE_THREADS / 32) * 32 * SH_ROW_Q * sizeof(float4);
+        if (f_rest) {
+            if (s->M != 16 || (uintptr_t)shs % 16 || (uintptr_t)f_rest % 16) {
+                set_error("split SH input requires M == 16 and 16-byte aligned f_dc / f_rest");
+                return DQO_ERR_INVALID_ARG;
+            }
+            preprocess_kernel<2><<<pre_blocks, PRE_THREADS, smem, stream>>>(pa);
+        } else if (staged) {
+            preprocess_kernel<1><<<pre_blocks, PRE_THREADS, smem, stream>>>(pa);
         } else {
-            preprocess_kernel<false><<<pre_blocks, PRE_THREADS, 0, stream>>>(pa);
+            preprocess_kernel<0><<<pre_blocks, PRE_THREADS, 0, stream>>>(pa);
         }
         DQO_LAUNCH_CHECK("preprocess", debug, stream);
         stage_mark(stream, ST_PREPROCESS);

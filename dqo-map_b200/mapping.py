@@ -156,3 +156,99 @@ class MappingStep:
             self.confidence[grad_mask.view(-1)] += 1
         self.opt.zero_grad(set_to_none=True)
         return total.detach(), lc.detach(), ld.detach()
+
+
+class FusedMappingStep:
+    """The same iteration as `MappingStep`, enqueued by ONE C-ABI call (`dqo_mapping_step`) with no host
+    synchronisation: activations, rasterize forward, masked L1 loss, backward, activation backward and Adam all run
+    inside the library on the raw parameter tensors, which are updated in place (opt-in).
+
+    params: dict of raw contiguous float32 CUDA tensors xyz [P,3], f_dc [P,1,3], f_rest [P,M-1,3], opacity [P,1],
+    scaling [P,3], rotation [P,4] (the tensors of GaussianPointCloud.parametrize); lrs: dict name -> lr.
+    `__call__` returns device tensors (total, colour, depth loss); reading them is the only synchronisation.
+    `check()` raises if the instance capacity was exceeded in the last step."""
+
+    ORDER = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")
+
+    def __init__(self, params, lrs, width, height, color_weight=0.8, depth_weight=1.0, depth_err_thres=0.1,
+                 confidence=None, betas=(0.9, 0.999), eps=1e-15, capacity=None, need_n_touched=True):
+        L = lib()
+        self.p = params
+        for k in self.ORDER:
+            t = params[k]
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError("FusedMappingStep expects contiguous float32 CUDA tensors (%s)" % k)
+        self.dev = params["xyz"].device
+        self.P = params["xyz"].shape[0]
+        self.M = 1 + (params["f_rest"].shape[1] if params["f_rest"].numel() else 0)
+        if self.M not in (1, 16):
+            raise ValueError("FusedMappingStep supports SH storage of 1 or 16 coefficients per channel")
+        self.W, self.H = int(width), int(height)
+        self.lrs = [float(lrs[k]) for k in self.ORDER]
+        self.betas, self.eps = betas, eps
+        self.cw, self.dw, self.thr = float(color_weight), float(depth_weight), float(depth_err_thres)
+        self.confidence = confidence
+        self.need_n_touched = need_n_touched
+        self.state = {k: (torch.zeros_like(params[k]), torch.zeros_like(params[k])) for k in self.ORDER}
+        self.step = 0
+        self.capacity = int(capacity) if capacity else max(8 * self.P, 1 << 16)
+        self._alloc()
+        self.loss = torch.zeros(4, dtype=torch.float32, device=self.dev)
+        self.counts = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        self.status = torch.zeros(_lib.ST_WORDS, dtype=torch.int32, device=self.dev)
+
+    def _alloc(self):
+        n = lib().dqo_mapping_step_workspace_bytes(self.P, self.M, self.W, self.H, self.capacity)
+        if n == 0:
+            raise _lib.DqoError("workspace size query failed: %s" % lib().dqo_last_error().decode())
+        self.ws = torch.empty((n,), dtype=torch.uint8, device=self.dev)
+
+    def __call__(self, rs, tile_mask, gt_color, gt_depth, render_mask=None):
+        """rs: GaussianRasterizationSettings of the keyframe (as built by SLAM/render.py:142-162)."""
+        from .rasterizer import _make_settings
+        mp = _lib.MapParams()
+        for i, k in enumerate(self.ORDER):
+            t = self.p[k]
+            mp.param[i] = ptr(t)
+            mp.exp_avg[i] = ptr(self.state[k][0])
+            mp.exp_avg_sq[i] = ptr(self.state[k][1])
+            mp.lr[i] = self.lrs[i]
+        mp.confidence = ptr(self.confidence)
+        mask = None
+        if render_mask is not None:
+            mask = render_mask if render_mask.dtype == torch.uint8 else render_mask.view(torch.uint8) \
+                if render_mask.dtype == torch.bool else (render_mask != 0).view(torch.uint8)
+            mask = mask.contiguous()
+        kf = _lib.Keyframe(ptr(gt_color.contiguous()), ptr(gt_depth.contiguous()), ptr(mask), ptr(tile_mask.contiguous()),
+                           ptr(rs.viewmatrix), ptr(rs.projmatrix), ptr(rs.campos), ptr(rs.bg), self.cw, self.dw, self.thr)
+        s = _make_settings(self.P, int(rs.sh_degree), self.M, self.W, self.H, rs.tanfovx, rs.tanfovy, rs.cx, rs.cy,
+                           rs.scale_modifier, rs.color_sigma, rs.opaque_threshold, rs.depth_threshold,
+                           rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, self.need_n_touched)
+        self.step += 1
+        with torch.cuda.device(self.dev):
+            check(lib().dqo_mapping_step(s, mp, kf, self.step, float(self.betas[0]), float(self.betas[1]),
+                                         float(self.eps), ptr(self.ws), self.capacity, ptr(self.loss), ptr(self.counts),
+                                         ptr(self.status), _stream()), "dqo_mapping_step")
+        return self.loss[0], self.loss[1], self.loss[2]
+
+    def check(self):
+        host = self.status.tolist()
+        if host[_lib.ST_OVERFLOW]:
+            raise _lib.DqoError("instance capacity %d exceeded (R = %d)" % (self.capacity, host[_lib.ST_NUM_RENDERED]))
+        return host
+
+    def rendered(self):
+        """Views (no copy) of the colour [3,H,W], depth [1,H,W], depth index [1,H,W] and T [1,H,W] of the last step."""
+        import ctypes as C
+        outs = [C.c_void_p() for _ in range(4)]
+        check(lib().dqo_mapping_step_outputs(self.P, self.M, self.W, self.H, self.capacity, ptr(self.ws),
+                                             *[C.byref(o) for o in outs]), "dqo_mapping_step_outputs")
+        base = self.ws.data_ptr()
+        H, W = self.H, self.W
+
+        def view(o, n, dtype, shape):
+            off = o.value - base
+            return self.ws[off:off + n * 4].view(dtype).view(shape)
+
+        return (view(outs[0], 3 * H * W, torch.float32, (3, H, W)), view(outs[1], H * W, torch.float32, (1, H, W)),
+                view(outs[2], H * W, torch.int32, (1, H, W)), view(outs[3], H * W, torch.float32, (1, H, W)))

@@ -202,6 +202,42 @@ int dqo_adam_step(const dqo_adam_tensor *tensors /* host array */, int32_t n_ten
                   double beta2, double eps, float *confidence /* [P] or NULL */, int32_t conf_tensor, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused mapping iteration (opt-in).  One call enqueues, on one stream and without any host
+ * synchronisation, what one iteration of Mapping.local_optimize does (SLAM/multiprocess/mapper.py:568-599 and
+ * loss_update :799-928 without the attach term): activations of the RAW parameters (exp / sigmoid / normalize,
+ * SLAM/gaussian_pointcloud.py:20-30, 724-826; the torch.cat of f_dc / f_rest is never materialised), rasterize
+ * forward, masked L1 colour + depth loss, rasterize backward, activation backward and Adam (eps / betas / lrs as in
+ * GaussianPointCloud.parametrize :331-378) on the raw parameters in place, plus the confidence bump (:909-910).
+ * Parameter order everywhere: 0 xyz [P,3], 1 f_dc [P,1,3], 2 f_rest [P,M-1,3], 3 opacity [P,1], 4 scaling [P,3],
+ * 5 rotation [P,4].  M must be 16 (f_dc + f_rest) or 1 (f_dc only).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dqo_map_params {
+    float *param[6];
+    float *exp_avg[6];
+    float *exp_avg_sq[6];
+    double lr[6];
+    float *confidence; /* [P] or NULL */
+} dqo_map_params;
+typedef struct dqo_keyframe {
+    const float *gt_color;      /* [H,W,3] */
+    const float *gt_depth;      /* [H,W] */
+    const uint8_t *render_mask; /* [H,W] or NULL */
+    const int32_t *tile_mask;   /* [ceil(H/16), ceil(W/16)] */
+    const float *viewmatrix, *projmatrix, *campos, *background;
+    float color_weight, depth_weight, depth_err_thres;
+} dqo_keyframe;
+size_t dqo_mapping_step_workspace_bytes(int32_t P, int32_t M, int32_t W, int32_t H, int64_t instance_capacity);
+/* loss_out: device float[4] {total, colour, depth, -}; counts_out: device int32[2]; status: device int32[DQO_ST_WORDS]
+ * (check DQO_ST_OVERFLOW together with the loss read-back; on overflow the parameters were still stepped with zero
+ * image gradients from an empty render, so callers size the capacity with a margin: see mapping.FusedMappingStep). */
+int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params *p, const dqo_keyframe *kf, int32_t step,
+                     double beta1, double beta2, double eps, void *workspace, int64_t instance_capacity,
+                     float *loss_out, int32_t *counts_out, int32_t *status, void *stream);
+/* Device pointers of the images rendered by the last step inside `workspace` (any output may be NULL). */
+int dqo_mapping_step_outputs(int32_t P, int32_t M, int32_t W, int32_t H, int64_t instance_capacity, void *workspace,
+                             float **color, float **depth, int32_t **hit_depth, float **T_map);
+
+/* ------------------------------------------------------------------------------------------------
  * Dual quadrics (SLAM/multiprocess/quadrics.py).  Batched over objects.
  *   dqo_quadric_init   : Object.__init__ single-view construction (quadrics.py:451-487)
  *   dqo_quadric_project: Ellipsoid.project + Ellipse.ComputeBbox (quadrics.py:388-425,148-248) in fp64

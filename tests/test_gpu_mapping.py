@@ -93,6 +93,60 @@ def _loop(raw, settings, tile_mask, gt_color, gt_depth, render_mask, iters, mode
     return psnr(out[0], gt_color.permute(2, 0, 1)), dl1, conf, params
 
 
+def _fused_c_loop(raw, settings, tile_mask, gt_color, gt_depth, render_mask, iters, W, H):
+    """The single-call fused step (dqo_mapping_step) on the raw parameters."""
+    params = {k: v.clone().contiguous() for k, v in raw.items()}
+    conf = torch.zeros(params["xyz"].shape[0], 1, device=DEV)
+    step = mapping.FusedMappingStep(params, LRS, W, H, 0.8, 1.0, 0.1, confidence=conf)
+    rs = settings()
+    for _ in range(iters):
+        step(rs, tile_mask, gt_color, gt_depth, render_mask)
+    step.check()
+    return params, conf, step
+
+
+def test_fused_c_step_matches_operator_path_single_step():
+    gt, cam, settings, raw, gt_color, gt_depth, render_mask = _scene(P=4000, deg=3)
+    H, W = cam.image_height, cam.image_width
+    params_c, conf_c, step = _fused_c_loop(raw, settings, gt["tile_mask"], gt_color, gt_depth, render_mask, 1, W, H)
+    # operator path: torch activations + autograd + C-ABI rasterizer / loss / Adam
+    params_t = {k: torch.nn.Parameter(v.clone()) for k, v in raw.items()}
+    conf_t = torch.zeros(params_t["xyz"].shape[0], 1, device=DEV)
+    ms = mapping.MappingStep(params_t, LRS, settings, 0.8, 1.0, 0.1, confidence=conf_t, optimizer="fused")
+    total_t, lc_t, ld_t = ms(None, gt["tile_mask"], gt_color, gt_depth, render_mask)
+    assert abs(float(step.loss[0]) - float(total_t)) <= 1e-5 * max(1.0, abs(float(total_t)))
+    for k in params_c:
+        a, b = params_c[k], params_t[k].detach()
+        # first Adam step moves every parameter with a non-zero gradient by exactly lr: compare the moved sets and values
+        assert float((a - b).abs().max()) <= 2.5 * LRS[k] * 1e-3 + 1e-7 or float(((a - b).abs() > 1e-6).float().mean()) < 2e-3, k
+    assert float((conf_c - conf_t).abs().max()) <= 1.0 and float((conf_c != conf_t).float().mean()) < 1e-3
+    color, depth, hit, T = step.rendered()
+    assert color.shape == (3, H, W) and bool(torch.isfinite(color).all())
+
+
+def test_fused_c_step_loop_quality():
+    gt, cam, settings, raw, gt_color, gt_depth, render_mask = _scene()
+    H, W = cam.image_height, cam.image_width
+    args = (raw, settings, gt["tile_mask"], gt_color, gt_depth, render_mask)
+    stock = [_loop(*args, 200, "ours_torch") for _ in range(3)]
+
+    def run():
+        params_c, _, _ = _fused_c_loop(*args, 200, W, H)
+        with torch.no_grad():
+            out = rasterizer.GaussianRasterizer(settings())(
+                means3D=params_c["xyz"], opacities=torch.sigmoid(params_c["opacity"]),
+                shs=torch.cat((params_c["f_dc"], params_c["f_rest"]), dim=1), scales=torch.exp(params_c["scaling"]),
+                rotations=torch.nn.functional.normalize(params_c["rotation"]), tile_mask=gt["tile_mask"])
+        hit = (out[3] != -1) & (gt_depth.permute(2, 0, 1) > 0)
+        return psnr(out[0], gt_color.permute(2, 0, 1)), float((out[1] - gt_depth.permute(2, 0, 1)).abs()[hit].mean())
+
+    fused = [run() for _ in range(3)]
+    ok, tol = _gate([r[0] for r in fused], [r[0] for r in stock], 0.0, 0.1)
+    assert ok, ([r[0] for r in fused], [r[0] for r in stock], tol)
+    ok, tol = _gate([r[1] for r in fused], [r[1] for r in stock], 0.01, 0.0)
+    assert ok, ([r[1] for r in fused], [r[1] for r in stock], tol)
+
+
 def _spread(vals):
     return max(vals) - min(vals)
 
