@@ -238,7 +238,7 @@ def main():
             pipe.forward(rs, inp["xyz"], inp["opacity"], inp["scales"], inp["rotations"], inp["tile_mask"], shs=inp["shs"])
             pipe.backward(gc, gd)
             if dist_on:
-                sharding.gather_object_table(obj_table)
+                sharding.gather_object_table(obj_table, rows_per_rank=1)
 
         # operator path (autograd wrapper + torch activations), kept as a second e2e figure
         params = {k: torch.nn.Parameter(v) for k, v in raw_params(inp).items()}
@@ -250,7 +250,7 @@ def main():
                 d.copy_(h, non_blocking=True)
             total, _, _ = step_obj(None, inp["tile_mask"], dev_kf[0], dev_kf[1], dev_kf[2])
             if dist_on:
-                sharding.gather_object_table(obj_table)
+                sharding.gather_object_table(obj_table, rows_per_rank=1)
             return float(total)  # D2H read of the loss
 
         # headline e2e: the fused mapping step (one C-ABI call per iteration); the keyframe of step k+1 is copied from
@@ -278,7 +278,7 @@ def main():
             total, _, _ = fstep(rs, inp["tile_mask"], kf_slots[cur][0], kf_slots[cur][1], kf_slots[cur][2])
             prefetch(cur ^ 1)  # the other slot was last read by the previous step, which has completed (loss read-back)
             if dist_on:
-                sharding.gather_object_table(obj_table)
+                sharding.gather_object_table(obj_table, rows_per_rank=1)
             return float(total)  # D2H read of the loss
 
         launch_fn = L.dqo_launch_count
@@ -291,7 +291,7 @@ def main():
             fwd = C.rasterize_gaussians(*args)
             C.rasterize_gaussians_backward(*rh.backward_args(inp, fwd, gc, gd))
             if dist_on:
-                sharding.gather_object_table(obj_table)
+                sharding.gather_object_table(obj_table, rows_per_rank=1)
 
         params = {k: torch.nn.Parameter(v) for k, v in raw_params(inp).items()}
         conf = torch.zeros(P, 1, device=dev)
@@ -304,7 +304,7 @@ def main():
             total = torch_mapping_iteration(params, opt, conf, rast_pkg.GaussianRasterizer, rs, inp["tile_mask"], dev_kf[0],
                                             dev_kf[1], dev_kf[2])
             if dist_on:
-                sharding.gather_object_table(obj_table)
+                sharding.gather_object_table(obj_table, rows_per_rank=1)
             return float(total)
 
         launch_fn = lambda: 0

@@ -73,10 +73,14 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_partial_kernel(LossArgs a) 
 
 __global__ void __launch_bounds__(LOSS_THREADS) loss_grad_kernel(LossArgs a, int nparts) {
     __shared__ double tot[4];
-    if (threadIdx.x < 4) { // fixed-order (deterministic) final reduction, redundantly per block
-        double t = 0.0;
-        for (int b = 0; b < nparts; b++) t += a.partial[4 * b + threadIdx.x];
-        tot[threadIdx.x] = t;
+    { // fixed-pattern (deterministic) final reduction, redundantly per block: warp q sums quantity q
+        const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (q < 4) {
+            double t = 0.0;
+            for (int b = lane; b < nparts; b += 32) t += a.partial[4 * b + q];
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+            if (lane == 0) tot[q] = t;
+        }
     }
     __syncthreads();
     const double cs = tot[0], cn = tot[1], ds = tot[2], dn = tot[3];

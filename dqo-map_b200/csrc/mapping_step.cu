@@ -110,8 +110,8 @@ __device__ __forceinline__ void adam_update(float &p, float g, float &m, float &
 // (mapper.py:909-910: confidence += 1 where any f_dc gradient is non-zero).
 struct SmallArgs {
     int P, M;
-    float *xyz, *opacity, *scaling, *rotation;
-    float *m_xyz, *v_xyz, *m_op, *v_op, *m_sc, *v_sc, *m_rot, *v_rot;
+    float *xyz, *opacity, *scaling, *rotation, *f_dc;
+    float *m_xyz, *v_xyz, *m_op, *v_op, *m_sc, *v_sc, *m_rot, *v_rot, *m_dc, *v_dc;
     const float *act_opacity, *act_scales;
     const float *g_means3D, *g_opacity, *g_scales, *g_rot, *g_sh;
     float *confidence;
@@ -160,38 +160,65 @@ __global__ void __launch_bounds__(256) adam_geometry_kernel(SmallArgs a) {
         reinterpret_cast<float4 *>(a.m_rot)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
         reinterpret_cast<float4 *>(a.v_rot)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
     }
-    if (a.confidence) {
+    { // f_dc: gradient = first coefficient of the merged SH gradient
         const float *gs = a.g_sh + (size_t)i * a.M * 3;
-        if (fabsf(gs[0]) != 0.f || fabsf(gs[1]) != 0.f || fabsf(gs[2]) != 0.f) a.confidence[i] += 1.0f;
+        const float g3[3] = {gs[0], gs[1], gs[2]};
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int e = 3 * i + c;
+            float p = a.f_dc[e], m = a.m_dc[e], v = a.v_dc[e];
+            adam_update(p, g3[c], m, v, a.k, a.k.step_size[1]);
+            a.f_dc[e] = p; a.m_dc[e] = m; a.v_dc[e] = v;
+        }
+        if (a.confidence && (fabsf(g3[0]) != 0.f || fabsf(g3[1]) != 0.f || fabsf(g3[2]) != 0.f)) a.confidence[i] += 1.0f;
     }
 }
 
-// Adam for the split SH parameters f_dc [P,3] / f_rest [P,3(M-1)] walking the merged gradient [P,M,3]
-struct ShAdamArgs {
-    long long total; // P * M * 3
-    int row; // M * 3
-    float *f_dc, *f_rest, *m_dc, *v_dc, *m_rest, *v_rest;
+// Adam for f_rest [P,45]: 128-bit accesses on the parameter and its two moments (6 of the 7 streams), the gradient is
+// gathered from the merged [P,16,3] layout (row stride 48, offset 3)
+struct RestAdamArgs {
+    long long n4; // number of float4 chunks of f_rest
+    float *f_rest, *m_rest, *v_rest;
     const float *g_sh;
     AdamScalars k;
 };
-template <int ROW>
-__global__ void __launch_bounds__(256) adam_sh_kernel(ShAdamArgs a) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.total) return;
-    const long long g_idx = i / ROW;
-    const int col = (int)(i - g_idx * ROW);
-    const float g = a.g_sh[i];
-    if (col < 3) {
-        const long long e = g_idx * 3 + col;
-        float p = a.f_dc[e], m = a.m_dc[e], v = a.v_dc[e];
-        adam_update(p, g, m, v, a.k, a.k.step_size[1]);
-        a.f_dc[e] = p; a.m_dc[e] = m; a.v_dc[e] = v;
-    } else {
-        const long long e = g_idx * (ROW - 3) + (col - 3);
-        float p = a.f_rest[e], m = a.m_rest[e], v = a.v_rest[e];
-        adam_update(p, g, m, v, a.k, a.k.step_size[2]);
-        a.f_rest[e] = p; a.m_rest[e] = m; a.v_rest[e] = v;
+__global__ void __launch_bounds__(256) adam_rest_kernel(RestAdamArgs a) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.n4) return;
+    float4 m = reinterpret_cast<float4 *>(a.m_rest)[q];
+    float4 v = reinterpret_cast<float4 *>(a.v_rest)[q];
+    const long long e0 = q * 4;
+    float g[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const long long e = e0 + c;
+        const long long row = e / 45;
+        const int col = (int)(e - row * 45);
+        g[c] = __ldg(&a.g_sh[row * 48 + 3 + col]);
     }
+    // zero gradient on zero moments is a fixed point of Adam (m' = v' = 0, p' = p - step * 0 / eps = p): nothing to
+    // read or write for Gaussians that no keyframe has touched yet (most of the map for any single view)
+    if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f && g[3] == 0.f && m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f &&
+        v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f)
+        return;
+    float4 p = reinterpret_cast<float4 *>(a.f_rest)[q];
+    const float ss = a.k.step_size[2];
+    adam_update(p.x, g[0], m.x, v.x, a.k, ss);
+    adam_update(p.y, g[1], m.y, v.y, a.k, ss);
+    adam_update(p.z, g[2], m.z, v.z, a.k, ss);
+    adam_update(p.w, g[3], m.w, v.w, a.k, ss);
+    reinterpret_cast<float4 *>(a.f_rest)[q] = p;
+    reinterpret_cast<float4 *>(a.m_rest)[q] = m;
+    reinterpret_cast<float4 *>(a.v_rest)[q] = v;
+}
+__global__ void adam_rest_tail_kernel(long long begin, long long end, RestAdamArgs a) {
+    const long long e = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= end) return;
+    const long long row = e / 45;
+    const int col = (int)(e - row * 45);
+    float p = a.f_rest[e], m = a.m_rest[e], v = a.v_rest[e];
+    adam_update(p, a.g_sh[row * 48 + 3 + col], m, v, a.k, a.k.step_size[2]);
+    a.f_rest[e] = p; a.m_rest[e] = m; a.v_rest[e] = v;
 }
 
 } // namespace dqo
@@ -260,20 +287,21 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
     for (int t = 0; t < 6; t++) k.step_size[t] = (float)(p->lr[t] / bc1);
     SmallArgs sa;
     sa.P = P; sa.M = M; sa.xyz = xyz; sa.opacity = p->param[3]; sa.scaling = p->param[4]; sa.rotation = p->param[5];
+    sa.f_dc = f_dc; sa.m_dc = p->exp_avg[1]; sa.v_dc = p->exp_avg_sq[1];
     sa.m_xyz = p->exp_avg[0]; sa.v_xyz = p->exp_avg_sq[0]; sa.m_op = p->exp_avg[3]; sa.v_op = p->exp_avg_sq[3];
     sa.m_sc = p->exp_avg[4]; sa.v_sc = p->exp_avg_sq[4]; sa.m_rot = p->exp_avg[5]; sa.v_rot = p->exp_avg_sq[5];
     sa.act_opacity = act_op; sa.act_scales = act_sc; sa.g_means3D = g_means3D; sa.g_opacity = g_op; sa.g_scales = g_sc;
     sa.g_rot = g_rot; sa.g_sh = g_sh; sa.confidence = p->confidence; sa.k = k;
     adam_geometry_kernel<<<nb, 256, 0, stream>>>(sa);
     DQO_LAUNCH_CHECK("adam geometry", s->debug, stream);
-    ShAdamArgs sh;
-    sh.total = (long long)P * M * 3; sh.row = M * 3; sh.f_dc = f_dc; sh.f_rest = f_rest; sh.m_dc = p->exp_avg[1];
-    sh.v_dc = p->exp_avg_sq[1]; sh.m_rest = p->exp_avg[2]; sh.v_rest = p->exp_avg_sq[2]; sh.g_sh = g_sh; sh.k = k;
-    if (M == 16)
-        adam_sh_kernel<48><<<(unsigned)((sh.total + 255) / 256), 256, 0, stream>>>(sh);
-    else
-        adam_sh_kernel<3><<<(unsigned)((sh.total + 255) / 256), 256, 0, stream>>>(sh);
-    DQO_LAUNCH_CHECK("adam sh", s->debug, stream);
+    if (M == 16) {
+        RestAdamArgs ra;
+        const long long total = (long long)P * 45;
+        ra.n4 = total / 4; ra.f_rest = f_rest; ra.m_rest = p->exp_avg[2]; ra.v_rest = p->exp_avg_sq[2]; ra.g_sh = g_sh; ra.k = k;
+        if (ra.n4 > 0) adam_rest_kernel<<<(unsigned)((ra.n4 + 255) / 256), 256, 0, stream>>>(ra);
+        if (total % 4) adam_rest_tail_kernel<<<1, 32, 0, stream>>>(ra.n4 * 4, total, ra);
+        DQO_LAUNCH_CHECK("adam f_rest", s->debug, stream);
+    }
     return DQO_OK;
 }
 

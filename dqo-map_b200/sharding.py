@@ -28,12 +28,19 @@ def local_objects(owner, rank):
     return sorted(o for o, r in owner.items() if r == rank)
 
 
-def gather_object_table(local_table, group=None):
+def gather_object_table(local_table, group=None, rows_per_rank=None):
     """all_gather of a per-object float table [n_local, F] with variable n_local (e.g. F = 12:
     obj_id, count, center 3, quaternion 4, axes 3).  Returns the concatenated [n_total, F] table on every rank,
-    sorted by column 0 (object id)."""
+    sorted by column 0 (object id).  When every rank is known to hold exactly `rows_per_rank` rows (static object
+    assignment) the size exchange and its host synchronisation are skipped: one collective, fully asynchronous."""
     world = dist.get_world_size(group)
     dev = local_table.device
+    if rows_per_rank is not None:
+        if local_table.shape[0] != rows_per_rank:
+            raise ValueError("rows_per_rank does not match the local table")
+        out = torch.empty((world * rows_per_rank, local_table.shape[1]), dtype=local_table.dtype, device=dev)
+        dist.all_gather_into_tensor(out, local_table.contiguous(), group=group)
+        return out
     n_local = torch.tensor([local_table.shape[0]], dtype=torch.int64, device=dev)
     sizes = [torch.zeros_like(n_local) for _ in range(world)]
     dist.all_gather(sizes, n_local, group=group)

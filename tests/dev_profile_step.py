@@ -1,0 +1,25 @@
+"""Dev tool: a few fused mapping steps of the c2 workload for ncu (never a bench number)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import refharness as rh
+import bench
+from dqo_map_b200 import rasterizer, mapping
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+dev = torch.device("cuda:0")
+inp, cam, settings = bench.build_workload(cfg, dev, 0)
+P, H, W = inp["xyz"].shape[0], cam.image_height, cam.image_width
+rs = settings(rasterizer.GaussianRasterizationSettings)
+gt_color, gt_depth, mask = bench.make_keyframe(inp, cam, settings, rasterizer)
+probe = rasterizer.rasterize_gaussians(*rh.raster_args(inp))
+fparams = {k: v.contiguous() for k, v in bench.raw_params(inp).items()}
+fstep = mapping.FusedMappingStep(fparams, bench.LRS, W, H, 0.8, 1.0, 0.1, confidence=torch.zeros(P, 1, device=dev),
+                                 capacity=int(probe[0] * 1.3) + 4096)
+del probe
+for _ in range(iters):
+    t = fstep(rs, inp["tile_mask"], gt_color, gt_depth, mask)
+torch.cuda.synchronize()
+print(float(t[0]), fstep.check())

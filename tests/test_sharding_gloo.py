@@ -22,6 +22,8 @@ def _worker(rank, world, port, results):
         assert full.shape == (5, 12)
         assert full[:, 0].tolist() == [0.0, 1.0, 2.0, 3.0, 4.0]
         assert full[:, 1].tolist() == [700.0, 300.0, 250.0, 50.0, 20.0]
+        fixed = sharding.gather_object_table(torch.full((2, 12), float(rank)), rows_per_rank=2)
+        assert fixed.shape == (4, 12) and fixed[:, 0].tolist() == [0.0, 0.0, 1.0, 1.0]
         n_local = sum(counts[o] for o in mine)
         g = {"xyz": torch.full((n_local, 3), float(rank)), "opacity": torch.full((n_local, 1), 0.5 + rank)}
         got = sharding.gather_gaussians(g, dst=0)
