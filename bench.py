@@ -368,8 +368,14 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = alg[dom] / (stage_ms[dom] / 1000.0) / 1e9 if stage_ms[dom] > 0 else 0.0
+        # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+        # written by profiles/extract_ncu.py); only valid for the configuration it was captured on.
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(a.config, {}).get(dom)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes": int(alg[dom]), "kernel_ms": stage_ms[dom],
                     "per_stage": {k: {"ms": stage_ms.get(k, 0.0), "alg_bytes": int(v),

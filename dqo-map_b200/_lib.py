@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdqomap_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_WORDS = 0, 1, 2, 3, 8
 ADAM_MAX_TENSORS = 16
@@ -63,6 +63,13 @@ PROTOTYPES = {
     "dqo_knn3": (C.c_int, [C.c_int32, c_p, c_p, c_p, c_p, C.c_size_t, c_p]),
     "dqo_accumulate_error": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [c_p] * 5
                              + [C.c_float, C.c_float, C.c_float, C.c_int32] + [c_p] * 7 + [c_p]),
+    "dqo_render_range": (C.c_int, [C.c_int32, C.c_int32, c_p, C.c_float, c_p, c_p, c_p, c_p]),
+    "dqo_pixelmask_to_tilemask": (C.c_int, [C.c_int32, C.c_int32, c_p, C.c_float, c_p, c_p, c_p]),
+    "dqo_color_error_map": (C.c_int, [C.c_int32, C.c_int32, c_p, c_p, c_p, c_p]),
+    "dqo_topk_tilemask_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "dqo_topk_tilemask": (C.c_int, [C.c_int32, C.c_int32, c_p, C.c_int32, C.c_int32, c_p, c_p, c_p, c_p]),
+    "dqo_tilemask_to_pixelmask": (C.c_int, [C.c_int32, C.c_int32, c_p, c_p, c_p]),
+    "dqo_render_error_maps": (C.c_int, [C.c_int32, C.c_int32] + [c_p] * 8 + [c_p]),
     "dqo_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "dqo_masked_l1_loss": (C.c_int, [C.c_int32, C.c_int32] + [c_p] * 6 + [C.c_float, C.c_float, C.c_float]
                            + [c_p] * 5 + [c_p]),

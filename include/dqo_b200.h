@@ -166,6 +166,36 @@ int dqo_accumulate_error(int32_t W, int32_t H, int32_t P, const float *color_err
                          float *rescale_counter, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Mask builders and error maps of the mapper (inline PyTorch in the reference).
+ * Tiles are the rasterizer's 16x16 blocks (the callers pass stride 16: mapper.py:956,968,985).
+ *   dqo_render_range          render_mask = (T_map != 1) and transmission2tilemask(render_mask, 16, ratio)
+ *                             (mapper.py:983-987, SLAM/utils.py:752-763); *render_count = render_mask.sum()
+ *   dqo_pixelmask_to_tilemask transmission2tilemask on a caller-made bool mask (SLAM/utils.py:752-763)
+ *   dqo_color_error_map       sum_c |render - gt|, 0 where render.sum(c) == 0; CHW in, HW out (mapper.py:948-955)
+ *   dqo_topk_tilemask         colorerror2tilemask (SLAM/utils.py:765-796): tile means in avg_pool2d's accumulation
+ *                             order, the k = int(n_tiles * top_ratio) largest set to 1 (ties: lower tile index);
+ *                             or_into != 0 ORs into an existing mask (mapper.py:969); render_mask, when given, is the
+ *                             x16 nearest upsampling cropped to the image (mapper.py:971-980)
+ *   dqo_tilemask_to_pixelmask that upsampling alone
+ *   dqo_render_error_maps     colour / depth / normal error images of error_gaussians_remove (mapper.py:1008-1025);
+ *                             gt maps are HWC / HW (frame_map), renders CHW; feeds dqo_accumulate_error
+ * ---------------------------------------------------------------------------------------------- */
+int dqo_render_range(int32_t W, int32_t H, const float *T_map, float tile_mask_ratio, uint8_t *render_mask /* [H,W] or NULL */,
+                     int32_t *tile_mask /* [ceil(H/16), ceil(W/16)] */, int32_t *render_count /* [1] or NULL */, void *stream);
+int dqo_pixelmask_to_tilemask(int32_t W, int32_t H, const uint8_t *pixelmask, float tile_mask_ratio, int32_t *tile_mask,
+                              int32_t *pixel_count /* [1] or NULL */, void *stream);
+int dqo_color_error_map(int32_t W, int32_t H, const float *render /* [3,H,W] */, const float *gt /* [3,H,W] */,
+                        float *color_error /* [H,W] */, void *stream);
+size_t dqo_topk_tilemask_workspace_bytes(int32_t W, int32_t H);
+int dqo_topk_tilemask(int32_t W, int32_t H, const float *error /* [H,W] */, int32_t k, int32_t or_into, int32_t *tile_mask,
+                      uint8_t *render_mask /* [H,W] or NULL */, void *workspace, void *stream);
+int dqo_tilemask_to_pixelmask(int32_t W, int32_t H, const int32_t *tile_mask, uint8_t *render_mask, void *stream);
+int dqo_render_error_maps(int32_t W, int32_t H, const float *render_color /* [3,H,W] */, const float *render_depth /* [H,W] */,
+                          const float *gt_color_hwc /* [H,W,3] */, const float *gt_depth /* [H,W] */,
+                          const int32_t *depth_index /* [H,W] */, float *color_error, float *depth_error,
+                          float *normal_error /* zeros; NULL to skip */, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Mapping step (no native boundary exists in the reference: SLAM/multiprocess/mapper.py:799-928 is
  * inline PyTorch).  Masked L1 colour + depth loss and its image gradients in two launches.
  *   colour: mean |img - gt| over render_mask pixels x 3 channels          (mapper.py:847, loss_utils.py:27-31)
