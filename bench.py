@@ -228,11 +228,40 @@ def main():
     if a.impl == "ours":
         L = _lib.lib()
         rs = settings(rasterizer.GaussianRasterizationSettings)
-        # capacity from one synchronous probe; the timed loop never synchronises
+        # one synchronous single-phase probe gives R, the workload statistics of the byte model and the policy's input;
+        # the timed loop never synchronises
+        from dqo_map_b200.binning_policy import BinningPolicy
+        rasterizer.set_binning_mode("single")
         probe = rasterizer.rasterize_gaussians(*rh.raster_args(inp))
         R = probe[0]
-        pipe = rasterizer.RasterPipeline(P, M, W, H, int(R * 1.05) + 4096, dev)
-        del probe
+        pst = probe[10]._dqo_state
+        host0 = list(pst.status_host)
+        V = host0[_lib.ST_NUM_VISIBLE]
+        ex = rh.export_ours(pst, P, W, H)
+        th, tw = (H + 15) // 16, (W + 15) // 16
+        nc = np.zeros((th * 16, tw * 16), np.int64)
+        nc[:H, :W] = ex["n_contrib"]
+        max_c = nc.reshape(th, 16, tw, 16).max(axis=(1, 3)).reshape(-1)
+        rg = ex["ranges"].astype(np.int64)
+        length = rg[:, 1] - rg[:, 0]
+        Rt = int(np.minimum(length, ((max_c + 255) // 256) * 256).sum())
+        Npx = int((length > 0).sum()) * 256
+        stats = {"P": P, "V": V, "R": R, "Rt": Rt, "Npx": Npx, "tile_num": host0[_lib.ST_TILE_NUM],
+                 "walked": host0[_lib.ST_WALKED]}
+        del probe, pst, ex
+        # binning plan (dqo-map_b200/binning_policy.py): single-phase unless the blend walks a small part of the lists
+        policy = BinningPolicy()
+        policy.update(host0, 0, 0)
+        front, back = policy.plan(1 << 30)
+        if front > 0:
+            trial = rasterizer.RasterPipeline(P, M, W, H, front + back, dev, front, back)
+            trial.forward(rs, inp["xyz"], inp["opacity"], inp["scales"], inp["rotations"], inp["tile_mask"], shs=inp["shs"])
+            policy.update(trial.check(), front, back)
+            front, back = policy.plan(1 << 30)
+            del trial
+        capacity = front + back if front > 0 else int(R * 1.05) + 4096
+        pipe = rasterizer.RasterPipeline(P, M, W, H, capacity, dev, front, back)
+        stats["binning"] = {"front_instances": front, "back_instances": back} if front > 0 else "single-phase"
 
         def kernel_step():
             pipe.forward(rs, inp["xyz"], inp["opacity"], inp["scales"], inp["rotations"], inp["tile_mask"], shs=inp["shs"])
@@ -257,7 +286,10 @@ def main():
         # pinned host memory on a side stream while step k computes (every step still copies its own keyframe)
         fparams = {k: v.contiguous() for k, v in raw_params(inp).items()}
         fconf = torch.zeros(P, 1, device=dev)
-        fstep = mapping.FusedMappingStep(fparams, LRS, W, H, 0.8, 1.0, 0.1, confidence=fconf, capacity=int(R * 1.3) + 4096)
+        fback = int(back * 1.3) + 65536 if front > 0 else 0  # parameters move during the loop: extra headroom
+        fstep = mapping.FusedMappingStep(fparams, LRS, W, H, 0.8, 1.0, 0.1, confidence=fconf,
+                                         capacity=(front + fback) if front > 0 else int(R * 1.3) + 4096,
+                                         front_instances=front, back_instances=fback)
         copy_stream = torch.cuda.Stream(device=dev)
         kf_slots = [[torch.empty_like(t, device=dev) for t in host_kf] for _ in range(2)]
         kf_ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -334,22 +366,17 @@ def main():
             acc += np.array(list(buf))
         L.dqo_profile_enable(0)
         acc /= reps
-        names = ["", "preprocess", "depth_sort", "scan", "duplicate", "tile_sort", "ranges", "compact", "render_fwd", "",
-                 "render_bwd", "gaussian_bwd"]
+        names = ["", "preprocess", "depth_sort", "scan", "duplicate", "tile_sort", "ranges", "render_front", "back_binning",
+                 "compact", "render_fwd", "", "render_bwd", "gaussian_bwd"]
         stage_ms = {n: float(acc[i]) for i, n in enumerate(names) if n}
         host = pipe.check()
-        R, V = host[_lib.ST_NUM_RENDERED], host[_lib.ST_NUM_VISIBLE]
-        st = type("S", (), {})()
-        st.settings, st.geom, st.binning, st.image, st.status, st.capacity = pipe.settings, pipe.geom, pipe.binning, pipe.image, pipe.status, pipe.capacity
-        ex = rh.export_ours(st, P, W, H)
-        th, tw = (H + 15) // 16, (W + 15) // 16
-        nc = np.zeros((th * 16, tw * 16), np.int64)
-        nc[:H, :W] = ex["n_contrib"]
-        max_c = nc.reshape(th, 16, tw, 16).max(axis=(1, 3)).reshape(-1)
-        rg = ex["ranges"].astype(np.int64)
-        length = rg[:, 1] - rg[:, 0]
-        Rt = int(np.minimum(length, ((max_c + 255) // 256) * 256).sum())
-        Npx = int((length > 0).sum()) * 256
+        two_phase = front > 0
+        if two_phase:  # the forward blend is the front pass plus the resumed back pass
+            stage_ms["render_fwd"] += stage_ms["render_front"]
+            stats["R_front"], stats["R_back"] = host[_lib.ST_R_FRONT], host[_lib.ST_R_BACK]
+            stats["unfinished_tiles"] = host[_lib.ST_UNFINISHED]
+        else:
+            stage_ms.pop("render_front"), stage_ms.pop("back_binning")
         bit = max(1, int(th * tw).bit_length())
         D_t = (bit + 7) // 8
         # algorithmic (compulsory) bytes per launch, byte model of SURVEY.md §8d adapted to this design
@@ -357,13 +384,15 @@ def main():
             "preprocess": P * (44 + 12 * M) + V * 64 + P * 17,
             "depth_sort": P * 8 * (1 + 2 * 4),
             "scan": P * 12,
-            "duplicate": P * 16 + R * 8,
-            "tile_sort": R * 8 * (1 + 2 * D_t),
-            "ranges": R * 4 + th * tw * 8,
+            "duplicate": P * 16 + (host[_lib.ST_R_FRONT] if two_phase else R) * 8,
+            "tile_sort": (front if two_phase else R) * 8 * (1 + 2 * D_t),
+            "ranges": (front if two_phase else R) * 4 + th * tw * 8,
             "render_fwd": 52 * Rt + (40 + 32) * Npx,
             "render_bwd": 52 * Rt + 72 * Npx + 36 * R,
             "gaussian_bwd": V * (100 + 12 * M) + P * (76 + 12 * M),
         }
+        if two_phase:  # count (rect + offsets + order + bitmaps) + scan + duplicate/sort/ranges over the back region
+            alg["back_binning"] = P * 28 + back * 8 * (2 + 2 * D_t) + th * tw * 8
         dom = max((k for k in alg), key=lambda k: stage_ms.get(k, 0.0))
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -381,7 +410,6 @@ def main():
                     "per_stage": {k: {"ms": stage_ms.get(k, 0.0), "alg_bytes": int(v),
                                       "gbps": (v / (stage_ms[k] / 1000.0) / 1e9) if stage_ms.get(k, 0) > 0 else None}
                                   for k, v in alg.items()}}
-        stats = {"P": P, "V": V, "R": R, "Rt": Rt, "Npx": Npx, "tile_num": host[_lib.ST_TILE_NUM]}
 
     if rank == 0:
         out = {

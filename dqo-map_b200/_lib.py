@@ -8,9 +8,10 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdqomap_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
-ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_WORDS = 0, 1, 2, 3, 8
+ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_R_FRONT, ST_R_BACK, ST_WALKED, ST_UNFINISHED = range(8)
+ST_WORDS = 8
 ADAM_MAX_TENSORS = 16
 
 c_p = C.c_void_p
@@ -23,6 +24,7 @@ class RastSettings(C.Structure):
         ("scale_modifier", C.c_float), ("color_sigma", C.c_float), ("opaque_threshold", C.c_float),
         ("depth_threshold", C.c_float), ("normal_threshold", C.c_float), ("T_threshold", C.c_float),
         ("prefiltered", C.c_int32), ("debug", C.c_int32), ("need_n_touched", C.c_int32),
+        ("front_instances", C.c_int32), ("back_instances", C.c_int32),
     ]
 
 

@@ -34,16 +34,21 @@ extern "C" void dqo_profile_enable(int on) {
     dqo::g_profile = on;
     for (int i = 0; i < dqo::ST_COUNT; i++) dqo::g_ev_set[i] = false;
 }
-// ms_out[i] = time between stage mark i-1 and i (0 for the two BEGIN marks / missing marks); returns ST_COUNT
+// ms_out[i] = time between stage mark i and the previous recorded mark (0 for the two BEGIN marks / missing marks);
+// returns ST_COUNT
 extern "C" int dqo_profile_read(float *ms_out, int n) {
     using namespace dqo;
     for (int i = 0; i < n; i++) ms_out[i] = 0.f;
     if (!g_ev_made) return ST_COUNT;
+    int prev = g_ev_set[0] ? 0 : -1;
     for (int i = 1; i < ST_COUNT && i < n; i++) {
-        if (i == ST_BEGIN_BWD || !g_ev_set[i] || !g_ev_set[i - 1]) continue;
-        cudaEventSynchronize(g_ev[i]);
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, g_ev[i - 1], g_ev[i]) == cudaSuccess) ms_out[i] = ms;
+        if (!g_ev_set[i]) continue;
+        if (i != ST_BEGIN_BWD && prev >= 0) {
+            cudaEventSynchronize(g_ev[i]);
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, g_ev[prev], g_ev[i]) == cudaSuccess) ms_out[i] = ms;
+        }
+        prev = i;
     }
     return ST_COUNT;
 }

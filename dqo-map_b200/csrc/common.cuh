@@ -13,7 +13,7 @@
 
 #define DQO_TILE 16
 #define DQO_TILE_PIX 256
-#define DQO_ABI_VERSION 4
+#define DQO_ABI_VERSION 5
 
 namespace dqo {
 
@@ -23,8 +23,9 @@ void stage_mark(cudaStream_t stream, int stage);  // records a CUDA event when s
 
 // stage ids of dqo_profile_read()
 enum {
-    ST_BEGIN_FWD = 0, ST_PREPROCESS, ST_DEPTH_SORT, ST_SCAN, ST_DUPLICATE, ST_TILE_SORT, ST_RANGES, ST_COMPACT,
-    ST_RENDER_FWD, ST_BEGIN_BWD, ST_RENDER_BWD, ST_GAUSS_BWD, ST_COUNT
+    ST_BEGIN_FWD = 0, ST_PREPROCESS, ST_DEPTH_SORT, ST_SCAN, ST_DUPLICATE, ST_TILE_SORT, ST_RANGES,
+    ST_RENDER_FRONT, ST_BACK_BIN, // two-phase binning only: front blend, then count/scan/duplicate/sort/ranges of the back phase
+    ST_COMPACT, ST_RENDER_FWD, ST_BEGIN_BWD, ST_RENDER_BWD, ST_GAUSS_BWD, ST_COUNT
 };
 
 #define DQO_CUDA_CHECK(expr)                                                                  \
@@ -165,6 +166,8 @@ struct GeomLayout {
     size_t rect;       // uint2[P] {min.x | max.x<<16, min.y | max.y<<16}
     size_t clamped;    // u8[P] bit c = colour channel c clamped (forward.cu:151-153)
     size_t gacc;       // f32[16P] gradient accumulators of the backward blend (see DQO_GACC_FLOATS)
+    size_t tiles_b;    // u32[P] two-phase: tiles touched among the unfinished tiles, in depth-rank order
+    size_t offsets_b;  // u32[P] two-phase: inclusive scan of tiles_b
     size_t cub;        // CUB temp storage
     size_t cub_bytes;
     size_t total;
@@ -184,6 +187,10 @@ struct ImgLayout {
     size_t final_T;    // f32[T*256]
     size_t hit_geo;    // f32[6][T*256]: hit_normal_c.xyz, hit_point_c.xyz (forward.cu:807-808)
     size_t mask_bits;  // u32[tiles_y][mask_words]: tile_mask != 0 as a bitmap
+    size_t ranges_b;   // uint2[T] two-phase: ranges of the back-phase lists (relative to the back region)
+    size_t unfinished; // i32[T] two-phase: 1 when the front phase left some pixel of the tile unterminated
+    size_t mask_bits_b; // u32[tiles_y][mask_words]: mask_bits & unfinished
+    size_t state;      // f32[4][T*256] two-phase: running T (-1 = pixel terminated) and colour accumulators
     int mask_words;
     size_t total;
     int tiles_x, tiles_y, T;

@@ -115,11 +115,12 @@ struct SmallArgs {
     const float *act_opacity, *act_scales;
     const float *g_means3D, *g_opacity, *g_scales, *g_rot, *g_sh;
     float *confidence;
+    const int *status; // the step is skipped when the forward flagged an instance overflow (gradients are invalid)
     AdamScalars k;
 };
 __global__ void __launch_bounds__(256) adam_geometry_kernel(SmallArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.P) return;
+    if (i >= a.P || a.status[DQO_ST_OVERFLOW]) return;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const int e = 3 * i + c;
@@ -180,11 +181,12 @@ struct RestAdamArgs {
     long long n4; // number of float4 chunks of f_rest
     float *f_rest, *m_rest, *v_rest;
     const float *g_sh;
+    const int *status;
     AdamScalars k;
 };
 __global__ void __launch_bounds__(256) adam_rest_kernel(RestAdamArgs a) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= a.n4) return;
+    if (q >= a.n4 || a.status[DQO_ST_OVERFLOW]) return;
     float4 m = reinterpret_cast<float4 *>(a.m_rest)[q];
     float4 v = reinterpret_cast<float4 *>(a.v_rest)[q];
     const long long e0 = q * 4;
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(256) adam_rest_kernel(RestAdamArgs a) {
 }
 __global__ void adam_rest_tail_kernel(long long begin, long long end, RestAdamArgs a) {
     const long long e = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= end) return;
+    if (e >= end || a.status[DQO_ST_OVERFLOW]) return;
     const long long row = e / 45;
     const int col = (int)(e - row * 45);
     float p = a.f_rest[e], m = a.m_rest[e], v = a.v_rest[e];
@@ -291,13 +293,13 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
     sa.m_xyz = p->exp_avg[0]; sa.v_xyz = p->exp_avg_sq[0]; sa.m_op = p->exp_avg[3]; sa.v_op = p->exp_avg_sq[3];
     sa.m_sc = p->exp_avg[4]; sa.v_sc = p->exp_avg_sq[4]; sa.m_rot = p->exp_avg[5]; sa.v_rot = p->exp_avg_sq[5];
     sa.act_opacity = act_op; sa.act_scales = act_sc; sa.g_means3D = g_means3D; sa.g_opacity = g_op; sa.g_scales = g_sc;
-    sa.g_rot = g_rot; sa.g_sh = g_sh; sa.confidence = p->confidence; sa.k = k;
+    sa.g_rot = g_rot; sa.g_sh = g_sh; sa.confidence = p->confidence; sa.status = status; sa.k = k;
     adam_geometry_kernel<<<nb, 256, 0, stream>>>(sa);
     DQO_LAUNCH_CHECK("adam geometry", s->debug, stream);
     if (M == 16) {
         RestAdamArgs ra;
         const long long total = (long long)P * 45;
-        ra.n4 = total / 4; ra.f_rest = f_rest; ra.m_rest = p->exp_avg[2]; ra.v_rest = p->exp_avg_sq[2]; ra.g_sh = g_sh; ra.k = k;
+        ra.n4 = total / 4; ra.f_rest = f_rest; ra.m_rest = p->exp_avg[2]; ra.v_rest = p->exp_avg_sq[2]; ra.g_sh = g_sh; ra.status = status; ra.k = k;
         if (ra.n4 > 0) adam_rest_kernel<<<(unsigned)((ra.n4 + 255) / 256), 256, 0, stream>>>(ra);
         if (total % 4) adam_rest_tail_kernel<<<1, 32, 0, stream>>>(ra.n4 * 4, total, ra);
         DQO_LAUNCH_CHECK("adam f_rest", s->debug, stream);

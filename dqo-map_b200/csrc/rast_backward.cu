@@ -20,6 +20,8 @@ struct RenderBwdArgs {
     float depth_thr, normal_thr;
     const uint2 *ranges;
     const uint32_t *point_list;
+    const uint2 *ranges_b;          // two-phase binning: back lists (nullptr in single-phase mode)
+    const uint32_t *point_list_b;
     const float4 *rec;
     const float *view, *means3D, *scales, *rotations, *bg;
     const uint32_t *n_contrib;
@@ -196,7 +198,17 @@ __global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(RenderBwdAr
 
     const int tile = blockIdx.x;
     const uint2 range = a.ranges[tile];
-    if (range.x == range.y) return;
+    // the tile's list is the front list followed by the back list (two-phase binning); position p lives in the
+    // front list when p < len_a
+    const int len_a = (int)(range.y - range.x);
+    uint32_t start_b = 0;
+    bool has_b = false;
+    if (a.ranges_b) {
+        const uint2 rb = a.ranges_b[tile];
+        start_b = rb.x;
+        has_b = rb.x != rb.y;
+    }
+    if (len_a == 0 && !has_b) return;
     const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -256,7 +268,7 @@ __global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(RenderBwdAr
             const int slot = e * RB_THREADS + tid;
             if (slot < n) {
                 const int pos = max_c - 1 - (i * 256 + slot);
-                const int id = (int)a.point_list[range.x + pos];
+                const int id = (int)(pos < len_a ? a.point_list[range.x + pos] : a.point_list_b[start_b + (pos - len_a)]);
                 const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
                 const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
                 const float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
@@ -766,6 +778,9 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     ra.depth_thr = s->depth_threshold; ra.normal_thr = s->normal_threshold;
     ra.ranges = (const uint2 *)(img + IL.ranges);
     ra.point_list = (const uint32_t *)(bin + BL.vals_out);
+    const bool two_phase = s->front_instances > 0;
+    ra.ranges_b = two_phase ? (const uint2 *)(img + IL.ranges_b) : nullptr;
+    ra.point_list_b = two_phase ? ra.point_list + s->front_instances : nullptr;
     ra.rec = (const float4 *)(geom + GL.rec);
     ra.view = viewmatrix; ra.means3D = means3D; ra.scales = scales; ra.rotations = rotations; ra.bg = background;
     ra.n_contrib = (const uint32_t *)(img + IL.n_contrib);

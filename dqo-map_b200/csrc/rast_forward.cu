@@ -48,6 +48,8 @@ int make_geom_layout(int P, GeomLayout *L) {
     L->rect = bump(cur, n * 8);
     L->clamped = bump(cur, n);
     L->gacc = bump(cur, n * DQO_GACC_FLOATS * 4);
+    L->tiles_b = bump(cur, n * 4);
+    L->offsets_b = bump(cur, n * 4);
     size_t sort_bytes = 0, scan_bytes = 0;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
                                                     (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 32);
@@ -103,6 +105,10 @@ void make_img_layout(int W, int H, ImgLayout *L) {
     L->hit_geo = bump(cur, T * DQO_TILE_PIX * 4 * 6);
     L->mask_words = (L->tiles_x + 31) / 32;
     L->mask_bits = bump(cur, (size_t)(L->tiles_y > 0 ? L->tiles_y : 1) * L->mask_words * 4);
+    L->ranges_b = bump(cur, T * 8);
+    L->unfinished = bump(cur, T * 4);
+    L->mask_bits_b = bump(cur, (size_t)(L->tiles_y > 0 ? L->tiles_y : 1) * L->mask_words * 4);
+    L->state = bump(cur, T * DQO_TILE_PIX * 4 * 4);
     L->total = align_up(cur, 256);
 }
 
@@ -448,31 +454,58 @@ __global__ void mark_visible_kernel(int P, const float *__restrict__ means, cons
 // Gaussians in depth-rank order so that a stable sort by tile id alone reproduces the reference order.
 // One warp serves 32 consecutive ranks: the run of each Gaussian is written by all lanes together (coalesced)
 // when no tile of its rectangle is masked out, otherwise by its owner lane walking the mask bitmap.
-// Threads also pad the unused tail [R, capacity) of the key buffer with the sentinel tile id.
-template <typename KeyT>
+//   MODE 0 (single phase): every rank; threads also pad the unused tail [R, capacity) of the key buffer with the
+//          sentinel tile id; overflow when R > capacity.
+//   MODE 1 (front phase):  only the ranks whose inclusive offset fits into `capacity` (= front_instances), i.e. the
+//          nearest Gaussians; R_front is reported; the key buffer was pre-filled with the sentinel.
+//   MODE 2 (back phase):   counts / offsets are the back-phase ones (rank order, tiles_rank), the bitmap holds the
+//          unfinished tiles only; overflow when R_back > capacity.
+template <typename KeyT, int MODE>
 __global__ void __launch_bounds__(256)
     duplicate_kernel(int P, int64_t capacity, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
-                     const uint32_t *__restrict__ offsets, const uint2 *__restrict__ rect,
-                     const uint32_t *__restrict__ mask_bits, int mask_words, int grid_x, KeyT *__restrict__ keys,
-                     uint32_t *__restrict__ vals, int *status) {
+                     const uint32_t *__restrict__ tiles_rank, const uint32_t *__restrict__ offsets,
+                     const uint2 *__restrict__ rect, const uint32_t *__restrict__ mask_bits, int mask_words, int grid_x,
+                     KeyT *__restrict__ keys, uint32_t *__restrict__ vals, int *status) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const uint32_t R = offsets[P - 1];
-    const bool overflow = (int64_t)R > capacity;
-    if (i == 0) {
-        status[DQO_ST_NUM_RENDERED] = (int)R;
-        status[DQO_ST_OVERFLOW] = overflow ? 1 : 0;
+    if (MODE == 0) {
+        const bool overflow = (int64_t)R > capacity;
+        if (i == 0) {
+            status[DQO_ST_NUM_RENDERED] = (int)R;
+            status[DQO_ST_OVERFLOW] = overflow ? 1 : 0;
+        }
+        const int64_t R_eff = overflow ? 0 : (int64_t)R;
+        if (i >= R_eff && i < capacity) keys[i] = (KeyT)~(KeyT)0;
+        if (overflow) return;
+    } else if (MODE == 1) {
+        if (i == 0) status[DQO_ST_NUM_RENDERED] = (int)R;
+    } else {
+        const bool overflow = (int64_t)R > capacity;
+        if (i == 0) {
+            status[DQO_ST_R_BACK] = (int)R;
+            if (overflow) status[DQO_ST_OVERFLOW] = 1;
+        }
+        if (overflow) return;
     }
-    const int64_t R_eff = overflow ? 0 : (int64_t)R;
-    if (i >= R_eff && i < capacity) keys[i] = (KeyT)~(KeyT)0;
-    if (overflow) return;
     uint32_t id = 0, n = 0, off = 0;
     uint2 rc = make_uint2(0, 0);
     if (i < P) {
         id = order[i];
-        n = tiles[id];
+        const uint32_t end = offsets[i];
+        if (MODE == 2) {
+            n = tiles_rank[i];
+        } else {
+            n = tiles[id];
+            if (MODE == 1) {
+                if ((int64_t)end > capacity)
+                    n = 0;
+                else if (i == P - 1 || (int64_t)offsets[i + 1] > capacity)
+                    status[DQO_ST_R_FRONT] = (int)end;
+            }
+        }
         if (n) {
-            off = offsets[i] - n;
+            off = end - n;
             rc = rect[id];
         }
     }
@@ -511,12 +544,45 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Back phase, step 1: bitmap of the tiles that are both masked in and unfinished after the front phase.
+__global__ void mask_unfinished_kernel(int tiles_x, int tiles_y, int mask_words, const uint32_t *__restrict__ mask_bits,
+                                       const int *__restrict__ unfinished, uint32_t *mask_bits_b) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= tiles_y * mask_words) return;
+    const int y = w / mask_words, x0 = (w % mask_words) * 32;
+    uint32_t bits = 0;
+    for (int b = 0; b < 32 && x0 + b < tiles_x; b++)
+        if (unfinished[y * tiles_x + x0 + b]) bits |= 1u << b;
+    mask_bits_b[w] = bits & mask_bits[w];
+}
+
+// Back phase, step 2: per rank, the number of unfinished tiles inside the rectangle of every Gaussian that the
+// front phase left out (inclusive offset beyond front_instances).
+__global__ void __launch_bounds__(256)
+    count_back_kernel(int P, int64_t front, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
+                      const uint32_t *__restrict__ offsets, const uint2 *__restrict__ rect,
+                      const uint32_t *__restrict__ mask_bits_b, int mask_words, uint32_t *tiles_rank) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    uint32_t n = 0;
+    if ((int64_t)offsets[i] > front) {
+        const uint32_t id = order[i];
+        if (tiles[id]) {
+            const uint2 rc = rect[id];
+            const uint32_t minx = rc.x & 0xFFFF, maxx = rc.x >> 16, miny = rc.y & 0xFFFF, maxy = rc.y >> 16;
+            for (uint32_t y = miny; y < maxy; y++) n += mask_row_count(mask_bits_b, mask_words, y, minx, maxx);
+        }
+    }
+    tiles_rank[i] = n;
+}
+
 // per-tile [start, end) in the sorted list (rasterizer_impl.cu:120-142); each thread checks 8 consecutive keys
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
-    tile_ranges_kernel(int64_t capacity, const KeyT *__restrict__ keys, const int *__restrict__ status, uint2 *ranges) {
+    tile_ranges_kernel(int64_t capacity, const KeyT *__restrict__ keys, const int *__restrict__ status, int count_word,
+                       uint2 *ranges) {
     const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    const int64_t L = status[DQO_ST_OVERFLOW] ? 0 : status[DQO_ST_NUM_RENDERED];
+    const int64_t L = status[DQO_ST_OVERFLOW] ? 0 : status[count_word];
     if (base >= L) return;
     uint32_t prev = (base > 0) ? (uint32_t)keys[base - 1] : 0xFFFFFFFFu;
     KeyT k[8];
@@ -549,7 +615,8 @@ __global__ void __launch_bounds__(256)
 }
 
 // compact list of non-empty tiles in row-major order (rasterizer_impl.cu:348-365 on the host in the reference)
-__global__ void __launch_bounds__(1024) compact_tiles_kernel(int T, const uint2 *__restrict__ ranges, int *tile_indices,
+__global__ void __launch_bounds__(1024) compact_tiles_kernel(int T, const uint2 *__restrict__ ranges,
+                                                             const uint2 *__restrict__ ranges_b, int *tile_indices,
                                                              int *status) {
     __shared__ int warp_sums[32];
     __shared__ int base;
@@ -562,6 +629,10 @@ __global__ void __launch_bounds__(1024) compact_tiles_kernel(int T, const uint2 
         if (t < T) {
             const uint2 r = ranges[t];
             flag = (r.x != r.y) ? 1 : 0;
+            if (ranges_b) {
+                const uint2 rb = ranges_b[t];
+                flag |= (rb.x != rb.y) ? 1 : 0;
+            }
         }
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, flag);
         const int within = __popc(bal & ((1u << lane) - 1));
@@ -597,6 +668,12 @@ struct RenderArgs {
     size_t plane; // T*256
     float *out_color, *out_depth, *out_hit_cw, *out_hit_dw, *out_T;
     int *out_hit_depth, *out_hit_color, *n_touched;
+    // two-phase binning (PHASE 1 / 2)
+    const uint2 *ranges_b;
+    const uint32_t *point_list_b;
+    int *unfinished;
+    float *state;
+    int *status;
 };
 
 // Front-to-back blend of one 16x16 tile (forward.cu:636-866).  Warp w owns the 8x4 pixel sub-block
@@ -605,6 +682,13 @@ struct RenderArgs {
 // index list and only walks the splats that can contribute to its pixels.  Skipped splats are exactly those the
 // reference rejects for all 32 pixels (alpha < 1/255), so every output is unchanged; `contributor` is the list
 // position, recovered from the batch index instead of being counted.
+//   PHASE 0: the tile's whole list (single-phase binning).
+//   PHASE 1: the front list only (nearest Gaussians).  A tile whose pixels have not all terminated when the list ends
+//            is flagged unfinished and parks the running (T, C) of its pixels; every other per-pixel quantity is
+//            already in the output images.
+//   PHASE 2: unfinished tiles resume from the parked state and walk their back list; list positions continue at the
+//            length of the front list, so n_contrib and the blend order are those of the concatenated (= reference) list.
+template <int PHASE>
 __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
     __shared__ float4 s_r0[256];
     __shared__ float4 s_r1[256];
@@ -622,9 +706,19 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
     const bool inside = pix_x < (uint32_t)a.W && pix_y < (uint32_t)a.H;
     const size_t pix_id = (size_t)a.W * pix_y + pix_x;
     const size_t HW = (size_t)a.W * a.H;
-    const uint2 range = a.ranges[tile];
+    const size_t sp = (size_t)tile * 256 + ly * 16 + lx;
+    uint2 range = a.ranges[tile];
+    const uint32_t *__restrict__ point_list = a.point_list;
+    int base = 0; // list position of the first entry walked by this launch
+    if (PHASE == 2) {
+        base = (int)(range.y - range.x);
+        range = a.ranges_b[tile];
+        if (range.x == range.y) return; // finished in the front phase (or nothing behind it)
+        point_list = a.point_list_b;
+    }
 
-    if (range.x == range.y) { // tile not rendered: reference fill values (rasterize_points.cu:79-86)
+    if (PHASE != 2 && range.x == range.y) { // tile not rendered: reference fill values (rasterize_points.cu:79-86)
+        if (PHASE == 1 && tid == 0) a.unfinished[tile] = 1; // nothing in front: the back phase may still reach it
         if (inside) {
             a.out_color[pix_id] = 0.f;
             a.out_color[HW + pix_id] = 0.f;
@@ -645,19 +739,37 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
 
     bool done = !inside;
     float T = 1.0f, end_T = 1.0f;
-    int last_j = -1, last_i = 0;
+    int ncontrib = 0;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f;
     float depth_ = 0.f;
     bool hit = false;
     int hit_id = -1, hit_color_id = -1;
     float cw_max = -1.f, hit_cw = 0.f, hit_dw = 0.f;
+    bool was_done = false;
+    if (PHASE == 2 && base > 0 && inside) { // resume: parked (T, C) + what the front phase wrote to the outputs
+        T = a.state[sp];
+        C0 = a.state[a.plane + sp];
+        C1 = a.state[2 * a.plane + sp];
+        C2 = a.state[3 * a.plane + sp];
+        if (T < 0.f) done = was_done = true;
+        ncontrib = (int)a.n_contrib[sp];
+        end_T = a.final_T[sp];
+        hit_id = a.out_hit_depth[pix_id];
+        hit = hit_id >= 0;
+        hit_color_id = a.out_hit_color[pix_id];
+        hit_cw = a.out_hit_cw[pix_id];
+        cw_max = hit_color_id >= 0 ? hit_cw : -1.f;
+        hit_dw = a.out_hit_dw[pix_id];
+        depth_ = a.out_depth[pix_id];
+    }
 
-    for (int i = 0; i < rounds; i++) {
+    int i = 0;
+    for (; i < rounds; i++) {
         if (__syncthreads_count(done) == 256) break;
         const int progress = i * 256 + tid;
         const int n = min(256, total - i * 256);
         if (progress < total) {
-            const int id = (int)a.point_list[range.x + progress];
+            const int id = (int)point_list[range.x + progress];
             const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
             const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
             const float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
@@ -717,7 +829,6 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
                     depth_ = hz;
                 else
                     depth_ = a.depth[id];
-                const size_t sp = (size_t)tile * 256 + ly * 16 + lx;
                 a.hit_geo[sp] = ncx;
                 a.hit_geo[a.plane + sp] = ncy;
                 a.hit_geo[2 * a.plane + sp] = ncz;
@@ -747,17 +858,29 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
                     const unsigned m = __match_any_sync(__activemask(), id);
                     if (lane == __ffs(m) - 1) atomicAdd(&a.n_touched[id], __popc(m));
                 }
-                last_j = j;
-                last_i = i;
+                ncontrib = base + i * 256 + j + 1;
                 end_T = test_T;
             }
             T = test_T;
         }
     }
-    if (inside) {
-        const size_t sp = (size_t)tile * 256 + ly * 16 + lx;
+    if (tid == 0 && a.status) atomicAdd(&a.status[DQO_ST_WALKED], min(total, i * 256));
+    if (PHASE == 1) {
+        const bool unfinished = __syncthreads_count(done) < 256;
+        if (tid == 0) {
+            a.unfinished[tile] = unfinished ? 1 : 0;
+            if (unfinished) atomicAdd(&a.status[DQO_ST_UNFINISHED], 1);
+        }
+        if (unfinished && inside) {
+            a.state[sp] = done ? -1.0f : T;
+            a.state[a.plane + sp] = C0;
+            a.state[2 * a.plane + sp] = C1;
+            a.state[3 * a.plane + sp] = C2;
+        }
+    }
+    if (inside && !was_done) {
         a.final_T[sp] = end_T;
-        a.n_contrib[sp] = (uint32_t)(last_i * 256 + last_j + 1);
+        a.n_contrib[sp] = (uint32_t)ncontrib;
         a.out_color[pix_id] = ffma(T, a.bg[0], C0);
         a.out_color[HW + pix_id] = ffma(T, a.bg[1], C1);
         a.out_color[2 * HW + pix_id] = ffma(T, a.bg[2], C2);
@@ -792,13 +915,17 @@ __global__ void export_instances_kernel(int64_t capacity, const int *__restrict_
 }
 __global__ void export_pixels_kernel(int W, int H, int grid_x, const uint32_t *__restrict__ n_contrib,
                                      const float *__restrict__ final_T, const uint2 *__restrict__ ranges,
-                                     uint32_t *out_nc, float *out_T) {
+                                     const uint2 *__restrict__ ranges_b, uint32_t *out_nc, float *out_T) {
     const int tile = blockIdx.x, tid = threadIdx.x;
     const int lx = tid & 15, ly = tid >> 4;
     const int px = (tile % grid_x) * 16 + lx, py = (tile / grid_x) * 16 + ly;
     if (px >= W || py >= H) return;
     const uint2 r = ranges[tile];
-    const bool rendered = r.x != r.y;
+    bool rendered = r.x != r.y;
+    if (ranges_b) {
+        const uint2 rb = ranges_b[tile];
+        rendered |= rb.x != rb.y;
+    }
     const size_t sp = (size_t)tile * 256 + tid;
     if (out_nc) out_nc[(size_t)py * W + px] = rendered ? n_contrib[sp] : 0u;
     if (out_T) out_T[(size_t)py * W + px] = rendered ? final_T[sp] : 1.0f;
@@ -950,10 +1077,23 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     const float focal_x = s->W / (2.0f * s->tanfovx);
     GeomLayout GL;
     BinLayout BL;
-    const uint32_t *point_list = nullptr;
     const float4 *rec = nullptr;
     const float *depth = nullptr;
     const bool keys16 = T < 65535;
+    const bool two_phase = P > 0 && s->front_instances > 0;
+    const int64_t front = two_phase ? s->front_instances : 0, back = two_phase ? s->back_instances : 0;
+    if (two_phase && (front % 256 != 0 || back <= 0 || front + back > capacity)) {
+        set_error("dqo_rast_forward: front_instances must be a multiple of 256 and front + back instances must fit the "
+                  "instance capacity");
+        return DQO_ERR_INVALID_ARG;
+    }
+    uint2 *ranges_b = two_phase ? (uint2 *)(img + IL.ranges_b) : nullptr;
+    if (two_phase) DQO_CUDA_CHECK(cudaMemsetAsync(ranges_b, 0, (size_t)T * sizeof(uint2), stream));
+    uint32_t *vals_in = nullptr, *vals_out = nullptr;
+    char *keys_in = nullptr, *keys_out = nullptr, *cub_tmp = nullptr;
+    size_t cub_tmp_bytes = 0;
+    const uint32_t *d_order = nullptr, *d_tiles = nullptr, *d_offsets = nullptr, *d_mask_bits = nullptr;
+    const uint2 *d_rect = nullptr;
     if (P > 0) {
         if (make_geom_layout(P, &GL)) return DQO_ERR_WORKSPACE;
         if (make_bin_layout(capacity, &BL)) return DQO_ERR_WORKSPACE;
@@ -1018,49 +1158,25 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         DQO_LAUNCH_CHECK("scan", debug, stream);
         stage_mark(stream, ST_SCAN);
 
-        uint32_t *vals_in = (uint32_t *)(bin + BL.vals_in), *vals_out = (uint32_t *)(bin + BL.vals_out);
-        const int64_t nthreads = capacity > P ? capacity : P;
-        const unsigned dup_blocks = (unsigned)((nthreads + 255) / 256);
-        const int bit = (int)higher_msb((uint32_t)T);
-        cub_bytes = BL.cub_bytes;
-        if (keys16) {
-            uint16_t *keys_in = (uint16_t *)(bin + BL.keys_in), *keys_out = (uint16_t *)(bin + BL.keys_out);
-            duplicate_kernel<uint16_t><<<dup_blocks, 256, 0, stream>>>(P, capacity, order, pa.tiles, offsets, pa.rect, mask_bits,
-                                                                      IL.mask_words, IL.tiles_x, keys_in, vals_in, status);
-            DQO_LAUNCH_CHECK("duplicate", debug, stream);
-            stage_mark(stream, ST_DUPLICATE);
-            DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(bin + BL.cub, cub_bytes, (const uint16_t *)keys_in, keys_out,
-                                                           (const uint32_t *)vals_in, vals_out, (int)capacity, 0,
-                                                           bit < 16 ? bit : 16, stream));
-            DQO_LAUNCH_CHECK("tile sort", debug, stream);
-            stage_mark(stream, ST_TILE_SORT);
-            tile_ranges_kernel<uint16_t><<<(unsigned)((capacity + 2047) / 2048), 256, 0, stream>>>(capacity, keys_out, status, ranges);
-        } else {
-            uint32_t *keys_in = (uint32_t *)(bin + BL.keys_in), *keys_out = (uint32_t *)(bin + BL.keys_out);
-            duplicate_kernel<uint32_t><<<dup_blocks, 256, 0, stream>>>(P, capacity, order, pa.tiles, offsets, pa.rect, mask_bits,
-                                                                      IL.mask_words, IL.tiles_x, keys_in, vals_in, status);
-            DQO_LAUNCH_CHECK("duplicate", debug, stream);
-            stage_mark(stream, ST_DUPLICATE);
-            DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(bin + BL.cub, cub_bytes, (const uint32_t *)keys_in, keys_out,
-                                                           (const uint32_t *)vals_in, vals_out, (int)capacity, 0, bit, stream));
-            DQO_LAUNCH_CHECK("tile sort", debug, stream);
-            stage_mark(stream, ST_TILE_SORT);
-            tile_ranges_kernel<uint32_t><<<(unsigned)((capacity + 2047) / 2048), 256, 0, stream>>>(capacity, keys_out, status, ranges);
-        }
-        DQO_LAUNCH_CHECK("tile ranges", debug, stream);
-        stage_mark(stream, ST_RANGES);
-        point_list = vals_out;
+        vals_in = (uint32_t *)(bin + BL.vals_in);
+        vals_out = (uint32_t *)(bin + BL.vals_out);
+        keys_in = bin + BL.keys_in;
+        keys_out = bin + BL.keys_out;
+        cub_tmp = bin + BL.cub;
+        cub_tmp_bytes = BL.cub_bytes;
+        d_order = order;
+        d_tiles = pa.tiles;
+        d_offsets = offsets;
+        d_rect = pa.rect;
+        d_mask_bits = mask_bits;
     }
-    compact_tiles_kernel<<<1, 1024, 0, stream>>>(T, ranges, tile_indices, status);
-    DQO_LAUNCH_CHECK("compact tiles", debug, stream);
-    stage_mark(stream, ST_COMPACT);
 
     RenderArgs ra;
     ra.W = s->W; ra.H = s->H; ra.grid_x = IL.tiles_x;
     ra.fx = focal_x; ra.fy = focal_y; ra.cx = s->cx; ra.cy = s->cy; ra.scale_mod = s->scale_modifier;
     ra.opaque_thr = s->opaque_threshold; ra.depth_thr = s->depth_threshold; ra.normal_thr = s->normal_threshold;
     ra.T_thr = s->T_threshold;
-    ra.ranges = ranges; ra.point_list = point_list; ra.rec = rec; ra.depth = depth;
+    ra.ranges = ranges; ra.point_list = vals_out; ra.rec = rec; ra.depth = depth;
     ra.view = viewmatrix; ra.means3D = means3D; ra.scales = scales; ra.rotations = rotations; ra.bg = background;
     ra.n_contrib = (uint32_t *)(img + IL.n_contrib);
     ra.final_T = (float *)(img + IL.final_T);
@@ -1069,8 +1185,96 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     ra.out_color = out_color; ra.out_depth = out_depth; ra.out_hit_cw = out_hit_color_weight;
     ra.out_hit_dw = out_hit_depth_weight; ra.out_T = out_T; ra.out_hit_depth = out_hit_depth;
     ra.out_hit_color = out_hit_color; ra.n_touched = s->need_n_touched ? n_touched : nullptr;
-    render_forward_kernel<<<T, 256, 0, stream>>>(ra);
-    DQO_LAUNCH_CHECK("render forward", debug, stream);
+    ra.ranges_b = ranges_b; ra.point_list_b = vals_out ? vals_out + front : nullptr;
+    ra.unfinished = (int *)(img + IL.unfinished);
+    ra.state = (float *)(img + IL.state);
+    ra.status = status;
+
+    const int bit = (int)higher_msb((uint32_t)T);
+    const int sort_bits = keys16 ? (bit < 16 ? bit : 16) : bit;
+    const size_t ksz = keys16 ? 2 : 4;
+    // one binning phase: duplicate -> stable sort by tile id -> ranges.  `n` = sort size (host constant).
+    auto bin_phase = [&](int mode, int64_t n, int64_t at, const uint32_t *tiles_rank, const uint32_t *offs,
+                         const uint32_t *bits, int count_word, uint2 *out_ranges) -> int {
+        void *kin = keys_in + at * ksz, *kout = keys_out + at * ksz;
+        uint32_t *vin = vals_in + at, *vout = vals_out + at;
+        const int64_t nthreads = (mode == 0 && n > P) ? n : P;
+        const unsigned blocks = (unsigned)((nthreads + 255) / 256);
+        if (mode != 0) DQO_CUDA_CHECK(cudaMemsetAsync(kin, 0xFF, (size_t)n * ksz, stream));
+#define DQO_DUP(KT, MODE)                                                                                              \
+    duplicate_kernel<KT, MODE><<<blocks, 256, 0, stream>>>(P, n, d_order, d_tiles, tiles_rank, offs, d_rect, bits,     \
+                                                           IL.mask_words, IL.tiles_x, (KT *)kin, vin, status)
+        if (keys16) {
+            if (mode == 0) DQO_DUP(uint16_t, 0); else if (mode == 1) DQO_DUP(uint16_t, 1); else DQO_DUP(uint16_t, 2);
+        } else {
+            if (mode == 0) DQO_DUP(uint32_t, 0); else if (mode == 1) DQO_DUP(uint32_t, 1); else DQO_DUP(uint32_t, 2);
+        }
+#undef DQO_DUP
+        DQO_LAUNCH_CHECK("duplicate", debug, stream);
+        if (mode != 2) stage_mark(stream, ST_DUPLICATE);
+        size_t tmp = cub_tmp_bytes;
+        if (keys16) {
+            DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, (const uint16_t *)kin, (uint16_t *)kout,
+                                                           (const uint32_t *)vin, vout, (int)n, 0, sort_bits, stream));
+        } else {
+            DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, (const uint32_t *)kin, (uint32_t *)kout,
+                                                           (const uint32_t *)vin, vout, (int)n, 0, sort_bits, stream));
+        }
+        DQO_LAUNCH_CHECK("tile sort", debug, stream);
+        if (mode != 2) stage_mark(stream, ST_TILE_SORT);
+        const unsigned rb = (unsigned)((n + 2047) / 2048);
+        if (keys16)
+            tile_ranges_kernel<uint16_t><<<rb, 256, 0, stream>>>(n, (const uint16_t *)kout, status, count_word, out_ranges);
+        else
+            tile_ranges_kernel<uint32_t><<<rb, 256, 0, stream>>>(n, (const uint32_t *)kout, status, count_word, out_ranges);
+        DQO_LAUNCH_CHECK("tile ranges", debug, stream);
+        if (mode != 2) stage_mark(stream, ST_RANGES);
+        return DQO_OK;
+    };
+
+    if (!two_phase) {
+        if (P > 0) {
+            const int rc = bin_phase(0, capacity, 0, nullptr, d_offsets, d_mask_bits, DQO_ST_NUM_RENDERED, ranges);
+            if (rc) return rc;
+        }
+        compact_tiles_kernel<<<1, 1024, 0, stream>>>(T, ranges, nullptr, tile_indices, status);
+        DQO_LAUNCH_CHECK("compact tiles", debug, stream);
+        stage_mark(stream, ST_COMPACT);
+        render_forward_kernel<0><<<T, 256, 0, stream>>>(ra);
+        DQO_LAUNCH_CHECK("render forward", debug, stream);
+        stage_mark(stream, ST_RENDER_FWD);
+        return DQO_OK;
+    }
+
+    // two-phase: nearest Gaussians first, the rest only into the tiles that are still unfinished
+    char *geom = (char *)geom_buffer;
+    uint32_t *tiles_b = (uint32_t *)(geom + GL.tiles_b), *offsets_b = (uint32_t *)(geom + GL.offsets_b);
+    uint32_t *mask_bits_b = (uint32_t *)(img + IL.mask_bits_b);
+    int rc = bin_phase(1, front, 0, nullptr, d_offsets, d_mask_bits, DQO_ST_R_FRONT, ranges);
+    if (rc) return rc;
+    render_forward_kernel<1><<<T, 256, 0, stream>>>(ra);
+    DQO_LAUNCH_CHECK("render forward (front)", debug, stream);
+    stage_mark(stream, ST_RENDER_FRONT);
+    {
+        const int nw = IL.tiles_y * IL.mask_words;
+        mask_unfinished_kernel<<<(nw + 255) / 256, 256, 0, stream>>>(IL.tiles_x, IL.tiles_y, IL.mask_words, d_mask_bits,
+                                                                      ra.unfinished, mask_bits_b);
+        DQO_LAUNCH_CHECK("unfinished mask", debug, stream);
+        count_back_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, front, d_order, d_tiles, d_offsets, d_rect, mask_bits_b,
+                                                               IL.mask_words, tiles_b);
+        DQO_LAUNCH_CHECK("back count", debug, stream);
+        size_t tmp = GL.cub_bytes;
+        DQO_CUDA_CHECK(cub::DeviceScan::InclusiveSum(geom + GL.cub, tmp, (const uint32_t *)tiles_b, offsets_b, P, stream));
+        DQO_LAUNCH_CHECK("back scan", debug, stream);
+    }
+    rc = bin_phase(2, back, front, tiles_b, offsets_b, mask_bits_b, DQO_ST_R_BACK, ranges_b);
+    if (rc) return rc;
+    stage_mark(stream, ST_BACK_BIN);
+    compact_tiles_kernel<<<1, 1024, 0, stream>>>(T, ranges, ranges_b, tile_indices, status);
+    DQO_LAUNCH_CHECK("compact tiles", debug, stream);
+    stage_mark(stream, ST_COMPACT);
+    render_forward_kernel<2><<<T, 256, 0, stream>>>(ra);
+    DQO_LAUNCH_CHECK("render forward (back)", debug, stream);
     stage_mark(stream, ST_RENDER_FWD);
     return DQO_OK;
 }
@@ -1082,6 +1286,10 @@ extern "C" int dqo_rast_export_state(const dqo_rast_settings *s, const void *geo
                                      float *conic_opacity, float *rgb, uint32_t *tiles_touched, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!s || !image_buffer || !status) return DQO_ERR_INVALID_ARG;
+    if (s->front_instances > 0 && (sorted_keys || point_list || ranges_out)) {
+        set_error("dqo_rast_export_state: the full sorted instance list only exists in single-phase mode (front_instances = 0)");
+        return DQO_ERR_INVALID_ARG;
+    }
     ImgLayout IL;
     make_img_layout(s->W, s->H, &IL);
     const char *img = (const char *)image_buffer;
@@ -1091,7 +1299,9 @@ extern "C" int dqo_rast_export_state(const dqo_rast_settings *s, const void *geo
     if (n_contrib || final_T)
         export_pixels_kernel<<<IL.T, 256, 0, stream>>>(s->W, s->H, IL.tiles_x, (const uint32_t *)(img + IL.n_contrib),
                                                        (const float *)(img + IL.final_T),
-                                                       (const uint2 *)(img + IL.ranges), n_contrib, final_T);
+                                                       (const uint2 *)(img + IL.ranges),
+                                                       s->front_instances > 0 ? (const uint2 *)(img + IL.ranges_b) : nullptr,
+                                                       n_contrib, final_T);
     if (P > 0) {
         GeomLayout GL;
         BinLayout BL;

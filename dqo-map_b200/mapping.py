@@ -171,9 +171,11 @@ class FusedMappingStep:
     ORDER = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")
 
     def __init__(self, params, lrs, width, height, color_weight=0.8, depth_weight=1.0, depth_err_thres=0.1,
-                 confidence=None, betas=(0.9, 0.999), eps=1e-15, capacity=None, need_n_touched=True):
+                 confidence=None, betas=(0.9, 0.999), eps=1e-15, capacity=None, need_n_touched=True,
+                 front_instances=0, back_instances=0):
         L = lib()
         self.p = params
+        self.front, self.back = int(front_instances), int(back_instances)
         for k in self.ORDER:
             t = params[k]
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
@@ -223,7 +225,8 @@ class FusedMappingStep:
                            ptr(rs.viewmatrix), ptr(rs.projmatrix), ptr(rs.campos), ptr(rs.bg), self.cw, self.dw, self.thr)
         s = _make_settings(self.P, int(rs.sh_degree), self.M, self.W, self.H, rs.tanfovx, rs.tanfovy, rs.cx, rs.cy,
                            rs.scale_modifier, rs.color_sigma, rs.opaque_threshold, rs.depth_threshold,
-                           rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, self.need_n_touched)
+                           rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, self.need_n_touched,
+                           self.front, self.back)
         self.step += 1
         with torch.cuda.device(self.dev):
             check(lib().dqo_mapping_step(s, mp, kf, self.step, float(self.betas[0]), float(self.betas[1]),
@@ -234,8 +237,17 @@ class FusedMappingStep:
     def check(self):
         host = self.status.tolist()
         if host[_lib.ST_OVERFLOW]:
-            raise _lib.DqoError("instance capacity %d exceeded (R = %d)" % (self.capacity, host[_lib.ST_NUM_RENDERED]))
+            self.step -= 1  # the device skipped the update: the step did not happen
+            raise _lib.DqoError("instance capacity exceeded (capacity %d, front %d, back %d; R = %d, back needs %d): the "
+                                "step was skipped on the device, repeat it with larger buffers"
+                                % (self.capacity, self.front, self.back, host[_lib.ST_NUM_RENDERED], host[_lib.ST_R_BACK]))
         return host
+
+    def set_binning(self, front_instances, back_instances):
+        """Switch between single-phase (0, 0) and two-phase binning; front + back must fit the capacity."""
+        if front_instances and front_instances + back_instances > self.capacity:
+            raise ValueError("front + back instances exceed the capacity of this step's workspace")
+        self.front, self.back = int(front_instances), int(back_instances)
 
     def rendered(self):
         """Views (no copy) of the colour [3,H,W], depth [1,H,W], depth index [1,H,W] and T [1,H,W] of the last step."""

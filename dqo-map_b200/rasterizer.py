@@ -13,6 +13,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import RastSettings, check, lib, ptr
+from .binning_policy import BinningPolicy
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -44,6 +45,24 @@ class GaussianRasterizationSettings(NamedTuple):
 # ---------------------------------------------------------------------------------------------------
 _capacity_hint = {}
 NEED_N_TOUCHED = True  # reference behaviour (forward.cu:833-835); set False to skip the per-pair counter
+# "auto": binning_policy.BinningPolicy picks single-phase or occlusion-aware two-phase binning per device from the status
+# words of earlier calls (identical results either way); "single": always bin every instance, which is what
+# dqo_rast_export_state needs to rebuild the reference's full sorted list.
+BINNING = "auto"
+_FIXED = (0, 0)
+_policy = {}
+
+
+def set_binning_mode(mode, front_instances=0, back_instances=0):
+    """'auto' (default), 'single', or 'fixed' with explicit (front_instances, back_instances) -- the latter raises on
+    overflow instead of adapting (tests, experiments)."""
+    global BINNING, _FIXED
+    if mode not in ("auto", "single", "fixed"):
+        raise ValueError("binning mode must be 'auto', 'single' or 'fixed'")
+    if mode == "fixed" and (front_instances <= 0 or front_instances % 256 or back_instances <= 0):
+        raise ValueError("fixed binning needs front_instances (multiple of 256) and back_instances > 0")
+    BINNING, _FIXED = mode, (int(front_instances), int(back_instances))
+    _policy.clear()
 
 
 def _stream():
@@ -59,10 +78,11 @@ def _f32c(t):
 
 
 def _make_settings(P, D, M, W, H, tanfovx, tanfovy, cx, cy, scale_modifier, color_sigma, opaque_threshold,
-                   depth_threshold, normal_threshold, T_threshold, prefiltered, debug, need_n_touched=True):
+                   depth_threshold, normal_threshold, T_threshold, prefiltered, debug, need_n_touched=True,
+                   front_instances=0, back_instances=0):
     return RastSettings(P, D, M, W, H, tanfovx, tanfovy, cx, cy, scale_modifier, color_sigma, opaque_threshold,
                         depth_threshold, normal_threshold, T_threshold, int(bool(prefiltered)), int(bool(debug)),
-                        int(bool(need_n_touched)))
+                        int(bool(need_n_touched)), int(front_instances), int(back_instances))
 
 
 class ForwardState:
@@ -111,22 +131,27 @@ def _forward_impl(background, means3D, colors, opacity, scales, rotations, scale
     status = torch.empty((_lib.ST_WORDS,), **i32)
 
     st = ForwardState()
-    st.settings = _make_settings(P, int(degree), M, W, H, tan_fovx, tan_fovy, cx, cy, scale_modifier, color_sigma,
-                                 opaque_threshold, hit_depth_threshold, hit_normal_threshold, T_threshold, prefiltered,
-                                 debug, NEED_N_TOUCHED)
     st.image = torch.empty((L.dqo_rast_image_bytes(W, H),), dtype=torch.uint8, device=dev)
     st.tile_indices, st.status = tile_indices, status
     st.geom = torch.empty((L.dqo_rast_geom_bytes(P) if P > 0 else 0,), dtype=torch.uint8, device=dev)
     key = (dev.index, )
+    policy = _policy.setdefault(key, BinningPolicy()) if (BINNING == "auto" and sync) else None
     capacity = max(_capacity_hint.get(key, 0), 4 * P, 1 << 16) if P > 0 else 0
     while True:
-        st.capacity = capacity
-        st.binning = torch.empty((L.dqo_rast_binning_bytes(capacity) if P > 0 else 0,), dtype=torch.uint8, device=dev)
+        front, back = policy.plan(1 << 30) if (policy is not None and P > 0) else (0, 0)
+        if BINNING == "fixed" and P > 0:
+            front, back = _FIXED
+        cap = front + back if front > 0 else capacity
+        st.settings = _make_settings(P, int(degree), M, W, H, tan_fovx, tan_fovy, cx, cy, scale_modifier, color_sigma,
+                                     opaque_threshold, hit_depth_threshold, hit_normal_threshold, T_threshold,
+                                     prefiltered, debug, NEED_N_TOUCHED, front, back)
+        st.capacity = cap
+        st.binning = torch.empty((L.dqo_rast_binning_bytes(cap) if P > 0 else 0,), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             code = L.dqo_rast_forward(
                 st.settings, ptr(bg_c), ptr(means_c), ptr(sh_c), ptr(colors_c), ptr(opac_c), ptr(scales_c), ptr(rot_c),
                 ptr(cov_c), ptr(view_c), ptr(proj_c), ptr(campos_c), ptr(mask_c), ptr(st.geom), ptr(st.binning),
-                capacity, ptr(st.image), ptr(tile_indices), ptr(out_color), ptr(out_depth), ptr(out_hit_depth),
+                cap, ptr(st.image), ptr(tile_indices), ptr(out_color), ptr(out_depth), ptr(out_hit_depth),
                 ptr(out_hit_color), ptr(out_hit_cw), ptr(out_hit_dw), ptr(out_T), ptr(radii), ptr(n_touched),
                 ptr(status), _stream())
         check(code, "dqo_rast_forward")
@@ -135,11 +160,15 @@ def _forward_impl(background, means3D, colors, opacity, scales, rotations, scale
             break
         host = status.tolist()  # the single host synchronisation of the forward, after all launches
         st.status_host = host
-        if not host[_lib.ST_OVERFLOW]:
-            _capacity_hint[key] = max(_capacity_hint.get(key, 0), int(host[_lib.ST_NUM_RENDERED] * 1.25) + 1024)
+        retry = policy.update(host, front, back) if policy is not None else bool(host[_lib.ST_OVERFLOW])
+        if retry and BINNING == "fixed":
+            raise _lib.DqoError("fixed two-phase binning overflowed: back phase needs %d instances, %d given"
+                                % (host[_lib.ST_R_BACK], back))
+        if front == 0:
+            capacity = int(host[_lib.ST_NUM_RENDERED] * 1.25) + 1024
+            _capacity_hint[key] = capacity if retry else max(_capacity_hint.get(key, 0), capacity)
+        if not retry:
             break
-        capacity = int(host[_lib.ST_NUM_RENDERED] * 1.25) + 1024
-        _capacity_hint[key] = capacity
     outs = (out_color, out_depth, out_hit_color, out_hit_depth, out_hit_cw, out_hit_dw, out_T, radii, n_touched)
     return st, outs
 
@@ -181,9 +210,12 @@ class RasterPipeline:
     `backward()` only enqueue kernels.  `check()` reads the device status words (one host sync) and raises if the
     instance capacity was exceeded — call it whenever convenient, e.g. together with the loss read-back."""
 
-    def __init__(self, P, M, W, H, capacity, device):
+    def __init__(self, P, M, W, H, capacity, device, front_instances=0, back_instances=0):
         L = lib()
         dev = torch.device(device)
+        if front_instances and front_instances + back_instances > capacity:
+            raise ValueError("front + back instances exceed the capacity")
+        self.front, self.back = int(front_instances), int(back_instances)
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         u8 = dict(dtype=torch.uint8, device=dev)
@@ -208,7 +240,8 @@ class RasterPipeline:
                 need_n_touched=True):
         self.settings = _make_settings(self.P, int(rs.sh_degree), self.M, self.W, self.H, rs.tanfovx, rs.tanfovy, rs.cx,
                                        rs.cy, rs.scale_modifier, rs.color_sigma, rs.opaque_threshold, rs.depth_threshold,
-                                       rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, need_n_touched)
+                                       rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, need_n_touched,
+                                       self.front, self.back)
         self._in = (rs, means3D, shs, colors_precomp, scales, rotations)
         check(lib().dqo_rast_forward(
             self.settings, ptr(rs.bg), ptr(means3D), ptr(shs), ptr(colors_precomp), ptr(opacities), ptr(scales),
@@ -229,9 +262,38 @@ class RasterPipeline:
     def check(self):
         host = self.status.tolist()
         if host[_lib.ST_OVERFLOW]:
-            raise _lib.DqoError("instance capacity %d exceeded (R = %d): results invalid, re-create the pipeline larger"
-                                % (self.capacity, host[_lib.ST_NUM_RENDERED]))
+            raise _lib.DqoError("instance capacity %d (front %d, back %d) exceeded (R = %d, back needs %d): results invalid, "
+                                "re-create the pipeline larger" % (self.capacity, self.front, self.back,
+                                                                   host[_lib.ST_NUM_RENDERED], host[_lib.ST_R_BACK]))
         return host
+
+
+def plan_binning(rs, means3D, opacities, scales, rotations, tile_mask, shs=None, colors_precomp=None):
+    """Sizing helper for the pre-allocated paths (RasterPipeline, mapping.FusedMappingStep): one synchronous
+    single-phase forward on the given view and, when binning_policy opts for two-phase binning, one two-phase trial.
+    Returns (R, front_instances, back_instances); front == 0 means single phase (capacity ~ 1.05 R), otherwise the
+    buffers need front + back instances."""
+    P = means3D.shape[0]
+    M = shs.shape[1] if shs is not None else 0
+    H, W = int(rs.image_height), int(rs.image_width)
+    probe = RasterPipeline(P, M, W, H, max(4 * P, 1 << 16), means3D.device)
+    while True:
+        probe.forward(rs, means3D, opacities, scales, rotations, tile_mask, shs=shs, colors_precomp=colors_precomp)
+        host = probe.status.tolist()
+        if not host[_lib.ST_OVERFLOW]:
+            break
+        probe = RasterPipeline(P, M, W, H, int(host[_lib.ST_NUM_RENDERED] * 1.05) + 4096, means3D.device)
+    R = host[_lib.ST_NUM_RENDERED]
+    policy = BinningPolicy()
+    policy.update(host, 0, 0)
+    front, back = policy.plan(1 << 30)
+    del probe
+    if front > 0:
+        trial = RasterPipeline(P, M, W, H, front + back, means3D.device, front, back)
+        trial.forward(rs, means3D, opacities, scales, rotations, tile_mask, shs=shs, colors_precomp=colors_precomp)
+        policy.update(trial.check(), front, back)
+        front, back = policy.plan(1 << 30)
+    return R, front, back
 
 
 # ---------------------------------------------------------------------------------------------------

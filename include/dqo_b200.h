@@ -31,8 +31,9 @@ int dqo_abi_version(void);
 const char *dqo_last_error(void);
 /* Instrumentation (bench.py): number of this library's own kernel launches so far (CUB library calls count as one),
  * and optional per-stage CUDA-event timing of the rasterizer on the launching stream.  Stage order:
- * 0 begin-fwd, 1 preprocess, 2 depth sort, 3 scan, 4 duplicate, 5 tile sort, 6 ranges, 7 compact, 8 render-fwd,
- * 9 begin-bwd, 10 render-bwd, 11 gaussian-bwd.  dqo_profile_read synchronises on the recorded events. */
+ * 0 begin-fwd, 1 preprocess, 2 depth sort, 3 scan, 4 duplicate, 5 tile sort, 6 ranges, 7 front blend and 8 back-phase
+ * binning (two-phase binning only), 9 compact, 10 render-fwd, 11 begin-bwd, 12 render-bwd, 13 gaussian-bwd; each value is
+ * the time since the previous recorded mark.  dqo_profile_read synchronises on the recorded events. */
 long long dqo_launch_count(void);
 void dqo_profile_enable(int on);
 int dqo_profile_read(float *ms_out, int n);
@@ -58,6 +59,14 @@ typedef struct dqo_rast_settings {
     int32_t prefiltered;
     int32_t debug;            /* nonzero: synchronise after every stage and report the failing one */
     int32_t need_n_touched;   /* 1 = reference behaviour (count per-Gaussian touches, forward.cu:833-835) */
+    /* Occlusion-aware two-phase binning (results identical to single-phase).  0 = single phase: all R
+     * instances are binned and sorted, `instance_capacity` must hold R.  > 0: only the nearest Gaussians (in depth-rank
+     * order) whose instances fit into `front_instances` are binned first; tiles whose pixels all terminated are done;
+     * the remaining Gaussians are then binned only into the unfinished tiles, into `back_instances` slots.
+     * front_instances (a multiple of 256) + back_instances <= instance_capacity; DQO_ST_OVERFLOW is raised when the
+     * back phase needs more than back_instances.  The same values must be passed to the backward pass. */
+    int32_t front_instances;
+    int32_t back_instances;
 } dqo_rast_settings;
 
 /* status words written on the device by the forward pass (int32[8]) */
@@ -65,6 +74,10 @@ typedef struct dqo_rast_settings {
 #define DQO_ST_TILE_NUM 1     /* number of non-empty tiles (rasterizer_impl.cu:365) */
 #define DQO_ST_OVERFLOW 2     /* 1 if R exceeded the instance capacity: outputs are invalid, re-run larger */
 #define DQO_ST_NUM_VISIBLE 3  /* Gaussians with radii > 0 */
+#define DQO_ST_R_FRONT 4      /* two-phase: instances binned in the front phase */
+#define DQO_ST_R_BACK 5       /* two-phase: instances needed by the back phase */
+#define DQO_ST_WALKED 6       /* list entries staged by the forward blend before early termination (all phases) */
+#define DQO_ST_UNFINISHED 7   /* two-phase: rendered tiles still unfinished after the front phase */
 #define DQO_ST_WORDS 8
 
 /* Workspace sizing (replaces the three resize callbacks of CudaRasterizer::Rasterizer::forward,
@@ -258,8 +271,9 @@ typedef struct dqo_keyframe {
 } dqo_keyframe;
 size_t dqo_mapping_step_workspace_bytes(int32_t P, int32_t M, int32_t W, int32_t H, int64_t instance_capacity);
 /* loss_out: device float[4] {total, colour, depth, -}; counts_out: device int32[2]; status: device int32[DQO_ST_WORDS]
- * (check DQO_ST_OVERFLOW together with the loss read-back; on overflow the parameters were still stepped with zero
- * image gradients from an empty render, so callers size the capacity with a margin: see mapping.FusedMappingStep). */
+ * (check DQO_ST_OVERFLOW together with the loss read-back; on overflow the render is invalid and the Adam update is
+ * skipped on the device -- parameters and moments are untouched, repeat the step with a larger capacity and the same
+ * `step` number: see mapping.FusedMappingStep.check). */
 int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params *p, const dqo_keyframe *kf, int32_t step,
                      double beta1, double beta2, double eps, void *workspace, int64_t instance_capacity,
                      float *loss_out, int32_t *counts_out, int32_t *status, void *stream);

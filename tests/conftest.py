@@ -30,3 +30,12 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def _default_binning_mode(request):
+    """Every GPU test starts from the library default ('auto' binning policy, no remembered state)."""
+    if "gpu" in request.keywords:
+        from dqo_map_b200 import rasterizer
+        rasterizer.set_binning_mode("auto")
+    yield

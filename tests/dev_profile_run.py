@@ -14,9 +14,12 @@ inp, cam, settings = bench.build_workload(cfg, dev, 0)
 P, H, W, M = inp["xyz"].shape[0], cam.image_height, cam.image_width, inp["shs"].shape[1]
 gc, gd = rh.make_pixel_grads(H, W, dev)
 rs = settings(rasterizer.GaussianRasterizationSettings)
-probe = rasterizer.rasterize_gaussians(*rh.raster_args(inp))
-pipe = rasterizer.RasterPipeline(P, M, W, H, int(probe[0] * 1.05) + 4096, dev)
-del probe
+R, front, back = rasterizer.plan_binning(rs, inp["xyz"], inp["opacity"], inp["scales"], inp["rotations"], inp["tile_mask"],
+                                         shs=inp["shs"])
+if len(sys.argv) > 3 and sys.argv[3] == "single":
+    front = back = 0
+print("R", R, "front", front, "back", back)
+pipe = rasterizer.RasterPipeline(P, M, W, H, (front + back) if front else int(R * 1.05) + 4096, dev, front, back)
 for _ in range(iters):
     pipe.forward(rs, inp["xyz"], inp["opacity"], inp["scales"], inp["rotations"], inp["tile_mask"], shs=inp["shs"])
     pipe.backward(gc, gd)

@@ -14,11 +14,16 @@ inp, cam, settings = bench.build_workload(cfg, dev, 0)
 P, H, W = inp["xyz"].shape[0], cam.image_height, cam.image_width
 rs = settings(rasterizer.GaussianRasterizationSettings)
 gt_color, gt_depth, mask = bench.make_keyframe(inp, cam, settings, rasterizer)
-probe = rasterizer.rasterize_gaussians(*rh.raster_args(inp))
+R, front, back = rasterizer.plan_binning(rs, inp["xyz"], inp["opacity"], inp["scales"], inp["rotations"], inp["tile_mask"],
+                                         shs=inp["shs"])
+if len(sys.argv) > 3 and sys.argv[3] == "single":
+    front = back = 0
+fback = int(back * 1.3) + 65536 if front else 0
+print("R", R, "front", front, "back", fback)
 fparams = {k: v.contiguous() for k, v in bench.raw_params(inp).items()}
 fstep = mapping.FusedMappingStep(fparams, bench.LRS, W, H, 0.8, 1.0, 0.1, confidence=torch.zeros(P, 1, device=dev),
-                                 capacity=int(probe[0] * 1.3) + 4096)
-del probe
+                                 capacity=(front + fback) if front else int(R * 1.3) + 4096, front_instances=front,
+                                 back_instances=fback)
 for _ in range(iters):
     t = fstep(rs, inp["tile_mask"], gt_color, gt_depth, mask)
 torch.cuda.synchronize()

@@ -159,6 +159,9 @@ def export_ours(st, P, W, H):
     rgb = torch.zeros((P, 3), dtype=torch.float32, device=dev)
     tiles_touched = torch.zeros((P,), dtype=torch.int32, device=dev)
     p = _lib.ptr
+    lists = st.settings.front_instances == 0  # the full sorted list only exists after single-phase binning
+    if not lists:
+        keys = plist = ranges = None
     _lib.check(L.dqo_rast_export_state(st.settings, p(st.geom), p(st.binning), st.capacity, p(st.image), p(st.status),
                                        p(keys), p(plist), p(ranges), p(ncontrib), p(final_T), p(means2D), p(depths),
                                        p(conic), p(rgb), p(tiles_touched), torch.cuda.current_stream().cuda_stream),
@@ -166,8 +169,10 @@ def export_ours(st, P, W, H):
     torch.cuda.synchronize()
     R = int(st.status[0].item())
     return {
-        "keys_sorted": keys.cpu().numpy().view(np.uint64)[:R], "point_list": plist.cpu().numpy().view(np.uint32)[:R],
-        "ranges": ranges.cpu().numpy().view(np.uint32), "n_contrib": ncontrib.cpu().numpy().view(np.uint32),
+        "keys_sorted": keys.cpu().numpy().view(np.uint64)[:R] if lists else None,
+        "point_list": plist.cpu().numpy().view(np.uint32)[:R] if lists else None,
+        "ranges": ranges.cpu().numpy().view(np.uint32) if lists else None,
+        "n_contrib": ncontrib.cpu().numpy().view(np.uint32),
         "accum_alpha": final_T.cpu().numpy(), "means2D": means2D.cpu().numpy(), "depths": depths.cpu().numpy(),
         "conic_opacity": conic.cpu().numpy(), "rgb": rgb.cpu().numpy(),
         "tiles_touched": tiles_touched.cpu().numpy().view(np.uint32),

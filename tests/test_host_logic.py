@@ -94,3 +94,49 @@ def test_fused_adam_accepts_reference_param_groups():
     opt = FusedAdam(groups, lr=0.0, eps=1e-15)
     assert [g["name"] for g in opt.param_groups] == ["xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation"]
     assert opt.step() is None  # no gradients -> nothing to do, no GPU touched
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# binning policy (pure host logic)
+# ---------------------------------------------------------------------------------------------------------------------
+def _status(R=0, overflow=0, r_front=0, r_back=0, walked=0, unfinished=0):
+    return [R, 100, overflow, 1000, r_front, r_back, walked, unfinished]
+
+
+def test_binning_policy_stays_single_for_small_or_fully_walked_scenes():
+    from dqo_map_b200.binning_policy import BinningPolicy
+    p = BinningPolicy()
+    assert p.plan(1 << 30) == (0, 0)
+    assert p.update(_status(R=500_000, walked=10_000), 0, 0) is False     # too small to bother
+    assert p.plan(1 << 30) == (0, 0)
+    assert p.update(_status(R=15_000_000, walked=12_000_000), 0, 0) is False  # nearly everything is read
+    assert p.plan(1 << 30) == (0, 0)
+    assert p.update(_status(R=15_000_000, overflow=1), 0, 0) is True
+
+
+def test_binning_policy_enters_tightens_and_leaves_two_phase():
+    from dqo_map_b200.binning_policy import BinningPolicy
+    p = BinningPolicy()
+    R = 15_000_000
+    p.update(_status(R=R, walked=1_200_000), 0, 0)
+    front, back = p.plan(1 << 30)
+    assert front % 256 == 0 and 2_000_000 <= front <= R // 2
+    assert front + back >= R  # first two-phase call cannot overflow
+    # observed: few unfinished tiles -> the back region shrinks to what was needed plus headroom
+    assert p.update(_status(R=R, r_front=front - 100, r_back=300_000, unfinished=40), front, back) is False
+    f2, b2 = p.plan(1 << 30)
+    assert f2 == front and 300_000 < b2 < back
+    # a harder keyframe overflows the back region: repeat with room for what it reported
+    assert p.update(_status(R=R, overflow=1, r_front=front - 100, r_back=2 * b2), f2, b2) is True
+    f3, b3 = p.plan(1 << 30)
+    assert b3 > 2 * b2
+    # a scene where nothing finishes early: give up and do not probe again immediately
+    assert p.update(_status(R=R, r_front=f3, r_back=R - f3, unfinished=3000), f3, b3) is False
+    assert p.plan(1 << 30) == (0, 0)
+    p.update(_status(R=R, walked=1_000_000), 0, 0)
+    assert p.plan(1 << 30) == (0, 0)  # cooling down
+    # capacity too small for the plan -> clipped or single phase, never an invalid pair
+    p2 = BinningPolicy()
+    p2.update(_status(R=R, walked=1_200_000), 0, 0)
+    f, b = p2.plan(1 << 20)
+    assert (f, b) == (0, 0) or (f % 256 == 0 and f + b <= 1 << 20)
