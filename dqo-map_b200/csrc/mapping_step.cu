@@ -175,6 +175,113 @@ __global__ void __launch_bounds__(256) adam_geometry_kernel(SmallArgs a) {
     }
 }
 
+// Same update with every flat tensor streamed in 128-bit accesses: blocks are split into five roles by index range.
+//   role 0  xyz      [3P]  plain Adam on g_means3D                        float4 chunks of the flat array
+//   role 1  scaling  [3P]  g * exp(x) (the saved activation)              float4 chunks
+//   role 2  opacity  [P]   g * o (1 - o)                                  float4 chunks
+//   role 3  rotation [P,4] normalisation backward, one Gaussian per thread (already one float4 per tensor)
+//   role 4  f_dc     [P,3] gradient gathered from the merged SH gradient (stride 3M), + confidence bump
+// Requires 16-byte aligned tensors (checked by the caller; adam_geometry_kernel is the fallback).
+struct FlatArgs {
+    SmallArgs s;
+    long long n4_vec3, n4_scalar; // float4 chunks of a [3P] / [P] array
+    unsigned nb_vec3, nb_scalar, nb_gauss;
+};
+__device__ __forceinline__ void adam4(float4 &p, const float4 g, float4 &m, float4 &v, const AdamScalars &k, float ss) {
+    adam_update(p.x, g.x, m.x, v.x, k, ss);
+    adam_update(p.y, g.y, m.y, v.y, k, ss);
+    adam_update(p.z, g.z, m.z, v.z, k, ss);
+    adam_update(p.w, g.w, m.w, v.w, k, ss);
+}
+// flat Adam over [begin of tail, n) for the (< 4) elements a float4 sweep leaves over
+__device__ __forceinline__ void adam_tail(float *p, float *m, float *v, const float *g, const float *act, int mode,
+                                          long long from, long long n, const AdamScalars &k, float ss) {
+    for (long long e = from + threadIdx.x; e < n; e += blockDim.x) {
+        float gg = g[e];
+        if (mode == 1) gg *= act[e];
+        if (mode == 2) gg *= act[e] * (1.0f - act[e]);
+        float pp = p[e], mm = m[e], vv = v[e];
+        adam_update(pp, gg, mm, vv, k, ss);
+        p[e] = pp; m[e] = mm; v[e] = vv;
+    }
+}
+__global__ void __launch_bounds__(256) adam_flat_kernel(FlatArgs fa) {
+    const SmallArgs &a = fa.s;
+    if (a.status[DQO_ST_OVERFLOW]) return;
+    unsigned b = blockIdx.x;
+    if (b < 2 * fa.nb_vec3) { // roles 0 / 1
+        const bool sc = b >= fa.nb_vec3;
+        if (sc) b -= fa.nb_vec3;
+        float *P_ = sc ? a.scaling : a.xyz, *M_ = sc ? a.m_sc : a.m_xyz, *V_ = sc ? a.v_sc : a.v_xyz;
+        const float *G_ = sc ? a.g_scales : a.g_means3D;
+        const float ss = a.k.step_size[sc ? 4 : 0];
+        const long long q = (long long)b * blockDim.x + threadIdx.x;
+        if (q < fa.n4_vec3) {
+            float4 g = reinterpret_cast<const float4 *>(G_)[q];
+            if (sc) {
+                const float4 e = reinterpret_cast<const float4 *>(a.act_scales)[q];
+                g.x *= e.x; g.y *= e.y; g.z *= e.z; g.w *= e.w;
+            }
+            float4 p = reinterpret_cast<float4 *>(P_)[q], m = reinterpret_cast<float4 *>(M_)[q], v = reinterpret_cast<float4 *>(V_)[q];
+            adam4(p, g, m, v, a.k, ss);
+            reinterpret_cast<float4 *>(P_)[q] = p;
+            reinterpret_cast<float4 *>(M_)[q] = m;
+            reinterpret_cast<float4 *>(V_)[q] = v;
+        }
+        if (b == 0) adam_tail(P_, M_, V_, G_, a.act_scales, sc ? 1 : 0, fa.n4_vec3 * 4, 3ll * a.P, a.k, ss);
+        return;
+    }
+    b -= 2 * fa.nb_vec3;
+    if (b < fa.nb_scalar) { // role 2
+        const float ss = a.k.step_size[3];
+        const long long q = (long long)b * blockDim.x + threadIdx.x;
+        if (q < fa.n4_scalar) {
+            float4 g = reinterpret_cast<const float4 *>(a.g_opacity)[q];
+            const float4 o = reinterpret_cast<const float4 *>(a.act_opacity)[q];
+            g.x *= o.x * (1.0f - o.x); g.y *= o.y * (1.0f - o.y); g.z *= o.z * (1.0f - o.z); g.w *= o.w * (1.0f - o.w);
+            float4 p = reinterpret_cast<float4 *>(a.opacity)[q], m = reinterpret_cast<float4 *>(a.m_op)[q],
+                   v = reinterpret_cast<float4 *>(a.v_op)[q];
+            adam4(p, g, m, v, a.k, ss);
+            reinterpret_cast<float4 *>(a.opacity)[q] = p;
+            reinterpret_cast<float4 *>(a.m_op)[q] = m;
+            reinterpret_cast<float4 *>(a.v_op)[q] = v;
+        }
+        if (b == 0) adam_tail(a.opacity, a.m_op, a.v_op, a.g_opacity, a.act_opacity, 2, fa.n4_scalar * 4, a.P, a.k, ss);
+        return;
+    }
+    b -= fa.nb_scalar;
+    const bool dc = b >= fa.nb_gauss;
+    if (dc) b -= fa.nb_gauss;
+    const int i = (int)(b * blockDim.x + threadIdx.x);
+    if (i >= a.P) return;
+    if (!dc) { // role 3: rotation, q = r / max(|r|, eps); dL/dr = (g - q (q . g)) / max(|r|, eps)
+        float4 r = reinterpret_cast<float4 *>(a.rotation)[i];
+        const float4 g = reinterpret_cast<const float4 *>(a.g_rot)[i];
+        const float nrm = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
+        const float d = fmaxf(nrm, 1e-12f);
+        const float qx = r.x / d, qy = r.y / d, qz = r.z / d, qw = r.w / d;
+        const float qg = qx * g.x + qy * g.y + qz * g.z + qw * g.w;
+        const float inv = (nrm > 1e-12f) ? 1.0f / d : 0.0f;
+        const float4 gr = make_float4((g.x - qx * qg) * inv, (g.y - qy * qg) * inv, (g.z - qz * qg) * inv, (g.w - qw * qg) * inv);
+        float4 m = reinterpret_cast<float4 *>(a.m_rot)[i], v = reinterpret_cast<float4 *>(a.v_rot)[i];
+        adam4(r, gr, m, v, a.k, a.k.step_size[5]);
+        reinterpret_cast<float4 *>(a.rotation)[i] = r;
+        reinterpret_cast<float4 *>(a.m_rot)[i] = m;
+        reinterpret_cast<float4 *>(a.v_rot)[i] = v;
+    } else { // role 4: f_dc (first coefficient of the merged SH gradient) + confidence
+        const float *gs = a.g_sh + (size_t)i * a.M * 3;
+        const float g3[3] = {gs[0], gs[1], gs[2]};
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int e = 3 * i + c;
+            float p = a.f_dc[e], m = a.m_dc[e], v = a.v_dc[e];
+            adam_update(p, g3[c], m, v, a.k, a.k.step_size[1]);
+            a.f_dc[e] = p; a.m_dc[e] = m; a.v_dc[e] = v;
+        }
+        if (a.confidence && (fabsf(g3[0]) != 0.f || fabsf(g3[1]) != 0.f || fabsf(g3[2]) != 0.f)) a.confidence[i] += 1.0f;
+    }
+}
+
 // Adam for f_rest [P,45]: 128-bit accesses on the parameter and its two moments (6 of the 7 streams), the gradient is
 // gathered from the merged [P,16,3] layout (row stride 48, offset 3)
 struct RestAdamArgs {
@@ -294,7 +401,26 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
     sa.m_sc = p->exp_avg[4]; sa.v_sc = p->exp_avg_sq[4]; sa.m_rot = p->exp_avg[5]; sa.v_rot = p->exp_avg_sq[5];
     sa.act_opacity = act_op; sa.act_scales = act_sc; sa.g_means3D = g_means3D; sa.g_opacity = g_op; sa.g_scales = g_sc;
     sa.g_rot = g_rot; sa.g_sh = g_sh; sa.confidence = p->confidence; sa.status = status; sa.k = k;
-    adam_geometry_kernel<<<nb, 256, 0, stream>>>(sa);
+    bool aligned = true;
+    {
+        const void *ptrs[] = {sa.xyz, sa.m_xyz, sa.v_xyz, sa.scaling, sa.m_sc, sa.v_sc, sa.opacity, sa.m_op, sa.v_op,
+                              sa.rotation, sa.m_rot, sa.v_rot, g_means3D, g_sc, g_op, g_rot, act_op, act_sc};
+        for (const void *q : ptrs) aligned &= ((uintptr_t)q % 16 == 0);
+    }
+    if (aligned) {
+        FlatArgs fa;
+        fa.s = sa;
+        fa.n4_vec3 = 3ll * P / 4;
+        fa.n4_scalar = P / 4;
+        fa.nb_vec3 = (unsigned)((fa.n4_vec3 + 255) / 256);
+        if (fa.nb_vec3 == 0) fa.nb_vec3 = 1; // the tail loop lives in block 0 of each role
+        fa.nb_scalar = (unsigned)((fa.n4_scalar + 255) / 256);
+        if (fa.nb_scalar == 0) fa.nb_scalar = 1;
+        fa.nb_gauss = (unsigned)nb;
+        adam_flat_kernel<<<2 * fa.nb_vec3 + fa.nb_scalar + 2 * fa.nb_gauss, 256, 0, stream>>>(fa);
+    } else {
+        adam_geometry_kernel<<<nb, 256, 0, stream>>>(sa);
+    }
     DQO_LAUNCH_CHECK("adam geometry", s->debug, stream);
     if (M == 16) {
         RestAdamArgs ra;
