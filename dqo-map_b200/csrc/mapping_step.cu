@@ -187,6 +187,9 @@ struct FlatArgs {
     long long n4_vec3, n4_scalar; // float4 chunks of a [3P] / [P] array
     unsigned nb_vec3, nb_scalar, nb_gauss;
 };
+// zero gradient on zero moments is a fixed point of Adam (m' = v' = 0, p' = p - step * 0 / eps = p): such elements
+// need no parameter read, no arithmetic (IEEE sqrt / div take their slow paths on zeros) and no write-back
+__device__ __forceinline__ bool all_zero(const float4 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f && a.w == 0.f; }
 __device__ __forceinline__ void adam4(float4 &p, const float4 g, float4 &m, float4 &v, const AdamScalars &k, float ss) {
     adam_update(p.x, g.x, m.x, v.x, k, ss);
     adam_update(p.y, g.y, m.y, v.y, k, ss);
@@ -218,15 +221,18 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(FlatArgs fa) {
         const long long q = (long long)b * blockDim.x + threadIdx.x;
         if (q < fa.n4_vec3) {
             float4 g = reinterpret_cast<const float4 *>(G_)[q];
-            if (sc) {
-                const float4 e = reinterpret_cast<const float4 *>(a.act_scales)[q];
-                g.x *= e.x; g.y *= e.y; g.z *= e.z; g.w *= e.w;
+            float4 m = reinterpret_cast<float4 *>(M_)[q], v = reinterpret_cast<float4 *>(V_)[q];
+            if (!(all_zero(g) && all_zero(m) && all_zero(v))) {
+                if (sc) {
+                    const float4 e = reinterpret_cast<const float4 *>(a.act_scales)[q];
+                    g.x *= e.x; g.y *= e.y; g.z *= e.z; g.w *= e.w;
+                }
+                float4 p = reinterpret_cast<float4 *>(P_)[q];
+                adam4(p, g, m, v, a.k, ss);
+                reinterpret_cast<float4 *>(P_)[q] = p;
+                reinterpret_cast<float4 *>(M_)[q] = m;
+                reinterpret_cast<float4 *>(V_)[q] = v;
             }
-            float4 p = reinterpret_cast<float4 *>(P_)[q], m = reinterpret_cast<float4 *>(M_)[q], v = reinterpret_cast<float4 *>(V_)[q];
-            adam4(p, g, m, v, a.k, ss);
-            reinterpret_cast<float4 *>(P_)[q] = p;
-            reinterpret_cast<float4 *>(M_)[q] = m;
-            reinterpret_cast<float4 *>(V_)[q] = v;
         }
         if (b == 0) adam_tail(P_, M_, V_, G_, a.act_scales, sc ? 1 : 0, fa.n4_vec3 * 4, 3ll * a.P, a.k, ss);
         return;
@@ -237,14 +243,16 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(FlatArgs fa) {
         const long long q = (long long)b * blockDim.x + threadIdx.x;
         if (q < fa.n4_scalar) {
             float4 g = reinterpret_cast<const float4 *>(a.g_opacity)[q];
-            const float4 o = reinterpret_cast<const float4 *>(a.act_opacity)[q];
-            g.x *= o.x * (1.0f - o.x); g.y *= o.y * (1.0f - o.y); g.z *= o.z * (1.0f - o.z); g.w *= o.w * (1.0f - o.w);
-            float4 p = reinterpret_cast<float4 *>(a.opacity)[q], m = reinterpret_cast<float4 *>(a.m_op)[q],
-                   v = reinterpret_cast<float4 *>(a.v_op)[q];
-            adam4(p, g, m, v, a.k, ss);
-            reinterpret_cast<float4 *>(a.opacity)[q] = p;
-            reinterpret_cast<float4 *>(a.m_op)[q] = m;
-            reinterpret_cast<float4 *>(a.v_op)[q] = v;
+            float4 m = reinterpret_cast<float4 *>(a.m_op)[q], v = reinterpret_cast<float4 *>(a.v_op)[q];
+            if (!(all_zero(g) && all_zero(m) && all_zero(v))) {
+                const float4 o = reinterpret_cast<const float4 *>(a.act_opacity)[q];
+                g.x *= o.x * (1.0f - o.x); g.y *= o.y * (1.0f - o.y); g.z *= o.z * (1.0f - o.z); g.w *= o.w * (1.0f - o.w);
+                float4 p = reinterpret_cast<float4 *>(a.opacity)[q];
+                adam4(p, g, m, v, a.k, ss);
+                reinterpret_cast<float4 *>(a.opacity)[q] = p;
+                reinterpret_cast<float4 *>(a.m_op)[q] = m;
+                reinterpret_cast<float4 *>(a.v_op)[q] = v;
+            }
         }
         if (b == 0) adam_tail(a.opacity, a.m_op, a.v_op, a.g_opacity, a.act_opacity, 2, fa.n4_scalar * 4, a.P, a.k, ss);
         return;
@@ -255,15 +263,16 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(FlatArgs fa) {
     const int i = (int)(b * blockDim.x + threadIdx.x);
     if (i >= a.P) return;
     if (!dc) { // role 3: rotation, q = r / max(|r|, eps); dL/dr = (g - q (q . g)) / max(|r|, eps)
-        float4 r = reinterpret_cast<float4 *>(a.rotation)[i];
         const float4 g = reinterpret_cast<const float4 *>(a.g_rot)[i];
+        float4 m = reinterpret_cast<float4 *>(a.m_rot)[i], v = reinterpret_cast<float4 *>(a.v_rot)[i];
+        if (all_zero(g) && all_zero(m) && all_zero(v)) return; // the normalisation backward of a zero gradient is zero
+        float4 r = reinterpret_cast<float4 *>(a.rotation)[i];
         const float nrm = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
         const float d = fmaxf(nrm, 1e-12f);
         const float qx = r.x / d, qy = r.y / d, qz = r.z / d, qw = r.w / d;
         const float qg = qx * g.x + qy * g.y + qz * g.z + qw * g.w;
         const float inv = (nrm > 1e-12f) ? 1.0f / d : 0.0f;
         const float4 gr = make_float4((g.x - qx * qg) * inv, (g.y - qy * qg) * inv, (g.z - qz * qg) * inv, (g.w - qw * qg) * inv);
-        float4 m = reinterpret_cast<float4 *>(a.m_rot)[i], v = reinterpret_cast<float4 *>(a.v_rot)[i];
         adam4(r, gr, m, v, a.k, a.k.step_size[5]);
         reinterpret_cast<float4 *>(a.rotation)[i] = r;
         reinterpret_cast<float4 *>(a.m_rot)[i] = m;
@@ -271,12 +280,21 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(FlatArgs fa) {
     } else { // role 4: f_dc (first coefficient of the merged SH gradient) + confidence
         const float *gs = a.g_sh + (size_t)i * a.M * 3;
         const float g3[3] = {gs[0], gs[1], gs[2]};
+        float m3[3], v3[3];
+        bool zero = true;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            m3[c] = a.m_dc[3 * i + c];
+            v3[c] = a.v_dc[3 * i + c];
+            zero &= (g3[c] == 0.f && m3[c] == 0.f && v3[c] == 0.f);
+        }
+        if (zero) return; // also no confidence bump: every f_dc gradient is zero
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const int e = 3 * i + c;
-            float p = a.f_dc[e], m = a.m_dc[e], v = a.v_dc[e];
-            adam_update(p, g3[c], m, v, a.k, a.k.step_size[1]);
-            a.f_dc[e] = p; a.m_dc[e] = m; a.v_dc[e] = v;
+            float p = a.f_dc[e];
+            adam_update(p, g3[c], m3[c], v3[c], a.k, a.k.step_size[1]);
+            a.f_dc[e] = p; a.m_dc[e] = m3[c]; a.v_dc[e] = v3[c];
         }
         if (a.confidence && (fabsf(g3[0]) != 0.f || fabsf(g3[1]) != 0.f || fabsf(g3[2]) != 0.f)) a.confidence[i] += 1.0f;
     }
