@@ -126,7 +126,8 @@ def _oracle_as_ref(inp):
     return sc, pre, bn, img, ref
 
 
-@pytest.mark.parametrize("cfg,P,deg,mask", [("small", 20000, 3, "ones"), ("small", 12000, 1, "half"), ("c1", 30000, 0, "ones")])
+@pytest.mark.parametrize("cfg,P,deg,mask", [("small", 20000, 3, "ones"), ("small", 12000, 1, "half"), ("c1", 30000, 0, "ones"),
+                                            ("ragged", 15000, 2, "ones"), ("ragged", 9000, 2, "half")])
 def test_against_cpu_oracle(cfg, P, deg, mask):
     inp = rh.make_inputs(cfg, torch.device(DEV), seed=77, P=P, sh_degree=deg, mask=mask)
     cam = inp["cam"]
@@ -153,7 +154,8 @@ def test_against_cpu_oracle(cfg, P, deg, mask):
 
 
 @pytest.mark.skipif(not rh.reference_available(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("cfg,mask,precomp", [("c1", "ones", False), ("c1", "half", True), ("c2", "ones", False)])
+@pytest.mark.parametrize("cfg,mask,precomp", [("c1", "ones", False), ("c1", "half", True), ("c2", "ones", False),
+                                              ("ragged", "half", False)])
 def test_against_live_reference(cfg, mask, precomp):
     """Full BASELINE sizes against the unmodified reference extension on the same GPU."""
     _, C, _, _ = rh.load_reference()
