@@ -94,10 +94,9 @@ __device__ __forceinline__ bool bwd_pair(BwdPix &p, const float4 r0, const float
     const float G = expf(power);
     const float alpha = fminf(0.99f, fmul(r1.y, G));
     if (alpha < 1.0f / 255.0f) return false;
-    // one approximate reciprocal (MUFU.RCP, <= 1 ulp on [0.01, 1]) instead of the reference's two IEEE divisions
-    // (backward.cu:947,975): gradients are gated at 1e-3 relative, the integer decisions above are untouched
-    const float inv_1ma = __fdividef(1.0f, 1.f - alpha);
-    p.T = p.T * inv_1ma;
+    // IEEE division as in the reference (backward.cu:947): the conic -> cov3D -> rotation chain downstream amplifies a
+    // 1-ulp change of T to ~1e-3 in dL_drotations, so approximations here are not free
+    p.T = p.T / (1.f - alpha);
     const float dchannel_dcolor = alpha * p.T;
     p.acc0 = p.last_alpha * p.lc0 + (1.f - p.last_alpha) * p.acc0;
     p.acc1 = p.last_alpha * p.lc1 + (1.f - p.last_alpha) * p.acc1;
@@ -108,7 +107,7 @@ __device__ __forceinline__ bool bwd_pair(BwdPix &p, const float4 r0, const float
     float dL_dalpha = (r2.x - p.acc0) * p.dLp0 + (r2.y - p.acc1) * p.dLp1 + (r2.z - p.acc2) * p.dLp2;
     dL_dalpha *= p.T;
     p.last_alpha = alpha;
-    if (p.bg_dot != 0.f) dL_dalpha += (-p.T_final * inv_1ma) * p.bg_dot; // background term (zero for bg = 0)
+    if (p.bg_dot != 0.f) dL_dalpha += (-p.T_final / (1.f - alpha)) * p.bg_dot; // background term (backward.cu:975), 0 for bg = 0
     const float dL_dG = r1.y * dL_dalpha;
     const float gdx = G * dx, gdy = G * dy;
     const float dG_ddelx = -gdx * r0.z - gdy * r0.w;

@@ -893,6 +893,116 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
     }
 }
 
+// Re-blend of an already binned view with another colour per Gaussian.  The reference renders its
+// semantic / instance images by running the whole rasterizer again with colors_precomp (SLAM/render.py:227-262):
+// preprocess, duplicate, sort and ranges are repeated although only the colour differs.  This kernel walks the lists of
+// the existing forward state (front list, then back list) with exactly the forward's alpha / hit / termination logic
+// (forward.cu:760-848), so the image is bit-identical to what a second full forward would return in `out_color`.
+struct ExtraArgs {
+    int W, H, grid_x;
+    float opaque_thr, T_thr;
+    const uint2 *ranges, *ranges_b;
+    const uint32_t *point_list, *point_list_b;
+    const float4 *rec;
+    const float *colors; // [P,3]
+    const float *bg;
+    float *out_color;
+};
+__global__ void __launch_bounds__(256) blend_extra_kernel(ExtraArgs a) {
+    __shared__ float4 s_r0[256];
+    __shared__ float4 s_r1[256];
+    __shared__ float4 s_col[256];
+    __shared__ uint8_t s_mask[256];
+    __shared__ uint8_t s_list[8][256];
+
+    const int tile = blockIdx.x;
+    const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t pix_x = tile_x * DQO_TILE + lx, pix_y = tile_y * DQO_TILE + ly;
+    const bool inside = pix_x < (uint32_t)a.W && pix_y < (uint32_t)a.H;
+    const size_t pix_id = (size_t)a.W * pix_y + pix_x;
+    const size_t HW = (size_t)a.W * a.H;
+    const uint2 range_a = a.ranges[tile];
+    uint2 range_b = make_uint2(0, 0);
+    if (a.ranges_b) range_b = a.ranges_b[tile];
+    if (range_a.x == range_a.y && range_b.x == range_b.y) { // tile not rendered: fill value (rasterize_points.cu:79)
+        if (inside) a.out_color[pix_id] = a.out_color[HW + pix_id] = a.out_color[2 * HW + pix_id] = 0.f;
+        return;
+    }
+    const float pixfx = (float)pix_x, pixfy = (float)pix_y;
+    const float tile_px = (float)(tile_x * DQO_TILE), tile_py = (float)(tile_y * DQO_TILE);
+    bool done = !inside, hit = false, stop = false;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    for (int seg = 0; seg < 2 && !stop; seg++) {
+        const uint2 range = seg ? range_b : range_a;
+        const uint32_t *__restrict__ list = seg ? a.point_list_b : a.point_list;
+        const int total = (int)(range.y - range.x);
+        const int rounds = (total + 255) / 256;
+        for (int i = 0; i < rounds; i++) {
+            if (__syncthreads_count(done) == 256) {
+                stop = true;
+                break;
+            }
+            const int progress = i * 256 + tid;
+            const int n = min(256, total - i * 256);
+            if (progress < total) {
+                const int id = (int)list[range.x + progress];
+                const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
+                const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
+                const float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
+                s_r0[tid] = r0;
+                s_r1[tid] = r1;
+                s_col[tid] = make_float4(a.colors[3 * (size_t)id], a.colors[3 * (size_t)id + 1], a.colors[3 * (size_t)id + 2], 0.f);
+                s_mask[tid] = (uint8_t)subblock_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, r1.w, tile_px, tile_py);
+            }
+            __syncthreads();
+            int cnt = 0;
+            if (!__all_sync(0xFFFFFFFFu, done)) {
+                for (int b = 0; b < n; b += 32) {
+                    const int j = b + lane;
+                    const bool m = (j < n) && ((s_mask[j] >> warp) & 1);
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, m);
+                    if (m) s_list[warp][cnt + __popc(bal & ((1u << lane) - 1))] = (uint8_t)j;
+                    cnt += __popc(bal);
+                }
+                __syncwarp();
+            }
+            for (int k = 0; !done && k < cnt; k++) {
+                const int j = s_list[warp][k];
+                const float4 r0 = s_r0[j];
+                const float4 r1 = s_r1[j];
+                const float dx = fsub(r0.x, pixfx), dy = fsub(r0.y, pixfy);
+                const float power = ffma(ffma(dx, fmul(dx, r0.z), fmul(dy, fmul(dy, r1.x))), -0.5f, -fmul(dy, fmul(dx, r0.w)));
+                if (power > 0.0f || power < r1.z) continue;
+                const float alpha = fminf(0.99f, fmul(r1.y, expf(power)));
+                if (alpha < 1.0f / 255.0f) continue;
+                if (alpha >= a.opaque_thr) hit = true;
+                const float test_T = fmul(T, fsub(1.0f, alpha));
+                if (test_T < a.T_thr && hit) {
+                    done = true;
+                    continue;
+                }
+                if (test_T >= a.T_thr) {
+                    const float w = fmul(alpha, T);
+                    const float4 c = s_col[j];
+                    C0 = ffma(c.x, w, C0);
+                    C1 = ffma(c.y, w, C1);
+                    C2 = ffma(c.z, w, C2);
+                }
+                T = test_T;
+            }
+            __syncthreads();
+        }
+    }
+    if (inside) {
+        a.out_color[pix_id] = ffma(T, a.bg[0], C0);
+        a.out_color[HW + pix_id] = ffma(T, a.bg[1], C1);
+        a.out_color[2 * HW + pix_id] = ffma(T, a.bg[2], C2);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // state export for parity tests
 // ------------------------------------------------------------------------------------------------
@@ -1276,6 +1386,39 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     render_forward_kernel<2><<<T, 256, 0, stream>>>(ra);
     DQO_LAUNCH_CHECK("render forward (back)", debug, stream);
     stage_mark(stream, ST_RENDER_FWD);
+    return DQO_OK;
+}
+
+extern "C" int dqo_rast_blend_extra(const dqo_rast_settings *s, const float *background, const float *colors,
+                                    const void *geom_buffer, const void *binning_buffer, int64_t capacity,
+                                    const void *image_buffer, const int32_t *status, float *out_color, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!s || s->W <= 0 || s->H <= 0 || s->P < 0 || !background || !image_buffer || !status || !out_color ||
+        (s->P > 0 && (!colors || !geom_buffer || !binning_buffer))) {
+        set_error("dqo_rast_blend_extra: invalid argument");
+        return DQO_ERR_INVALID_ARG;
+    }
+    ImgLayout IL;
+    make_img_layout(s->W, s->H, &IL);
+    const char *img = (const char *)image_buffer;
+    ExtraArgs a;
+    a.W = s->W; a.H = s->H; a.grid_x = IL.tiles_x; a.opaque_thr = s->opaque_threshold; a.T_thr = s->T_threshold;
+    a.ranges = (const uint2 *)(img + IL.ranges);
+    a.ranges_b = nullptr; a.point_list = nullptr; a.point_list_b = nullptr; a.rec = nullptr;
+    if (s->P > 0) {
+        GeomLayout GL;
+        BinLayout BL;
+        if (make_geom_layout(s->P, &GL) || make_bin_layout(capacity, &BL)) return DQO_ERR_WORKSPACE;
+        a.rec = (const float4 *)((const char *)geom_buffer + GL.rec);
+        a.point_list = (const uint32_t *)((const char *)binning_buffer + BL.vals_out);
+        if (s->front_instances > 0) {
+            a.ranges_b = (const uint2 *)(img + IL.ranges_b);
+            a.point_list_b = a.point_list + s->front_instances;
+        }
+    }
+    a.colors = colors; a.bg = background; a.out_color = out_color;
+    blend_extra_kernel<<<IL.T, 256, 0, stream>>>(a);
+    DQO_LAUNCH_CHECK("blend extra colours", s->debug, stream);
     return DQO_OK;
 }
 

@@ -330,6 +330,23 @@ def rasterize_gaussians_backward(tile_indices, tile_num, background, means3D, ra
                           projmatrix, dL_dout_color, dL_dout_depth, sh, campos, hit_image)
 
 
+def blend_extra_colors(state, colors_precomp, background):
+    """[3,H,W] colour image of the view held by `state` (the ForwardState of a previous forward, reachable as
+    `geomBuffer._dqo_state` / `ctx.state` / `GaussianRasterizer.last_state`) blended with `colors_precomp` [P,3] instead of
+    the colours it was rendered with -- what a second full rasterizer call with colors_precomp would return as its first
+    output (SLAM/render.py:227-262), for the cost of one blend pass.  No gradient."""
+    s = state.settings
+    if colors_precomp.shape[0] != s.P or colors_precomp.dim() != 2 or colors_precomp.shape[1] != 3:
+        raise ValueError("colors_precomp must be [P,3] for the P Gaussians of the rendered view")
+    dev = state.status.device
+    out = torch.empty((3, s.H, s.W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().dqo_rast_blend_extra(s, ptr(_f32c(background)), ptr(_f32c(colors_precomp.detach())), ptr(state.geom),
+                                         ptr(state.binning), state.capacity, ptr(state.image), ptr(state.status),
+                                         ptr(out), _stream()), "dqo_rast_blend_extra")
+    return out
+
+
 def mark_visible(means3D, viewmatrix, projmatrix):
     P = means3D.size(0)
     present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
@@ -362,6 +379,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         (color, depth, hit_color, hit_depth, hit_cw, hit_dw, T_map, radii, n_touched) = outs
         ctx.raster_settings = rs
         ctx.state = st
+        _RasterizeGaussians.last_state = st
         ctx.num_rendered = st.status_host[_lib.ST_NUM_RENDERED]
         ctx.num_tile = st.status_host[_lib.ST_TILE_NUM]
         ctx.save_for_backward(colors_precomp, hit_depth, means3D, scales, rotations, cov3Ds_precomp, radii, sh)

@@ -147,6 +147,15 @@ int dqo_rast_backward(const dqo_rast_settings *s, const float *background, const
 int dqo_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
                      uint8_t *present, void *stream);
 
+/* Re-blend of the view binned by the last dqo_rast_forward with another colour per Gaussian.
+ * Replaces the second / third full rasterizer call of Renderer.render (SLAM/render.py:227-262, colors_precomp =
+ * semantic or instance colours): same lists, same alpha / hit / termination logic, so `out_color` [3,H,W] equals the
+ * colour image a full forward with colors_precomp = `colors` [P,3] would return, at the cost of one blend pass.
+ * Forward only (the reference consumes these images without gradient: mapper.py:944-969). */
+int dqo_rast_blend_extra(const dqo_rast_settings *s, const float *background, const float *colors,
+                         const void *geom_buffer, const void *binning_buffer, int64_t instance_capacity,
+                         const void *image_buffer, const int32_t *status, float *out_color, void *stream);
+
 /* Introspection for parity tests: re-materialises the reference's binning artefacts from the
  * private workspace in the reference's own formats (rasterizer_impl.h:29-66): 64-bit sorted keys
  * (tile<<32 | depth bits), sorted Gaussian ids, per-tile ranges, and row-major per-pixel / per-Gaussian state.

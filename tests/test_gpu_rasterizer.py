@@ -219,6 +219,8 @@ def test_two_phase_binning_equals_single_phase(cfg, mask, precomp):
     H, W = cam.image_height, cam.image_width
     gc, gd = rh.make_pixel_grads(H, W, DEV)
     o1, ex1, bw1 = _run_ours(inp, gc, gd)
+    _, _, bw1b = _run_ours(inp, gc, gd)   # run-to-run noise of the float atomics (see _check_grads)
+    floor = {n: float((a - b).norm() / (a.norm() + 1e-30)) for n, a, b in zip(GRADS, bw1, bw1b) if a.numel()}
     R = o1[0]
     tested = 0
     for frac in (0.002, 0.05, 0.3, 0.98):
@@ -235,7 +237,7 @@ def test_two_phase_binning_equals_single_phase(cfg, mask, precomp):
             if a.numel() == 0:
                 continue
             rel = float((a - b).norm() / (a.norm() + 1e-30))
-            assert rel <= 1e-3, (frac, name, rel)  # same kernels, different atomic order (see _check_grads)
+            assert rel <= max(1e-3, 2.5 * floor[name]), (frac, name, rel, floor[name])  # same kernels, other atomic order
         tested += 1
     assert tested == 4
     rasterizer.set_binning_mode("single")
@@ -388,3 +390,45 @@ def test_autograd_api_matches_pybind_path():
     assert vis.dtype == torch.bool and bool(vis[o[9] > 0].all())
     assert np.array_equal(t2n(vis), oracle.mark_visible(t2n(inp["xyz"]), t2n(cam.world_view_transform),
                                                         t2n(cam.full_proj_transform)))
+
+
+@pytest.mark.parametrize("cfg,mask,binning", [("small", "half", ("single",)), ("c1", "ones", ("single",)),
+                                              ("c2", "ones", ("fixed", 2_000_128, 1_000_000))])
+def test_extra_colour_blend_equals_second_full_render(cfg, mask, binning):
+    """the semantic / instance images of Renderer.render (render.py:227-262) from the lists of the main
+    render: bit-identical to a full second rasterizer call with colors_precomp (ours, and the reference when present)."""
+    from dqo_map_b200 import render as render_mod
+    inp = rh.make_inputs(cfg, torch.device(DEV), mask=mask)
+    cam = inp["cam"]
+    P = inp["xyz"].shape[0]
+    g = torch.Generator().manual_seed(3)
+    sem, inst = torch.rand(P, 3, generator=g).to(DEV), (torch.randint(0, 20, (P, 1), generator=g) / 255.0).repeat(1, 3).to(DEV)
+    normal = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=1).to(DEV)
+    rd = synthetic.RENDER_DEFAULTS
+    rs = rasterizer.GaussianRasterizationSettings(
+        image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        bg=torch.tensor([0.1, 0.2, 0.3], device=DEV), scale_modifier=1.0, viewmatrix=cam.world_view_transform,
+        projmatrix=cam.full_proj_transform, sh_degree=inp["sh_degree"], campos=cam.camera_center,
+        opaque_threshold=rd["opaque_threshold"], normal_threshold=rd["normal_threshold"],
+        depth_threshold=rd["depth_threshold"], prefiltered=False, debug=False, cx=cam.cx, cy=cam.cy)
+    data = dict(xyz=inp["xyz"], opacity=inp["opacity"], scales=inp["scales"], rotations=inp["rotations"], shs=inp["shs"],
+                normal=normal, semantics_color=sem, instance=inst)
+    rasterizer.set_binning_mode(*binning)
+    res = render_mod.render(rs, data, inp["tile_mask"])
+    rasterizer.set_binning_mode("single")
+    for key, colors in (("semantic_seg", sem), ("instance", inst)):
+        full = rasterizer.GaussianRasterizer(rs)(means3D=inp["xyz"], opacities=inp["opacity"], colors_precomp=colors,
+                                                 scales=inp["scales"], rotations=inp["rotations"], tile_mask=inp["tile_mask"])
+        assert torch.equal(res[key], full[0]), key
+        if rh.reference_available():
+            ref_pkg = rh.load_reference()[0]
+            rs_ref = ref_pkg.GaussianRasterizationSettings(**rs._asdict())
+            ref_img = ref_pkg.GaussianRasterizer(rs_ref)(means3D=inp["xyz"], opacities=inp["opacity"], colors_precomp=colors,
+                                                         scales=inp["scales"], rotations=inp["rotations"],
+                                                         tile_mask=inp["tile_mask"])[0]
+            assert torch.equal(res[key], ref_img), key
+    # the normal map is the reference's gather of per-Gaussian normals through the depth index map (render.py:212-216)
+    di = res["depth_index_map"][0]
+    want = torch.zeros(3, cam.image_height, cam.image_width, device=DEV)
+    want[:, di > -1] = normal[di[di > -1].long()].T
+    assert torch.equal(res["normal"], want)
