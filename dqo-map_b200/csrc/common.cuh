@@ -190,6 +190,7 @@ struct ImgLayout {
     size_t ranges_b;   // uint2[T] two-phase: ranges of the back-phase lists (relative to the back region)
     size_t unfinished; // i32[T] two-phase: 1 when the front phase left some pixel of the tile unterminated
     size_t mask_bits_b; // u32[tiles_y][mask_words]: mask_bits & unfinished
+    size_t row_any_b;  // u32[ceil(tiles_y/32)]: bit y set <=> row y of mask_bits_b has any bit set
     size_t state;      // f32[4][T*256] two-phase: running T (-1 = pixel terminated) and colour accumulators
     int mask_words;
     size_t total;

@@ -189,11 +189,12 @@ __device__ __noinline__ void bwd_depth_path(const float *scales, const float *ro
 
 // Reverse blend of one 16x16 tile.  Same thread / warp layout and per-warp culled lists as the forward kernel; the
 // two pixels of a thread add into the same 9 partial sums before the single warp reduction per splat.
+struct __align__(16) SplatB {
+    float4 r0, r1, c; // {x, y, conic.x, conic.y} {conic.z, opacity, power_reject, -} {r, g, b, Gaussian id bits}
+};
+
 __global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(RenderBwdArgs a) {
-    __shared__ float4 s_r0[256];
-    __shared__ float4 s_r1[256];
-    __shared__ float4 s_r2[256];
-    __shared__ int s_id[256];
+    __shared__ SplatB s_sp[256]; // one 48-byte record per staged splat: a single base + j*48 address in the loop
     __shared__ uint8_t s_mask[256];
     __shared__ uint8_t s_list[RB_THREADS / 32][256];
     __shared__ int s_max;
@@ -274,10 +275,9 @@ __global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(RenderBwdAr
                 const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
                 const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
                 const float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
-                s_id[slot] = id;
-                s_r0[slot] = r0;
-                s_r1[slot] = r1;
-                s_r2[slot] = r2;
+                s_sp[slot].r0 = r0;
+                s_sp[slot].r1 = r1;
+                s_sp[slot].c = make_float4(r2.x, r2.y, r2.z, __int_as_float(id));
                 s_mask[slot] = (uint8_t)subblock_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, r1.w, tile_px, tile_py);
             }
         }
@@ -297,9 +297,9 @@ __global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(RenderBwdAr
             const int j = s_list[warp][k];
             const int posj = max_c - 1 - (i * 256 + j);
             const unsigned mk = s_mask[j];
-            const float4 r0 = s_r0[j];
-            const float4 r1 = s_r1[j];
-            const float4 r2 = s_r2[j];
+            const float4 r0 = s_sp[j].r0;
+            const float4 r1 = s_sp[j].r1;
+            const float4 r2 = s_sp[j].c;
             float v[9];
 #pragma unroll
             for (int q = 0; q < 9; q++) v[q] = 0.f;
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(RenderBwdAr
             if ((mk >> b_hi) & 1) contrib |= bwd_pair(px[1], r0, r1, r2, posj, pixfx, ddelx_dx, ddely_dy, v);
             if (!__any_sync(0xFFFFFFFFu, contrib)) continue;
             const float total = warp_reduce9(v, lane);
-            if (my_slot >= 0) atomicAdd(&a.gacc[(size_t)s_id[j] * DQO_GACC_FLOATS + my_slot], total);
+            if (my_slot >= 0) atomicAdd(&a.gacc[(size_t)__float_as_int(r2.w) * DQO_GACC_FLOATS + my_slot], total);
         }
     }
 #pragma unroll

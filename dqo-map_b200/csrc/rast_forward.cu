@@ -108,6 +108,7 @@ void make_img_layout(int W, int H, ImgLayout *L) {
     L->ranges_b = bump(cur, T * 8);
     L->unfinished = bump(cur, T * 4);
     L->mask_bits_b = bump(cur, (size_t)(L->tiles_y > 0 ? L->tiles_y : 1) * L->mask_words * 4);
+    L->row_any_b = bump(cur, (size_t)((L->tiles_y + 31) / 32 + 1) * 4);
     L->state = bump(cur, T * DQO_TILE_PIX * 4 * 4);
     L->total = align_up(cur, 256);
 }
@@ -464,8 +465,9 @@ template <typename KeyT, int MODE>
 __global__ void __launch_bounds__(256)
     duplicate_kernel(int P, int64_t capacity, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
                      const uint32_t *__restrict__ tiles_rank, const uint32_t *__restrict__ offsets,
-                     const uint2 *__restrict__ rect, const uint32_t *__restrict__ mask_bits, int mask_words, int grid_x,
-                     KeyT *__restrict__ keys, uint32_t *__restrict__ vals, int *status) {
+                     const uint2 *__restrict__ rect, const uint32_t *__restrict__ mask_bits,
+                     const uint32_t *__restrict__ row_any, int mask_words, int grid_x, KeyT *__restrict__ keys,
+                     uint32_t *__restrict__ vals, int *status) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const uint32_t R = offsets[P - 1];
@@ -526,7 +528,8 @@ __global__ void __launch_bounds__(256)
             }
         } else if (lane == src) {
             uint32_t o = s_off;
-            for (uint32_t y = miny; y < maxy; y++)
+            for (uint32_t y = miny; y < maxy; y++) {
+                if (MODE == 2 && !((__ldg(&row_any[y >> 5]) >> (y & 31)) & 1)) continue; // no unfinished tile in this row
                 for (uint32_t wd = minx >> 5; wd <= (maxx - 1) >> 5; wd++) {
                     uint32_t m = __ldg(&mask_bits[y * mask_words + wd]);
                     const uint32_t lo = (wd == (minx >> 5)) ? (minx & 31) : 0;
@@ -540,20 +543,40 @@ __global__ void __launch_bounds__(256)
                         o++;
                     }
                 }
+            }
         }
     }
 }
 
-// Back phase, step 1: bitmap of the tiles that are both masked in and unfinished after the front phase.
-__global__ void mask_unfinished_kernel(int tiles_x, int tiles_y, int mask_words, const uint32_t *__restrict__ mask_bits,
-                                       const int *__restrict__ unfinished, uint32_t *mask_bits_b) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= tiles_y * mask_words) return;
-    const int y = w / mask_words, x0 = (w % mask_words) * 32;
-    uint32_t bits = 0;
-    for (int b = 0; b < 32 && x0 + b < tiles_x; b++)
-        if (unfinished[y * tiles_x + x0 + b]) bits |= 1u << b;
-    mask_bits_b[w] = bits & mask_bits[w];
+// Back phase, step 1 (one block): bitmap of the tiles that are both masked in and unfinished after the front phase,
+// plus one summary bit per tile row so that the per-Gaussian passes below skip rows (and, mostly, whole Gaussians)
+// without touching the bitmap.
+__global__ void __launch_bounds__(1024)
+    mask_unfinished_kernel(int tiles_x, int tiles_y, int mask_words, const uint32_t *__restrict__ mask_bits,
+                           const int *__restrict__ unfinished, uint32_t *mask_bits_b, uint32_t *row_any) {
+    __shared__ uint32_t s_any[64];
+    const int row_words = (tiles_y + 31) / 32;
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) s_any[k] = 0;
+    __syncthreads();
+    for (int w = threadIdx.x; w < tiles_y * mask_words; w += blockDim.x) {
+        const int y = w / mask_words, x0 = (w % mask_words) * 32;
+        uint32_t bits = 0;
+        for (int b = 0; b < 32 && x0 + b < tiles_x; b++)
+            if (unfinished[y * tiles_x + x0 + b]) bits |= 1u << b;
+        bits &= mask_bits[w];
+        mask_bits_b[w] = bits;
+        if (bits && (y >> 5) < 64) atomicOr(&s_any[y >> 5], 1u << (y & 31));
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < row_words; k += blockDim.x) row_any[k] = (k < 64) ? s_any[k] : 0xFFFFFFFFu;
+}
+
+// rows of [miny, maxy) that hold any unfinished tile, as a bit mask of row word `wd`
+__device__ __forceinline__ uint32_t rows_in_range(const uint32_t *__restrict__ row_any, uint32_t wd, uint32_t miny,
+                                                  uint32_t maxy) {
+    const uint32_t lo = (wd == (miny >> 5)) ? (miny & 31) : 0;
+    const uint32_t hi = (wd == ((maxy - 1) >> 5)) ? ((maxy - 1) & 31) : 31;
+    return __ldg(&row_any[wd]) & (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi));
 }
 
 // Back phase, step 2: per rank, the number of unfinished tiles inside the rectangle of every Gaussian that the
@@ -561,7 +584,8 @@ __global__ void mask_unfinished_kernel(int tiles_x, int tiles_y, int mask_words,
 __global__ void __launch_bounds__(256)
     count_back_kernel(int P, int64_t front, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
                       const uint32_t *__restrict__ offsets, const uint2 *__restrict__ rect,
-                      const uint32_t *__restrict__ mask_bits_b, int mask_words, uint32_t *tiles_rank) {
+                      const uint32_t *__restrict__ mask_bits_b, const uint32_t *__restrict__ row_any, int mask_words,
+                      uint32_t *tiles_rank) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     uint32_t n = 0;
@@ -570,7 +594,14 @@ __global__ void __launch_bounds__(256)
         if (tiles[id]) {
             const uint2 rc = rect[id];
             const uint32_t minx = rc.x & 0xFFFF, maxx = rc.x >> 16, miny = rc.y & 0xFFFF, maxy = rc.y >> 16;
-            for (uint32_t y = miny; y < maxy; y++) n += mask_row_count(mask_bits_b, mask_words, y, minx, maxx);
+            for (uint32_t wd = miny >> 5; wd <= (maxy - 1) >> 5; wd++) {
+                uint32_t rows = rows_in_range(row_any, wd, miny, maxy);
+                while (rows) {
+                    const uint32_t y = wd * 32 + (__ffs(rows) - 1);
+                    rows &= rows - 1;
+                    n += mask_row_count(mask_bits_b, mask_words, y, minx, maxx);
+                }
+            }
         }
     }
     tiles_rank[i] = n;
@@ -653,6 +684,10 @@ __global__ void __launch_bounds__(1024) compact_tiles_kernel(int T, const uint2 
     if (threadIdx.x == 0) status[DQO_ST_TILE_NUM] = base;
 }
 
+struct __align__(16) SplatS {
+    float4 r0, r1, c; // {x, y, conic.x, conic.y} {conic.z, opacity, power_reject, -} {r, g, b, Gaussian id bits}
+};
+
 struct RenderArgs {
     int W, H, grid_x;
     float fx, fy, cx, cy, scale_mod;
@@ -690,10 +725,7 @@ struct RenderArgs {
 //            length of the front list, so n_contrib and the blend order are those of the concatenated (= reference) list.
 template <int PHASE>
 __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
-    __shared__ float4 s_r0[256];
-    __shared__ float4 s_r1[256];
-    __shared__ float4 s_r2[256];
-    __shared__ int s_id[256];
+    __shared__ SplatS s_sp[256]; // one 48-byte record per staged splat: a single base + j*48 address in the loop
     __shared__ uint8_t s_mask[256];
     __shared__ uint8_t s_list[8][256];
 
@@ -773,10 +805,9 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
             const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
             const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
             const float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
-            s_id[tid] = id;
-            s_r0[tid] = r0;
-            s_r1[tid] = r1;
-            s_r2[tid] = r2;
+            s_sp[tid].r0 = r0;
+            s_sp[tid].r1 = r1;
+            s_sp[tid].c = make_float4(r2.x, r2.y, r2.z, __int_as_float(id));
             s_mask[tid] = (uint8_t)subblock_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, r1.w, tile_px, tile_py);
         }
         __syncthreads();
@@ -794,8 +825,8 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
         }
         for (int k = 0; !done && k < cnt; k++) {
             const int j = s_list[warp][k];
-            const float4 r0 = s_r0[j];
-            const float4 r1 = s_r1[j];
+            const float4 r0 = s_sp[j].r0;
+            const float4 r1 = s_sp[j].r1;
             const float dx = fsub(r0.x, pixfx), dy = fsub(r0.y, pixfy);
             const float power = ffma(ffma(dx, fmul(dx, r0.z), fmul(dy, fmul(dy, r1.x))), -0.5f, -fmul(dy, fmul(dx, r0.w)));
             if (power > 0.0f || power < r1.z) continue;
@@ -803,7 +834,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
             if (alpha < 1.0f / 255.0f) continue;
 
             if (!hit && alpha >= a.opaque_thr) {
-                const int id = s_id[j];
+                const int id = __float_as_int(s_sp[j].c.w);
                 const float sx = a.scales[3 * id], sy = a.scales[3 * id + 1], sz = a.scales[3 * id + 2];
                 const float4 q = reinterpret_cast<const float4 *>(a.rotations)[id];
                 const QuatMat R = quat_to_glm(q.x, q.y, q.z, q.w);
@@ -844,17 +875,17 @@ __global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
             }
             if (test_T >= a.T_thr) {
                 const float w = fmul(alpha, T);
-                const float4 r2 = s_r2[j];
+                const float4 r2 = s_sp[j].c;
                 C0 = ffma(r2.x, w, C0);
                 C1 = ffma(r2.y, w, C1);
                 C2 = ffma(r2.z, w, C2);
                 if (w > cw_max) {
                     cw_max = w;
-                    hit_color_id = s_id[j];
+                    hit_color_id = __float_as_int(r2.w);
                     hit_cw = w;
                 }
                 if (a.n_touched && test_T > 0.5f) {
-                    const int id = s_id[j];
+                    const int id = __float_as_int(r2.w);
                     const unsigned m = __match_any_sync(__activemask(), id);
                     if (lane == __ffs(m) - 1) atomicAdd(&a.n_touched[id], __popc(m));
                 }
@@ -909,9 +940,7 @@ struct ExtraArgs {
     float *out_color;
 };
 __global__ void __launch_bounds__(256) blend_extra_kernel(ExtraArgs a) {
-    __shared__ float4 s_r0[256];
-    __shared__ float4 s_r1[256];
-    __shared__ float4 s_col[256];
+    __shared__ SplatS s_sp[256];
     __shared__ uint8_t s_mask[256];
     __shared__ uint8_t s_list[8][256];
 
@@ -952,9 +981,9 @@ __global__ void __launch_bounds__(256) blend_extra_kernel(ExtraArgs a) {
                 const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
                 const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
                 const float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
-                s_r0[tid] = r0;
-                s_r1[tid] = r1;
-                s_col[tid] = make_float4(a.colors[3 * (size_t)id], a.colors[3 * (size_t)id + 1], a.colors[3 * (size_t)id + 2], 0.f);
+                s_sp[tid].r0 = r0;
+                s_sp[tid].r1 = r1;
+                s_sp[tid].c = make_float4(a.colors[3 * (size_t)id], a.colors[3 * (size_t)id + 1], a.colors[3 * (size_t)id + 2], 0.f);
                 s_mask[tid] = (uint8_t)subblock_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, r1.w, tile_px, tile_py);
             }
             __syncthreads();
@@ -971,8 +1000,8 @@ __global__ void __launch_bounds__(256) blend_extra_kernel(ExtraArgs a) {
             }
             for (int k = 0; !done && k < cnt; k++) {
                 const int j = s_list[warp][k];
-                const float4 r0 = s_r0[j];
-                const float4 r1 = s_r1[j];
+                const float4 r0 = s_sp[j].r0;
+                const float4 r1 = s_sp[j].r1;
                 const float dx = fsub(r0.x, pixfx), dy = fsub(r0.y, pixfy);
                 const float power = ffma(ffma(dx, fmul(dx, r0.z), fmul(dy, fmul(dy, r1.x))), -0.5f, -fmul(dy, fmul(dx, r0.w)));
                 if (power > 0.0f || power < r1.z) continue;
@@ -986,7 +1015,7 @@ __global__ void __launch_bounds__(256) blend_extra_kernel(ExtraArgs a) {
                 }
                 if (test_T >= a.T_thr) {
                     const float w = fmul(alpha, T);
-                    const float4 c = s_col[j];
+                    const float4 c = s_sp[j].c;
                     C0 = ffma(c.x, w, C0);
                     C1 = ffma(c.y, w, C1);
                     C2 = ffma(c.z, w, C2);
@@ -1300,6 +1329,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     ra.state = (float *)(img + IL.state);
     ra.status = status;
 
+    const uint32_t *row_any_b = (const uint32_t *)(img + IL.row_any_b);
     const int bit = (int)higher_msb((uint32_t)T);
     const int sort_bits = keys16 ? (bit < 16 ? bit : 16) : bit;
     const size_t ksz = keys16 ? 2 : 4;
@@ -1313,7 +1343,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         if (mode != 0) DQO_CUDA_CHECK(cudaMemsetAsync(kin, 0xFF, (size_t)n * ksz, stream));
 #define DQO_DUP(KT, MODE)                                                                                              \
     duplicate_kernel<KT, MODE><<<blocks, 256, 0, stream>>>(P, n, d_order, d_tiles, tiles_rank, offs, d_rect, bits,     \
-                                                           IL.mask_words, IL.tiles_x, (KT *)kin, vin, status)
+                                                           row_any_b, IL.mask_words, IL.tiles_x, (KT *)kin, vin, status)
         if (keys16) {
             if (mode == 0) DQO_DUP(uint16_t, 0); else if (mode == 1) DQO_DUP(uint16_t, 1); else DQO_DUP(uint16_t, 2);
         } else {
@@ -1366,12 +1396,11 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     DQO_LAUNCH_CHECK("render forward (front)", debug, stream);
     stage_mark(stream, ST_RENDER_FRONT);
     {
-        const int nw = IL.tiles_y * IL.mask_words;
-        mask_unfinished_kernel<<<(nw + 255) / 256, 256, 0, stream>>>(IL.tiles_x, IL.tiles_y, IL.mask_words, d_mask_bits,
-                                                                      ra.unfinished, mask_bits_b);
+        mask_unfinished_kernel<<<1, 1024, 0, stream>>>(IL.tiles_x, IL.tiles_y, IL.mask_words, d_mask_bits, ra.unfinished,
+                                                       mask_bits_b, (uint32_t *)(img + IL.row_any_b));
         DQO_LAUNCH_CHECK("unfinished mask", debug, stream);
         count_back_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, front, d_order, d_tiles, d_offsets, d_rect, mask_bits_b,
-                                                               IL.mask_words, tiles_b);
+                                                               row_any_b, IL.mask_words, tiles_b);
         DQO_LAUNCH_CHECK("back count", debug, stream);
         size_t tmp = GL.cub_bytes;
         DQO_CUDA_CHECK(cub::DeviceScan::InclusiveSum(geom + GL.cub, tmp, (const uint32_t *)tiles_b, offsets_b, P, stream));
