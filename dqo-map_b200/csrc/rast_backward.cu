@@ -76,6 +76,7 @@ __device__ __forceinline__ int slot_of_lane(int lane) {
     return ok ? s9 : -1;
 }
 
+#define RB_BATCH 512
 #define RB_THREADS 128 // 4 warps x (8x8 pixels); every thread owns the pixels (x, y) and (x, y + 4)
 
 // per-pixel state of the reverse traversal (backward.cu:881-900)
@@ -194,9 +195,12 @@ struct __align__(16) SplatB {
 };
 
 __global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(RenderBwdArgs a) {
-    __shared__ SplatB s_sp[256]; // one 48-byte record per staged splat: a single base + j*48 address in the loop
-    __shared__ uint8_t s_mask[256];
-    __shared__ uint8_t s_list[RB_THREADS / 32][256];
+    // RB_BATCH entries are staged per round.  With 512 most tiles need a single round (max n_contrib is a few hundred):
+    // the four warps then walk their own lists without meeting at a barrier after every 256 entries, where the fast
+    // ones used to wait for the slowest sub-block.
+    __shared__ SplatB s_sp[RB_BATCH]; // one 48-byte record per staged splat: a single base + j*48 address in the loop
+    __shared__ uint8_t s_mask[RB_BATCH];
+    __shared__ uint16_t s_list[RB_THREADS / 32][RB_BATCH];
     __shared__ int s_max;
 
     const int tile = blockIdx.x;
@@ -262,15 +266,15 @@ __global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(RenderBwdAr
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
     const int my_slot = slot_of_lane(lane);
 
-    const int rounds = (max_c + 255) / 256;
+    const int rounds = (max_c + RB_BATCH - 1) / RB_BATCH;
     for (int i = 0; i < rounds; i++) {
         __syncthreads();
-        const int n = min(256, max_c - i * 256);
+        const int n = min(RB_BATCH, max_c - i * RB_BATCH);
 #pragma unroll
-        for (int e = 0; e < 256 / RB_THREADS; e++) {
+        for (int e = 0; e < RB_BATCH / RB_THREADS; e++) {
             const int slot = e * RB_THREADS + tid;
             if (slot < n) {
-                const int pos = max_c - 1 - (i * 256 + slot);
+                const int pos = max_c - 1 - (i * RB_BATCH + slot);
                 const int id = (int)(pos < len_a ? a.point_list[range.x + pos] : a.point_list_b[start_b + (pos - len_a)]);
                 const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
                 const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
@@ -286,16 +290,16 @@ __global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(RenderBwdAr
         int cnt = 0;
         for (int b = 0; b < n; b += 32) {
             const int j = b + lane;
-            const int posj = max_c - 1 - (i * 256 + j);
+            const int posj = max_c - 1 - (i * RB_BATCH + j);
             const bool m = (j < n) && (posj < warp_max) && (s_mask[j] & warp_bits);
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, m);
-            if (m) s_list[warp][cnt + __popc(bal & ((1u << lane) - 1))] = (uint8_t)j;
+            if (m) s_list[warp][cnt + __popc(bal & ((1u << lane) - 1))] = (uint16_t)j;
             cnt += __popc(bal);
         }
         __syncwarp();
         for (int k = 0; k < cnt; k++) {
             const int j = s_list[warp][k];
-            const int posj = max_c - 1 - (i * 256 + j);
+            const int posj = max_c - 1 - (i * RB_BATCH + j);
             const unsigned mk = s_mask[j];
             const float4 r0 = s_sp[j].r0;
             const float4 r1 = s_sp[j].r1;

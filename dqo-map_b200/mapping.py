@@ -199,6 +199,20 @@ class FusedMappingStep:
         self.counts = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.status = torch.zeros(_lib.ST_WORDS, dtype=torch.int32, device=self.dev)
 
+    def _map_params(self):
+        """ctypes view of the parameter / moment tensors; rebuilt only when a tensor was replaced (pointer changed)."""
+        key = tuple(self.p[k].data_ptr() for k in self.ORDER) + (self.confidence.data_ptr() if self.confidence is not None else 0,)
+        if getattr(self, "_mp_key", None) != key:
+            mp = _lib.MapParams()
+            for i, k in enumerate(self.ORDER):
+                mp.param[i] = ptr(self.p[k])
+                mp.exp_avg[i] = ptr(self.state[k][0])
+                mp.exp_avg_sq[i] = ptr(self.state[k][1])
+                mp.lr[i] = self.lrs[i]
+            mp.confidence = ptr(self.confidence)
+            self._mp, self._mp_key = mp, key
+        return self._mp
+
     def _alloc(self):
         n = lib().dqo_mapping_step_workspace_bytes(self.P, self.M, self.W, self.H, self.capacity)
         if n == 0:
@@ -208,14 +222,7 @@ class FusedMappingStep:
     def __call__(self, rs, tile_mask, gt_color, gt_depth, render_mask=None):
         """rs: GaussianRasterizationSettings of the keyframe (as built by SLAM/render.py:142-162)."""
         from .rasterizer import _make_settings
-        mp = _lib.MapParams()
-        for i, k in enumerate(self.ORDER):
-            t = self.p[k]
-            mp.param[i] = ptr(t)
-            mp.exp_avg[i] = ptr(self.state[k][0])
-            mp.exp_avg_sq[i] = ptr(self.state[k][1])
-            mp.lr[i] = self.lrs[i]
-        mp.confidence = ptr(self.confidence)
+        mp = self._map_params()
         mask = None
         if render_mask is not None:
             mask = render_mask if render_mask.dtype == torch.uint8 else render_mask.view(torch.uint8) \
@@ -228,10 +235,13 @@ class FusedMappingStep:
                            rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, self.need_n_touched,
                            self.front, self.back)
         self.step += 1
-        with torch.cuda.device(self.dev):
-            check(lib().dqo_mapping_step(s, mp, kf, self.step, float(self.betas[0]), float(self.betas[1]),
-                                         float(self.eps), ptr(self.ws), self.capacity, ptr(self.loss), ptr(self.counts),
-                                         ptr(self.status), _stream()), "dqo_mapping_step")
+        args = (s, mp, kf, self.step, float(self.betas[0]), float(self.betas[1]), float(self.eps), ptr(self.ws),
+                self.capacity, ptr(self.loss), ptr(self.counts), ptr(self.status))
+        if torch.cuda.current_device() == self.dev.index:  # the common case: no device switch on the hot path
+            check(lib().dqo_mapping_step(*args, _stream()), "dqo_mapping_step")
+        else:
+            with torch.cuda.device(self.dev):
+                check(lib().dqo_mapping_step(*args, _stream()), "dqo_mapping_step")
         return self.loss[0], self.loss[1], self.loss[2]
 
     def check(self):

@@ -264,6 +264,28 @@ def test_auto_binning_policy_converges_and_keeps_results():
     rasterizer.set_binning_mode("single")
 
 
+@pytest.mark.skipif(not rh.reference_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("binning", [("single",), ("fixed", 65_536, 3_000_000)])
+def test_more_than_65535_tiles_uses_32bit_keys(binning):
+    """Images with >= 65535 tiles switch the tile-id sort keys from u16 to u32 (both binning modes)."""
+    _, C, _, _ = rh.load_reference()
+    inp = rh.make_inputs("huge", torch.device(DEV))
+    inp["scales"] = inp["scales"] * 3.0
+    cam = inp["cam"]
+    H, W, P = cam.image_height, cam.image_width, inp["xyz"].shape[0]
+    assert ((H + 15) // 16) * ((W + 15) // 16) >= 65535
+    gc, gd = rh.make_pixel_grads(H, W, DEV)
+    fwd = C.rasterize_gaussians(*rh.raster_args(inp))
+    bwd = C.rasterize_gaussians_backward(*rh.backward_args(inp, fwd, gc, gd))
+    o, ex, bw = _run_ours(inp, gc, gd, binning=binning)
+    assert o[0] == fwd[0] and o[1] == fwd[1]
+    for i in (2, 3, 4, 5, 6, 7, 8, 9, 14):
+        assert torch.equal(o[i], fwd[i]), i
+    assert torch.equal(o[13][:o[1]], fwd[13][:fwd[1]])
+    ref = {n: t2n(t) for n, t in zip(GRADS, bwd)}
+    _check_grads(bw, ref)
+
+
 def test_full_size_properties():
     """Size-independent properties at BASELINE config 2 (1M Gaussians, 1200x680)."""
     inp = rh.make_inputs("c2", torch.device(DEV))
