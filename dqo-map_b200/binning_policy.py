@@ -19,7 +19,10 @@ ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_R_FRONT, ST_R_BACK
 MIN_INSTANCES = 1 << 21      # below this the fixed cost of the extra launches outweighs any saving
 WALKED_FRACTION = 0.35       # enter two-phase when the blend walked less than this fraction of R
 GIVE_UP_FRACTION = 0.75      # leave two-phase when front + back instances exceed this fraction of R
-FRONT_OVER_WALKED = 2.0      # front slots per walked entry (a global depth prefix is coarser than per-tile prefixes)
+import os
+
+# front slots per walked entry (a global depth prefix is coarser than per-tile prefixes); env override for experiments
+FRONT_OVER_WALKED = float(os.environ.get("DQO_FRONT_OVER_WALKED", "2.0"))
 BACK_HEADROOM = 1.5
 BACK_FLOOR = 1 << 16
 RETRY_AFTER = 64             # calls to wait before probing two-phase again after giving up

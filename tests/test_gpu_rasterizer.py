@@ -265,7 +265,7 @@ def test_auto_binning_policy_converges_and_keeps_results():
 
 
 @pytest.mark.skipif(not rh.reference_available(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("binning", [("single",), ("fixed", 65_536, 3_000_000)])
+@pytest.mark.parametrize("binning", ["single", "two_phase"])
 def test_more_than_65535_tiles_uses_32bit_keys(binning):
     """Images with >= 65535 tiles switch the tile-id sort keys from u16 to u32 (both binning modes)."""
     _, C, _, _ = rh.load_reference()
@@ -277,13 +277,14 @@ def test_more_than_65535_tiles_uses_32bit_keys(binning):
     gc, gd = rh.make_pixel_grads(H, W, DEV)
     fwd = C.rasterize_gaussians(*rh.raster_args(inp))
     bwd = C.rasterize_gaussians_backward(*rh.backward_args(inp, fwd, gc, gd))
-    o, ex, bw = _run_ours(inp, gc, gd, binning=binning)
+    bwd2 = C.rasterize_gaussians_backward(*rh.backward_args(inp, fwd, gc, gd))
+    mode = ("single",) if binning == "single" else ("fixed", max(256, (fwd[0] // 8) // 256 * 256), fwd[0] + 1024)
+    o, ex, bw = _run_ours(inp, gc, gd, binning=mode)
     assert o[0] == fwd[0] and o[1] == fwd[1]
     for i in (2, 3, 4, 5, 6, 7, 8, 9, 14):
         assert torch.equal(o[i], fwd[i]), i
     assert torch.equal(o[13][:o[1]], fwd[13][:fwd[1]])
-    ref = {n: t2n(t) for n, t in zip(GRADS, bwd)}
-    _check_grads(bw, ref)
+    _check_grads(bw, {n: t2n(t) for n, t in zip(GRADS, bwd)}, ref2={n: t2n(t) for n, t in zip(GRADS, bwd2)})
 
 
 def test_full_size_properties():
