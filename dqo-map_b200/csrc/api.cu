@@ -1,5 +1,6 @@
 // Error reporting and ABI bookkeeping for libdqomap_b200.so.
 #include "common.cuh"
+#include <mutex>
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -14,6 +15,24 @@ void set_error(const char *fmt, ...) {
 
 static long long g_launches = 0;
 void note_launch(int n) { g_launches += n; }
+
+// One non-blocking side stream per device for work that can overlap the caller's stream (fork / join with events;
+// capturable into a CUDA graph together with the caller's stream).
+static std::mutex g_side_mu;
+static cudaStream_t g_side[64] = {};
+cudaStream_t side_stream() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_side_mu);
+    if (!g_side[dev]) {
+        // highest priority: the forked kernels are small and latency-bound, they should slip in between the blocks of
+        // the large kernel they overlap instead of queueing behind its whole grid
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&g_side[dev], cudaStreamNonBlocking, hi) != cudaSuccess) g_side[dev] = nullptr;
+    }
+    return g_side[dev];
+}
 
 static int g_profile = 0;
 static cudaEvent_t g_ev[ST_COUNT];

@@ -20,6 +20,7 @@ namespace dqo {
 void set_error(const char *fmt, ...);
 void note_launch(int n = 1);                      // counts this library's own kernel launches (dqo_launch_count)
 void stage_mark(cudaStream_t stream, int stage);  // records a CUDA event when stage profiling is enabled
+cudaStream_t side_stream(); // per-device non-blocking helper stream (nullptr if unavailable)
 
 // stage ids of dqo_profile_read()
 enum {

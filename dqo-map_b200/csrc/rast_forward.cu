@@ -163,22 +163,45 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const SH sh, float3 pos, fl
             res[c] = ffma(-c1x, sh[9 + c], r);
         }
         if (deg > 1) {
-            float xx = x * x, yy = y * y, zz = z * z;
-            float xy = x * y, yz = y * z, xz = x * z;
+            // operation order of the compiled reference (forward.cu:122-150, SASS of preprocessCUDA): squares and
+            // products rounded separately, 2*zz as zz + zz, every coefficient = (polynomial) * constant rounded before
+            // the FFMA with the SH value; in the degree-3 block 3*xx - yy, 4*zz - xx, 2*zz - 3*xx, .. - 3*yy and
+            // xx - 3*yy are fused
+            const float xx = fmul(x, x), yy = fmul(y, y), zz = fmul(z, z);
+            const float xy = fmul(x, y), yz = fmul(y, z), xz = fmul(x, z);
+            const float zz2 = fadd(zz, zz);
+            const float xx_yy = fadd(xx, -yy);
+            const float k0 = fmul(xy, SH_C2[0]);
+            const float k1 = fmul(yz, SH_C2[1]);
+            const float k2 = fmul(fadd(-yy, fadd(-xx, zz2)), SH_C2[2]);
+            const float k3 = fmul(xz, SH_C2[3]);
+            const float k4 = fmul(xx_yy, SH_C2[4]);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                res[c] = res[c] + SH_C2[0] * xy * sh[12 + c] + SH_C2[1] * yz * sh[15 + c] +
-                         SH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + c] + SH_C2[3] * xz * sh[21 + c] +
-                         SH_C2[4] * (xx - yy) * sh[24 + c];
+                float r = ffma(k0, sh[12 + c], res[c]);
+                r = ffma(k1, sh[15 + c], r);
+                r = ffma(k2, sh[18 + c], r);
+                r = ffma(k3, sh[21 + c], r);
+                res[c] = ffma(k4, sh[24 + c], r);
             }
             if (deg > 2) {
+                const float e4 = fadd(-yy, ffma(zz, 4.0f, -xx));                  // 4zz - xx - yy
+                const float t0 = fmul(fmul(y, SH_C3[0]), ffma(xx, 3.0f, -yy));
+                const float t1 = fmul(fmul(xy, SH_C3[1]), z);
+                const float t2 = fmul(fmul(y, SH_C3[2]), e4);
+                const float t3 = fmul(fmul(z, SH_C3[3]), ffma(yy, -3.0f, ffma(xx, -3.0f, zz2)));
+                const float t4 = fmul(e4, fmul(x, SH_C3[4]));
+                const float t5 = fmul(xx_yy, fmul(z, SH_C3[5]));
+                const float t6 = fmul(fmul(x, SH_C3[6]), ffma(yy, -3.0f, xx));
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    res[c] = res[c] + SH_C3[0] * y * (3.0f * xx - yy) * sh[27 + c] + SH_C3[1] * xy * z * sh[30 + c] +
-                             SH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + c] +
-                             SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
-                             SH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + c] + SH_C3[5] * z * (xx - yy) * sh[42 + c] +
-                             SH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + c];
+                    float r = ffma(t0, sh[27 + c], res[c]);
+                    r = ffma(t1, sh[30 + c], r);
+                    r = ffma(t2, sh[33 + c], r);
+                    r = ffma(t3, sh[36 + c], r);
+                    r = ffma(t4, sh[39 + c], r);
+                    r = ffma(t5, sh[42 + c], r);
+                    res[c] = ffma(t6, sh[45 + c], r);
                 }
             }
         }
@@ -210,6 +233,20 @@ __device__ __forceinline__ bool frustum_test(float px, float py, float pz, const
     // the reference compares against the double literals -1.3 / 1.3
     if (vz <= 0.2f || (double)ppx < -1.3 || (double)ppx > 1.3 || (double)ppy < -1.3 || (double)ppy > 1.3) return false;
     return true;
+}
+
+// Depth-sort keys from the positions alone: float bits of the view depth, 0xFFFFFFFF for Gaussians outside the frustum.
+// (Gaussians that pass the frustum test but emit no instance keep their depth key: they carry zero tiles, so the
+// relative order of the emitting ones -- all that matters -- is unchanged.)  Being independent of the rest of the
+// preprocess, the depth sort runs on a side stream concurrently with it.
+__global__ void __launch_bounds__(256) depth_key_kernel(int P, const float *__restrict__ means, const float *__restrict__ view,
+                                                        const float *__restrict__ proj, uint32_t *depth_key, uint32_t *ids) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    float vz, ppx, ppy;
+    const bool ok = frustum_test(means[3 * idx], means[3 * idx + 1], means[3 * idx + 2], view, proj, &vz, &ppx, &ppy);
+    depth_key[idx] = ok ? __float_as_uint(vz) : 0xFFFFFFFFu;
+    ids[idx] = (uint32_t)idx;
 }
 
 // tile_mask != 0 as one bitmap row per tile row: the per-Gaussian tile count and the instance emission then cost
@@ -296,9 +333,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
     if (idx >= a.P) return;
     int radius_out = 0;
     uint32_t tiles_out = 0;
-    uint32_t key_out = 0xFFFFFFFFu;
     uint8_t flags_out = 0; // bits 0-2: clamped channels, bit 7: splat record valid
-    a.ids[idx] = (uint32_t)idx;
     if (a.n_touched) a.n_touched[idx] = 0;
 
     const float px = a.means3D[3 * idx], py = a.means3D[3 * idx + 1], pz = a.means3D[3 * idx + 2];
@@ -431,13 +466,11 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
                 flags_out = cl | 0x80;
                 radius_out = my_radius;
                 for (uint32_t y = miny; y < maxy; y++) tiles_out += mask_row_count(a.mask_bits, a.mask_words, y, minx, maxx);
-                if (tiles_out > 0) key_out = __float_as_uint(vz);
             }
         }
     }
     a.radii[idx] = radius_out;
     a.tiles[idx] = tiles_out;
-    a.depth_key[idx] = key_out;
     a.clamped[idx] = flags_out;
     const unsigned vis = __ballot_sync(__activemask(), radius_out > 0);
     if ((threadIdx.x & 31) == 0 && vis) atomicAdd(&a.status[DQO_ST_NUM_VISIBLE], __popc(vis));
@@ -1265,6 +1298,35 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         pa.status = status;
         rec = pa.rec;
         depth = pa.depth;
+        // fork: depth keys + the (depth, id) sort of the Gaussians (stable LSD sort on the depth bits) on the side
+        // stream, concurrently with the rest of the preprocess
+        uint32_t *order = (uint32_t *)(geom + GL.order);
+        depth_key_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, projmatrix, pa.depth_key, pa.ids);
+        DQO_LAUNCH_CHECK("depth keys", debug, stream);
+        cudaStream_t sort_stream = debug ? nullptr : side_stream();
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+        if (sort_stream) {
+            if (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+                if (ev_fork) cudaEventDestroy(ev_fork);
+                ev_fork = ev_join = nullptr;
+                sort_stream = nullptr;
+            }
+        }
+        if (sort_stream) {
+            DQO_CUDA_CHECK(cudaEventRecord(ev_fork, stream));
+            DQO_CUDA_CHECK(cudaStreamWaitEvent(sort_stream, ev_fork, 0));
+        } else {
+            sort_stream = stream;
+        }
+        {
+            size_t cub_bytes = GL.cub_bytes;
+            DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(geom + GL.cub, cub_bytes, (const uint32_t *)pa.depth_key,
+                                                           (uint32_t *)(geom + GL.depth_key2), (const uint32_t *)pa.ids,
+                                                           order, P, 0, 32, sort_stream));
+            DQO_LAUNCH_CHECK("depth sort", debug, stream);
+            if (ev_join) DQO_CUDA_CHECK(cudaEventRecord(ev_join, sort_stream));
+        }
         const bool staged = shs && !f_rest && s->M == 16 && ((uintptr_t)shs % 16 == 0);
         const int pre_blocks = (P + PRE_THREADS - 1) / PRE_THREADS;
         const size_t smem = (size_t)(PRE_THREADS / 32) * 32 * SH_ROW_Q * sizeof(float4);
@@ -1282,17 +1344,16 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         DQO_LAUNCH_CHECK("preprocess", debug, stream);
         stage_mark(stream, ST_PREPROCESS);
 
-        // (depth, id) order of the Gaussians: stable LSD sort on the depth bits
-        uint32_t *order = (uint32_t *)(geom + GL.order);
-        size_t cub_bytes = GL.cub_bytes;
-        DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(geom + GL.cub, cub_bytes, (const uint32_t *)pa.depth_key,
-                                                       (uint32_t *)(geom + GL.depth_key2), (const uint32_t *)pa.ids,
-                                                       order, P, 0, 32, stream));
-        DQO_LAUNCH_CHECK("depth sort", debug, stream);
+        // join
+        if (ev_join) {
+            DQO_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0));
+            cudaEventDestroy(ev_fork);
+            cudaEventDestroy(ev_join);
+        }
         stage_mark(stream, ST_DEPTH_SORT);
+        size_t cub_bytes = GL.cub_bytes;
         uint32_t *offsets = (uint32_t *)(geom + GL.offsets);
         TilesInRankOrder it((const uint32_t *)order, GatherTiles{pa.tiles});
-        cub_bytes = GL.cub_bytes;
         DQO_CUDA_CHECK(cub::DeviceScan::InclusiveSum(geom + GL.cub, cub_bytes, it, offsets, P, stream));
         DQO_LAUNCH_CHECK("scan", debug, stream);
         stage_mark(stream, ST_SCAN);

@@ -85,6 +85,7 @@ CONFIGS = {
     # name: (P, W, H, fx, fy, cx, cy, sh_degree)
     "tiny": (2000, 160, 96, 120.0, 120.0, 79.5, 47.5, 0),
     "small": (20000, 320, 240, 260.0, 260.0, 159.5, 119.5, 3),
+    "deg1": (12000, 320, 240, 260.0, 260.0, 159.5, 119.5, 1),
     "ragged": (15000, 333, 187, 270.0, 270.0, 166.0, 93.0, 2),   # neither dimension a multiple of the 16-pixel tile
     "huge": (30000, 4112, 4100, 2000.0, 2000.0, 2055.5, 2049.5, 0),   # 257 x 257 = 66049 tiles: 32-bit tile keys
     "c1": (100000, 640, 480, 525.0, 525.0, 319.5, 239.5, 0),

@@ -155,7 +155,7 @@ def test_against_cpu_oracle(cfg, P, deg, mask):
 
 @pytest.mark.skipif(not rh.reference_available(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("cfg,mask,precomp", [("c1", "ones", False), ("c1", "half", True), ("c2", "ones", False),
-                                              ("ragged", "half", False)])
+                                              ("ragged", "half", False), ("ragged", "ones", False), ("deg1", "ones", False)])
 def test_against_live_reference(cfg, mask, precomp):
     """Full BASELINE sizes against the unmodified reference extension on the same GPU."""
     _, C, _, _ = rh.load_reference()
