@@ -10,7 +10,8 @@ from collections import defaultdict
 STAGE_OF = {  # kernel-name substring -> bench.py stage key
     "preprocess_kernel": "preprocess", "duplicate_kernel": "duplicate", "render_forward_kernel": "render_fwd",
     "render_backward_kernel": "render_bwd", "gaussian_backward_kernel": "gaussian_bwd", "tile_ranges_kernel": "ranges",
-    "adam_geometry_kernel": "adam_geometry", "adam_rest_kernel": "adam_rest",
+    "adam_geometry_kernel": "adam_geometry", "adam_flat_kernel": "adam_flat", "adam_rest_kernel": "adam_rest",
+    "count_back_kernel": "back_binning",
 }
 WANT = [
     ("gpu__time_duration.sum", "time_us"),
@@ -68,8 +69,8 @@ def main():
             k[:46], len(recs), avg("time_us"), avg("dram_rd") / 1e6, avg("dram_wr") / 1e6, avg("dram_pct"), avg("l2_pct"),
             avg("l1_pct"), avg("sm_pct"), avg("issue_pct"), avg("occupancy_pct"), avg("regs"), avg("lanes_per_inst")))
         for sub, stage in STAGE_OF.items():
-            if sub in k:
-                traffic[stage] = int(avg("dram_rd") + avg("dram_wr"))
+            if sub in k:  # kernels of the same stage (e.g. the front and back instantiation) add up
+                traffic[stage] = traffic.get(stage, 0) + int(avg("dram_rd") + avg("dram_wr"))
         if "Onesweep" in k or "RadixSort" in k:
             traffic.setdefault("_radix_kernels", 0)
             traffic["_radix_kernels"] += int((avg("dram_rd") + avg("dram_wr")) * len(recs))
@@ -77,6 +78,8 @@ def main():
     tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_traffic.json")
     allt = json.load(open(tpath)) if os.path.exists(tpath) else {}
     allt.setdefault(config, {}).update(traffic)
+    if "adam_flat_kernel" in per:
+        allt[config].pop("adam_geometry", None)
     allt[config]["_source"] = os.path.basename(out_txt)
     json.dump(allt, open(tpath, "w"), indent=1, sort_keys=True)
     print("\n".join(lines))
