@@ -194,7 +194,7 @@ struct __align__(16) SplatB {
     float4 r0, r1, c; // {x, y, conic.x, conic.y} {conic.z, opacity, power_reject, -} {r, g, b, Gaussian id bits}
 };
 
-__global__ void __launch_bounds__(RB_THREADS) render_backward_kernel(RenderBwdArgs a) {
+__global__ void __launch_bounds__(RB_THREADS, 6) render_backward_kernel(RenderBwdArgs a) {
     // RB_BATCH entries are staged per round.  With 512 most tiles need a single round (max n_contrib is a few hundred):
     // the four warps then walk their own lists without meeting at a barrier after every 256 entries, where the fast
     // ones used to wait for the slowest sub-block.
@@ -352,7 +352,7 @@ __device__ __constant__ float B_SH_C3[7] = {-0.5900435899266435f, 2.890611442640
 // 32 x 192 B of SH gradients out with coalesced 128-bit accesses through a padded shared-memory tile.
 // SHMODE 1: staged merged SH, 2: staged split f_dc / f_rest inputs (gradients are still written merged), 0: plain.
 template <int SHMODE>
-__global__ void __launch_bounds__(GB_THREADS) gaussian_backward_kernel(GaussBwdArgs a) {
+__global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussBwdArgs a) {
     extern __shared__ float4 s_row[];
     constexpr bool STAGED = SHMODE != 0;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;

@@ -757,7 +757,7 @@ struct RenderArgs {
 //   PHASE 2: unfinished tiles resume from the parked state and walk their back list; list positions continue at the
 //            length of the front list, so n_contrib and the blend order are those of the concatenated (= reference) list.
 template <int PHASE>
-__global__ void __launch_bounds__(256) render_forward_kernel(RenderArgs a) {
+__global__ void __launch_bounds__(256, 4) render_forward_kernel(RenderArgs a) {
     __shared__ SplatS s_sp[256]; // one 48-byte record per staged splat: a single base + j*48 address in the loop
     __shared__ uint8_t s_mask[256];
     __shared__ uint8_t s_list[8][256];
