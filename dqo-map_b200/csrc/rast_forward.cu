@@ -34,7 +34,26 @@ static size_t bump(size_t &cur, size_t bytes) {
     return off;
 }
 
+int make_geom_layout_uncached(int P, GeomLayout *L);
+int make_bin_layout_uncached(int64_t C, BinLayout *L);
+// The layouts depend on CUB's temp-storage size queries, which cost several microseconds of host time each; the
+// forward, the backward and the fused step all ask for the same few sizes over and over, so the last result is kept
+// per thread.
 int make_geom_layout(int P, GeomLayout *L) {
+    static thread_local int last_P = -1;
+    static thread_local GeomLayout last_L;
+    if (P == last_P) {
+        *L = last_L;
+        return 0;
+    }
+    const int rc = make_geom_layout_uncached(P, L);
+    if (rc == 0) {
+        last_P = P;
+        last_L = *L;
+    }
+    return rc;
+}
+int make_geom_layout_uncached(int P, GeomLayout *L) {
     size_t cur = 0;
     size_t n = (size_t)(P > 0 ? P : 1);
     L->rec = bump(cur, n * 48);
@@ -70,6 +89,20 @@ int make_geom_layout(int P, GeomLayout *L) {
 }
 
 int make_bin_layout(int64_t C, BinLayout *L) {
+    static thread_local int64_t last_C = -1;
+    static thread_local BinLayout last_L;
+    if (C == last_C) {
+        *L = last_L;
+        return 0;
+    }
+    const int rc = make_bin_layout_uncached(C, L);
+    if (rc == 0) {
+        last_C = C;
+        last_L = *L;
+    }
+    return rc;
+}
+int make_bin_layout_uncached(int64_t C, BinLayout *L) {
     size_t cur = 0;
     size_t n = (size_t)(C > 0 ? C : 1);
     L->keys_in = bump(cur, n * 4);

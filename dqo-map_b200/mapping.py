@@ -192,10 +192,12 @@ class FusedMappingStep:
         self.confidence = confidence
         self.need_n_touched = need_n_touched
         self.state = {k: (torch.zeros_like(params[k]), torch.zeros_like(params[k])) for k in self.ORDER}
+        self._kf_cache = {}
         self.step = 0
         self.capacity = int(capacity) if capacity else max(8 * self.P, 1 << 16)
         self._alloc()
         self.loss = torch.zeros(4, dtype=torch.float32, device=self.dev)
+        self._loss_views = (self.loss[0], self.loss[1], self.loss[2])
         self.counts = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.status = torch.zeros(_lib.ST_WORDS, dtype=torch.int32, device=self.dev)
 
@@ -223,17 +225,28 @@ class FusedMappingStep:
         """rs: GaussianRasterizationSettings of the keyframe (as built by SLAM/render.py:142-162)."""
         from .rasterizer import _make_settings
         mp = self._map_params()
-        mask = None
-        if render_mask is not None:
-            mask = render_mask if render_mask.dtype == torch.uint8 else render_mask.view(torch.uint8) \
-                if render_mask.dtype == torch.bool else (render_mask != 0).view(torch.uint8)
-            mask = mask.contiguous()
-        kf = _lib.Keyframe(ptr(gt_color.contiguous()), ptr(gt_depth.contiguous()), ptr(mask), ptr(tile_mask.contiguous()),
-                           ptr(rs.viewmatrix), ptr(rs.projmatrix), ptr(rs.campos), ptr(rs.bg), self.cw, self.dw, self.thr)
-        s = _make_settings(self.P, int(rs.sh_degree), self.M, self.W, self.H, rs.tanfovx, rs.tanfovy, rs.cx, rs.cy,
-                           rs.scale_modifier, rs.color_sigma, rs.opaque_threshold, rs.depth_threshold,
-                           rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, self.need_n_touched,
-                           self.front, self.back)
+        # the ctypes views of a keyframe (settings + pointers) are cached per keyframe: a mapping window revisits the
+        # same few keyframes, and building the structs costs more host time than launching the step
+        key = (id(rs), tile_mask.data_ptr(), gt_color.data_ptr(), gt_depth.data_ptr(),
+               render_mask.data_ptr() if render_mask is not None else 0, self.front, self.back, self.need_n_touched)
+        hit = self._kf_cache.get(key)
+        if hit is None:
+            mask = None
+            if render_mask is not None:
+                mask = render_mask if render_mask.dtype == torch.uint8 else render_mask.view(torch.uint8) \
+                    if render_mask.dtype == torch.bool else (render_mask != 0).view(torch.uint8)
+                mask = mask.contiguous()
+            tensors = (gt_color.contiguous(), gt_depth.contiguous(), mask, tile_mask.contiguous(), rs)  # kept alive
+            kf = _lib.Keyframe(ptr(tensors[0]), ptr(tensors[1]), ptr(mask), ptr(tensors[3]), ptr(rs.viewmatrix),
+                               ptr(rs.projmatrix), ptr(rs.campos), ptr(rs.bg), self.cw, self.dw, self.thr)
+            s = _make_settings(self.P, int(rs.sh_degree), self.M, self.W, self.H, rs.tanfovx, rs.tanfovy, rs.cx, rs.cy,
+                               rs.scale_modifier, rs.color_sigma, rs.opaque_threshold, rs.depth_threshold,
+                               rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, self.need_n_touched,
+                               self.front, self.back)
+            if len(self._kf_cache) >= 64:
+                self._kf_cache.clear()
+            hit = self._kf_cache[key] = (s, kf, tensors)
+        s, kf = hit[0], hit[1]
         self.step += 1
         args = (s, mp, kf, self.step, float(self.betas[0]), float(self.betas[1]), float(self.eps), ptr(self.ws),
                 self.capacity, ptr(self.loss), ptr(self.counts), ptr(self.status))
@@ -242,7 +255,7 @@ class FusedMappingStep:
         else:
             with torch.cuda.device(self.dev):
                 check(lib().dqo_mapping_step(*args, _stream()), "dqo_mapping_step")
-        return self.loss[0], self.loss[1], self.loss[2]
+        return self._loss_views
 
     def check(self):
         host = self.status.tolist()
