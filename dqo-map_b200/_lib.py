@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdqomap_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_R_FRONT, ST_R_BACK, ST_WALKED, ST_UNFINISHED = range(8)
 ST_WORDS = 8
@@ -37,7 +37,7 @@ class AdamTensor(C.Structure):
 
 class MapParams(C.Structure):
     _fields_ = [("param", c_p * 6), ("exp_avg", c_p * 6), ("exp_avg_sq", c_p * 6), ("lr", C.c_double * 6),
-                ("confidence", c_p)]
+                ("confidence", c_p), ("ever", c_p)]
 
 
 class Keyframe(C.Structure):

@@ -29,7 +29,7 @@ int rast_backward_impl(const dqo_rast_settings *s, const float *background, cons
                        const void *image_buffer, const int32_t *status, const float *dL_dout_color,
                        const float *dL_dout_depth, const int32_t *hit_image, float *dL_dmeans2D, float *dL_dconic,
                        float *dL_dopacity, float *dL_dcolors, float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh,
-                       float *dL_dscales, float *dL_drotations, void *stream_);
+                       float *dL_dscales, float *dL_drotations, uint8_t *ever, void *stream_);
 
 struct StepLayout {
     size_t act_opacity, act_scales, act_rot;                    // activated copies [P], [P,3], [P,4]
@@ -115,6 +115,7 @@ struct SmallArgs {
     const float *act_opacity, *act_scales;
     const float *g_means3D, *g_opacity, *g_scales, *g_rot, *g_sh;
     float *confidence;
+    const uint8_t *ever; // per-Gaussian "has ever had a non-zero gradient" (nullptr: decide from the values instead)
     const int *status; // the step is skipped when the forward flagged an instance overflow (gradients are invalid)
     AdamScalars k;
 };
@@ -198,8 +199,10 @@ __device__ __forceinline__ void adam4(float4 &p, const float4 g, float4 &m, floa
 }
 // flat Adam over [begin of tail, n) for the (< 4) elements a float4 sweep leaves over
 __device__ __forceinline__ void adam_tail(float *p, float *m, float *v, const float *g, const float *act, int mode,
-                                          long long from, long long n, const AdamScalars &k, float ss) {
+                                          long long from, long long n, const AdamScalars &k, float ss, const uint8_t *ever,
+                                          int row_width) {
     for (long long e = from + threadIdx.x; e < n; e += blockDim.x) {
+        if (ever && !ever[e / row_width]) continue;
         float gg = g[e];
         if (mode == 1) gg *= act[e];
         if (mode == 2) gg *= act[e] * (1.0f - act[e]);
@@ -220,7 +223,16 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(FlatArgs fa) {
         const float ss = a.k.step_size[sc ? 4 : 0];
         const long long q = (long long)b * blockDim.x + threadIdx.x;
         if (q < fa.n4_vec3) {
+            bool e[4] = {true, true, true, true};
+            if (a.ever) { // gradients of never-touched Gaussians were not written: neither read nor used
+                const long long ra = (4 * q) / 3, rb = (4 * q + 3) / 3;
+                const bool ea = a.ever[ra] != 0, eb = a.ever[rb] != 0;
+                if (!(ea || eb)) return;
+#pragma unroll
+                for (int c = 0; c < 4; c++) e[c] = ((4 * q + c) / 3 == ra) ? ea : eb;
+            }
             float4 g = reinterpret_cast<const float4 *>(G_)[q];
+            g.x = e[0] ? g.x : 0.f; g.y = e[1] ? g.y : 0.f; g.z = e[2] ? g.z : 0.f; g.w = e[3] ? g.w : 0.f;
             float4 m = reinterpret_cast<float4 *>(M_)[q], v = reinterpret_cast<float4 *>(V_)[q];
             if (!(all_zero(g) && all_zero(m) && all_zero(v))) {
                 if (sc) {
@@ -234,7 +246,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(FlatArgs fa) {
                 reinterpret_cast<float4 *>(V_)[q] = v;
             }
         }
-        if (b == 0) adam_tail(P_, M_, V_, G_, a.act_scales, sc ? 1 : 0, fa.n4_vec3 * 4, 3ll * a.P, a.k, ss);
+        if (b == 0) adam_tail(P_, M_, V_, G_, a.act_scales, sc ? 1 : 0, fa.n4_vec3 * 4, 3ll * a.P, a.k, ss, a.ever, 3);
         return;
     }
     b -= 2 * fa.nb_vec3;
@@ -242,7 +254,14 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(FlatArgs fa) {
         const float ss = a.k.step_size[3];
         const long long q = (long long)b * blockDim.x + threadIdx.x;
         if (q < fa.n4_scalar) {
+            uint32_t e4 = 0x01010101u;
+            if (a.ever) {
+                e4 = reinterpret_cast<const uint32_t *>(a.ever)[q];
+                if (e4 == 0) return;
+            }
             float4 g = reinterpret_cast<const float4 *>(a.g_opacity)[q];
+            g.x = (e4 & 0xFFu) ? g.x : 0.f; g.y = (e4 & 0xFF00u) ? g.y : 0.f;
+            g.z = (e4 & 0xFF0000u) ? g.z : 0.f; g.w = (e4 & 0xFF000000u) ? g.w : 0.f;
             float4 m = reinterpret_cast<float4 *>(a.m_op)[q], v = reinterpret_cast<float4 *>(a.v_op)[q];
             if (!(all_zero(g) && all_zero(m) && all_zero(v))) {
                 const float4 o = reinterpret_cast<const float4 *>(a.act_opacity)[q];
@@ -254,7 +273,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(FlatArgs fa) {
                 reinterpret_cast<float4 *>(a.v_op)[q] = v;
             }
         }
-        if (b == 0) adam_tail(a.opacity, a.m_op, a.v_op, a.g_opacity, a.act_opacity, 2, fa.n4_scalar * 4, a.P, a.k, ss);
+        if (b == 0) adam_tail(a.opacity, a.m_op, a.v_op, a.g_opacity, a.act_opacity, 2, fa.n4_scalar * 4, a.P, a.k, ss, a.ever, 1);
         return;
     }
     b -= fa.nb_scalar;
@@ -262,6 +281,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(FlatArgs fa) {
     if (dc) b -= fa.nb_gauss;
     const int i = (int)(b * blockDim.x + threadIdx.x);
     if (i >= a.P) return;
+    if (a.ever && !a.ever[i]) return;
     if (!dc) { // role 3: rotation, q = r / max(|r|, eps); dL/dr = (g - q (q . g)) / max(|r|, eps)
         const float4 g = reinterpret_cast<const float4 *>(a.g_rot)[i];
         float4 m = reinterpret_cast<float4 *>(a.m_rot)[i], v = reinterpret_cast<float4 *>(a.v_rot)[i];
@@ -306,22 +326,30 @@ struct RestAdamArgs {
     long long n4; // number of float4 chunks of f_rest
     float *f_rest, *m_rest, *v_rest;
     const float *g_sh;
+    const uint8_t *ever;
     const int *status;
     AdamScalars k;
 };
 __global__ void __launch_bounds__(256) adam_rest_kernel(RestAdamArgs a) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= a.n4 || a.status[DQO_ST_OVERFLOW]) return;
+    const long long e0 = q * 4;
+    bool ea = true, eb = true;
+    const long long ra = e0 / 45;
+    if (a.ever) {
+        ea = a.ever[ra] != 0;
+        eb = a.ever[(e0 + 3) / 45] != 0;
+        if (!(ea || eb)) return;
+    }
     float4 m = reinterpret_cast<float4 *>(a.m_rest)[q];
     float4 v = reinterpret_cast<float4 *>(a.v_rest)[q];
-    const long long e0 = q * 4;
     float g[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         const long long e = e0 + c;
         const long long row = e / 45;
         const int col = (int)(e - row * 45);
-        g[c] = __ldg(&a.g_sh[row * 48 + 3 + col]);
+        g[c] = ((row == ra) ? ea : eb) ? __ldg(&a.g_sh[row * 48 + 3 + col]) : 0.f;
     }
     // zero gradient on zero moments is a fixed point of Adam (m' = v' = 0, p' = p - step * 0 / eps = p): nothing to
     // read or write for Gaussians that no keyframe has touched yet (most of the map for any single view)
@@ -342,6 +370,7 @@ __global__ void adam_rest_tail_kernel(long long begin, long long end, RestAdamAr
     const long long e = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= end || a.status[DQO_ST_OVERFLOW]) return;
     const long long row = e / 45;
+    if (a.ever && !a.ever[row]) return;
     const int col = (int)(e - row * 45);
     float p = a.f_rest[e], m = a.m_rest[e], v = a.v_rest[e];
     adam_update(p, a.g_sh[row * 48 + 3 + col], m, v, a.k, a.k.step_size[2]);
@@ -404,7 +433,7 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
     rc = rast_backward_impl(s, kf->background, xyz, f_dc, f_rest, nullptr, act_sc, act_rot, nullptr, kf->viewmatrix,
                             kf->projmatrix, kf->campos, radii, ws + L.geom, ws + L.binning, capacity, ws + L.image, status,
                             g_img, g_depth, hit_depth, nullptr, nullptr, g_op, nullptr, g_means3D, nullptr, g_sh, g_sc,
-                            g_rot, stream_);
+                            g_rot, p->ever, stream_);
     if (rc) return rc;
 
     AdamScalars k;
@@ -418,12 +447,13 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
     sa.m_xyz = p->exp_avg[0]; sa.v_xyz = p->exp_avg_sq[0]; sa.m_op = p->exp_avg[3]; sa.v_op = p->exp_avg_sq[3];
     sa.m_sc = p->exp_avg[4]; sa.v_sc = p->exp_avg_sq[4]; sa.m_rot = p->exp_avg[5]; sa.v_rot = p->exp_avg_sq[5];
     sa.act_opacity = act_op; sa.act_scales = act_sc; sa.g_means3D = g_means3D; sa.g_opacity = g_op; sa.g_scales = g_sc;
-    sa.g_rot = g_rot; sa.g_sh = g_sh; sa.confidence = p->confidence; sa.status = status; sa.k = k;
+    sa.g_rot = g_rot; sa.g_sh = g_sh; sa.confidence = p->confidence; sa.ever = p->ever; sa.status = status; sa.k = k;
     bool aligned = true;
     {
         const void *ptrs[] = {sa.xyz, sa.m_xyz, sa.v_xyz, sa.scaling, sa.m_sc, sa.v_sc, sa.opacity, sa.m_op, sa.v_op,
                               sa.rotation, sa.m_rot, sa.v_rot, g_means3D, g_sc, g_op, g_rot, act_op, act_sc};
         for (const void *q : ptrs) aligned &= ((uintptr_t)q % 16 == 0);
+        aligned &= ((uintptr_t)p->ever % 4 == 0);
     }
     if (aligned) {
         FlatArgs fa;
@@ -443,7 +473,7 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
     if (M == 16) {
         RestAdamArgs ra;
         const long long total = (long long)P * 45;
-        ra.n4 = total / 4; ra.f_rest = f_rest; ra.m_rest = p->exp_avg[2]; ra.v_rest = p->exp_avg_sq[2]; ra.g_sh = g_sh; ra.status = status; ra.k = k;
+        ra.n4 = total / 4; ra.f_rest = f_rest; ra.m_rest = p->exp_avg[2]; ra.v_rest = p->exp_avg_sq[2]; ra.g_sh = g_sh; ra.ever = p->ever; ra.status = status; ra.k = k;
         if (ra.n4 > 0) adam_rest_kernel<<<(unsigned)((ra.n4 + 255) / 256), 256, 0, stream>>>(ra);
         if (total % 4) adam_rest_tail_kernel<<<1, 32, 0, stream>>>(ra.n4 * 4, total, ra);
         DQO_LAUNCH_CHECK("adam f_rest", s->debug, stream);

@@ -335,6 +335,10 @@ struct GaussBwdArgs {
     const uint8_t *clamped;
     const float *gacc;
     float *dL_dmeans2D, *dL_dconic, *dL_dopacity, *dL_dcolors, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drot;
+    // Fused mapping step only (nullptr otherwise): ever[i] != 0 once Gaussian i has received a non-zero gradient.  A
+    // Gaussian that never has is a fixed point of Adam (zero gradient on zero moments), so its gradients are neither
+    // written here nor read by the optimiser kernels: one byte instead of ~240 B written and ~600 B read per step.
+    uint8_t *ever;
 };
 
 __device__ __constant__ float B_SH_C0 = 0.28209479177387814f;
@@ -406,6 +410,16 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
     float drot[4] = {g[12], g[13], g[14], g[15]};
     float dscale[3] = {0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    bool write_out = live;
+    if (a.ever && live) {
+        // all outputs are products with the accumulator record: an all-zero record means all-zero gradients
+        bool nz = false;
+#pragma unroll
+        for (int k = 0; k < DQO_GACC_FLOATS; k++) nz |= (g[k] != 0.f);
+        const bool was = a.ever[idx] != 0;
+        if (nz && !was) a.ever[idx] = 1;
+        write_out = nz || was;
+    }
     float *dsh = (a.dL_dsh && live) ? a.dL_dsh + (size_t)idx * M * 3 : nullptr;
     float shg[48]; // staged path: this Gaussian's SH gradients (flat [k][c])
     if (STAGED) {
@@ -666,17 +680,18 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
         for (int i = 0; i < 12; i++)
             wbuf[lane * GB_ROW_Q + i] = make_float4(shg[4 * i], shg[4 * i + 1], shg[4 * i + 2], shg[4 * i + 3]);
         __syncwarp();
+        const unsigned rows_out = __ballot_sync(0xFFFFFFFFu, write_out);
         if (nrow > 0) {
             float4 *gd = reinterpret_cast<float4 *>(a.dL_dsh) + (size_t)base_g * 12;
             const int nq = nrow * 12;
 #pragma unroll
             for (int i = 0; i < 12; i++) {
                 const int q = i * 32 + lane;
-                if (q < nq) gd[q] = wbuf[(q / 12) * GB_ROW_Q + (q % 12)];
+                if (q < nq && ((rows_out >> (q / 12)) & 1)) gd[q] = wbuf[(q / 12) * GB_ROW_Q + (q % 12)];
             }
         }
     }
-    if (!live) return;
+    if (!write_out) return;
 
     if (a.dL_dmeans2D) {
         a.dL_dmeans2D[3 * idx] = g[0];
@@ -717,7 +732,7 @@ int rast_backward_impl(const dqo_rast_settings *s, const float *background, cons
                        const void *image_buffer, const int32_t *status, const float *dL_dout_color,
                        const float *dL_dout_depth, const int32_t *hit_image, float *dL_dmeans2D, float *dL_dconic,
                        float *dL_dopacity, float *dL_dcolors, float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh,
-                       float *dL_dscales, float *dL_drotations, void *stream_);
+                       float *dL_dscales, float *dL_drotations, uint8_t *ever, void *stream_);
 }
 
 extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *background, const float *means3D,
@@ -733,7 +748,7 @@ extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *backgr
     return rast_backward_impl(s, background, means3D, shs, nullptr, colors_precomp, scales, rotations, cov3D_precomp,
                               viewmatrix, projmatrix, campos, radii, geom_buffer, binning_buffer, capacity, image_buffer,
                               status, dL_dout_color, dL_dout_depth, hit_image, dL_dmeans2D, dL_dconic, dL_dopacity,
-                              dL_dcolors, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, stream_);
+                              dL_dcolors, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, nullptr, stream_);
 }
 
 int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background, const float *means3D,
@@ -745,7 +760,7 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
                                  const float *dL_dout_depth, const int32_t *hit_image, float *dL_dmeans2D,
                                  float *dL_dconic, float *dL_dopacity, float *dL_dcolors, float *dL_dmeans3D,
                                  float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
-                                 void *stream_) {
+                                 uint8_t *ever, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!s || s->P < 0) {
         set_error("dqo_rast_backward: invalid settings");
@@ -809,6 +824,7 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     ga.dL_dmeans2D = dL_dmeans2D; ga.dL_dconic = dL_dconic; ga.dL_dopacity = dL_dopacity; ga.dL_dcolors = dL_dcolors;
     ga.dL_dmeans3D = dL_dmeans3D; ga.dL_dcov3D = dL_dcov3D; ga.dL_dsh = (s->M > 0) ? dL_dsh : nullptr;
     ga.dL_dscales = dL_dscales; ga.dL_drot = dL_drotations;
+    ga.ever = ever;
     const bool staged = shs && !f_rest && dL_dsh && s->M == 16 && ((uintptr_t)shs % 16 == 0) && ((uintptr_t)dL_dsh % 16 == 0);
     const int gb_blocks = (P + GB_THREADS - 1) / GB_THREADS;
     const size_t gb_smem = (size_t)(GB_THREADS / 32) * 32 * GB_ROW_Q * sizeof(float4);

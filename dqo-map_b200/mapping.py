@@ -192,6 +192,9 @@ class FusedMappingStep:
         self.confidence = confidence
         self.need_n_touched = need_n_touched
         self.state = {k: (torch.zeros_like(params[k]), torch.zeros_like(params[k])) for k in self.ORDER}
+        # one byte per Gaussian: has it ever received a non-zero gradient?  (zero-initialised with the moments; Gaussians
+        # that never have are skipped by the backward's gradient writes and by the optimiser, see dqo_map_params.ever)
+        self.ever = torch.zeros(self.P, dtype=torch.uint8, device=self.dev)
         self._kf_cache = {}
         self.step = 0
         self.capacity = int(capacity) if capacity else max(8 * self.P, 1 << 16)
@@ -212,6 +215,7 @@ class FusedMappingStep:
                 mp.exp_avg_sq[i] = ptr(self.state[k][1])
                 mp.lr[i] = self.lrs[i]
             mp.confidence = ptr(self.confidence)
+            mp.ever = ptr(self.ever)
             self._mp, self._mp_key = mp, key
         return self._mp
 
@@ -265,6 +269,10 @@ class FusedMappingStep:
                                 "step was skipped on the device, repeat it with larger buffers"
                                 % (self.capacity, self.front, self.back, host[_lib.ST_NUM_RENDERED], host[_lib.ST_R_BACK]))
         return host
+
+    def mark_all_touched(self):
+        """Call after writing non-zero values into `self.state` by hand (e.g. restoring a checkpoint)."""
+        self.ever.fill_(1)
 
     def set_binning(self, front_instances, back_instances):
         """Switch between single-phase (0, 0) and two-phase binning; front + back must fit the capacity."""

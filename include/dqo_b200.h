@@ -269,6 +269,11 @@ typedef struct dqo_map_params {
     float *exp_avg_sq[6];
     double lr[6];
     float *confidence; /* [P] or NULL */
+    /* [P] bytes or NULL.  ever[i] becomes 1 when Gaussian i first receives a non-zero gradient.  A Gaussian that never
+     * has is a fixed point of Adam (zero gradient on zero moments): its gradients are then neither written by the backward
+     * nor read by the optimiser.  Owned by the caller, zero-initialised TOGETHER WITH the moments (set to 1 wherever moments
+     * are restored non-zero). */
+    uint8_t *ever;
 } dqo_map_params;
 typedef struct dqo_keyframe {
     const float *gt_color;      /* [H,W,3] */
