@@ -1352,14 +1352,6 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         } else {
             sort_stream = stream;
         }
-        {
-            size_t cub_bytes = GL.cub_bytes;
-            DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(geom + GL.cub, cub_bytes, (const uint32_t *)pa.depth_key,
-                                                           (uint32_t *)(geom + GL.depth_key2), (const uint32_t *)pa.ids,
-                                                           order, P, 0, 32, sort_stream));
-            DQO_LAUNCH_CHECK("depth sort", debug, stream);
-            if (ev_join) DQO_CUDA_CHECK(cudaEventRecord(ev_join, sort_stream));
-        }
         const bool staged = shs && !f_rest && s->M == 16 && ((uintptr_t)shs % 16 == 0);
         const int pre_blocks = (P + PRE_THREADS - 1) / PRE_THREADS;
         const size_t smem = (size_t)(PRE_THREADS / 32) * 32 * SH_ROW_Q * sizeof(float4);
@@ -1376,6 +1368,17 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         }
         DQO_LAUNCH_CHECK("preprocess", debug, stream);
         stage_mark(stream, ST_PREPROCESS);
+        // enqueued after the preprocess so that the big kernel starts right behind the key kernel and the small,
+        // high-priority sort kernels slip in between its blocks (enqueueing them first delayed the preprocess by the
+        // host time of six launches)
+        {
+            size_t cub_bytes = GL.cub_bytes;
+            DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(geom + GL.cub, cub_bytes, (const uint32_t *)pa.depth_key,
+                                                           (uint32_t *)(geom + GL.depth_key2), (const uint32_t *)pa.ids,
+                                                           order, P, 0, 32, sort_stream));
+            DQO_LAUNCH_CHECK("depth sort", debug, stream);
+            if (ev_join) DQO_CUDA_CHECK(cudaEventRecord(ev_join, sort_stream));
+        }
 
         // join
         if (ev_join) {
