@@ -158,3 +158,50 @@ def make_tile_mask(name, kind="ones", seed=7):
 
 RENDER_DEFAULTS = dict(opaque_threshold=0.6, normal_threshold=math.cos(math.radians(60.0)), depth_threshold=1.0,
                        color_sigma=3.0, T_threshold=0.0001, scale_modifier=1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Multi-object scene (BASELINE config 3, "Cube-Diorama room-shaped": ~20 object IDs + background), SURVEY.md 8d/8e.
+# Every object owns its Gaussians; object 0 is the background shell (the largest unit of the bin packing).
+# ---------------------------------------------------------------------------------------------------------------------
+def object_counts(n_objects=20, seed=2024, background=200_000):
+    """Gaussians per object, object 0 = background.  Deterministic: every rank computes the same table."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    counts = (20_000 * (1.0 + 3.0 * torch.rand(n_objects, generator=g))).long().tolist()
+    return [int(background)] + [int(c) for c in counts]
+
+
+def make_object(obj_id, count, cam_name="c1", seed=2024, sh_degree=3):
+    """Activated Gaussians of one object: surfels on an ellipsoid placed in the camera frustum (object 0: a far wall)."""
+    Pn, W, H, fx, fy, cx, cy, _ = CONFIGS[cam_name]
+    g = torch.Generator(device="cpu").manual_seed(seed * 1000 + obj_id)
+    cam = make_camera(cam_name)
+    P = int(count)
+    if obj_id == 0:
+        z = 4.5 + 0.05 * torch.randn(P, generator=g)
+        u, v = torch.rand(P, generator=g) * 2 - 1, torch.rand(P, generator=g) * 2 - 1
+        pts_c = torch.stack([u * z * (W / (2 * fx)), v * z * (H / (2 * fy)), z], dim=1)
+    else:
+        zc = 1.5 + 2.5 * float(torch.rand(1, generator=g))
+        uc, vc = (float(torch.rand(1, generator=g)) * 1.4 - 0.7), (float(torch.rand(1, generator=g)) * 1.4 - 0.7)
+        centre = torch.tensor([uc * zc * (W / (2 * fx)), vc * zc * (H / (2 * fy)), zc])
+        axes = 0.15 + 0.3 * torch.rand(3, generator=g)
+        d = torch.randn(P, 3, generator=g)
+        d = d / d.norm(dim=1, keepdim=True)
+        pts_c = centre + d * axes * (1.0 + 0.02 * torch.randn(P, 1, generator=g))
+    W2C = cam.world_view_transform.transpose(0, 1).double()
+    C2W = torch.linalg.inv(W2C)
+    xyz = (pts_c.double() @ C2W[:3, :3].T + C2W[:3, 3]).float()
+    s = torch.exp(math.log(0.004) + (math.log(0.03) - math.log(0.004)) * torch.rand(P, 2, generator=g))
+    scales = torch.cat([s, 0.1 * s.min(dim=1, keepdim=True).values], dim=1)
+    scales = torch.gather(scales, 1, torch.argsort(torch.rand(P, 3, generator=g), dim=1)).contiguous()
+    q = torch.randn(P, 4, generator=g)
+    op = torch.where(torch.rand(P, generator=g) < 0.7, torch.tensor(0.99), 0.05 + 0.85 * torch.rand(P, generator=g))
+    M = (sh_degree + 1) ** 2
+    base = torch.rand(3, generator=g)
+    shs = torch.zeros(P, M, 3)
+    shs[:, 0, :] = RGB2SH((base + 0.15 * torch.randn(P, 3, generator=g)).clamp(0, 1))
+    if M > 1:
+        shs[:, 1:, :] = 0.05 * torch.randn(P, M - 1, 3, generator=g)
+    return {"xyz": xyz.contiguous(), "scales": scales, "rotations": (q / q.norm(dim=1, keepdim=True)).contiguous(),
+            "opacity": op.unsqueeze(1).contiguous(), "shs": shs.contiguous(), "sh_degree": sh_degree, "obj_id": obj_id}
