@@ -407,6 +407,11 @@ def main():
                     "frac": achieved / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes": int(alg[dom]), "kernel_ms": stage_ms[dom],
+                    "note": "no stage is a dense contraction, so every stage is reported against the HBM roofline; the two "
+                            "blend kernels are in fact FP32-issue bound (ncu: ~65 % issue-active, 1-2 % DRAM, "
+                            "profiles/r01_ncu_full_final_summary.txt) -- their DRAM traffic is far below the algorithmic "
+                            "bytes of the SURVEY model because the per-pair atomics were replaced by one reduced RED per "
+                            "warp and splat and the lists are read once",
                     "per_stage": {k: {"ms": stage_ms.get(k, 0.0), "alg_bytes": int(v),
                                       "gbps": (v / (stage_ms[k] / 1000.0) / 1e9) if stage_ms.get(k, 0) > 0 else None}
                                   for k, v in alg.items()}}
