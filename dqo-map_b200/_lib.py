@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdqomap_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_R_FRONT, ST_R_BACK, ST_WALKED, ST_UNFINISHED = range(8)
 ST_WORDS = 8
@@ -73,6 +73,12 @@ PROTOTYPES = {
     "dqo_topk_tilemask": (C.c_int, [C.c_int32, C.c_int32, c_p, C.c_int32, C.c_int32, c_p, c_p, c_p, c_p]),
     "dqo_tilemask_to_pixelmask": (C.c_int, [C.c_int32, C.c_int32, c_p, c_p, c_p]),
     "dqo_render_error_maps": (C.c_int, [C.c_int32, C.c_int32] + [c_p] * 8 + [c_p]),
+    "dqo_depth_maxpool": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_p, c_p, c_p]),
+    "dqo_vertex_normal_workspace_bytes": (C.c_size_t, []),
+    "dqo_vertex_normal_map": (C.c_int, [C.c_int32, C.c_int32, c_p] + [C.c_float] * 4 + [c_p, c_p, c_p, c_p]),
+    "dqo_normal_map": (C.c_int, [C.c_int32, C.c_int32, c_p, c_p, c_p, c_p]),
+    "dqo_icp_workspace_bytes": (C.c_size_t, []),
+    "dqo_icp_level": (C.c_int, [C.c_int32, C.c_int32, c_p, c_p, c_p, c_p] + [C.c_float] * 7 + [C.c_int32, c_p, c_p, c_p, c_p]),
     "dqo_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "dqo_masked_l1_loss": (C.c_int, [C.c_int32, C.c_int32] + [c_p] * 6 + [C.c_float, C.c_float, C.c_float]
                            + [c_p] * 5 + [c_p]),

@@ -218,6 +218,30 @@ int dqo_render_error_maps(int32_t W, int32_t H, const float *render_color /* [3,
                           float *normal_error /* zeros; NULL to skip */, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Tracker front-end (inline PyTorch in the reference).
+ *   dqo_depth_maxpool       one level of ImagePyramids(.., "max"): MaxPool2d(1 << level) of the depth (SLAM/icp.py:342-360)
+ *   dqo_vertex_normal_map   compute_vertex_map + compute_normal_map fused (SLAM/utils.py:65-125): vertex [H,W,3] from depth
+ *                           and K, normal = cross(sobel_y, sobel_x) of the vertex map (replicate border), normalised,
+ *                           zero where depth <= min or >= max; normal may be NULL
+ *   dqo_normal_map          compute_normal_map on an existing vertex map
+ *   dqo_icp_level           ICP.icp (SLAM/icp.py:33-48): `iterations` Gauss-Newton steps of projective point-to-plane ICP
+ *                           at one pyramid level; frame 0 is the template.  pose10 is a device float[16] (row-major 4x4),
+ *                           updated in place -- no host round trip for the 6x6 solve (icp.py:313-335 inverts on the CPU);
+ *                           valid_ratio (device float, may be NULL) = valid correspondences / (H*W) of the last iteration.
+ * ---------------------------------------------------------------------------------------------- */
+int dqo_depth_maxpool(int32_t W, int32_t H, int32_t level, const float *depth, float *out /* [H>>level, W>>level] */,
+                      void *stream);
+size_t dqo_vertex_normal_workspace_bytes(void);
+int dqo_vertex_normal_map(int32_t W, int32_t H, const float *depth, float fx, float fy, float cx, float cy,
+                          float *vertex, float *normal, void *workspace, void *stream);
+int dqo_normal_map(int32_t W, int32_t H, const float *vertex, float *normal, void *workspace, void *stream);
+size_t dqo_icp_workspace_bytes(void);
+int dqo_icp_level(int32_t W, int32_t H, const float *vertex0, const float *vertex1, const float *normal0,
+                  const float *normal1, float fx, float fy, float cx, float cy, float distance_threshold,
+                  float normal_threshold_cos, float damping, int32_t iterations, float *pose10, float *valid_ratio,
+                  void *workspace, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Mapping step (no native boundary exists in the reference: SLAM/multiprocess/mapper.py:799-928 is
  * inline PyTorch).  Masked L1 colour + depth loss and its image gradients in two launches.
  *   colour: mean |img - gt| over render_mask pixels x 3 channels          (mapper.py:847, loss_utils.py:27-31)
