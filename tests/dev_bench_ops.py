@@ -103,6 +103,23 @@ def main():
     row["torch_restatement_cpu_ms_per_object"] = (time.perf_counter() - t0) * 1e3
     out["quadric_refine_64_objects"] = row
 
+    # --- tracker front-end at 1200x680: pyramids + 3 x 5 ICP iterations (icp.py:424-441) -----------------------------
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_icp_golden import synth_depth
+    from dqo_map_b200 import icp
+    from oracle import icp_oracle as io
+    Kn = np.array([[600.0, 0, 599.5], [0, 600.0, 339.5], [0, 0, 1.0]])
+    p1 = np.eye(4)
+    p1[:3, 3] = [0.02, -0.01, 0.015]
+    d0 = torch.from_numpy(synth_depth(680, 1200, Kn, np.eye(4))).to(DEV).view(680, 1200, 1)
+    d1 = torch.from_numpy(synth_depth(680, 1200, Kn, p1)).to(DEV).view(680, 1200, 1)
+    Kt = torch.from_numpy(Kn).float().to(DEV)
+    out["tracker_predict_pose_1200x680"] = {
+        "ours_ms": timed(lambda: icp.predict_pose(d0, d1, Kt), reps=10),
+        "reference_torch_ms": timed(lambda: io.predict_pose(d0, d1, Kt.clone()), reps=5),
+        "what": "depth max-pyramid, vertex + normal maps of both frames, 3 levels x 5 Gauss-Newton iterations; the torch "
+                "figure is oracle/icp_oracle.py (the reference's op sequence, host-side 6x6 inverse included) on the same GPU"}
+
     print(json.dumps(out))
 
 

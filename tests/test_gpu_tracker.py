@@ -32,7 +32,7 @@ def test_vertex_and_normal_pyramids_match_reference():
             # cross product is numerically zero (flat depth steps) and the reference normalises noise
             got = npyr[lvl].cpu().numpy()
             both = (np.linalg.norm(n_ref, axis=-1) > 0.5) & (np.linalg.norm(got, axis=-1) > 0.5)
-            assert (np.linalg.norm(n_ref, axis=-1) > 0.5).mean() > 0.8
+            assert (np.linalg.norm(n_ref, axis=-1) > 0.5).mean() > 0.2   # the far wall sits at depth.max() and is masked
             assert np.abs((got * n_ref).sum(-1)[both] - 1.0).max() < 1e-4
             assert ((np.linalg.norm(got, axis=-1) > 0.5) != (np.linalg.norm(n_ref, axis=-1) > 0.5)).mean() < 2e-3
         # the fused depth -> (vertex, normal) entry point equals the two-step path
@@ -83,3 +83,32 @@ def test_coarse_to_fine_pose_matches_reference_and_truth():
     p2, r2 = icp.predict_pose(d0, d1, K)
     assert torch.allclose(p2, pose, atol=1e-6)
     np.testing.assert_allclose(pose.cpu().numpy(), G["true_pose10"], rtol=0, atol=2e-3)   # and it is the right answer
+
+
+def test_against_pinned_oracle_on_fresh_views():
+    """Other motion, other resolution (not a multiple of the pyramid stride): CUDA vs oracle/icp_oracle.py (pinned to the
+    reference fixtures by tests/test_icp_oracle.py)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_icp_golden import synth_depth
+    from dqo_map_b200 import icp
+    from oracle import icp_oracle as io
+    H, W = 187, 333
+    Kn = np.array([[260.0, 0, 166.0], [0, 260.0, 93.0], [0, 0, 1.0]])
+    p1 = np.eye(4)
+    a = -0.015
+    p1[:3, :3] = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    p1[:3, 3] = [-0.02, 0.015, -0.01]
+    d0, d1 = torch.from_numpy(synth_depth(H, W, Kn, np.eye(4))), torch.from_numpy(synth_depth(H, W, Kn, p1))
+    K = torch.from_numpy(Kn).float()
+    want, want_ratio = io.predict_pose(d0.view(H, W, 1), d1.view(H, W, 1), K.clone())
+    got, ratio = icp.predict_pose(d0.to(DEV).view(H, W, 1), d1.to(DEV).view(H, W, 1), K.to(DEV))
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=0, atol=5e-4)
+    assert abs(float(ratio) - float(want_ratio)) < 5e-3
+    np.testing.assert_allclose(got.cpu().numpy(), p1.astype(np.float32), rtol=0, atol=3e-3)
+    # vertex maps are bit-identical to the oracle; degenerate input is left alone
+    v_got = icp.compute_vertex_map(d0.to(DEV).view(H, W, 1), K.to(DEV))
+    assert np.array_equal(v_got.cpu().numpy(), io.compute_vertex_map(d0.view(H, W, 1), K).numpy())
+    z = torch.zeros(H, W, 3, device=DEV)
+    pose, r0 = icp.ICP(3).icp(torch.eye(4, device=DEV), z, z, z, z, K.to(DEV))
+    assert torch.equal(pose, torch.eye(4, device=DEV)) and float(r0) == 0.0
