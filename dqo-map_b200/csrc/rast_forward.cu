@@ -1469,16 +1469,48 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         return DQO_OK;
     };
 
+    // The list of non-empty tiles (rasterizer_impl.cu:348-365) is an output only -- the blend reads the ranges -- so
+    // its single-block kernel runs on the side stream beside the final blend instead of in front of it.
+    cudaEvent_t ev_cf = nullptr, ev_cj = nullptr;
+    auto compact_fork = [&](const uint2 *rb) -> int {
+        cudaStream_t cs = debug ? nullptr : side_stream();
+        if (cs && (cudaEventCreateWithFlags(&ev_cf, cudaEventDisableTiming) != cudaSuccess ||
+                   cudaEventCreateWithFlags(&ev_cj, cudaEventDisableTiming) != cudaSuccess)) {
+            if (ev_cf) cudaEventDestroy(ev_cf);
+            ev_cf = ev_cj = nullptr;
+            cs = nullptr;
+        }
+        if (cs) {
+            DQO_CUDA_CHECK(cudaEventRecord(ev_cf, stream));
+            DQO_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_cf, 0));
+        } else {
+            cs = stream;
+        }
+        compact_tiles_kernel<<<1, 1024, 0, cs>>>(T, ranges, rb, tile_indices, status);
+        DQO_LAUNCH_CHECK("compact tiles", debug, stream);
+        if (ev_cj) DQO_CUDA_CHECK(cudaEventRecord(ev_cj, cs));
+        stage_mark(stream, ST_COMPACT);
+        return DQO_OK;
+    };
+    auto compact_join = [&]() -> int {
+        if (ev_cj) {
+            DQO_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_cj, 0));
+            cudaEventDestroy(ev_cf);
+            cudaEventDestroy(ev_cj);
+        }
+        return DQO_OK;
+    };
+
     if (!two_phase) {
         if (P > 0) {
             const int rc = bin_phase(0, capacity, 0, nullptr, d_offsets, d_mask_bits, DQO_ST_NUM_RENDERED, ranges);
             if (rc) return rc;
         }
-        compact_tiles_kernel<<<1, 1024, 0, stream>>>(T, ranges, nullptr, tile_indices, status);
-        DQO_LAUNCH_CHECK("compact tiles", debug, stream);
-        stage_mark(stream, ST_COMPACT);
+        int rc = compact_fork(nullptr);
+        if (rc) return rc;
         render_forward_kernel<0><<<T, 256, 0, stream>>>(ra);
         DQO_LAUNCH_CHECK("render forward", debug, stream);
+        if ((rc = compact_join())) return rc;
         stage_mark(stream, ST_RENDER_FWD);
         return DQO_OK;
     }
@@ -1506,11 +1538,10 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     rc = bin_phase(2, back, front, tiles_b, offsets_b, mask_bits_b, DQO_ST_R_BACK, ranges_b);
     if (rc) return rc;
     stage_mark(stream, ST_BACK_BIN);
-    compact_tiles_kernel<<<1, 1024, 0, stream>>>(T, ranges, ranges_b, tile_indices, status);
-    DQO_LAUNCH_CHECK("compact tiles", debug, stream);
-    stage_mark(stream, ST_COMPACT);
+    if ((rc = compact_fork(ranges_b))) return rc;
     render_forward_kernel<2><<<T, 256, 0, stream>>>(ra);
     DQO_LAUNCH_CHECK("render forward (back)", debug, stream);
+    if ((rc = compact_join())) return rc;
     stage_mark(stream, ST_RENDER_FWD);
     return DQO_OK;
 }
