@@ -270,6 +270,17 @@ class FusedMappingStep:
                                 % (self.capacity, self.front, self.back, host[_lib.ST_NUM_RENDERED], host[_lib.ST_R_BACK]))
         return host
 
+    def resize(self, capacity, front_instances=None, back_instances=None):
+        """Re-allocates the step workspace for a larger instance capacity (after check() reported an overflow); the
+        parameters, the Adam state and the step counter are untouched, so the skipped step can simply be repeated."""
+        self.capacity = int(capacity)
+        if front_instances is not None:
+            self.front, self.back = int(front_instances), int(back_instances or 0)
+        if self.front and self.front + self.back > self.capacity:
+            raise ValueError("front + back instances exceed the capacity")
+        self._alloc()
+        self._kf_cache.clear()
+
     def mark_all_touched(self):
         """Call after writing non-zero values into `self.state` by hand (e.g. restoring a checkpoint)."""
         self.ever.fill_(1)

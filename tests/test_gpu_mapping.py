@@ -157,6 +157,14 @@ def test_fused_c_step_two_phase_binning_and_overflow_skip():
         for k in params:
             assert torch.equal(params[k], before[k]), k
             assert torch.equal(step.state[k][0], moments[k][0]) and torch.equal(step.state[k][1], moments[k][1])
+        # recover: larger back region, same workspace owner, the skipped step is repeated and equals a clean second step
+        step.resize(front + R + 1024, front, R + 1024)
+        step(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
+        step.check()
+        assert step.step == 2
+        step_1(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
+        step_1.check()
+        assert abs(float(step.loss[0]) - float(step_1.loss[0])) <= 1e-5 * max(1.0, abs(float(step_1.loss[0])))
 
 
 def test_fused_c_step_loop_quality():
