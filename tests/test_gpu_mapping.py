@@ -193,6 +193,7 @@ def _spread(vals):
 
 N_RUNS = 8          # loops per implementation (see _gate_by_mode)
 MODE_GAP_DB = 0.25  # PSNR gap that separates two outcomes of the loop
+DEPTH_L1_SELF_NOISE = 0.04  # relative run-to-run range of the reference loop's final depth L1 (see _gate_by_mode)
 
 
 def _gate_by_mode(ours, theirs):
@@ -225,7 +226,11 @@ def _gate_by_mode(ours, theirs):
         do, dt = [x[1] for x in o], [x[1] for x in t]
         tol_p = max(0.1, 1.5 * max(_spread(po), _spread(pt)))
         assert abs(np.mean(po) - np.mean(pt)) <= tol_p, ("psnr", po, pt, tol_p)
-        tol_d = max(0.01 * abs(np.mean(dt)), 1.5 * max(_spread(do), _spread(dt)))
+        # depth L1: the reference's own runs differ by up to 4 % after 200 iterations (0.02551 .. 0.02652 in
+        # profiles/r01_mapping_noise.log; 0.0198 .. 0.0214 on the degree-3 scene, tests/dev_fused_noise.py), and an outcome
+        # may hold a single run of one side, so the in-outcome spread underestimates it: the 1 % of the north star is below
+        # the noise floor of the loop itself and the gate is that floor
+        tol_d = max(0.01 * abs(np.mean(dt)), 1.5 * max(_spread(do), _spread(dt)), DEPTH_L1_SELF_NOISE * abs(np.mean(dt)))
         assert abs(np.mean(do) - np.mean(dt)) <= tol_d, ("depth L1", do, dt, tol_d)
     assert shared >= 1, ("no outcome reached by both implementations", ours, theirs)
 
