@@ -50,12 +50,6 @@ class BinningPolicy:
             return 0, 0
         return front, back
 
-    def required_capacity(self, r_hint):
-        """Instance capacity the next call needs given the last known R."""
-        if self.front > 0:
-            return self.front + self.back
-        return int(r_hint * 1.25) + 1024
-
     def update(self, status, used_front, used_back):
         """Digest the status words of a finished call that ran with (used_front, used_back).  Returns True when that
         call has to be repeated (overflow)."""

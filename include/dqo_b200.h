@@ -91,7 +91,9 @@ size_t dqo_rast_image_bytes(int32_t W, int32_t H);
  * Optional inputs are NULL when absent (the reference detects empty tensors via null data_ptr).
  * Every output image is fully written by the call (including the fill values of
  * rasterize_points.cu:79-89 for tiles that are not rendered), so callers may pass uninitialised memory.
- * `status` is device int32[DQO_ST_WORDS].  No host synchronisation is performed. */
+ * `status` is device int32[DQO_ST_WORDS].  No host synchronisation is performed.  All work is ordered on `stream`;
+ * two small stages run on an internal per-device side stream that is forked from and joined back into `stream` with events
+ * before the call returns. */
 int dqo_rast_forward(const dqo_rast_settings *s,
                      const float *background,     /* [3] */
                      const float *means3D,        /* [P,3] */
