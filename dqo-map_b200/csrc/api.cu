@@ -16,8 +16,7 @@ void set_error(const char *fmt, ...) {
 static long long g_launches = 0;
 void note_launch(int n) { g_launches += n; }
 
-// One non-blocking side stream per device for work that can overlap the caller's stream (fork / join with events;
-// capturable into a CUDA graph together with the caller's stream).
+// One non-blocking side stream per device for work that can overlap the caller's stream (fork / join with events).
 static std::mutex g_side_mu;
 static cudaStream_t g_side[64] = {};
 cudaStream_t side_stream() {

@@ -16,8 +16,8 @@
 //   * occlusion-aware two-phase binning (front_instances > 0): only a depth-rank prefix of the Gaussians is binned for
 //     every tile, the rest only for tiles that have not terminated (render_forward_kernel<1> / <2>);
 //   * the latency-bound depth sort and the tile-list compaction run on a per-device high-priority side stream, forked
-//     from and joined back into the caller's stream with events (nothing is left running when the call returns to the
-//     stream's order, and the pattern is capturable in a CUDA graph).
+//     from and joined back into the caller's stream with events (everything is ordered on the caller's stream again
+//     before the call returns).
 #include "common.cuh"
 #include <cub/cub.cuh>
 #include <math.h>
