@@ -140,3 +140,19 @@ def test_binning_policy_enters_tightens_and_leaves_two_phase():
     p2.update(_status(R=R, walked=1_200_000), 0, 0)
     f, b = p2.plan(1 << 20)
     assert (f, b) == (0, 0) or (f % 256 == 0 and f + b <= 1 << 20)
+
+
+def test_object_scene_table_is_deterministic_and_packs_evenly():
+    """The multi-object workload (bench_objects.py): every rank derives the same object table and the same owner map."""
+    from dqo_map_b200 import sharding, synthetic
+    c1, c2 = synthetic.object_counts(20), synthetic.object_counts(20)
+    assert c1 == c2 and len(c1) == 21 and c1[0] == 200_000 and all(20_000 <= c <= 80_000 for c in c1[1:])
+    for world in (1, 2, 4, 8):
+        owner, load = sharding.assign_objects(c1, world)
+        assert sorted(owner) == list(range(21)) and sum(load) == sum(c1)
+        assert sorted(o for r in range(world) for o in sharding.local_objects(owner, r)) == list(range(21))
+        # LPT: no rank exceeds the mean by more than the largest object
+        assert max(load) <= sum(c1) / world + max(c1)
+    obj = synthetic.make_object(3, 500)
+    assert obj["xyz"].shape == (500, 3) and obj["shs"].shape == (500, 16, 3) and obj["obj_id"] == 3
+    assert torch.equal(obj["xyz"], synthetic.make_object(3, 500)["xyz"])
