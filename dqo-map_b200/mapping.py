@@ -261,10 +261,20 @@ class FusedMappingStep:
                 check(lib().dqo_mapping_step(*args, _stream()), "dqo_mapping_step")
         return self._loss_views
 
-    def check(self):
+    def check(self, auto_resize=False):
+        """Reads the device status words (one host synchronisation).  On an instance overflow the device skipped the
+        update of that step; by default this raises, with auto_resize=True the workspace is re-allocated large enough for
+        what the device reported and None is returned: repeat the step."""
         host = self.status.tolist()
         if host[_lib.ST_OVERFLOW]:
             self.step -= 1  # the device skipped the update: the step did not happen
+            if auto_resize:
+                if self.front:
+                    back = int(host[_lib.ST_R_BACK] * 1.5) + 65536
+                    self.resize(self.front + back, self.front, back)
+                else:
+                    self.resize(int(host[_lib.ST_NUM_RENDERED] * 1.3) + 4096)
+                return None
             raise _lib.DqoError("instance capacity exceeded (capacity %d, front %d, back %d; R = %d, back needs %d): the "
                                 "step was skipped on the device, repeat it with larger buffers"
                                 % (self.capacity, self.front, self.back, host[_lib.ST_NUM_RENDERED], host[_lib.ST_R_BACK]))

@@ -157,10 +157,13 @@ def test_fused_c_step_two_phase_binning_and_overflow_skip():
         for k in params:
             assert torch.equal(params[k], before[k]), k
             assert torch.equal(step.state[k][0], moments[k][0]) and torch.equal(step.state[k][1], moments[k][1])
-        # recover: larger back region, same workspace owner, the skipped step is repeated and equals a clean second step
-        step.resize(front + R + 1024, front, R + 1024)
+        # recover: check(auto_resize=True) re-allocates for what the device reported; the skipped step is repeated and
+        # equals a clean second step
+        step.set_binning(front, 256)
         step(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
-        step.check()
+        assert step.check(auto_resize=True) is None and step.back >= host[_lib.ST_R_BACK]
+        step(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
+        assert step.check(auto_resize=True) is not None
         assert step.step == 2
         step_1(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
         step_1.check()
