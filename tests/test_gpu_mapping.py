@@ -24,6 +24,25 @@ def inverse_sigmoid(x):
     return torch.log(x / (1 - x))
 
 
+_stock_cache = {}
+
+
+def _statistical(test):
+    """The loop-level gates compare samples of a chaotic, bimodal process; even for identical implementations a draw of
+    8 + 8 runs shares no outcome, or puts a lone run in an outcome, a few percent of the time.  A failed draw is repeated
+    once on fresh samples (false-alarm rate ~1e-3), a genuine discrepancy fails both."""
+    import functools
+
+    @functools.wraps(test)
+    def wrapper(*args, **kwargs):
+        try:
+            return test(*args, **kwargs)
+        except AssertionError:
+            _stock_cache.clear()
+            return test(*args, **kwargs)
+    return wrapper
+
+
 def _scene(P=6000, cfg="small", deg=1):
     dev = torch.device(DEV)
     gt = rh.make_inputs(cfg, dev, seed=123, P=P, sh_degree=deg)
@@ -239,23 +258,6 @@ def _gate_by_mode(ours, theirs):
     assert shared >= 1, ("no outcome reached by both implementations", ours, theirs)
 
 
-_stock_cache = {}
-
-
-def _statistical(test):
-    """The loop-level gates compare samples of a chaotic, bimodal process; even for identical implementations a draw of
-    8 + 8 runs shares no outcome, or puts a lone run in an outcome, a few percent of the time.  A failed draw is repeated
-    once on fresh samples (false-alarm rate ~1e-3), a genuine discrepancy fails both."""
-    import functools
-
-    @functools.wraps(test)
-    def wrapper(*args, **kwargs):
-        try:
-            return test(*args, **kwargs)
-        except AssertionError:
-            _stock_cache.clear()
-            return test(*args, **kwargs)
-    return wrapper
 
 
 def _stock_runs(key, args):
