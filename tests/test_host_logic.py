@@ -156,3 +156,17 @@ def test_object_scene_table_is_deterministic_and_packs_evenly():
     obj = synthetic.make_object(3, 500)
     assert obj["xyz"].shape == (500, 3) and obj["shs"].shape == (500, 16, 3) and obj["obj_id"] == 3
     assert torch.equal(obj["xyz"], synthetic.make_object(3, 500)["xyz"])
+
+
+def test_integration_snippets_are_valid_python():
+    """The binding stubs shown in INTEGRATION.md / README.md must at least parse."""
+    import ast
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = 0
+    for doc in ("INTEGRATION.md",):
+        text = open(os.path.join(root, doc)).read()
+        for block in re.findall(r"```python\n(.*?)```", text, flags=re.S):
+            ast.parse(block)
+            n += 1
+    assert n >= 3
