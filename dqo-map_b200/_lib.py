@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdqomap_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_R_FRONT, ST_R_BACK, ST_WALKED, ST_UNFINISHED = range(8)
 ST_WORDS = 8
@@ -62,6 +62,9 @@ PROTOTYPES = {
     "dqo_mark_visible": (C.c_int, [C.c_int32, c_p, c_p, c_p, c_p, c_p]),
     "dqo_rast_export_state": (C.c_int, [C.POINTER(RastSettings), c_p, c_p, C.c_int64, c_p, c_p] + [c_p] * 10 + [c_p]),
     "dqo_rast_blend_extra": (C.c_int, [C.POINTER(RastSettings), c_p, c_p, c_p, c_p, C.c_int64, c_p, c_p, c_p, c_p]),
+    "dqo_sort_pairs_temp_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "dqo_sort_pairs_u32": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int32, c_p, c_p, C.c_int64, C.c_int32, c_p, c_p]),
+    "dqo_sort_pairs_u16": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int32, c_p, c_p, C.c_int64, C.c_int32, c_p, c_p]),
     "dqo_knn_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "dqo_knn3": (C.c_int, [C.c_int32, c_p, c_p, c_p, c_p, C.c_size_t, c_p]),
     "dqo_accumulate_error": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [c_p] * 5

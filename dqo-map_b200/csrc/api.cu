@@ -1,8 +1,18 @@
-// Error reporting and ABI bookkeeping for libdqomap_b200.so.
+// Error reporting, ABI bookkeeping and the few host-side resources of libdqomap_b200.so.
+//
+// The library keeps no state that couples independent callers:
+//   * the last-error string and the stage-profiling events are per calling thread;
+//   * the helper ("side") stream and the four fork / join events a forward pass needs are owned by the pair
+//     (device, caller's stream): two callers on different streams never share a side stream, so their forked work does
+//     not serialise, and nothing is created or destroyed on the hot path after the first call on a stream;
+//   * the launch counter is a relaxed atomic (instrumentation only).
 #include "common.cuh"
+#include <atomic>
 #include <mutex>
 #include <stdarg.h>
 #include <stdio.h>
+#include <unordered_map>
+#include <nvtx3/nvToolsExt.h>
 
 namespace dqo {
 static thread_local char g_err[512] = "";
@@ -13,29 +23,52 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-static long long g_launches = 0;
-void note_launch(int n) { g_launches += n; }
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-// One non-blocking side stream per device for work that can overlap the caller's stream (fork / join with events).
-static std::mutex g_side_mu;
-static cudaStream_t g_side[64] = {};
-cudaStream_t side_stream() {
+// NVTX ranges around the C-ABI entry points (visible in nsys / ncu --nvtx; a no-op without a tool attached)
+void nvtx_push(const char *name) { nvtxRangePushA(name); }
+void nvtx_pop() { nvtxRangePop(); }
+
+struct FjKey {
+    int dev;
+    cudaStream_t stream;
+    bool operator==(const FjKey &o) const { return dev == o.dev && stream == o.stream; }
+};
+struct FjHash {
+    size_t operator()(const FjKey &k) const { return std::hash<void *>()((void *)k.stream) * 31u + (size_t)k.dev; }
+};
+static std::mutex g_fj_mu;
+static std::unordered_map<FjKey, ForkJoin *, FjHash> g_fj;
+#define DQO_MAX_FORK_JOIN 1024
+
+ForkJoin *fork_join(cudaStream_t caller) {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lock(g_side_mu);
-    if (!g_side[dev]) {
-        // highest priority: the forked kernels are small and latency-bound, they should slip in between the blocks of
-        // the large kernel they overlap instead of queueing behind its whole grid
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (cudaStreamCreateWithPriority(&g_side[dev], cudaStreamNonBlocking, hi) != cudaSuccess) g_side[dev] = nullptr;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_fj_mu);
+    const FjKey key{dev, caller};
+    auto it = g_fj.find(key);
+    if (it != g_fj.end()) return it->second;
+    if (g_fj.size() >= DQO_MAX_FORK_JOIN) return nullptr; // callers fall back to their own stream (no overlap)
+    ForkJoin *fj = new ForkJoin();
+    // highest priority: the forked kernels are small and latency-bound, they should slip in between the blocks of the
+    // large kernel they overlap instead of queueing behind its whole grid
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    bool ok = cudaStreamCreateWithPriority(&fj->side, cudaStreamNonBlocking, hi) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreateWithFlags(&fj->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        delete fj; // leaks at most a stream / a few events on a failing device; the caller runs unforked
+        return nullptr;
     }
-    return g_side[dev];
+    g_fj[key] = fj;
+    return fj;
 }
 
-static int g_profile = 0;
-static cudaEvent_t g_ev[ST_COUNT];
-static bool g_ev_made = false, g_ev_set[ST_COUNT];
+static thread_local int g_profile = 0;
+static thread_local cudaEvent_t g_ev[ST_COUNT];
+static thread_local bool g_ev_made = false, g_ev_set[ST_COUNT];
 void stage_mark(cudaStream_t stream, int stage) {
     if (!g_profile) return;
     if (!g_ev_made) {
@@ -47,7 +80,7 @@ void stage_mark(cudaStream_t stream, int stage) {
 }
 } // namespace dqo
 
-extern "C" long long dqo_launch_count(void) { return dqo::g_launches; }
+extern "C" long long dqo_launch_count(void) { return dqo::g_launches.load(std::memory_order_relaxed); }
 extern "C" void dqo_profile_enable(int on) {
     dqo::g_profile = on;
     for (int i = 0; i < dqo::ST_COUNT; i++) dqo::g_ev_set[i] = false;

@@ -13,14 +13,22 @@
 
 #define DQO_TILE 16
 #define DQO_TILE_PIX 256
-#define DQO_ABI_VERSION 8
+#define DQO_ABI_VERSION 9
 
 namespace dqo {
 
 void set_error(const char *fmt, ...);
 void note_launch(int n = 1);                      // counts this library's own kernel launches (dqo_launch_count)
-void stage_mark(cudaStream_t stream, int stage);  // records a CUDA event when stage profiling is enabled
-cudaStream_t side_stream(); // per-device non-blocking helper stream (nullptr if unavailable)
+void stage_mark(cudaStream_t stream, int stage);  // records a CUDA event when stage profiling is enabled (per thread)
+void nvtx_push(const char *name);                 // NVTX range around a C-ABI entry point
+void nvtx_pop();
+// Helper stream + fork / join events owned by (current device, caller's stream); created on the first call on that
+// stream, then reused: no stream / event creation on the hot path, no sharing between callers on different streams.
+struct ForkJoin {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+ForkJoin *fork_join(cudaStream_t caller); // nullptr: run unforked on the caller's stream
 
 // stage ids of dqo_profile_read()
 enum {
@@ -158,27 +166,27 @@ __host__ __device__ inline uint32_t higher_msb(uint32_t n) { // rasterizer_impl.
 struct GeomLayout {
     size_t rec;        // float4[3P]: {x,y,conic.x,conic.y} {conic.z,opacity,power_reject,extent.y} {r,g,b,extent.x}
     size_t depth;      // f32[P] view-space depth (forward.cu:339)
-    size_t depth_key;  // u32[P] float bits of view depth, 0xFFFFFFFF when the Gaussian emits no instance
-    size_t depth_key2; // u32[P] sorted keys (scratch)
-    size_t ids;        // u32[P] iota
+    size_t depth_key;  // u32[P] float bits of view depth, 0xFFFFFFFF when the Gaussian is outside the frustum
+    size_t depth_key2; // u32[P] sort ping-pong buffer
+    size_t ids;        // u32[P] sort ping-pong buffer (values)
     size_t order;      // u32[P] Gaussian ids in (depth, id) order
     size_t tiles;      // u32[P] tiles_touched
     size_t offsets;    // u32[P] inclusive scan of tiles_touched in depth-rank order
     size_t rect;       // uint2[P] {min.x | max.x<<16, min.y | max.y<<16}
     size_t clamped;    // u8[P] bit c = colour channel c clamped (forward.cu:151-153)
     size_t gacc;       // f32[16P] gradient accumulators of the backward blend (see DQO_GACC_FLOATS)
-    size_t tiles_b;    // u32[P] two-phase: tiles touched among the unfinished tiles, in depth-rank order
-    size_t offsets_b;  // u32[P] two-phase: inclusive scan of tiles_b
-    size_t cub;        // CUB temp storage
-    size_t cub_bytes;
+    size_t lb;         // u64[2][emit_blocks] look-back words of the two emission kernels + 2 tickets (sort.cuh)
+    size_t lb_bytes;
+    int emit_blocks;
+    size_t sort_temp;  // histograms / look-back words of the depth sort (sort.cuh: SortTemp)
     size_t total;
 };
-// binning buffer: instance lists
+// binning buffer: instance lists.  The radix sort ping-pongs between the (a) and (b) arrays; where the sorted list ends
+// up depends only on the number of digit passes, i.e. on the tile count of the image (bin_sorted_in_a).
 struct BinLayout {
-    size_t keys_in, keys_out; // tile id per instance (unsorted / sorted): u16[C] when the image has < 65535 tiles, else u32[C]
-    size_t vals_in, vals_out; // u32[C] Gaussian id per instance; vals_out == reference point_list
-    size_t cub;
-    size_t cub_bytes;
+    size_t keys_a, keys_b; // tile id per instance: u16[C] when the image has < 65535 tiles, else u32[C]
+    size_t vals_a, vals_b; // u32[C] Gaussian id per instance; the sorted one == reference point_list
+    size_t sort_temp;
     size_t total;
 };
 // image buffer: per-tile ranges and tile-major per-pixel state for the backward pass
@@ -247,6 +255,16 @@ __device__ __forceinline__ unsigned subblock_mask(float mx, float my, float A, f
 int make_geom_layout(int P, GeomLayout *L);
 int make_bin_layout(int64_t C, BinLayout *L);
 void make_img_layout(int W, int H, ImgLayout *L);
+
+// number of key bits the tile sort looks at for an image of T tiles (rasterizer_impl.cu:327: getHigherMsb(tiles))
+inline int tile_sort_bits(int T) {
+    const int bit = (int)higher_msb((uint32_t)T);
+    return (T < 65535) ? (bit < 16 ? bit : 16) : bit;
+}
+// true: after the tile sort the sorted keys / point list live in keys_a / vals_a, false: in keys_b / vals_b
+inline bool bin_sorted_in_a(int T) { return ((tile_sort_bits(T) < 1 ? 1 : tile_sort_bits(T)) + 7) / 8 % 2 == 0; }
+inline size_t bin_point_list(const BinLayout &BL, int T) { return bin_sorted_in_a(T) ? BL.vals_a : BL.vals_b; }
+inline size_t bin_sorted_keys(const BinLayout &BL, int T) { return bin_sorted_in_a(T) ? BL.keys_a : BL.keys_b; }
 
 // per-Gaussian gradient accumulator written by the backward blend (16 floats = 64 B)
 // {dmean2D.x, dmean2D.y, dconic.x, dconic.y | dconic.w, dopacity, dcolor.r, dcolor.g | dcolor.b, dmean3D.xyz | drot.rxyz}

@@ -14,7 +14,7 @@
 // Candidates are visited in the reference order (box ascending, sorted position ascending) with the same
 // strict '>' insertion, so ties resolve identically.
 #include "common.cuh"
-#include <cub/cub.cuh>
+#include "sort.cuh"
 #include <float.h>
 #include <limits.h>
 
@@ -29,7 +29,7 @@ struct KnnLayout {
     size_t sp;        // float4[P] sorted points (w = original index bits)
     size_t boxes;     // float[6] per 1024-box
     size_t subboxes;  // float[6] per 32-sub-box
-    size_t cub, cub_bytes, total;
+    size_t sort_temp, total;
 };
 
 static size_t kbump(size_t &cur, size_t bytes) {
@@ -48,15 +48,9 @@ static int make_knn_layout(int P, KnnLayout *L) {
     L->sp = kbump(cur, n * 16);
     L->boxes = kbump(cur, ((n + KNN_BOX - 1) / KNN_BOX) * 24);
     L->subboxes = kbump(cur, ((n + KNN_SUB - 1) / KNN_SUB) * 24);
-    size_t sort_bytes = 0;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 32);
-    if (e != cudaSuccess) {
-        set_error("cub sort size query failed: %s", cudaGetErrorString(e));
-        return (int)e;
-    }
-    L->cub_bytes = sort_bytes;
-    L->cub = kbump(cur, sort_bytes);
+    SortTemp T;
+    make_sort_temp((int64_t)n, 30, &T);
+    L->sort_temp = kbump(cur, T.total);
     L->total = align_up(cur, 256);
     return 0;
 }
@@ -108,7 +102,7 @@ __device__ __forceinline__ uint32_t prep_morton(uint32_t x) { // simple_knn.cu:4
 }
 
 __global__ void __launch_bounds__(256)
-    knn_morton_kernel(int P, const float *__restrict__ pts, const uint32_t *__restrict__ mm, uint32_t *codes, uint32_t *ids) {
+    knn_morton_kernel(int P, const float *__restrict__ pts, const uint32_t *__restrict__ mm, uint32_t *codes) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     uint32_t m[3];
@@ -119,7 +113,6 @@ __global__ void __launch_bounds__(256)
         m[c] = prep_morton((uint32_t)t);
     }
     codes[i] = m[0] | (m[1] << 1) | (m[2] << 2);
-    ids[i] = (uint32_t)i;
 }
 
 __global__ void __launch_bounds__(256)
@@ -298,11 +291,16 @@ extern "C" int dqo_knn3(int32_t P, const float *points, float *mean_dist2, int32
     const int nb256 = (P + 255) / 256;
     knn_init_kernel<<<1, 32, 0, stream>>>(mm);
     knn_minmax_kernel<<<min(nb256, 148 * 8), 256, 0, stream>>>(P, points, mm);
-    knn_morton_kernel<<<nb256, 256, 0, stream>>>(P, points, mm, codes, ids);
+    knn_morton_kernel<<<nb256, 256, 0, stream>>>(P, points, mm, codes);
     DQO_LAUNCH_CHECK("knn morton", 0, stream);
-    size_t cub_bytes = L.cub_bytes;
-    DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, (const uint32_t *)codes, codes_sorted,
-                                                   (const uint32_t *)ids, ids_sorted, P, 0, 32, stream));
+    // stable sort of the 30-bit Morton codes (cub::DeviceRadixSort::SortPairs in the reference, simple_knn.cu:241-244; equal codes
+    // keep index order either way).  4 digit passes: the sorted ids end up in the (a) value buffer = ids_sorted; the
+    // values are implicit (value = index), `ids` is only the ping-pong scratch.
+    {
+        const int rc = radix_sort_pairs<uint32_t>(codes, codes_sorted, ids_sorted, ids, true, nullptr, nullptr, P, 30,
+                                                  ws + L.sort_temp, stream);
+        if (rc) return rc;
+    }
     knn_gather_kernel<<<nb256, 256, 0, stream>>>(P, points, ids_sorted, sp);
     const int nboxes = (P + KNN_BOX - 1) / KNN_BOX;
     knn_boxes_kernel<<<nboxes, KNN_BOX, 0, stream>>>(P, sp, boxes, subboxes);

@@ -798,7 +798,7 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     ra.fx = focal_x; ra.fy = focal_y; ra.cx = s->cx; ra.cy = s->cy;
     ra.depth_thr = s->depth_threshold; ra.normal_thr = s->normal_threshold;
     ra.ranges = (const uint2 *)(img + IL.ranges);
-    ra.point_list = (const uint32_t *)(bin + BL.vals_out);
+    ra.point_list = (const uint32_t *)(bin + bin_point_list(BL, IL.T));
     const bool two_phase = s->front_instances > 0;
     ra.ranges_b = two_phase ? (const uint2 *)(img + IL.ranges_b) : nullptr;
     ra.point_list_b = two_phase ? ra.point_list + s->front_instances : nullptr;

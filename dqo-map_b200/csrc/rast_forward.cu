@@ -19,46 +19,22 @@
 //     from and joined back into the caller's stream with events (everything is ordered on the caller's stream again
 //     before the call returns).
 #include "common.cuh"
-#include <cub/cub.cuh>
+#include "sort.cuh"
 #include <math.h>
+#include <stdio.h>
 
 namespace dqo {
 
 // ------------------------------------------------------------------------------------------------
 // layouts
 // ------------------------------------------------------------------------------------------------
-struct GatherTiles {
-    const uint32_t *tiles;
-    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t &id) const { return tiles[id]; }
-};
-typedef cub::TransformInputIterator<uint32_t, GatherTiles, const uint32_t *> TilesInRankOrder;
-
 static size_t bump(size_t &cur, size_t bytes) {
     size_t off = align_up(cur, 256);
     cur = off + bytes;
     return off;
 }
 
-int make_geom_layout_uncached(int P, GeomLayout *L);
-int make_bin_layout_uncached(int64_t C, BinLayout *L);
-// The layouts depend on CUB's temp-storage size queries, which cost several microseconds of host time each; the
-// forward, the backward and the fused step all ask for the same few sizes over and over, so the last result is kept
-// per thread.
 int make_geom_layout(int P, GeomLayout *L) {
-    static thread_local int last_P = -1;
-    static thread_local GeomLayout last_L;
-    if (P == last_P) {
-        *L = last_L;
-        return 0;
-    }
-    const int rc = make_geom_layout_uncached(P, L);
-    if (rc == 0) {
-        last_P = P;
-        last_L = *L;
-    }
-    return rc;
-}
-int make_geom_layout_uncached(int P, GeomLayout *L) {
     size_t cur = 0;
     size_t n = (size_t)(P > 0 ? P : 1);
     L->rec = bump(cur, n * 48);
@@ -72,61 +48,27 @@ int make_geom_layout_uncached(int P, GeomLayout *L) {
     L->rect = bump(cur, n * 8);
     L->clamped = bump(cur, n);
     L->gacc = bump(cur, n * DQO_GACC_FLOATS * 4);
-    L->tiles_b = bump(cur, n * 4);
-    L->offsets_b = bump(cur, n * 4);
-    size_t sort_bytes = 0, scan_bytes = 0;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 32);
-    if (e != cudaSuccess) {
-        set_error("cub sort size query failed: %s", cudaGetErrorString(e));
-        return (int)e;
-    }
-    TilesInRankOrder it((const uint32_t *)nullptr, GatherTiles{nullptr});
-    e = cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, it, (uint32_t *)nullptr, (int)n);
-    if (e != cudaSuccess) {
-        set_error("cub scan size query failed: %s", cudaGetErrorString(e));
-        return (int)e;
-    }
-    L->cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
-    L->cub = bump(cur, L->cub_bytes);
+    // look-back words + tickets of the two emission kernels (front / single phase, back phase): cleared together
+    L->emit_blocks = (int)((n + 255) / 256);
+    L->lb = bump(cur, (size_t)2 * L->emit_blocks * 8 + 256);
+    L->lb_bytes = (size_t)2 * L->emit_blocks * 8 + 256;
+    SortTemp T;
+    make_sort_temp((int64_t)n, 32, &T);
+    L->sort_temp = bump(cur, T.total);
     L->total = align_up(cur, 256);
     return 0;
 }
 
 int make_bin_layout(int64_t C, BinLayout *L) {
-    static thread_local int64_t last_C = -1;
-    static thread_local BinLayout last_L;
-    if (C == last_C) {
-        *L = last_L;
-        return 0;
-    }
-    const int rc = make_bin_layout_uncached(C, L);
-    if (rc == 0) {
-        last_C = C;
-        last_L = *L;
-    }
-    return rc;
-}
-int make_bin_layout_uncached(int64_t C, BinLayout *L) {
     size_t cur = 0;
     size_t n = (size_t)(C > 0 ? C : 1);
-    L->keys_in = bump(cur, n * 4);
-    L->keys_out = bump(cur, n * 4);
-    L->vals_in = bump(cur, n * 4);
-    L->vals_out = bump(cur, n * 4);
-    size_t sort_bytes = 0, sort16_bytes = 0;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 32);
-    if (e == cudaSuccess)
-        e = cub::DeviceRadixSort::SortPairs(nullptr, sort16_bytes, (const uint16_t *)nullptr, (uint16_t *)nullptr,
-                                            (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 16);
-    if (e != cudaSuccess) {
-        set_error("cub sort size query failed: %s", cudaGetErrorString(e));
-        return (int)e;
-    }
-    if (sort16_bytes > sort_bytes) sort_bytes = sort16_bytes;
-    L->cub_bytes = sort_bytes;
-    L->cub = bump(cur, sort_bytes);
+    L->keys_a = bump(cur, n * 4);
+    L->keys_b = bump(cur, n * 4);
+    L->vals_a = bump(cur, n * 4);
+    L->vals_b = bump(cur, n * 4);
+    SortTemp T;
+    make_sort_temp((int64_t)n, 32, &T);
+    L->sort_temp = bump(cur, T.total);
     L->total = align_up(cur, 256);
     return 0;
 }
@@ -278,13 +220,12 @@ __device__ __forceinline__ bool frustum_test(float px, float py, float pz, const
 // relative order of the emitting ones -- all that matters -- is unchanged.)  Being independent of the rest of the
 // preprocess, the depth sort runs on a side stream concurrently with it.
 __global__ void __launch_bounds__(256) depth_key_kernel(int P, const float *__restrict__ means, const float *__restrict__ view,
-                                                        const float *__restrict__ proj, uint32_t *depth_key, uint32_t *ids) {
+                                                        const float *__restrict__ proj, uint32_t *depth_key) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     float vz, ppx, ppy;
     const bool ok = frustum_test(means[3 * idx], means[3 * idx + 1], means[3 * idx + 2], view, proj, &vz, &ppx, &ppy);
     depth_key[idx] = ok ? __float_as_uint(vz) : 0xFFFFFFFFu;
-    ids[idx] = (uint32_t)idx;
 }
 
 // tile_mask != 0 as one bitmap row per tile row: the per-Gaussian tile count and the instance emission then cost
@@ -522,80 +463,129 @@ __global__ void mark_visible_kernel(int P, const float *__restrict__ means, cons
     present[idx] = frustum_test(means[3 * idx], means[3 * idx + 1], means[3 * idx + 2], view, proj, &vz, &ppx, &ppy) ? 1 : 0;
 }
 
-// Emits one (tile, gaussian) pair per masked tile of the rectangle (rasterizer_impl.cu:70-115), walking the
-// Gaussians in depth-rank order so that a stable sort by tile id alone reproduces the reference order.
-// One warp serves 32 consecutive ranks: the run of each Gaussian is written by all lanes together (coalesced)
-// when no tile of its rectangle is masked out, otherwise by its owner lane walking the mask bitmap.
-//   MODE 0 (single phase): every rank; threads also pad the unused tail [R, capacity) of the key buffer with the
-//          sentinel tile id; overflow when R > capacity.
+// rows of [miny, maxy) that hold any unfinished tile, as a bit mask of row word `wd`
+__device__ __forceinline__ uint32_t rows_in_range(const uint32_t *__restrict__ row_any, uint32_t wd, uint32_t miny,
+                                                  uint32_t maxy) {
+    const uint32_t lo = (wd == (miny >> 5)) ? (miny & 31) : 0;
+    const uint32_t hi = (wd == ((maxy - 1) >> 5)) ? ((maxy - 1) & 31) : 31;
+    return __ldg(&row_any[wd]) & (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi));
+}
+
+// Prefix sum of the per-Gaussian tile counts (rasterizer_impl.cu:303) and emission of one (tile, gaussian) pair per
+// masked tile of the rectangle (duplicateWithKeys, rasterizer_impl.cu:70-115) in ONE kernel, walking the Gaussians in
+// depth-rank order so that a stable sort by tile id alone reproduces the reference order.
+// A block owns 256 consecutive ranks: block-wide inclusive scan of the counts, decoupled look-back over the earlier
+// blocks' aggregates (sort.cuh), then one warp serves 32 consecutive ranks -- the run of each Gaussian is written by
+// all lanes together (coalesced) when no tile of its rectangle is masked out, otherwise by its owner lane walking the
+// mask bitmap.  R never visits the host and nothing is padded: the sort that follows reads its count from `status`.
+//   MODE 0 (single phase): every rank; writes beyond `capacity` are dropped and DQO_ST_OVERFLOW is raised by the last rank.
 //   MODE 1 (front phase):  only the ranks whose inclusive offset fits into `capacity` (= front_instances), i.e. the
-//          nearest Gaussians; R_front is reported; the key buffer was pre-filled with the sentinel.
-//   MODE 2 (back phase):   counts / offsets are the back-phase ones (rank order, tiles_rank), the bitmap holds the
-//          unfinished tiles only; overflow when R_back > capacity.
+//          nearest Gaussians; R_front is reported.  `offsets` still receives the full scan (R, and the back phase's
+//          "not binned yet" test).
+//   MODE 2 (back phase):   the count of a rank is the number of UNFINISHED tiles in its rectangle (0 for the ranks the
+//          front phase binned: offsets[rank] <= front); overflow when R_back > capacity.
 template <typename KeyT, int MODE>
 __global__ void __launch_bounds__(256)
-    duplicate_kernel(int P, int64_t capacity, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
-                     const uint32_t *__restrict__ tiles_rank, const uint32_t *__restrict__ offsets,
-                     const uint2 *__restrict__ rect, const uint32_t *__restrict__ mask_bits,
-                     const uint32_t *__restrict__ row_any, int mask_words, int grid_x, KeyT *__restrict__ keys,
-                     uint32_t *__restrict__ vals, int *status) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const uint32_t R = offsets[P - 1];
-    if (MODE == 0) {
-        const bool overflow = (int64_t)R > capacity;
-        if (i == 0) {
-            status[DQO_ST_NUM_RENDERED] = (int)R;
-            status[DQO_ST_OVERFLOW] = overflow ? 1 : 0;
-        }
-        const int64_t R_eff = overflow ? 0 : (int64_t)R;
-        if (i >= R_eff && i < capacity) keys[i] = (KeyT)~(KeyT)0;
-        if (overflow) return;
-    } else if (MODE == 1) {
-        if (i == 0) status[DQO_ST_NUM_RENDERED] = (int)R;
-    } else {
-        const bool overflow = (int64_t)R > capacity;
-        if (i == 0) {
-            status[DQO_ST_R_BACK] = (int)R;
-            if (overflow) status[DQO_ST_OVERFLOW] = 1;
-        }
-        if (overflow) return;
-    }
-    uint32_t id = 0, n = 0, off = 0;
+    emit_kernel(int P, int64_t capacity, int64_t front, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
+                uint32_t *offsets, const uint2 *__restrict__ rect, const uint32_t *__restrict__ mask_bits,
+                const uint32_t *__restrict__ row_any, int mask_words, int grid_x, KeyT *__restrict__ keys,
+                uint32_t *__restrict__ vals, unsigned long long *lb, uint32_t *ticket, int *status) {
+    __shared__ uint32_t s_n[257];
+    __shared__ uint32_t s_warp_tot[8];
+    __shared__ uint32_t s_excl, s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int tile = (int)s_tile;
+    const int64_t i = (int64_t)tile * 256 + tid;
+    uint32_t id = 0, n = 0;
     uint2 rc = make_uint2(0, 0);
     if (i < P) {
         id = order[i];
-        const uint32_t end = offsets[i];
         if (MODE == 2) {
-            n = tiles_rank[i];
+            if ((int64_t)offsets[i] > front && tiles[id]) {
+                rc = rect[id];
+                const uint32_t minx = rc.x & 0xFFFF, maxx = rc.x >> 16, miny = rc.y & 0xFFFF, maxy = rc.y >> 16;
+                for (uint32_t wd = miny >> 5; wd <= (maxy - 1) >> 5; wd++) {
+                    uint32_t rows = rows_in_range(row_any, wd, miny, maxy);
+                    while (rows) {
+                        const uint32_t y = wd * 32 + (__ffs(rows) - 1);
+                        rows &= rows - 1;
+                        n += mask_row_count(mask_bits, mask_words, y, minx, maxx);
+                    }
+                }
+            }
         } else {
             n = tiles[id];
-            if (MODE == 1) {
-                if ((int64_t)end > capacity)
-                    n = 0;
-                else if (i == P - 1 || (int64_t)offsets[i + 1] > capacity)
-                    status[DQO_ST_R_FRONT] = (int)end;
-            }
+            if (n) rc = rect[id];
         }
-        if (n) {
-            off = end - n;
-            rc = rect[id];
+    }
+    s_n[tid] = n;
+    if (MODE == 1 && tid == 255) s_n[256] = (i + 1 < P) ? tiles[order[i + 1]] : 0u;
+    // block-wide inclusive scan
+    uint32_t incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const uint32_t t = s_warp_tot[w];
+        if (w < warp) woff += t;
+        block_total += t;
+    }
+    if (warp == 0) {
+        if (lane == 0) lb_store(&lb[tile], tile == 0 ? LB_INCLUSIVE : LB_PARTIAL, block_total);
+        uint32_t excl = 0;
+        if (tile > 0) {
+            excl = lb_exclusive_prefix(lb, tile, lane);
+            if (lane == 0) lb_store(&lb[tile], LB_INCLUSIVE, excl + block_total);
+        }
+        if (lane == 0) s_excl = excl;
+    }
+    __syncthreads();
+    const uint32_t end = s_excl + woff + incl; // inclusive offset of rank i
+    uint32_t off = end - n;
+    if (i < P) {
+        if (MODE != 2) offsets[i] = end;
+        if (MODE == 0) {
+            if (i == P - 1) {
+                status[DQO_ST_NUM_RENDERED] = (int)end;
+                status[DQO_ST_OVERFLOW] = ((int64_t)end > capacity) ? 1 : 0;
+            }
+        } else if (MODE == 1) {
+            if (i == P - 1) status[DQO_ST_NUM_RENDERED] = (int)end;
+            if ((int64_t)end > capacity)
+                n = 0;
+            else if (i == P - 1 || (int64_t)end + (int64_t)s_n[tid + 1] > capacity)
+                status[DQO_ST_R_FRONT] = (int)end;
+        } else {
+            if (i == P - 1) {
+                status[DQO_ST_R_BACK] = (int)end;
+                if ((int64_t)end > capacity) status[DQO_ST_OVERFLOW] = 1;
+            }
         }
     }
     unsigned todo = __ballot_sync(0xFFFFFFFFu, n != 0);
     while (todo) {
         const int src = __ffs(todo) - 1;
         todo &= todo - 1;
-        const uint32_t s_id = __shfl_sync(0xFFFFFFFFu, id, src), s_n = __shfl_sync(0xFFFFFFFFu, n, src);
+        const uint32_t s_id = __shfl_sync(0xFFFFFFFFu, id, src), sn = __shfl_sync(0xFFFFFFFFu, n, src);
         const uint32_t s_off = __shfl_sync(0xFFFFFFFFu, off, src);
         const uint32_t rx = __shfl_sync(0xFFFFFFFFu, rc.x, src), ry = __shfl_sync(0xFFFFFFFFu, rc.y, src);
         const uint32_t minx = rx & 0xFFFF, maxx = rx >> 16, miny = ry & 0xFFFF, maxy = ry >> 16;
         const uint32_t w = maxx - minx;
-        if (s_n == w * (maxy - miny)) { // nothing masked inside the rectangle
-            for (uint32_t k = lane; k < s_n; k += 32) {
+        if (sn == w * (maxy - miny)) { // nothing masked inside the rectangle
+            for (uint32_t k = lane; k < sn; k += 32) {
                 const uint32_t dy = k / w, dx = k - dy * w;
-                keys[s_off + k] = (KeyT)((miny + dy) * grid_x + minx + dx);
-                vals[s_off + k] = s_id;
+                if ((int64_t)s_off + k < capacity) {
+                    keys[s_off + k] = (KeyT)((miny + dy) * grid_x + minx + dx);
+                    vals[s_off + k] = s_id;
+                }
             }
         } else if (lane == src) {
             uint32_t o = s_off;
@@ -609,8 +599,10 @@ __global__ void __launch_bounds__(256)
                     while (m) {
                         const uint32_t x = wd * 32 + (__ffs(m) - 1);
                         m &= m - 1;
-                        keys[o] = (KeyT)(y * grid_x + x);
-                        vals[o] = s_id;
+                        if ((int64_t)o < capacity) {
+                            keys[o] = (KeyT)(y * grid_x + x);
+                            vals[o] = s_id;
+                        }
                         o++;
                     }
                 }
@@ -640,42 +632,6 @@ __global__ void __launch_bounds__(1024)
     }
     __syncthreads();
     for (int k = threadIdx.x; k < row_words; k += blockDim.x) row_any[k] = (k < 64) ? s_any[k] : 0xFFFFFFFFu;
-}
-
-// rows of [miny, maxy) that hold any unfinished tile, as a bit mask of row word `wd`
-__device__ __forceinline__ uint32_t rows_in_range(const uint32_t *__restrict__ row_any, uint32_t wd, uint32_t miny,
-                                                  uint32_t maxy) {
-    const uint32_t lo = (wd == (miny >> 5)) ? (miny & 31) : 0;
-    const uint32_t hi = (wd == ((maxy - 1) >> 5)) ? ((maxy - 1) & 31) : 31;
-    return __ldg(&row_any[wd]) & (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi));
-}
-
-// Back phase, step 2: per rank, the number of unfinished tiles inside the rectangle of every Gaussian that the
-// front phase left out (inclusive offset beyond front_instances).
-__global__ void __launch_bounds__(256)
-    count_back_kernel(int P, int64_t front, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
-                      const uint32_t *__restrict__ offsets, const uint2 *__restrict__ rect,
-                      const uint32_t *__restrict__ mask_bits_b, const uint32_t *__restrict__ row_any, int mask_words,
-                      uint32_t *tiles_rank) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    uint32_t n = 0;
-    if ((int64_t)offsets[i] > front) {
-        const uint32_t id = order[i];
-        if (tiles[id]) {
-            const uint2 rc = rect[id];
-            const uint32_t minx = rc.x & 0xFFFF, maxx = rc.x >> 16, miny = rc.y & 0xFFFF, maxy = rc.y >> 16;
-            for (uint32_t wd = miny >> 5; wd <= (maxy - 1) >> 5; wd++) {
-                uint32_t rows = rows_in_range(row_any, wd, miny, maxy);
-                while (rows) {
-                    const uint32_t y = wd * 32 + (__ffs(rows) - 1);
-                    rows &= rows - 1;
-                    n += mask_row_count(mask_bits_b, mask_words, y, minx, maxx);
-                }
-            }
-        }
-    }
-    tiles_rank[i] = n;
 }
 
 // per-tile [start, end) in the sorted list (rasterizer_impl.cu:120-142); each thread checks 8 consecutive keys
@@ -1280,6 +1236,8 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         return DQO_ERR_INVALID_ARG;
     }
     stage_mark(stream, ST_BEGIN_FWD);
+    nvtx_push("dqo_rast_forward");
+    // ranges and ranges_b are neighbours in the image buffer's layout only by accident: clear them separately
     DQO_CUDA_CHECK(cudaMemsetAsync(ranges, 0, (size_t)T * sizeof(uint2), stream));
     DQO_CUDA_CHECK(cudaMemsetAsync(status, 0, DQO_ST_WORDS * sizeof(int), stream));
 
@@ -1295,21 +1253,27 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     if (two_phase && (front % 256 != 0 || back <= 0 || front + back > capacity)) {
         set_error("dqo_rast_forward: front_instances must be a multiple of 256 and front + back instances must fit the "
                   "instance capacity");
+        nvtx_pop();
         return DQO_ERR_INVALID_ARG;
     }
     uint2 *ranges_b = two_phase ? (uint2 *)(img + IL.ranges_b) : nullptr;
     if (two_phase) DQO_CUDA_CHECK(cudaMemsetAsync(ranges_b, 0, (size_t)T * sizeof(uint2), stream));
-    uint32_t *vals_in = nullptr, *vals_out = nullptr;
-    char *keys_in = nullptr, *keys_out = nullptr, *cub_tmp = nullptr;
-    size_t cub_tmp_bytes = 0;
-    const uint32_t *d_order = nullptr, *d_tiles = nullptr, *d_offsets = nullptr, *d_mask_bits = nullptr;
+    uint32_t *vals_a = nullptr, *vals_b = nullptr;
+    char *keys_a = nullptr, *keys_b = nullptr, *sort_temp = nullptr;
+    const uint32_t *d_order = nullptr, *d_tiles = nullptr, *d_mask_bits = nullptr;
+    uint32_t *d_offsets = nullptr;
     const uint2 *d_rect = nullptr;
+    unsigned long long *d_lb = nullptr;
+    uint32_t *d_ticket = nullptr;
+    int emit_blocks = 0;
+    ForkJoin *fj = debug ? nullptr : fork_join(stream); // side stream + events owned by (device, caller stream)
     if (P > 0) {
         if (make_geom_layout(P, &GL)) return DQO_ERR_WORKSPACE;
         if (make_bin_layout(capacity, &BL)) return DQO_ERR_WORKSPACE;
         char *geom = (char *)geom_buffer;
         char *bin = (char *)binning_buffer;
         uint32_t *mask_bits = (uint32_t *)(img + IL.mask_bits);
+        DQO_CUDA_CHECK(cudaMemsetAsync(geom + GL.lb, 0, GL.lb_bytes, stream));
         {
             const int nw = IL.tiles_y * IL.mask_words;
             mask_bits_kernel<<<(nw + 7) / 8, 256, 0, stream>>>(IL.tiles_x, IL.tiles_y, IL.mask_words, tile_mask, mask_bits);
@@ -1339,23 +1303,13 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         // fork: depth keys + the (depth, id) sort of the Gaussians (stable LSD sort on the depth bits) on the side
         // stream, concurrently with the rest of the preprocess
         uint32_t *order = (uint32_t *)(geom + GL.order);
-        depth_key_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, projmatrix, pa.depth_key, pa.ids);
+        depth_key_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, projmatrix, pa.depth_key);
         DQO_LAUNCH_CHECK("depth keys", debug, stream);
-        cudaStream_t sort_stream = debug ? nullptr : side_stream();
-        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-        if (sort_stream) {
-            if (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
-                if (ev_fork) cudaEventDestroy(ev_fork);
-                ev_fork = ev_join = nullptr;
-                sort_stream = nullptr;
-            }
-        }
-        if (sort_stream) {
-            DQO_CUDA_CHECK(cudaEventRecord(ev_fork, stream));
-            DQO_CUDA_CHECK(cudaStreamWaitEvent(sort_stream, ev_fork, 0));
-        } else {
-            sort_stream = stream;
+        cudaStream_t sort_stream = stream;
+        if (fj) {
+            DQO_CUDA_CHECK(cudaEventRecord(fj->ev[0], stream));
+            DQO_CUDA_CHECK(cudaStreamWaitEvent(fj->side, fj->ev[0], 0));
+            sort_stream = fj->side;
         }
         const bool staged = shs && !f_rest && s->M == 16 && ((uintptr_t)shs % 16 == 0);
         const int pre_blocks = (P + PRE_THREADS - 1) / PRE_THREADS;
@@ -1374,50 +1328,44 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         DQO_LAUNCH_CHECK("preprocess", debug, stream);
         stage_mark(stream, ST_PREPROCESS);
         // enqueued after the preprocess so that the big kernel starts right behind the key kernel and the small,
-        // high-priority sort kernels slip in between its blocks (enqueueing them first delayed the preprocess by the
-        // host time of six launches)
+        // high-priority sort kernels slip in between its blocks.  4 passes (even): the sorted ids end up in `order`
+        // (vals_a), values are implicit (value = index) so no iota array is read.
         {
-            size_t cub_bytes = GL.cub_bytes;
-            DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(geom + GL.cub, cub_bytes, (const uint32_t *)pa.depth_key,
-                                                           (uint32_t *)(geom + GL.depth_key2), (const uint32_t *)pa.ids,
-                                                           order, P, 0, 32, sort_stream));
-            DQO_LAUNCH_CHECK("depth sort", debug, stream);
-            if (ev_join) DQO_CUDA_CHECK(cudaEventRecord(ev_join, sort_stream));
+            const int rc = radix_sort_pairs<uint32_t>(pa.depth_key, (uint32_t *)(geom + GL.depth_key2), order, pa.ids, true,
+                                                      nullptr, nullptr, P, 32, geom + GL.sort_temp, sort_stream);
+            if (rc) return rc;
+            if (debug) DQO_CUDA_CHECK(cudaStreamSynchronize(sort_stream));
         }
-
-        // join
-        if (ev_join) {
-            DQO_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0));
-            cudaEventDestroy(ev_fork);
-            cudaEventDestroy(ev_join);
+        if (fj) { // join
+            DQO_CUDA_CHECK(cudaEventRecord(fj->ev[1], fj->side));
+            DQO_CUDA_CHECK(cudaStreamWaitEvent(stream, fj->ev[1], 0));
         }
         stage_mark(stream, ST_DEPTH_SORT);
-        size_t cub_bytes = GL.cub_bytes;
-        uint32_t *offsets = (uint32_t *)(geom + GL.offsets);
-        TilesInRankOrder it((const uint32_t *)order, GatherTiles{pa.tiles});
-        DQO_CUDA_CHECK(cub::DeviceScan::InclusiveSum(geom + GL.cub, cub_bytes, it, offsets, P, stream));
-        DQO_LAUNCH_CHECK("scan", debug, stream);
-        stage_mark(stream, ST_SCAN);
 
-        vals_in = (uint32_t *)(bin + BL.vals_in);
-        vals_out = (uint32_t *)(bin + BL.vals_out);
-        keys_in = bin + BL.keys_in;
-        keys_out = bin + BL.keys_out;
-        cub_tmp = bin + BL.cub;
-        cub_tmp_bytes = BL.cub_bytes;
+        vals_a = (uint32_t *)(bin + BL.vals_a);
+        vals_b = (uint32_t *)(bin + BL.vals_b);
+        keys_a = bin + BL.keys_a;
+        keys_b = bin + BL.keys_b;
+        sort_temp = bin + BL.sort_temp;
         d_order = order;
         d_tiles = pa.tiles;
-        d_offsets = offsets;
+        d_offsets = (uint32_t *)(geom + GL.offsets);
         d_rect = pa.rect;
         d_mask_bits = mask_bits;
+        d_lb = (unsigned long long *)(geom + GL.lb);
+        emit_blocks = GL.emit_blocks;
+        d_ticket = (uint32_t *)(geom + GL.lb + (size_t)2 * emit_blocks * 8);
     }
 
+    const int sort_bits = tile_sort_bits(T);
+    const bool in_a = bin_sorted_in_a(T);
+    uint32_t *point_list = in_a ? vals_a : vals_b;
     RenderArgs ra;
     ra.W = s->W; ra.H = s->H; ra.grid_x = IL.tiles_x;
     ra.fx = focal_x; ra.fy = focal_y; ra.cx = s->cx; ra.cy = s->cy; ra.scale_mod = s->scale_modifier;
     ra.opaque_thr = s->opaque_threshold; ra.depth_thr = s->depth_threshold; ra.normal_thr = s->normal_threshold;
     ra.T_thr = s->T_threshold;
-    ra.ranges = ranges; ra.point_list = vals_out; ra.rec = rec; ra.depth = depth;
+    ra.ranges = ranges; ra.point_list = point_list; ra.rec = rec; ra.depth = depth;
     ra.view = viewmatrix; ra.means3D = means3D; ra.scales = scales; ra.rotations = rotations; ra.bg = background;
     ra.n_contrib = (uint32_t *)(img + IL.n_contrib);
     ra.final_T = (float *)(img + IL.final_T);
@@ -1426,49 +1374,48 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     ra.out_color = out_color; ra.out_depth = out_depth; ra.out_hit_cw = out_hit_color_weight;
     ra.out_hit_dw = out_hit_depth_weight; ra.out_T = out_T; ra.out_hit_depth = out_hit_depth;
     ra.out_hit_color = out_hit_color; ra.n_touched = s->need_n_touched ? n_touched : nullptr;
-    ra.ranges_b = ranges_b; ra.point_list_b = vals_out ? vals_out + front : nullptr;
+    ra.ranges_b = ranges_b; ra.point_list_b = point_list ? point_list + front : nullptr;
     ra.unfinished = (int *)(img + IL.unfinished);
     ra.state = (float *)(img + IL.state);
     ra.status = status;
 
     const uint32_t *row_any_b = (const uint32_t *)(img + IL.row_any_b);
-    const int bit = (int)higher_msb((uint32_t)T);
-    const int sort_bits = keys16 ? (bit < 16 ? bit : 16) : bit;
     const size_t ksz = keys16 ? 2 : 4;
-    // one binning phase: duplicate -> stable sort by tile id -> ranges.  `n` = sort size (host constant).
-    auto bin_phase = [&](int mode, int64_t n, int64_t at, const uint32_t *tiles_rank, const uint32_t *offs,
-                         const uint32_t *bits, int count_word, uint2 *out_ranges) -> int {
-        void *kin = keys_in + at * ksz, *kout = keys_out + at * ksz;
-        uint32_t *vin = vals_in + at, *vout = vals_out + at;
-        const int64_t nthreads = (mode == 0 && n > P) ? n : P;
-        const unsigned blocks = (unsigned)((nthreads + 255) / 256);
-        if (mode != 0) DQO_CUDA_CHECK(cudaMemsetAsync(kin, 0xFF, (size_t)n * ksz, stream));
-#define DQO_DUP(KT, MODE)                                                                                              \
-    duplicate_kernel<KT, MODE><<<blocks, 256, 0, stream>>>(P, n, d_order, d_tiles, tiles_rank, offs, d_rect, bits,     \
-                                                           row_any_b, IL.mask_words, IL.tiles_x, (KT *)kin, vin, status)
+    // one binning phase: scan + emit -> stable sort by tile id (count read on the device) -> ranges.
+    // `n` = slots of this phase's region, which starts at instance `at` of the binning arrays.
+    auto bin_phase = [&](int mode, int64_t n, int64_t at, const uint32_t *bits, int count_word, uint2 *out_ranges) -> int {
+        void *ka = keys_a + at * ksz, *kb = keys_b + at * ksz;
+        uint32_t *va = vals_a + at, *vb = vals_b + at;
+        unsigned long long *lb = d_lb + (mode == 2 ? emit_blocks : 0);
+        uint32_t *ticket = d_ticket + (mode == 2 ? 1 : 0);
+#define DQO_EMIT(KT, MODE)                                                                                             \
+    emit_kernel<KT, MODE><<<emit_blocks, 256, 0, stream>>>(P, n, front, d_order, d_tiles, d_offsets, d_rect, bits,     \
+                                                          row_any_b, IL.mask_words, IL.tiles_x, (KT *)ka, va, lb,      \
+                                                          ticket, status)
         if (keys16) {
-            if (mode == 0) DQO_DUP(uint16_t, 0); else if (mode == 1) DQO_DUP(uint16_t, 1); else DQO_DUP(uint16_t, 2);
+            if (mode == 0) DQO_EMIT(uint16_t, 0); else if (mode == 1) DQO_EMIT(uint16_t, 1); else DQO_EMIT(uint16_t, 2);
         } else {
-            if (mode == 0) DQO_DUP(uint32_t, 0); else if (mode == 1) DQO_DUP(uint32_t, 1); else DQO_DUP(uint32_t, 2);
+            if (mode == 0) DQO_EMIT(uint32_t, 0); else if (mode == 1) DQO_EMIT(uint32_t, 1); else DQO_EMIT(uint32_t, 2);
         }
-#undef DQO_DUP
-        DQO_LAUNCH_CHECK("duplicate", debug, stream);
+#undef DQO_EMIT
+        DQO_LAUNCH_CHECK("scan + emit", debug, stream);
         if (mode != 2) stage_mark(stream, ST_DUPLICATE);
-        size_t tmp = cub_tmp_bytes;
-        if (keys16) {
-            DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, (const uint16_t *)kin, (uint16_t *)kout,
-                                                           (const uint32_t *)vin, vout, (int)n, 0, sort_bits, stream));
-        } else {
-            DQO_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, (const uint32_t *)kin, (uint32_t *)kout,
-                                                           (const uint32_t *)vin, vout, (int)n, 0, sort_bits, stream));
-        }
-        DQO_LAUNCH_CHECK("tile sort", debug, stream);
+        int rc;
+        if (keys16)
+            rc = radix_sort_pairs<uint16_t>((uint16_t *)ka, (uint16_t *)kb, va, vb, false, status + count_word,
+                                            status + DQO_ST_OVERFLOW, n, sort_bits, sort_temp, stream);
+        else
+            rc = radix_sort_pairs<uint32_t>((uint32_t *)ka, (uint32_t *)kb, va, vb, false, status + count_word,
+                                            status + DQO_ST_OVERFLOW, n, sort_bits, sort_temp, stream);
+        if (rc) return rc;
+        if (debug) DQO_CUDA_CHECK(cudaStreamSynchronize(stream));
         if (mode != 2) stage_mark(stream, ST_TILE_SORT);
+        const void *ks = in_a ? ka : kb;
         const unsigned rb = (unsigned)((n + 2047) / 2048);
         if (keys16)
-            tile_ranges_kernel<uint16_t><<<rb, 256, 0, stream>>>(n, (const uint16_t *)kout, status, count_word, out_ranges);
+            tile_ranges_kernel<uint16_t><<<rb, 256, 0, stream>>>(n, (const uint16_t *)ks, status, count_word, out_ranges);
         else
-            tile_ranges_kernel<uint32_t><<<rb, 256, 0, stream>>>(n, (const uint32_t *)kout, status, count_word, out_ranges);
+            tile_ranges_kernel<uint32_t><<<rb, 256, 0, stream>>>(n, (const uint32_t *)ks, status, count_word, out_ranges);
         DQO_LAUNCH_CHECK("tile ranges", debug, stream);
         if (mode != 2) stage_mark(stream, ST_RANGES);
         return DQO_OK;
@@ -1476,39 +1423,27 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
 
     // The list of non-empty tiles (rasterizer_impl.cu:348-365) is an output only -- the blend reads the ranges -- so
     // its single-block kernel runs on the side stream beside the final blend instead of in front of it.
-    cudaEvent_t ev_cf = nullptr, ev_cj = nullptr;
     auto compact_fork = [&](const uint2 *rb) -> int {
-        cudaStream_t cs = debug ? nullptr : side_stream();
-        if (cs && (cudaEventCreateWithFlags(&ev_cf, cudaEventDisableTiming) != cudaSuccess ||
-                   cudaEventCreateWithFlags(&ev_cj, cudaEventDisableTiming) != cudaSuccess)) {
-            if (ev_cf) cudaEventDestroy(ev_cf);
-            ev_cf = ev_cj = nullptr;
-            cs = nullptr;
-        }
-        if (cs) {
-            DQO_CUDA_CHECK(cudaEventRecord(ev_cf, stream));
-            DQO_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_cf, 0));
-        } else {
-            cs = stream;
+        cudaStream_t cs = stream;
+        if (fj) {
+            DQO_CUDA_CHECK(cudaEventRecord(fj->ev[2], stream));
+            DQO_CUDA_CHECK(cudaStreamWaitEvent(fj->side, fj->ev[2], 0));
+            cs = fj->side;
         }
         compact_tiles_kernel<<<1, 1024, 0, cs>>>(T, ranges, rb, tile_indices, status);
         DQO_LAUNCH_CHECK("compact tiles", debug, stream);
-        if (ev_cj) DQO_CUDA_CHECK(cudaEventRecord(ev_cj, cs));
+        if (fj) DQO_CUDA_CHECK(cudaEventRecord(fj->ev[3], cs));
         stage_mark(stream, ST_COMPACT);
         return DQO_OK;
     };
     auto compact_join = [&]() -> int {
-        if (ev_cj) {
-            DQO_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_cj, 0));
-            cudaEventDestroy(ev_cf);
-            cudaEventDestroy(ev_cj);
-        }
+        if (fj) DQO_CUDA_CHECK(cudaStreamWaitEvent(stream, fj->ev[3], 0));
         return DQO_OK;
     };
 
     if (!two_phase) {
         if (P > 0) {
-            const int rc = bin_phase(0, capacity, 0, nullptr, d_offsets, d_mask_bits, DQO_ST_NUM_RENDERED, ranges);
+            const int rc = bin_phase(0, capacity, 0, d_mask_bits, DQO_ST_NUM_RENDERED, ranges);
             if (rc) return rc;
         }
         int rc = compact_fork(nullptr);
@@ -1517,30 +1452,21 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         DQO_LAUNCH_CHECK("render forward", debug, stream);
         if ((rc = compact_join())) return rc;
         stage_mark(stream, ST_RENDER_FWD);
+        nvtx_pop();
         return DQO_OK;
     }
 
     // two-phase: nearest Gaussians first, the rest only into the tiles that are still unfinished
-    char *geom = (char *)geom_buffer;
-    uint32_t *tiles_b = (uint32_t *)(geom + GL.tiles_b), *offsets_b = (uint32_t *)(geom + GL.offsets_b);
     uint32_t *mask_bits_b = (uint32_t *)(img + IL.mask_bits_b);
-    int rc = bin_phase(1, front, 0, nullptr, d_offsets, d_mask_bits, DQO_ST_R_FRONT, ranges);
+    int rc = bin_phase(1, front, 0, d_mask_bits, DQO_ST_R_FRONT, ranges);
     if (rc) return rc;
     render_forward_kernel<1><<<T, 256, 0, stream>>>(ra);
     DQO_LAUNCH_CHECK("render forward (front)", debug, stream);
     stage_mark(stream, ST_RENDER_FRONT);
-    {
-        mask_unfinished_kernel<<<1, 1024, 0, stream>>>(IL.tiles_x, IL.tiles_y, IL.mask_words, d_mask_bits, ra.unfinished,
-                                                       mask_bits_b, (uint32_t *)(img + IL.row_any_b));
-        DQO_LAUNCH_CHECK("unfinished mask", debug, stream);
-        count_back_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, front, d_order, d_tiles, d_offsets, d_rect, mask_bits_b,
-                                                               row_any_b, IL.mask_words, tiles_b);
-        DQO_LAUNCH_CHECK("back count", debug, stream);
-        size_t tmp = GL.cub_bytes;
-        DQO_CUDA_CHECK(cub::DeviceScan::InclusiveSum(geom + GL.cub, tmp, (const uint32_t *)tiles_b, offsets_b, P, stream));
-        DQO_LAUNCH_CHECK("back scan", debug, stream);
-    }
-    rc = bin_phase(2, back, front, tiles_b, offsets_b, mask_bits_b, DQO_ST_R_BACK, ranges_b);
+    mask_unfinished_kernel<<<1, 1024, 0, stream>>>(IL.tiles_x, IL.tiles_y, IL.mask_words, d_mask_bits, ra.unfinished,
+                                                   mask_bits_b, (uint32_t *)(img + IL.row_any_b));
+    DQO_LAUNCH_CHECK("unfinished mask", debug, stream);
+    rc = bin_phase(2, back, front, mask_bits_b, DQO_ST_R_BACK, ranges_b);
     if (rc) return rc;
     stage_mark(stream, ST_BACK_BIN);
     if ((rc = compact_fork(ranges_b))) return rc;
@@ -1548,6 +1474,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     DQO_LAUNCH_CHECK("render forward (back)", debug, stream);
     if ((rc = compact_join())) return rc;
     stage_mark(stream, ST_RENDER_FWD);
+    nvtx_pop();
     return DQO_OK;
 }
 
@@ -1572,7 +1499,7 @@ extern "C" int dqo_rast_blend_extra(const dqo_rast_settings *s, const float *bac
         BinLayout BL;
         if (make_geom_layout(s->P, &GL) || make_bin_layout(capacity, &BL)) return DQO_ERR_WORKSPACE;
         a.rec = (const float4 *)((const char *)geom_buffer + GL.rec);
-        a.point_list = (const uint32_t *)((const char *)binning_buffer + BL.vals_out);
+        a.point_list = (const uint32_t *)((const char *)binning_buffer + bin_point_list(BL, IL.T));
         if (s->front_instances > 0) {
             a.ranges_b = (const uint2 *)(img + IL.ranges_b);
             a.point_list_b = a.point_list + s->front_instances;
@@ -1617,11 +1544,11 @@ extern "C" int dqo_rast_export_state(const dqo_rast_settings *s, const void *geo
             const unsigned nb = (unsigned)((capacity + 255) / 256);
             if (IL.T < 65535)
                 export_instances_kernel<uint16_t><<<nb, 256, 0, stream>>>(
-                    capacity, status, (const uint16_t *)(bin + BL.keys_out), (const uint32_t *)(bin + BL.vals_out),
+                    capacity, status, (const uint16_t *)(bin + bin_sorted_keys(BL, IL.T)), (const uint32_t *)(bin + bin_point_list(BL, IL.T)),
                     (const float *)(geom + GL.depth), sorted_keys, point_list);
             else
                 export_instances_kernel<uint32_t><<<nb, 256, 0, stream>>>(
-                    capacity, status, (const uint32_t *)(bin + BL.keys_out), (const uint32_t *)(bin + BL.vals_out),
+                    capacity, status, (const uint32_t *)(bin + bin_sorted_keys(BL, IL.T)), (const uint32_t *)(bin + bin_point_list(BL, IL.T)),
                     (const float *)(geom + GL.depth), sorted_keys, point_list);
         }
         if (means2D || depths || conic_opacity || rgb || tiles_touched) {

@@ -1,0 +1,91 @@
+// Hand-written stable LSD radix sort ("onesweep": one histogram kernel + one fused rank / look-back / scatter kernel per
+// 8-bit digit) and a single-pass decoupled look-back prefix sum for sm_100a.
+//
+// Replaces the library sorts / scans of the reference's binning (cub::DeviceRadixSort::SortPairs,
+// RAST/cuda_rasterizer/rasterizer_impl.cu:327-336; cub::DeviceScan::InclusiveSum, :303; simple_knn.cu:237) on the hot
+// path.  What the library calls cannot do and these can:
+//   * the item count is read from DEVICE memory (a status word written by the kernel that produced the keys), so
+//     the host never has to know R: no sentinel padding of the unused tail, no sort over the whole capacity;
+//   * a "skip" word (the overflow flag) turns the whole sort into a no-op on the device;
+//   * values may be implicit (value = index), which saves the iota array of the depth sort.
+// Stability (equal keys keep their input order) is what makes "depth-rank emission + sort by tile id" reproduce the
+// reference's (tile, depth, index) order bit for bit.
+#pragma once
+#include "common.cuh"
+
+namespace dqo {
+
+#define RS_THREADS 256
+#define RS_ITEMS 16
+#define RS_TILE (RS_THREADS * RS_ITEMS) // 4096 keys per block
+#define RS_MAX_PASSES 4
+
+struct SortTemp {
+    size_t hist;    // u32[RS_MAX_PASSES][256] digit histograms of the whole input
+    size_t ticket;  // u32[RS_MAX_PASSES] dynamic tile ids (look-back needs "tile j started before tile j+1")
+    size_t status;  // u32[passes][tiles][256] look-back words: 2 flag bits | 30 value bits
+    size_t total;   // bytes; the whole region is cleared by ONE memset per sort
+    int tiles;
+};
+
+inline int radix_passes(int nbits) { return nbits <= 0 ? 1 : (nbits + 7) / 8; }
+
+inline void make_sort_temp(int64_t capacity, int nbits, SortTemp *T) {
+    const int passes = radix_passes(nbits);
+    T->tiles = (int)((capacity + RS_TILE - 1) / RS_TILE);
+    if (T->tiles < 1) T->tiles = 1;
+    size_t cur = 0;
+    T->hist = cur;
+    cur += (size_t)RS_MAX_PASSES * 256 * 4;
+    T->ticket = cur;
+    cur += 256;
+    T->status = cur;
+    cur += (size_t)passes * T->tiles * 256 * 4;
+    T->total = align_up(cur, 256);
+}
+
+// Sorts (key, value) pairs by key bits [0, nbits), stable.  n = min(*count, capacity) (count == nullptr: capacity), 0 when
+// *skip != 0.  The data ping-pongs between the two buffer pairs: with an even number of passes the result ends up in
+// (keys_a, vals_a), with an odd number in (keys_b, vals_b) -- see radix_result_in_a().  vals_a == nullptr on input means
+// value = index (vals_b and, for an even number of passes, a scratch vals_a are still needed: pass it as vals_scratch).
+// `temp` must hold make_sort_temp(capacity, nbits).total bytes.  Enqueues 1 memset + 1 + passes kernels on `stream`.
+template <typename KeyT>
+int radix_sort_pairs(KeyT *keys_a, KeyT *keys_b, uint32_t *vals_a, uint32_t *vals_b, bool implicit_vals,
+                     const int *count, const int *skip, int64_t capacity, int nbits, void *temp, cudaStream_t stream);
+
+inline bool radix_result_in_a(int nbits) { return radix_passes(nbits) % 2 == 0; }
+
+// ---- single-pass prefix sum building blocks (used inside the emission kernels) -------------------------------------
+// look-back word: flag in the high 32 bits (0 = empty, 1 = block aggregate, 2 = inclusive prefix), value in the low 32
+#define LB_PARTIAL 1ull
+#define LB_INCLUSIVE 2ull
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long *p) {
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+__device__ __forceinline__ void lb_store(unsigned long long *p, unsigned long long flag, uint32_t value) {
+    *reinterpret_cast<volatile unsigned long long *>(p) = (flag << 32) | value;
+}
+// Exclusive prefix of block `tile` given every earlier block's aggregate; executed by one full warp.  Block j publishes
+// lb_store(&status[j], LB_PARTIAL, aggregate) before calling this, and LB_INCLUSIVE afterwards.
+__device__ __forceinline__ uint32_t lb_exclusive_prefix(const unsigned long long *status, int tile, int lane) {
+    uint32_t excl = 0;
+    int j = tile - 1;
+    while (j >= 0) {
+        const int idx = j - lane;
+        unsigned long long s = (idx >= 0) ? lb_load(&status[idx]) : (LB_INCLUSIVE << 32);
+        while (__any_sync(0xFFFFFFFFu, (s >> 32) == 0)) {
+            if ((s >> 32) == 0) s = lb_load(&status[idx]);
+        }
+        const unsigned incl = __ballot_sync(0xFFFFFFFFu, (s >> 32) == LB_INCLUSIVE);
+        const int first = incl ? (__ffs(incl) - 1) : 31;
+        uint32_t v = (lane <= first) ? (uint32_t)s : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        excl += v;
+        if (incl) break;
+        j -= 32;
+    }
+    return excl;
+}
+
+} // namespace dqo

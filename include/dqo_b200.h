@@ -29,11 +29,12 @@ extern "C" {
 int dqo_abi_version(void);
 /* Human-readable description of the last error on this thread (never NULL). */
 const char *dqo_last_error(void);
-/* Instrumentation (bench.py): number of this library's own kernel launches so far (CUB library calls count as one),
- * and optional per-stage CUDA-event timing of the rasterizer on the launching stream.  Stage order:
- * 0 begin-fwd, 1 preprocess, 2 depth sort, 3 scan, 4 duplicate, 5 tile sort, 6 ranges, 7 front blend and 8 back-phase
- * binning (two-phase binning only), 9 compact, 10 render-fwd, 11 begin-bwd, 12 render-bwd, 13 gaussian-bwd; each value is
- * the time since the previous recorded mark.  dqo_profile_read synchronises on the recorded events. */
+/* Instrumentation (bench.py): number of this library's own kernel launches so far (every kernel is this library's: no
+ * CUB / Thrust / cuBLAS call anywhere), and optional per-stage CUDA-event timing of the rasterizer on the launching
+ * stream, per calling thread.  Stage order: 0 begin-fwd, 1 preprocess, 2 depth sort, 3 (unused: the scan is fused into the
+ * emission), 4 scan + emit, 5 tile sort, 6 ranges, 7 front blend and 8 back-phase binning (two-phase binning only),
+ * 9 compact, 10 render-fwd, 11 begin-bwd, 12 render-bwd, 13 gaussian-bwd; each value is the time since the previous
+ * recorded mark.  dqo_profile_read synchronises on the recorded events. */
 long long dqo_launch_count(void);
 void dqo_profile_enable(int on);
 int dqo_profile_read(float *ms_out, int n);
@@ -92,8 +93,8 @@ size_t dqo_rast_image_bytes(int32_t W, int32_t H);
  * Every output image is fully written by the call (including the fill values of
  * rasterize_points.cu:79-89 for tiles that are not rendered), so callers may pass uninitialised memory.
  * `status` is device int32[DQO_ST_WORDS].  No host synchronisation is performed.  All work is ordered on `stream`;
- * two small stages run on an internal per-device side stream that is forked from and joined back into `stream` with events
- * before the call returns. */
+ * two small stages run on a helper stream owned by the pair (device, `stream`) that is forked from and joined back into
+ * `stream` with events before the call returns (capturable in a CUDA graph; callers on different streams share nothing). */
 int dqo_rast_forward(const dqo_rast_settings *s,
                      const float *background,     /* [3] */
                      const float *means3D,        /* [P,3] */
@@ -168,6 +169,25 @@ int dqo_rast_export_state(const dqo_rast_settings *s, const void *geom_buffer, c
                           uint32_t *n_contrib /* [H,W] */, float *final_T /* [H,W] */,
                           float *means2D /* [P,2] */, float *depths /* [P] */, float *conic_opacity /* [P,4] */,
                           float *rgb /* [P,3] */, uint32_t *tiles_touched /* [P] */, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stable LSD radix sort of (key, value) pairs with a DEVICE-side item count (csrc/sort.cu).  Replaces the library
+ * sorts of the reference's binning and kNN: cub::DeviceRadixSort::SortPairs at RAST/cuda_rasterizer/rasterizer_impl.cu:
+ * 327-336 and KNN/simple_knn.cu:241-244.  The rasterizer and dqo_knn3 use it internally; it is exported for tests and
+ * for callers that bin by other keys.
+ *   n = min(*count, capacity) (count == NULL: capacity); nothing is sorted when *skip != 0 (skip may be NULL).
+ *   Bits [0, key_bits) of the keys are sorted, 8 per pass; the data ping-pongs between the (a) and (b) buffers and ends
+ *   up in (a) after an even number of passes (key_bits in 9..16 or 25..32), in (b) after an odd one.
+ *   implicit_vals != 0: values are the input positions 0..n-1; vals_a is then scratch only (may be NULL for one pass).
+ *   temp: dqo_sort_pairs_temp_bytes(capacity, key_bits) bytes of device memory.
+ * ---------------------------------------------------------------------------------------------- */
+size_t dqo_sort_pairs_temp_bytes(int64_t capacity, int32_t key_bits);
+int dqo_sort_pairs_u32(uint32_t *keys_a, uint32_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, int32_t implicit_vals,
+                       const int32_t *count, const int32_t *skip, int64_t capacity, int32_t key_bits, void *temp,
+                       void *stream);
+int dqo_sort_pairs_u16(uint16_t *keys_a, uint16_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, int32_t implicit_vals,
+                       const int32_t *count, const int32_t *skip, int64_t capacity, int32_t key_bits, void *temp,
+                       void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * simple-knn.  Replaces SimpleKNN::knn (KNN/simple_knn.cu:216-252) behind distCUDA2 (KNN/spatial.cu:15-28):
