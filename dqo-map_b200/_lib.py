@@ -67,6 +67,12 @@ PROTOTYPES = {
     "dqo_sort_pairs_u16": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int32, c_p, c_p, C.c_int64, C.c_int32, c_p, c_p]),
     "dqo_knn_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "dqo_knn3": (C.c_int, [C.c_int32, c_p, c_p, c_p, c_p, C.c_size_t, c_p]),
+    "dqo_bbox_mask": (C.c_int, [C.c_int32, c_p, C.c_int32, c_p, C.c_float, c_p, c_p, c_p, c_p]),
+    "dqo_gaussian_radius": (C.c_int, [C.c_int32, c_p, c_p, c_p]),
+    "dqo_scale_init": (C.c_int, [C.c_int32, C.c_int32, c_p, c_p, c_p] + [C.c_float] * 6 + [c_p, c_p, c_p, c_p]),
+    "dqo_knn_cross3_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "dqo_knn_cross3": (C.c_int, [C.c_int32, c_p, C.c_int32, c_p, c_p, c_p, c_p, C.c_size_t, c_p]),
+    "dqo_inside_mask": (C.c_int, [C.c_int32, c_p, c_p, c_p, C.c_float, c_p, c_p]),
     "dqo_accumulate_error": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [c_p] * 5
                              + [C.c_float, C.c_float, C.c_float, C.c_int32] + [c_p] * 7 + [c_p]),
     "dqo_render_range": (C.c_int, [C.c_int32, C.c_int32, c_p, C.c_float, c_p, c_p, c_p, c_p]),

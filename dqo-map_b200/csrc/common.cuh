@@ -175,9 +175,10 @@ struct GeomLayout {
     size_t rect;       // uint2[P] {min.x | max.x<<16, min.y | max.y<<16}
     size_t clamped;    // u8[P] bit c = colour channel c clamped (forward.cu:151-153)
     size_t gacc;       // f32[16P] gradient accumulators of the backward blend (see DQO_GACC_FLOATS)
-    size_t lb;         // u64[2][emit_blocks] look-back words of the two emission kernels + 2 tickets (sort.cuh)
-    size_t lb_bytes;
-    int emit_blocks;
+    size_t tiles_b;    // u32[P] two-phase: unfinished tiles in the rectangle of every rank the front phase left out
+    size_t sums;       // per phase: u32[emit_blocks] totals of 256 ranks + u32[emit_groups] totals of 64 such blocks
+    size_t sums_stride;
+    int emit_blocks, emit_groups;
     size_t sort_temp;  // histograms / look-back words of the depth sort (sort.cuh: SortTemp)
     size_t total;
 };

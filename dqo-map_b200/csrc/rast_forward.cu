@@ -49,9 +49,13 @@ int make_geom_layout(int P, GeomLayout *L) {
     L->clamped = bump(cur, n);
     L->gacc = bump(cur, n * DQO_GACC_FLOATS * 4);
     // look-back words + tickets of the two emission kernels (front / single phase, back phase): cleared together
+    L->tiles_b = bump(cur, n * 4);
     L->emit_blocks = (int)((n + 255) / 256);
-    L->lb = bump(cur, (size_t)2 * L->emit_blocks * 8 + 256);
-    L->lb_bytes = (size_t)2 * L->emit_blocks * 8 + 256;
+    L->emit_groups = (L->emit_blocks + 63) / 64;
+    // per phase (front / single, back): u32 block totals [emit_blocks] + u32 group totals [emit_groups]; the group totals
+    // are accumulated with atomics, so the region is cleared at the start of every forward
+    L->sums_stride = align_up((size_t)(L->emit_blocks + L->emit_groups) * 4, 256);
+    L->sums = bump(cur, 2 * L->sums_stride);
     SortTemp T;
     make_sort_temp((int64_t)n, 32, &T);
     L->sort_temp = bump(cur, T.total);
@@ -471,83 +475,121 @@ __device__ __forceinline__ uint32_t rows_in_range(const uint32_t *__restrict__ r
     return __ldg(&row_any[wd]) & (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi));
 }
 
-// Prefix sum of the per-Gaussian tile counts (rasterizer_impl.cu:303) and emission of one (tile, gaussian) pair per
-// masked tile of the rectangle (duplicateWithKeys, rasterizer_impl.cu:70-115) in ONE kernel, walking the Gaussians in
-// depth-rank order so that a stable sort by tile id alone reproduces the reference order.
-// A block owns 256 consecutive ranks: block-wide inclusive scan of the counts, decoupled look-back over the earlier
-// blocks' aggregates (sort.cuh), then one warp serves 32 consecutive ranks -- the run of each Gaussian is written by
-// all lanes together (coalesced) when no tile of its rectangle is masked out, otherwise by its owner lane walking the
-// mask bitmap.  R never visits the host and nothing is padded: the sort that follows reads its count from `status`.
+// Number of instances rank i emits: tiles_touched of its Gaussian (MODE 0 / 1), or the number of UNFINISHED tiles in its
+// rectangle when the front phase did not bin it (MODE 2: offsets[rank] > front).
+template <int MODE>
+__device__ __forceinline__ uint32_t rank_count(int64_t i, uint32_t id, int64_t front, const uint32_t *__restrict__ tiles,
+                                               const uint32_t *offsets, const uint2 *__restrict__ rect,
+                                               const uint32_t *__restrict__ mask_bits, const uint32_t *__restrict__ row_any,
+                                               int mask_words) {
+    if (MODE != 2) return tiles[id];
+    uint32_t n = 0;
+    if ((int64_t)offsets[i] > front && tiles[id]) {
+        const uint2 rc = rect[id];
+        const uint32_t minx = rc.x & 0xFFFF, maxx = rc.x >> 16, miny = rc.y & 0xFFFF, maxy = rc.y >> 16;
+        for (uint32_t wd = miny >> 5; wd <= (maxy - 1) >> 5; wd++) {
+            uint32_t rows = rows_in_range(row_any, wd, miny, maxy);
+            while (rows) {
+                const uint32_t y = wd * 32 + (__ffs(rows) - 1);
+                rows &= rows - 1;
+                n += mask_row_count(mask_bits, mask_words, y, minx, maxx);
+            }
+        }
+    }
+    return n;
+}
+
+// Step 1 of the prefix sum of the per-rank instance counts (rasterizer_impl.cu:303, in depth-rank order): the total of
+// every block of 256 ranks, and the totals of groups of 64 blocks.  The emission kernel then finds its exclusive prefix
+// by adding at most P/16384 group totals and 63 block totals -- no chain of blocks waiting for each other (a single-pass
+// look-back scan had every one of the ~4000 simultaneously resident blocks wait for its predecessors: 3x slower).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    rank_sums_kernel(int P, int64_t front, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
+                     const uint32_t *offsets, const uint2 *__restrict__ rect, const uint32_t *__restrict__ mask_bits,
+                     const uint32_t *__restrict__ row_any, int mask_words, uint32_t *tiles_rank, uint32_t *sums,
+                     uint32_t *group_sums) {
+    __shared__ uint32_t s_w[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 256 + tid;
+    uint32_t n = 0;
+    if (i < P) {
+        n = rank_count<MODE>(i, order[i], front, tiles, offsets, rect, mask_bits, row_any, mask_words);
+        if (MODE == 2) tiles_rank[i] = n;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
+    if (lane == 0) s_w[warp] = n;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += s_w[w];
+        sums[blockIdx.x] = t;
+        if (t) atomicAdd(&group_sums[blockIdx.x >> 6], t);
+    }
+}
+
+// Step 2: emission of one (tile, gaussian) pair per masked tile of the rectangle (duplicateWithKeys,
+// rasterizer_impl.cu:70-115), walking the Gaussians in depth-rank order so that a stable sort by tile id alone
+// reproduces the reference order.  A block owns 256 consecutive ranks: exclusive prefix from the block / group totals,
+// block-wide inclusive scan of the counts, then one warp serves 32 consecutive ranks -- the run of each Gaussian is
+// written by all lanes together (coalesced) when no tile of its rectangle is masked out, otherwise by its owner lane
+// walking the mask bitmap.  R never visits the host and nothing is padded: the sort that follows reads its count from
+// `status`.
 //   MODE 0 (single phase): every rank; writes beyond `capacity` are dropped and DQO_ST_OVERFLOW is raised by the last rank.
 //   MODE 1 (front phase):  only the ranks whose inclusive offset fits into `capacity` (= front_instances), i.e. the
 //          nearest Gaussians; R_front is reported.  `offsets` still receives the full scan (R, and the back phase's
 //          "not binned yet" test).
-//   MODE 2 (back phase):   the count of a rank is the number of UNFINISHED tiles in its rectangle (0 for the ranks the
-//          front phase binned: offsets[rank] <= front); overflow when R_back > capacity.
+//   MODE 2 (back phase):   the count of a rank is the number of unfinished tiles in its rectangle (tiles_rank, written by
+//          rank_sums_kernel<2>); overflow when R_back > capacity.
 template <typename KeyT, int MODE>
 __global__ void __launch_bounds__(256)
-    emit_kernel(int P, int64_t capacity, int64_t front, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
-                uint32_t *offsets, const uint2 *__restrict__ rect, const uint32_t *__restrict__ mask_bits,
-                const uint32_t *__restrict__ row_any, int mask_words, int grid_x, KeyT *__restrict__ keys,
-                uint32_t *__restrict__ vals, unsigned long long *lb, uint32_t *ticket, int *status) {
+    emit_kernel(int P, int64_t capacity, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
+                const uint32_t *__restrict__ tiles_rank, uint32_t *offsets, const uint2 *__restrict__ rect,
+                const uint32_t *__restrict__ mask_bits, const uint32_t *__restrict__ row_any, int mask_words, int grid_x,
+                KeyT *__restrict__ keys, uint32_t *__restrict__ vals, const uint32_t *__restrict__ sums,
+                const uint32_t *__restrict__ group_sums, int *status) {
     __shared__ uint32_t s_n[257];
-    __shared__ uint32_t s_warp_tot[8];
-    __shared__ uint32_t s_excl, s_tile;
+    __shared__ uint32_t s_warp_tot[8], s_warp_pre[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const int tile = (int)s_tile;
+    const int tile = blockIdx.x;
     const int64_t i = (int64_t)tile * 256 + tid;
+    // exclusive prefix of this block: whole groups of 64 blocks, then the blocks of its own group
+    uint32_t pre = 0;
+    for (int j = tid; j < (tile >> 6); j += 256) pre += group_sums[j];
+    {
+        const int j = ((tile >> 6) << 6) + tid;
+        if (tid < 64 && j < tile) pre += sums[j];
+    }
     uint32_t id = 0, n = 0;
     uint2 rc = make_uint2(0, 0);
     if (i < P) {
         id = order[i];
-        if (MODE == 2) {
-            if ((int64_t)offsets[i] > front && tiles[id]) {
-                rc = rect[id];
-                const uint32_t minx = rc.x & 0xFFFF, maxx = rc.x >> 16, miny = rc.y & 0xFFFF, maxy = rc.y >> 16;
-                for (uint32_t wd = miny >> 5; wd <= (maxy - 1) >> 5; wd++) {
-                    uint32_t rows = rows_in_range(row_any, wd, miny, maxy);
-                    while (rows) {
-                        const uint32_t y = wd * 32 + (__ffs(rows) - 1);
-                        rows &= rows - 1;
-                        n += mask_row_count(mask_bits, mask_words, y, minx, maxx);
-                    }
-                }
-            }
-        } else {
-            n = tiles[id];
-            if (n) rc = rect[id];
-        }
+        n = (MODE == 2) ? tiles_rank[i] : tiles[id];
+        if (n) rc = rect[id];
     }
     s_n[tid] = n;
     if (MODE == 1 && tid == 255) s_n[256] = (i + 1 < P) ? tiles[order[i + 1]] : 0u;
-    // block-wide inclusive scan
+    // block-wide inclusive scan of n, block-wide sum of pre
     uint32_t incl = n;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
         if (lane >= o) incl += t;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xFFFFFFFFu, pre, o);
     if (lane == 31) s_warp_tot[warp] = incl;
+    if (lane == 0) s_warp_pre[warp] = pre;
     __syncthreads();
-    uint32_t woff = 0, block_total = 0;
+    uint32_t woff = 0, block_excl = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) {
-        const uint32_t t = s_warp_tot[w];
-        if (w < warp) woff += t;
-        block_total += t;
+        if (w < warp) woff += s_warp_tot[w];
+        block_excl += s_warp_pre[w];
     }
-    if (warp == 0) {
-        if (lane == 0) lb_store(&lb[tile], tile == 0 ? LB_INCLUSIVE : LB_PARTIAL, block_total);
-        uint32_t excl = 0;
-        if (tile > 0) {
-            excl = lb_exclusive_prefix(lb, tile, lane);
-            if (lane == 0) lb_store(&lb[tile], LB_INCLUSIVE, excl + block_total);
-        }
-        if (lane == 0) s_excl = excl;
-    }
-    __syncthreads();
+    const uint32_t s_excl = block_excl;
     const uint32_t end = s_excl + woff + incl; // inclusive offset of rank i
     uint32_t off = end - n;
     if (i < P) {
@@ -1263,8 +1305,8 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     const uint32_t *d_order = nullptr, *d_tiles = nullptr, *d_mask_bits = nullptr;
     uint32_t *d_offsets = nullptr;
     const uint2 *d_rect = nullptr;
-    unsigned long long *d_lb = nullptr;
-    uint32_t *d_ticket = nullptr;
+    uint32_t *d_sums = nullptr, *d_tiles_b = nullptr;
+    size_t sums_stride = 0;
     int emit_blocks = 0;
     ForkJoin *fj = debug ? nullptr : fork_join(stream); // side stream + events owned by (device, caller stream)
     if (P > 0) {
@@ -1273,7 +1315,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         char *geom = (char *)geom_buffer;
         char *bin = (char *)binning_buffer;
         uint32_t *mask_bits = (uint32_t *)(img + IL.mask_bits);
-        DQO_CUDA_CHECK(cudaMemsetAsync(geom + GL.lb, 0, GL.lb_bytes, stream));
+        DQO_CUDA_CHECK(cudaMemsetAsync(geom + GL.sums, 0, 2 * GL.sums_stride, stream));
         {
             const int nw = IL.tiles_y * IL.mask_words;
             mask_bits_kernel<<<(nw + 7) / 8, 256, 0, stream>>>(IL.tiles_x, IL.tiles_y, IL.mask_words, tile_mask, mask_bits);
@@ -1352,9 +1394,10 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         d_offsets = (uint32_t *)(geom + GL.offsets);
         d_rect = pa.rect;
         d_mask_bits = mask_bits;
-        d_lb = (unsigned long long *)(geom + GL.lb);
+        d_sums = (uint32_t *)(geom + GL.sums);
+        d_tiles_b = (uint32_t *)(geom + GL.tiles_b);
+        sums_stride = GL.sums_stride / 4;
         emit_blocks = GL.emit_blocks;
-        d_ticket = (uint32_t *)(geom + GL.lb + (size_t)2 * emit_blocks * 8);
     }
 
     const int sort_bits = tile_sort_bits(T);
@@ -1386,12 +1429,18 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     auto bin_phase = [&](int mode, int64_t n, int64_t at, const uint32_t *bits, int count_word, uint2 *out_ranges) -> int {
         void *ka = keys_a + at * ksz, *kb = keys_b + at * ksz;
         uint32_t *va = vals_a + at, *vb = vals_b + at;
-        unsigned long long *lb = d_lb + (mode == 2 ? emit_blocks : 0);
-        uint32_t *ticket = d_ticket + (mode == 2 ? 1 : 0);
+        uint32_t *sums = d_sums + (mode == 2 ? sums_stride : 0), *group_sums = sums + emit_blocks;
+        if (mode == 2)
+            rank_sums_kernel<2><<<emit_blocks, 256, 0, stream>>>(P, front, d_order, d_tiles, d_offsets, d_rect, bits, row_any_b,
+                                                                 IL.mask_words, d_tiles_b, sums, group_sums);
+        else
+            rank_sums_kernel<0><<<emit_blocks, 256, 0, stream>>>(P, front, d_order, d_tiles, d_offsets, d_rect, bits, row_any_b,
+                                                                 IL.mask_words, nullptr, sums, group_sums);
+        DQO_LAUNCH_CHECK("rank sums", debug, stream);
 #define DQO_EMIT(KT, MODE)                                                                                             \
-    emit_kernel<KT, MODE><<<emit_blocks, 256, 0, stream>>>(P, n, front, d_order, d_tiles, d_offsets, d_rect, bits,     \
-                                                          row_any_b, IL.mask_words, IL.tiles_x, (KT *)ka, va, lb,      \
-                                                          ticket, status)
+    emit_kernel<KT, MODE><<<emit_blocks, 256, 0, stream>>>(P, n, d_order, d_tiles, d_tiles_b, d_offsets, d_rect, bits,  \
+                                                          row_any_b, IL.mask_words, IL.tiles_x, (KT *)ka, va, sums,    \
+                                                          group_sums, status)
         if (keys16) {
             if (mode == 0) DQO_EMIT(uint16_t, 0); else if (mode == 1) DQO_EMIT(uint16_t, 1); else DQO_EMIT(uint16_t, 2);
         } else {

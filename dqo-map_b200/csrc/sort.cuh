@@ -1,5 +1,5 @@
-// Hand-written stable LSD radix sort ("onesweep": one histogram kernel + one fused rank / look-back / scatter kernel per
-// 8-bit digit) and a single-pass decoupled look-back prefix sum for sm_100a.
+// Hand-written stable LSD radix sort (per 8-bit digit: count -> scan -> scatter, see sort.cu) and a single-pass
+// decoupled look-back prefix sum for sm_100a.
 //
 // Replaces the library sorts / scans of the reference's binning (cub::DeviceRadixSort::SortPairs,
 // RAST/cuda_rasterizer/rasterizer_impl.cu:327-336; cub::DeviceScan::InclusiveSum, :303; simple_knn.cu:237) on the hot
@@ -21,26 +21,29 @@ namespace dqo {
 #define RS_MAX_PASSES 4
 
 struct SortTemp {
-    size_t hist;    // u32[RS_MAX_PASSES][256] digit histograms of the whole input
-    size_t ticket;  // u32[RS_MAX_PASSES] dynamic tile ids (look-back needs "tile j started before tile j+1")
-    size_t status;  // u32[passes][tiles][256] look-back words: 2 flag bits | 30 value bits
-    size_t total;   // bytes; the whole region is cleared by ONE memset per sort
-    int tiles;
+    size_t counts;  // u32[256][tiles] digit-major count matrix of the current pass, scanned in place
+    size_t ticket;  // u32[RS_MAX_PASSES] dynamic block ids of the scan kernel (+ padding)
+    size_t lb;      // u64[RS_MAX_PASSES][scan_blocks] look-back words of the scan kernel
+    size_t clear_bytes; // ticket + lb: cleared by ONE memset per sort
+    size_t total;
+    int tiles, scan_blocks;
 };
 
 inline int radix_passes(int nbits) { return nbits <= 0 ? 1 : (nbits + 7) / 8; }
 
 inline void make_sort_temp(int64_t capacity, int nbits, SortTemp *T) {
-    const int passes = radix_passes(nbits);
+    (void)nbits;
     T->tiles = (int)((capacity + RS_TILE - 1) / RS_TILE);
     if (T->tiles < 1) T->tiles = 1;
+    T->scan_blocks = (int)(((int64_t)256 * T->tiles + 4095) / 4096);
     size_t cur = 0;
-    T->hist = cur;
-    cur += (size_t)RS_MAX_PASSES * 256 * 4;
+    T->counts = cur;
+    cur += align_up((size_t)256 * T->tiles * 4, 256);
     T->ticket = cur;
     cur += 256;
-    T->status = cur;
-    cur += (size_t)passes * T->tiles * 256 * 4;
+    T->lb = cur;
+    cur += align_up((size_t)RS_MAX_PASSES * T->scan_blocks * 8, 256);
+    T->clear_bytes = cur - T->ticket;
     T->total = align_up(cur, 256);
 }
 
@@ -48,7 +51,7 @@ inline void make_sort_temp(int64_t capacity, int nbits, SortTemp *T) {
 // *skip != 0.  The data ping-pongs between the two buffer pairs: with an even number of passes the result ends up in
 // (keys_a, vals_a), with an odd number in (keys_b, vals_b) -- see radix_result_in_a().  vals_a == nullptr on input means
 // value = index (vals_b and, for an even number of passes, a scratch vals_a are still needed: pass it as vals_scratch).
-// `temp` must hold make_sort_temp(capacity, nbits).total bytes.  Enqueues 1 memset + 1 + passes kernels on `stream`.
+// `temp` must hold make_sort_temp(capacity, nbits).total bytes.  Enqueues 1 memset + 3 kernels per pass on `stream`.
 template <typename KeyT>
 int radix_sort_pairs(KeyT *keys_a, KeyT *keys_b, uint32_t *vals_a, uint32_t *vals_b, bool implicit_vals,
                      const int *count, const int *skip, int64_t capacity, int nbits, void *temp, cudaStream_t stream);

@@ -199,6 +199,38 @@ int dqo_knn3(int32_t P, const float *points /* [P,3] */, float *mean_dist2 /* [P
              void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Map geometry around distCUDA2 (inline PyTorch in the reference).
+ *   dqo_bbox_mask       bbox_filter (SLAM/utils.py:801-808): mask[i] = total_xyz[i] strictly inside the bounding box of
+ *                       local_xyz grown by `padding`; the box never visits the host.  count (device int, may be NULL) =
+ *                       mask.sum().  workspace32: 32 bytes of device memory.
+ *   dqo_gaussian_radius GaussianPointCloud.get_radius (SLAM/gaussian_pointcloud.py:739-743): (sum(exp s) - min(exp s)) / 2
+ *   dqo_scale_init      GaussianPointCloud.update_geometry after the kNN (gaussian_pointcloud.py:540-569): the first n_new
+ *                       rows of xyz_total are the new points, knn_idx [n_new,3] their neighbours in xyz_total (dqo_knn3);
+ *                       d_k = |p - p_k| - 3 radius_k, invalid = any d_k < 0 (the rows update_geometry deletes),
+ *                       s = clip(sqrt(mean d_k^2), min_radius, max_radius),
+ *                       log_scales = log(scale_factor * s * xyz_factor); valid_count (device int, may be NULL) = survivors
+ *                       (update_geometry keeps the old scales when it is 0).
+ *   dqo_knn_cross3      squared distances (ascending) and indices of the 3 nearest points of `ref` for every point of
+ *                       `query`: what temp_points_filter asks pytorch3d.ops.knn_points for (mapper.py:1366-1372, K = 3);
+ *                       fewer than 3 reference points: padded with zeros like pytorch3d (index -1 when n_ref == 0);
+ *                       equal distances: lower reference index first.
+ *   dqo_inside_mask     (sqrt(dist2) < ratio * ref_radius[idx]).any(-1)   (mapper.py:1376-1377, ratio 0.6)
+ * ---------------------------------------------------------------------------------------------- */
+int dqo_bbox_mask(int32_t n_local, const float *local_xyz, int32_t n_total, const float *total_xyz, float padding,
+                  uint8_t *mask /* [n_total] */, int32_t *count, void *workspace32, void *stream);
+int dqo_gaussian_radius(int32_t n, const float *log_scales /* [n,3] */, float *radius /* [n] */, void *stream);
+int dqo_scale_init(int32_t n_new, int32_t n_total, const float *xyz_total /* [n_total,3] */,
+                   const float *radius_total /* [n_total] */, const int32_t *knn_idx /* [n_new,3] */, float min_radius,
+                   float max_radius, float scale_factor, float xyz_factor_x, float xyz_factor_y, float xyz_factor_z,
+                   float *log_scales /* [n_new,3] */, uint8_t *invalid /* [n_new] */, int32_t *valid_count, void *stream);
+size_t dqo_knn_cross3_workspace_bytes(int32_t n_query, int32_t n_ref);
+int dqo_knn_cross3(int32_t n_query, const float *query /* [n_query,3] */, int32_t n_ref, const float *ref /* [n_ref,3] */,
+                   float *dist2 /* [n_query,3] */, int32_t *idx /* [n_query,3] */, void *workspace, size_t workspace_bytes,
+                   void *stream);
+int dqo_inside_mask(int32_t n, const float *dist2, const int32_t *idx, const float *ref_radius, float ratio,
+                    uint8_t *mask /* [n] */, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * cuda_utils.  Replaces accumulate_gaussian_error_impl (CU/map_process.cu:194-245) behind
  * accumulate_gaussian_error (CU/cuda_utils.cu:17-60).  All seven [P] outputs are fully written.
  * ---------------------------------------------------------------------------------------------- */
