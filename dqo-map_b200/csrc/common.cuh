@@ -13,7 +13,7 @@
 
 #define DQO_TILE 16
 #define DQO_TILE_PIX 256
-#define DQO_ABI_VERSION 9
+#define DQO_ABI_VERSION 10
 
 namespace dqo {
 

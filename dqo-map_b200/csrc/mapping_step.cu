@@ -1,5 +1,6 @@
 // Fused mapping iteration: one C-ABI call enqueues the whole step of the reference's hot loop
-// (SLAM/multiprocess/mapper.py:568-599 + loss_update :799-928, without the attach term) on one stream, with no host
+// (SLAM/multiprocess/mapper.py:568-599 + loss_update :799-928: masked L1 colour + depth loss and the attach term
+// :810-829; the SSIM / normal / semantic / instance terms are not part of the fused step) on one stream, with no host
 // synchronisation and no intermediate tensor owned by the host:
 //
 //   raw parameters --activate--> rasterize forward --> masked L1 colour/depth loss + image gradients
@@ -37,6 +38,7 @@ struct StepLayout {
     size_t color, depth, hit_depth, hit_color, hit_cw, hit_dw, T, radii, n_touched, tile_indices;
     size_t g_img, g_depth, loss_ws;                             // loss gradients + reduction scratch
     size_t g_means3D, g_sh, g_opacity, g_scales, g_rot;         // activated-space parameter gradients
+    size_t adam;                                                // AdamScalars of this step, written on the device
     size_t total;
 };
 static size_t sbump(size_t &cur, size_t bytes) {
@@ -74,6 +76,7 @@ static int make_step_layout(int P, int M, int W, int H, int64_t capacity, StepLa
     L->g_opacity = sbump(cur, n * 4);
     L->g_scales = sbump(cur, n * 12);
     L->g_rot = sbump(cur, n * 16);
+    L->adam = sbump(cur, 256);
     L->total = align_up(cur, 256);
     return 0;
 }
@@ -98,6 +101,11 @@ __global__ void __launch_bounds__(256) activate_kernel(int P, const float *__res
 struct AdamScalars {
     float beta1, beta2, omb1, omb2, bc2_sqrt, eps;
     float step_size[6]; // xyz, f_dc, f_rest, opacity, scaling, rotation
+    // attach term (mapper.py:810-829): d/dp of 1000 * mean((p - p0)^2) over the masked rows = attach_grad * (p - p0),
+    // and the value itself = attach_val * sum((p - p0)^2); index 0 xyz, 1 scaling, 2 rotation; 0 when disabled
+    float attach_grad[3], attach_val[3];
+    float attach_logit_thr; // a Gaussian is anchored when sigmoid(init_opacity) < thr
+    int skip;               // the forward flagged an instance overflow: gradients are invalid, no update
 };
 __device__ __forceinline__ void adam_update(float &p, float g, float &m, float &v, const AdamScalars &k, float step_size) {
     m = m + k.omb1 * (g - m);
@@ -106,8 +114,63 @@ __device__ __forceinline__ void adam_update(float &p, float g, float &m, float &
     p = p - step_size * (m / denom);
 }
 
+// One thread: the step number lives on the device (step_state[0] counts the updates that really happened, step_state[1]
+// the steps skipped because the forward overflowed its instance capacity -- sticky until the host resets it), so the
+// call takes no per-step host argument and the whole iteration can be replayed from a CUDA graph.
+struct PrepareArgs {
+    const int *status;
+    int *step_state; // may be NULL: host_step is used
+    int host_step;
+    double beta1, beta2, eps, lr[6];
+    double attach_weight;
+    float attach_thr;
+    const int *attach_count; // NULL: no attach term
+    AdamScalars *out;
+};
+__global__ void adam_prepare_kernel(PrepareArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int overflow = a.status[DQO_ST_OVERFLOW];
+    int step = a.host_step;
+    if (a.step_state) {
+        if (overflow) {
+            a.step_state[1] += 1;
+            step = a.step_state[0] + 1;
+        } else {
+            step = a.step_state[0] + 1;
+            a.step_state[0] = step;
+        }
+    }
+    AdamScalars k;
+    const double bc1 = 1.0 - pow(a.beta1, (double)step), bc2 = 1.0 - pow(a.beta2, (double)step);
+    k.beta1 = (float)a.beta1; k.beta2 = (float)a.beta2; k.omb1 = (float)(1.0 - a.beta1); k.omb2 = (float)(1.0 - a.beta2);
+    k.bc2_sqrt = (float)sqrt(bc2); k.eps = (float)a.eps;
+    for (int t = 0; t < 6; t++) k.step_size[t] = (float)(a.lr[t] / bc1);
+    const int widths[3] = {3, 3, 4};
+    const int n_attach = a.attach_count ? *a.attach_count : 0;
+    for (int t = 0; t < 3; t++) {
+        const double denom = (double)n_attach * widths[t];
+        k.attach_grad[t] = n_attach > 0 ? (float)(2.0 * a.attach_weight / denom) : 0.f;
+        k.attach_val[t] = n_attach > 0 ? (float)(a.attach_weight / denom) : 0.f;
+    }
+    k.attach_logit_thr = a.attach_thr;
+    k.skip = overflow;
+    *a.out = k;
+}
+// number of Gaussians whose initial opacity is below the attach threshold (mapper.py:810-812)
+__global__ void __launch_bounds__(256) attach_count_kernel(int P, const float *__restrict__ init_opacity, float thr, int *count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = (i < P) && (1.0f / (1.0f + expf(-init_opacity[i])) < thr);
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, in);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, __popc(b));
+}
+__device__ __forceinline__ bool anchored(const float *__restrict__ init_opacity, long long i, float thr) {
+    return (1.0f / (1.0f + expf(-init_opacity[i]))) < thr;
+}
+
 // Activation backward + Adam for the 11 geometric parameters of a Gaussian, plus the confidence bump
-// (mapper.py:909-910: confidence += 1 where any f_dc gradient is non-zero).
+// (mapper.py:909-910: confidence += 1 where any f_dc gradient is non-zero) and the attach term (mapper.py:810-829):
+// Gaussians whose INITIAL opacity is below 0.9 are anchored to their initial xyz / log-scale / raw rotation by
+// 1000 * (mse + mse + mse); its gradient 2000 / (n_anchored * width) * (p - p0) is added to the rasterizer's gradient.
 struct SmallArgs {
     int P, M;
     float *xyz, *opacity, *scaling, *rotation, *f_dc;
@@ -116,71 +179,110 @@ struct SmallArgs {
     const float *g_means3D, *g_opacity, *g_scales, *g_rot, *g_sh;
     float *confidence;
     const uint8_t *ever; // per-Gaussian "has ever had a non-zero gradient" (nullptr: decide from the values instead)
-    const int *status; // the step is skipped when the forward flagged an instance overflow (gradients are invalid)
-    AdamScalars k;
+    const float *init_xyz, *init_scaling, *init_rotation, *init_opacity; // attach reference (all nullptr: no attach term)
+    float *attach_out;   // loss_out[3]: value of the attach term (accumulated, zeroed by the loss kernel)
+    const AdamScalars *kd; // this step's scalars, written by adam_prepare_kernel
 };
+__device__ __forceinline__ void block_add(float v, float *out) { // sum over the block, one atomic per block
+    __shared__ float s_part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_part[w];
+        if (t != 0.f) atomicAdd(out, t);
+    }
+}
 __global__ void __launch_bounds__(256) adam_geometry_kernel(SmallArgs a) {
+    const AdamScalars k = *a.kd;
+    if (k.skip) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.P || a.status[DQO_ST_OVERFLOW]) return;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        const int e = 3 * i + c;
-        float p = a.xyz[e], m = a.m_xyz[e], v = a.v_xyz[e];
-        adam_update(p, a.g_means3D[e], m, v, a.k, a.k.step_size[0]);
-        a.xyz[e] = p; a.m_xyz[e] = m; a.v_xyz[e] = v;
-    }
-    { // opacity: o = sigmoid(x), dL/dx = g * o * (1 - o)
-        const float o = a.act_opacity[i];
-        const float g = a.g_opacity[i] * (o * (1.0f - o));
-        float p = a.opacity[i], m = a.m_op[i], v = a.v_op[i];
-        adam_update(p, g, m, v, a.k, a.k.step_size[3]);
-        a.opacity[i] = p; a.m_op[i] = m; a.v_op[i] = v;
-    }
-#pragma unroll
-    for (int c = 0; c < 3; c++) { // scale: s = exp(x), dL/dx = g * s
-        const int e = 3 * i + c;
-        const float g = a.g_scales[e] * a.act_scales[e];
-        float p = a.scaling[e], m = a.m_sc[e], v = a.v_sc[e];
-        adam_update(p, g, m, v, a.k, a.k.step_size[4]);
-        a.scaling[e] = p; a.m_sc[e] = m; a.v_sc[e] = v;
-    }
-    { // rotation: q = r / max(|r|, eps); dL/dr = (g - q (q . g)) / max(|r|, eps)
-        float4 r = reinterpret_cast<float4 *>(a.rotation)[i];
-        const float4 g = reinterpret_cast<const float4 *>(a.g_rot)[i];
-        const float nrm = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
-        const float d = fmaxf(nrm, 1e-12f);
-        const float qx = r.x / d, qy = r.y / d, qz = r.z / d, qw = r.w / d;
-        const float qg = qx * g.x + qy * g.y + qz * g.z + qw * g.w;
-        const float inv = (nrm > 1e-12f) ? 1.0f / d : 0.0f;
-        const float gr[4] = {(g.x - qx * qg) * inv, (g.y - qy * qg) * inv, (g.z - qz * qg) * inv, (g.w - qw * qg) * inv};
-        float pr[4] = {r.x, r.y, r.z, r.w};
-        float4 m4 = reinterpret_cast<float4 *>(a.m_rot)[i], v4 = reinterpret_cast<float4 *>(a.v_rot)[i];
-        float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-        for (int c = 0; c < 4; c++) adam_update(pr[c], gr[c], mm[c], vv[c], a.k, a.k.step_size[5]);
-        reinterpret_cast<float4 *>(a.rotation)[i] = make_float4(pr[0], pr[1], pr[2], pr[3]);
-        reinterpret_cast<float4 *>(a.m_rot)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
-        reinterpret_cast<float4 *>(a.v_rot)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-    }
-    { // f_dc: gradient = first coefficient of the merged SH gradient
-        const float *gs = a.g_sh + (size_t)i * a.M * 3;
-        const float g3[3] = {gs[0], gs[1], gs[2]};
+    float att = 0.f;
+    if (i < a.P) {
+        const bool anch = a.init_opacity && anchored(a.init_opacity, i, k.attach_logit_thr);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const int e = 3 * i + c;
-            float p = a.f_dc[e], m = a.m_dc[e], v = a.v_dc[e];
-            adam_update(p, g3[c], m, v, a.k, a.k.step_size[1]);
-            a.f_dc[e] = p; a.m_dc[e] = m; a.v_dc[e] = v;
+            float p = a.xyz[e], m = a.m_xyz[e], v = a.v_xyz[e];
+            float g = a.g_means3D[e];
+            if (anch) {
+                const float d = p - a.init_xyz[e];
+                g += k.attach_grad[0] * d;
+                att += k.attach_val[0] * d * d;
+            }
+            adam_update(p, g, m, v, k, k.step_size[0]);
+            a.xyz[e] = p; a.m_xyz[e] = m; a.v_xyz[e] = v;
         }
-        if (a.confidence && (fabsf(g3[0]) != 0.f || fabsf(g3[1]) != 0.f || fabsf(g3[2]) != 0.f)) a.confidence[i] += 1.0f;
+        { // opacity: o = sigmoid(x), dL/dx = g * o * (1 - o)
+            const float o = a.act_opacity[i];
+            const float g = a.g_opacity[i] * (o * (1.0f - o));
+            float p = a.opacity[i], m = a.m_op[i], v = a.v_op[i];
+            adam_update(p, g, m, v, k, k.step_size[3]);
+            a.opacity[i] = p; a.m_op[i] = m; a.v_op[i] = v;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) { // scale: s = exp(x), dL/dx = g * s
+            const int e = 3 * i + c;
+            float g = a.g_scales[e] * a.act_scales[e];
+            float p = a.scaling[e], m = a.m_sc[e], v = a.v_sc[e];
+            if (anch) {
+                const float d = p - a.init_scaling[e];
+                g += k.attach_grad[1] * d;
+                att += k.attach_val[1] * d * d;
+            }
+            adam_update(p, g, m, v, k, k.step_size[4]);
+            a.scaling[e] = p; a.m_sc[e] = m; a.v_sc[e] = v;
+        }
+        { // rotation: q = r / max(|r|, eps); dL/dr = (g - q (q . g)) / max(|r|, eps)
+            float4 r = reinterpret_cast<float4 *>(a.rotation)[i];
+            const float4 g = reinterpret_cast<const float4 *>(a.g_rot)[i];
+            const float nrm = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
+            const float d = fmaxf(nrm, 1e-12f);
+            const float qx = r.x / d, qy = r.y / d, qz = r.z / d, qw = r.w / d;
+            const float qg = qx * g.x + qy * g.y + qz * g.z + qw * g.w;
+            const float inv = (nrm > 1e-12f) ? 1.0f / d : 0.0f;
+            float gr[4] = {(g.x - qx * qg) * inv, (g.y - qy * qg) * inv, (g.z - qz * qg) * inv, (g.w - qw * qg) * inv};
+            float pr[4] = {r.x, r.y, r.z, r.w};
+            if (anch) {
+                const float4 r0 = reinterpret_cast<const float4 *>(a.init_rotation)[i];
+                const float d0[4] = {r.x - r0.x, r.y - r0.y, r.z - r0.z, r.w - r0.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    gr[c] += k.attach_grad[2] * d0[c];
+                    att += k.attach_val[2] * d0[c] * d0[c];
+                }
+            }
+            float4 m4 = reinterpret_cast<float4 *>(a.m_rot)[i], v4 = reinterpret_cast<float4 *>(a.v_rot)[i];
+            float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int c = 0; c < 4; c++) adam_update(pr[c], gr[c], mm[c], vv[c], k, k.step_size[5]);
+            reinterpret_cast<float4 *>(a.rotation)[i] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+            reinterpret_cast<float4 *>(a.m_rot)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+            reinterpret_cast<float4 *>(a.v_rot)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        }
+        { // f_dc: gradient = first coefficient of the merged SH gradient
+            const float *gs = a.g_sh + (size_t)i * a.M * 3;
+            const float g3[3] = {gs[0], gs[1], gs[2]};
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const int e = 3 * i + c;
+                float p = a.f_dc[e], m = a.m_dc[e], v = a.v_dc[e];
+                adam_update(p, g3[c], m, v, k, k.step_size[1]);
+                a.f_dc[e] = p; a.m_dc[e] = m; a.v_dc[e] = v;
+            }
+            if (a.confidence && (fabsf(g3[0]) != 0.f || fabsf(g3[1]) != 0.f || fabsf(g3[2]) != 0.f)) a.confidence[i] += 1.0f;
+        }
     }
+    if (a.init_opacity) block_add(att, a.attach_out);
 }
 
 // Same update with every flat tensor streamed in 128-bit accesses: blocks are split into five roles by index range.
-//   role 0  xyz      [3P]  plain Adam on g_means3D                        float4 chunks of the flat array
-//   role 1  scaling  [3P]  g * exp(x) (the saved activation)              float4 chunks
+//   role 0  xyz      [3P]  Adam on g_means3D (+ attach)                   float4 chunks of the flat array
+//   role 1  scaling  [3P]  g * exp(x) (the saved activation) (+ attach)   float4 chunks
 //   role 2  opacity  [P]   g * o (1 - o)                                  float4 chunks
-//   role 3  rotation [P,4] normalisation backward, one Gaussian per thread (already one float4 per tensor)
+//   role 3  rotation [P,4] normalisation backward (+ attach), one Gaussian per thread (one float4 per tensor)
 //   role 4  f_dc     [P,3] gradient gathered from the merged SH gradient (stride 3M), + confidence bump
 // Requires 16-byte aligned tensors (checked by the caller; adam_geometry_kernel is the fallback).
 struct FlatArgs {
@@ -197,138 +299,179 @@ __device__ __forceinline__ void adam4(float4 &p, const float4 g, float4 &m, floa
     adam_update(p.z, g.z, m.z, v.z, k, ss);
     adam_update(p.w, g.w, m.w, v.w, k, ss);
 }
-// flat Adam over [begin of tail, n) for the (< 4) elements a float4 sweep leaves over
-__device__ __forceinline__ void adam_tail(float *p, float *m, float *v, const float *g, const float *act, int mode,
-                                          long long from, long long n, const AdamScalars &k, float ss, const uint8_t *ever,
-                                          int row_width) {
+// flat Adam over [from, n) for the (< 4) elements a float4 sweep leaves over; returns the attach value of those elements
+__device__ __forceinline__ float adam_tail(float *p, float *m, float *v, const float *g, const float *act, int mode,
+                                           long long from, long long n, const AdamScalars &k, float ss, const uint8_t *ever,
+                                           int row_width, const float *init, const float *init_opacity, int attach_slot) {
+    float att = 0.f;
     for (long long e = from + threadIdx.x; e < n; e += blockDim.x) {
         if (ever && !ever[e / row_width]) continue;
         float gg = g[e];
         if (mode == 1) gg *= act[e];
         if (mode == 2) gg *= act[e] * (1.0f - act[e]);
         float pp = p[e], mm = m[e], vv = v[e];
+        if (init && anchored(init_opacity, e / row_width, k.attach_logit_thr)) {
+            const float d = pp - init[e];
+            gg += k.attach_grad[attach_slot] * d;
+            att += k.attach_val[attach_slot] * d * d;
+        }
         adam_update(pp, gg, mm, vv, k, ss);
         p[e] = pp; m[e] = mm; v[e] = vv;
     }
+    return att;
 }
-// `b` is a virtual block index: with most Gaussians skipped (one flag byte read, nothing else) the kernel is bound by
-// the rate at which blocks can be launched, so every real block walks ADAM_VBLOCKS consecutive virtual blocks.
-constexpr int ADAM_VBLOCKS = 1; // 4 was measured slower (70 vs 40 us): the roles have very different costs
-__device__ __forceinline__ void adam_flat_body(const FlatArgs &fa, unsigned b) {
+// `b` is a virtual block index (one role per block).  Returns this thread's share of the attach value.
+__device__ __forceinline__ float adam_flat_body(const FlatArgs &fa, const AdamScalars &k, unsigned b) {
     const SmallArgs &a = fa.s;
+    float att = 0.f;
     if (b < 2 * fa.nb_vec3) { // roles 0 / 1
         const bool sc = b >= fa.nb_vec3;
         if (sc) b -= fa.nb_vec3;
         float *P_ = sc ? a.scaling : a.xyz, *M_ = sc ? a.m_sc : a.m_xyz, *V_ = sc ? a.v_sc : a.v_xyz;
         const float *G_ = sc ? a.g_scales : a.g_means3D;
-        const float ss = a.k.step_size[sc ? 4 : 0];
+        const float *I_ = a.init_opacity ? (sc ? a.init_scaling : a.init_xyz) : nullptr;
+        const int slot = sc ? 1 : 0;
+        const float ss = k.step_size[sc ? 4 : 0];
         const long long q = (long long)b * blockDim.x + threadIdx.x;
         if (q < fa.n4_vec3) {
-            bool e[4] = {true, true, true, true};
+            const long long ra = (4 * q) / 3, rb = (4 * q + 3) / 3;
+            bool ea = true, eb = true;
             if (a.ever) { // gradients of never-touched Gaussians were not written: neither read nor used
-                const long long ra = (4 * q) / 3, rb = (4 * q + 3) / 3;
-                const bool ea = a.ever[ra] != 0, eb = a.ever[rb] != 0;
-                if (!(ea || eb)) return;
+                ea = a.ever[ra] != 0;
+                eb = a.ever[rb] != 0;
+            }
+            if (ea || eb) {
+                bool e[4], an[4] = {false, false, false, false};
 #pragma unroll
                 for (int c = 0; c < 4; c++) e[c] = ((4 * q + c) / 3 == ra) ? ea : eb;
-            }
-            float4 g = reinterpret_cast<const float4 *>(G_)[q];
-            g.x = e[0] ? g.x : 0.f; g.y = e[1] ? g.y : 0.f; g.z = e[2] ? g.z : 0.f; g.w = e[3] ? g.w : 0.f;
-            float4 m = reinterpret_cast<float4 *>(M_)[q], v = reinterpret_cast<float4 *>(V_)[q];
-            if (!(all_zero(g) && all_zero(m) && all_zero(v))) {
-                if (sc) {
-                    const float4 e = reinterpret_cast<const float4 *>(a.act_scales)[q];
-                    g.x *= e.x; g.y *= e.y; g.z *= e.z; g.w *= e.w;
+                float4 g = reinterpret_cast<const float4 *>(G_)[q];
+                g.x = e[0] ? g.x : 0.f; g.y = e[1] ? g.y : 0.f; g.z = e[2] ? g.z : 0.f; g.w = e[3] ? g.w : 0.f;
+                float4 m = reinterpret_cast<float4 *>(M_)[q], v = reinterpret_cast<float4 *>(V_)[q];
+                bool any_an = false;
+                if (I_) {
+                    const bool aa = ea && anchored(a.init_opacity, ra, k.attach_logit_thr);
+                    const bool ab = eb && (rb == ra ? aa : anchored(a.init_opacity, rb, k.attach_logit_thr));
+#pragma unroll
+                    for (int c = 0; c < 4; c++) an[c] = ((4 * q + c) / 3 == ra) ? aa : ab;
+                    any_an = aa || ab;
                 }
-                float4 p = reinterpret_cast<float4 *>(P_)[q];
-                adam4(p, g, m, v, a.k, ss);
-                reinterpret_cast<float4 *>(P_)[q] = p;
-                reinterpret_cast<float4 *>(M_)[q] = m;
-                reinterpret_cast<float4 *>(V_)[q] = v;
+                // a parameter only leaves its initial value through an update, which leaves non-zero moments behind: with
+                // zero gradient AND zero moments the attach gradient is zero as well
+                if (!(all_zero(g) && all_zero(m) && all_zero(v))) {
+                    if (sc) {
+                        const float4 ex = reinterpret_cast<const float4 *>(a.act_scales)[q];
+                        g.x *= ex.x; g.y *= ex.y; g.z *= ex.z; g.w *= ex.w;
+                    }
+                    float4 p = reinterpret_cast<float4 *>(P_)[q];
+                    if (any_an) {
+                        const float4 p0 = reinterpret_cast<const float4 *>(I_)[q];
+                        const float d[4] = {p.x - p0.x, p.y - p0.y, p.z - p0.z, p.w - p0.w};
+                        float ga[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+                            if (an[c]) {
+                                ga[c] = k.attach_grad[slot] * d[c];
+                                att += k.attach_val[slot] * d[c] * d[c];
+                            }
+                        g.x += ga[0]; g.y += ga[1]; g.z += ga[2]; g.w += ga[3];
+                    }
+                    adam4(p, g, m, v, k, ss);
+                    reinterpret_cast<float4 *>(P_)[q] = p;
+                    reinterpret_cast<float4 *>(M_)[q] = m;
+                    reinterpret_cast<float4 *>(V_)[q] = v;
+                }
             }
         }
-        if (b == 0) adam_tail(P_, M_, V_, G_, a.act_scales, sc ? 1 : 0, fa.n4_vec3 * 4, 3ll * a.P, a.k, ss, a.ever, 3);
-        return;
+        if (b == 0)
+            att += adam_tail(P_, M_, V_, G_, a.act_scales, sc ? 1 : 0, fa.n4_vec3 * 4, 3ll * a.P, k, ss, a.ever, 3, I_,
+                             a.init_opacity, slot);
+        return att;
     }
     b -= 2 * fa.nb_vec3;
     if (b < fa.nb_scalar) { // role 2
-        const float ss = a.k.step_size[3];
+        const float ss = k.step_size[3];
         const long long q = (long long)b * blockDim.x + threadIdx.x;
         if (q < fa.n4_scalar) {
             uint32_t e4 = 0x01010101u;
-            if (a.ever) {
-                e4 = reinterpret_cast<const uint32_t *>(a.ever)[q];
-                if (e4 == 0) return;
-            }
-            float4 g = reinterpret_cast<const float4 *>(a.g_opacity)[q];
-            g.x = (e4 & 0xFFu) ? g.x : 0.f; g.y = (e4 & 0xFF00u) ? g.y : 0.f;
-            g.z = (e4 & 0xFF0000u) ? g.z : 0.f; g.w = (e4 & 0xFF000000u) ? g.w : 0.f;
-            float4 m = reinterpret_cast<float4 *>(a.m_op)[q], v = reinterpret_cast<float4 *>(a.v_op)[q];
-            if (!(all_zero(g) && all_zero(m) && all_zero(v))) {
-                const float4 o = reinterpret_cast<const float4 *>(a.act_opacity)[q];
-                g.x *= o.x * (1.0f - o.x); g.y *= o.y * (1.0f - o.y); g.z *= o.z * (1.0f - o.z); g.w *= o.w * (1.0f - o.w);
-                float4 p = reinterpret_cast<float4 *>(a.opacity)[q];
-                adam4(p, g, m, v, a.k, ss);
-                reinterpret_cast<float4 *>(a.opacity)[q] = p;
-                reinterpret_cast<float4 *>(a.m_op)[q] = m;
-                reinterpret_cast<float4 *>(a.v_op)[q] = v;
+            if (a.ever) e4 = reinterpret_cast<const uint32_t *>(a.ever)[q];
+            if (e4 != 0) {
+                float4 g = reinterpret_cast<const float4 *>(a.g_opacity)[q];
+                g.x = (e4 & 0xFFu) ? g.x : 0.f; g.y = (e4 & 0xFF00u) ? g.y : 0.f;
+                g.z = (e4 & 0xFF0000u) ? g.z : 0.f; g.w = (e4 & 0xFF000000u) ? g.w : 0.f;
+                float4 m = reinterpret_cast<float4 *>(a.m_op)[q], v = reinterpret_cast<float4 *>(a.v_op)[q];
+                if (!(all_zero(g) && all_zero(m) && all_zero(v))) {
+                    const float4 o = reinterpret_cast<const float4 *>(a.act_opacity)[q];
+                    g.x *= o.x * (1.0f - o.x); g.y *= o.y * (1.0f - o.y); g.z *= o.z * (1.0f - o.z); g.w *= o.w * (1.0f - o.w);
+                    float4 p = reinterpret_cast<float4 *>(a.opacity)[q];
+                    adam4(p, g, m, v, k, ss);
+                    reinterpret_cast<float4 *>(a.opacity)[q] = p;
+                    reinterpret_cast<float4 *>(a.m_op)[q] = m;
+                    reinterpret_cast<float4 *>(a.v_op)[q] = v;
+                }
             }
         }
-        if (b == 0) adam_tail(a.opacity, a.m_op, a.v_op, a.g_opacity, a.act_opacity, 2, fa.n4_scalar * 4, a.P, a.k, ss, a.ever, 1);
-        return;
+        if (b == 0)
+            adam_tail(a.opacity, a.m_op, a.v_op, a.g_opacity, a.act_opacity, 2, fa.n4_scalar * 4, a.P, k, ss, a.ever, 1, nullptr,
+                      nullptr, 0);
+        return 0.f;
     }
     b -= fa.nb_scalar;
     const bool dc = b >= fa.nb_gauss;
     if (dc) b -= fa.nb_gauss;
     const int i = (int)(b * blockDim.x + threadIdx.x);
-    if (i >= a.P) return;
-    if (a.ever && !a.ever[i]) return;
+    if (i >= a.P) return 0.f;
+    if (a.ever && !a.ever[i]) return 0.f;
     if (!dc) { // role 3: rotation, q = r / max(|r|, eps); dL/dr = (g - q (q . g)) / max(|r|, eps)
         const float4 g = reinterpret_cast<const float4 *>(a.g_rot)[i];
         float4 m = reinterpret_cast<float4 *>(a.m_rot)[i], v = reinterpret_cast<float4 *>(a.v_rot)[i];
-        if (all_zero(g) && all_zero(m) && all_zero(v)) return; // the normalisation backward of a zero gradient is zero
+        if (all_zero(g) && all_zero(m) && all_zero(v)) return 0.f; // normalisation backward of a zero gradient is zero
         float4 r = reinterpret_cast<float4 *>(a.rotation)[i];
         const float nrm = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
         const float d = fmaxf(nrm, 1e-12f);
         const float qx = r.x / d, qy = r.y / d, qz = r.z / d, qw = r.w / d;
         const float qg = qx * g.x + qy * g.y + qz * g.z + qw * g.w;
         const float inv = (nrm > 1e-12f) ? 1.0f / d : 0.0f;
-        const float4 gr = make_float4((g.x - qx * qg) * inv, (g.y - qy * qg) * inv, (g.z - qz * qg) * inv, (g.w - qw * qg) * inv);
-        adam4(r, gr, m, v, a.k, a.k.step_size[5]);
+        float4 gr = make_float4((g.x - qx * qg) * inv, (g.y - qy * qg) * inv, (g.z - qz * qg) * inv, (g.w - qw * qg) * inv);
+        if (a.init_opacity && anchored(a.init_opacity, i, k.attach_logit_thr)) {
+            const float4 r0 = reinterpret_cast<const float4 *>(a.init_rotation)[i];
+            const float d0[4] = {r.x - r0.x, r.y - r0.y, r.z - r0.z, r.w - r0.w};
+            gr.x += k.attach_grad[2] * d0[0]; gr.y += k.attach_grad[2] * d0[1];
+            gr.z += k.attach_grad[2] * d0[2]; gr.w += k.attach_grad[2] * d0[3];
+            att = k.attach_val[2] * (d0[0] * d0[0] + d0[1] * d0[1] + d0[2] * d0[2] + d0[3] * d0[3]);
+        }
+        adam4(r, gr, m, v, k, k.step_size[5]);
         reinterpret_cast<float4 *>(a.rotation)[i] = r;
         reinterpret_cast<float4 *>(a.m_rot)[i] = m;
         reinterpret_cast<float4 *>(a.v_rot)[i] = v;
-    } else { // role 4: f_dc (first coefficient of the merged SH gradient) + confidence
-        const float *gs = a.g_sh + (size_t)i * a.M * 3;
-        const float g3[3] = {gs[0], gs[1], gs[2]};
-        float m3[3], v3[3];
-        bool zero = true;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            m3[c] = a.m_dc[3 * i + c];
-            v3[c] = a.v_dc[3 * i + c];
-            zero &= (g3[c] == 0.f && m3[c] == 0.f && v3[c] == 0.f);
-        }
-        if (zero) return; // also no confidence bump: every f_dc gradient is zero
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const int e = 3 * i + c;
-            float p = a.f_dc[e];
-            adam_update(p, g3[c], m3[c], v3[c], a.k, a.k.step_size[1]);
-            a.f_dc[e] = p; a.m_dc[e] = m3[c]; a.v_dc[e] = v3[c];
-        }
-        if (a.confidence && (fabsf(g3[0]) != 0.f || fabsf(g3[1]) != 0.f || fabsf(g3[2]) != 0.f)) a.confidence[i] += 1.0f;
+        return att;
     }
+    // role 4: f_dc (first coefficient of the merged SH gradient) + confidence
+    const float *gs = a.g_sh + (size_t)i * a.M * 3;
+    const float g3[3] = {gs[0], gs[1], gs[2]};
+    float m3[3], v3[3];
+    bool zero = true;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        m3[c] = a.m_dc[3 * i + c];
+        v3[c] = a.v_dc[3 * i + c];
+        zero &= (g3[c] == 0.f && m3[c] == 0.f && v3[c] == 0.f);
+    }
+    if (zero) return 0.f; // also no confidence bump: every f_dc gradient is zero
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int e = 3 * i + c;
+        float p = a.f_dc[e];
+        adam_update(p, g3[c], m3[c], v3[c], k, k.step_size[1]);
+        a.f_dc[e] = p; a.m_dc[e] = m3[c]; a.v_dc[e] = v3[c];
+    }
+    if (a.confidence && (fabsf(g3[0]) != 0.f || fabsf(g3[1]) != 0.f || fabsf(g3[2]) != 0.f)) a.confidence[i] += 1.0f;
+    return 0.f;
 }
 __global__ void __launch_bounds__(256) adam_flat_kernel(FlatArgs fa) {
-    if (fa.s.status[DQO_ST_OVERFLOW]) return;
-    const unsigned total = 2 * fa.nb_vec3 + fa.nb_scalar + 2 * fa.nb_gauss;
-#pragma unroll 1
-    for (int k = 0; k < ADAM_VBLOCKS; k++) {
-        const unsigned b = blockIdx.x * ADAM_VBLOCKS + k;
-        if (b >= total) return;
-        adam_flat_body(fa, b);
-    }
+    const AdamScalars k = *fa.s.kd;
+    if (k.skip) return;
+    const float att = adam_flat_body(fa, k, blockIdx.x);
+    if (fa.s.init_opacity) block_add(att, fa.s.attach_out);
 }
 
 // Adam for f_rest [P,45]: 128-bit accesses on the parameter and its two moments (6 of the 7 streams), the gradient is
@@ -338,12 +481,11 @@ struct RestAdamArgs {
     float *f_rest, *m_rest, *v_rest;
     const float *g_sh;
     const uint8_t *ever;
-    const int *status;
-    AdamScalars k;
+    const AdamScalars *kd;
 };
-constexpr int ADAM_REST_CHUNKS = 8; // float4 chunks per thread (see ADAM_VBLOCKS)
+constexpr int ADAM_REST_CHUNKS = 8; // float4 chunks per thread: most are skipped after reading one flag byte
 template <typename IndexT>
-__device__ __forceinline__ void adam_rest_body(const RestAdamArgs &a, IndexT q) {
+__device__ __forceinline__ void adam_rest_body(const RestAdamArgs &a, const AdamScalars &k, IndexT q) {
     const IndexT e0 = q * 4;
     bool ea = true, eb = true;
     const IndexT ra = e0 / 45;
@@ -368,37 +510,39 @@ __device__ __forceinline__ void adam_rest_body(const RestAdamArgs &a, IndexT q) 
         v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f)
         return;
     float4 p = reinterpret_cast<float4 *>(a.f_rest)[q];
-    const float ss = a.k.step_size[2];
-    adam_update(p.x, g[0], m.x, v.x, a.k, ss);
-    adam_update(p.y, g[1], m.y, v.y, a.k, ss);
-    adam_update(p.z, g[2], m.z, v.z, a.k, ss);
-    adam_update(p.w, g[3], m.w, v.w, a.k, ss);
+    const float ss = k.step_size[2];
+    adam_update(p.x, g[0], m.x, v.x, k, ss);
+    adam_update(p.y, g[1], m.y, v.y, k, ss);
+    adam_update(p.z, g[2], m.z, v.z, k, ss);
+    adam_update(p.w, g[3], m.w, v.w, k, ss);
     reinterpret_cast<float4 *>(a.f_rest)[q] = p;
     reinterpret_cast<float4 *>(a.m_rest)[q] = m;
     reinterpret_cast<float4 *>(a.v_rest)[q] = v;
 }
 __global__ void __launch_bounds__(256) adam_rest_kernel(RestAdamArgs a) {
-    if (a.status[DQO_ST_OVERFLOW]) return;
+    const AdamScalars k = *a.kd;
+    if (k.skip) return;
     const long long base = (long long)blockIdx.x * (256 * ADAM_REST_CHUNKS) + threadIdx.x;
     const bool small = a.n4 * 4 < (1ll << 31); // 32-bit index arithmetic (the / 45 is the hot instruction of a skipped chunk)
 #pragma unroll 1
-    for (int k = 0; k < ADAM_REST_CHUNKS; k++) {
-        const long long q = base + (long long)k * 256;
+    for (int c = 0; c < ADAM_REST_CHUNKS; c++) {
+        const long long q = base + (long long)c * 256;
         if (q >= a.n4) return;
         if (small)
-            adam_rest_body<unsigned>(a, (unsigned)q);
+            adam_rest_body<unsigned>(a, k, (unsigned)q);
         else
-            adam_rest_body<long long>(a, q);
+            adam_rest_body<long long>(a, k, q);
     }
 }
 __global__ void adam_rest_tail_kernel(long long begin, long long end, RestAdamArgs a) {
     const long long e = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= end || a.status[DQO_ST_OVERFLOW]) return;
+    const AdamScalars k = *a.kd;
+    if (e >= end || k.skip) return;
     const long long row = e / 45;
     if (a.ever && !a.ever[row]) return;
     const int col = (int)(e - row * 45);
     float p = a.f_rest[e], m = a.m_rest[e], v = a.v_rest[e];
-    adam_update(p, a.g_sh[row * 48 + 3 + col], m, v, a.k, a.k.step_size[2]);
+    adam_update(p, a.g_sh[row * 48 + 3 + col], m, v, k, k.step_size[2]);
     a.f_rest[e] = p; a.m_rest[e] = m; a.v_rest[e] = v;
 }
 
@@ -416,10 +560,11 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
                                 double beta1, double beta2, double eps, void *workspace, int64_t capacity,
                                 float *loss_out, int32_t *counts_out, int32_t *status, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!s || !p || !kf || !workspace || !loss_out || !counts_out || !status || step < 1 || s->P <= 0) {
+    if (!s || !p || !kf || !workspace || !loss_out || !counts_out || !status || (step < 1 && !p->step_state) || s->P <= 0) {
         set_error("dqo_mapping_step: invalid argument");
         return DQO_ERR_INVALID_ARG;
     }
+    nvtx_push("dqo_mapping_step");
     if (!(s->M == 16 || s->M == 1)) {
         set_error("dqo_mapping_step supports M == 16 (SH degree 3 storage) or M == 1");
         return DQO_ERR_INVALID_ARG;
@@ -461,22 +606,40 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
                             g_rot, p->ever, stream_);
     if (rc) return rc;
 
-    AdamScalars k;
-    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
-    k.beta1 = (float)beta1; k.beta2 = (float)beta2; k.omb1 = (float)(1.0 - beta1); k.omb2 = (float)(1.0 - beta2);
-    k.bc2_sqrt = (float)sqrt(bc2); k.eps = (float)eps;
-    for (int t = 0; t < 6; t++) k.step_size[t] = (float)(p->lr[t] / bc1);
+    // step number, bias corrections, attach scales and the overflow decision: one thread on the device
+    AdamScalars *kd = (AdamScalars *)(ws + L.adam);
+    const bool attach = p->init_opacity != nullptr;
+    if (attach && (!p->init_xyz || !p->init_scaling || !p->init_rotation || !p->attach_count)) {
+        set_error("dqo_mapping_step: the attach term needs init_xyz / init_scaling / init_rotation / init_opacity and attach_count");
+        return DQO_ERR_INVALID_ARG;
+    }
+    {
+        PrepareArgs pa;
+        pa.status = status; pa.step_state = p->step_state; pa.host_step = step;
+        pa.beta1 = beta1; pa.beta2 = beta2; pa.eps = eps;
+        for (int t = 0; t < 6; t++) pa.lr[t] = p->lr[t];
+        pa.attach_weight = attach ? (double)p->attach_weight : 0.0;
+        pa.attach_thr = p->attach_opacity_thres;
+        pa.attach_count = attach ? p->attach_count : nullptr;
+        pa.out = kd;
+        adam_prepare_kernel<<<1, 32, 0, stream>>>(pa);
+        DQO_LAUNCH_CHECK("adam prepare", s->debug, stream);
+    }
     SmallArgs sa;
     sa.P = P; sa.M = M; sa.xyz = xyz; sa.opacity = p->param[3]; sa.scaling = p->param[4]; sa.rotation = p->param[5];
     sa.f_dc = f_dc; sa.m_dc = p->exp_avg[1]; sa.v_dc = p->exp_avg_sq[1];
     sa.m_xyz = p->exp_avg[0]; sa.v_xyz = p->exp_avg_sq[0]; sa.m_op = p->exp_avg[3]; sa.v_op = p->exp_avg_sq[3];
     sa.m_sc = p->exp_avg[4]; sa.v_sc = p->exp_avg_sq[4]; sa.m_rot = p->exp_avg[5]; sa.v_rot = p->exp_avg_sq[5];
     sa.act_opacity = act_op; sa.act_scales = act_sc; sa.g_means3D = g_means3D; sa.g_opacity = g_op; sa.g_scales = g_sc;
-    sa.g_rot = g_rot; sa.g_sh = g_sh; sa.confidence = p->confidence; sa.ever = p->ever; sa.status = status; sa.k = k;
+    sa.g_rot = g_rot; sa.g_sh = g_sh; sa.confidence = p->confidence; sa.ever = p->ever; sa.kd = kd;
+    sa.init_xyz = attach ? p->init_xyz : nullptr; sa.init_scaling = attach ? p->init_scaling : nullptr;
+    sa.init_rotation = attach ? p->init_rotation : nullptr; sa.init_opacity = attach ? p->init_opacity : nullptr;
+    sa.attach_out = loss_out + 3;
     bool aligned = true;
     {
         const void *ptrs[] = {sa.xyz, sa.m_xyz, sa.v_xyz, sa.scaling, sa.m_sc, sa.v_sc, sa.opacity, sa.m_op, sa.v_op,
-                              sa.rotation, sa.m_rot, sa.v_rot, g_means3D, g_sc, g_op, g_rot, act_op, act_sc};
+                              sa.rotation, sa.m_rot, sa.v_rot, g_means3D, g_sc, g_op, g_rot, act_op, act_sc,
+                              sa.init_xyz, sa.init_scaling, sa.init_rotation};
         for (const void *q : ptrs) aligned &= ((uintptr_t)q % 16 == 0);
         aligned &= ((uintptr_t)p->ever % 4 == 0);
     }
@@ -491,7 +654,7 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
         if (fa.nb_scalar == 0) fa.nb_scalar = 1;
         fa.nb_gauss = (unsigned)nb;
         const unsigned vblocks = 2 * fa.nb_vec3 + fa.nb_scalar + 2 * fa.nb_gauss;
-        adam_flat_kernel<<<(vblocks + ADAM_VBLOCKS - 1) / ADAM_VBLOCKS, 256, 0, stream>>>(fa);
+        adam_flat_kernel<<<vblocks, 256, 0, stream>>>(fa);
     } else {
         adam_geometry_kernel<<<nb, 256, 0, stream>>>(sa);
     }
@@ -499,12 +662,29 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
     if (M == 16) {
         RestAdamArgs ra;
         const long long total = (long long)P * 45;
-        ra.n4 = total / 4; ra.f_rest = f_rest; ra.m_rest = p->exp_avg[2]; ra.v_rest = p->exp_avg_sq[2]; ra.g_sh = g_sh; ra.ever = p->ever; ra.status = status; ra.k = k;
+        ra.n4 = total / 4; ra.f_rest = f_rest; ra.m_rest = p->exp_avg[2]; ra.v_rest = p->exp_avg_sq[2]; ra.g_sh = g_sh;
+        ra.ever = p->ever; ra.kd = kd;
         if (ra.n4 > 0)
             adam_rest_kernel<<<(unsigned)((ra.n4 + 256 * ADAM_REST_CHUNKS - 1) / (256 * ADAM_REST_CHUNKS)), 256, 0, stream>>>(ra);
         if (total % 4) adam_rest_tail_kernel<<<1, 32, 0, stream>>>(ra.n4 * 4, total, ra);
         DQO_LAUNCH_CHECK("adam f_rest", s->debug, stream);
     }
+    nvtx_pop();
+    return DQO_OK;
+}
+
+// Number of Gaussians the attach term anchors (sigmoid(init_opacity) < thres), counted once per optimisation window
+// (the reference recomputes `attach_mask.sum()` every iteration from the same init_stat: mapper.py:810-812).
+extern "C" int dqo_attach_count(int32_t P, const float *init_opacity, float opacity_thres, int32_t *count, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (P < 0 || !count || (P > 0 && !init_opacity)) {
+        set_error("dqo_attach_count: invalid argument");
+        return DQO_ERR_INVALID_ARG;
+    }
+    DQO_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), stream));
+    if (P == 0) return DQO_OK;
+    attach_count_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, init_opacity, opacity_thres, count);
+    DQO_LAUNCH_CHECK("attach count", 0, stream);
     return DQO_OK;
 }
 

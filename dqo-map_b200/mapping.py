@@ -159,14 +159,22 @@ class MappingStep:
 
 
 class FusedMappingStep:
-    """The same iteration as `MappingStep`, enqueued by ONE C-ABI call (`dqo_mapping_step`) with no host
-    synchronisation: activations, rasterize forward, masked L1 loss, backward, activation backward and Adam all run
-    inside the library on the raw parameter tensors, which are updated in place (opt-in).
+    """The iteration of `Mapping.local_optimize` (mapper.py:568-599 + loss_update :799-928) enqueued by ONE C-ABI call
+    (`dqo_mapping_step`) with no host synchronisation: activations, rasterize forward, masked L1 colour + depth loss,
+    backward, activation backward, the attach term and Adam all run inside the library on the raw parameter tensors,
+    which are updated in place (opt-in).
+
+    Loss terms: masked L1 colour, masked L1 depth and -- after `begin_window(attach=True)` -- the attach term
+    (mapper.py:810-829).  NOT covered: the SSIM term of the mask-less final global pass (:841), the normal term (weight 0
+    in every shipped config) and the semantic / instance colour terms (:876-903); use `MappingStep` (operator path,
+    differentiable torch tensors) for those configurations.
 
     params: dict of raw contiguous float32 CUDA tensors xyz [P,3], f_dc [P,1,3], f_rest [P,M-1,3], opacity [P,1],
-    scaling [P,3], rotation [P,4] (the tensors of GaussianPointCloud.parametrize); lrs: dict name -> lr.
-    `__call__` returns device tensors (total, colour, depth loss); reading them is the only synchronisation.
-    `check()` raises if the instance capacity was exceeded in the last step."""
+    scaling [P,3], rotation [P,4] (the tensors of GaussianPointCloud.parametrize); lrs: dict name -> lr (re-read on
+    every call).  `__call__` returns device tensors (total, colour, depth loss); reading them is the only
+    synchronisation.  The Adam step number lives on the device; `check()` reports how many steps the device skipped
+    since the last check (instance overflow) -- the counter is sticky, so checking once after a window is enough.
+    `graph(...)` captures the step of one keyframe into a CUDA graph (one launch per iteration instead of ~45)."""
 
     ORDER = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")
 
@@ -186,7 +194,7 @@ class FusedMappingStep:
         if self.M not in (1, 16):
             raise ValueError("FusedMappingStep supports SH storage of 1 or 16 coefficients per channel")
         self.W, self.H = int(width), int(height)
-        self.lrs = [float(lrs[k]) for k in self.ORDER]
+        self.lrs = lrs
         self.betas, self.eps = betas, eps
         self.cw, self.dw, self.thr = float(color_weight), float(depth_weight), float(depth_err_thres)
         self.confidence = confidence
@@ -195,8 +203,12 @@ class FusedMappingStep:
         # one byte per Gaussian: has it ever received a non-zero gradient?  (zero-initialised with the moments; Gaussians
         # that never have are skipped by the backward's gradient writes and by the optimiser, see dqo_map_params.ever)
         self.ever = torch.zeros(self.P, dtype=torch.uint8, device=self.dev)
+        # [0] Adam steps taken, [1] steps skipped by the device (overflow), sticky until check()
+        self.step_state = torch.zeros(4, dtype=torch.int32, device=self.dev)
+        self.init = None            # attach reference (history_stat of local_optimize), see begin_window
+        self.attach_count = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.attach_weight, self.attach_thres = 1000.0, 0.9
         self._kf_cache = {}
-        self.step = 0
         self.capacity = int(capacity) if capacity else max(8 * self.P, 1 << 16)
         self._alloc()
         self.loss = torch.zeros(4, dtype=torch.float32, device=self.dev)
@@ -204,18 +216,59 @@ class FusedMappingStep:
         self.counts = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.status = torch.zeros(_lib.ST_WORDS, dtype=torch.int32, device=self.dev)
 
+    @property
+    def step(self):
+        """Adam steps taken so far (device counter; one host synchronisation)."""
+        return int(self.step_state[0].item())
+
+    def begin_window(self, attach=True, attach_weight=1000.0, opacity_thres=0.9):
+        """Start of an optimisation window, as `Mapping.local_optimize` does it (mapper.py:531-548): a fresh Adam (zero
+        moments, step 0) and, with attach=True, `history_stat` = the current raw parameters as the anchor of the attach
+        term for Gaussians whose initial opacity is below `opacity_thres` (mapper.py:810-829)."""
+        for m, v in self.state.values():
+            m.zero_()
+            v.zero_()
+        self.ever.zero_()
+        self.step_state.zero_()
+        self._mp_key = None
+        if not attach:
+            self.init = None
+            return
+        self.init = {k: self.p[k].detach().clone() for k in ("xyz", "scaling", "rotation", "opacity")}
+        self.attach_weight, self.attach_thres = float(attach_weight), float(opacity_thres)
+        with torch.cuda.device(self.dev):
+            check(lib().dqo_attach_count(self.P, ptr(self.init["opacity"]), self.attach_thres, ptr(self.attach_count),
+                                         _stream()), "dqo_attach_count")
+
+    def attach_loss(self):
+        """Value of the attach term at the parameters the last step started from (device scalar; the reference reports it
+        as `scale_loss`, mapper.py:919)."""
+        return self.loss[3]
+
     def _map_params(self):
-        """ctypes view of the parameter / moment tensors; rebuilt only when a tensor was replaced (pointer changed)."""
-        key = tuple(self.p[k].data_ptr() for k in self.ORDER) + (self.confidence.data_ptr() if self.confidence is not None else 0,)
+        """ctypes view of the parameter / moment tensors; rebuilt when a tensor was replaced or a learning rate changed."""
+        lrs = tuple(float(self.lrs[k]) for k in self.ORDER)
+        key = tuple(self.p[k].data_ptr() for k in self.ORDER) + lrs + (
+            self.confidence.data_ptr() if self.confidence is not None else 0,
+            self.init["xyz"].data_ptr() if self.init is not None else 0, self.attach_weight, self.attach_thres)
         if getattr(self, "_mp_key", None) != key:
+            for k in self.ORDER:
+                if not self.p[k].is_contiguous():
+                    raise ValueError("FusedMappingStep expects contiguous parameters (%s)" % k)
             mp = _lib.MapParams()
             for i, k in enumerate(self.ORDER):
                 mp.param[i] = ptr(self.p[k])
                 mp.exp_avg[i] = ptr(self.state[k][0])
                 mp.exp_avg_sq[i] = ptr(self.state[k][1])
-                mp.lr[i] = self.lrs[i]
+                mp.lr[i] = lrs[i]
             mp.confidence = ptr(self.confidence)
             mp.ever = ptr(self.ever)
+            if self.init is not None:
+                mp.init_xyz, mp.init_scaling = ptr(self.init["xyz"]), ptr(self.init["scaling"])
+                mp.init_rotation, mp.init_opacity = ptr(self.init["rotation"]), ptr(self.init["opacity"])
+                mp.attach_count = ptr(self.attach_count)
+            mp.attach_weight, mp.attach_opacity_thres = self.attach_weight, self.attach_thres
+            mp.step_state = ptr(self.step_state)
             self._mp, self._mp_key = mp, key
         return self._mp
 
@@ -225,34 +278,41 @@ class FusedMappingStep:
             raise _lib.DqoError("workspace size query failed: %s" % lib().dqo_last_error().decode())
         self.ws = torch.empty((n,), dtype=torch.uint8, device=self.dev)
 
-    def __call__(self, rs, tile_mask, gt_color, gt_depth, render_mask=None):
-        """rs: GaussianRasterizationSettings of the keyframe (as built by SLAM/render.py:142-162)."""
+    def _keyframe(self, rs, tile_mask, gt_color, gt_depth, render_mask):
         from .rasterizer import _make_settings
-        mp = self._map_params()
         # the ctypes views of a keyframe (settings + pointers) are cached per keyframe: a mapping window revisits the
-        # same few keyframes, and building the structs costs more host time than launching the step
+        # same few keyframes, and building the structs costs more host time than launching the step.  Inputs must be
+        # contiguous (no hidden copies that an in-place update of the source would miss).
         key = (id(rs), tile_mask.data_ptr(), gt_color.data_ptr(), gt_depth.data_ptr(),
-               render_mask.data_ptr() if render_mask is not None else 0, self.front, self.back, self.need_n_touched)
+               render_mask.data_ptr() if render_mask is not None else 0, self.front, self.back, self.need_n_touched,
+               self.cw, self.dw, self.thr)
         hit = self._kf_cache.get(key)
         if hit is None:
-            mask = None
-            if render_mask is not None:
-                mask = render_mask if render_mask.dtype == torch.uint8 else render_mask.view(torch.uint8) \
-                    if render_mask.dtype == torch.bool else (render_mask != 0).view(torch.uint8)
-                mask = mask.contiguous()
-            tensors = (gt_color.contiguous(), gt_depth.contiguous(), mask, tile_mask.contiguous(), rs)  # kept alive
-            kf = _lib.Keyframe(ptr(tensors[0]), ptr(tensors[1]), ptr(mask), ptr(tensors[3]), ptr(rs.viewmatrix),
+            mask = render_mask
+            if mask is not None and mask.dtype == torch.bool:
+                mask = mask.view(torch.uint8)
+            for name, t in (("gt_color", gt_color), ("gt_depth", gt_depth), ("render_mask", mask), ("tile_mask", tile_mask)):
+                if t is not None and not t.is_contiguous():
+                    raise ValueError("FusedMappingStep expects a contiguous %s" % name)
+            if mask is not None and mask.dtype != torch.uint8:
+                raise TypeError("render_mask must be a bool or uint8 tensor")
+            tensors = (gt_color, gt_depth, mask, tile_mask, rs)  # kept alive with the cache entry
+            kf = _lib.Keyframe(ptr(gt_color), ptr(gt_depth), ptr(mask), ptr(tile_mask), ptr(rs.viewmatrix),
                                ptr(rs.projmatrix), ptr(rs.campos), ptr(rs.bg), self.cw, self.dw, self.thr)
             s = _make_settings(self.P, int(rs.sh_degree), self.M, self.W, self.H, rs.tanfovx, rs.tanfovy, rs.cx, rs.cy,
                                rs.scale_modifier, rs.color_sigma, rs.opaque_threshold, rs.depth_threshold,
                                rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, self.need_n_touched,
                                self.front, self.back)
-            if len(self._kf_cache) >= 64:
+            if len(self._kf_cache) >= 256:
                 self._kf_cache.clear()
             hit = self._kf_cache[key] = (s, kf, tensors)
-        s, kf = hit[0], hit[1]
-        self.step += 1
-        args = (s, mp, kf, self.step, float(self.betas[0]), float(self.betas[1]), float(self.eps), ptr(self.ws),
+        return hit[0], hit[1]
+
+    def __call__(self, rs, tile_mask, gt_color, gt_depth, render_mask=None):
+        """rs: GaussianRasterizationSettings of the keyframe (as built by SLAM/render.py:142-162)."""
+        mp = self._map_params()
+        s, kf = self._keyframe(rs, tile_mask, gt_color, gt_depth, render_mask)
+        args = (s, mp, kf, 0, float(self.betas[0]), float(self.betas[1]), float(self.eps), ptr(self.ws),
                 self.capacity, ptr(self.loss), ptr(self.counts), ptr(self.status))
         if torch.cuda.current_device() == self.dev.index:  # the common case: no device switch on the hot path
             check(lib().dqo_mapping_step(*args, _stream()), "dqo_mapping_step")
@@ -261,28 +321,48 @@ class FusedMappingStep:
                 check(lib().dqo_mapping_step(*args, _stream()), "dqo_mapping_step")
         return self._loss_views
 
+    def graph(self, rs, tile_mask, gt_color, gt_depth, render_mask=None, warmup=True):
+        """CUDA graph of this keyframe's step: `g = step.graph(...); g.replay()` runs one iteration with a single launch.
+        Possible because nothing in the step depends on a host value that changes between iterations (the Adam step
+        number is a device counter).  The tensors of the keyframe and the parameters must stay where they are; learning
+        rates and loss weights are frozen into the graph (re-capture after changing them).  With warmup=True one real
+        step is taken first (on the current stream) so that lazily created resources exist before the capture."""
+        if warmup:
+            self(rs, tile_mask, gt_color, gt_depth, render_mask)
+            torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="relaxed"):
+            self(rs, tile_mask, gt_color, gt_depth, render_mask)
+        return g
+
     def check(self, auto_resize=False):
-        """Reads the device status words (one host synchronisation).  On an instance overflow the device skipped the
-        update of that step; by default this raises, with auto_resize=True the workspace is re-allocated large enough for
-        what the device reported and None is returned: repeat the step."""
+        """Reads the device status words and the step counters (one host synchronisation).  Every step whose forward
+        overflowed the instance capacity was skipped on the device (parameters, moments and the Adam step number
+        untouched) and counted; the count is sticky until this call, so a window can be checked once at its end.  By
+        default a non-zero count raises; with auto_resize=True the workspace is re-allocated large enough for what the
+        device last reported and the number of skipped steps is returned: repeat them.  Returns the status words
+        (list) when nothing was skipped."""
         host = self.status.tolist()
-        if host[_lib.ST_OVERFLOW]:
-            self.step -= 1  # the device skipped the update: the step did not happen
+        skipped = int(self.step_state[1].item())
+        if skipped:
+            self.step_state[1] = 0
             if auto_resize:
                 if self.front:
-                    back = int(host[_lib.ST_R_BACK] * 1.5) + 65536
+                    back = max(self.back * 2, int(host[_lib.ST_R_BACK] * 1.5) + 65536)
                     self.resize(self.front + back, self.front, back)
                 else:
-                    self.resize(int(host[_lib.ST_NUM_RENDERED] * 1.3) + 4096)
-                return None
-            raise _lib.DqoError("instance capacity exceeded (capacity %d, front %d, back %d; R = %d, back needs %d): the "
-                                "step was skipped on the device, repeat it with larger buffers"
-                                % (self.capacity, self.front, self.back, host[_lib.ST_NUM_RENDERED], host[_lib.ST_R_BACK]))
+                    self.resize(max(self.capacity * 2, int(host[_lib.ST_NUM_RENDERED] * 1.3) + 4096))
+                return skipped
+            raise _lib.DqoError("instance capacity exceeded in %d step(s) (capacity %d, front %d, back %d; last R = %d, back "
+                                "needs %d): those steps were skipped on the device, repeat them with larger buffers"
+                                % (skipped, self.capacity, self.front, self.back, host[_lib.ST_NUM_RENDERED],
+                                   host[_lib.ST_R_BACK]))
         return host
 
     def resize(self, capacity, front_instances=None, back_instances=None):
-        """Re-allocates the step workspace for a larger instance capacity (after check() reported an overflow); the
-        parameters, the Adam state and the step counter are untouched, so the skipped step can simply be repeated."""
+        """Re-allocates the step workspace for a larger instance capacity (after check() reported skipped steps); the
+        parameters, the Adam state and the step counter are untouched, so the skipped steps can simply be repeated.
+        Graphs captured before the resize are stale."""
         self.capacity = int(capacity)
         if front_instances is not None:
             self.front, self.back = int(front_instances), int(back_instances or 0)

@@ -334,7 +334,9 @@ int dqo_adam_step(const dqo_adam_tensor *tensors /* host array */, int32_t n_ten
 /* ------------------------------------------------------------------------------------------------
  * Fused mapping iteration (opt-in).  One call enqueues, on one stream and without any host
  * synchronisation, what one iteration of Mapping.local_optimize does (SLAM/multiprocess/mapper.py:568-599 and
- * loss_update :799-928 without the attach term): activations of the RAW parameters (exp / sigmoid / normalize,
+ * loss_update :799-928: masked L1 colour + depth loss and the attach term; NOT the SSIM term of the mask-less final global
+ * pass :841, the normal term (weight 0 in every shipped config) or the semantic / instance colour terms :876-903 -- callers
+ * that need those use the operator path, whose outputs are differentiable torch tensors): activations of the RAW parameters (exp / sigmoid / normalize,
  * SLAM/gaussian_pointcloud.py:20-30, 724-826; the torch.cat of f_dc / f_rest is never materialised), rasterize
  * forward, masked L1 colour + depth loss, rasterize backward, activation backward and Adam (eps / betas / lrs as in
  * GaussianPointCloud.parametrize :331-378) on the raw parameters in place, plus the confidence bump (:909-910).
@@ -352,6 +354,19 @@ typedef struct dqo_map_params {
      * nor read by the optimiser.  Owned by the caller, zero-initialised TOGETHER WITH the moments (set to 1 wherever moments
      * are restored non-zero). */
     uint8_t *ever;
+    /* Attach term of loss_update (mapper.py:810-829): Gaussians whose INITIAL opacity sigmoid(init_opacity) is below
+     * attach_opacity_thres (0.9) are anchored to their initial raw xyz / scaling / rotation by
+     * attach_weight (1000) * (mse + mse + mse); the gradient is added to the rasterizer's before Adam, the value lands in
+     * loss_out[3] (the reference's "scale_loss" report).  init_* are the history_stat tensors of local_optimize
+     * (mapper.py:535-545); attach_count is a device int written by dqo_attach_count.  init_opacity == NULL disables it. */
+    const float *init_xyz, *init_scaling, *init_rotation, *init_opacity;
+    const int32_t *attach_count;
+    float attach_weight, attach_opacity_thres;
+    /* device int32[4] or NULL.  [0] = Adam steps taken so far (the bias corrections use [0] + 1), [1] = steps SKIPPED because
+     * the forward overflowed its instance capacity; both are maintained on the device, so the call has no per-step host
+     * argument (CUDA-graph replayable) and a skipped step can neither be missed (sticky until the caller clears [1]) nor
+     * advance the bias correction.  NULL: the `step` argument is used and nothing is counted. */
+    int32_t *step_state;
 } dqo_map_params;
 typedef struct dqo_keyframe {
     const float *gt_color;      /* [H,W,3] */
@@ -362,13 +377,15 @@ typedef struct dqo_keyframe {
     float color_weight, depth_weight, depth_err_thres;
 } dqo_keyframe;
 size_t dqo_mapping_step_workspace_bytes(int32_t P, int32_t M, int32_t W, int32_t H, int64_t instance_capacity);
-/* loss_out: device float[4] {total, colour, depth, -}; counts_out: device int32[2]; status: device int32[DQO_ST_WORDS]
+/* loss_out: device float[4] {total, colour, depth, attach}; counts_out: device int32[2]; status: device int32[DQO_ST_WORDS]
  * (check DQO_ST_OVERFLOW together with the loss read-back; on overflow the render is invalid and the Adam update is
  * skipped on the device -- parameters and moments are untouched, repeat the step with a larger capacity and the same
  * `step` number: see mapping.FusedMappingStep.check). */
 int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params *p, const dqo_keyframe *kf, int32_t step,
                      double beta1, double beta2, double eps, void *workspace, int64_t instance_capacity,
                      float *loss_out, int32_t *counts_out, int32_t *status, void *stream);
+/* attach_count = number of Gaussians with sigmoid(init_opacity) < opacity_thres (device int; mapper.py:810-812). */
+int dqo_attach_count(int32_t P, const float *init_opacity, float opacity_thres, int32_t *count, void *stream);
 /* Device pointers of the images rendered by the last step inside `workspace` (any output may be NULL). */
 int dqo_mapping_step_outputs(int32_t P, int32_t M, int32_t W, int32_t H, int64_t instance_capacity, void *workspace,
                              float **color, float **depth, int32_t **hit_depth, float **T_map);

@@ -167,26 +167,187 @@ def test_fused_c_step_two_phase_binning_and_overflow_skip():
 
     before = {k: v.clone() for k, v in params.items()}
     moments = {k: (m.clone(), v.clone()) for k, (m, v) in step.state.items()}
-    if host[_lib.ST_R_BACK] > 512:
-        step.set_binning(front, 256)
+    assert host[_lib.ST_R_BACK] > 512, "scene must leave unfinished tiles for the overflow half of this test"
+    step.set_binning(front, 256)
+    for _ in range(3):   # three overflowing steps in a row: all skipped, all counted (sticky counter)
         step(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
-        with pytest.raises(_lib.DqoError):
-            step.check()
-        assert step.step == 1
-        for k in params:
-            assert torch.equal(params[k], before[k]), k
-            assert torch.equal(step.state[k][0], moments[k][0]) and torch.equal(step.state[k][1], moments[k][1])
-        # recover: check(auto_resize=True) re-allocates for what the device reported; the skipped step is repeated and
-        # equals a clean second step
-        step.set_binning(front, 256)
-        step(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
-        assert step.check(auto_resize=True) is None and step.back >= host[_lib.ST_R_BACK]
-        step(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
-        assert step.check(auto_resize=True) is not None
-        assert step.step == 2
+    with pytest.raises(_lib.DqoError, match="3 step"):
+        step.check()
+    assert step.step == 1
+    for k in params:
+        assert torch.equal(params[k], before[k]), k
+        assert torch.equal(step.state[k][0], moments[k][0]) and torch.equal(step.state[k][1], moments[k][1])
+    # an overflow followed by steps that fit is still reported (the status words of the last step alone would hide it)
+    step.set_binning(front, 256)
+    step(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
+    step.set_binning(front, R + 1024)
+    step(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
+    assert step.step == 2
+    with pytest.raises(_lib.DqoError, match="1 step"):
+        step.check()
+    assert isinstance(step.check(), list)   # the counter was cleared by the failing check
+    # recover: check(auto_resize=True) re-allocates for what the device reported; the skipped step is repeated and the
+    # bias correction continues at the right step number
+    step.set_binning(front, 256)
+    step(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
+    assert step.check(auto_resize=True) == 1 and step.back >= host[_lib.ST_R_BACK]
+    step(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
+    assert isinstance(step.check(auto_resize=True), list)
+    assert step.step == 3
+    for _ in range(2):
         step_1(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
-        step_1.check()
-        assert abs(float(step.loss[0]) - float(step_1.loss[0])) <= 1e-5 * max(1.0, abs(float(step_1.loss[0])))
+    step_1.check()
+    assert abs(float(step.loss[0]) - float(step_1.loss[0])) <= 2e-4 * max(1.0, abs(float(step_1.loss[0])))
+
+
+def _torch_attach_reference(raw, init, settings, tile_mask, gt_color, gt_depth, render_mask, iters, Rast=None, Sett=None):
+    """loss_update with the attach term, literally (mapper.py:799-928): stock torch ops around a rasterizer."""
+    Rast = Rast or rasterizer.GaussianRasterizer
+    Sett = Sett or rasterizer.GaussianRasterizationSettings
+    params = {k: torch.nn.Parameter(v.clone()) for k, v in raw.items()}
+    groups = [{"params": [params[k]], "lr": LRS_OP[k], "name": k} for k in mapping.FusedMappingStep.ORDER]
+    opt = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+    losses, attach = [], []
+    for _ in range(iters):
+        opacity = torch.sigmoid(init["opacity"])
+        attach_mask = (opacity < 0.9).squeeze()
+        l2 = lambda a, b: ((a - b) ** 2).mean()
+        attach_loss = 1000 * (l2(params["scaling"][attach_mask], init["scaling"][attach_mask])
+                              + l2(params["xyz"][attach_mask], init["xyz"][attach_mask])
+                              + l2(params["rotation"][attach_mask], init["rotation"][attach_mask]))
+        out = Rast(settings(None, Sett))(
+            means3D=params["xyz"], opacities=torch.sigmoid(params["opacity"]),
+            shs=torch.cat((params["f_dc"], params["f_rest"]), dim=1), scales=torch.exp(params["scaling"]),
+            rotations=torch.nn.functional.normalize(params["rotation"]), tile_mask=tile_mask)
+        image, depth, depth_index = out[0].permute(1, 2, 0), out[1].permute(1, 2, 0), out[3].permute(1, 2, 0)
+        color_loss = torch.abs(image[render_mask] - gt_color[render_mask]).mean()
+        depth_error = depth - gt_depth
+        valid = (depth_index != -1).squeeze() & (gt_depth > 0).squeeze() & (depth_error < 0.1).squeeze() & render_mask
+        depth_loss = torch.abs(depth_error[valid]).mean()
+        loss = 1.0 * depth_loss + 0.8 * color_loss
+        (loss + attach_loss).backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses.append(float(loss))
+        attach.append(float(attach_loss))
+    return params, losses, attach
+
+
+LRS_OP = dict(xyz=1e-3, f_dc=5e-4, f_rest=2.5e-5, opacity=5e-3, scaling=4e-3, rotation=1e-3)
+
+
+def test_fused_step_attach_term_matches_torch_autograd():
+    """The attach term (mapper.py:810-829): per-step losses and the attach value follow the literal torch loop, and the
+    anchored Gaussians (initial opacity < 0.9) stay closer to their initial state than without the term."""
+    gt, cam, settings, raw, gt_color, gt_depth, render_mask = _scene(P=5000, deg=3)
+    H, W = cam.image_height, cam.image_width
+    iters = 8
+    init = {k: raw[k].clone() for k in ("xyz", "scaling", "rotation", "opacity")}
+    n_anch = int((torch.sigmoid(init["opacity"]) < 0.9).sum())
+    assert 0 < n_anch < raw["xyz"].shape[0]
+    p_ref, l_ref, a_ref = _torch_attach_reference(raw, init, settings, gt["tile_mask"], gt_color, gt_depth, render_mask, iters)
+
+    def fused(attach):
+        params = {k: v.clone().contiguous() for k, v in raw.items()}
+        step = mapping.FusedMappingStep(params, LRS_OP, W, H, 0.8, 1.0, 0.1)
+        step.begin_window(attach=attach)
+        losses, att = [], []
+        for _ in range(iters):
+            total, _, _ = step(settings(), gt["tile_mask"], gt_color, gt_depth, render_mask)
+            losses.append(float(total))
+            att.append(float(step.attach_loss()))
+        step.check()
+        return params, losses, att, step
+
+    p_on, l_on, a_on, step = fused(True)
+    assert int(step.attach_count.item()) == n_anch
+    assert a_on[0] == 0.0 and a_ref[0] == 0.0            # parameters start at their anchor
+    for i in range(iters):
+        assert abs(l_on[i] - l_ref[i]) <= 3e-4 * abs(l_ref[i]), (i, l_on, l_ref)
+        assert abs(a_on[i] - a_ref[i]) <= 2e-3 * max(a_ref[i], 1e-6) + 1e-7, (i, a_on, a_ref)
+    anch = (torch.sigmoid(init["opacity"]) < 0.9).squeeze()
+    for k in ("xyz", "scaling", "rotation"):
+        d = (p_on[k] - p_ref[k].detach()).abs()
+        # Adam normalises the gradient: a noise-level sign flip moves an element by ~lr; gate the population
+        assert float((d > 0.5 * LRS_OP[k]).float().mean()) < 5e-3, k
+    p_off, _, a_off, _ = fused(False)
+    assert all(v == 0.0 for v in a_off)
+    moved_on = (p_on["xyz"][anch] - init["xyz"][anch]).norm()
+    moved_off = (p_off["xyz"][anch] - init["xyz"][anch]).norm()
+    assert float(moved_on) < float(moved_off)
+
+
+def test_fused_step_cuda_graph_replay_equals_eager():
+    gt, cam, settings, raw, gt_color, gt_depth, render_mask = _scene(P=4000, deg=3)
+    H, W = cam.image_height, cam.image_width
+    rs = settings()
+
+    def make():
+        params = {k: v.clone().contiguous() for k, v in raw.items()}
+        st = mapping.FusedMappingStep(params, LRS, W, H, 0.8, 1.0, 0.1, confidence=torch.zeros(params["xyz"].shape[0], 1, device=DEV))
+        st.begin_window(attach=True)
+        return params, st
+
+    p_e, st_e = make()
+    eager = []
+    for _ in range(6):
+        eager.append(float(st_e(rs, gt["tile_mask"], gt_color, gt_depth, render_mask)[0]))
+    st_e.check()
+    p_g, st_g = make()
+    g = st_g.graph(rs, gt["tile_mask"], gt_color, gt_depth, render_mask)   # warm-up = step 1
+    replay = [float(st_g.loss[0])]
+    for _ in range(5):
+        g.replay()
+        replay.append(float(st_g.loss[0]))
+    st_g.check()
+    assert st_g.step == 6 and st_e.step == 6
+    for a, b in zip(eager, replay):
+        assert abs(a - b) <= 2e-4 * abs(a), (eager, replay)   # float-atomic order differs between the two runs
+    assert float((p_e["xyz"] - p_g["xyz"]).abs().max()) <= 6 * LRS["xyz"]
+
+
+def test_short_horizon_loss_trajectories_agree():
+    """Ten iterations, per-step loss of the three implementations side by side (fused C step, operator path with torch
+    activations + FusedAdam, stock torch loop around the reference rasterizer when it is built).  Before the chaotic
+    divergence of long loops sets in the trajectories coincide: 1e-5 relative over the first five steps (observed: 1e-7),
+    2e-3 up to the tenth (observed: 5e-4 at step 10, growing ~3x per step as Adam amplifies float-atomic noise)."""
+    gt, cam, settings, raw, gt_color, gt_depth, render_mask = _scene(P=6000, deg=3)
+    H, W = cam.image_height, cam.image_width
+    iters = 10
+    params = {k: v.clone().contiguous() for k, v in raw.items()}
+    st = mapping.FusedMappingStep(params, LRS, W, H, 0.8, 1.0, 0.1)
+    rs = settings()
+    fused = [float(st(rs, gt["tile_mask"], gt_color, gt_depth, render_mask)[0]) for _ in range(iters)]
+    st.check()
+    pt = {k: torch.nn.Parameter(v.clone()) for k, v in raw.items()}
+    ms = mapping.MappingStep(pt, LRS, settings, 0.8, 1.0, 0.1, optimizer="fused")
+    oper = [float(ms(None, gt["tile_mask"], gt_color, gt_depth, render_mask)[0]) for _ in range(iters)]
+    trajs = {"operator": oper}
+    if rh.reference_available():
+        ref_pkg = rh.load_reference()[0]
+        pr = {k: torch.nn.Parameter(v.clone()) for k, v in raw.items()}
+        groups = [{"params": [pr[k]], "lr": LRS[k], "name": k} for k in mapping.FusedMappingStep.ORDER]
+        opt = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+        ref = []
+        for _ in range(iters):
+            out = ref_pkg.GaussianRasterizer(settings(None, ref_pkg.GaussianRasterizationSettings))(
+                means3D=pr["xyz"], opacities=torch.sigmoid(pr["opacity"]), shs=torch.cat((pr["f_dc"], pr["f_rest"]), dim=1),
+                scales=torch.exp(pr["scaling"]), rotations=torch.nn.functional.normalize(pr["rotation"]),
+                tile_mask=gt["tile_mask"])
+            image, depth, depth_index = out[0].permute(1, 2, 0), out[1].permute(1, 2, 0), out[3].permute(1, 2, 0)
+            color_loss = torch.abs(image[render_mask] - gt_color[render_mask]).mean()
+            depth_error = depth - gt_depth
+            valid = (depth_index != -1).squeeze() & (gt_depth > 0).squeeze() & (depth_error < 0.1).squeeze() & render_mask
+            loss = 1.0 * torch.abs(depth_error[valid]).mean() + 0.8 * color_loss
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            ref.append(float(loss))
+        trajs["reference"] = ref
+    assert fused[-1] < fused[0]
+    for name, t in trajs.items():
+        for i in range(iters):
+            assert abs(fused[i] - t[i]) <= (1e-5 if i < 5 else 2e-3) * abs(t[i]), (name, i, fused, t)
 
 
 @_statistical
