@@ -86,7 +86,7 @@ def main():
         rs = settings(rasterizer.GaussianRasterizationSettings, d["sh_degree"])
         # keyframe of this object = render of a perturbed copy; its mask and tile mask as Mapping.evaluate_render_range
         # builds them (mapper.py:983-987)
-        gt_color, gt_depth, _ = bench.make_keyframe(d, cam, lambda S: settings(S, d["sh_degree"]), rasterizer)
+        gt_color, gt_depth, _ = bench.make_keyframe(d, lambda S: settings(S, d["sh_degree"]), rasterizer)
         with torch.no_grad():
             cur = rasterizer.GaussianRasterizer(rs)(means3D=d["xyz"], opacities=d["opacity"], shs=d["shs"],
                                                     scales=d["scales"], rotations=d["rotations"], tile_mask=ones)
@@ -94,13 +94,15 @@ def main():
         R = int(rasterizer._RasterizeGaussians.last_state.status_host[0])
         raw = {k: v.contiguous() for k, v in bench.raw_params(d).items()}
         host = [t.cpu().pin_memory() for t in (gt_color, gt_depth, render_mask)]
-        e = {"id": o, "P": counts[o], "rs_ours": rs, "rs": settings(Sett, d["sh_degree"]), "tile_mask": tile_mask,
-             "kf": [gt_color, gt_depth, render_mask], "host": host, "slot": [torch.empty_like(t, device=dev) for t in host]}
+        e = {"id": o, "P": counts[o], "rs_ours": rs, "rs": settings(Sett, d["sh_degree"]), "tile_mask": tile_mask.contiguous(),
+             "kf": [gt_color, gt_depth, render_mask.contiguous()], "host": host, "slot": [torch.empty_like(t, device=dev) for t in host]}
         if a.impl == "ours":
             e["step"] = mapping.FusedMappingStep(raw, bench.LRS, W, H, 0.8, 1.0, 0.1,
                                                  confidence=torch.zeros(counts[o], 1, device=dev), capacity=int(R * 1.5) + 65536)
+            e["step"].begin_window(attach=True)
         else:
             e["params"] = {k: torch.nn.Parameter(v) for k, v in raw.items()}
+            e["init"] = {k: e["params"][k].detach().clone() for k in ("xyz", "scaling", "rotation", "opacity")}
             groups = [{"params": [e["params"][k]], "lr": bench.LRS[k], "name": k} for k in mapping.FusedMappingStep.ORDER]
             e["opt"] = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
             e["conf"] = torch.zeros(counts[o], 1, device=dev)
@@ -112,7 +114,8 @@ def main():
     def one(e, kf):
         if a.impl == "ours":
             return e["step"](e["rs_ours"], e["tile_mask"], kf[0], kf[1], kf[2])[0]
-        return bench.torch_mapping_iteration(e["params"], e["opt"], e["conf"], Rast, e["rs"], e["tile_mask"], kf[0], kf[1], kf[2])
+        return bench.torch_mapping_iteration(e["params"], e["init"], e["opt"], e["conf"], Rast, e["rs"], e["tile_mask"], kf[0],
+                                             kf[1], kf[2])
 
     # An object covers a few dozen tiles with deep lists: one object's blend kernels keep only a fraction of the 148 SMs
     # busy.  Objects are independent, so their steps go round-robin onto several streams and overlap on the device (the
@@ -136,8 +139,6 @@ def main():
 
     def kernel_step():
         fan_out(lambda e: one(e, e["kf"]))
-        if dist_on:
-            sharding.gather_object_table(table, rows_per_rank=rows)
 
     def e2e_object(e):
         for dst, src in zip(e["slot"], e["host"]):
@@ -146,14 +147,12 @@ def main():
 
     def e2e_step():
         losses = fan_out(e2e_object)
-        if dist_on:
-            sharding.gather_object_table(table, rows_per_rank=rows)
         return [float(x) for x in losses]  # D2H read of every object's loss
 
     sampler = bench.ClockSampler(local_rank)
     sampler.start()
-    ms = bench.timed(kernel_step, a.steps, a.warmup, dist_on)
-    ms_e2e = bench.timed(e2e_step, a.steps, a.warmup, dist_on)
+    ms = bench.timed(kernel_step, a.steps, a.warmup, dist_on, sampler)
+    ms_e2e = bench.timed(e2e_step, a.steps, a.warmup, dist_on, sampler)
     if a.impl == "ours":
         for e in objs:
             e["step"].check()

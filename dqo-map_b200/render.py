@@ -2,8 +2,14 @@
 normal / index / transmission maps and, when the Gaussians carry them, the semantic and instance colour images.
 
 The reference obtains the two extra images by running the complete rasterizer two more times with colors_precomp
-(render.py:227-262).  Here the view is preprocessed, binned and sorted once; each extra image is one additional blend
-pass over the same lists (`dqo_rast_blend_extra`), bit-identical to what the extra full calls would return."""
+(render.py:227-262); those calls are differentiable: with the default configuration (use_semantics, semantic_color_weight
+0.1) the L1 on "semantic_seg" back-propagates into the trainable `_semantics` group (gaussian_pointcloud.py:372-378) and
+into the geometry.  So:
+  * while autograd is recording and any input of an extra image requires grad, that image comes from a second full,
+    differentiable GaussianRasterizer call -- exactly the reference's graph;
+  * otherwise (evaluation renders: evaluate_render_range, error_gaussians_remove, get_render_output) the view is
+    preprocessed, binned and sorted once and each extra image is one additional blend pass over the same lists
+    (`dqo_rast_blend_extra`), bit-identical to what the extra full call returns."""
 import torch
 
 from . import rasterizer
@@ -12,7 +18,8 @@ from . import rasterizer
 def render(raster_settings, gaussian_data, tile_mask=None):
     """gaussian_data: dict with xyz, opacity, scales, rotations, shs, normal and optional semantics_color / instance
     ([P,3] each), already activated, as `Renderer.render` receives it (render.py:180-186).  Returns the reference's result
-    dict (render.py:218-266).  Gradients flow through "render" and "depth" only, as in the reference."""
+    dict (render.py:218-266).  Gradients flow through "render", "depth" and -- via the full differentiable path, see the
+    module docstring -- "semantic_seg" / "instance", as in the reference."""
     rs = raster_settings
     means3D = gaussian_data["xyz"]
     dev = means3D.device
@@ -36,8 +43,16 @@ def render(raster_settings, gaussian_data, tile_mask=None):
     for key, name in (("semantics_color", "semantic_seg"), ("instance", "instance")):  # render.py:227-262
         c = gaussian_data.get(key)
         if c is not None and c.numel() > 1:
-            with torch.no_grad():
-                results[name] = rasterizer.blend_extra_colors(state, c, rs.bg)
+            needs_grad = torch.is_grad_enabled() and any(
+                t is not None and t.requires_grad
+                for t in (c, means3D, gaussian_data["opacity"], gaussian_data["scales"], gaussian_data["rotations"]))
+            if needs_grad:
+                results[name] = rast(means3D=means3D, opacities=gaussian_data["opacity"], shs=None, colors_precomp=c,
+                                     scales=gaussian_data["scales"], rotations=gaussian_data["rotations"],
+                                     cov3D_precomp=None, normal_w=gaussian_data.get("normal"), tile_mask=tile_mask)[0]
+            else:
+                with torch.no_grad():
+                    results[name] = rasterizer.blend_extra_colors(state, c, rs.bg)
         else:
             results[name] = None
     if n_touched is not None:

@@ -32,7 +32,8 @@ def gather_object_table(local_table, group=None, rows_per_rank=None):
     """all_gather of a per-object float table [n_local, F] with variable n_local (e.g. F = 12:
     obj_id, count, center 3, quaternion 4, axes 3).  Returns the concatenated [n_total, F] table on every rank,
     sorted by column 0 (object id).  When every rank is known to hold exactly `rows_per_rank` rows (static object
-    assignment) the size exchange and its host synchronisation are skipped: one collective, fully asynchronous."""
+    assignment; ranks with fewer objects pad with rows whose id is negative) the size exchange and its host
+    synchronisation are skipped: one collective, fully asynchronous, same ordering."""
     world = dist.get_world_size(group)
     dev = local_table.device
     if rows_per_rank is not None:
@@ -40,7 +41,9 @@ def gather_object_table(local_table, group=None, rows_per_rank=None):
             raise ValueError("rows_per_rank does not match the local table")
         out = torch.empty((world * rows_per_rank, local_table.shape[1]), dtype=local_table.dtype, device=dev)
         dist.all_gather_into_tensor(out, local_table.contiguous(), group=group)
-        return out
+        # same row order as the general path: by object id (device-side argsort, no host synchronisation); padding rows of
+        # ranks that own fewer objects (id < 0) come first
+        return out[torch.argsort(out[:, 0], stable=True)] if out.shape[0] > 1 else out
     n_local = torch.tensor([local_table.shape[0]], dtype=torch.int64, device=dev)
     sizes = [torch.zeros_like(n_local) for _ in range(world)]
     dist.all_gather(sizes, n_local, group=group)

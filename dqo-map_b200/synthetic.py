@@ -205,3 +205,51 @@ def make_object(obj_id, count, cam_name="c1", seed=2024, sh_degree=3):
         shs[:, 1:, :] = 0.05 * torch.randn(P, M - 1, 3, generator=g)
     return {"xyz": xyz.contiguous(), "scales": scales, "rotations": (q / q.norm(dim=1, keepdim=True)).contiguous(),
             "opacity": op.unsqueeze(1).contiguous(), "shs": shs.contiguous(), "sh_degree": sh_degree, "obj_id": obj_id}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 5 shape: 3 M Gaussians at 1920x1080 with 64 objects + background (SURVEY.md 8d/8e).  The background
+# shell is split SPATIALLY into pieces of about one object's size (SURVEY 8e: "split spatially only if it dominates"):
+# every unit of the bin packing is then small against a rank's share and LPT balances to a few percent at 8 ranks.
+# ---------------------------------------------------------------------------------------------------------------------
+def scene_units_c5(n_objects=64, total=3_000_000, background_fraction=0.2, seed=2024):
+    """[(unit_id, n_gaussians, kind, piece, n_pieces)]: units 1..n_objects are objects, the others background pieces.
+    Deterministic: every rank computes the same table."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    w = 0.5 + torch.rand(n_objects, generator=g)
+    n_obj_total = int(total * (1.0 - background_fraction))
+    counts = (w / w.sum() * n_obj_total).long().tolist()
+    mean = n_obj_total // n_objects
+    n_pieces = max(1, round((total - n_obj_total) / mean))
+    piece = (total - sum(counts)) // n_pieces
+    units = [(1 + i, int(c), "object", 0, 1) for i, c in enumerate(counts)]
+    units += [(1 + n_objects + k, int(piece), "background", k, n_pieces) for k in range(n_pieces)]
+    return units
+
+
+def make_background_piece(unit_id, count, piece, n_pieces, cam_name="c5", seed=2024, sh_degree=3):
+    """Vertical strip `piece` of `n_pieces` of the far wall (object 0 of make_object), same surfel statistics."""
+    Pn, W, H, fx, fy, cx, cy, _ = CONFIGS[cam_name]
+    g = torch.Generator(device="cpu").manual_seed(seed * 1000 + unit_id)
+    cam = make_camera(cam_name)
+    P = int(count)
+    z = 4.5 + 0.05 * torch.randn(P, generator=g)
+    lo, hi = -1.0 + 2.0 * piece / n_pieces, -1.0 + 2.0 * (piece + 1) / n_pieces
+    u, v = lo + (hi - lo) * torch.rand(P, generator=g), torch.rand(P, generator=g) * 2 - 1
+    pts_c = torch.stack([u * z * (W / (2 * fx)), v * z * (H / (2 * fy)), z], dim=1)
+    W2C = cam.world_view_transform.transpose(0, 1).double()
+    C2W = torch.linalg.inv(W2C)
+    xyz = (pts_c.double() @ C2W[:3, :3].T + C2W[:3, 3]).float()
+    s = torch.exp(math.log(0.004) + (math.log(0.03) - math.log(0.004)) * torch.rand(P, 2, generator=g))
+    scales = torch.cat([s, 0.1 * s.min(dim=1, keepdim=True).values], dim=1)
+    scales = torch.gather(scales, 1, torch.argsort(torch.rand(P, 3, generator=g), dim=1)).contiguous()
+    q = torch.randn(P, 4, generator=g)
+    op = torch.where(torch.rand(P, generator=g) < 0.7, torch.tensor(0.99), 0.05 + 0.85 * torch.rand(P, generator=g))
+    M = (sh_degree + 1) ** 2
+    base = torch.rand(3, generator=g)
+    shs = torch.zeros(P, M, 3)
+    shs[:, 0, :] = RGB2SH((base + 0.15 * torch.randn(P, 3, generator=g)).clamp(0, 1))
+    if M > 1:
+        shs[:, 1:, :] = 0.05 * torch.randn(P, M - 1, 3, generator=g)
+    return {"xyz": xyz.contiguous(), "scales": scales, "rotations": (q / q.norm(dim=1, keepdim=True)).contiguous(),
+            "opacity": op.unsqueeze(1).contiguous(), "shs": shs.contiguous(), "sh_degree": sh_degree, "obj_id": unit_id}

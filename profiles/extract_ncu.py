@@ -8,10 +8,10 @@ import csv, io, json, os, subprocess, sys
 from collections import defaultdict
 
 STAGE_OF = {  # kernel-name substring -> bench.py stage key
-    "preprocess_kernel": "preprocess", "duplicate_kernel": "duplicate", "render_forward_kernel": "render_fwd",
+    "preprocess_kernel": "preprocess", "emit_kernel": "emit", "rank_sums_kernel": "emit", "render_forward_kernel": "render_fwd",
     "render_backward_kernel": "render_bwd", "gaussian_backward_kernel": "gaussian_bwd", "tile_ranges_kernel": "ranges",
     "adam_geometry_kernel": "adam_geometry", "adam_flat_kernel": "adam_flat", "adam_rest_kernel": "adam_rest",
-    "count_back_kernel": "back_binning",
+    "radix_": "sorts",
 }
 WANT = [
     ("gpu__time_duration.sum", "time_us"),
@@ -26,6 +26,7 @@ WANT = [
     ("launch__registers_per_thread", "regs"),
     ("smsp__thread_inst_executed_per_inst_executed.ratio", "lanes_per_inst"),
     ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
+    ("smsp__inst_executed.sum", "warp_inst"),
 ]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "msecond": 1e3,
          "usecond": 1.0, "nsecond": 1e-3, "second": 1e6}
@@ -70,7 +71,10 @@ def main():
             avg("l1_pct"), avg("sm_pct"), avg("issue_pct"), avg("occupancy_pct"), avg("regs"), avg("lanes_per_inst")))
         for sub, stage in STAGE_OF.items():
             if sub in k:  # kernels of the same stage (e.g. the front and back instantiation) add up
-                traffic[stage] = traffic.get(stage, 0) + int(avg("dram_rd") + avg("dram_wr"))
+                n_launch = len(recs) if stage in ("sorts", "emit") else 1  # multi-launch stages: totals of the capture
+                traffic[stage] = traffic.get(stage, 0) + int(avg("dram_rd") + avg("dram_wr")) * n_launch
+                if avg("warp_inst") == avg("warp_inst"):
+                    traffic[stage + "_warp_inst"] = traffic.get(stage + "_warp_inst", 0) + int(avg("warp_inst")) * n_launch
         if "Onesweep" in k or "RadixSort" in k:
             traffic.setdefault("_radix_kernels", 0)
             traffic["_radix_kernels"] += int((avg("dram_rd") + avg("dram_wr")) * len(recs))

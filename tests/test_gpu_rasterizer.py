@@ -476,3 +476,47 @@ def test_extra_colour_blend_equals_second_full_render(cfg, mask, binning):
     want = torch.zeros(3, cam.image_height, cam.image_width, device=DEV)
     want[:, di > -1] = normal[di[di > -1].long()].T
     assert torch.equal(res["normal"], want)
+
+
+def test_render_semantic_image_is_differentiable_like_the_reference():
+    """Renderer.render's semantic / instance images are full differentiable rasterizer calls in the reference
+    (SLAM/render.py:227-262), and loss_update's semantic L1 (mapper.py:876-879) trains `_semantics` and the geometry through
+    them.  render() must hand back the same graph: gradients reach the semantic colours and the positions and equal those
+    of an explicit second GaussianRasterizer call."""
+    from dqo_map_b200 import render as render_mod
+    inp = rh.make_inputs("small", torch.device(DEV), mask="ones")
+    cam = inp["cam"]
+    P = inp["xyz"].shape[0]
+    g = torch.Generator().manual_seed(4)
+    rd = synthetic.RENDER_DEFAULTS
+    rs = rasterizer.GaussianRasterizationSettings(
+        image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        bg=torch.zeros(3, device=DEV), scale_modifier=1.0, viewmatrix=cam.world_view_transform,
+        projmatrix=cam.full_proj_transform, sh_degree=inp["sh_degree"], campos=cam.camera_center,
+        opaque_threshold=rd["opaque_threshold"], normal_threshold=rd["normal_threshold"],
+        depth_threshold=rd["depth_threshold"], prefiltered=False, debug=False, cx=cam.cx, cy=cam.cy)
+    gt_sem = torch.rand(3, cam.image_height, cam.image_width, generator=g).to(DEV)
+    sem0 = torch.rand(P, 3, generator=g).to(DEV)
+    normal = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=1).to(DEV)
+
+    def leaves():
+        return sem0.clone().requires_grad_(True), inp["xyz"].clone().requires_grad_(True)
+
+    sem_a, xyz_a = leaves()
+    data = dict(xyz=xyz_a, opacity=inp["opacity"], scales=inp["scales"], rotations=inp["rotations"], shs=inp["shs"],
+                normal=normal, semantics_color=sem_a, instance=None)
+    res = render_mod.render(rs, data, inp["tile_mask"])
+    assert res["semantic_seg"].requires_grad and res["instance"] is None
+    (0.1 * (res["semantic_seg"] - gt_sem).abs().mean()).backward()
+    sem_b, xyz_b = leaves()
+    full = rasterizer.GaussianRasterizer(rs)(means3D=xyz_b, opacities=inp["opacity"], colors_precomp=sem_b,
+                                             scales=inp["scales"], rotations=inp["rotations"], tile_mask=inp["tile_mask"])[0]
+    assert torch.equal(res["semantic_seg"].detach(), full.detach())
+    (0.1 * (full - gt_sem).abs().mean()).backward()
+    assert float(sem_a.grad.abs().sum()) > 0 and float(xyz_a.grad.abs().sum()) > 0
+    assert float((sem_a.grad - sem_b.grad).norm() / sem_b.grad.norm()) <= 1e-4
+    assert float((xyz_a.grad - xyz_b.grad).norm() / xyz_b.grad.norm()) <= 1e-3
+    # evaluation renders (no grad) take the shared-binning blend and return the same image
+    with torch.no_grad():
+        res_ng = render_mod.render(rs, dict(data, xyz=inp["xyz"], semantics_color=sem0), inp["tile_mask"])
+    assert torch.equal(res_ng["semantic_seg"], full.detach())
