@@ -520,3 +520,59 @@ def test_render_semantic_image_is_differentiable_like_the_reference():
     with torch.no_grad():
         res_ng = render_mod.render(rs, dict(data, xyz=inp["xyz"], semantics_color=sem0), inp["tile_mask"])
     assert torch.equal(res_ng["semantic_seg"], full.detach())
+
+
+def _arbiter_inputs(inp, o, ex):
+    cam = inp["cam"]
+    rd = synthetic.RENDER_DEFAULTS
+    scene = dict(xyz=inp["xyz"], scales=inp["scales"], rotations=inp["rotations"], opacity=inp["opacity"],
+                 shs=None if inp["precomp"] else inp["shs"], rgb=inp["rgb"] if inp["precomp"] else None,
+                 view=cam.world_view_transform, proj=cam.full_proj_transform, campos=cam.camera_center, bg=inp["bg"],
+                 W=cam.image_width, H=cam.image_height, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, cx=cam.cx, cy=cam.cy,
+                 sh_degree=0 if inp["precomp"] else inp["sh_degree"], scale_modifier=rd["scale_modifier"],
+                 opaque_threshold=rd["opaque_threshold"], depth_threshold=rd["depth_threshold"],
+                 normal_threshold=rd["normal_threshold"])
+    lists = dict(point_list=torch.from_numpy(ex["point_list"].astype(np.int64)),
+                 ranges=torch.from_numpy(ex["ranges"].astype(np.int64)),
+                 n_contrib=torch.from_numpy(ex["n_contrib"].astype(np.int64)), hit=o[5][0].long(), radii=o[9])
+    return scene, lists
+
+
+@pytest.mark.parametrize("cfg,mask,precomp", [("tiny", "ones", False), ("small", "half", False), ("deg1", "ones", False),
+                                              ("tiny", "ones", True)])
+def test_gradients_against_float64_arbiter(cfg, mask, precomp):
+    """VERDICT r1 / SURVEY 7: the 1e-3 gradient gate with a float64 evaluation of the same function as arbiter
+    (oracle/f64_arbiter.py: torch float64 + autograd, independent of every hand-written backward):
+        |ours - f64| <= max(1e-3 |f64|, 1.5 |reference - f64|)   per gradient tensor, norm-wise.
+    No multiple-of-self-noise floor and no re-draw: both float32 implementations are measured against the exact value.
+    The reference's error is the largest of four runs: its float atomics land in unspecified order and the norm is
+    dominated by ONE ill-conditioned Gaussian per scene (tests/dev_arbiter_diag.py: > 99 % of the squared error of ours
+    AND of the reference sits in the same Gaussian, and the reference's own four runs range 4.8e-4 .. 9.1e-4)."""
+    from oracle import f64_arbiter
+    inp = rh.make_inputs(cfg, torch.device(DEV), mask=mask, precomp=precomp)
+    cam = inp["cam"]
+    gc, gd = rh.make_pixel_grads(cam.image_height, cam.image_width, DEV)
+    o, ex, bw = _run_ours(inp, gc, gd)
+    scene, lists = _arbiter_inputs(inp, o, ex)
+    exact = f64_arbiter.gradients(scene, lists, gc, gd, device=DEV)
+    ours = dict(zip(GRADS, bw))
+    refs = []
+    if rh.reference_available():
+        C = rh.load_reference()[1]
+        fwd = C.rasterize_gaussians(*rh.raster_args(inp))
+        refs = [dict(zip(GRADS, C.rasterize_gaussians_backward(*rh.backward_args(inp, fwd, gc, gd)))) for _ in range(4)]
+    checked = 0
+    for name, e in exact.items():
+        if e.numel() <= 1:
+            continue
+        e = e.double()
+        a = ours[name].double().reshape(e.shape)
+        nrm = float(e.norm())
+        assert nrm > 0, name
+        err = float((a - e).norm())
+        gate = 1e-3 * nrm
+        if refs:
+            gate = max(gate, 1.5 * max(float((r[name].double().reshape(e.shape) - e).norm()) for r in refs))
+        assert err <= gate, (name, err / nrm, gate / nrm)
+        checked += 1
+    assert checked == 5
