@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdqomap_b200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_R_FRONT, ST_R_BACK, ST_WALKED, ST_UNFINISHED = range(8)
 ST_WORDS = 8
@@ -37,7 +37,7 @@ class AdamTensor(C.Structure):
 
 class MapParams(C.Structure):
     _fields_ = [("param", c_p * 6), ("exp_avg", c_p * 6), ("exp_avg_sq", c_p * 6), ("lr", C.c_double * 6),
-                ("confidence", c_p), ("ever", c_p),
+                ("confidence", c_p), ("ever", c_p), ("ever_list", c_p), ("ever_count", c_p),
                 ("init_xyz", c_p), ("init_scaling", c_p), ("init_rotation", c_p), ("init_opacity", c_p),
                 ("attach_count", c_p), ("attach_weight", C.c_float), ("attach_opacity_thres", C.c_float),
                 ("step_state", c_p)]

@@ -13,7 +13,7 @@
 
 #define DQO_TILE 16
 #define DQO_TILE_PIX 256
-#define DQO_ABI_VERSION 10
+#define DQO_ABI_VERSION 11
 
 namespace dqo {
 

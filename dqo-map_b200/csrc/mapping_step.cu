@@ -30,7 +30,8 @@ int rast_backward_impl(const dqo_rast_settings *s, const float *background, cons
                        const void *image_buffer, const int32_t *status, const float *dL_dout_color,
                        const float *dL_dout_depth, const int32_t *hit_image, float *dL_dmeans2D, float *dL_dconic,
                        float *dL_dopacity, float *dL_dcolors, float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh,
-                       float *dL_dscales, float *dL_drotations, uint8_t *ever, void *stream_);
+                       float *dL_dscales, float *dL_drotations, uint8_t *ever, uint32_t *ever_list, int32_t *ever_count,
+                       void *stream_);
 
 struct StepLayout {
     size_t act_opacity, act_scales, act_rot;                    // activated copies [P], [P,3], [P,4]
@@ -195,87 +196,132 @@ __device__ __forceinline__ void block_add(float v, float *out) { // sum over the
         if (t != 0.f) atomicAdd(out, t);
     }
 }
+// all 14 geometric parameters of Gaussian i; returns its share of the attach value
+__device__ __forceinline__ float adam_gaussian(const SmallArgs &a, const AdamScalars &k, int i) {
+    float att = 0.f;
+    const bool anch = a.init_opacity && anchored(a.init_opacity, i, k.attach_logit_thr);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int e = 3 * i + c;
+        float p = a.xyz[e], m = a.m_xyz[e], v = a.v_xyz[e];
+        float g = a.g_means3D[e];
+        if (anch) {
+            const float d = p - a.init_xyz[e];
+            g += k.attach_grad[0] * d;
+            att += k.attach_val[0] * d * d;
+        }
+        adam_update(p, g, m, v, k, k.step_size[0]);
+        a.xyz[e] = p; a.m_xyz[e] = m; a.v_xyz[e] = v;
+    }
+    { // opacity: o = sigmoid(x), dL/dx = g * o * (1 - o)
+        const float o = a.act_opacity[i];
+        const float g = a.g_opacity[i] * (o * (1.0f - o));
+        float p = a.opacity[i], m = a.m_op[i], v = a.v_op[i];
+        if (!(g == 0.f && m == 0.f && v == 0.f)) { // zero gradient on zero moments: fixed point (lr_opacity is 0 anyway)
+            adam_update(p, g, m, v, k, k.step_size[3]);
+            a.opacity[i] = p; a.m_op[i] = m; a.v_op[i] = v;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) { // scale: s = exp(x), dL/dx = g * s
+        const int e = 3 * i + c;
+        float g = a.g_scales[e] * a.act_scales[e];
+        float p = a.scaling[e], m = a.m_sc[e], v = a.v_sc[e];
+        if (anch) {
+            const float d = p - a.init_scaling[e];
+            g += k.attach_grad[1] * d;
+            att += k.attach_val[1] * d * d;
+        }
+        adam_update(p, g, m, v, k, k.step_size[4]);
+        a.scaling[e] = p; a.m_sc[e] = m; a.v_sc[e] = v;
+    }
+    { // rotation: q = r / max(|r|, eps); dL/dr = (g - q (q . g)) / max(|r|, eps)
+        float4 r = reinterpret_cast<float4 *>(a.rotation)[i];
+        const float4 g = reinterpret_cast<const float4 *>(a.g_rot)[i];
+        const float nrm = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
+        const float d = fmaxf(nrm, 1e-12f);
+        const float qx = r.x / d, qy = r.y / d, qz = r.z / d, qw = r.w / d;
+        const float qg = qx * g.x + qy * g.y + qz * g.z + qw * g.w;
+        const float inv = (nrm > 1e-12f) ? 1.0f / d : 0.0f;
+        float gr[4] = {(g.x - qx * qg) * inv, (g.y - qy * qg) * inv, (g.z - qz * qg) * inv, (g.w - qw * qg) * inv};
+        float pr[4] = {r.x, r.y, r.z, r.w};
+        if (anch) {
+            const float4 r0 = reinterpret_cast<const float4 *>(a.init_rotation)[i];
+            const float d0[4] = {r.x - r0.x, r.y - r0.y, r.z - r0.z, r.w - r0.w};
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                gr[c] += k.attach_grad[2] * d0[c];
+                att += k.attach_val[2] * d0[c] * d0[c];
+            }
+        }
+        float4 m4 = reinterpret_cast<float4 *>(a.m_rot)[i], v4 = reinterpret_cast<float4 *>(a.v_rot)[i];
+        float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int c = 0; c < 4; c++) adam_update(pr[c], gr[c], mm[c], vv[c], k, k.step_size[5]);
+        reinterpret_cast<float4 *>(a.rotation)[i] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+        reinterpret_cast<float4 *>(a.m_rot)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+        reinterpret_cast<float4 *>(a.v_rot)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+    { // f_dc: gradient = first coefficient of the merged SH gradient
+        const float *gs = a.g_sh + (size_t)i * a.M * 3;
+        const float g3[3] = {gs[0], gs[1], gs[2]};
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int e = 3 * i + c;
+            float p = a.f_dc[e], m = a.m_dc[e], v = a.v_dc[e];
+            adam_update(p, g3[c], m, v, k, k.step_size[1]);
+            a.f_dc[e] = p; a.m_dc[e] = m; a.v_dc[e] = v;
+        }
+        if (a.confidence && (fabsf(g3[0]) != 0.f || fabsf(g3[1]) != 0.f || fabsf(g3[2]) != 0.f)) a.confidence[i] += 1.0f;
+    }
+    return att;
+}
+// one thread per Gaussian over the whole cloud (unaligned tensors, or no `ever` bookkeeping)
 __global__ void __launch_bounds__(256) adam_geometry_kernel(SmallArgs a) {
     const AdamScalars k = *a.kd;
     if (k.skip) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float att = 0.f;
-    if (i < a.P) {
-        const bool anch = a.init_opacity && anchored(a.init_opacity, i, k.attach_logit_thr);
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const int e = 3 * i + c;
-            float p = a.xyz[e], m = a.m_xyz[e], v = a.v_xyz[e];
-            float g = a.g_means3D[e];
-            if (anch) {
-                const float d = p - a.init_xyz[e];
-                g += k.attach_grad[0] * d;
-                att += k.attach_val[0] * d * d;
-            }
-            adam_update(p, g, m, v, k, k.step_size[0]);
-            a.xyz[e] = p; a.m_xyz[e] = m; a.v_xyz[e] = v;
-        }
-        { // opacity: o = sigmoid(x), dL/dx = g * o * (1 - o)
-            const float o = a.act_opacity[i];
-            const float g = a.g_opacity[i] * (o * (1.0f - o));
-            float p = a.opacity[i], m = a.m_op[i], v = a.v_op[i];
-            adam_update(p, g, m, v, k, k.step_size[3]);
-            a.opacity[i] = p; a.m_op[i] = m; a.v_op[i] = v;
-        }
-#pragma unroll
-        for (int c = 0; c < 3; c++) { // scale: s = exp(x), dL/dx = g * s
-            const int e = 3 * i + c;
-            float g = a.g_scales[e] * a.act_scales[e];
-            float p = a.scaling[e], m = a.m_sc[e], v = a.v_sc[e];
-            if (anch) {
-                const float d = p - a.init_scaling[e];
-                g += k.attach_grad[1] * d;
-                att += k.attach_val[1] * d * d;
-            }
-            adam_update(p, g, m, v, k, k.step_size[4]);
-            a.scaling[e] = p; a.m_sc[e] = m; a.v_sc[e] = v;
-        }
-        { // rotation: q = r / max(|r|, eps); dL/dr = (g - q (q . g)) / max(|r|, eps)
-            float4 r = reinterpret_cast<float4 *>(a.rotation)[i];
-            const float4 g = reinterpret_cast<const float4 *>(a.g_rot)[i];
-            const float nrm = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
-            const float d = fmaxf(nrm, 1e-12f);
-            const float qx = r.x / d, qy = r.y / d, qz = r.z / d, qw = r.w / d;
-            const float qg = qx * g.x + qy * g.y + qz * g.z + qw * g.w;
-            const float inv = (nrm > 1e-12f) ? 1.0f / d : 0.0f;
-            float gr[4] = {(g.x - qx * qg) * inv, (g.y - qy * qg) * inv, (g.z - qz * qg) * inv, (g.w - qw * qg) * inv};
-            float pr[4] = {r.x, r.y, r.z, r.w};
-            if (anch) {
-                const float4 r0 = reinterpret_cast<const float4 *>(a.init_rotation)[i];
-                const float d0[4] = {r.x - r0.x, r.y - r0.y, r.z - r0.z, r.w - r0.w};
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    gr[c] += k.attach_grad[2] * d0[c];
-                    att += k.attach_val[2] * d0[c] * d0[c];
-                }
-            }
-            float4 m4 = reinterpret_cast<float4 *>(a.m_rot)[i], v4 = reinterpret_cast<float4 *>(a.v_rot)[i];
-            float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-            for (int c = 0; c < 4; c++) adam_update(pr[c], gr[c], mm[c], vv[c], k, k.step_size[5]);
-            reinterpret_cast<float4 *>(a.rotation)[i] = make_float4(pr[0], pr[1], pr[2], pr[3]);
-            reinterpret_cast<float4 *>(a.m_rot)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
-            reinterpret_cast<float4 *>(a.v_rot)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-        }
-        { // f_dc: gradient = first coefficient of the merged SH gradient
-            const float *gs = a.g_sh + (size_t)i * a.M * 3;
-            const float g3[3] = {gs[0], gs[1], gs[2]};
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const int e = 3 * i + c;
-                float p = a.f_dc[e], m = a.m_dc[e], v = a.v_dc[e];
-                adam_update(p, g3[c], m, v, k, k.step_size[1]);
-                a.f_dc[e] = p; a.m_dc[e] = m; a.v_dc[e] = v;
-            }
-            if (a.confidence && (fabsf(g3[0]) != 0.f || fabsf(g3[1]) != 0.f || fabsf(g3[2]) != 0.f)) a.confidence[i] += 1.0f;
-        }
-    }
+    if (i < a.P && !(a.ever && !a.ever[i])) att = adam_gaussian(a, k, i);
     if (a.init_opacity) block_add(att, a.attach_out);
+}
+// The optimiser over the COMPACT LIST of Gaussians that have ever received a gradient (dqo_map_params.ever_list,
+// appended to by the backward pass): for a single keyframe that is 10-20 % of a 1 M-Gaussian map, and walking the whole
+// cloud just to skip the rest (one flag byte per Gaussian and tensor) cost more than the updates themselves.  Persistent
+// grid: the list length is only known on the device.
+struct ListArgs {
+    SmallArgs s;
+    const uint32_t *list;
+    const int *count;
+    float *f_rest, *m_rest, *v_rest;
+};
+__global__ void __launch_bounds__(256) adam_list_kernel(ListArgs a) {
+    const AdamScalars k = *a.s.kd;
+    if (k.skip) return;
+    const int n = *a.count;
+    float att = 0.f;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x)
+        att += adam_gaussian(a.s, k, (int)a.list[l]);
+    if (a.s.init_opacity) block_add(att, a.s.attach_out);
+}
+// f_rest [P,45] of the listed Gaussians: consecutive threads walk the 45 coefficients of one Gaussian (180-byte runs);
+// the gradient comes from the merged [P,16,3] layout (row stride 48, offset 3)
+__global__ void __launch_bounds__(256) adam_rest_list_kernel(ListArgs a) {
+    const AdamScalars k = *a.s.kd;
+    if (k.skip) return;
+    const unsigned total = (unsigned)(*a.count) * 45u;
+    const float ss = k.step_size[2];
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const unsigned l = e / 45u, c = e - l * 45u;
+        const size_t i = a.list[l];
+        const size_t pe = i * 45 + c;
+        const float g = __ldg(&a.s.g_sh[i * 48 + 3 + c]);
+        float m = a.m_rest[pe], v = a.v_rest[pe];
+        if (g == 0.f && m == 0.f && v == 0.f) continue;
+        float p = a.f_rest[pe];
+        adam_update(p, g, m, v, k, ss);
+        a.f_rest[pe] = p; a.m_rest[pe] = m; a.v_rest[pe] = v;
+    }
 }
 
 // Same update with every flat tensor streamed in 128-bit accesses: blocks are split into five roles by index range.
@@ -603,7 +649,7 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
     rc = rast_backward_impl(s, kf->background, xyz, f_dc, f_rest, nullptr, act_sc, act_rot, nullptr, kf->viewmatrix,
                             kf->projmatrix, kf->campos, radii, ws + L.geom, ws + L.binning, capacity, ws + L.image, status,
                             g_img, g_depth, hit_depth, nullptr, nullptr, g_op, nullptr, g_means3D, nullptr, g_sh, g_sc,
-                            g_rot, p->ever, stream_);
+                            g_rot, p->ever, p->ever_list, p->ever_count, stream_);
     if (rc) return rc;
 
     // step number, bias corrections, attach scales and the overflow decision: one thread on the device
@@ -642,6 +688,19 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
                               sa.init_xyz, sa.init_scaling, sa.init_rotation};
         for (const void *q : ptrs) aligned &= ((uintptr_t)q % 16 == 0);
         aligned &= ((uintptr_t)p->ever % 4 == 0);
+    }
+    const bool use_list = p->ever && p->ever_list && p->ever_count && (long long)P * 45 < (1ll << 32);
+    if (use_list) {
+        ListArgs la;
+        la.s = sa; la.list = p->ever_list; la.count = p->ever_count;
+        la.f_rest = f_rest; la.m_rest = p->exp_avg[2]; la.v_rest = p->exp_avg_sq[2];
+        const int blocks = nb < 148 * 8 ? nb : 148 * 8;
+        adam_list_kernel<<<blocks, 256, 0, stream>>>(la);
+        if (M == 16) adam_rest_list_kernel<<<148 * 8, 256, 0, stream>>>(la);
+        DQO_LAUNCH_CHECK("adam (listed Gaussians)", s->debug, stream);
+        note_launch(M == 16 ? 1 : 0);
+        nvtx_pop();
+        return DQO_OK;
     }
     if (aligned) {
         FlatArgs fa;

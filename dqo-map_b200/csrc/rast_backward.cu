@@ -339,6 +339,8 @@ struct GaussBwdArgs {
     // Gaussian that never has is a fixed point of Adam (zero gradient on zero moments), so its gradients are neither
     // written here nor read by the optimiser kernels: one byte instead of ~240 B written and ~600 B read per step.
     uint8_t *ever;
+    uint32_t *ever_list; // optional compact list of the Gaussians whose flag is set (append order), with its length
+    int *ever_count;
 };
 
 __device__ __constant__ float B_SH_C0 = 0.28209479177387814f;
@@ -417,7 +419,10 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
 #pragma unroll
         for (int k = 0; k < DQO_GACC_FLOATS; k++) nz |= (g[k] != 0.f);
         const bool was = a.ever[idx] != 0;
-        if (nz && !was) a.ever[idx] = 1;
+        if (nz && !was) {
+            a.ever[idx] = 1;
+            if (a.ever_list) a.ever_list[atomicAdd(a.ever_count, 1)] = (uint32_t)idx; // (the compiler aggregates per warp)
+        }
         write_out = nz || was;
     }
     float *dsh = (a.dL_dsh && live) ? a.dL_dsh + (size_t)idx * M * 3 : nullptr;
@@ -732,7 +737,8 @@ int rast_backward_impl(const dqo_rast_settings *s, const float *background, cons
                        const void *image_buffer, const int32_t *status, const float *dL_dout_color,
                        const float *dL_dout_depth, const int32_t *hit_image, float *dL_dmeans2D, float *dL_dconic,
                        float *dL_dopacity, float *dL_dcolors, float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh,
-                       float *dL_dscales, float *dL_drotations, uint8_t *ever, void *stream_);
+                       float *dL_dscales, float *dL_drotations, uint8_t *ever, uint32_t *ever_list,
+                       int32_t *ever_count, void *stream_);
 }
 
 extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *background, const float *means3D,
@@ -748,7 +754,8 @@ extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *backgr
     return rast_backward_impl(s, background, means3D, shs, nullptr, colors_precomp, scales, rotations, cov3D_precomp,
                               viewmatrix, projmatrix, campos, radii, geom_buffer, binning_buffer, capacity, image_buffer,
                               status, dL_dout_color, dL_dout_depth, hit_image, dL_dmeans2D, dL_dconic, dL_dopacity,
-                              dL_dcolors, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, nullptr, stream_);
+                              dL_dcolors, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, nullptr, nullptr, nullptr,
+                              stream_);
 }
 
 int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background, const float *means3D,
@@ -760,7 +767,7 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
                                  const float *dL_dout_depth, const int32_t *hit_image, float *dL_dmeans2D,
                                  float *dL_dconic, float *dL_dopacity, float *dL_dcolors, float *dL_dmeans3D,
                                  float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
-                                 uint8_t *ever, void *stream_) {
+                                 uint8_t *ever, uint32_t *ever_list, int32_t *ever_count, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!s || s->P < 0) {
         set_error("dqo_rast_backward: invalid settings");
@@ -825,6 +832,8 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     ga.dL_dmeans3D = dL_dmeans3D; ga.dL_dcov3D = dL_dcov3D; ga.dL_dsh = (s->M > 0) ? dL_dsh : nullptr;
     ga.dL_dscales = dL_dscales; ga.dL_drot = dL_drotations;
     ga.ever = ever;
+    ga.ever_list = (ever && ever_list && ever_count) ? ever_list : nullptr;
+    ga.ever_count = ever_count;
     const bool staged = shs && !f_rest && dL_dsh && s->M == 16 && ((uintptr_t)shs % 16 == 0) && ((uintptr_t)dL_dsh % 16 == 0);
     const int gb_blocks = (P + GB_THREADS - 1) / GB_THREADS;
     const size_t gb_smem = (size_t)(GB_THREADS / 32) * 32 * GB_ROW_Q * sizeof(float4);

@@ -203,6 +203,9 @@ class FusedMappingStep:
         # one byte per Gaussian: has it ever received a non-zero gradient?  (zero-initialised with the moments; Gaussians
         # that never have are skipped by the backward's gradient writes and by the optimiser, see dqo_map_params.ever)
         self.ever = torch.zeros(self.P, dtype=torch.uint8, device=self.dev)
+        # compact list of the flagged Gaussians + its length: the optimiser walks the list, not the cloud
+        self.ever_list = torch.zeros(self.P, dtype=torch.int32, device=self.dev)
+        self.ever_count = torch.zeros(1, dtype=torch.int32, device=self.dev)
         # [0] Adam steps taken, [1] steps skipped by the device (overflow), sticky until check()
         self.step_state = torch.zeros(4, dtype=torch.int32, device=self.dev)
         self.init = None            # attach reference (history_stat of local_optimize), see begin_window
@@ -229,6 +232,7 @@ class FusedMappingStep:
             m.zero_()
             v.zero_()
         self.ever.zero_()
+        self.ever_count.zero_()
         self.step_state.zero_()
         self._mp_key = None
         if not attach:
@@ -263,6 +267,7 @@ class FusedMappingStep:
                 mp.lr[i] = lrs[i]
             mp.confidence = ptr(self.confidence)
             mp.ever = ptr(self.ever)
+            mp.ever_list, mp.ever_count = ptr(self.ever_list), ptr(self.ever_count)
             if self.init is not None:
                 mp.init_xyz, mp.init_scaling = ptr(self.init["xyz"]), ptr(self.init["scaling"])
                 mp.init_rotation, mp.init_opacity = ptr(self.init["rotation"]), ptr(self.init["opacity"])
@@ -374,6 +379,8 @@ class FusedMappingStep:
     def mark_all_touched(self):
         """Call after writing non-zero values into `self.state` by hand (e.g. restoring a checkpoint)."""
         self.ever.fill_(1)
+        self.ever_list.copy_(torch.arange(self.P, dtype=torch.int32, device=self.dev))
+        self.ever_count.fill_(self.P)
 
     def set_binning(self, front_instances, back_instances):
         """Switch between single-phase (0, 0) and two-phase binning; front + back must fit the capacity."""

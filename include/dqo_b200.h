@@ -354,6 +354,11 @@ typedef struct dqo_map_params {
      * nor read by the optimiser.  Owned by the caller, zero-initialised TOGETHER WITH the moments (set to 1 wherever moments
      * are restored non-zero). */
     uint8_t *ever;
+    /* Optional, with `ever`: compact list of the Gaussians whose flag is set (u32[P], append order) and its length (device
+     * int), zero-initialised together with `ever`.  The backward appends a Gaussian when its flag flips; the optimiser then
+     * walks the list instead of the whole cloud.  NULL: the optimiser scans all P Gaussians and skips by flag. */
+    uint32_t *ever_list;
+    int32_t *ever_count;
     /* Attach term of loss_update (mapper.py:810-829): Gaussians whose INITIAL opacity sigmoid(init_opacity) is below
      * attach_opacity_thres (0.9) are anchored to their initial raw xyz / scaling / rotation by
      * attach_weight (1000) * (mse + mse + mse); the gradient is added to the rasterizer's before Adam, the value lands in
