@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdqomap_b200.so")
+# DQO_B200_LIB: another build of the same library (kernel A/B experiments, tests/dev_*.py); there is still no fallback
+LIB_PATH = os.environ.get("DQO_B200_LIB") or os.path.join(_HERE, "csrc", "libdqomap_b200.so")
 ABI_VERSION = 11
 
 ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_R_FRONT, ST_R_BACK, ST_WALKED, ST_UNFINISHED = range(8)

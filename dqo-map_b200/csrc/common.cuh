@@ -234,20 +234,20 @@ __device__ __forceinline__ unsigned subblock_mask(float mx, float my, float A, f
     const float tau = ex * ex * (A * C - B * B) / C * 1.0001f;
     if (!(tau < 3.0e38f)) return m; // inf / NaN: extent test only
     const float invA = 1.f / A, invC = 1.f / C;
+    // The form is convex with its minimum at the splat centre, so over a rectangle that does not contain the centre the
+    // minimum lies on an edge that faces it: at most one vertical and one horizontal edge need the 1-D minimisation.
+    // Only the candidate sub-blocks are visited (a warp iterates as often as its lane with the most candidates).
     unsigned keep = 0;
-#pragma unroll
-    for (int b = 0; b < 8; b++) {
-        if (!((m >> b) & 1)) continue;
+    for (unsigned todo = m; todo; todo &= todo - 1) {
+        const int b = __ffs(todo) - 1;
         const float dxl = tile_px + 8.f * (b & 1) - mx, dxh = dxl + 7.f;
         const float dyl = tile_py + 4.f * (b >> 1) - my, dyh = dyl + 3.f;
-        if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) {
-            keep |= 1u << b;
-            continue;
-        }
-        float f = edge_min_qf(A, B, C, dxl, dyl, dyh, invC);
-        f = fminf(f, edge_min_qf(A, B, C, dxh, dyl, dyh, invC));
-        f = fminf(f, edge_min_qf(C, B, A, dyl, dxl, dxh, invA));
-        f = fminf(f, edge_min_qf(C, B, A, dyh, dxl, dxh, invA));
+        const bool in_x = dxl <= 0.f && dxh >= 0.f, in_y = dyl <= 0.f && dyh >= 0.f;
+        float f = (in_x && in_y) ? 0.f : 3.4e38f;
+        const float fx = edge_min_qf(A, B, C, dxl > 0.f ? dxl : dxh, dyl, dyh, invC);
+        const float fy = edge_min_qf(C, B, A, dyl > 0.f ? dyl : dyh, dxl, dxh, invA);
+        if (!in_x) f = fminf(f, fx);
+        if (!in_y) f = fminf(f, fy);
         if (!(f > tau)) keep |= 1u << b;
     }
     return keep;

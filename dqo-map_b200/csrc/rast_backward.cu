@@ -76,53 +76,76 @@ __device__ __forceinline__ int slot_of_lane(int lane) {
     return ok ? s9 : -1;
 }
 
+// shared-memory accessors of the blend loop: the window address is computed once and kept opaque, so the compiler
+// cannot rematerialise it (S2R + LEA) inside the loop as it does for indexed __shared__ arrays under register pressure
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 #define RB_BATCH 512
+#ifndef RB_OCC
+#define RB_OCC 6
+#endif
 #define RB_THREADS 128 // 4 warps x (8x8 pixels); every thread owns the pixels (x, y) and (x, y + 4)
 
 // per-pixel state of the reverse traversal (backward.cu:881-900)
 struct BwdPix {
-    float T, T_final, acc0, acc1, acc2, last_alpha, lc0, lc1, lc2, dLp0, dLp1, dLp2, bg_dot, pixfy;
+    float T, T_final, acc0, acc1, acc2, dLp0, dLp1, dLp2, bg_dot, pixfy;
     int last_contributor;
 };
 
 // One (splat, pixel) pair of the reverse blend (backward.cu:926-995): adds this pixel's 9 partial gradients to v.
-__device__ __forceinline__ bool bwd_pair(BwdPix &p, const float4 r0, const float4 r1, const float4 r2, int posj, float pixfx,
-                                         float ddelx_dx, float ddely_dy, float v[9]) {
-    if (!(posj < p.last_contributor)) return false;
+// The rejections of the reference (position behind the pixel's last contributor, power > 0, alpha < 1/255; the staged
+// power_reject bound is implied by the alpha test) are folded into ONE predicate after the exponential, so the pair
+// is a straight-line prologue plus a single guarded update instead of four exits.
+__device__ __forceinline__ bool bwd_pair(BwdPix &p, bool reach, const float4 r0, const float4 r1, const float4 r2, int posj,
+                                         float pixfx, float ddelx_dx, float ddely_dy, float v[9]) {
     const float dx = fsub(r0.x, pixfx), dy = fsub(r0.y, p.pixfy);
     const float power = ffma(ffma(dx, fmul(dx, r0.z), fmul(dy, fmul(dy, r1.x))), -0.5f, -fmul(dy, fmul(dx, r0.w)));
-    if (power > 0.0f || power < r1.z) return false;
     const float G = expf(power);
     const float alpha = fminf(0.99f, fmul(r1.y, G));
-    if (alpha < 1.0f / 255.0f) return false;
-    // IEEE division as in the reference (backward.cu:947): the conic -> cov3D -> rotation chain downstream amplifies a
-    // 1-ulp change of T to ~1e-3 in dL_drotations, so approximations here are not free
-    p.T = p.T / (1.f - alpha);
-    const float dchannel_dcolor = alpha * p.T;
-    p.acc0 = p.last_alpha * p.lc0 + (1.f - p.last_alpha) * p.acc0;
-    p.acc1 = p.last_alpha * p.lc1 + (1.f - p.last_alpha) * p.acc1;
-    p.acc2 = p.last_alpha * p.lc2 + (1.f - p.last_alpha) * p.acc2;
-    p.lc0 = r2.x;
-    p.lc1 = r2.y;
-    p.lc2 = r2.z;
-    float dL_dalpha = (r2.x - p.acc0) * p.dLp0 + (r2.y - p.acc1) * p.dLp1 + (r2.z - p.acc2) * p.dLp2;
-    dL_dalpha *= p.T;
-    p.last_alpha = alpha;
-    if (p.bg_dot != 0.f) dL_dalpha += (-p.T_final / (1.f - alpha)) * p.bg_dot; // background term (backward.cu:975), 0 for bg = 0
-    const float dL_dG = r1.y * dL_dalpha;
-    const float gdx = G * dx, gdy = G * dy;
-    const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
-    const float dG_ddely = -gdy * r1.x - gdx * r0.w;
-    v[0] += dL_dG * dG_ddelx * ddelx_dx;
-    v[1] += dL_dG * dG_ddely * ddely_dy;
-    v[2] += -0.5f * gdx * dx * dL_dG;
-    v[3] += -0.5f * gdx * dy * dL_dG;
-    v[4] += -0.5f * gdy * dy * dL_dG;
-    v[5] += G * dL_dalpha;
-    v[6] += dchannel_dcolor * p.dLp0;
-    v[7] += dchannel_dcolor * p.dLp1;
-    v[8] += dchannel_dcolor * p.dLp2;
-    return true;
+    const bool live = reach && (posj < p.last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+    if (live) {
+        // IEEE division as in the reference (backward.cu:947): the conic -> cov3D -> rotation chain downstream amplifies
+        // a 1-ulp change of T to ~1e-3 in dL_drotations, so approximations here are not free
+        p.T = p.T / (1.f - alpha);
+        const float dchannel_dcolor = alpha * p.T;
+        // accum_rec of the reference (backward.cu:953-961) is last_alpha * last_color + (1 - last_alpha) * accum_rec,
+        // evaluated when the NEXT contributor is visited; the same expression is evaluated here one visit earlier, so
+        // last_alpha / last_color need not be carried (8 registers for the two pixels of a thread)
+        float dL_dalpha = (r2.x - p.acc0) * p.dLp0 + (r2.y - p.acc1) * p.dLp1 + (r2.z - p.acc2) * p.dLp2;
+        dL_dalpha *= p.T;
+        p.acc0 = alpha * r2.x + (1.f - alpha) * p.acc0;
+        p.acc1 = alpha * r2.y + (1.f - alpha) * p.acc1;
+        p.acc2 = alpha * r2.z + (1.f - alpha) * p.acc2;
+        if (p.bg_dot != 0.f) dL_dalpha += (-p.T_final / (1.f - alpha)) * p.bg_dot; // background term (backward.cu:975), 0 for bg = 0
+        const float dL_dG = r1.y * dL_dalpha;
+        const float gdx = G * dx, gdy = G * dy;
+        const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
+        const float dG_ddely = -gdy * r1.x - gdx * r0.w;
+        v[0] += dL_dG * dG_ddelx * ddelx_dx;
+        v[1] += dL_dG * dG_ddely * ddely_dy;
+        v[2] += -0.5f * gdx * dx * dL_dG;
+        v[3] += -0.5f * gdx * dy * dL_dG;
+        v[4] += -0.5f * gdy * dy * dL_dG;
+        v[5] += G * dL_dalpha;
+        v[6] += dchannel_dcolor * p.dLp0;
+        v[7] += dchannel_dcolor * p.dLp1;
+        v[8] += dchannel_dcolor * p.dLp2;
+    }
+    return live;
 }
 
 // depth gradient to the single hit Gaussian of a pixel (backward.cu:998-1065)
@@ -194,12 +217,13 @@ struct __align__(16) SplatB {
     float4 r0, r1, c; // {x, y, conic.x, conic.y} {conic.z, opacity, power_reject, -} {r, g, b, Gaussian id bits}
 };
 
-__global__ void __launch_bounds__(RB_THREADS, 6) render_backward_kernel(RenderBwdArgs a) {
+__global__ void __launch_bounds__(RB_THREADS, RB_OCC) render_backward_kernel(RenderBwdArgs a) {
     // RB_BATCH entries are staged per round.  With 512 most tiles need a single round (max n_contrib is a few hundred):
     // the four warps then walk their own lists without meeting at a barrier after every 256 entries, where the fast
     // ones used to wait for the slowest sub-block.
     __shared__ SplatB s_sp[RB_BATCH]; // one 48-byte record per staged splat: a single base + j*48 address in the loop
     __shared__ uint8_t s_mask[RB_BATCH];
+    // per-warp list entry: batch slot (9 bits) | reach bit of the upper pixel row block << 14 | of the lower << 15
     __shared__ uint16_t s_list[RB_THREADS / 32][RB_BATCH];
     __shared__ int s_max;
 
@@ -252,8 +276,6 @@ __global__ void __launch_bounds__(RB_THREADS, 6) render_backward_kernel(RenderBw
         }
         p.bg_dot = a.bg[0] * p.dLp0 + a.bg[1] * p.dLp1 + a.bg[2] * p.dLp2;
         p.acc0 = p.acc1 = p.acc2 = 0.f;
-        p.last_alpha = 0.f;
-        p.lc0 = p.lc1 = p.lc2 = 0.f;
         warp_max = max(warp_max, p.last_contributor);
     }
     if (tid == 0) s_max = 0;
@@ -266,6 +288,7 @@ __global__ void __launch_bounds__(RB_THREADS, 6) render_backward_kernel(RenderBw
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
     const int my_slot = slot_of_lane(lane);
 
+    const uint32_t sp_base = smem_addr(s_sp), list_base = smem_addr(&s_list[warp][0]);
     const int rounds = (max_c + RB_BATCH - 1) / RB_BATCH;
     for (int i = 0; i < rounds; i++) {
         __syncthreads();
@@ -291,25 +314,28 @@ __global__ void __launch_bounds__(RB_THREADS, 6) render_backward_kernel(RenderBw
         for (int b = 0; b < n; b += 32) {
             const int j = b + lane;
             const int posj = max_c - 1 - (i * RB_BATCH + j);
-            const bool m = (j < n) && (posj < warp_max) && (s_mask[j] & warp_bits);
+            const unsigned mk = (j < n) ? s_mask[j] : 0u;
+            const bool m = (posj < warp_max) && (mk & warp_bits);
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, m);
-            if (m) s_list[warp][cnt + __popc(bal & ((1u << lane) - 1))] = (uint16_t)j;
+            if (m) s_list[warp][cnt + __popc(bal & ((1u << lane) - 1))] =
+                       (uint16_t)(j | (((mk >> b_lo) & 1u) << 14) | (((mk >> b_hi) & 1u) << 15));
             cnt += __popc(bal);
         }
         __syncwarp();
+        const int pos_top = max_c - 1 - i * RB_BATCH; // list position of batch slot 0
         for (int k = 0; k < cnt; k++) {
-            const int j = s_list[warp][k];
-            const int posj = max_c - 1 - (i * RB_BATCH + j);
-            const unsigned mk = s_mask[j];
-            const float4 r0 = s_sp[j].r0;
-            const float4 r1 = s_sp[j].r1;
-            const float4 r2 = s_sp[j].c;
+            const uint32_t e = lds_u16(list_base + 2 * k);
+            const int j = (int)(e & 0x3FFFu);
+            const uint32_t rec = sp_base + (uint32_t)j * 48u;
+            const float4 r0 = lds128(rec);
+            const float4 r1 = lds128(rec + 16);
+            const float4 r2 = lds128(rec + 32);
+            const int posj = pos_top - j;
             float v[9];
 #pragma unroll
             for (int q = 0; q < 9; q++) v[q] = 0.f;
-            bool contrib = false;
-            if ((mk >> b_lo) & 1) contrib |= bwd_pair(px[0], r0, r1, r2, posj, pixfx, ddelx_dx, ddely_dy, v);
-            if ((mk >> b_hi) & 1) contrib |= bwd_pair(px[1], r0, r1, r2, posj, pixfx, ddelx_dx, ddely_dy, v);
+            bool contrib = bwd_pair(px[0], (e & 0x4000u) != 0, r0, r1, r2, posj, pixfx, ddelx_dx, ddely_dy, v);
+            contrib |= bwd_pair(px[1], (e & 0x8000u) != 0, r0, r1, r2, posj, pixfx, ddelx_dx, ddely_dy, v);
             if (!__any_sync(0xFFFFFFFFu, contrib)) continue;
             const float total = warp_reduce9(v, lane);
             if (my_slot >= 0) atomicAdd(&a.gacc[(size_t)__float_as_int(r2.w) * DQO_GACC_FLOATS + my_slot], total);

@@ -792,11 +792,31 @@ struct RenderArgs {
 //            already in the output images.
 //   PHASE 2: unfinished tiles resume from the parked state and walk their back list; list positions continue at the
 //            length of the front list, so n_contrib and the blend order are those of the concatenated (= reference) list.
-template <int PHASE>
+// shared-memory accessors of the blend loops: the window address is computed once and kept opaque, so the compiler
+// cannot rematerialise it (S2R + LEA) inside the loop as it does for indexed __shared__ arrays under register pressure
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16x2(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+#define RF_LIST_STRIDE 264 // u16 entries per warp list: 256 + sentinel padding, multiple of 4
+
+template <int PHASE, bool NT>
 __global__ void __launch_bounds__(256, 4) render_forward_kernel(RenderArgs a) {
-    __shared__ SplatS s_sp[256]; // one 48-byte record per staged splat: a single base + j*48 address in the loop
+    __shared__ SplatS s_sp[257]; // one 48-byte record per staged splat (+ an all-zero sentinel that never contributes)
     __shared__ uint8_t s_mask[256];
-    __shared__ uint8_t s_list[8][256];
+    __shared__ __align__(16) uint16_t s_list[8][RF_LIST_STRIDE];
 
     const int tile = blockIdx.x;
     const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
@@ -837,36 +857,47 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(RenderArgs a) {
     const float tile_px = (float)(tile_x * DQO_TILE), tile_py = (float)(tile_y * DQO_TILE);
     const int total = (int)(range.y - range.x);
     const int rounds = (total + 255) / 256;
+    if (tid == 0) s_sp[256].r0 = s_sp[256].r1 = s_sp[256].c = make_float4(0.f, 0.f, 0.f, 0.f); // opacity 0: alpha = 0
 
-    bool done = !inside;
+    // Per-pixel state.  Two of the reference's flags live inside other values so that the walk needs no predicate <->
+    // register traffic: `done` is the SIGN BIT of T (T itself is never negative), and the first-opaque-hit state is one
+    // integer: -1 no hit yet, -2 hit found by an earlier launch (PHASE 2 resume), >= 0 the Gaussian hit in this launch.
     float T = 1.0f, end_T = 1.0f;
     int ncontrib = 0;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f;
     float depth_ = 0.f;
-    bool hit = false;
+    int hit_state = -1;
     int hit_id = -1, hit_color_id = -1;
-    float cw_max = -1.f, hit_cw = 0.f, hit_dw = 0.f;
+    float cw_max = -1.f, hit_dw = 0.f;
     bool was_done = false;
     if (PHASE == 2 && base > 0 && inside) { // resume: parked (T, C) + what the front phase wrote to the outputs
         T = a.state[sp];
         C0 = a.state[a.plane + sp];
         C1 = a.state[2 * a.plane + sp];
         C2 = a.state[3 * a.plane + sp];
-        if (T < 0.f) done = was_done = true;
+        was_done = T < 0.f; // parked as -1: terminated in the front phase, nothing left to do
         ncontrib = (int)a.n_contrib[sp];
         end_T = a.final_T[sp];
         hit_id = a.out_hit_depth[pix_id];
-        hit = hit_id >= 0;
+        hit_state = hit_id >= 0 ? -2 : -1;
         hit_color_id = a.out_hit_color[pix_id];
-        hit_cw = a.out_hit_cw[pix_id];
-        cw_max = hit_color_id >= 0 ? hit_cw : -1.f;
+        cw_max = hit_color_id >= 0 ? a.out_hit_cw[pix_id] : -1.f;
         hit_dw = a.out_hit_dw[pix_id];
         depth_ = a.out_depth[pix_id];
     }
+    if (!inside) T = -1.0f;
+    const float opaque_thr = a.opaque_thr, T_thr = a.T_thr;
+    const uint32_t sp_base = smem_addr(s_sp), list_base = smem_addr(&s_list[warp][0]);
 
+    // The walk keeps the warp converged: every lane executes every list entry of its warp and folds the reference's
+    // early-outs (forward.cu:766-848) into predicates, so the body is straight-line code.  Lists are padded with the
+    // sentinel to an even length and walked two entries per trip (one all-terminated vote per trip).  The geometry of the
+    // first opaque hit (forward.cu:785-812) depends only on the hit Gaussian and the pixel: the loop records the event,
+    // the plane / normal math runs once per pixel after the walk.
+    float hit_w = 0.f; // alpha * T at the hit event
     int i = 0;
     for (; i < rounds; i++) {
-        if (__syncthreads_count(done) == 256) break;
+        if (__syncthreads_count(__float_as_int(T) < 0) == 256) break;
         const int progress = i * 256 + tid;
         const int n = min(256, total - i * 256);
         if (progress < total) {
@@ -882,88 +913,105 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(RenderArgs a) {
         __syncthreads();
         // per-warp compaction of the batch (order preserved)
         int cnt = 0;
-        if (!__all_sync(0xFFFFFFFFu, done)) {
+        if (!__all_sync(0xFFFFFFFFu, __float_as_int(T) < 0)) {
             for (int b = 0; b < n; b += 32) {
                 const int j = b + lane;
                 const bool m = (j < n) && ((s_mask[j] >> warp) & 1);
                 const unsigned bal = __ballot_sync(0xFFFFFFFFu, m);
-                if (m) s_list[warp][cnt + __popc(bal & ((1u << lane) - 1))] = (uint8_t)j;
+                if (m) s_list[warp][cnt + __popc(bal & ((1u << lane) - 1))] = (uint16_t)j;
                 cnt += __popc(bal);
             }
+            if (lane == 0) s_list[warp][cnt] = 256; // sentinel: pads an odd list
             __syncwarp();
         }
-        for (int k = 0; !done && k < cnt; k++) {
-            const int j = s_list[warp][k];
-            const float4 r0 = s_sp[j].r0;
-            const float4 r1 = s_sp[j].r1;
-            const float dx = fsub(r0.x, pixfx), dy = fsub(r0.y, pixfy);
-            const float power = ffma(ffma(dx, fmul(dx, r0.z), fmul(dy, fmul(dy, r1.x))), -0.5f, -fmul(dy, fmul(dx, r0.w)));
-            if (power > 0.0f || power < r1.z) continue;
-            const float alpha = fminf(0.99f, fmul(r1.y, expf(power)));
-            if (alpha < 1.0f / 255.0f) continue;
-
-            if (!hit && alpha >= a.opaque_thr) {
-                const int id = __float_as_int(s_sp[j].c.w);
-                const float sx = a.scales[3 * id], sy = a.scales[3 * id + 1], sz = a.scales[3 * id + 2];
-                const float4 q = reinterpret_cast<const float4 *>(a.rotations)[id];
-                const QuatMat R = quat_to_glm(q.x, q.y, q.z, q.w);
-                const int ax = arg_min3(sx, sy, sz);
-                const float nx = R.c0[ax], ny = R.c1[ax], nz = R.c2[ax];
-                const float smax = fmul(fmaxf(fmaxf(sx, sy), sz), a.scale_mod);
-                const float *v = a.view;
-                const float ncx = xform_row3(v, 0, nx, ny, nz), ncy = xform_row3(v, 1, nx, ny, nz),
-                            ncz = xform_row3(v, 2, nx, ny, nz);
-                const float wx = a.means3D[3 * id], wy = a.means3D[3 * id + 1], wz = a.means3D[3 * id + 2];
-                const float pcx = xform_row(v, 0, wx, wy, wz), pcy = xform_row(v, 1, wx, wy, wz),
-                            pcz = xform_row(v, 2, wx, wy, wz);
-                const float3 ray = pixel_ray(pix_x, pix_y, a.fx, a.fy, a.cx, a.cy);
-                const float num = dot3_ref(pcx, ncx, pcy, ncy, pcz, ncz);
-                const float den = dot3_ref(ray.x, ncx, ray.y, ncy, ray.z, ncz);
-                const float t = (float)((double)num / ((double)den + 1e-8));
-                const float hx = fmul(t, ray.x), hy = fmul(t, ray.y), hz = fmul(t, ray.z);
-                const float depth_distance = fabsf(fsub(hz, pcz));
-                const float angle_distance = fabsf(den);
-                hit_id = id;
-                hit_dw = fmul(alpha, T);
-                if (depth_distance <= fmul(smax, a.depth_thr) && angle_distance >= a.normal_thr)
-                    depth_ = hz;
-                else
-                    depth_ = a.depth[id];
-                a.hit_geo[sp] = ncx;
-                a.hit_geo[a.plane + sp] = ncy;
-                a.hit_geo[2 * a.plane + sp] = ncz;
-                a.hit_geo[3 * a.plane + sp] = hx;
-                a.hit_geo[4 * a.plane + sp] = hy;
-                a.hit_geo[5 * a.plane + sp] = hz;
-                hit = true;
-            }
-            const float test_T = fmul(T, fsub(1.0f, alpha));
-            if (test_T < a.T_thr && hit) {
-                done = true;
-                continue;
-            }
-            if (test_T >= a.T_thr) {
+        int last_j = -1; // batch slot of the last entry accumulated by this pixel
+        for (int k = 0; k < cnt; k += 2) {
+            if (__all_sync(0xFFFFFFFFu, __float_as_int(T) < 0)) break;
+            const uint32_t jj = lds_u16x2(list_base + 2 * k);
+            unsigned nt_m[2] = {0u, 0u};
+            int nt_id[2] = {0, 0};
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int j = h ? (int)(jj >> 16) : (int)(jj & 0xFFFFu);
+                const uint32_t e = sp_base + (uint32_t)j * 48u;
+                const float4 r0 = lds128(e);
+                const float4 r1 = lds128(e + 16);
+                const float4 r2 = lds128(e + 32);
+                const float dx = fsub(r0.x, pixfx), dy = fsub(r0.y, pixfy);
+                const float power = ffma(ffma(dx, fmul(dx, r0.z), fmul(dy, fmul(dy, r1.x))), -0.5f, -fmul(dy, fmul(dx, r0.w)));
+                const float alpha = fminf(0.99f, fmul(r1.y, expf(power)));
+                // live: the pixel is still being blended and the pair passes the reference's rejections (power > 0,
+                // alpha < 1/255; the staged power_reject bound is implied by the alpha test)
+                const bool live = (__float_as_int(T) >= 0) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
                 const float w = fmul(alpha, T);
-                const float4 r2 = s_sp[j].c;
-                C0 = ffma(r2.x, w, C0);
-                C1 = ffma(r2.y, w, C1);
-                C2 = ffma(r2.z, w, C2);
-                if (w > cw_max) {
-                    cw_max = w;
-                    hit_color_id = __float_as_int(r2.w);
-                    hit_cw = w;
+                const float test_T = fmul(T, fsub(1.0f, alpha));
+                const int id = __float_as_int(r2.w);
+                const bool opq = live && (hit_state == -1) && (alpha >= opaque_thr); // first opaque hit of this pixel
+                hit_state = opq ? id : hit_state;
+                hit_w = opq ? w : hit_w;
+                const bool acc = live && (test_T >= T_thr);
+                const bool stop = live && (test_T < T_thr) && (hit_state != -1);
+                C0 = acc ? ffma(r2.x, w, C0) : C0;
+                C1 = acc ? ffma(r2.y, w, C1) : C1;
+                C2 = acc ? ffma(r2.z, w, C2) : C2;
+                const bool better = acc && (w > cw_max);
+                cw_max = better ? w : cw_max;
+                hit_color_id = better ? id : hit_color_id;
+                if (NT) { // pairs with T > 0.5 (forward.cu:836-839): one vote per entry, one rare branch per trip
+                    nt_m[h] = __ballot_sync(0xFFFFFFFFu, acc && test_T > 0.5f);
+                    nt_id[h] = id;
                 }
-                if (a.n_touched && test_T > 0.5f) {
-                    const int id = __float_as_int(r2.w);
-                    const unsigned m = __match_any_sync(__activemask(), id);
-                    if (lane == __ffs(m) - 1) atomicAdd(&a.n_touched[id], __popc(m));
-                }
-                ncontrib = base + i * 256 + j + 1;
-                end_T = test_T;
+                last_j = acc ? j : last_j;
+                end_T = acc ? test_T : end_T;
+                // a terminated pixel keeps its T (the output needs it) with the sign bit set
+                T = live ? (stop ? -T : test_T) : T;
             }
-            T = test_T;
+            if (NT && (nt_m[0] | nt_m[1]) != 0 && lane == 0) {
+                if (nt_m[0]) atomicAdd(&a.n_touched[nt_id[0]], __popc(nt_m[0]));
+                if (nt_m[1]) atomicAdd(&a.n_touched[nt_id[1]], __popc(nt_m[1]));
+            }
         }
+        if (last_j >= 0) ncontrib = base + i * 256 + last_j + 1;
     }
+    const bool done = __float_as_int(T) < 0;
+    T = fabsf(T);
+    if (hit_state >= 0) { // geometry of the first opaque hit (forward.cu:785-812)
+        const int id = hit_state;
+        const float sx = a.scales[3 * id], sy = a.scales[3 * id + 1], sz = a.scales[3 * id + 2];
+        const float4 q = reinterpret_cast<const float4 *>(a.rotations)[id];
+        const QuatMat R = quat_to_glm(q.x, q.y, q.z, q.w);
+        const int ax = arg_min3(sx, sy, sz);
+        const float nx = ax == 0 ? R.c0[0] : (ax == 1 ? R.c0[1] : R.c0[2]);
+        const float ny = ax == 0 ? R.c1[0] : (ax == 1 ? R.c1[1] : R.c1[2]);
+        const float nz = ax == 0 ? R.c2[0] : (ax == 1 ? R.c2[1] : R.c2[2]);
+        const float smax = fmul(fmaxf(fmaxf(sx, sy), sz), a.scale_mod);
+        const float *v = a.view;
+        const float ncx = xform_row3(v, 0, nx, ny, nz), ncy = xform_row3(v, 1, nx, ny, nz),
+                    ncz = xform_row3(v, 2, nx, ny, nz);
+        const float wx = a.means3D[3 * id], wy = a.means3D[3 * id + 1], wz = a.means3D[3 * id + 2];
+        const float pcx = xform_row(v, 0, wx, wy, wz), pcy = xform_row(v, 1, wx, wy, wz),
+                    pcz = xform_row(v, 2, wx, wy, wz);
+        const float3 ray = pixel_ray(pix_x, pix_y, a.fx, a.fy, a.cx, a.cy);
+        const float num = dot3_ref(pcx, ncx, pcy, ncy, pcz, ncz);
+        const float den = dot3_ref(ray.x, ncx, ray.y, ncy, ray.z, ncz);
+        const float t = (float)((double)num / ((double)den + 1e-8));
+        const float hx = fmul(t, ray.x), hy = fmul(t, ray.y), hz = fmul(t, ray.z);
+        const float depth_distance = fabsf(fsub(hz, pcz));
+        const float angle_distance = fabsf(den);
+        hit_id = id;
+        hit_dw = hit_w;
+        if (depth_distance <= fmul(smax, a.depth_thr) && angle_distance >= a.normal_thr)
+            depth_ = hz;
+        else
+            depth_ = a.depth[id];
+        a.hit_geo[sp] = ncx;
+        a.hit_geo[a.plane + sp] = ncy;
+        a.hit_geo[2 * a.plane + sp] = ncz;
+        a.hit_geo[3 * a.plane + sp] = hx;
+        a.hit_geo[4 * a.plane + sp] = hy;
+        a.hit_geo[5 * a.plane + sp] = hz;
+    }
+    const float hit_cw = hit_color_id >= 0 ? cw_max : 0.f;
     if (tid == 0 && a.status) atomicAdd(&a.status[DQO_ST_WALKED], min(total, i * 256));
     if (PHASE == 1) {
         const bool unfinished = __syncthreads_count(done) < 256;
@@ -1497,7 +1545,8 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         }
         int rc = compact_fork(nullptr);
         if (rc) return rc;
-        render_forward_kernel<0><<<T, 256, 0, stream>>>(ra);
+        if (ra.n_touched) render_forward_kernel<0, true><<<T, 256, 0, stream>>>(ra);
+        else render_forward_kernel<0, false><<<T, 256, 0, stream>>>(ra);
         DQO_LAUNCH_CHECK("render forward", debug, stream);
         if ((rc = compact_join())) return rc;
         stage_mark(stream, ST_RENDER_FWD);
@@ -1509,7 +1558,8 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     uint32_t *mask_bits_b = (uint32_t *)(img + IL.mask_bits_b);
     int rc = bin_phase(1, front, 0, d_mask_bits, DQO_ST_R_FRONT, ranges);
     if (rc) return rc;
-    render_forward_kernel<1><<<T, 256, 0, stream>>>(ra);
+    if (ra.n_touched) render_forward_kernel<1, true><<<T, 256, 0, stream>>>(ra);
+    else render_forward_kernel<1, false><<<T, 256, 0, stream>>>(ra);
     DQO_LAUNCH_CHECK("render forward (front)", debug, stream);
     stage_mark(stream, ST_RENDER_FRONT);
     mask_unfinished_kernel<<<1, 1024, 0, stream>>>(IL.tiles_x, IL.tiles_y, IL.mask_words, d_mask_bits, ra.unfinished,
@@ -1519,7 +1569,8 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     if (rc) return rc;
     stage_mark(stream, ST_BACK_BIN);
     if ((rc = compact_fork(ranges_b))) return rc;
-    render_forward_kernel<2><<<T, 256, 0, stream>>>(ra);
+    if (ra.n_touched) render_forward_kernel<2, true><<<T, 256, 0, stream>>>(ra);
+    else render_forward_kernel<2, false><<<T, 256, 0, stream>>>(ra);
     DQO_LAUNCH_CHECK("render forward (back)", debug, stream);
     if ((rc = compact_join())) return rc;
     stage_mark(stream, ST_RENDER_FWD);
