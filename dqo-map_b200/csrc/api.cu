@@ -7,6 +7,7 @@
 //     not serialise, and nothing is created or destroyed on the hot path after the first call on a stream;
 //   * the launch counter is a relaxed atomic (instrumentation only).
 #include "common.cuh"
+#include <cstdlib>
 #include <atomic>
 #include <mutex>
 #include <stdarg.h>
@@ -24,6 +25,13 @@ void set_error(const char *fmt, ...) {
 }
 
 static std::atomic<long long> g_launches{0};
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("DQO_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // NVTX ranges around the C-ABI entry points (visible in nsys / ncu --nvtx; a no-op without a tool attached)

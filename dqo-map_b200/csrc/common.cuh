@@ -57,6 +57,36 @@ enum {
         }                                                                                     \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------
+// The step is a chain of ~45 short kernels on one stream; with plain stream order every kernel boundary costs the drain
+// of the previous grid plus the launch / block-scheduling latency of the next.  Kernels that start with pdl_enter() and
+// are launched through launch_pdl() let the next grid become resident while the previous one is finishing: the
+// dependent's blocks are scheduled as soon as every block of the predecessor has STARTED (launch_dependents is the first
+// instruction) and then block in griddepcontrol.wait until the predecessor has COMPLETED and its writes are visible, so
+// no kernel touches memory earlier than under stream order.  Rule: launch_pdl() only for kernels that call pdl_enter()
+// before their first global-memory access (a kernel without the wait could finish before its predecessor and break the
+// transitive ordering of the chain).  Memsets / event waits between kernels simply fall back to full serialisation.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled(); // api.cu: on unless the environment says DQO_PDL=0 (A/B measurements)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- exact-op helpers -------------------------------------------------------------------------

@@ -34,6 +34,7 @@ __device__ __forceinline__ bool depth_valid(const LossArgs &a, size_t p, bool m,
 }
 
 __global__ void __launch_bounds__(LOSS_THREADS) loss_partial_kernel(LossArgs a) {
+    pdl_enter();
     const size_t N = (size_t)a.W * a.H;
     double cs = 0.0, ds = 0.0;
     double cn = 0.0, dn = 0.0;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_partial_kernel(LossArgs a) 
 }
 
 __global__ void __launch_bounds__(LOSS_THREADS) loss_grad_kernel(LossArgs a, int nparts) {
+    pdl_enter();
     __shared__ double tot[4];
     { // fixed-pattern (deterministic) final reduction, redundantly per block: warp q sums quantity q
         const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -144,6 +146,7 @@ __device__ __forceinline__ void adam_elem(float &p, float g, float &m, float &v,
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(AdamPack k) {
+    pdl_enter();
     int t = 0;
     const int chunk = blockIdx.x;
     while (t + 1 < k.n && chunk >= k.chunk_start[t + 1]) t++;
@@ -184,6 +187,7 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamPack k) {
 }
 
 __global__ void __launch_bounds__(256) confidence_kernel(long long rows, int width, const float *__restrict__ grad, float *conf) {
+    pdl_enter();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     bool any = false;
@@ -209,6 +213,7 @@ __device__ __forceinline__ void scatter_max(float *addr, float val) {
     if (val > 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(val));
 }
 __global__ void __launch_bounds__(256) acc_error_kernel(AccErrArgs a) {
+    pdl_enter();
     const size_t N = (size_t)a.W * a.H;
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
@@ -237,6 +242,7 @@ __global__ void __launch_bounds__(256) acc_error_kernel(AccErrArgs a) {
     }
 }
 __global__ void __launch_bounds__(256) acc_error_mean_kernel(AccErrArgs a) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.P) return;
     const int c = a.cc[i], d = a.dc[i], n = a.nc[i];
@@ -274,8 +280,8 @@ extern "C" int dqo_masked_l1_loss(int32_t W, int32_t H, const float *image, cons
     const size_t N = (size_t)W * H;
     int blocks = (int)((N + LOSS_THREADS - 1) / LOSS_THREADS);
     if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
-    loss_partial_kernel<<<blocks, LOSS_THREADS, 0, stream>>>(a);
-    loss_grad_kernel<<<blocks, LOSS_THREADS, 0, stream>>>(a, blocks);
+    launch_pdl(loss_partial_kernel, dim3(blocks), dim3(LOSS_THREADS), 0, stream, a);
+    launch_pdl(loss_grad_kernel, dim3(blocks), dim3(LOSS_THREADS), 0, stream, a, blocks);
     DQO_LAUNCH_CHECK("masked l1 loss", 0, stream);
     return DQO_OK;
 }
@@ -313,14 +319,14 @@ extern "C" int dqo_adam_step(const dqo_adam_tensor *tensors, int32_t n_tensors, 
     k.chunk_start[n] = chunks;
     k.n = n;
     if (chunks > 0) {
-        adam_kernel<<<chunks, 256, 0, stream>>>(k);
+        launch_pdl(adam_kernel, dim3(chunks), dim3(256), 0, stream, k);
         DQO_LAUNCH_CHECK("adam", 0, stream);
     }
     if (confidence && conf_tensor >= 0 && conf_tensor < n_tensors) {
         const dqo_adam_tensor &t = tensors[conf_tensor];
         if (t.grad && t.row_width > 0 && t.numel > 0) {
             const long long rows = t.numel / t.row_width;
-            confidence_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(rows, t.row_width, t.grad, confidence);
+            launch_pdl(confidence_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, stream, rows, t.row_width, t.grad, confidence);
             DQO_LAUNCH_CHECK("confidence", 0, stream);
         }
     }
@@ -363,8 +369,8 @@ extern "C" int dqo_accumulate_error(int32_t W, int32_t H, int32_t P, const float
     a.di = depth_index; a.cthr = color_thr; a.dthr = depth_thr; a.nthr = normal_thr; a.check_max = check_max;
     a.gce = gs_color_error; a.gde = gs_depth_error; a.gne = gs_normal_error; a.resc = rescale_counter;
     a.cc = color_counter; a.dc = depth_counter; a.nc = normal_counter;
-    acc_error_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(a);
-    if (!check_max) acc_error_mean_kernel<<<(P + 255) / 256, 256, 0, stream>>>(a);
+    launch_pdl(acc_error_kernel, dim3((unsigned)((N + 255) / 256)), dim3(256), 0, stream, a);
+    if (!check_max) launch_pdl(acc_error_mean_kernel, dim3((P + 255) / 256), dim3(256), 0, stream, a);
     DQO_LAUNCH_CHECK("accumulate error", 0, stream);
     return DQO_OK;
 }

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) activate_kernel(int P, const float *__res
                                                        const float *__restrict__ scaling_log,
                                                        const float *__restrict__ rotation_raw, float *opacity, float *scales,
                                                        float *rot) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     opacity[i] = 1.0f / (1.0f + expf(-opacity_raw[i]));
@@ -129,6 +130,7 @@ struct PrepareArgs {
     AdamScalars *out;
 };
 __global__ void adam_prepare_kernel(PrepareArgs a) {
+    pdl_enter();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int overflow = a.status[DQO_ST_OVERFLOW];
     int step = a.host_step;
@@ -159,6 +161,7 @@ __global__ void adam_prepare_kernel(PrepareArgs a) {
 }
 // number of Gaussians whose initial opacity is below the attach threshold (mapper.py:810-812)
 __global__ void __launch_bounds__(256) attach_count_kernel(int P, const float *__restrict__ init_opacity, float thr, int *count) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = (i < P) && (1.0f / (1.0f + expf(-init_opacity[i])) < thr);
     const unsigned b = __ballot_sync(0xFFFFFFFFu, in);
@@ -278,6 +281,7 @@ __device__ __forceinline__ float adam_gaussian(const SmallArgs &a, const AdamSca
 }
 // one thread per Gaussian over the whole cloud (unaligned tensors, or no `ever` bookkeeping)
 __global__ void __launch_bounds__(256) adam_geometry_kernel(SmallArgs a) {
+    pdl_enter();
     const AdamScalars k = *a.kd;
     if (k.skip) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,6 +300,7 @@ struct ListArgs {
     float *f_rest, *m_rest, *v_rest;
 };
 __global__ void __launch_bounds__(256) adam_list_kernel(ListArgs a) {
+    pdl_enter();
     const AdamScalars k = *a.s.kd;
     if (k.skip) return;
     const int n = *a.count;
@@ -307,6 +312,7 @@ __global__ void __launch_bounds__(256) adam_list_kernel(ListArgs a) {
 // f_rest [P,45] of the listed Gaussians: consecutive threads walk the 45 coefficients of one Gaussian (180-byte runs);
 // the gradient comes from the merged [P,16,3] layout (row stride 48, offset 3)
 __global__ void __launch_bounds__(256) adam_rest_list_kernel(ListArgs a) {
+    pdl_enter();
     const AdamScalars k = *a.s.kd;
     if (k.skip) return;
     const unsigned total = (unsigned)(*a.count) * 45u;
@@ -514,6 +520,7 @@ __device__ __forceinline__ float adam_flat_body(const FlatArgs &fa, const AdamSc
     return 0.f;
 }
 __global__ void __launch_bounds__(256) adam_flat_kernel(FlatArgs fa) {
+    pdl_enter();
     const AdamScalars k = *fa.s.kd;
     if (k.skip) return;
     const float att = adam_flat_body(fa, k, blockIdx.x);
@@ -566,6 +573,7 @@ __device__ __forceinline__ void adam_rest_body(const RestAdamArgs &a, const Adam
     reinterpret_cast<float4 *>(a.v_rest)[q] = v;
 }
 __global__ void __launch_bounds__(256) adam_rest_kernel(RestAdamArgs a) {
+    pdl_enter();
     const AdamScalars k = *a.kd;
     if (k.skip) return;
     const long long base = (long long)blockIdx.x * (256 * ADAM_REST_CHUNKS) + threadIdx.x;
@@ -581,6 +589,7 @@ __global__ void __launch_bounds__(256) adam_rest_kernel(RestAdamArgs a) {
     }
 }
 __global__ void adam_rest_tail_kernel(long long begin, long long end, RestAdamArgs a) {
+    pdl_enter();
     const long long e = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const AdamScalars k = *a.kd;
     if (e >= end || k.skip) return;
@@ -628,7 +637,7 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
     float *act_op = (float *)(ws + L.act_opacity), *act_sc = (float *)(ws + L.act_scales), *act_rot = (float *)(ws + L.act_rot);
     float *xyz = p->param[0], *f_dc = p->param[1], *f_rest = (M == 16) ? p->param[2] : nullptr;
     const int nb = (P + 255) / 256;
-    activate_kernel<<<nb, 256, 0, stream>>>(P, p->param[3], p->param[4], p->param[5], act_op, act_sc, act_rot);
+    launch_pdl(activate_kernel, dim3(nb), dim3(256), 0, stream, P, p->param[3], p->param[4], p->param[5], act_op, act_sc, act_rot);
     DQO_LAUNCH_CHECK("activate", s->debug, stream);
 
     float *color = (float *)(ws + L.color), *depth = (float *)(ws + L.depth);
@@ -668,7 +677,7 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
         pa.attach_thr = p->attach_opacity_thres;
         pa.attach_count = attach ? p->attach_count : nullptr;
         pa.out = kd;
-        adam_prepare_kernel<<<1, 32, 0, stream>>>(pa);
+        launch_pdl(adam_prepare_kernel, dim3(1), dim3(32), 0, stream, pa);
         DQO_LAUNCH_CHECK("adam prepare", s->debug, stream);
     }
     SmallArgs sa;
@@ -695,8 +704,8 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
         la.s = sa; la.list = p->ever_list; la.count = p->ever_count;
         la.f_rest = f_rest; la.m_rest = p->exp_avg[2]; la.v_rest = p->exp_avg_sq[2];
         const int blocks = nb < 148 * 8 ? nb : 148 * 8;
-        adam_list_kernel<<<blocks, 256, 0, stream>>>(la);
-        if (M == 16) adam_rest_list_kernel<<<148 * 8, 256, 0, stream>>>(la);
+        launch_pdl(adam_list_kernel, dim3(blocks), dim3(256), 0, stream, la);
+        if (M == 16) launch_pdl(adam_rest_list_kernel, dim3(148 * 8), dim3(256), 0, stream, la);
         DQO_LAUNCH_CHECK("adam (listed Gaussians)", s->debug, stream);
         note_launch(M == 16 ? 1 : 0);
         nvtx_pop();
@@ -713,9 +722,9 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
         if (fa.nb_scalar == 0) fa.nb_scalar = 1;
         fa.nb_gauss = (unsigned)nb;
         const unsigned vblocks = 2 * fa.nb_vec3 + fa.nb_scalar + 2 * fa.nb_gauss;
-        adam_flat_kernel<<<vblocks, 256, 0, stream>>>(fa);
+        launch_pdl(adam_flat_kernel, dim3(vblocks), dim3(256), 0, stream, fa);
     } else {
-        adam_geometry_kernel<<<nb, 256, 0, stream>>>(sa);
+        launch_pdl(adam_geometry_kernel, dim3(nb), dim3(256), 0, stream, sa);
     }
     DQO_LAUNCH_CHECK("adam geometry", s->debug, stream);
     if (M == 16) {
@@ -724,8 +733,8 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
         ra.n4 = total / 4; ra.f_rest = f_rest; ra.m_rest = p->exp_avg[2]; ra.v_rest = p->exp_avg_sq[2]; ra.g_sh = g_sh;
         ra.ever = p->ever; ra.kd = kd;
         if (ra.n4 > 0)
-            adam_rest_kernel<<<(unsigned)((ra.n4 + 256 * ADAM_REST_CHUNKS - 1) / (256 * ADAM_REST_CHUNKS)), 256, 0, stream>>>(ra);
-        if (total % 4) adam_rest_tail_kernel<<<1, 32, 0, stream>>>(ra.n4 * 4, total, ra);
+            launch_pdl(adam_rest_kernel, dim3((unsigned)((ra.n4 + 256 * ADAM_REST_CHUNKS - 1) / (256 * ADAM_REST_CHUNKS))), dim3(256), 0, stream, ra);
+        if (total % 4) launch_pdl(adam_rest_tail_kernel, dim3(1), dim3(32), 0, stream, ra.n4 * 4, total, ra);
         DQO_LAUNCH_CHECK("adam f_rest", s->debug, stream);
     }
     nvtx_pop();
@@ -742,7 +751,7 @@ extern "C" int dqo_attach_count(int32_t P, const float *init_opacity, float opac
     }
     DQO_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), stream));
     if (P == 0) return DQO_OK;
-    attach_count_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, init_opacity, opacity_thres, count);
+    launch_pdl(attach_count_kernel, dim3((P + 255) / 256), dim3(256), 0, stream, P, init_opacity, opacity_thres, count);
     DQO_LAUNCH_CHECK("attach count", 0, stream);
     return DQO_OK;
 }

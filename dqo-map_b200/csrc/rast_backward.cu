@@ -218,6 +218,7 @@ struct __align__(16) SplatB {
 };
 
 __global__ void __launch_bounds__(RB_THREADS, RB_OCC) render_backward_kernel(RenderBwdArgs a) {
+    pdl_enter();
     // RB_BATCH entries are staged per round.  With 512 most tiles need a single round (max n_contrib is a few hundred):
     // the four warps then walk their own lists without meeting at a barrier after every 256 entries, where the fast
     // ones used to wait for the slowest sub-block.
@@ -385,6 +386,7 @@ __device__ __constant__ float B_SH_C3[7] = {-0.5900435899266435f, 2.890611442640
 // SHMODE 1: staged merged SH, 2: staged split f_dc / f_rest inputs (gradients are still written merged), 0: plain.
 template <int SHMODE>
 __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussBwdArgs a) {
+    pdl_enter();
     extern __shared__ float4 s_row[];
     constexpr bool STAGED = SHMODE != 0;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -842,7 +844,7 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     ra.hit_geo = (const float *)(img + IL.hit_geo);
     ra.plane = (size_t)IL.T * 256;
     ra.dL_dpix = dL_dout_color; ra.dL_ddepth = dL_dout_depth; ra.hit_image = hit_image; ra.gacc = gacc;
-    render_backward_kernel<<<IL.T, RB_THREADS, 0, stream>>>(ra);
+    launch_pdl(render_backward_kernel, dim3(IL.T), dim3(RB_THREADS), 0, stream, ra);
     DQO_LAUNCH_CHECK("render backward", s->debug, stream);
     stage_mark(stream, ST_RENDER_BWD);
 
@@ -868,11 +870,11 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
             set_error("split SH input requires M == 16 and 16-byte aligned f_dc / f_rest / dL_dsh");
             return DQO_ERR_INVALID_ARG;
         }
-        gaussian_backward_kernel<2><<<gb_blocks, GB_THREADS, gb_smem, stream>>>(ga);
+        launch_pdl(gaussian_backward_kernel<2>, dim3(gb_blocks), dim3(GB_THREADS), gb_smem, stream, ga);
     } else if (staged)
-        gaussian_backward_kernel<1><<<gb_blocks, GB_THREADS, gb_smem, stream>>>(ga);
+        launch_pdl(gaussian_backward_kernel<1>, dim3(gb_blocks), dim3(GB_THREADS), gb_smem, stream, ga);
     else
-        gaussian_backward_kernel<0><<<gb_blocks, GB_THREADS, 0, stream>>>(ga);
+        launch_pdl(gaussian_backward_kernel<0>, dim3(gb_blocks), dim3(GB_THREADS), 0, stream, ga);
     DQO_LAUNCH_CHECK("gaussian backward", s->debug, stream);
     stage_mark(stream, ST_GAUSS_BWD);
     return DQO_OK;

@@ -225,6 +225,7 @@ __device__ __forceinline__ bool frustum_test(float px, float py, float pz, const
 // preprocess, the depth sort runs on a side stream concurrently with it.
 __global__ void __launch_bounds__(256) depth_key_kernel(int P, const float *__restrict__ means, const float *__restrict__ view,
                                                         const float *__restrict__ proj, uint32_t *depth_key) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     float vz, ppx, ppy;
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(256) depth_key_kernel(int P, const float *__re
 // tile_mask != 0 as one bitmap row per tile row: the per-Gaussian tile count and the instance emission then cost
 // O(rows x words) instead of one global load per tile of the rectangle
 __global__ void mask_bits_kernel(int gx, int gy, int words, const int *__restrict__ tile_mask, uint32_t *bits) {
+    pdl_enter();
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= gy * words) return;
     const int y = w / words, word = w % words, x = word * 32 + (threadIdx.x & 31);
@@ -275,6 +277,7 @@ struct ShPtr {
 // 45-float rows of f_rest are conflict-free for per-thread scalar reads as they lie.  SHMODE 0: plain pointer.
 template <int SHMODE>
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
+    pdl_enter();
     extern __shared__ float4 s_sh[];
     constexpr bool STAGED = SHMODE == 1;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -461,6 +464,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
 
 __global__ void mark_visible_kernel(int P, const float *__restrict__ means, const float *__restrict__ view,
                                     const float *__restrict__ proj, uint8_t *present) {
+    pdl_enter();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     float vz, ppx, ppy;
@@ -509,6 +513,7 @@ __global__ void __launch_bounds__(256)
                      const uint32_t *offsets, const uint2 *__restrict__ rect, const uint32_t *__restrict__ mask_bits,
                      const uint32_t *__restrict__ row_any, int mask_words, uint32_t *tiles_rank, uint32_t *sums,
                      uint32_t *group_sums) {
+    pdl_enter();
     __shared__ uint32_t s_w[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t i = (int64_t)blockIdx.x * 256 + tid;
@@ -550,6 +555,7 @@ __global__ void __launch_bounds__(256)
                 const uint32_t *__restrict__ mask_bits, const uint32_t *__restrict__ row_any, int mask_words, int grid_x,
                 KeyT *__restrict__ keys, uint32_t *__restrict__ vals, const uint32_t *__restrict__ sums,
                 const uint32_t *__restrict__ group_sums, int *status) {
+    pdl_enter();
     __shared__ uint32_t s_n[257];
     __shared__ uint32_t s_warp_tot[8], s_warp_pre[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -659,6 +665,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(1024)
     mask_unfinished_kernel(int tiles_x, int tiles_y, int mask_words, const uint32_t *__restrict__ mask_bits,
                            const int *__restrict__ unfinished, uint32_t *mask_bits_b, uint32_t *row_any) {
+    pdl_enter();
     __shared__ uint32_t s_any[64];
     const int row_words = (tiles_y + 31) / 32;
     for (int k = threadIdx.x; k < 64; k += blockDim.x) s_any[k] = 0;
@@ -681,6 +688,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(256)
     tile_ranges_kernel(int64_t capacity, const KeyT *__restrict__ keys, const int *__restrict__ status, int count_word,
                        uint2 *ranges) {
+    pdl_enter();
     const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
     const int64_t L = status[DQO_ST_OVERFLOW] ? 0 : status[count_word];
     if (base >= L) return;
@@ -718,6 +726,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(1024) compact_tiles_kernel(int T, const uint2 *__restrict__ ranges,
                                                              const uint2 *__restrict__ ranges_b, int *tile_indices,
                                                              int *status) {
+    pdl_enter();
     __shared__ int warp_sums[32];
     __shared__ int base;
     if (threadIdx.x == 0) base = 0;
@@ -814,6 +823,7 @@ __device__ __forceinline__ uint32_t lds_u16x2(uint32_t addr) {
 
 template <int PHASE, bool NT>
 __global__ void __launch_bounds__(256, 4) render_forward_kernel(RenderArgs a) {
+    pdl_enter();
     __shared__ SplatS s_sp[257]; // one 48-byte record per staged splat (+ an all-zero sentinel that never contributes)
     __shared__ uint8_t s_mask[256];
     __shared__ __align__(16) uint16_t s_list[8][RF_LIST_STRIDE];
@@ -1057,6 +1067,7 @@ struct ExtraArgs {
     float *out_color;
 };
 __global__ void __launch_bounds__(256) blend_extra_kernel(ExtraArgs a) {
+    pdl_enter();
     __shared__ SplatS s_sp[256];
     __shared__ uint8_t s_mask[256];
     __shared__ uint8_t s_list[8][256];
@@ -1156,6 +1167,7 @@ template <typename KeyT>
 __global__ void export_instances_kernel(int64_t capacity, const int *__restrict__ status,
                                         const KeyT *__restrict__ keys, const uint32_t *__restrict__ vals,
                                         const float *__restrict__ depth, uint64_t *out_keys, uint32_t *out_list) {
+    pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= capacity) return;
     const int64_t L = status[DQO_ST_OVERFLOW] ? 0 : status[DQO_ST_NUM_RENDERED];
@@ -1172,6 +1184,7 @@ __global__ void export_instances_kernel(int64_t capacity, const int *__restrict_
 __global__ void export_pixels_kernel(int W, int H, int grid_x, const uint32_t *__restrict__ n_contrib,
                                      const float *__restrict__ final_T, const uint2 *__restrict__ ranges,
                                      const uint2 *__restrict__ ranges_b, uint32_t *out_nc, float *out_T) {
+    pdl_enter();
     const int tile = blockIdx.x, tid = threadIdx.x;
     const int lx = tid & 15, ly = tid >> 4;
     const int px = (tile % grid_x) * 16 + lx, py = (tile / grid_x) * 16 + ly;
@@ -1189,6 +1202,7 @@ __global__ void export_pixels_kernel(int W, int H, int grid_x, const uint32_t *_
 __global__ void export_gauss_kernel(int P, const float4 *__restrict__ rec, const uint32_t *__restrict__ tiles,
                                     const uint8_t *__restrict__ flags, const float *__restrict__ depth_in, float *means2D,
                                     float *depths, float *conic_o, float *rgb, uint32_t *tiles_out) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const bool valid = (flags[i] & 0x80) != 0;
@@ -1244,7 +1258,7 @@ extern "C" int dqo_mark_visible(int32_t P, const float *means3D, const float *vi
         return DQO_ERR_INVALID_ARG;
     }
     if (P == 0) return DQO_OK;
-    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, projmatrix, present);
+    launch_pdl(mark_visible_kernel, dim3((P + 255) / 256), dim3(256), 0, stream, P, means3D, viewmatrix, projmatrix, present);
     DQO_LAUNCH_CHECK("mark_visible", 0, stream);
     return DQO_OK;
 }
@@ -1366,7 +1380,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         DQO_CUDA_CHECK(cudaMemsetAsync(geom + GL.sums, 0, 2 * GL.sums_stride, stream));
         {
             const int nw = IL.tiles_y * IL.mask_words;
-            mask_bits_kernel<<<(nw + 7) / 8, 256, 0, stream>>>(IL.tiles_x, IL.tiles_y, IL.mask_words, tile_mask, mask_bits);
+            launch_pdl(mask_bits_kernel, dim3((nw + 7) / 8), dim3(256), 0, stream, IL.tiles_x, IL.tiles_y, IL.mask_words, tile_mask, mask_bits);
             DQO_LAUNCH_CHECK("mask bits", debug, stream);
         }
         PreArgs pa;
@@ -1393,7 +1407,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         // fork: depth keys + the (depth, id) sort of the Gaussians (stable LSD sort on the depth bits) on the side
         // stream, concurrently with the rest of the preprocess
         uint32_t *order = (uint32_t *)(geom + GL.order);
-        depth_key_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, projmatrix, pa.depth_key);
+        launch_pdl(depth_key_kernel, dim3((P + 255) / 256), dim3(256), 0, stream, P, means3D, viewmatrix, projmatrix, pa.depth_key);
         DQO_LAUNCH_CHECK("depth keys", debug, stream);
         cudaStream_t sort_stream = stream;
         if (fj) {
@@ -1409,11 +1423,11 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
                 set_error("split SH input requires M == 16 and 16-byte aligned f_dc / f_rest");
                 return DQO_ERR_INVALID_ARG;
             }
-            preprocess_kernel<2><<<pre_blocks, PRE_THREADS, smem, stream>>>(pa);
+            launch_pdl(preprocess_kernel<2>, dim3(pre_blocks), dim3(PRE_THREADS), smem, stream, pa);
         } else if (staged) {
-            preprocess_kernel<1><<<pre_blocks, PRE_THREADS, smem, stream>>>(pa);
+            launch_pdl(preprocess_kernel<1>, dim3(pre_blocks), dim3(PRE_THREADS), smem, stream, pa);
         } else {
-            preprocess_kernel<0><<<pre_blocks, PRE_THREADS, 0, stream>>>(pa);
+            launch_pdl(preprocess_kernel<0>, dim3(pre_blocks), dim3(PRE_THREADS), 0, stream, pa);
         }
         DQO_LAUNCH_CHECK("preprocess", debug, stream);
         stage_mark(stream, ST_PREPROCESS);
@@ -1479,14 +1493,14 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         uint32_t *va = vals_a + at, *vb = vals_b + at;
         uint32_t *sums = d_sums + (mode == 2 ? sums_stride : 0), *group_sums = sums + emit_blocks;
         if (mode == 2)
-            rank_sums_kernel<2><<<emit_blocks, 256, 0, stream>>>(P, front, d_order, d_tiles, d_offsets, d_rect, bits, row_any_b,
+            launch_pdl(rank_sums_kernel<2>, dim3(emit_blocks), dim3(256), 0, stream, P, front, d_order, d_tiles, d_offsets, d_rect, bits, row_any_b,
                                                                  IL.mask_words, d_tiles_b, sums, group_sums);
         else
-            rank_sums_kernel<0><<<emit_blocks, 256, 0, stream>>>(P, front, d_order, d_tiles, d_offsets, d_rect, bits, row_any_b,
+            launch_pdl(rank_sums_kernel<0>, dim3(emit_blocks), dim3(256), 0, stream, P, front, d_order, d_tiles, d_offsets, d_rect, bits, row_any_b,
                                                                  IL.mask_words, nullptr, sums, group_sums);
         DQO_LAUNCH_CHECK("rank sums", debug, stream);
 #define DQO_EMIT(KT, MODE)                                                                                             \
-    emit_kernel<KT, MODE><<<emit_blocks, 256, 0, stream>>>(P, n, d_order, d_tiles, d_tiles_b, d_offsets, d_rect, bits,  \
+    launch_pdl(emit_kernel<KT, MODE>, dim3(emit_blocks), dim3(256), 0, stream, P, n, d_order, d_tiles, d_tiles_b, d_offsets, d_rect, bits,  \
                                                           row_any_b, IL.mask_words, IL.tiles_x, (KT *)ka, va, sums,    \
                                                           group_sums, status)
         if (keys16) {
@@ -1510,9 +1524,9 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         const void *ks = in_a ? ka : kb;
         const unsigned rb = (unsigned)((n + 2047) / 2048);
         if (keys16)
-            tile_ranges_kernel<uint16_t><<<rb, 256, 0, stream>>>(n, (const uint16_t *)ks, status, count_word, out_ranges);
+            launch_pdl(tile_ranges_kernel<uint16_t>, dim3(rb), dim3(256), 0, stream, n, (const uint16_t *)ks, status, count_word, out_ranges);
         else
-            tile_ranges_kernel<uint32_t><<<rb, 256, 0, stream>>>(n, (const uint32_t *)ks, status, count_word, out_ranges);
+            launch_pdl(tile_ranges_kernel<uint32_t>, dim3(rb), dim3(256), 0, stream, n, (const uint32_t *)ks, status, count_word, out_ranges);
         DQO_LAUNCH_CHECK("tile ranges", debug, stream);
         if (mode != 2) stage_mark(stream, ST_RANGES);
         return DQO_OK;
@@ -1527,7 +1541,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
             DQO_CUDA_CHECK(cudaStreamWaitEvent(fj->side, fj->ev[2], 0));
             cs = fj->side;
         }
-        compact_tiles_kernel<<<1, 1024, 0, cs>>>(T, ranges, rb, tile_indices, status);
+        launch_pdl(compact_tiles_kernel, dim3(1), dim3(1024), 0, cs, T, ranges, rb, tile_indices, status);
         DQO_LAUNCH_CHECK("compact tiles", debug, stream);
         if (fj) DQO_CUDA_CHECK(cudaEventRecord(fj->ev[3], cs));
         stage_mark(stream, ST_COMPACT);
@@ -1545,8 +1559,8 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         }
         int rc = compact_fork(nullptr);
         if (rc) return rc;
-        if (ra.n_touched) render_forward_kernel<0, true><<<T, 256, 0, stream>>>(ra);
-        else render_forward_kernel<0, false><<<T, 256, 0, stream>>>(ra);
+        if (ra.n_touched) launch_pdl(render_forward_kernel<0, true>, dim3(T), dim3(256), 0, stream, ra);
+        else launch_pdl(render_forward_kernel<0, false>, dim3(T), dim3(256), 0, stream, ra);
         DQO_LAUNCH_CHECK("render forward", debug, stream);
         if ((rc = compact_join())) return rc;
         stage_mark(stream, ST_RENDER_FWD);
@@ -1558,19 +1572,19 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     uint32_t *mask_bits_b = (uint32_t *)(img + IL.mask_bits_b);
     int rc = bin_phase(1, front, 0, d_mask_bits, DQO_ST_R_FRONT, ranges);
     if (rc) return rc;
-    if (ra.n_touched) render_forward_kernel<1, true><<<T, 256, 0, stream>>>(ra);
-    else render_forward_kernel<1, false><<<T, 256, 0, stream>>>(ra);
+    if (ra.n_touched) launch_pdl(render_forward_kernel<1, true>, dim3(T), dim3(256), 0, stream, ra);
+    else launch_pdl(render_forward_kernel<1, false>, dim3(T), dim3(256), 0, stream, ra);
     DQO_LAUNCH_CHECK("render forward (front)", debug, stream);
     stage_mark(stream, ST_RENDER_FRONT);
-    mask_unfinished_kernel<<<1, 1024, 0, stream>>>(IL.tiles_x, IL.tiles_y, IL.mask_words, d_mask_bits, ra.unfinished,
+    launch_pdl(mask_unfinished_kernel, dim3(1), dim3(1024), 0, stream, IL.tiles_x, IL.tiles_y, IL.mask_words, d_mask_bits, ra.unfinished,
                                                    mask_bits_b, (uint32_t *)(img + IL.row_any_b));
     DQO_LAUNCH_CHECK("unfinished mask", debug, stream);
     rc = bin_phase(2, back, front, mask_bits_b, DQO_ST_R_BACK, ranges_b);
     if (rc) return rc;
     stage_mark(stream, ST_BACK_BIN);
     if ((rc = compact_fork(ranges_b))) return rc;
-    if (ra.n_touched) render_forward_kernel<2, true><<<T, 256, 0, stream>>>(ra);
-    else render_forward_kernel<2, false><<<T, 256, 0, stream>>>(ra);
+    if (ra.n_touched) launch_pdl(render_forward_kernel<2, true>, dim3(T), dim3(256), 0, stream, ra);
+    else launch_pdl(render_forward_kernel<2, false>, dim3(T), dim3(256), 0, stream, ra);
     DQO_LAUNCH_CHECK("render forward (back)", debug, stream);
     if ((rc = compact_join())) return rc;
     stage_mark(stream, ST_RENDER_FWD);
@@ -1606,7 +1620,7 @@ extern "C" int dqo_rast_blend_extra(const dqo_rast_settings *s, const float *bac
         }
     }
     a.colors = colors; a.bg = background; a.out_color = out_color;
-    blend_extra_kernel<<<IL.T, 256, 0, stream>>>(a);
+    launch_pdl(blend_extra_kernel, dim3(IL.T), dim3(256), 0, stream, a);
     DQO_LAUNCH_CHECK("blend extra colours", s->debug, stream);
     return DQO_OK;
 }
@@ -1629,7 +1643,7 @@ extern "C" int dqo_rast_export_state(const dqo_rast_settings *s, const void *geo
     if (ranges_out)
         DQO_CUDA_CHECK(cudaMemcpyAsync(ranges_out, img + IL.ranges, (size_t)IL.T * 8, cudaMemcpyDeviceToDevice, stream));
     if (n_contrib || final_T)
-        export_pixels_kernel<<<IL.T, 256, 0, stream>>>(s->W, s->H, IL.tiles_x, (const uint32_t *)(img + IL.n_contrib),
+        launch_pdl(export_pixels_kernel, dim3(IL.T), dim3(256), 0, stream, s->W, s->H, IL.tiles_x, (const uint32_t *)(img + IL.n_contrib),
                                                        (const float *)(img + IL.final_T),
                                                        (const uint2 *)(img + IL.ranges),
                                                        s->front_instances > 0 ? (const uint2 *)(img + IL.ranges_b) : nullptr,
@@ -1643,16 +1657,16 @@ extern "C" int dqo_rast_export_state(const dqo_rast_settings *s, const void *geo
         if (sorted_keys || point_list) {
             const unsigned nb = (unsigned)((capacity + 255) / 256);
             if (IL.T < 65535)
-                export_instances_kernel<uint16_t><<<nb, 256, 0, stream>>>(
+                launch_pdl(export_instances_kernel<uint16_t>, dim3(nb), dim3(256), 0, stream, 
                     capacity, status, (const uint16_t *)(bin + bin_sorted_keys(BL, IL.T)), (const uint32_t *)(bin + bin_point_list(BL, IL.T)),
                     (const float *)(geom + GL.depth), sorted_keys, point_list);
             else
-                export_instances_kernel<uint32_t><<<nb, 256, 0, stream>>>(
+                launch_pdl(export_instances_kernel<uint32_t>, dim3(nb), dim3(256), 0, stream, 
                     capacity, status, (const uint32_t *)(bin + bin_sorted_keys(BL, IL.T)), (const uint32_t *)(bin + bin_point_list(BL, IL.T)),
                     (const float *)(geom + GL.depth), sorted_keys, point_list);
         }
         if (means2D || depths || conic_opacity || rgb || tiles_touched) {
-            export_gauss_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
+            launch_pdl(export_gauss_kernel, dim3((P + 255) / 256), dim3(256), 0, stream, 
                 P, (const float4 *)(geom + GL.rec), (const uint32_t *)(geom + GL.tiles),
                 (const uint8_t *)(geom + GL.clamped), (const float *)(geom + GL.depth), means2D, depths, conic_opacity, rgb,
                 tiles_touched);

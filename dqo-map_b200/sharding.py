@@ -6,6 +6,8 @@ object owns an independently optimised quadric (quadrics.py:2245-2295).  Rank r 
 no gradient exchange; NCCL (gloo in the CPU tests) is used only to gather the small per-object table
 (pose / quadric parameters) and, on demand, the Gaussians themselves to rank 0 for tracking / whole-scene rendering.
 """
+import math
+
 import torch
 import torch.distributed as dist
 
@@ -60,26 +62,51 @@ def gather_object_table(local_table, group=None, rows_per_rank=None):
     return table
 
 
-def gather_gaussians(tensors, dst=0, group=None):
-    """Gathers variable-length per-rank Gaussian tensors (dict name -> [n_local, ...]) to rank `dst`.
-    Returns the concatenated dict on `dst`, None elsewhere.  Counts travel first, payloads as padded gathers."""
+def gather_gaussians(tensors, dst=0, group=None, sizes=None):
+    """Gathers variable-length per-rank Gaussian tensors (dict name -> [n_local, ...] float32) to rank `dst`.
+    Returns the concatenated dict on `dst`, None elsewhere.
+
+    Every rank packs its tensors into ONE [n_local, F] buffer (F = 59 floats for the six parameter groups of the
+    mapping step) and sends exactly its own rows; `dst` posts one receive per peer straight into the row range of the
+    result, so nothing is padded, nothing is re-concatenated and there is one message per peer instead of one
+    collective per tensor.  `sizes` (rows per rank): pass it when the assignment is static (sharding.assign_objects makes
+    it known everywhere) and the size exchange with its host synchronisation is skipped."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     names = sorted(tensors)
     any_t = tensors[names[0]]
     dev = any_t.device
-    n_local = torch.tensor([any_t.shape[0]], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    mx = max(max(sizes), 1)
-    out = {}
-    for name in names:
-        t = tensors[name].contiguous()
-        padded = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-        padded[: t.shape[0]] = t
-        bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
-        dist.gather(padded, bufs, dst=dst, group=group)
-        if rank == dst:
-            out[name] = torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
-    return out if rank == dst else None
+    n_here = any_t.shape[0]
+    if sizes is None:
+        n_local = torch.tensor([n_here], dtype=torch.int64, device=dev)
+        got = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(got, n_local, group=group)
+        sizes = [int(s.item()) for s in got]
+    if sizes[rank] != n_here:
+        raise ValueError("sizes[rank] does not match the local tensors")
+    widths = [math.prod(tensors[n].shape[1:]) for n in names]
+    packed = torch.cat([tensors[n].reshape(n_here, -1).to(torch.float32) for n in names], dim=1).contiguous()
+    F = packed.shape[1]
+    if rank != dst:
+        if n_here:
+            dist.send(packed, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+        return None
+    total = sum(sizes)
+    out = torch.empty((total, F), dtype=torch.float32, device=dev)
+    off, ops = 0, []
+    for r in range(world):
+        rows = out[off:off + sizes[r]]
+        if r == dst:
+            rows.copy_(packed)
+        elif sizes[r]:
+            src = dist.get_global_rank(group, r) if group is not None else r
+            ops.append(dist.P2POp(dist.irecv, rows, src, group))
+        off += sizes[r]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    result, col = {}, 0
+    for n, w in zip(names, widths):
+        result[n] = out[:, col:col + w].reshape((total,) + tuple(tensors[n].shape[1:])).contiguous()
+        col += w
+    return result

@@ -454,3 +454,91 @@ def test_mapping_loop_matches_reference_rasterizer():
     fused = [_loop(*args, 200, "fused") for _ in range(N_RUNS)]
     ref = [_loop(*args, 200, "reference", rast_pkg) for _ in range(N_RUNS)]
     _gate_by_mode([(r[0], r[1]) for r in fused], [(r[0], r[1]) for r in ref])
+
+
+@pytest.mark.skipif(not rh.reference_available(), reason="oracle/_ref not built")
+def test_mapping_loop_config2_size_against_reference_loop():
+    """BASELINE config 2 as benchmarked (1 M Gaussians, SH degree 3, 1200x680, window of 5 keyframes, masked L1 + attach
+    loss, Adam): 200 iterations of the fused C step against 200 iterations of the reference's own loop (its unmodified
+    rasterizer, torch loss with boolean indexing, torch.optim.Adam), two runs each.
+
+    Measured on a B200 (profiles/r02_c2_loop_noise.log): the loss trajectories of all implementations coincide to
+    <= 5e-5 relative over the first five iterations and then separate -- TWO RUNS OF THE REFERENCE LOOP ITSELF end
+    0.02 .. 0.7 dB apart per keyframe (22.78 vs 23.49 dB on keyframe 3), because Adam with eps = 1e-15 turns the sign of
+    float-atomic noise in near-zero gradients into full +-lr steps.  Size does not average this out, so the 0.1 dB / 1 %
+    of the north star can only be applied where the loop is still deterministic:
+      * sharp gate: per-iteration loss within 1e-4 relative of the reference loop over the first five iterations;
+      * end-of-loop gate: per keyframe, |mean(ours) - mean(reference)| <= max(0.1 dB, 1.5 x the larger run-to-run
+        difference of either side), likewise depth L1 with max(1 %, ...) -- no clustering, no re-draw."""
+    import bench
+    dev = torch.device(DEV)
+    ref_pkg = rh.load_reference()[0]
+    inp, views = bench.make_views("c2", dev, 0, 5)
+    cam0 = views[0]["cam"]
+    P, H, W = inp["xyz"].shape[0], cam0.image_height, cam0.image_width
+    for v in views:
+        v["rs"] = v["settings"](rasterizer.GaussianRasterizationSettings)
+        v["rs_ref"] = v["settings"](ref_pkg.GaussianRasterizationSettings)
+        v["kf"] = bench.make_keyframe(inp, v["settings"], rasterizer)
+    iters = 200
+    R = max(rasterizer.plan_binning(v["rs"], inp["xyz"], inp["opacity"], inp["scales"], inp["rotations"], inp["tile_mask"],
+                                    shs=inp["shs"])[0] for v in views)
+
+    def quality(params):
+        res = []
+        for v in views:
+            with torch.no_grad():
+                out = rasterizer.GaussianRasterizer(v["rs"])(
+                    means3D=params["xyz"], opacities=torch.sigmoid(params["opacity"]),
+                    shs=torch.cat((params["f_dc"], params["f_rest"]), dim=1), scales=torch.exp(params["scaling"]),
+                    rotations=torch.nn.functional.normalize(params["rotation"]), tile_mask=inp["tile_mask"])
+            gt_color, gt_depth = v["kf"][0].permute(2, 0, 1), v["kf"][1].permute(2, 0, 1)
+            hit = (out[3] != -1) & (gt_depth > 0)
+            res.append((psnr(out[0], gt_color), float((out[1] - gt_depth).abs()[hit].mean())))
+        return res
+
+    def run_fused():
+        fparams = {k: t.contiguous() for k, t in bench.raw_params(inp).items()}
+        st = mapping.FusedMappingStep(fparams, bench.LRS, W, H, 0.8, 1.0, 0.1, confidence=torch.zeros(P, 1, device=dev),
+                                      capacity=int(R * 1.3) + 4096)
+        st.begin_window(attach=True)
+        losses = []
+        for k in range(iters):
+            v = views[k % len(views)]
+            t = st(v["rs"], inp["tile_mask"], *v["kf"])
+            if k < 5:
+                losses.append(float(t[0]))
+        st.check()
+        return quality(fparams), losses, st.confidence.clone()
+
+    def run_reference():
+        rparams = {k: torch.nn.Parameter(t) for k, t in bench.raw_params(inp).items()}
+        init = {k: rparams[k].detach().clone() for k in ("xyz", "scaling", "rotation", "opacity")}
+        conf = torch.zeros(P, 1, device=dev)
+        opt = torch.optim.Adam([{"params": [rparams[k]], "lr": bench.LRS[k], "name": k} for k in bench.ORDER], lr=0.0, eps=1e-15)
+        losses = []
+        for k in range(iters):
+            v = views[k % len(views)]
+            t = bench.torch_mapping_iteration(rparams, init, opt, conf, ref_pkg.GaussianRasterizer, v["rs_ref"],
+                                              inp["tile_mask"], *v["kf"])
+            if k < 5:
+                losses.append(float(t))
+        return quality({k: t.detach() for k, t in rparams.items()}), losses, conf
+
+    start = quality(bench.raw_params(inp))
+    f = [run_fused() for _ in range(2)]
+    r = [run_reference() for _ in range(2)]
+    for i in range(5):  # the deterministic regime
+        for a in f:
+            assert abs(a[1][i] - r[0][1][i]) <= 1e-4 * abs(r[0][1][i]), ("loss", i, a[1], r[0][1])
+    for vi in range(len(views)):
+        pf, pr = [a[0][vi][0] for a in f], [a[0][vi][0] for a in r]
+        df, dr = [a[0][vi][1] for a in f], [a[0][vi][1] for a in r]
+        tol_p = max(0.1, 1.5 * max(abs(pf[0] - pf[1]), abs(pr[0] - pr[1])))
+        tol_d = max(0.01 * np.mean(dr), 1.5 * max(abs(df[0] - df[1]), abs(dr[0] - dr[1])))
+        assert abs(np.mean(pf) - np.mean(pr)) <= tol_p, ("psnr", vi, pf, pr, tol_p)
+        assert abs(np.mean(df) - np.mean(dr)) <= tol_d, ("depth L1", vi, df, dr, tol_d)
+        assert min(pf) > start[vi][0] + 3.0, "the loop must optimise"
+    # confidence (mapper.py:909-910): the counters of the two loops agree for all but a sliver of the cloud
+    diff = (f[0][2] - r[0][2]).abs()
+    assert float((diff > 2).float().mean()) <= 0.01
