@@ -232,6 +232,7 @@ struct ImgLayout {
     size_t mask_bits_b; // u32[tiles_y][mask_words]: mask_bits & unfinished
     size_t row_any_b;  // u32[ceil(tiles_y/32)]: bit y set <=> row y of mask_bits_b has any bit set
     size_t state;      // f32[4][T*256] two-phase: running T (-1 = pixel terminated) and colour accumulators
+    size_t sat, sat_b; // u32[(tiles_y+1)*(tiles_x+1)] summed-area tables of mask_bits / mask_bits_b
     int mask_words;
     size_t total;
     int tiles_x, tiles_y, T;

@@ -94,6 +94,8 @@ void make_img_layout(int W, int H, ImgLayout *L) {
     L->mask_bits_b = bump(cur, (size_t)(L->tiles_y > 0 ? L->tiles_y : 1) * L->mask_words * 4);
     L->row_any_b = bump(cur, (size_t)((L->tiles_y + 31) / 32 + 1) * 4);
     L->state = bump(cur, T * DQO_TILE_PIX * 4 * 4);
+    L->sat = bump(cur, (size_t)(L->tiles_y + 1) * (L->tiles_x + 1) * 4);
+    L->sat_b = bump(cur, (size_t)(L->tiles_y + 1) * (L->tiles_x + 1) * 4);
     L->total = align_up(cur, 256);
 }
 
@@ -110,6 +112,7 @@ struct PreArgs {
     const float *f_rest; // split-SH mode: shs = f_dc [P,3], f_rest [P,45]
     const float *view, *proj, *campos;
     const uint32_t *mask_bits;
+    const uint32_t *sat; // summed-area table of the tile mask, (grid_y + 1) x (grid_x + 1)
     int mask_words;
     int *radii;
     int *n_touched;
@@ -257,6 +260,43 @@ __device__ __forceinline__ uint32_t mask_row_count(const uint32_t *__restrict__ 
         c += __popc(m);
     }
     return c;
+}
+
+// Summed-area table of a tile bitmap: sat[y * (gx + 1) + x] = number of set bits in rows [0, y) x columns [0, x).
+// The number of masked tiles in a rectangle is then four loads, whatever its size (the row-by-row popcount it replaces
+// was a chain of dependent loads per Gaussian: 15 % of the preprocess).  Built by ONE block: row prefixes from the
+// bitmap words, then a running sum down every column.
+__device__ __forceinline__ void build_sat(int gx, int gy, int words, const uint32_t *bits, uint32_t *sat) {
+    const int stride = gx + 1;
+    for (int x = threadIdx.x; x < stride; x += blockDim.x) sat[x] = 0;
+    for (int e = threadIdx.x; e < gy * stride; e += blockDim.x) {
+        const int y = e / stride, x = e - y * stride; // bits of row y in columns [0, x)
+        uint32_t c = 0;
+        for (int w = 0; w * 32 < x; w++) {
+            uint32_t m = bits[y * words + w];
+            if (x - w * 32 < 32) m &= (1u << (x - w * 32)) - 1u;
+            c += __popc(m);
+        }
+        sat[(y + 1) * stride + x] = c;
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < stride; x += blockDim.x) {
+        uint32_t run = 0;
+        for (int y = 1; y <= gy; y++) {
+            run += sat[y * stride + x];
+            sat[y * stride + x] = run;
+        }
+    }
+}
+__device__ __forceinline__ uint32_t sat_count(const uint32_t *__restrict__ sat, int gx, uint32_t minx, uint32_t maxx,
+                                              uint32_t miny, uint32_t maxy) {
+    const uint32_t stride = (uint32_t)gx + 1u;
+    return __ldg(&sat[maxy * stride + maxx]) - __ldg(&sat[miny * stride + maxx]) - __ldg(&sat[maxy * stride + minx]) +
+           __ldg(&sat[miny * stride + minx]);
+}
+__global__ void __launch_bounds__(1024) mask_sat_kernel(int gx, int gy, int words, const uint32_t *bits, uint32_t *sat) {
+    pdl_enter();
+    build_sat(gx, gy, words, bits, sat);
 }
 
 struct ShRegs { // 48 SH floats of one Gaussian held in registers (flat [k][c] order)
@@ -451,7 +491,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
                 a.rect[idx] = make_uint2(minx | (maxx << 16), miny | (maxy << 16));
                 flags_out = cl | 0x80;
                 radius_out = my_radius;
-                for (uint32_t y = miny; y < maxy; y++) tiles_out += mask_row_count(a.mask_bits, a.mask_words, y, minx, maxx);
+                tiles_out = sat_count(a.sat, a.grid_x, minx, maxx, miny, maxy);
             }
         }
     }
@@ -471,34 +511,18 @@ __global__ void mark_visible_kernel(int P, const float *__restrict__ means, cons
     present[idx] = frustum_test(means[3 * idx], means[3 * idx + 1], means[3 * idx + 2], view, proj, &vz, &ppx, &ppy) ? 1 : 0;
 }
 
-// rows of [miny, maxy) that hold any unfinished tile, as a bit mask of row word `wd`
-__device__ __forceinline__ uint32_t rows_in_range(const uint32_t *__restrict__ row_any, uint32_t wd, uint32_t miny,
-                                                  uint32_t maxy) {
-    const uint32_t lo = (wd == (miny >> 5)) ? (miny & 31) : 0;
-    const uint32_t hi = (wd == ((maxy - 1) >> 5)) ? ((maxy - 1) & 31) : 31;
-    return __ldg(&row_any[wd]) & (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi));
-}
-
 // Number of instances rank i emits: tiles_touched of its Gaussian (MODE 0 / 1), or the number of UNFINISHED tiles in its
 // rectangle when the front phase did not bin it (MODE 2: offsets[rank] > front).
 template <int MODE>
 __device__ __forceinline__ uint32_t rank_count(int64_t i, uint32_t id, int64_t front, const uint32_t *__restrict__ tiles,
                                                const uint32_t *offsets, const uint2 *__restrict__ rect,
-                                               const uint32_t *__restrict__ mask_bits, const uint32_t *__restrict__ row_any,
-                                               int mask_words) {
+                                               const uint32_t *__restrict__ sat_b, int grid_x) {
     if (MODE != 2) return tiles[id];
     uint32_t n = 0;
     if ((int64_t)offsets[i] > front && tiles[id]) {
         const uint2 rc = rect[id];
         const uint32_t minx = rc.x & 0xFFFF, maxx = rc.x >> 16, miny = rc.y & 0xFFFF, maxy = rc.y >> 16;
-        for (uint32_t wd = miny >> 5; wd <= (maxy - 1) >> 5; wd++) {
-            uint32_t rows = rows_in_range(row_any, wd, miny, maxy);
-            while (rows) {
-                const uint32_t y = wd * 32 + (__ffs(rows) - 1);
-                rows &= rows - 1;
-                n += mask_row_count(mask_bits, mask_words, y, minx, maxx);
-            }
-        }
+        n = sat_count(sat_b, grid_x, minx, maxx, miny, maxy);
     }
     return n;
 }
@@ -510,16 +534,15 @@ __device__ __forceinline__ uint32_t rank_count(int64_t i, uint32_t id, int64_t f
 template <int MODE>
 __global__ void __launch_bounds__(256)
     rank_sums_kernel(int P, int64_t front, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
-                     const uint32_t *offsets, const uint2 *__restrict__ rect, const uint32_t *__restrict__ mask_bits,
-                     const uint32_t *__restrict__ row_any, int mask_words, uint32_t *tiles_rank, uint32_t *sums,
-                     uint32_t *group_sums) {
+                     const uint32_t *offsets, const uint2 *__restrict__ rect, const uint32_t *__restrict__ sat_b, int grid_x,
+                     uint32_t *tiles_rank, uint32_t *sums, uint32_t *group_sums) {
     pdl_enter();
     __shared__ uint32_t s_w[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t i = (int64_t)blockIdx.x * 256 + tid;
     uint32_t n = 0;
     if (i < P) {
-        n = rank_count<MODE>(i, order[i], front, tiles, offsets, rect, mask_bits, row_any, mask_words);
+        n = rank_count<MODE>(i, order[i], front, tiles, offsets, rect, sat_b, grid_x);
         if (MODE == 2) tiles_rank[i] = n;
     }
 #pragma unroll
@@ -664,7 +687,7 @@ __global__ void __launch_bounds__(256)
 // without touching the bitmap.
 __global__ void __launch_bounds__(1024)
     mask_unfinished_kernel(int tiles_x, int tiles_y, int mask_words, const uint32_t *__restrict__ mask_bits,
-                           const int *__restrict__ unfinished, uint32_t *mask_bits_b, uint32_t *row_any) {
+                           const int *__restrict__ unfinished, uint32_t *mask_bits_b, uint32_t *row_any, uint32_t *sat_b) {
     pdl_enter();
     __shared__ uint32_t s_any[64];
     const int row_words = (tiles_y + 31) / 32;
@@ -681,6 +704,8 @@ __global__ void __launch_bounds__(1024)
     }
     __syncthreads();
     for (int k = threadIdx.x; k < row_words; k += blockDim.x) row_any[k] = (k < 64) ? s_any[k] : 0xFFFFFFFFu;
+    __syncthreads(); // mask_bits_b was written by this block
+    build_sat(tiles_x, tiles_y, mask_words, mask_bits_b, sat_b);
 }
 
 // per-tile [start, end) in the sorted list (rasterizer_impl.cu:120-142); each thread checks 8 consecutive keys
@@ -1382,6 +1407,9 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
             const int nw = IL.tiles_y * IL.mask_words;
             launch_pdl(mask_bits_kernel, dim3((nw + 7) / 8), dim3(256), 0, stream, IL.tiles_x, IL.tiles_y, IL.mask_words, tile_mask, mask_bits);
             DQO_LAUNCH_CHECK("mask bits", debug, stream);
+            launch_pdl(mask_sat_kernel, dim3(1), dim3(1024), 0, stream, IL.tiles_x, IL.tiles_y, IL.mask_words, mask_bits,
+                       (uint32_t *)(img + IL.sat));
+            DQO_LAUNCH_CHECK("mask summed-area table", debug, stream);
         }
         PreArgs pa;
         pa.P = P; pa.D = s->D; pa.M = s->M; pa.W = s->W; pa.H = s->H;
@@ -1392,7 +1420,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         pa.means3D = means3D; pa.scales = scales; pa.rotations = rotations; pa.opacities = opacities;
         pa.shs = shs; pa.f_rest = f_rest; pa.cov3D_precomp = cov3D_precomp; pa.colors_precomp = colors_precomp;
         pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
-        pa.mask_bits = mask_bits; pa.mask_words = IL.mask_words;
+        pa.mask_bits = mask_bits; pa.mask_words = IL.mask_words; pa.sat = (const uint32_t *)(img + IL.sat);
         pa.radii = radii; pa.n_touched = n_touched;
         pa.rec = (float4 *)(geom + GL.rec);
         pa.depth = (float *)(geom + GL.depth);
@@ -1493,11 +1521,11 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         uint32_t *va = vals_a + at, *vb = vals_b + at;
         uint32_t *sums = d_sums + (mode == 2 ? sums_stride : 0), *group_sums = sums + emit_blocks;
         if (mode == 2)
-            launch_pdl(rank_sums_kernel<2>, dim3(emit_blocks), dim3(256), 0, stream, P, front, d_order, d_tiles, d_offsets, d_rect, bits, row_any_b,
-                                                                 IL.mask_words, d_tiles_b, sums, group_sums);
+            launch_pdl(rank_sums_kernel<2>, dim3(emit_blocks), dim3(256), 0, stream, P, front, d_order, d_tiles, d_offsets, d_rect,
+                       (const uint32_t *)(img + IL.sat_b), IL.tiles_x, d_tiles_b, sums, group_sums);
         else
-            launch_pdl(rank_sums_kernel<0>, dim3(emit_blocks), dim3(256), 0, stream, P, front, d_order, d_tiles, d_offsets, d_rect, bits, row_any_b,
-                                                                 IL.mask_words, nullptr, sums, group_sums);
+            launch_pdl(rank_sums_kernel<0>, dim3(emit_blocks), dim3(256), 0, stream, P, front, d_order, d_tiles, d_offsets, d_rect,
+                       (const uint32_t *)nullptr, IL.tiles_x, (uint32_t *)nullptr, sums, group_sums);
         DQO_LAUNCH_CHECK("rank sums", debug, stream);
 #define DQO_EMIT(KT, MODE)                                                                                             \
     launch_pdl(emit_kernel<KT, MODE>, dim3(emit_blocks), dim3(256), 0, stream, P, n, d_order, d_tiles, d_tiles_b, d_offsets, d_rect, bits,  \
@@ -1577,7 +1605,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     DQO_LAUNCH_CHECK("render forward (front)", debug, stream);
     stage_mark(stream, ST_RENDER_FRONT);
     launch_pdl(mask_unfinished_kernel, dim3(1), dim3(1024), 0, stream, IL.tiles_x, IL.tiles_y, IL.mask_words, d_mask_bits, ra.unfinished,
-                                                   mask_bits_b, (uint32_t *)(img + IL.row_any_b));
+                                                   mask_bits_b, (uint32_t *)(img + IL.row_any_b), (uint32_t *)(img + IL.sat_b));
     DQO_LAUNCH_CHECK("unfinished mask", debug, stream);
     rc = bin_phase(2, back, front, mask_bits_b, DQO_ST_R_BACK, ranges_b);
     if (rc) return rc;
