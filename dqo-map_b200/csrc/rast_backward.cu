@@ -395,32 +395,6 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
     float *wrest = reinterpret_cast<float *>(wbuf), *wdc = wrest + 1440;
     const int base_g = blockIdx.x * blockDim.x + warp * 32;
     const int nrow = min(32, a.P - base_g);
-    if (SHMODE == 2 && nrow > 0) {
-        if (nrow == 32) {
-            const float4 *g4 = reinterpret_cast<const float4 *>(a.f_rest + (size_t)base_g * 45);
-#pragma unroll
-            for (int i = 0; i < 12; i++) {
-                const int q = i * 32 + lane;
-                if (q < 360) wbuf[q] = __ldg(g4 + q);
-            }
-            const float4 *gd4 = reinterpret_cast<const float4 *>(a.shs + (size_t)base_g * 3);
-            if (lane < 24) reinterpret_cast<float4 *>(wdc)[lane] = __ldg(gd4 + lane);
-        } else {
-            for (int q = lane; q < nrow * 45; q += 32) wrest[q] = a.f_rest[(size_t)base_g * 45 + q];
-            for (int q = lane; q < nrow * 3; q += 32) wdc[q] = a.shs[(size_t)base_g * 3 + q];
-        }
-        __syncwarp();
-    }
-    if (SHMODE == 1 && nrow > 0) {
-        const float4 *gsh = reinterpret_cast<const float4 *>(a.shs) + (size_t)base_g * 12;
-        const int nq = nrow * 12;
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            const int q = i * 32 + lane;
-            if (q < nq) wbuf[(q / 12) * GB_ROW_Q + (q % 12)] = __ldg(gsh + q);
-        }
-        __syncwarp();
-    }
     const bool live = idx < a.P;
     const bool active = live && a.radii[idx] > 0;
     const int M = a.M;
@@ -436,16 +410,58 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
 #pragma unroll
         for (int k = 0; k < DQO_GACC_FLOATS; k++) g[k] = 0.f;
     }
+    // Every output is a sum of products with the accumulator record, so a Gaussian whose record is all zero (most of a
+    // large map: it is in the frustum but contributes to no pixel that carries a gradient) has all-zero gradients and
+    // needs neither its parameters (236 B) nor the chain below: only Gaussians with `need` are loaded and evaluated.
+    bool nz = false;
+#pragma unroll
+    for (int k = 0; k < DQO_GACC_FLOATS; k++) nz |= (g[k] != 0.f);
+    const bool need = active && nz;
+    const unsigned need_rows = __ballot_sync(0xFFFFFFFFu, need);
+    const bool whole_block = nrow == 32 && __popc(need_rows) >= 12; // dense: the warp's block in 12 coalesced 128-bit loads
+    if (SHMODE == 2 && need_rows) {
+        if (whole_block) {
+            const float4 *g4 = reinterpret_cast<const float4 *>(a.f_rest + (size_t)base_g * 45);
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const int q = i * 32 + lane;
+                if (q < 360) wbuf[q] = __ldg(g4 + q);
+            }
+            const float4 *gd4 = reinterpret_cast<const float4 *>(a.shs + (size_t)base_g * 3);
+            if (lane < 24) reinterpret_cast<float4 *>(wdc)[lane] = __ldg(gd4 + lane);
+        } else { // sparse: only the needed rows, 180 + 12 contiguous bytes each
+            for (unsigned m = need_rows; m; m &= m - 1) {
+                const int r = __ffs(m) - 1;
+                const float *src = a.f_rest + (size_t)(base_g + r) * 45;
+                wrest[r * 45 + lane] = __ldg(src + lane);
+                if (lane < 13) wrest[r * 45 + 32 + lane] = __ldg(src + 32 + lane);
+                else if (lane < 16) wdc[r * 3 + (lane - 13)] = __ldg(a.shs + (size_t)(base_g + r) * 3 + (lane - 13));
+            }
+        }
+        __syncwarp();
+    }
+    if (SHMODE == 1 && need_rows) {
+        const float4 *gsh = reinterpret_cast<const float4 *>(a.shs) + (size_t)base_g * 12;
+        if (whole_block) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const int q = i * 32 + lane;
+                wbuf[(q / 12) * GB_ROW_Q + (q % 12)] = __ldg(gsh + q);
+            }
+        } else {
+            for (unsigned m = need_rows; m; m &= m - 1) {
+                const int r = __ffs(m) - 1;
+                if (lane < 12) wbuf[r * GB_ROW_Q + lane] = __ldg(gsh + r * 12 + lane);
+            }
+        }
+        __syncwarp();
+    }
     float dmean[3] = {g[9], g[10], g[11]};
     float drot[4] = {g[12], g[13], g[14], g[15]};
     float dscale[3] = {0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     bool write_out = live;
     if (a.ever && live) {
-        // all outputs are products with the accumulator record: an all-zero record means all-zero gradients
-        bool nz = false;
-#pragma unroll
-        for (int k = 0; k < DQO_GACC_FLOATS; k++) nz |= (g[k] != 0.f);
         const bool was = a.ever[idx] != 0;
         if (nz && !was) {
             a.ever[idx] = 1;
@@ -460,7 +476,7 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
         for (int k = 0; k < 48; k++) shg[k] = 0.f;
     }
 
-    if (active) {
+    if (need) {
         const float mx = a.means3D[3 * idx], my = a.means3D[3 * idx + 1], mz = a.means3D[3 * idx + 2];
         const float *v = a.view;
         float cov3[6];
@@ -704,7 +720,7 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
     } else if (!STAGED && dsh) {
         for (int k = 0; k < 3 * M; k++) dsh[k] = 0.f;
     }
-    if (!STAGED && active && !a.shs && dsh) {
+    if (!STAGED && need && !a.shs && dsh) {
         for (int k = 0; k < 3 * M; k++) dsh[k] = 0.f;
     }
     if (STAGED) { // own row -> shared -> coalesced 128-bit stores of the warp's contiguous 32 x 192 B block
