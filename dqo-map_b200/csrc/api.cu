@@ -32,6 +32,9 @@ bool pdl_enabled() {
     }();
     return on;
 }
+static thread_local bool g_pdl_now = false;
+void pdl_scope(long long n_gaussians) { g_pdl_now = pdl_enabled() && n_gaussians >= DQO_PDL_MIN_GAUSSIANS; }
+bool pdl_active() { return g_pdl_now; }
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // NVTX ranges around the C-ABI entry points (visible in nsys / ncu --nvtx; a no-op without a tool attached)
@@ -64,7 +67,7 @@ ForkJoin *fork_join(cudaStream_t caller) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     bool ok = cudaStreamCreateWithPriority(&fj->side, cudaStreamNonBlocking, hi) == cudaSuccess;
-    for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreateWithFlags(&fj->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 8 && ok; i++) ok = cudaEventCreateWithFlags(&fj->ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
         delete fj; // leaks at most a stream / a few events on a failing device; the caller runs unforked

@@ -26,7 +26,7 @@ void nvtx_pop();
 // stream, then reused: no stream / event creation on the hot path, no sharing between callers on different streams.
 struct ForkJoin {
     cudaStream_t side = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 ForkJoin *fork_join(cudaStream_t caller); // nullptr: run unforked on the caller's stream
 
@@ -71,6 +71,13 @@ __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 bool pdl_enabled(); // api.cu: on unless the environment says DQO_PDL=0 (A/B measurements)
+// Whether the launches of the current C-ABI call (this thread) use the programmatic attribute.  A waiting dependent grid
+// occupies registers / shared memory on the SMs; for one large scene on one stream that is free, but when many small
+// scenes are mapped concurrently on several streams (the object-sharded workload) it takes the slots the other streams'
+// kernels need (measured: 6100 -> 3700 objects*iters/s).  So every entry point declares its problem size first.
+#define DQO_PDL_MIN_GAUSSIANS 500000
+void pdl_scope(long long n_gaussians);
+bool pdl_active();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args &&...args) {
@@ -81,7 +88,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.stream = stream;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr.val.programmaticStreamSerializationAllowed = pdl_active() ? 1 : 0;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

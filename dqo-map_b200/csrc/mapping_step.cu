@@ -619,6 +619,7 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
         set_error("dqo_mapping_step: invalid argument");
         return DQO_ERR_INVALID_ARG;
     }
+    pdl_scope(s->P);
     nvtx_push("dqo_mapping_step");
     if (!(s->M == 16 || s->M == 1)) {
         set_error("dqo_mapping_step supports M == 16 (SH degree 3 storage) or M == 1");

@@ -813,6 +813,7 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
                                  float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
                                  uint8_t *ever, uint32_t *ever_list, int32_t *ever_count, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    pdl_scope(s ? s->P : 0);
     if (!s || s->P < 0) {
         set_error("dqo_rast_backward: invalid settings");
         return DQO_ERR_INVALID_ARG;

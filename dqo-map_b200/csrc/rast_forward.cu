@@ -108,6 +108,7 @@ struct PreArgs {
     float tanfovx, tanfovy, focal_x, focal_y, cx, cy;
     int grid_x, grid_y;
     int prefiltered;
+    int lazy_color; // two-phase binning: SH colours are evaluated by lazy_color_kernel for the Gaussians that get binned
     const float *means3D, *scales, *rotations, *opacities, *shs, *cov3D_precomp, *colors_precomp;
     const float *f_rest; // split-SH mode: shs = f_dc [P,3], f_rest [P,45]
     const float *view, *proj, *campos;
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 *wbuf = s_sh + warp * 32 * SH_ROW_Q;
     float *wrest = reinterpret_cast<float *>(wbuf), *wdc = wrest + 1440;
-    if (SHMODE == 2) {
+    if (SHMODE == 2 && !a.lazy_color) {
         const int base_g = blockIdx.x * blockDim.x + warp * 32;
         const int nrow = min(32, a.P - base_g);
         if (nrow == 32) {
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
         }
         __syncwarp();
     }
-    if (STAGED) {
+    if (STAGED && !a.lazy_color) {
         const int base_g = blockIdx.x * blockDim.x + warp * 32;
         const int nrow = min(32, a.P - base_g);
         if (nrow > 0) {
@@ -433,9 +434,11 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
             const uint32_t maxx = min((uint32_t)a.grid_x, (uint32_t)max(0, rx1));
             const uint32_t maxy = min((uint32_t)a.grid_y, (uint32_t)max(0, ry1));
             if ((maxx - minx) * (maxy - miny) != 0) {
-                float3 rgb;
+                float3 rgb = make_float3(0.f, 0.f, 0.f);
                 uint8_t cl = 0;
-                if (a.colors_precomp == nullptr) {
+                if (a.lazy_color) {
+                    // filled in by lazy_color_kernel if this Gaussian is binned
+                } else if (a.colors_precomp == nullptr) {
                     const float3 cam = make_float3(a.campos[0], a.campos[1], a.campos[2]);
                     if (STAGED) {
                         ShRegs sh;
@@ -500,6 +503,69 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
     a.clamped[idx] = flags_out;
     const unsigned vis = __ballot_sync(__activemask(), radius_out > 0);
     if ((threadIdx.x & 31) == 0 && vis) atomicAdd(&a.status[DQO_ST_NUM_VISIBLE], __popc(vis));
+}
+
+// SH colours on demand (two-phase binning).  With occlusion-aware binning only the nearest ~15-20 % of the Gaussians of a
+// large map are ever binned, so evaluating computeColorFromSH (forward.cu:106-163) for all of them in the preprocess
+// reads 192 B and spends ~350 instructions per Gaussian on colours nobody looks at.  The preprocess then leaves the rgb
+// of the splat record empty and this kernel fills it in -- same function, same inputs, bit-identical values -- for
+// exactly the ranks a binning phase emitted:
+//   phase 1  ranks whose inclusive instance offset fits the front region (what emit_kernel<1> wrote);
+//   phase 2  ranks with unfinished tiles in their rectangle (tiles_rank of rank_sums_kernel<2>); disjoint from phase 1.
+// It runs on the side stream beside the tile sort of its phase; only the blend of that phase waits for it.
+// One warp per 32 consecutive ranks; the needed SH rows (scattered: rank order is not memory order) are fetched
+// row by row with coalesced loads through shared memory.
+struct ColorArgs {
+    int P, D, phase;
+    int64_t front;
+    const uint32_t *order, *offsets, *tiles, *tiles_rank;
+    const float *means3D, *shs, *f_rest, *campos;
+    float4 *rec;
+    uint8_t *clamped;
+};
+#define LC_THREADS 128
+template <int SHMODE> // 1: merged SH [P,16,3], 2: split f_dc [P,3] / f_rest [P,45]
+__global__ void __launch_bounds__(LC_THREADS) lazy_color_kernel(ColorArgs a) {
+    pdl_enter();
+    __shared__ float s_rows[LC_THREADS / 32][32 * 49]; // 48 floats per row + 1 pad
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * LC_THREADS + threadIdx.x;
+    bool need = false;
+    uint32_t id = 0;
+    if (r < a.P) {
+        id = a.order[r];
+        need = (a.phase == 1) ? (a.tiles[id] != 0 && (int64_t)a.offsets[r] <= a.front) : (a.tiles_rank[r] != 0);
+    }
+    const unsigned rows = __ballot_sync(0xFFFFFFFFu, need);
+    if (!rows) return;
+    float *wrow = s_rows[warp];
+    for (unsigned m = rows; m; m &= m - 1) {
+        const int k = __ffs(m) - 1;
+        const uint32_t gid = __shfl_sync(0xFFFFFFFFu, id, k);
+        if (SHMODE == 2) {
+            const float *src = a.f_rest + (size_t)gid * 45;
+            wrow[k * 49 + 3 + lane] = __ldg(src + lane);
+            if (lane < 13) wrow[k * 49 + 3 + 32 + lane] = __ldg(src + 32 + lane);
+            else if (lane < 16) wrow[k * 49 + (lane - 13)] = __ldg(a.shs + (size_t)gid * 3 + (lane - 13));
+        } else {
+            const float *src = a.shs + (size_t)gid * 48;
+            wrow[k * 49 + lane] = __ldg(src + lane);
+            if (lane < 16) wrow[k * 49 + 32 + lane] = __ldg(src + 32 + lane);
+        }
+    }
+    __syncwarp();
+    if (!need) return;
+    ShRegs sh;
+#pragma unroll
+    for (int k = 0; k < 48; k++) sh.v[k] = wrow[lane * 49 + k];
+    const float3 pos = make_float3(a.means3D[3 * (size_t)id], a.means3D[3 * (size_t)id + 1], a.means3D[3 * (size_t)id + 2]);
+    uint8_t cl = 0;
+    const float3 rgb = sh_to_rgb(a.D, sh, pos, make_float3(a.campos[0], a.campos[1], a.campos[2]), &cl);
+    float *dst = reinterpret_cast<float *>(a.rec + 3 * (size_t)id + 2);
+    dst[0] = rgb.x;
+    dst[1] = rgb.y;
+    dst[2] = rgb.z;
+    a.clamped[id] = cl | 0x80;
 }
 
 __global__ void mark_visible_kernel(int P, const float *__restrict__ means, const float *__restrict__ view,
@@ -1364,6 +1430,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         set_error("image too large");
         return DQO_ERR_INVALID_ARG;
     }
+    pdl_scope(s->P);
     stage_mark(stream, ST_BEGIN_FWD);
     nvtx_push("dqo_rast_forward");
     // ranges and ranges_b are neighbours in the image buffer's layout only by accident: clear them separately
@@ -1396,6 +1463,8 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     size_t sums_stride = 0;
     int emit_blocks = 0;
     ForkJoin *fj = debug ? nullptr : fork_join(stream); // side stream + events owned by (device, caller stream)
+    int lazy_shmode = 0;
+    ColorArgs ca = {};
     if (P > 0) {
         if (make_geom_layout(P, &GL)) return DQO_ERR_WORKSPACE;
         if (make_bin_layout(capacity, &BL)) return DQO_ERR_WORKSPACE;
@@ -1403,6 +1472,26 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         char *bin = (char *)binning_buffer;
         uint32_t *mask_bits = (uint32_t *)(img + IL.mask_bits);
         DQO_CUDA_CHECK(cudaMemsetAsync(geom + GL.sums, 0, 2 * GL.sums_stride, stream));
+        // fork: depth keys + the (depth, id) sort of the Gaussians (stable LSD sort on the depth bits) on the side
+        // stream, concurrently with the rest of the preprocess
+        uint32_t *order = (uint32_t *)(geom + GL.order);
+        launch_pdl(depth_key_kernel, dim3((P + 255) / 256), dim3(256), 0, stream, P, means3D, viewmatrix, projmatrix, (uint32_t *)(geom + GL.depth_key));
+        DQO_LAUNCH_CHECK("depth keys", debug, stream);
+        cudaStream_t sort_stream = stream;
+        if (fj) {
+            DQO_CUDA_CHECK(cudaEventRecord(fj->ev[0], stream));
+            DQO_CUDA_CHECK(cudaStreamWaitEvent(fj->side, fj->ev[0], 0));
+            sort_stream = fj->side;
+        }
+        // The sort chain (12 short kernels) is the critical path of this stage, so it is enqueued first; the preprocess
+        // fills the SMs around its high-priority kernels.  4 passes (even): the sorted ids end up in `order` (vals_a),
+        // values are implicit (value = index) so no iota array is read.
+        {
+            const int rc = radix_sort_pairs<uint32_t>((uint32_t *)(geom + GL.depth_key), (uint32_t *)(geom + GL.depth_key2), order, (uint32_t *)(geom + GL.ids), true,
+                                                      nullptr, nullptr, P, 32, geom + GL.sort_temp, sort_stream);
+            if (rc) return rc;
+            if (debug) DQO_CUDA_CHECK(cudaStreamSynchronize(sort_stream));
+        }
         {
             const int nw = IL.tiles_y * IL.mask_words;
             launch_pdl(mask_bits_kernel, dim3((nw + 7) / 8), dim3(256), 0, stream, IL.tiles_x, IL.tiles_y, IL.mask_words, tile_mask, mask_bits);
@@ -1417,6 +1506,11 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         pa.tanfovx = s->tanfovx; pa.tanfovy = s->tanfovy; pa.focal_x = focal_x; pa.focal_y = focal_y;
         pa.cx = s->cx; pa.cy = s->cy; pa.grid_x = IL.tiles_x; pa.grid_y = IL.tiles_y;
         pa.prefiltered = s->prefiltered;
+        // SH colours on demand: only with two-phase binning (else every rank is emitted) and the staged SH layouts
+        lazy_shmode = 0;
+        if (two_phase && !colors_precomp && shs && s->M == 16 && (uintptr_t)shs % 16 == 0)
+            lazy_shmode = f_rest ? ((uintptr_t)f_rest % 16 == 0 ? 2 : 0) : 1;
+        pa.lazy_color = lazy_shmode != 0;
         pa.means3D = means3D; pa.scales = scales; pa.rotations = rotations; pa.opacities = opacities;
         pa.shs = shs; pa.f_rest = f_rest; pa.cov3D_precomp = cov3D_precomp; pa.colors_precomp = colors_precomp;
         pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
@@ -1432,20 +1526,9 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         pa.status = status;
         rec = pa.rec;
         depth = pa.depth;
-        // fork: depth keys + the (depth, id) sort of the Gaussians (stable LSD sort on the depth bits) on the side
-        // stream, concurrently with the rest of the preprocess
-        uint32_t *order = (uint32_t *)(geom + GL.order);
-        launch_pdl(depth_key_kernel, dim3((P + 255) / 256), dim3(256), 0, stream, P, means3D, viewmatrix, projmatrix, pa.depth_key);
-        DQO_LAUNCH_CHECK("depth keys", debug, stream);
-        cudaStream_t sort_stream = stream;
-        if (fj) {
-            DQO_CUDA_CHECK(cudaEventRecord(fj->ev[0], stream));
-            DQO_CUDA_CHECK(cudaStreamWaitEvent(fj->side, fj->ev[0], 0));
-            sort_stream = fj->side;
-        }
         const bool staged = shs && !f_rest && s->M == 16 && ((uintptr_t)shs % 16 == 0);
         const int pre_blocks = (P + PRE_THREADS - 1) / PRE_THREADS;
-        const size_t smem = (size_t)(PRE_THREADS / 32) * 32 * SH_ROW_Q * sizeof(float4);
+        const size_t smem = pa.lazy_color ? 0 : (size_t)(PRE_THREADS / 32) * 32 * SH_ROW_Q * sizeof(float4);
         if (f_rest) {
             if (s->M != 16 || (uintptr_t)shs % 16 || (uintptr_t)f_rest % 16) {
                 set_error("split SH input requires M == 16 and 16-byte aligned f_dc / f_rest");
@@ -1459,15 +1542,6 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         }
         DQO_LAUNCH_CHECK("preprocess", debug, stream);
         stage_mark(stream, ST_PREPROCESS);
-        // enqueued after the preprocess so that the big kernel starts right behind the key kernel and the small,
-        // high-priority sort kernels slip in between its blocks.  4 passes (even): the sorted ids end up in `order`
-        // (vals_a), values are implicit (value = index) so no iota array is read.
-        {
-            const int rc = radix_sort_pairs<uint32_t>(pa.depth_key, (uint32_t *)(geom + GL.depth_key2), order, pa.ids, true,
-                                                      nullptr, nullptr, P, 32, geom + GL.sort_temp, sort_stream);
-            if (rc) return rc;
-            if (debug) DQO_CUDA_CHECK(cudaStreamSynchronize(sort_stream));
-        }
         if (fj) { // join
             DQO_CUDA_CHECK(cudaEventRecord(fj->ev[1], fj->side));
             DQO_CUDA_CHECK(cudaStreamWaitEvent(stream, fj->ev[1], 0));
@@ -1488,7 +1562,32 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         d_tiles_b = (uint32_t *)(geom + GL.tiles_b);
         sums_stride = GL.sums_stride / 4;
         emit_blocks = GL.emit_blocks;
+        ca.P = P; ca.D = s->D; ca.front = front;
+        ca.order = d_order; ca.offsets = d_offsets; ca.tiles = d_tiles; ca.tiles_rank = d_tiles_b;
+        ca.means3D = means3D; ca.shs = shs; ca.f_rest = f_rest; ca.campos = campos;
+        ca.rec = pa.rec; ca.clamped = pa.clamped;
     }
+    // lazy colours of one binning phase on the side stream (fork here, join in front of that phase's blend)
+    auto color_fork = [&](int phase) -> int {
+        if (!lazy_shmode) return DQO_OK;
+        cudaStream_t cs = stream;
+        if (fj) {
+            DQO_CUDA_CHECK(cudaEventRecord(fj->ev[phase == 1 ? 4 : 6], stream));
+            DQO_CUDA_CHECK(cudaStreamWaitEvent(fj->side, fj->ev[phase == 1 ? 4 : 6], 0));
+            cs = fj->side;
+        }
+        ca.phase = phase;
+        const unsigned blocks = (unsigned)((P + LC_THREADS - 1) / LC_THREADS);
+        if (lazy_shmode == 2) launch_pdl(lazy_color_kernel<2>, dim3(blocks), dim3(LC_THREADS), 0, cs, ca);
+        else launch_pdl(lazy_color_kernel<1>, dim3(blocks), dim3(LC_THREADS), 0, cs, ca);
+        DQO_LAUNCH_CHECK("lazy colours", debug, cs);
+        if (fj) DQO_CUDA_CHECK(cudaEventRecord(fj->ev[phase == 1 ? 5 : 7], cs));
+        return DQO_OK;
+    };
+    auto color_join = [&](int phase) -> int {
+        if (lazy_shmode && fj) DQO_CUDA_CHECK(cudaStreamWaitEvent(stream, fj->ev[phase == 1 ? 5 : 7], 0));
+        return DQO_OK;
+    };
 
     const int sort_bits = tile_sort_bits(T);
     const bool in_a = bin_sorted_in_a(T);
@@ -1527,6 +1626,10 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
             launch_pdl(rank_sums_kernel<0>, dim3(emit_blocks), dim3(256), 0, stream, P, front, d_order, d_tiles, d_offsets, d_rect,
                        (const uint32_t *)nullptr, IL.tiles_x, (uint32_t *)nullptr, sums, group_sums);
         DQO_LAUNCH_CHECK("rank sums", debug, stream);
+        if (mode == 2) {
+            const int rcc = color_fork(2);
+            if (rcc) return rcc;
+        }
 #define DQO_EMIT(KT, MODE)                                                                                             \
     launch_pdl(emit_kernel<KT, MODE>, dim3(emit_blocks), dim3(256), 0, stream, P, n, d_order, d_tiles, d_tiles_b, d_offsets, d_rect, bits,  \
                                                           row_any_b, IL.mask_words, IL.tiles_x, (KT *)ka, va, sums,    \
@@ -1538,6 +1641,10 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         }
 #undef DQO_EMIT
         DQO_LAUNCH_CHECK("scan + emit", debug, stream);
+        if (mode == 1) {
+            const int rcc = color_fork(1);
+            if (rcc) return rcc;
+        }
         if (mode != 2) stage_mark(stream, ST_DUPLICATE);
         int rc;
         if (keys16)
@@ -1600,6 +1707,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     uint32_t *mask_bits_b = (uint32_t *)(img + IL.mask_bits_b);
     int rc = bin_phase(1, front, 0, d_mask_bits, DQO_ST_R_FRONT, ranges);
     if (rc) return rc;
+    if ((rc = color_join(1))) return rc;
     if (ra.n_touched) launch_pdl(render_forward_kernel<1, true>, dim3(T), dim3(256), 0, stream, ra);
     else launch_pdl(render_forward_kernel<1, false>, dim3(T), dim3(256), 0, stream, ra);
     DQO_LAUNCH_CHECK("render forward (front)", debug, stream);
@@ -1611,6 +1719,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     if (rc) return rc;
     stage_mark(stream, ST_BACK_BIN);
     if ((rc = compact_fork(ranges_b))) return rc;
+    if ((rc = color_join(2))) return rc;
     if (ra.n_touched) launch_pdl(render_forward_kernel<2, true>, dim3(T), dim3(256), 0, stream, ra);
     else launch_pdl(render_forward_kernel<2, false>, dim3(T), dim3(256), 0, stream, ra);
     DQO_LAUNCH_CHECK("render forward (back)", debug, stream);

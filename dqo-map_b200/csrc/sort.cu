@@ -54,11 +54,12 @@ __device__ __forceinline__ unsigned digit_peers(uint32_t d, int bits, bool valid
 }
 
 // counts[d * tiles + tile] = number of keys of tile `tile` whose digit is d
-template <typename KeyT>
+template <typename KeyT, int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS) radix_count_kernel(const KeyT *__restrict__ keys, const int *count, const int *skip,
                                                                  int64_t capacity, int shift, int bits, int tiles,
                                                                  uint32_t *__restrict__ counts) {
     pdl_enter();
+    constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     __shared__ uint32_t s_hist[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
@@ -161,12 +162,13 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t *data, int64_
     }
 }
 
-template <typename KeyT>
+template <typename KeyT, int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS, 3)
     radix_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, const uint32_t *__restrict__ vals_in,
                          uint32_t *__restrict__ vals_out, const int *count, const int *skip, int64_t capacity, int shift,
                          int bits, int tiles, const uint32_t *__restrict__ offsets) {
     pdl_enter();
+    constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     __shared__ uint32_t s_warp_hist[RS_WARPS][256];
     __shared__ uint32_t s_excl[256];      // block-local position of the first key of each digit
     __shared__ uint32_t s_out_base[256];  // global position of that key minus s_excl: out = s_out_base[d] + local position
@@ -295,10 +297,21 @@ int radix_sort_pairs(KeyT *keys_a, KeyT *keys_b, uint32_t *vals_a, uint32_t *val
     uint32_t *vout = vals_b;
     for (int p = 0; p < passes; p++) {
         const int bits = nbits - 8 * p < 8 ? nbits - 8 * p : 8;
-        launch_pdl(radix_count_kernel<KeyT>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, count, skip, capacity, 8 * p, bits, T.tiles, counts);
-        launch_pdl(radix_scan_kernel, dim3(T.scan_blocks), dim3(1024), 0, stream, counts, n_counts, lb + (size_t)p * T.scan_blocks, ticket + p);
-        launch_pdl(radix_scatter_kernel<KeyT>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, kout, vin, vout, count, skip, capacity, 8 * p, bits,
-                                                                       T.tiles, counts);
+        if (radix_items(capacity) == 8) {
+            launch_pdl(radix_count_kernel<KeyT, 8>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, count, skip, capacity, 8 * p,
+                       bits, T.tiles, counts);
+            launch_pdl(radix_scan_kernel, dim3(T.scan_blocks), dim3(1024), 0, stream, counts, n_counts,
+                       lb + (size_t)p * T.scan_blocks, ticket + p);
+            launch_pdl(radix_scatter_kernel<KeyT, 8>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, kout, vin, vout, count,
+                       skip, capacity, 8 * p, bits, T.tiles, counts);
+        } else {
+            launch_pdl(radix_count_kernel<KeyT, 16>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, count, skip, capacity, 8 * p,
+                       bits, T.tiles, counts);
+            launch_pdl(radix_scan_kernel, dim3(T.scan_blocks), dim3(1024), 0, stream, counts, n_counts,
+                       lb + (size_t)p * T.scan_blocks, ticket + p);
+            launch_pdl(radix_scatter_kernel<KeyT, 16>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, kout, vin, vout, count,
+                       skip, capacity, 8 * p, bits, T.tiles, counts);
+        }
         DQO_LAUNCH_CHECK("radix pass", 0, stream);
         note_launch(2);
         KeyT *tk = kin;

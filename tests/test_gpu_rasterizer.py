@@ -545,9 +545,10 @@ def test_gradients_against_float64_arbiter(cfg, mask, precomp):
     (oracle/f64_arbiter.py: torch float64 + autograd, independent of every hand-written backward):
         |ours - f64| <= max(1e-3 |f64|, 1.5 |reference - f64|)   per gradient tensor, norm-wise.
     No multiple-of-self-noise floor and no re-draw: both float32 implementations are measured against the exact value.
-    The reference's error is the largest of four runs: its float atomics land in unspecified order and the norm is
-    dominated by ONE ill-conditioned Gaussian per scene (tests/dev_arbiter_diag.py: > 99 % of the squared error of ours
-    AND of the reference sits in the same Gaussian, and the reference's own four runs range 4.8e-4 .. 9.1e-4)."""
+    Both errors are medians of four runs: the float atomics of either implementation land in unspecified order and the
+    norm is dominated by ONE ill-conditioned Gaussian per scene (tests/dev_arbiter_diag.py: > 99 % of the squared error
+    of ours AND of the reference sits in the same Gaussian; the reference's own four runs range 4.8e-4 .. 9.1e-4, ours
+    5e-4 .. 1.1e-3)."""
     from oracle import f64_arbiter
     inp = rh.make_inputs(cfg, torch.device(DEV), mask=mask, precomp=precomp)
     cam = inp["cam"]
@@ -555,7 +556,9 @@ def test_gradients_against_float64_arbiter(cfg, mask, precomp):
     o, ex, bw = _run_ours(inp, gc, gd)
     scene, lists = _arbiter_inputs(inp, o, ex)
     exact = f64_arbiter.gradients(scene, lists, gc, gd, device=DEV)
-    ours = dict(zip(GRADS, bw))
+    # both float32 implementations accumulate with float atomics in unspecified order: four runs each, medians compared
+    ours = [dict(zip(GRADS, bw))] + [dict(zip(GRADS, rasterizer.rasterize_gaussians_backward(*rh.backward_args(inp, o, gc, gd))))
+                                     for _ in range(3)]
     refs = []
     if rh.reference_available():
         C = rh.load_reference()[1]
@@ -566,13 +569,12 @@ def test_gradients_against_float64_arbiter(cfg, mask, precomp):
         if e.numel() <= 1:
             continue
         e = e.double()
-        a = ours[name].double().reshape(e.shape)
         nrm = float(e.norm())
         assert nrm > 0, name
-        err = float((a - e).norm())
+        err = float(np.median([float((a[name].double().reshape(e.shape) - e).norm()) for a in ours]))
         gate = 1e-3 * nrm
         if refs:
-            gate = max(gate, 1.5 * max(float((r[name].double().reshape(e.shape) - e).norm()) for r in refs))
+            gate = max(gate, 1.5 * float(np.median([float((r[name].double().reshape(e.shape) - e).norm()) for r in refs])))
         assert err <= gate, (name, err / nrm, gate / nrm)
         checked += 1
     assert checked == 5
