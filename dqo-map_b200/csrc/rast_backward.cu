@@ -94,59 +94,13 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     return v;
 }
 
-#define RB_BATCH 512
+#ifndef RB_BATCH
+#define RB_BATCH 256 // 80-byte records + mask + four u16 lists: 23 KB per block, eight blocks per SM
+#endif
 #ifndef RB_OCC
-#define RB_OCC 6
+#define RB_OCC 8 // 64 registers: the loop is latency-bound (one dependent chain per warp), warps are what hides it
 #endif
 #define RB_THREADS 128 // 4 warps x (8x8 pixels); every thread owns the pixels (x, y) and (x, y + 4)
-
-// per-pixel state of the reverse traversal (backward.cu:881-900)
-struct BwdPix {
-    float T, T_final, acc0, acc1, acc2, dLp0, dLp1, dLp2, bg_dot, pixfy;
-    int last_contributor;
-};
-
-// One (splat, pixel) pair of the reverse blend (backward.cu:926-995): adds this pixel's 9 partial gradients to v.
-// The rejections of the reference (position behind the pixel's last contributor, power > 0, alpha < 1/255; the staged
-// power_reject bound is implied by the alpha test) are folded into ONE predicate after the exponential, so the pair
-// is a straight-line prologue plus a single guarded update instead of four exits.
-__device__ __forceinline__ bool bwd_pair(BwdPix &p, bool reach, const float4 r0, const float4 r1, const float4 r2, int posj,
-                                         float pixfx, float ddelx_dx, float ddely_dy, float v[9]) {
-    const float dx = fsub(r0.x, pixfx), dy = fsub(r0.y, p.pixfy);
-    const float power = ffma(ffma(dx, fmul(dx, r0.z), fmul(dy, fmul(dy, r1.x))), -0.5f, -fmul(dy, fmul(dx, r0.w)));
-    const float G = expf(power);
-    const float alpha = fminf(0.99f, fmul(r1.y, G));
-    const bool live = reach && (posj < p.last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-    if (live) {
-        // IEEE division as in the reference (backward.cu:947): the conic -> cov3D -> rotation chain downstream amplifies
-        // a 1-ulp change of T to ~1e-3 in dL_drotations, so approximations here are not free
-        p.T = p.T / (1.f - alpha);
-        const float dchannel_dcolor = alpha * p.T;
-        // accum_rec of the reference (backward.cu:953-961) is last_alpha * last_color + (1 - last_alpha) * accum_rec,
-        // evaluated when the NEXT contributor is visited; the same expression is evaluated here one visit earlier, so
-        // last_alpha / last_color need not be carried (8 registers for the two pixels of a thread)
-        float dL_dalpha = (r2.x - p.acc0) * p.dLp0 + (r2.y - p.acc1) * p.dLp1 + (r2.z - p.acc2) * p.dLp2;
-        dL_dalpha *= p.T;
-        p.acc0 = alpha * r2.x + (1.f - alpha) * p.acc0;
-        p.acc1 = alpha * r2.y + (1.f - alpha) * p.acc1;
-        p.acc2 = alpha * r2.z + (1.f - alpha) * p.acc2;
-        if (p.bg_dot != 0.f) dL_dalpha += (-p.T_final / (1.f - alpha)) * p.bg_dot; // background term (backward.cu:975), 0 for bg = 0
-        const float dL_dG = r1.y * dL_dalpha;
-        const float gdx = G * dx, gdy = G * dy;
-        const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
-        const float dG_ddely = -gdy * r1.x - gdx * r0.w;
-        v[0] += dL_dG * dG_ddelx * ddelx_dx;
-        v[1] += dL_dG * dG_ddely * ddely_dy;
-        v[2] += -0.5f * gdx * dx * dL_dG;
-        v[3] += -0.5f * gdx * dy * dL_dG;
-        v[4] += -0.5f * gdy * dy * dL_dG;
-        v[5] += G * dL_dalpha;
-        v[6] += dchannel_dcolor * p.dLp0;
-        v[7] += dchannel_dcolor * p.dLp1;
-        v[8] += dchannel_dcolor * p.dLp2;
-    }
-    return live;
-}
 
 // depth gradient to the single hit Gaussian of a pixel (backward.cu:998-1065)
 __device__ __noinline__ void bwd_depth_path(const float *scales, const float *rotations, const float *means3D,
@@ -211,18 +165,33 @@ __device__ __noinline__ void bwd_depth_path(const float *scales, const float *ro
     }
 }
 
-// Reverse blend of one 16x16 tile.  Same thread / warp layout and per-warp culled lists as the forward kernel; the
-// two pixels of a thread add into the same 9 partial sums before the single warp reduction per splat.
+// Reverse blend of one 16x16 tile.  Same per-warp culled lists as the forward kernel; a warp owns an 8x8 pixel block and
+// every thread the two pixels (x, y) and (x, y + 4).
+//
+// The loop is bound by instruction issue, not by any pipe, so the two pixels of a thread are evaluated as the two
+// halves of Blackwell's packed FP32 instructions (fma / mul / add .f32x2, __ffma2_rn & co.): one issue slot per pair of
+// IEEE-rounded operations (measured: 8 FFMA + 16 integer ops per iteration take 0.67 ms, 4 FFMA2 + 16 integer ops
+// 0.41 ms, tests/microbench/ffma2.cu).  Every per-lane result is the same correctly rounded value a scalar
+// instruction gives.  The staged record keeps each field DUPLICATED ({v, v}) so that a 128-bit shared-memory load
+// yields ready-made operand pairs; conic.y is stored negated (sign flips commute with rounding), which turns the
+// subtractions of the power and of dG/ddelta into plain FMAs.  exp (FFMA.SAT / .RM sequence), min and the IEEE
+// division stay scalar.
 struct __align__(16) SplatB {
-    float4 r0, r1, c; // {x, y, conic.x, conic.y} {conic.z, opacity, power_reject, -} {r, g, b, Gaussian id bits}
+    float2 x, y, cx, ncy, cz, op, r, g, b; // duplicated fields: {v, v}
+    float id_bits, pad;                    // 80 bytes
 };
+typedef float2 f2;
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 dup(float v) { return make_float2(v, v); }
+__device__ __forceinline__ f2 lo_hi(float4 q, int h) { return h ? make_float2(q.z, q.w) : make_float2(q.x, q.y); }
 
 __global__ void __launch_bounds__(RB_THREADS, RB_OCC) render_backward_kernel(RenderBwdArgs a) {
     pdl_enter();
-    // RB_BATCH entries are staged per round.  With 512 most tiles need a single round (max n_contrib is a few hundred):
-    // the four warps then walk their own lists without meeting at a barrier after every 256 entries, where the fast
-    // ones used to wait for the slowest sub-block.
-    __shared__ SplatB s_sp[RB_BATCH]; // one 48-byte record per staged splat: a single base + j*48 address in the loop
+    // RB_BATCH entries are staged per round; most tiles need a single round (max n_contrib is a few hundred): the four
+    // warps then walk their own lists without meeting at a barrier, where the fast ones would wait for the slowest.
+    __shared__ SplatB s_sp[RB_BATCH];
     __shared__ uint8_t s_mask[RB_BATCH];
     // per-warp list entry: batch slot (9 bits) | reach bit of the upper pixel row block << 14 | of the lower << 15
     __shared__ uint16_t s_list[RB_THREADS / 32][RB_BATCH];
@@ -247,38 +216,38 @@ __global__ void __launch_bounds__(RB_THREADS, RB_OCC) render_backward_kernel(Ren
     const int lx = (warp & 1) * 8 + (lane & 7), ly0 = (warp >> 1) * 8 + (lane >> 3);
     const uint32_t pix_x = tile_x * DQO_TILE + lx;
     const size_t HW = (size_t)a.W * a.H;
-    const float pixfx = (float)pix_x;
     const float tile_px = (float)(tile_x * DQO_TILE), tile_py = (float)(tile_y * DQO_TILE);
     const int b_lo = 2 * (2 * (warp >> 1)) + (warp & 1), b_hi = b_lo + 2;
     const unsigned warp_bits = (1u << b_lo) | (1u << b_hi);
 
-    BwdPix px[2];
-    uint32_t pix_y[2];
-    bool inside[2];
-    size_t pix_id[2], sp[2];
+    // per-pixel state of the reverse traversal (backward.cu:881-900), pixel h in half h of every pair
+    float Tv[2], Tfin[2], dl0[2], dl1[2], dl2[2], bgd[2];
+    int last_c[2];
     int warp_max = 0;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int ly = ly0 + 4 * h;
-        pix_y[h] = tile_y * DQO_TILE + ly;
-        inside[h] = pix_x < (uint32_t)a.W && pix_y[h] < (uint32_t)a.H;
-        pix_id[h] = (size_t)a.W * pix_y[h] + pix_x;
-        sp[h] = (size_t)tile * 256 + ly * 16 + lx;
-        BwdPix &p = px[h];
-        p.pixfy = (float)pix_y[h];
-        p.T_final = inside[h] ? a.final_T[sp[h]] : 0.f;
-        p.T = p.T_final;
-        p.last_contributor = inside[h] ? (int)a.n_contrib[sp[h]] : 0;
-        p.dLp0 = p.dLp1 = p.dLp2 = 0.f;
-        if (inside[h]) {
-            p.dLp0 = a.dL_dpix[pix_id[h]];
-            p.dLp1 = a.dL_dpix[HW + pix_id[h]];
-            p.dLp2 = a.dL_dpix[2 * HW + pix_id[h]];
+        const uint32_t py = tile_y * DQO_TILE + ly;
+        const bool inside = pix_x < (uint32_t)a.W && py < (uint32_t)a.H;
+        const size_t pid = (size_t)a.W * py + pix_x, sp = (size_t)tile * 256 + ly * 16 + lx;
+        Tfin[h] = inside ? a.final_T[sp] : 0.f;
+        Tv[h] = Tfin[h];
+        last_c[h] = inside ? (int)a.n_contrib[sp] : 0;
+        dl0[h] = dl1[h] = dl2[h] = 0.f;
+        if (inside) {
+            dl0[h] = a.dL_dpix[pid];
+            dl1[h] = a.dL_dpix[HW + pid];
+            dl2[h] = a.dL_dpix[2 * HW + pid];
         }
-        p.bg_dot = a.bg[0] * p.dLp0 + a.bg[1] * p.dLp1 + a.bg[2] * p.dLp2;
-        p.acc0 = p.acc1 = p.acc2 = 0.f;
-        warp_max = max(warp_max, p.last_contributor);
+        bgd[h] = a.bg[0] * dl0[h] + a.bg[1] * dl1[h] + a.bg[2] * dl2[h];
+        warp_max = max(warp_max, last_c[h]);
     }
+    f2 T2 = make_float2(Tv[0], Tv[1]);
+    const f2 dLp0 = make_float2(dl0[0], dl0[1]), dLp1 = make_float2(dl1[0], dl1[1]), dLp2 = make_float2(dl2[0], dl2[1]);
+    f2 acc0 = dup(0.f), acc1 = dup(0.f), acc2 = dup(0.f);
+    const bool any_bg = bgd[0] != 0.f || bgd[1] != 0.f; // background term (backward.cu:975), 0 for bg = 0
+    const f2 npx = dup(-(float)pix_x);
+    const f2 npy = make_float2(-(float)(tile_y * DQO_TILE + ly0), -(float)(tile_y * DQO_TILE + ly0 + 4));
     if (tid == 0) s_max = 0;
     __syncthreads();
     // entries at positions >= warp_max contribute to no pixel of this warp, >= max_c to no pixel of the tile
@@ -286,8 +255,9 @@ __global__ void __launch_bounds__(RB_THREADS, RB_OCC) render_backward_kernel(Ren
     if (lane == 0) atomicMax(&s_max, warp_max);
     __syncthreads();
     const int max_c = s_max;
-    const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+    const f2 ddel = make_float2(0.5f * a.W, 0.5f * a.H); // {ddelx_dx, ddely_dy}
     const int my_slot = slot_of_lane(lane);
+    const f2 one2 = dup(1.f), mone2 = dup(-1.f), mhalf2 = dup(-0.5f);
 
     const uint32_t sp_base = smem_addr(s_sp), list_base = smem_addr(&s_list[warp][0]);
     const int rounds = (max_c + RB_BATCH - 1) / RB_BATCH;
@@ -303,9 +273,12 @@ __global__ void __launch_bounds__(RB_THREADS, RB_OCC) render_backward_kernel(Ren
                 const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
                 const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
                 const float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
-                s_sp[slot].r0 = r0;
-                s_sp[slot].r1 = r1;
-                s_sp[slot].c = make_float4(r2.x, r2.y, r2.z, __int_as_float(id));
+                float4 *dst = reinterpret_cast<float4 *>(&s_sp[slot]);
+                dst[0] = make_float4(r0.x, r0.x, r0.y, r0.y);
+                dst[1] = make_float4(r0.z, r0.z, -r0.w, -r0.w);
+                dst[2] = make_float4(r1.x, r1.x, r1.y, r1.y);
+                dst[3] = make_float4(r2.x, r2.x, r2.y, r2.y);
+                dst[4] = make_float4(r2.z, r2.z, __int_as_float(id), 0.f);
                 s_mask[slot] = (uint8_t)subblock_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, r1.w, tile_px, tile_py);
             }
         }
@@ -327,28 +300,74 @@ __global__ void __launch_bounds__(RB_THREADS, RB_OCC) render_backward_kernel(Ren
         for (int k = 0; k < cnt; k++) {
             const uint32_t e = lds_u16(list_base + 2 * k);
             const int j = (int)(e & 0x3FFFu);
-            const uint32_t rec = sp_base + (uint32_t)j * 48u;
-            const float4 r0 = lds128(rec);
-            const float4 r1 = lds128(rec + 16);
-            const float4 r2 = lds128(rec + 32);
+            const uint32_t rec = sp_base + (uint32_t)j * 80u;
+            const float4 q0 = lds128(rec), q1 = lds128(rec + 16), q2 = lds128(rec + 32);
+            const f2 x2 = lo_hi(q0, 0), y2 = lo_hi(q0, 1), cx2 = lo_hi(q1, 0), ncy2 = lo_hi(q1, 1), cz2 = lo_hi(q2, 0),
+                     op2 = lo_hi(q2, 1);
             const int posj = pos_top - j;
-            float v[9];
-#pragma unroll
-            for (int q = 0; q < 9; q++) v[q] = 0.f;
-            bool contrib = bwd_pair(px[0], (e & 0x4000u) != 0, r0, r1, r2, posj, pixfx, ddelx_dx, ddely_dy, v);
-            contrib |= bwd_pair(px[1], (e & 0x8000u) != 0, r0, r1, r2, posj, pixfx, ddelx_dx, ddely_dy, v);
-            if (!__any_sync(0xFFFFFFFFu, contrib)) continue;
+            // power (backward.cu:931-934), both pixels at once, in the forward's operation order
+            const f2 dx2 = add2(x2, npx), dy2 = add2(y2, npy);
+            const f2 inner = fma2(dx2, mul2(dx2, cx2), mul2(dy2, mul2(dy2, cz2)));
+            const f2 power = fma2(inner, mhalf2, mul2(dy2, mul2(dx2, ncy2)));
+            const f2 G2 = make_float2(expf(power.x), expf(power.y));
+            const f2 al = mul2(op2, G2);
+            const f2 alpha = make_float2(fminf(0.99f, al.x), fminf(0.99f, al.y));
+            const bool live0 = (e & 0x4000u) && (posj < last_c[0]) && !(power.x > 0.0f) && !(alpha.x < 1.0f / 255.0f);
+            const bool live1 = (e & 0x8000u) && (posj < last_c[1]) && !(power.y > 0.0f) && !(alpha.y < 1.0f / 255.0f);
+            if (!__any_sync(0xFFFFFFFFu, live0 || live1)) continue;
+            const float4 q3 = lds128(rec + 32 + 16), q4 = lds128(rec + 64);
+            const f2 cr = lo_hi(q3, 0), cg = lo_hi(q3, 1), cb = lo_hi(q4, 0);
+            const f2 om = fma2(alpha, mone2, one2); // 1 - alpha
+            // IEEE division as in the reference (backward.cu:947): the conic -> cov3D -> rotation chain downstream amplifies
+            // a 1-ulp change of T to ~1e-3 in dL_drotations, so approximations here are not free
+            const f2 Tn = make_float2(T2.x / om.x, T2.y / om.y);
+            // accum_rec of the reference (backward.cu:953-961) is last_alpha * last_color + (1 - last_alpha) * accum_rec,
+            // evaluated when the NEXT contributor is visited; the same expression is evaluated here one visit earlier, so
+            // last_alpha / last_color need not be carried
+            f2 dLa = mul2(fma2(acc0, mone2, cr), dLp0);
+            dLa = fma2(fma2(acc1, mone2, cg), dLp1, dLa);
+            dLa = fma2(fma2(acc2, mone2, cb), dLp2, dLa);
+            dLa = mul2(dLa, Tn);
+            const f2 n0 = fma2(om, acc0, mul2(alpha, cr)), n1 = fma2(om, acc1, mul2(alpha, cg)),
+                     n2 = fma2(om, acc2, mul2(alpha, cb));
+            if (any_bg) {
+                dLa.x += (-Tfin[0] / om.x) * bgd[0];
+                dLa.y += (-Tfin[1] / om.y) * bgd[1];
+            }
+            // a rejected pair keeps its pixel's state and contributes zeros: the three roots of the nine products below
+            T2 = make_float2(live0 ? Tn.x : T2.x, live1 ? Tn.y : T2.y);
+            acc0 = make_float2(live0 ? n0.x : acc0.x, live1 ? n0.y : acc0.y);
+            acc1 = make_float2(live0 ? n1.x : acc1.x, live1 ? n1.y : acc1.y);
+            acc2 = make_float2(live0 ? n2.x : acc2.x, live1 ? n2.y : acc2.y);
+            dLa = make_float2(live0 ? dLa.x : 0.f, live1 ? dLa.y : 0.f);
+            const f2 G = make_float2(live0 ? G2.x : 0.f, live1 ? G2.y : 0.f);
+            const f2 aT = mul2(alpha, Tn);
+            const f2 dch = make_float2(live0 ? aT.x : 0.f, live1 ? aT.y : 0.f); // dchannel_dcolor
+            const f2 dL_dG = mul2(op2, dLa);
+            const f2 gdx = mul2(G, dx2), gdy = mul2(G, dy2);
+            // dG_ddelx = -gdx * conic.x - gdy * conic.y, dG_ddely = -gdy * conic.z - gdx * conic.y
+            const f2 dGx = fma2(gdy, ncy2, mul2(mul2(gdx, mone2), cx2));
+            const f2 dGy = fma2(gdx, ncy2, mul2(mul2(gdy, mone2), cz2));
+            const f2 hx = mul2(mul2(gdx, mhalf2), dL_dG), hy = mul2(mul2(gdy, mhalf2), dL_dG);
+            const f2 p0 = mul2(mul2(dL_dG, dGx), dup(ddel.x)), p1 = mul2(mul2(dL_dG, dGy), dup(ddel.y));
+            const f2 p2 = mul2(hx, dx2), p3 = mul2(hx, dy2), p4 = mul2(hy, dy2), p5 = mul2(G, dLa);
+            const f2 p6 = mul2(dch, dLp0), p7 = mul2(dch, dLp1), p8 = mul2(dch, dLp2);
+            float v[9] = {p0.x + p0.y, p1.x + p1.y, p2.x + p2.y, p3.x + p3.y, p4.x + p4.y,
+                          p5.x + p5.y, p6.x + p6.y, p7.x + p7.y, p8.x + p8.y};
             const float total = warp_reduce9(v, lane);
-            if (my_slot >= 0) atomicAdd(&a.gacc[(size_t)__float_as_int(r2.w) * DQO_GACC_FLOATS + my_slot], total);
+            if (my_slot >= 0) atomicAdd(&a.gacc[(size_t)__float_as_int(q4.z) * DQO_GACC_FLOATS + my_slot], total);
         }
     }
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        if (!inside[h]) continue;
-        const int gid = a.hit_image[pix_id[h]];
+        const int ly = ly0 + 4 * h;
+        const uint32_t py = tile_y * DQO_TILE + ly;
+        if (!(pix_x < (uint32_t)a.W && py < (uint32_t)a.H)) continue;
+        const size_t pid = (size_t)a.W * py + pix_x;
+        const int gid = a.hit_image[pid];
         if (gid >= 0)
-            bwd_depth_path(a.scales, a.rotations, a.means3D, a.view, a.hit_geo, a.plane, sp[h], a.gacc, gid,
-                           a.dL_ddepth[pix_id[h]], pix_x, pix_y[h], a.fx, a.fy, a.cx, a.cy, a.depth_thr, a.normal_thr);
+            bwd_depth_path(a.scales, a.rotations, a.means3D, a.view, a.hit_geo, a.plane, (size_t)tile * 256 + ly * 16 + lx,
+                           a.gacc, gid, a.dL_ddepth[pid], pix_x, py, a.fx, a.fy, a.cx, a.cy, a.depth_thr, a.normal_thr);
     }
 }
 
