@@ -913,7 +913,7 @@ __device__ __forceinline__ uint32_t lds_u16x2(uint32_t addr) {
 #define RF_LIST_STRIDE 264 // u16 entries per warp list: 256 + sentinel padding, multiple of 4
 
 template <int PHASE, bool NT>
-__global__ void __launch_bounds__(256, 4) render_forward_kernel(RenderArgs a) {
+__global__ void __launch_bounds__(256, PHASE == 2 ? 2 : 4) render_forward_kernel(RenderArgs a) {
     pdl_enter();
     __shared__ SplatS s_sp[257]; // one 48-byte record per staged splat (+ an all-zero sentinel that never contributes)
     __shared__ uint8_t s_mask[256];
@@ -996,22 +996,47 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(RenderArgs a) {
     // first opaque hit (forward.cu:785-812) depends only on the hit Gaussian and the pixel: the loop records the event,
     // the plane / normal math runs once per pixel after the walk.
     float hit_w = 0.f; // alpha * T at the hit event
+    // PHASE 2 walks the long tails of a few hundred unfinished tiles (thousands of entries each, most pixels already
+    // terminated): one or two resident blocks per SM, every round a chain of two dependent memory round trips (list
+    // entry -> splat record) with little blending behind it.  There the next round's entry is fetched into registers
+    // while the current round is compacted and blended (software pipelining; the other phases have the occupancy to
+    // hide the latency and no registers to spare).
+    int pf_id = 0;
+    float4 pf0 = make_float4(0.f, 0.f, 0.f, 0.f), pf1 = pf0, pf2 = pf0;
+    if (PHASE == 2 && tid < total) {
+        pf_id = (int)point_list[range.x + tid];
+        pf0 = __ldg(&a.rec[3 * (size_t)pf_id]);
+        pf1 = __ldg(&a.rec[3 * (size_t)pf_id + 1]);
+        pf2 = __ldg(&a.rec[3 * (size_t)pf_id + 2]);
+    }
     int i = 0;
     for (; i < rounds; i++) {
         if (__syncthreads_count(__float_as_int(T) < 0) == 256) break;
         const int progress = i * 256 + tid;
         const int n = min(256, total - i * 256);
         if (progress < total) {
-            const int id = (int)point_list[range.x + progress];
-            const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
-            const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
-            const float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
+            int id;
+            float4 r0, r1, r2;
+            if (PHASE == 2) {
+                id = pf_id; r0 = pf0; r1 = pf1; r2 = pf2;
+            } else {
+                id = (int)point_list[range.x + progress];
+                r0 = __ldg(&a.rec[3 * (size_t)id]);
+                r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
+                r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
+            }
             s_sp[tid].r0 = r0;
             s_sp[tid].r1 = r1;
             s_sp[tid].c = make_float4(r2.x, r2.y, r2.z, __int_as_float(id));
             s_mask[tid] = (uint8_t)subblock_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r2.w, r1.w, tile_px, tile_py);
         }
         __syncthreads();
+        if (PHASE == 2 && progress + 256 < total) {
+            pf_id = (int)point_list[range.x + progress + 256];
+            pf0 = __ldg(&a.rec[3 * (size_t)pf_id]);
+            pf1 = __ldg(&a.rec[3 * (size_t)pf_id + 1]);
+            pf2 = __ldg(&a.rec[3 * (size_t)pf_id + 2]);
+        }
         // per-warp compaction of the batch (order preserved)
         int cnt = 0;
         if (!__all_sync(0xFFFFFFFFu, __float_as_int(T) < 0)) {
