@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # DQO_B200_LIB: another build of the same library (kernel A/B experiments, tests/dev_*.py); there is still no fallback
 LIB_PATH = os.environ.get("DQO_B200_LIB") or os.path.join(_HERE, "csrc", "libdqomap_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_R_FRONT, ST_R_BACK, ST_WALKED, ST_UNFINISHED = range(8)
 ST_WORDS = 8
@@ -25,7 +25,7 @@ class RastSettings(C.Structure):
         ("scale_modifier", C.c_float), ("color_sigma", C.c_float), ("opaque_threshold", C.c_float),
         ("depth_threshold", C.c_float), ("normal_threshold", C.c_float), ("T_threshold", C.c_float),
         ("prefiltered", C.c_int32), ("debug", C.c_int32), ("need_n_touched", C.c_int32),
-        ("front_instances", C.c_int32), ("back_instances", C.c_int32),
+        ("front_instances", C.c_int32), ("back_instances", C.c_int32), ("geom_clean", C.c_int32),
     ]
 
 
@@ -58,6 +58,7 @@ PROTOTYPES = {
     "dqo_profile_enable": (None, [C.c_int]),
     "dqo_profile_read": (C.c_int, [C.POINTER(C.c_float), C.c_int]),
     "dqo_rast_geom_bytes": (C.c_size_t, [C.c_int32]),
+    "dqo_rast_geom_init": (C.c_int, [C.c_int32, c_p, c_p]),
     "dqo_rast_binning_bytes": (C.c_size_t, [C.c_int64]),
     "dqo_rast_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "dqo_rast_forward": (C.c_int, [C.POINTER(RastSettings)] + [c_p] * 12 + [c_p, c_p, C.c_int64, c_p] + [c_p] * 12),
@@ -98,6 +99,7 @@ PROTOTYPES = {
     "dqo_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                                 c_p, C.c_int32, c_p]),
     "dqo_mapping_step_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
+    "dqo_mapping_step_workspace_init": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, c_p, c_p]),
     "dqo_mapping_step": (C.c_int, [C.POINTER(RastSettings), C.POINTER(MapParams), C.POINTER(Keyframe), C.c_int32,
                                    C.c_double, C.c_double, C.c_double, c_p, C.c_int64, c_p, c_p, c_p, c_p]),
     "dqo_attach_count": (C.c_int, [C.c_int32, c_p, C.c_float, c_p, c_p]),

@@ -13,7 +13,7 @@
 
 #define DQO_TILE 16
 #define DQO_TILE_PIX 256
-#define DQO_ABI_VERSION 11
+#define DQO_ABI_VERSION 12
 
 namespace dqo {
 
@@ -211,7 +211,7 @@ struct GeomLayout {
     size_t offsets;    // u32[P] inclusive scan of tiles_touched in depth-rank order
     size_t rect;       // uint2[P] {min.x | max.x<<16, min.y | max.y<<16}
     size_t clamped;    // u8[P] bit c = colour channel c clamped (forward.cu:151-153)
-    size_t gacc;       // f32[16P] gradient accumulators of the backward blend (see DQO_GACC_FLOATS)
+    size_t gacc;       // f64[16P] gradient accumulators of the backward blend (see DQO_GACC_FLOATS)
     size_t tiles_b;    // u32[P] two-phase: unfinished tiles in the rectangle of every rank the front phase left out
     size_t sums;       // per phase: u32[emit_blocks] totals of 256 ranks + u32[emit_groups] totals of 64 such blocks
     size_t sums_stride;
@@ -305,7 +305,9 @@ inline bool bin_sorted_in_a(int T) { return ((tile_sort_bits(T) < 1 ? 1 : tile_s
 inline size_t bin_point_list(const BinLayout &BL, int T) { return bin_sorted_in_a(T) ? BL.vals_a : BL.vals_b; }
 inline size_t bin_sorted_keys(const BinLayout &BL, int T) { return bin_sorted_in_a(T) ? BL.keys_a : BL.keys_b; }
 
-// per-Gaussian gradient accumulator written by the backward blend (16 floats = 64 B)
+// per-Gaussian gradient accumulator written by the backward blend: 16 DOUBLES (128 B).  Every warp adds its fp32 partial
+// sums with fp64 atomics, so the order in which warps and tiles arrive no longer shows in the result (the reference's
+// float atomics make its gradients differ run to run by up to 1e-3 for ill-conditioned Gaussians)
 // {dmean2D.x, dmean2D.y, dconic.x, dconic.y | dconic.w, dopacity, dcolor.r, dcolor.g | dcolor.b, dmean3D.xyz | drot.rxyz}
 #define DQO_GACC_FLOATS 16
 

@@ -22,7 +22,7 @@ int rast_forward_impl(const dqo_rast_settings *s, const float *background, const
                       void *binning_buffer, int64_t capacity, void *image_buffer, int32_t *tile_indices, float *out_color,
                       float *out_depth, int32_t *out_hit_depth, int32_t *out_hit_color, float *out_hit_color_weight,
                       float *out_hit_depth_weight, float *out_T, int32_t *radii, int32_t *n_touched, int32_t *status,
-                      void *stream_);
+                      void *stream_, void (*pre_hook)(void *, void *), void *hook_ctx);
 int rast_backward_impl(const dqo_rast_settings *s, const float *background, const float *means3D, const float *shs,
                        const float *f_rest, const float *colors_precomp, const float *scales, const float *rotations,
                        const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix, const float *campos,
@@ -611,6 +611,17 @@ extern "C" size_t dqo_mapping_step_workspace_bytes(int32_t P, int32_t M, int32_t
     return L.total;
 }
 
+extern "C" int dqo_rast_geom_init(int32_t P, void *geom_buffer, void *stream);
+extern "C" int dqo_mapping_step_workspace_init(int32_t P, int32_t M, int32_t W, int32_t H, int64_t capacity, void *workspace,
+                                               void *stream) {
+    StepLayout L;
+    if (!workspace || make_step_layout(P, M, W, H, capacity, &L)) {
+        set_error("dqo_mapping_step_workspace_init: invalid argument");
+        return DQO_ERR_INVALID_ARG;
+    }
+    return dqo_rast_geom_init(P, (char *)workspace + L.geom, stream);
+}
+
 extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params *p, const dqo_keyframe *kf, int32_t step,
                                 double beta1, double beta2, double eps, void *workspace, int64_t capacity,
                                 float *loss_out, int32_t *counts_out, int32_t *status, void *stream_) {
@@ -638,8 +649,18 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
     float *act_op = (float *)(ws + L.act_opacity), *act_sc = (float *)(ws + L.act_scales), *act_rot = (float *)(ws + L.act_rot);
     float *xyz = p->param[0], *f_dc = p->param[1], *f_rest = (M == 16) ? p->param[2] : nullptr;
     const int nb = (P + 255) / 256;
-    launch_pdl(activate_kernel, dim3(nb), dim3(256), 0, stream, P, p->param[3], p->param[4], p->param[5], act_op, act_sc, act_rot);
-    DQO_LAUNCH_CHECK("activate", s->debug, stream);
+    // the activations are launched by the forward pass right behind the fork of its depth sort (which needs positions only)
+    struct ActivateCtx {
+        int P, nb;
+        const float *op, *sc, *rot;
+        float *act_op, *act_sc, *act_rot;
+    } actx = {P, nb, p->param[3], p->param[4], p->param[5], act_op, act_sc, act_rot};
+    auto activate_hook = [](void *ctx, void *st) {
+        const ActivateCtx *c = (const ActivateCtx *)ctx;
+        launch_pdl(activate_kernel, dim3(c->nb), dim3(256), 0, (cudaStream_t)st, c->P, c->op, c->sc, c->rot, c->act_op, c->act_sc,
+                   c->act_rot);
+        note_launch();
+    };
 
     float *color = (float *)(ws + L.color), *depth = (float *)(ws + L.depth);
     int32_t *hit_depth = (int32_t *)(ws + L.hit_depth), *radii = (int32_t *)(ws + L.radii);
@@ -647,7 +668,8 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
                                kf->projmatrix, kf->campos, kf->tile_mask, ws + L.geom, ws + L.binning, capacity,
                                ws + L.image, (int32_t *)(ws + L.tile_indices), color, depth, hit_depth,
                                (int32_t *)(ws + L.hit_color), (float *)(ws + L.hit_cw), (float *)(ws + L.hit_dw),
-                               (float *)(ws + L.T), radii, (int32_t *)(ws + L.n_touched), status, stream_);
+                               (float *)(ws + L.T), radii, (int32_t *)(ws + L.n_touched), status, stream_, activate_hook,
+                               &actx);
     if (rc) return rc;
     float *g_img = (float *)(ws + L.g_img), *g_depth = (float *)(ws + L.g_depth);
     rc = dqo_masked_l1_loss(W, H, color, depth, hit_depth, kf->gt_color, kf->gt_depth, kf->render_mask, kf->color_weight,

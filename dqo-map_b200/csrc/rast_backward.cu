@@ -30,7 +30,7 @@ struct RenderBwdArgs {
     size_t plane;
     const float *dL_dpix, *dL_ddepth;
     const int *hit_image;
-    float *gacc;
+    double *gacc;
 };
 
 // Sum 9 per-lane values over the warp; on return lanes with (lane & 1) == 0 whose slot index < 9 hold the
@@ -104,7 +104,7 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 
 // depth gradient to the single hit Gaussian of a pixel (backward.cu:998-1065)
 __device__ __noinline__ void bwd_depth_path(const float *scales, const float *rotations, const float *means3D,
-                                            const float *view, const float *hit_geo, size_t plane, size_t sp, float *gacc,
+                                            const float *view, const float *hit_geo, size_t plane, size_t sp, double *gacc,
                                             int gid, float g, uint32_t pix_x, uint32_t pix_y, float fx, float fy, float cx,
                                             float cy, float depth_thr, float normal_thr) {
     const float3 ray = pixel_ray(pix_x, pix_y, fx, fy, cx, cy);
@@ -118,16 +118,16 @@ __device__ __noinline__ void bwd_depth_path(const float *scales, const float *ro
     const float ndotr = dot3_ref(ncx, ray.x, ncy, ray.y, ncz, ray.z);
     const float angle_distance = fabsf(ndotr);
     const float depth_distance = fabsf(fsub(hz, pcz));
-    float *acc = gacc + (size_t)gid * DQO_GACC_FLOATS;
+    double *acc = gacc + (size_t)gid * DQO_GACC_FLOATS;
     if (depth_distance <= fmul(depth_thr, scale_max) && angle_distance >= normal_thr) {
         const float nr = (float)((double)ndotr + 1e-8);
         const float inv_nr = 1.f / nr;
         const float inv_nr2 = inv_nr * inv_nr;
         const float np = ncx * pcx + ncy * pcy + ncz * pcz;
         const float dpx = ray.z * ncx * inv_nr, dpy = ray.z * ncy * inv_nr, dpz = ray.z * ncz * inv_nr;
-        atomicAdd(&acc[9], g * (dpx * v[0] + dpy * v[1] + dpz * v[2]));
-        atomicAdd(&acc[10], g * (dpx * v[4] + dpy * v[5] + dpz * v[6]));
-        atomicAdd(&acc[11], g * (dpx * v[8] + dpy * v[9] + dpz * v[10]));
+        atomicAdd(&acc[9], (double)(g * (dpx * v[0] + dpy * v[1] + dpz * v[2])));
+        atomicAdd(&acc[10], (double)(g * (dpx * v[4] + dpy * v[5] + dpz * v[6])));
+        atomicAdd(&acc[11], (double)(g * (dpx * v[8] + dpy * v[9] + dpz * v[10])));
         const int axis = arg_min3(sx, sy, sz);
         const float n1c = ray.z * (nr * pcx - np * ray.x) * inv_nr2;
         const float n2c = ray.z * (nr * pcy - np * ray.y) * inv_nr2;
@@ -154,14 +154,14 @@ __device__ __noinline__ void bwd_depth_path(const float *scales, const float *ro
             d2[0] = 2 * q0; d2[1] = 2 * q3; d2[2] = -4 * q2;
             d3[0] = 2 * q1; d3[1] = 2 * q2; d3[2] = 0;
         }
-        atomicAdd(&acc[12], g * (n1w * d0[0] + n2w * d0[1] + n3w * d0[2]));
-        atomicAdd(&acc[13], g * (n1w * d1[0] + n2w * d1[1] + n3w * d1[2]));
-        atomicAdd(&acc[14], g * (n1w * d2[0] + n2w * d2[1] + n3w * d2[2]));
-        atomicAdd(&acc[15], g * (n1w * d3[0] + n2w * d3[1] + n3w * d3[2]));
+        atomicAdd(&acc[12], (double)(g * (n1w * d0[0] + n2w * d0[1] + n3w * d0[2])));
+        atomicAdd(&acc[13], (double)(g * (n1w * d1[0] + n2w * d1[1] + n3w * d1[2])));
+        atomicAdd(&acc[14], (double)(g * (n1w * d2[0] + n2w * d2[1] + n3w * d2[2])));
+        atomicAdd(&acc[15], (double)(g * (n1w * d3[0] + n2w * d3[1] + n3w * d3[2])));
     } else {
-        atomicAdd(&acc[9], g * v[2]);
-        atomicAdd(&acc[10], g * v[6]);
-        atomicAdd(&acc[11], g * v[10]);
+        atomicAdd(&acc[9], (double)(g * v[2]));
+        atomicAdd(&acc[10], (double)(g * v[6]));
+        atomicAdd(&acc[11], (double)(g * v[10]));
     }
 }
 
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(RB_THREADS, RB_OCC) render_backward_kernel(Ren
             float v[9] = {p0.x + p0.y, p1.x + p1.y, p2.x + p2.y, p3.x + p3.y, p4.x + p4.y,
                           p5.x + p5.y, p6.x + p6.y, p7.x + p7.y, p8.x + p8.y};
             const float total = warp_reduce9(v, lane);
-            if (my_slot >= 0) atomicAdd(&a.gacc[(size_t)__float_as_int(q4.z) * DQO_GACC_FLOATS + my_slot], total);
+            if (my_slot >= 0) atomicAdd(&a.gacc[(size_t)__float_as_int(q4.z) * DQO_GACC_FLOATS + my_slot], (double)total);
         }
     }
 #pragma unroll
@@ -379,7 +379,7 @@ struct GaussBwdArgs {
     const float *view, *proj, *campos;
     const int *radii;
     const uint8_t *clamped;
-    const float *gacc;
+    double *gacc; // read, and the records that were non-zero cleared again (dqo_rast_settings.geom_clean)
     float *dL_dmeans2D, *dL_dconic, *dL_dopacity, *dL_dcolors, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drot;
     // Fused mapping step only (nullptr otherwise): ever[i] != 0 once Gaussian i has received a non-zero gradient.  A
     // Gaussian that never has is a fixed point of Adam (zero gradient on zero moments), so its gradients are neither
@@ -419,11 +419,11 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
     const int M = a.M;
     float g[DQO_GACC_FLOATS];
     if (active) {
-        const float4 *gp = reinterpret_cast<const float4 *>(a.gacc + (size_t)idx * DQO_GACC_FLOATS);
+        const double2 *gp = reinterpret_cast<const double2 *>(a.gacc + (size_t)idx * DQO_GACC_FLOATS);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const float4 t = gp[k];
-            g[4 * k] = t.x; g[4 * k + 1] = t.y; g[4 * k + 2] = t.z; g[4 * k + 3] = t.w;
+        for (int k = 0; k < 8; k++) {
+            const double2 t = gp[k];
+            g[2 * k] = (float)t.x; g[2 * k + 1] = (float)t.y;
         }
     } else {
 #pragma unroll
@@ -436,6 +436,11 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
 #pragma unroll
     for (int k = 0; k < DQO_GACC_FLOATS; k++) nz |= (g[k] != 0.f);
     const bool need = active && nz;
+    if (need) { // leave the accumulator clean for the next backward pass
+        double2 *gz = reinterpret_cast<double2 *>(a.gacc + (size_t)idx * DQO_GACC_FLOATS);
+#pragma unroll
+        for (int k = 0; k < 8; k++) gz[k] = make_double2(0.0, 0.0);
+    }
     const unsigned need_rows = __ballot_sync(0xFFFFFFFFu, need);
     const bool whole_block = nrow == 32 && __popc(need_rows) >= 12; // dense: the warp's block in 12 coalesced 128-bit loads
     if (SHMODE == 2 && need_rows) {
@@ -804,6 +809,19 @@ int rast_backward_impl(const dqo_rast_settings *s, const float *background, cons
                        int32_t *ever_count, void *stream_);
 }
 
+extern "C" int dqo_rast_geom_init(int32_t P, void *geom_buffer, void *stream_) {
+    if (P < 0 || (P > 0 && !geom_buffer)) {
+        set_error("dqo_rast_geom_init: invalid argument");
+        return DQO_ERR_INVALID_ARG;
+    }
+    if (P == 0) return DQO_OK;
+    GeomLayout GL;
+    if (make_geom_layout(P, &GL)) return DQO_ERR_WORKSPACE;
+    DQO_CUDA_CHECK(cudaMemsetAsync((char *)geom_buffer + GL.gacc, 0, (size_t)P * DQO_GACC_FLOATS * sizeof(double),
+                                   (cudaStream_t)stream_));
+    return DQO_OK;
+}
+
 extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *background, const float *means3D,
                                  const float *shs, const float *colors_precomp, const float *scales,
                                  const float *rotations, const float *cov3D_precomp, const float *viewmatrix,
@@ -858,9 +876,9 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     char *geom = (char *)geom_buffer;
     const char *bin = (const char *)binning_buffer;
     const char *img = (const char *)image_buffer;
-    float *gacc = (float *)(geom + GL.gacc);
+    double *gacc = (double *)(geom + GL.gacc);
     stage_mark(stream, ST_BEGIN_BWD);
-    DQO_CUDA_CHECK(cudaMemsetAsync(gacc, 0, (size_t)P * DQO_GACC_FLOATS * sizeof(float), stream));
+    if (!s->geom_clean) DQO_CUDA_CHECK(cudaMemsetAsync(gacc, 0, (size_t)P * DQO_GACC_FLOATS * sizeof(double), stream));
 
     const float focal_y = s->H / (2.0f * s->tanfovy);
     const float focal_x = s->W / (2.0f * s->tanfovx);

@@ -47,7 +47,7 @@ int make_geom_layout(int P, GeomLayout *L) {
     L->offsets = bump(cur, n * 4);
     L->rect = bump(cur, n * 8);
     L->clamped = bump(cur, n);
-    L->gacc = bump(cur, n * DQO_GACC_FLOATS * 4);
+    L->gacc = bump(cur, n * DQO_GACC_FLOATS * 8);
     // look-back words + tickets of the two emission kernels (front / single phase, back phase): cleared together
     L->tiles_b = bump(cur, n * 4);
     L->emit_blocks = (int)((n + 255) / 256);
@@ -268,24 +268,21 @@ __device__ __forceinline__ uint32_t mask_row_count(const uint32_t *__restrict__ 
 // was a chain of dependent loads per Gaussian: 15 % of the preprocess).  Built by ONE block: row prefixes from the
 // bitmap words, then a running sum down every column.
 __device__ __forceinline__ void build_sat(int gx, int gy, int words, const uint32_t *bits, uint32_t *sat) {
+    // one thread per column x: running sum over the rows of "set bits of row y in columns [0, x)", read straight from
+    // the bitmap words (a few hundred bytes, cache-resident); the table is only ever written, never read back
     const int stride = gx + 1;
-    for (int x = threadIdx.x; x < stride; x += blockDim.x) sat[x] = 0;
-    for (int e = threadIdx.x; e < gy * stride; e += blockDim.x) {
-        const int y = e / stride, x = e - y * stride; // bits of row y in columns [0, x)
-        uint32_t c = 0;
-        for (int w = 0; w * 32 < x; w++) {
-            uint32_t m = bits[y * words + w];
-            if (x - w * 32 < 32) m &= (1u << (x - w * 32)) - 1u;
-            c += __popc(m);
-        }
-        sat[(y + 1) * stride + x] = c;
-    }
-    __syncthreads();
     for (int x = threadIdx.x; x < stride; x += blockDim.x) {
+        const int full = x >> 5;
+        const uint32_t part = (x & 31) ? ((1u << (x & 31)) - 1u) : 0u;
         uint32_t run = 0;
-        for (int y = 1; y <= gy; y++) {
-            run += sat[y * stride + x];
-            sat[y * stride + x] = run;
+        sat[x] = 0;
+        for (int y = 0; y < gy; y++) {
+            const uint32_t *row = bits + y * words;
+            uint32_t c = 0;
+            for (int w = 0; w < full; w++) c += __popc(row[w]);
+            if (part) c += __popc(row[full] & part);
+            run += c;
+            sat[(y + 1) * stride + x] = run;
         }
     }
 }
@@ -539,18 +536,43 @@ __global__ void __launch_bounds__(LC_THREADS) lazy_color_kernel(ColorArgs a) {
     const unsigned rows = __ballot_sync(0xFFFFFFFFu, need);
     if (!rows) return;
     float *wrow = s_rows[warp];
-    for (unsigned m = rows; m; m &= m - 1) {
-        const int k = __ffs(m) - 1;
-        const uint32_t gid = __shfl_sync(0xFFFFFFFFu, id, k);
-        if (SHMODE == 2) {
-            const float *src = a.f_rest + (size_t)gid * 45;
-            wrow[k * 49 + 3 + lane] = __ldg(src + lane);
-            if (lane < 13) wrow[k * 49 + 3 + 32 + lane] = __ldg(src + 32 + lane);
-            else if (lane < 16) wrow[k * 49 + (lane - 13)] = __ldg(a.shs + (size_t)gid * 3 + (lane - 13));
-        } else {
-            const float *src = a.shs + (size_t)gid * 48;
-            wrow[k * 49 + lane] = __ldg(src + lane);
-            if (lane < 16) wrow[k * 49 + 32 + lane] = __ldg(src + 32 + lane);
+    // four rows per trip: all their loads are issued before the first shared-memory store waits for one of them
+    for (unsigned m = rows; m;) {
+        int k[4];
+        uint32_t gid[4];
+        float v0[4], v1[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            k[q] = m ? (__ffs(m) - 1) : -1;
+            m &= m - 1;
+            gid[q] = __shfl_sync(0xFFFFFFFFu, id, k[q] < 0 ? 0 : k[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            v0[q] = v1[q] = 0.f;
+            if (k[q] < 0) continue;
+            if (SHMODE == 2) {
+                const float *src = a.f_rest + (size_t)gid[q] * 45;
+                v0[q] = __ldg(src + lane);
+                if (lane < 13) v1[q] = __ldg(src + 32 + lane);
+                else if (lane < 16) v1[q] = __ldg(a.shs + (size_t)gid[q] * 3 + (lane - 13));
+            } else {
+                const float *src = a.shs + (size_t)gid[q] * 48;
+                v0[q] = __ldg(src + lane);
+                if (lane < 16) v1[q] = __ldg(src + 32 + lane);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (k[q] < 0) continue;
+            if (SHMODE == 2) {
+                wrow[k[q] * 49 + 3 + lane] = v0[q];
+                if (lane < 13) wrow[k[q] * 49 + 3 + 32 + lane] = v1[q];
+                else if (lane < 16) wrow[k[q] * 49 + (lane - 13)] = v1[q];
+            } else {
+                wrow[k[q] * 49 + lane] = v0[q];
+                if (lane < 16) wrow[k[q] * 49 + 32 + lane] = v1[q];
+            }
         }
     }
     __syncwarp();
@@ -759,14 +781,16 @@ __global__ void __launch_bounds__(1024)
     const int row_words = (tiles_y + 31) / 32;
     for (int k = threadIdx.x; k < 64; k += blockDim.x) s_any[k] = 0;
     __syncthreads();
-    for (int w = threadIdx.x; w < tiles_y * mask_words; w += blockDim.x) {
-        const int y = w / mask_words, x0 = (w % mask_words) * 32;
-        uint32_t bits = 0;
-        for (int b = 0; b < 32 && x0 + b < tiles_x; b++)
-            if (unfinished[y * tiles_x + x0 + b]) bits |= 1u << b;
-        bits &= mask_bits[w];
-        mask_bits_b[w] = bits;
-        if (bits && (y >> 5) < 64) atomicOr(&s_any[y >> 5], 1u << (y & 31));
+    // one warp per bitmap word: 32 flags -> one ballot
+    const int lane = threadIdx.x & 31;
+    for (int w = threadIdx.x >> 5; w < tiles_y * mask_words; w += blockDim.x >> 5) {
+        const int y = w / mask_words, x = (w % mask_words) * 32 + lane;
+        const bool u = x < tiles_x && unfinished[y * tiles_x + x] != 0;
+        const uint32_t bits = __ballot_sync(0xFFFFFFFFu, u) & mask_bits[w];
+        if (lane == 0) {
+            mask_bits_b[w] = bits;
+            if (bits && (y >> 5) < 64) atomicOr(&s_any[y >> 5], 1u << (y & 31));
+        }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < row_words; k += blockDim.x) row_any[k] = (k < 64) ? s_any[k] : 0xFFFFFFFFu;
@@ -1387,7 +1411,7 @@ int rast_forward_impl(const dqo_rast_settings *s, const float *background, const
                       void *binning_buffer, int64_t capacity, void *image_buffer, int32_t *tile_indices, float *out_color,
                       float *out_depth, int32_t *out_hit_depth, int32_t *out_hit_color, float *out_hit_color_weight,
                       float *out_hit_depth_weight, float *out_T, int32_t *radii, int32_t *n_touched, int32_t *status,
-                      void *stream_);
+                      void *stream_, void (*pre_hook)(void *, void *), void *hook_ctx);
 }
 
 extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *background, const float *means3D,
@@ -1402,7 +1426,8 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
     return rast_forward_impl(s, background, means3D, shs, nullptr, colors_precomp, opacities, scales, rotations,
                              cov3D_precomp, viewmatrix, projmatrix, campos, tile_mask, geom_buffer, binning_buffer,
                              capacity, image_buffer, tile_indices, out_color, out_depth, out_hit_depth, out_hit_color,
-                             out_hit_color_weight, out_hit_depth_weight, out_T, radii, n_touched, status, stream_);
+                             out_hit_color_weight, out_hit_depth_weight, out_T, radii, n_touched, status, stream_, nullptr,
+                             nullptr);
 }
 
 int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, const float *means3D,
@@ -1413,7 +1438,8 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
                                 int64_t capacity, void *image_buffer, int32_t *tile_indices, float *out_color,
                                 float *out_depth, int32_t *out_hit_depth, int32_t *out_hit_color,
                                 float *out_hit_color_weight, float *out_hit_depth_weight, float *out_T, int32_t *radii,
-                                int32_t *n_touched, int32_t *status, void *stream_) {
+                                int32_t *n_touched, int32_t *status, void *stream_, void (*pre_hook)(void *, void *),
+                                void *hook_ctx) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!s || s->P < 0 || s->W <= 0 || s->H <= 0 || !status) {
         set_error("dqo_rast_forward: invalid settings");
@@ -1517,6 +1543,9 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
             if (rc) return rc;
             if (debug) DQO_CUDA_CHECK(cudaStreamSynchronize(sort_stream));
         }
+        // work of the caller that only has to precede the preprocess (the fused step's activation kernel): enqueued
+        // behind the fork so that the sort chain, which only needs the positions, starts first
+        if (pre_hook) pre_hook(hook_ctx, stream_);
         {
             const int nw = IL.tiles_y * IL.mask_words;
             launch_pdl(mask_bits_kernel, dim3((nw + 7) / 8), dim3(256), 0, stream, IL.tiles_x, IL.tiles_y, IL.mask_words, tile_mask, mask_bits);

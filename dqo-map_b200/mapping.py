@@ -282,6 +282,10 @@ class FusedMappingStep:
         if n == 0:
             raise _lib.DqoError("workspace size query failed: %s" % lib().dqo_last_error().decode())
         self.ws = torch.empty((n,), dtype=torch.uint8, device=self.dev)
+        # persistent workspace: gradient accumulators cleared once, kept clean by every step (settings.geom_clean)
+        with torch.cuda.device(self.dev):
+            check(lib().dqo_mapping_step_workspace_init(self.P, self.M, self.W, self.H, self.capacity, ptr(self.ws), _stream()),
+                  "dqo_mapping_step_workspace_init")
 
     def _keyframe(self, rs, tile_mask, gt_color, gt_depth, render_mask):
         from .rasterizer import _make_settings
@@ -307,7 +311,7 @@ class FusedMappingStep:
             s = _make_settings(self.P, int(rs.sh_degree), self.M, self.W, self.H, rs.tanfovx, rs.tanfovy, rs.cx, rs.cy,
                                rs.scale_modifier, rs.color_sigma, rs.opaque_threshold, rs.depth_threshold,
                                rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, self.need_n_touched,
-                               self.front, self.back)
+                               self.front, self.back, geom_clean=True)
             if len(self._kf_cache) >= 256:
                 self._kf_cache.clear()
             hit = self._kf_cache[key] = (s, kf, tensors)

@@ -79,10 +79,10 @@ def _f32c(t):
 
 def _make_settings(P, D, M, W, H, tanfovx, tanfovy, cx, cy, scale_modifier, color_sigma, opaque_threshold,
                    depth_threshold, normal_threshold, T_threshold, prefiltered, debug, need_n_touched=True,
-                   front_instances=0, back_instances=0):
+                   front_instances=0, back_instances=0, geom_clean=False):
     return RastSettings(P, D, M, W, H, tanfovx, tanfovy, cx, cy, scale_modifier, color_sigma, opaque_threshold,
                         depth_threshold, normal_threshold, T_threshold, int(bool(prefiltered)), int(bool(debug)),
-                        int(bool(need_n_touched)), int(front_instances), int(back_instances))
+                        int(bool(need_n_touched)), int(front_instances), int(back_instances), int(bool(geom_clean)))
 
 
 class ForwardState:
@@ -227,6 +227,9 @@ class RasterPipeline:
         self.radii, self.n_touched = torch.empty((P,), **i32), torch.empty((P,), **i32)
         self.tile_indices, self.status = torch.empty((tiles,), **i32), torch.zeros((_lib.ST_WORDS,), **i32)
         self.geom = torch.empty((L.dqo_rast_geom_bytes(P),), **u8)
+        # persistent workspace: the gradient accumulators are cleared once here and kept clean by every backward pass
+        with torch.cuda.device(device):
+            check(L.dqo_rast_geom_init(P, ptr(self.geom), _stream()), "dqo_rast_geom_init")
         self.binning = torch.empty((L.dqo_rast_binning_bytes(self.capacity),), **u8)
         self.image = torch.empty((L.dqo_rast_image_bytes(W, H),), **u8)
         self.g_means2D, self.g_conic = torch.empty((P, 3), **f32), torch.empty((P, 4), **f32)
@@ -241,7 +244,7 @@ class RasterPipeline:
         self.settings = _make_settings(self.P, int(rs.sh_degree), self.M, self.W, self.H, rs.tanfovx, rs.tanfovy, rs.cx,
                                        rs.cy, rs.scale_modifier, rs.color_sigma, rs.opaque_threshold, rs.depth_threshold,
                                        rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, need_n_touched,
-                                       self.front, self.back)
+                                       self.front, self.back, geom_clean=True)
         self._in = (rs, means3D, shs, colors_precomp, scales, rotations)
         check(lib().dqo_rast_forward(
             self.settings, ptr(rs.bg), ptr(means3D), ptr(shs), ptr(colors_precomp), ptr(opacities), ptr(scales),

@@ -68,6 +68,11 @@ typedef struct dqo_rast_settings {
      * back phase needs more than back_instances.  The same values must be passed to the backward pass. */
     int32_t front_instances;
     int32_t back_instances;
+    /* 1: the caller guarantees that `geom_buffer` was initialised once with dqo_rast_geom_init() after its allocation and
+     * has since been written by this library only.  The backward pass leaves the per-Gaussian gradient accumulators
+     * inside it zeroed (it clears exactly the records it consumed), so with this promise it skips clearing all
+     * 128 B x P of them at its start.  0 (default): the accumulators are cleared on every backward call. */
+    int32_t geom_clean;
 } dqo_rast_settings;
 
 /* status words written on the device by the forward pass (int32[8]) */
@@ -84,6 +89,8 @@ typedef struct dqo_rast_settings {
 /* Workspace sizing (replaces the three resize callbacks of CudaRasterizer::Rasterizer::forward,
  * RAST/cuda_rasterizer/rasterizer.h:31-33 and rasterizer_impl.h:68-74 `required<T>`). */
 size_t dqo_rast_geom_bytes(int32_t P);
+/* One-time initialisation of a freshly allocated geometry buffer (see dqo_rast_settings.geom_clean). */
+int dqo_rast_geom_init(int32_t P, void *geom_buffer, void *stream);
 size_t dqo_rast_binning_bytes(int64_t instance_capacity);
 size_t dqo_rast_image_bytes(int32_t W, int32_t H);
 
@@ -382,6 +389,9 @@ typedef struct dqo_keyframe {
     float color_weight, depth_weight, depth_err_thres;
 } dqo_keyframe;
 size_t dqo_mapping_step_workspace_bytes(int32_t P, int32_t M, int32_t W, int32_t H, int64_t instance_capacity);
+/* One-time initialisation of a freshly allocated step workspace: lets the step run with dqo_rast_settings.geom_clean = 1. */
+int dqo_mapping_step_workspace_init(int32_t P, int32_t M, int32_t W, int32_t H, int64_t instance_capacity, void *workspace,
+                                    void *stream);
 /* loss_out: device float[4] {total, colour, depth, attach}; counts_out: device int32[2]; status: device int32[DQO_ST_WORDS]
  * (check DQO_ST_OVERFLOW together with the loss read-back; on overflow the render is invalid and the Adam update is
  * skipped on the device -- parameters and moments are untouched, repeat the step with a larger capacity and the same

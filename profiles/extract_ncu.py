@@ -11,6 +11,7 @@ STAGE_OF = {  # kernel-name substring -> bench.py stage key
     "preprocess_kernel": "preprocess", "emit_kernel": "emit", "rank_sums_kernel": "emit", "render_forward_kernel": "render_fwd",
     "render_backward_kernel": "render_bwd", "gaussian_backward_kernel": "gaussian_bwd", "tile_ranges_kernel": "ranges",
     "adam_geometry_kernel": "adam_geometry", "adam_flat_kernel": "adam_flat", "adam_rest_kernel": "adam_rest",
+    "adam_list_kernel": "adam_list", "adam_rest_list_kernel": "adam_rest_list", "lazy_color_kernel": "lazy_color",
     "radix_": "sorts",
 }
 WANT = [
@@ -34,7 +35,10 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us"
 
 def main():
     rep, out_txt, config = sys.argv[1], sys.argv[2], sys.argv[3]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):  # already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv`): reports of a whole
+        raw = open(rep).read()  # step exceed what gpurun copies back
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     head, units, body = rows[0], rows[1], rows[2:]
 

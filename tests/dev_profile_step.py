@@ -30,4 +30,12 @@ fstep.begin_window(attach=True)
 for _ in range(iters):
     t = fstep(rs, inp["tile_mask"], gt_color, gt_depth, mask)
 torch.cuda.synchronize()
+if iters >= 20:  # device time of the fused step alone (keyframe resident, no read-back): CUDA events over the next `iters` steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        t = fstep(rs, inp["tile_mask"], gt_color, gt_depth, mask)
+    e1.record()
+    torch.cuda.synchronize()
+    print("fused step %.4f ms" % (e0.elapsed_time(e1) / iters))
 print(float(t[0]), fstep.check())

@@ -34,7 +34,7 @@ def test_library_exports_every_symbol():
 
 
 def test_struct_layouts():
-    assert ctypes.sizeof(_lib.RastSettings) == 20 * 4
+    assert ctypes.sizeof(_lib.RastSettings) == 21 * 4
     assert ctypes.sizeof(_lib.AdamTensor) == 4 * 8 + 8 + 8 + 4 + 4
 
 
