@@ -578,3 +578,20 @@ def test_gradients_against_float64_arbiter(cfg, mask, precomp):
         assert err <= gate, (name, err / nrm, gate / nrm)
         checked += 1
     assert checked == 5
+
+
+@pytest.mark.parametrize("cfg,binning", [("small", ("single",)), ("c1", ("single",)), ("c2", ("fixed", 2_000_128, 4_000_000))])
+def test_backward_is_reproducible_run_to_run(cfg, binning):
+    """The backward blend adds each warp's fp32 partial sums into fp64 accumulators (common.cuh: DQO_GACC_FLOATS), so the
+    order in which warps and tiles arrive does not show in the result: repeated runs return bit-identical gradients (the
+    reference's float atomics make its own runs differ by up to 1e-3 in dL_drotations, profiles/r01_gradient_parity_*)."""
+    inp = rh.make_inputs(cfg, torch.device(DEV))
+    cam = inp["cam"]
+    gc, gd = rh.make_pixel_grads(cam.image_height, cam.image_width, DEV)
+    o, _, bw = _run_ours(inp, gc, gd, binning=binning)
+    first = [t.clone() for t in bw]
+    for _ in range(3):
+        again = rasterizer.rasterize_gaussians_backward(*rh.backward_args(inp, o, gc, gd))
+        for name, a, b in zip(GRADS, first, again):
+            assert torch.equal(a, b), name
+    rasterizer.set_binning_mode("single")
