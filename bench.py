@@ -702,7 +702,7 @@ def make_roofline(a, stats, cfg_stats, stage_ms, M, tiles, two_phase, front, hos
         "tile_sort": n_front * D_t * (2 + 2 * 6),                  # per pass: keys (count), pairs in, pairs out
         "ranges": n_front * 2 + tiles * 8,
         "render_fwd": 52 * Rt + (40 + 32) * Npx,
-        "render_bwd": 52 * Rt_bwd + 72 * Npx + 36 * Rt_bwd,        # staged entries only: what the kernel visits
+        "render_bwd": 52 * Rt_bwd + 72 * Npx + 72 * Rt_bwd,        # staged entries only; 9 fp64 atomics per warp and entry
         "gaussian_bwd": V * (100 + 12 * M) + P * (76 + 12 * M),
     }
     if two_phase:

@@ -8,6 +8,8 @@ mark_visible :251-270), implemented over the C-ABI of include/dqo_b200.h.  PyTor
 """
 from typing import NamedTuple
 
+import copy
+
 import torch
 import torch.nn as nn
 
@@ -134,8 +136,24 @@ def _forward_impl(background, means3D, colors, opacity, scales, rotations, scale
     st.image = torch.empty((L.dqo_rast_image_bytes(W, H),), dtype=torch.uint8, device=dev)
     st.tile_indices, st.status = tile_indices, status
     st.geom = torch.empty((L.dqo_rast_geom_bytes(P) if P > 0 else 0,), dtype=torch.uint8, device=dev)
-    key = (dev.index, )
-    policy = _policy.setdefault(key, BinningPolicy()) if (BINNING == "auto" and sync) else None
+    # Host-side state is keyed by what determines the workload, not by the device alone: the instance capacity by
+    # (device, image size, cloud size), the binning policy additionally by the view (the camera tensors of a keyframe
+    # persist, so their address identifies it) -- alternating keyframes with different R keep their own front / back split
+    # instead of thrashing one policy.  Both tables are bounded.
+    key = (dev.index, W, H, P)
+    pkey = key + (viewmatrix.data_ptr(),)
+    if len(_policy) > 512:
+        _policy.clear()
+    if len(_capacity_hint) > 512:
+        _capacity_hint.clear()
+    policy = None
+    if BINNING == "auto" and sync:
+        policy = _policy.get(pkey)
+        if policy is None:  # a view seen for the first time starts from what the last view of the same workload learned
+            last = _policy.get(key)
+            policy = _policy[pkey] = copy.copy(last) if last is not None else BinningPolicy()
+            policy.history = list(policy.history)
+        _policy[key] = policy
     capacity = max(_capacity_hint.get(key, 0), 4 * P, 1 << 16) if P > 0 else 0
     while True:
         front, back = policy.plan(1 << 30) if (policy is not None and P > 0) else (0, 0)

@@ -502,8 +502,11 @@ def test_mapping_loop_config2_size_against_reference_loop():
             res.append((psnr(out[0], gt_color), float((out[1] - gt_depth).abs()[hit].mean())))
         return res
 
-    def run_fused():
+    def run_fused(run):
         fparams = {k: t.contiguous() for k, t in bench.raw_params(inp).items()}
+        if run:  # the fused step is reproducible run to run (fp64 gradient accumulators): independent samples of the
+            g = torch.Generator(device="cpu").manual_seed(run)  # chaotic loop come from a 1e-7 nudge of the positions
+            fparams["xyz"] *= 1.0 + 1e-7 * torch.randn(fparams["xyz"].shape, generator=g).to(dev)
         st = mapping.FusedMappingStep(fparams, bench.LRS, W, H, 0.8, 1.0, 0.1, confidence=torch.zeros(P, 1, device=dev),
                                       capacity=int(R * 1.3) + 4096)
         st.begin_window(attach=True)
@@ -532,11 +535,10 @@ def test_mapping_loop_config2_size_against_reference_loop():
 
     start = quality(bench.raw_params(inp))
     n_runs = 4
-    f = [run_fused() for _ in range(n_runs)]
+    f = [run_fused(i) for i in range(n_runs)]
     r = [run_reference() for _ in range(n_runs)]
-    for i in range(5):  # the deterministic regime
-        for a in f:
-            assert abs(a[1][i] - r[0][1][i]) <= 1e-4 * abs(r[0][1][i]), ("loss", i, a[1], r[0][1])
+    for i in range(5):  # the deterministic regime (run 0 starts from exactly the reference's parameters)
+        assert abs(f[0][1][i] - r[0][1][i]) <= 1e-4 * abs(r[0][1][i]), ("loss", i, f[0][1], r[0][1])
     # end of the loop: window means per run; difference of the sample means against its standard error (each side's
     # run-to-run sigma estimated from its own runs, floored at the 0.15 dB / 1 % seen in the log above)
     pf, pr = [np.mean([q[0] for q in a[0]]) for a in f], [np.mean([q[0] for q in a[0]]) for a in r]
