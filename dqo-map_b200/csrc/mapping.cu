@@ -33,25 +33,87 @@ __device__ __forceinline__ bool depth_valid(const LossArgs &a, size_t p, bool m,
     return m && a.hit[p] != -1 && g > 0.f && e < a.depth_thr;
 }
 
-__global__ void __launch_bounds__(LOSS_THREADS) loss_partial_kernel(LossArgs a) {
+// Four consecutive pixels of every per-pixel array in 128-bit loads (the images are H*W-contiguous planes; gt_color is
+// [H,W,3], so four pixels are three float4).  `vec` is decided on the host: every base pointer 16-byte aligned and
+// N % 4 == 0 (true for the 16-pixel-aligned images of the benchmarks); otherwise the scalar path runs.
+struct LossPix4 {
+    float img[3][4], gt[3][4], d[4], g[4];
+    int hit[4];
+    bool m[4];
+};
+__device__ __forceinline__ void load_pix4(const LossArgs &a, size_t N, size_t q, bool need_depth, LossPix4 &x) {
+    const float4 i0 = reinterpret_cast<const float4 *>(a.image)[q];
+    const float4 i1 = reinterpret_cast<const float4 *>(a.image + N)[q];
+    const float4 i2 = reinterpret_cast<const float4 *>(a.image + 2 * N)[q];
+    const float4 g0 = reinterpret_cast<const float4 *>(a.gt_color)[3 * q];
+    const float4 g1 = reinterpret_cast<const float4 *>(a.gt_color)[3 * q + 1];
+    const float4 g2 = reinterpret_cast<const float4 *>(a.gt_color)[3 * q + 2];
+    const float iv[3][4] = {{i0.x, i0.y, i0.z, i0.w}, {i1.x, i1.y, i1.z, i1.w}, {i2.x, i2.y, i2.z, i2.w}};
+    const float gf[12] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w};
+    uchar4 mk = make_uchar4(1, 1, 1, 1);
+    if (a.mask) mk = reinterpret_cast<const uchar4 *>(a.mask)[q];
+    const uint8_t mv[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        x.m[k] = mv[k] != 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            x.img[c][k] = iv[c][k];
+            x.gt[c][k] = gf[3 * k + c];
+        }
+    }
+    if (need_depth) {
+        const float4 d = reinterpret_cast<const float4 *>(a.depth)[q];
+        const float4 g = reinterpret_cast<const float4 *>(a.gt_depth)[q];
+        const int4 h = reinterpret_cast<const int4 *>(a.hit)[q];
+        x.d[0] = d.x; x.d[1] = d.y; x.d[2] = d.z; x.d[3] = d.w;
+        x.g[0] = g.x; x.g[1] = g.y; x.g[2] = g.z; x.g[3] = g.w;
+        x.hit[0] = h.x; x.hit[1] = h.y; x.hit[2] = h.z; x.hit[3] = h.w;
+    }
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS) loss_partial_kernel(LossArgs a, int vec) {
     pdl_enter();
     const size_t N = (size_t)a.W * a.H;
     double cs = 0.0, ds = 0.0;
     double cn = 0.0, dn = 0.0;
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (size_t)gridDim.x * blockDim.x) {
-        const bool m = a.mask ? (a.mask[p] != 0) : true;
-        if (m) {
-            const float e0 = a.image[p] - a.gt_color[3 * p];
-            const float e1 = a.image[N + p] - a.gt_color[3 * p + 1];
-            const float e2 = a.image[2 * N + p] - a.gt_color[3 * p + 2];
-            cs += (double)(fabsf(e0) + fabsf(e1) + fabsf(e2));
-            cn += 1.0;
+    if (vec) {
+        const bool need_depth = a.depth_w > 0.f;
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N / 4; q += (size_t)gridDim.x * blockDim.x) {
+            LossPix4 x;
+            load_pix4(a, N, q, need_depth, x);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (x.m[k]) {
+                    cs += (double)(fabsf(x.img[0][k] - x.gt[0][k]) + fabsf(x.img[1][k] - x.gt[1][k]) +
+                                   fabsf(x.img[2][k] - x.gt[2][k]));
+                    cn += 1.0;
+                }
+                if (need_depth) {
+                    const float e = x.d[k] - x.g[k];
+                    if (x.m[k] && x.hit[k] != -1 && x.g[k] > 0.f && e < a.depth_thr) {
+                        ds += (double)fabsf(e);
+                        dn += 1.0;
+                    }
+                }
+            }
         }
-        if (a.depth_w > 0.f) {
-            float e;
-            if (depth_valid(a, p, m, &e)) {
-                ds += (double)fabsf(e);
-                dn += 1.0;
+    } else {
+        for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (size_t)gridDim.x * blockDim.x) {
+            const bool m = a.mask ? (a.mask[p] != 0) : true;
+            if (m) {
+                const float e0 = a.image[p] - a.gt_color[3 * p];
+                const float e1 = a.image[N + p] - a.gt_color[3 * p + 1];
+                const float e2 = a.image[2 * N + p] - a.gt_color[3 * p + 2];
+                cs += (double)(fabsf(e0) + fabsf(e1) + fabsf(e2));
+                cn += 1.0;
+            }
+            if (a.depth_w > 0.f) {
+                float e;
+                if (depth_valid(a, p, m, &e)) {
+                    ds += (double)fabsf(e);
+                    dn += 1.0;
+                }
             }
         }
     }
@@ -72,7 +134,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_partial_kernel(LossArgs a) 
     }
 }
 
-__global__ void __launch_bounds__(LOSS_THREADS) loss_grad_kernel(LossArgs a, int nparts) {
+__device__ __forceinline__ float sgn_scaled(float e, float g) { return (e > 0.f) ? g : ((e < 0.f) ? -g : 0.f); }
+
+__global__ void __launch_bounds__(LOSS_THREADS) loss_grad_kernel(LossArgs a, int nparts, int vec) {
     pdl_enter();
     __shared__ double tot[4];
     { // fixed-pattern (deterministic) final reduction, redundantly per block: warp q sums quantity q
@@ -99,20 +163,40 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_grad_kernel(LossArgs a, int
     const float gc = (cn > 0.0) ? (float)((double)a.color_w / (3.0 * cn)) : 0.f;
     const float gd = (a.depth_w > 0.f && dn > 0.0) ? (float)((double)a.depth_w / dn) : 0.f;
     const size_t N = (size_t)a.W * a.H;
+    if (vec) {
+        const bool need_depth = a.depth_w > 0.f;
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N / 4; q += (size_t)gridDim.x * blockDim.x) {
+            LossPix4 x;
+            load_pix4(a, N, q, need_depth, x);
+            float g[3][4], gdp[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) g[c][k] = x.m[k] ? sgn_scaled(x.img[c][k] - x.gt[c][k], gc) : 0.f;
+                gdp[k] = 0.f;
+                if (need_depth) {
+                    const float e = x.d[k] - x.g[k];
+                    if (x.m[k] && x.hit[k] != -1 && x.g[k] > 0.f && e < a.depth_thr) gdp[k] = sgn_scaled(e, gd);
+                }
+            }
+            reinterpret_cast<float4 *>(a.dimg)[q] = make_float4(g[0][0], g[0][1], g[0][2], g[0][3]);
+            reinterpret_cast<float4 *>(a.dimg + N)[q] = make_float4(g[1][0], g[1][1], g[1][2], g[1][3]);
+            reinterpret_cast<float4 *>(a.dimg + 2 * N)[q] = make_float4(g[2][0], g[2][1], g[2][2], g[2][3]);
+            reinterpret_cast<float4 *>(a.ddepth)[q] = make_float4(gdp[0], gdp[1], gdp[2], gdp[3]);
+        }
+        return;
+    }
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (size_t)gridDim.x * blockDim.x) {
         const bool m = a.mask ? (a.mask[p] != 0) : true;
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, gdp = 0.f;
         if (m) {
-            const float e0 = a.image[p] - a.gt_color[3 * p];
-            const float e1 = a.image[N + p] - a.gt_color[3 * p + 1];
-            const float e2 = a.image[2 * N + p] - a.gt_color[3 * p + 2];
-            g0 = (e0 > 0.f) ? gc : ((e0 < 0.f) ? -gc : 0.f);
-            g1 = (e1 > 0.f) ? gc : ((e1 < 0.f) ? -gc : 0.f);
-            g2 = (e2 > 0.f) ? gc : ((e2 < 0.f) ? -gc : 0.f);
+            g0 = sgn_scaled(a.image[p] - a.gt_color[3 * p], gc);
+            g1 = sgn_scaled(a.image[N + p] - a.gt_color[3 * p + 1], gc);
+            g2 = sgn_scaled(a.image[2 * N + p] - a.gt_color[3 * p + 2], gc);
         }
         if (a.depth_w > 0.f) {
             float e;
-            if (depth_valid(a, p, m, &e)) gdp = (e > 0.f) ? gd : ((e < 0.f) ? -gd : 0.f);
+            if (depth_valid(a, p, m, &e)) gdp = sgn_scaled(e, gd);
         }
         a.dimg[p] = g0;
         a.dimg[N + p] = g1;
@@ -280,8 +364,19 @@ extern "C" int dqo_masked_l1_loss(int32_t W, int32_t H, const float *image, cons
     const size_t N = (size_t)W * H;
     int blocks = (int)((N + LOSS_THREADS - 1) / LOSS_THREADS);
     if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
-    launch_pdl(loss_partial_kernel, dim3(blocks), dim3(LOSS_THREADS), 0, stream, a);
-    launch_pdl(loss_grad_kernel, dim3(blocks), dim3(LOSS_THREADS), 0, stream, a, blocks);
+    // 128-bit path: every array 16-byte aligned and a whole number of 4-pixel groups
+    int vec = (N % 4 == 0);
+    for (const void *q : {(const void *)image, (const void *)depth, (const void *)hit_depth, (const void *)gt_color,
+                          (const void *)gt_depth, (const void *)dL_dimage, (const void *)dL_ddepth})
+        vec &= ((uintptr_t)q % 16 == 0);
+    vec &= ((uintptr_t)render_mask % 4 == 0) && ((N * sizeof(float)) % 16 == 0);
+    if (vec) {
+        blocks = (int)((N / 4 + LOSS_THREADS - 1) / LOSS_THREADS);
+        if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
+        if (blocks < 1) blocks = 1;
+    }
+    launch_pdl(loss_partial_kernel, dim3(blocks), dim3(LOSS_THREADS), 0, stream, a, vec);
+    launch_pdl(loss_grad_kernel, dim3(blocks), dim3(LOSS_THREADS), 0, stream, a, blocks, vec);
     DQO_LAUNCH_CHECK("masked l1 loss", 0, stream);
     return DQO_OK;
 }

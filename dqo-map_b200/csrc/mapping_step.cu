@@ -199,24 +199,26 @@ __device__ __forceinline__ void block_add(float v, float *out) { // sum over the
         if (t != 0.f) atomicAdd(out, t);
     }
 }
-// all 14 geometric parameters of Gaussian i; returns its share of the attach value
-__device__ __forceinline__ float adam_gaussian(const SmallArgs &a, const AdamScalars &k, int i) {
+// One parameter group (role) of Gaussian i: 0 xyz, 1 opacity, 2 scaling, 3 rotation, 4 f_dc (+ confidence bump);
+// returns its share of the attach value
+__device__ __forceinline__ float adam_role(const SmallArgs &a, const AdamScalars &k, int i, int role) {
     float att = 0.f;
-    const bool anch = a.init_opacity && anchored(a.init_opacity, i, k.attach_logit_thr);
+    const bool anch = (role == 0 || role == 2 || role == 3) && a.init_opacity && anchored(a.init_opacity, i, k.attach_logit_thr);
+    if (role == 0) {
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        const int e = 3 * i + c;
-        float p = a.xyz[e], m = a.m_xyz[e], v = a.v_xyz[e];
-        float g = a.g_means3D[e];
-        if (anch) {
-            const float d = p - a.init_xyz[e];
-            g += k.attach_grad[0] * d;
-            att += k.attach_val[0] * d * d;
+        for (int c = 0; c < 3; c++) {
+            const int e = 3 * i + c;
+            float p = a.xyz[e], m = a.m_xyz[e], v = a.v_xyz[e];
+            float g = a.g_means3D[e];
+            if (anch) {
+                const float d = p - a.init_xyz[e];
+                g += k.attach_grad[0] * d;
+                att += k.attach_val[0] * d * d;
+            }
+            adam_update(p, g, m, v, k, k.step_size[0]);
+            a.xyz[e] = p; a.m_xyz[e] = m; a.v_xyz[e] = v;
         }
-        adam_update(p, g, m, v, k, k.step_size[0]);
-        a.xyz[e] = p; a.m_xyz[e] = m; a.v_xyz[e] = v;
-    }
-    { // opacity: o = sigmoid(x), dL/dx = g * o * (1 - o)
+    } else if (role == 1) { // opacity: o = sigmoid(x), dL/dx = g * o * (1 - o)
         const float o = a.act_opacity[i];
         const float g = a.g_opacity[i] * (o * (1.0f - o));
         float p = a.opacity[i], m = a.m_op[i], v = a.v_op[i];
@@ -224,21 +226,21 @@ __device__ __forceinline__ float adam_gaussian(const SmallArgs &a, const AdamSca
             adam_update(p, g, m, v, k, k.step_size[3]);
             a.opacity[i] = p; a.m_op[i] = m; a.v_op[i] = v;
         }
-    }
+    } else if (role == 2) {
 #pragma unroll
-    for (int c = 0; c < 3; c++) { // scale: s = exp(x), dL/dx = g * s
-        const int e = 3 * i + c;
-        float g = a.g_scales[e] * a.act_scales[e];
-        float p = a.scaling[e], m = a.m_sc[e], v = a.v_sc[e];
-        if (anch) {
-            const float d = p - a.init_scaling[e];
-            g += k.attach_grad[1] * d;
-            att += k.attach_val[1] * d * d;
+        for (int c = 0; c < 3; c++) { // scale: s = exp(x), dL/dx = g * s
+            const int e = 3 * i + c;
+            float g = a.g_scales[e] * a.act_scales[e];
+            float p = a.scaling[e], m = a.m_sc[e], v = a.v_sc[e];
+            if (anch) {
+                const float d = p - a.init_scaling[e];
+                g += k.attach_grad[1] * d;
+                att += k.attach_val[1] * d * d;
+            }
+            adam_update(p, g, m, v, k, k.step_size[4]);
+            a.scaling[e] = p; a.m_sc[e] = m; a.v_sc[e] = v;
         }
-        adam_update(p, g, m, v, k, k.step_size[4]);
-        a.scaling[e] = p; a.m_sc[e] = m; a.v_sc[e] = v;
-    }
-    { // rotation: q = r / max(|r|, eps); dL/dr = (g - q (q . g)) / max(|r|, eps)
+    } else if (role == 3) { // rotation: q = r / max(|r|, eps); dL/dr = (g - q (q . g)) / max(|r|, eps)
         float4 r = reinterpret_cast<float4 *>(a.rotation)[i];
         const float4 g = reinterpret_cast<const float4 *>(a.g_rot)[i];
         const float nrm = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
@@ -264,8 +266,7 @@ __device__ __forceinline__ float adam_gaussian(const SmallArgs &a, const AdamSca
         reinterpret_cast<float4 *>(a.rotation)[i] = make_float4(pr[0], pr[1], pr[2], pr[3]);
         reinterpret_cast<float4 *>(a.m_rot)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
         reinterpret_cast<float4 *>(a.v_rot)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-    }
-    { // f_dc: gradient = first coefficient of the merged SH gradient
+    } else { // f_dc: gradient = first coefficient of the merged SH gradient
         const float *gs = a.g_sh + (size_t)i * a.M * 3;
         const float g3[3] = {gs[0], gs[1], gs[2]};
 #pragma unroll
@@ -277,6 +278,13 @@ __device__ __forceinline__ float adam_gaussian(const SmallArgs &a, const AdamSca
         }
         if (a.confidence && (fabsf(g3[0]) != 0.f || fabsf(g3[1]) != 0.f || fabsf(g3[2]) != 0.f)) a.confidence[i] += 1.0f;
     }
+    return att;
+}
+// all 14 geometric parameters of Gaussian i
+__device__ __forceinline__ float adam_gaussian(const SmallArgs &a, const AdamScalars &k, int i) {
+    float att = 0.f;
+#pragma unroll
+    for (int role = 0; role < 5; role++) att += adam_role(a, k, i, role);
     return att;
 }
 // one thread per Gaussian over the whole cloud (unaligned tensors, or no `ever` bookkeeping)
@@ -305,8 +313,13 @@ __global__ void __launch_bounds__(256) adam_list_kernel(ListArgs a) {
     if (k.skip) return;
     const int n = *a.count;
     float att = 0.f;
-    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x)
-        att += adam_gaussian(a.s, k, (int)a.list[l]);
+    // one work item per (parameter group, listed Gaussian), group-major: a warp works on one group of 32 consecutive list
+    // entries, five times the loads in flight of a thread-per-Gaussian loop and no load queued behind another group's stores
+    const long long items = 5ll * n;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (long long)gridDim.x * blockDim.x) {
+        const int role = (int)(w / n), l = (int)(w - (long long)role * n);
+        att += adam_role(a.s, k, (int)a.list[l], role);
+    }
     if (a.s.init_opacity) block_add(att, a.s.attach_out);
 }
 // f_rest [P,45] of the listed Gaussians: consecutive threads walk the 45 coefficients of one Gaussian (180-byte runs);
@@ -726,7 +739,7 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
         ListArgs la;
         la.s = sa; la.list = p->ever_list; la.count = p->ever_count;
         la.f_rest = f_rest; la.m_rest = p->exp_avg[2]; la.v_rest = p->exp_avg_sq[2];
-        const int blocks = nb < 148 * 8 ? nb : 148 * 8;
+        const int blocks = 148 * 8;
         launch_pdl(adam_list_kernel, dim3(blocks), dim3(256), 0, stream, la);
         if (M == 16) launch_pdl(adam_rest_list_kernel, dim3(148 * 8), dim3(256), 0, stream, la);
         DQO_LAUNCH_CHECK("adam (listed Gaussians)", s->debug, stream);
