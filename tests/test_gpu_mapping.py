@@ -552,3 +552,46 @@ def test_mapping_loop_config2_size_against_reference_loop():
     # confidence (mapper.py:909-910): the counters of the two loops agree for all but a sliver of the cloud
     diff = (f[0][2] - r[0][2]).abs()
     assert float((diff > 2).float().mean()) <= 0.03 and float(diff.median()) == 0.0   # observed: 1.2 % after 200 iterations
+
+
+def test_fused_step_graph_replay_is_bit_identical_at_config2_size():
+    """1 M Gaussians, two-phase binning, programmatic dependent launches active (>= 500 k Gaussians), side-stream forks:
+    sixteen iterations with the step replayed from a CUDA graph from the fifth on give exactly the losses and positions of
+    sixteen eager calls (the step is reproducible: fp64 gradient accumulators, deterministic loss reduction)."""
+    import bench
+    dev = torch.device(DEV)
+    inp, views = bench.make_views("c2", dev, 0, 1)
+    v = views[0]
+    cam = v["cam"]
+    P, H, W = inp["xyz"].shape[0], cam.image_height, cam.image_width
+    rs = v["settings"](rasterizer.GaussianRasterizationSettings)
+    kf = bench.make_keyframe(inp, v["settings"], rasterizer)
+    R, front, back = rasterizer.plan_binning(rs, inp["xyz"], inp["opacity"], inp["scales"], inp["rotations"],
+                                             inp["tile_mask"], shs=inp["shs"])
+    assert front > 0, "config 2 is expected to run with two-phase binning"
+    back = max(back * 2, 1 << 19)
+
+    def run(use_graph, iters=16):
+        params = {k: t.contiguous() for k, t in bench.raw_params(inp).items()}
+        st = mapping.FusedMappingStep(params, bench.LRS, W, H, 0.8, 1.0, 0.1, confidence=torch.zeros(P, 1, device=dev),
+                                      capacity=front + back, front_instances=front, back_instances=back)
+        st.begin_window(attach=True)
+        losses, g = [], None
+        for k in range(iters):
+            if use_graph and k == 4:
+                torch.cuda.synchronize()
+                g = st.graph(rs, inp["tile_mask"], *kf, warmup=False)
+            if g is not None:
+                g.replay()
+                losses.append(float(st.loss[0]))
+            else:
+                losses.append(float(st(rs, inp["tile_mask"], *kf)[0]))
+        st.check()
+        return losses, params
+
+    la, pa = run(False)
+    lb, pb = run(True)
+    assert la == lb, (la, lb)
+    assert la[-1] < la[0]
+    for k in pa:
+        assert torch.equal(pa[k], pb[k]), k
