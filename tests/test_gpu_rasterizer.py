@@ -158,9 +158,11 @@ def test_against_cpu_oracle(cfg, P, deg, mask):
 
 @pytest.mark.skipif(not rh.reference_available(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("cfg,mask,precomp", [("c1", "ones", False), ("c1", "half", True), ("c2", "ones", False),
-                                              ("ragged", "half", False), ("ragged", "ones", False), ("deg1", "ones", False)])
+                                              ("ragged", "half", False), ("ragged", "ones", False), ("deg1", "ones", False),
+                                              ("c5", "ones", False)])
 def test_against_live_reference(cfg, mask, precomp):
-    """Full BASELINE sizes against the unmodified reference extension on the same GPU."""
+    """Full BASELINE sizes (config 1, 2 and 5: 3 M Gaussians at 1920x1080, ~10^8 instances) against the unmodified
+    reference extension on the same GPU."""
     _, C, _, _ = rh.load_reference()
     inp = rh.make_inputs(cfg, torch.device(DEV), mask=mask, precomp=precomp)
     cam = inp["cam"]
@@ -184,7 +186,8 @@ def test_against_live_reference(cfg, mask, precomp):
 
 
 @pytest.mark.skipif(not rh.reference_available(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("cfg,mask,front,back", [("c2", "ones", 2_000_128, 4_000_000), ("c1", "half", 65_536, 1_200_000)])
+@pytest.mark.parametrize("cfg,mask,front,back", [("c2", "ones", 2_000_128, 4_000_000), ("c1", "half", 65_536, 1_200_000),
+                                                 ("c5", "ones", 6_000_128, 30_000_000)])
 def test_two_phase_binning_against_live_reference(cfg, mask, front, back):
     """Occlusion-aware two-phase binning (front_instances > 0) against the unmodified reference: every per-pixel and
     per-Gaussian output the reference returns must still be bit-identical although most instances are never binned."""
