@@ -53,7 +53,7 @@ __device__ __forceinline__ unsigned digit_peers(uint32_t d, int bits, bool valid
     return valid ? peers : (1u << lane);
 }
 
-// counts[d * tiles + tile] = number of keys of tile `tile` whose digit is d
+// counts[d * tiles_used + tile] = number of keys of tile `tile` whose digit is d (tiles_used = ceil(n / keys per tile))
 template <typename KeyT, int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS) radix_count_kernel(const KeyT *__restrict__ keys, const int *count, const int *skip,
                                                                  int64_t capacity, int shift, int bits, int tiles,
@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_count_kernel(const KeyT *__r
     __syncthreads();
     const int64_t tile_start = (int64_t)tile * RS_TILE;
     // the loads only depend on the capacity (the buffers are capacity-sized): they are in flight while the count arrives
+    // (reading the count first costs the front tile sort 11 us at c2 and saves the oversized back region less)
     const int cap_count = (int)((capacity - tile_start) < RS_TILE ? (capacity - tile_start) : RS_TILE);
     keys += tile_start;
     const int wbase = warp * (32 * RS_ITEMS) + lane;
@@ -97,11 +98,15 @@ __global__ void __launch_bounds__(RS_THREADS) radix_count_kernel(const KeyT *__r
         }
     }
     __syncthreads();
-    counts[(size_t)tid * tiles + tile] = s_hist[tid];
+    // the count matrix is laid out for the tiles that hold keys (digit-major, row stride = used tiles), not for the
+    // capacity: a generously sized region costs empty blocks, not scan work
+    const int tiles_used = (int)((n + RS_TILE - 1) / RS_TILE);
+    if (tile < tiles_used) counts[(size_t)tid * tiles_used + tile] = s_hist[tid];
 }
 
 // in-place exclusive prefix sum of data[0, n): single pass, decoupled look-back (sort.cuh) over blocks of 4096 elements
-__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t *data, int64_t n, unsigned long long *lb, uint32_t *ticket) {
+__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t *data, const int *count, const int *skip, int64_t capacity,
+                                                          int keys_per_tile, unsigned long long *lb, uint32_t *ticket) {
     pdl_enter();
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_excl, s_tile;
@@ -109,6 +114,9 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t *data, int64_
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const int tile = (int)s_tile;
+    const int64_t items = sort_count(count, skip, capacity);
+    const int64_t n = 256 * ((items + keys_per_tile - 1) / keys_per_tile); // the used part of the count matrix
+    if ((int64_t)tile * RS_SCAN_BLOCK >= n) return; // (every later ticket is out of range too: nobody waits for this block)
     const int64_t base = (int64_t)tile * RS_SCAN_BLOCK + tid * 4;
     uint32_t v[4] = {0, 0, 0, 0};
     if (base + 3 < n) {
@@ -194,10 +202,11 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
         const int idx = wbase + i * 32;
         k[i] = (idx < cap_count) ? (uint32_t)keys_in[idx] : 0u;
     }
-    const uint32_t my_offset = offsets[(size_t)tid * tiles + tile]; // global position of this tile's first key of digit tid
     for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
     const int64_t n = sort_count(count, skip, capacity);
     if (tile_start >= n) return;
+    const int tiles_used = (int)((n + RS_TILE - 1) / RS_TILE);
+    const uint32_t my_offset = offsets[(size_t)tid * tiles_used + tile]; // global position of this tile's first key of digit tid
     __syncthreads();
     const int valid_count = (int)((n - tile_start) < RS_TILE ? (n - tile_start) : RS_TILE);
     const uint32_t mask = (1u << bits) - 1u;
@@ -291,7 +300,6 @@ int radix_sort_pairs(KeyT *keys_a, KeyT *keys_b, uint32_t *vals_a, uint32_t *val
     uint32_t *counts = (uint32_t *)(tp + T.counts), *ticket = (uint32_t *)(tp + T.ticket);
     unsigned long long *lb = (unsigned long long *)(tp + T.lb);
     DQO_CUDA_CHECK(cudaMemsetAsync(tp + T.ticket, 0, T.clear_bytes, stream)); // tickets + look-back words of every pass
-    const int64_t n_counts = (int64_t)256 * T.tiles;
     KeyT *kin = keys_a, *kout = keys_b;
     const uint32_t *vin = implicit_vals ? nullptr : vals_a;
     uint32_t *vout = vals_b;
@@ -300,15 +308,15 @@ int radix_sort_pairs(KeyT *keys_a, KeyT *keys_b, uint32_t *vals_a, uint32_t *val
         if (radix_items(capacity) == 8) {
             launch_pdl(radix_count_kernel<KeyT, 8>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, count, skip, capacity, 8 * p,
                        bits, T.tiles, counts);
-            launch_pdl(radix_scan_kernel, dim3(T.scan_blocks), dim3(1024), 0, stream, counts, n_counts,
-                       lb + (size_t)p * T.scan_blocks, ticket + p);
+            launch_pdl(radix_scan_kernel, dim3(T.scan_blocks), dim3(1024), 0, stream, counts, count, skip, capacity,
+                       RS_THREADS * 8, lb + (size_t)p * T.scan_blocks, ticket + p);
             launch_pdl(radix_scatter_kernel<KeyT, 8>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, kout, vin, vout, count,
                        skip, capacity, 8 * p, bits, T.tiles, counts);
         } else {
             launch_pdl(radix_count_kernel<KeyT, 16>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, count, skip, capacity, 8 * p,
                        bits, T.tiles, counts);
-            launch_pdl(radix_scan_kernel, dim3(T.scan_blocks), dim3(1024), 0, stream, counts, n_counts,
-                       lb + (size_t)p * T.scan_blocks, ticket + p);
+            launch_pdl(radix_scan_kernel, dim3(T.scan_blocks), dim3(1024), 0, stream, counts, count, skip, capacity,
+                       RS_THREADS * 16, lb + (size_t)p * T.scan_blocks, ticket + p);
             launch_pdl(radix_scatter_kernel<KeyT, 16>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, kout, vin, vout, count,
                        skip, capacity, 8 * p, bits, T.tiles, counts);
         }
