@@ -88,8 +88,10 @@ def gather_gaussians(tensors, dst=0, group=None, sizes=None):
     packed = torch.cat([tensors[n].reshape(n_here, -1).to(torch.float32) for n in names], dim=1).contiguous()
     F = packed.shape[1]
     if rank != dst:
-        if n_here:
-            dist.send(packed, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+        if n_here:  # batched like the receives on `dst` (an unbatched send is serialised with every other op of the group)
+            peer = dist.get_global_rank(group, dst) if group is not None else dst
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, packed, peer, group)]):
+                req.wait()
         return None
     total = sum(sizes)
     out = torch.empty((total, F), dtype=torch.float32, device=dev)
