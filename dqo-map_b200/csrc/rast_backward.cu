@@ -31,6 +31,7 @@ struct RenderBwdArgs {
     const float *dL_dpix, *dL_ddepth;
     const int *hit_image;
     double *gacc;
+    uint8_t *touched; // touched[id] = 1 whenever a record receives a contribution (plain store, every writer stores 1)
 };
 
 // Sum 9 per-lane values over the warp; on return lanes with (lane & 1) == 0 whose slot index < 9 hold the
@@ -104,7 +105,7 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 
 // depth gradient to the single hit Gaussian of a pixel (backward.cu:998-1065)
 __device__ __noinline__ void bwd_depth_path(const float *scales, const float *rotations, const float *means3D,
-                                            const float *view, const float *hit_geo, size_t plane, size_t sp, double *gacc,
+                                            const float *view, const float *hit_geo, size_t plane, size_t sp, double *gacc, uint8_t *touched,
                                             int gid, float g, uint32_t pix_x, uint32_t pix_y, float fx, float fy, float cx,
                                             float cy, float depth_thr, float normal_thr) {
     const float3 ray = pixel_ray(pix_x, pix_y, fx, fy, cx, cy);
@@ -119,6 +120,7 @@ __device__ __noinline__ void bwd_depth_path(const float *scales, const float *ro
     const float angle_distance = fabsf(ndotr);
     const float depth_distance = fabsf(fsub(hz, pcz));
     double *acc = gacc + (size_t)gid * DQO_GACC_FLOATS;
+    touched[gid] = 1;
     if (depth_distance <= fmul(depth_thr, scale_max) && angle_distance >= normal_thr) {
         const float nr = (float)((double)ndotr + 1e-8);
         const float inv_nr = 1.f / nr;
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(RB_THREADS, RB_OCC) render_backward_kernel(Ren
                           p5.x + p5.y, p6.x + p6.y, p7.x + p7.y, p8.x + p8.y};
             const float total = warp_reduce9(v, lane);
             if (my_slot >= 0) atomicAdd(&a.gacc[(size_t)__float_as_int(q4.z) * DQO_GACC_FLOATS + my_slot], (double)total);
+            if (lane == 0) a.touched[__float_as_int(q4.z)] = 1;
         }
     }
 #pragma unroll
@@ -367,7 +370,7 @@ __global__ void __launch_bounds__(RB_THREADS, RB_OCC) render_backward_kernel(Ren
         const int gid = a.hit_image[pid];
         if (gid >= 0)
             bwd_depth_path(a.scales, a.rotations, a.means3D, a.view, a.hit_geo, a.plane, (size_t)tile * 256 + ly * 16 + lx,
-                           a.gacc, gid, a.dL_ddepth[pid], pix_x, py, a.fx, a.fy, a.cx, a.cy, a.depth_thr, a.normal_thr);
+                           a.gacc, a.touched, gid, a.dL_ddepth[pid], pix_x, py, a.fx, a.fy, a.cx, a.cy, a.depth_thr, a.normal_thr);
     }
 }
 
@@ -380,6 +383,7 @@ struct GaussBwdArgs {
     const int *radii;
     const uint8_t *clamped;
     double *gacc; // read, and the records that were non-zero cleared again (dqo_rast_settings.geom_clean)
+    uint8_t *touched; // one byte instead of the 128-byte record for the Gaussians nothing was added to
     float *dL_dmeans2D, *dL_dconic, *dL_dopacity, *dL_dcolors, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drot;
     // Fused mapping step only (nullptr otherwise): ever[i] != 0 once Gaussian i has received a non-zero gradient.  A
     // Gaussian that never has is a fixed point of Adam (zero gradient on zero moments), so its gradients are neither
@@ -415,7 +419,8 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
     const int base_g = blockIdx.x * blockDim.x + warp * 32;
     const int nrow = min(32, a.P - base_g);
     const bool live = idx < a.P;
-    const bool active = live && a.radii[idx] > 0;
+    // only Gaussians the blend added to (a visible Gaussian that no pixel with a gradient saw has an all-zero record)
+    const bool active = live && a.touched[idx] != 0;
     const int M = a.M;
     float g[DQO_GACC_FLOATS];
     if (active) {
@@ -436,6 +441,7 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
 #pragma unroll
     for (int k = 0; k < DQO_GACC_FLOATS; k++) nz |= (g[k] != 0.f);
     const bool need = active && nz;
+    if (active) a.touched[idx] = 0;
     if (need) { // leave the accumulator clean for the next backward pass
         double2 *gz = reinterpret_cast<double2 *>(a.gacc + (size_t)idx * DQO_GACC_FLOATS);
 #pragma unroll
@@ -819,6 +825,7 @@ extern "C" int dqo_rast_geom_init(int32_t P, void *geom_buffer, void *stream_) {
     if (make_geom_layout(P, &GL)) return DQO_ERR_WORKSPACE;
     DQO_CUDA_CHECK(cudaMemsetAsync((char *)geom_buffer + GL.gacc, 0, (size_t)P * DQO_GACC_FLOATS * sizeof(double),
                                    (cudaStream_t)stream_));
+    DQO_CUDA_CHECK(cudaMemsetAsync((char *)geom_buffer + GL.touched, 0, (size_t)P, (cudaStream_t)stream_));
     return DQO_OK;
 }
 
@@ -878,7 +885,10 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     const char *img = (const char *)image_buffer;
     double *gacc = (double *)(geom + GL.gacc);
     stage_mark(stream, ST_BEGIN_BWD);
-    if (!s->geom_clean) DQO_CUDA_CHECK(cudaMemsetAsync(gacc, 0, (size_t)P * DQO_GACC_FLOATS * sizeof(double), stream));
+    if (!s->geom_clean) {
+        DQO_CUDA_CHECK(cudaMemsetAsync(gacc, 0, (size_t)P * DQO_GACC_FLOATS * sizeof(double), stream));
+        DQO_CUDA_CHECK(cudaMemsetAsync(geom + GL.touched, 0, (size_t)P, stream));
+    }
 
     const float focal_y = s->H / (2.0f * s->tanfovy);
     const float focal_x = s->W / (2.0f * s->tanfovx);
@@ -898,6 +908,7 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     ra.hit_geo = (const float *)(img + IL.hit_geo);
     ra.plane = (size_t)IL.T * 256;
     ra.dL_dpix = dL_dout_color; ra.dL_ddepth = dL_dout_depth; ra.hit_image = hit_image; ra.gacc = gacc;
+    ra.touched = (uint8_t *)(geom + GL.touched);
     launch_pdl(render_backward_kernel, dim3(IL.T), dim3(RB_THREADS), 0, stream, ra);
     DQO_LAUNCH_CHECK("render backward", s->debug, stream);
     stage_mark(stream, ST_RENDER_BWD);
@@ -910,6 +921,7 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     ga.view = viewmatrix; ga.proj = projmatrix; ga.campos = campos; ga.radii = radii;
     ga.clamped = (const uint8_t *)(geom + GL.clamped);
     ga.gacc = gacc;
+    ga.touched = (uint8_t *)(geom + GL.touched);
     ga.dL_dmeans2D = dL_dmeans2D; ga.dL_dconic = dL_dconic; ga.dL_dopacity = dL_dopacity; ga.dL_dcolors = dL_dcolors;
     ga.dL_dmeans3D = dL_dmeans3D; ga.dL_dcov3D = dL_dcov3D; ga.dL_dsh = (s->M > 0) ? dL_dsh : nullptr;
     ga.dL_dscales = dL_dscales; ga.dL_drot = dL_drotations;
