@@ -213,6 +213,7 @@ struct GeomLayout {
     size_t clamped;    // u8[P] bit c = colour channel c clamped (forward.cu:151-153)
     size_t gacc;       // f64[16P] gradient accumulators of the backward blend (see DQO_GACC_FLOATS)
     size_t touched;    // u8[P] set by the backward blend when it adds to a Gaussian's record, cleared by the consumer
+    size_t out_nz;     // u8[P] geom_clean == 2: 1 where the previous backward wrote non-zero gradient rows
     size_t tiles_b;    // u32[P] two-phase: unfinished tiles in the rectangle of every rank the front phase left out
     size_t sums;       // per phase: u32[emit_blocks] totals of 256 ranks + u32[emit_groups] totals of 64 such blocks
     size_t sums_stride;

@@ -391,6 +391,9 @@ struct GaussBwdArgs {
     uint8_t *ever;
     uint32_t *ever_list; // optional compact list of the Gaussians whose flag is set (append order), with its length
     int *ever_count;
+    // dqo_rast_settings.geom_clean == 2 (nullptr otherwise): out_nz[i] != 0 where the previous call wrote a non-zero row
+    // into the caller's gradient tensors; rows that were zero and stay zero are not written again.
+    uint8_t *out_nz;
 };
 
 __device__ __constant__ float B_SH_C0 = 0.28209479177387814f;
@@ -491,6 +494,11 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
     float dscale[3] = {0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     bool write_out = live;
+    if (a.out_nz && live) {
+        const bool was = a.out_nz[idx] != 0;
+        if (was != nz) a.out_nz[idx] = nz ? 1 : 0;
+        write_out = nz || was;
+    }
     if (a.ever && live) {
         const bool was = a.ever[idx] != 0;
         if (nz && !was) {
@@ -826,6 +834,7 @@ extern "C" int dqo_rast_geom_init(int32_t P, void *geom_buffer, void *stream_) {
     DQO_CUDA_CHECK(cudaMemsetAsync((char *)geom_buffer + GL.gacc, 0, (size_t)P * DQO_GACC_FLOATS * sizeof(double),
                                    (cudaStream_t)stream_));
     DQO_CUDA_CHECK(cudaMemsetAsync((char *)geom_buffer + GL.touched, 0, (size_t)P, (cudaStream_t)stream_));
+    DQO_CUDA_CHECK(cudaMemsetAsync((char *)geom_buffer + GL.out_nz, 0, (size_t)P, (cudaStream_t)stream_));
     return DQO_OK;
 }
 
@@ -926,6 +935,7 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     ga.dL_dmeans3D = dL_dmeans3D; ga.dL_dcov3D = dL_dcov3D; ga.dL_dsh = (s->M > 0) ? dL_dsh : nullptr;
     ga.dL_dscales = dL_dscales; ga.dL_drot = dL_drotations;
     ga.ever = ever;
+    ga.out_nz = (s->geom_clean == 2 && !ever) ? (uint8_t *)(geom + GL.out_nz) : nullptr;
     ga.ever_list = (ever && ever_list && ever_count) ? ever_list : nullptr;
     ga.ever_count = ever_count;
     const bool staged = shs && !f_rest && dL_dsh && s->M == 16 && ((uintptr_t)shs % 16 == 0) && ((uintptr_t)dL_dsh % 16 == 0);

@@ -49,6 +49,7 @@ int make_geom_layout(int P, GeomLayout *L) {
     L->clamped = bump(cur, n);
     L->gacc = bump(cur, n * DQO_GACC_FLOATS * 8);
     L->touched = bump(cur, n);
+    L->out_nz = bump(cur, n);
     // look-back words + tickets of the two emission kernels (front / single phase, back phase): cleared together
     L->tiles_b = bump(cur, n * 4);
     L->emit_blocks = (int)((n + 255) / 256);

@@ -84,7 +84,7 @@ def _make_settings(P, D, M, W, H, tanfovx, tanfovy, cx, cy, scale_modifier, colo
                    front_instances=0, back_instances=0, geom_clean=False):
     return RastSettings(P, D, M, W, H, tanfovx, tanfovy, cx, cy, scale_modifier, color_sigma, opaque_threshold,
                         depth_threshold, normal_threshold, T_threshold, int(bool(prefiltered)), int(bool(debug)),
-                        int(bool(need_n_touched)), int(front_instances), int(back_instances), int(bool(geom_clean)))
+                        int(bool(need_n_touched)), int(front_instances), int(back_instances), int(geom_clean))
 
 
 class ForwardState:
@@ -250,11 +250,13 @@ class RasterPipeline:
             check(L.dqo_rast_geom_init(P, ptr(self.geom), _stream()), "dqo_rast_geom_init")
         self.binning = torch.empty((L.dqo_rast_binning_bytes(self.capacity),), **u8)
         self.image = torch.empty((L.dqo_rast_image_bytes(W, H),), **u8)
-        self.g_means2D, self.g_conic = torch.empty((P, 3), **f32), torch.empty((P, 4), **f32)
-        self.g_opacity, self.g_colors = torch.empty((P, 1), **f32), torch.empty((P, 3), **f32)
-        self.g_means3D, self.g_cov3D = torch.empty((P, 3), **f32), torch.empty((P, 6), **f32)
-        self.g_sh = torch.empty((P, max(M, 0), 3), **f32)
-        self.g_scales, self.g_rot = torch.empty((P, 3), **f32), torch.empty((P, 4), **f32)
+        # gradient tensors: owned by the pipeline, zero-initialised once; with geom_clean = 2 the backward only rewrites
+        # the rows that are or were non-zero (do not write into them from outside)
+        self.g_means2D, self.g_conic = torch.zeros((P, 3), **f32), torch.zeros((P, 4), **f32)
+        self.g_opacity, self.g_colors = torch.zeros((P, 1), **f32), torch.zeros((P, 3), **f32)
+        self.g_means3D, self.g_cov3D = torch.zeros((P, 3), **f32), torch.zeros((P, 6), **f32)
+        self.g_sh = torch.zeros((P, max(M, 0), 3), **f32)
+        self.g_scales, self.g_rot = torch.zeros((P, 3), **f32), torch.zeros((P, 4), **f32)
         self.settings = None
 
     def forward(self, rs, means3D, opacities, scales, rotations, tile_mask, shs=None, colors_precomp=None,
@@ -262,7 +264,7 @@ class RasterPipeline:
         self.settings = _make_settings(self.P, int(rs.sh_degree), self.M, self.W, self.H, rs.tanfovx, rs.tanfovy, rs.cx,
                                        rs.cy, rs.scale_modifier, rs.color_sigma, rs.opaque_threshold, rs.depth_threshold,
                                        rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, need_n_touched,
-                                       self.front, self.back, geom_clean=True)
+                                       self.front, self.back, geom_clean=2)  # persistent, zero-initialised gradient buffers
         self._in = (rs, means3D, shs, colors_precomp, scales, rotations)
         check(lib().dqo_rast_forward(
             self.settings, ptr(rs.bg), ptr(means3D), ptr(shs), ptr(colors_precomp), ptr(opacities), ptr(scales),

@@ -71,7 +71,10 @@ typedef struct dqo_rast_settings {
     /* 1: the caller guarantees that `geom_buffer` was initialised once with dqo_rast_geom_init() after its allocation and
      * has since been written by this library only.  The backward pass leaves the per-Gaussian gradient accumulators
      * inside it zeroed (it clears exactly the records it consumed), so with this promise it skips clearing all
-     * 128 B x P of them at its start.  0 (default): the accumulators are cleared on every backward call. */
+     * 128 B x P of them at its start.  0 (default): the accumulators are cleared on every backward call.
+     * 2: as 1, and additionally the nine gradient output tensors of dqo_rast_backward are the SAME buffers in every call,
+     * zero-initialised by the caller before the first one and not written by anyone else: rows that were zero after the
+     * previous call and are zero again (most of a large map) are then not rewritten (~300 B per Gaussian). */
     int32_t geom_clean;
 } dqo_rast_settings;
 
