@@ -422,6 +422,12 @@ def _gate_by_mode(ours, theirs):
         tol_d = max(0.01 * abs(np.mean(dt)), 1.5 * max(_spread(do), _spread(dt)), DEPTH_L1_SELF_NOISE * abs(np.mean(dt)))
         assert abs(np.mean(do) - np.mean(dt)) <= tol_d, ("depth L1", do, dt, tol_d)
     assert shared >= 1, ("no outcome reached by both implementations", ours, theirs)
+    # an outcome only OUR runs reach must not be worse than every outcome of the other side (a regression that sends some
+    # of our runs into a distinct, worse state would otherwise pass unnoticed)
+    worst_theirs = min(x[0] for x in pooled if x[2] == 1)
+    for c in clusters:
+        if all(x[2] == 0 for x in c):
+            assert np.mean([x[0] for x in c]) >= worst_theirs - MODE_GAP_DB, ("our runs reach a worse outcome", c, theirs)
 
 
 
