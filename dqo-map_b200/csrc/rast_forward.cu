@@ -239,6 +239,26 @@ __global__ void __launch_bounds__(256) depth_key_kernel(int P, const float *__re
     depth_key[idx] = ok ? __float_as_uint(vz) : 0xFFFFFFFFu;
 }
 
+// Everything the forward pass needs zeroed (tile ranges, status words, prefix-sum totals, the scratch headers of its three
+// sorts) in ONE launch at its start instead of up to seven memset nodes spread over the chain: a memset between two
+// kernels is a full serialisation point (no programmatic overlap) and one more node to dispatch.
+#define DQO_CLEAR_MAX 8
+struct ClearArgs {
+    void *ptr[DQO_CLEAR_MAX];
+    unsigned long long bytes[DQO_CLEAR_MAX]; // multiples of 4, pointers 4-byte aligned
+    int n;
+};
+__global__ void __launch_bounds__(256) clear_regions_kernel(ClearArgs a) {
+    pdl_enter();
+    for (int r = 0; r < a.n; r++) {
+        uint32_t *p = (uint32_t *)a.ptr[r];
+        const unsigned long long words = a.bytes[r] / 4;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < words;
+             i += (unsigned long long)gridDim.x * blockDim.x)
+            p[i] = 0u;
+    }
+}
+
 // tile_mask != 0 as one bitmap row per tile row: the per-Gaussian tile count and the instance emission then cost
 // O(rows x words) instead of one global load per tile of the rectangle
 __global__ void mask_bits_kernel(int gx, int gy, int words, const int *__restrict__ tile_mask, uint32_t *bits) {
@@ -1486,9 +1506,15 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     pdl_scope(s->P);
     stage_mark(stream, ST_BEGIN_FWD);
     nvtx_push("dqo_rast_forward");
-    // ranges and ranges_b are neighbours in the image buffer's layout only by accident: clear them separately
-    DQO_CUDA_CHECK(cudaMemsetAsync(ranges, 0, (size_t)T * sizeof(uint2), stream));
-    DQO_CUDA_CHECK(cudaMemsetAsync(status, 0, DQO_ST_WORDS * sizeof(int), stream));
+    ClearArgs clr;
+    clr.n = 0;
+    auto clear_add = [&](void *ptr, size_t bytes) {
+        clr.ptr[clr.n] = ptr;
+        clr.bytes[clr.n] = bytes;
+        clr.n++;
+    };
+    clear_add(ranges, (size_t)T * sizeof(uint2));
+    clear_add(status, DQO_ST_WORDS * sizeof(int));
 
     const float focal_y = s->H / (2.0f * s->tanfovy);
     const float focal_x = s->W / (2.0f * s->tanfovx);
@@ -1506,7 +1532,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         return DQO_ERR_INVALID_ARG;
     }
     uint2 *ranges_b = two_phase ? (uint2 *)(img + IL.ranges_b) : nullptr;
-    if (two_phase) DQO_CUDA_CHECK(cudaMemsetAsync(ranges_b, 0, (size_t)T * sizeof(uint2), stream));
+    if (two_phase) clear_add(ranges_b, (size_t)T * sizeof(uint2));
     uint32_t *vals_a = nullptr, *vals_b = nullptr;
     char *keys_a = nullptr, *keys_b = nullptr, *sort_temp = nullptr;
     const uint32_t *d_order = nullptr, *d_tiles = nullptr, *d_mask_bits = nullptr;
@@ -1516,6 +1542,10 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     size_t sums_stride = 0;
     int emit_blocks = 0;
     ForkJoin *fj = debug ? nullptr : fork_join(stream); // side stream + events owned by (device, caller stream)
+    if (P <= 0) {
+        launch_pdl(clear_regions_kernel, dim3(64), dim3(256), 0, stream, clr);
+        DQO_LAUNCH_CHECK("clear", debug, stream);
+    }
     int lazy_shmode = 0;
     ColorArgs ca = {};
     if (P > 0) {
@@ -1524,7 +1554,17 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         char *geom = (char *)geom_buffer;
         char *bin = (char *)binning_buffer;
         uint32_t *mask_bits = (uint32_t *)(img + IL.mask_bits);
-        DQO_CUDA_CHECK(cudaMemsetAsync(geom + GL.sums, 0, 2 * GL.sums_stride, stream));
+        clear_add(geom + GL.sums, 2 * GL.sums_stride);
+        { // scratch headers of the depth sort and of the tile sorts (front and back share one scratch, disjoint pass slots)
+            void *q;
+            size_t nb;
+            sort_clear_region(geom + GL.sort_temp, P, 32, &q, &nb);
+            clear_add(q, nb);
+            sort_clear_region(bin + BL.sort_temp, capacity > 0 ? capacity : 1, 32, &q, &nb);
+            clear_add(q, nb);
+        }
+        launch_pdl(clear_regions_kernel, dim3(64), dim3(256), 0, stream, clr);
+        DQO_LAUNCH_CHECK("clear", debug, stream);
         // fork: depth keys + the (depth, id) sort of the Gaussians (stable LSD sort on the depth bits) on the side
         // stream, concurrently with the rest of the preprocess
         uint32_t *order = (uint32_t *)(geom + GL.order);
@@ -1541,7 +1581,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         // values are implicit (value = index) so no iota array is read.
         {
             const int rc = radix_sort_pairs<uint32_t>((uint32_t *)(geom + GL.depth_key), (uint32_t *)(geom + GL.depth_key2), order, (uint32_t *)(geom + GL.ids), true,
-                                                      nullptr, nullptr, P, 32, geom + GL.sort_temp, sort_stream);
+                                                      nullptr, nullptr, P, 32, geom + GL.sort_temp, sort_stream, 0, false, P);
             if (rc) return rc;
             if (debug) DQO_CUDA_CHECK(cudaStreamSynchronize(sort_stream));
         }
@@ -1703,12 +1743,19 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         }
         if (mode != 2) stage_mark(stream, ST_DUPLICATE);
         int rc;
+        // the scratch header was cleared at the start of the pass; the back-phase sort uses the pass slots behind the front
+        // sort's (with more than two passes per sort -- images of >= 65535 tiles -- it clears for itself)
+        const int sort_passes = radix_passes(sort_bits);
+        const bool own_clear = mode == 2 && 2 * sort_passes > RS_MAX_PASSES;
+        const int slot0 = (mode == 2 && !own_clear) ? sort_passes : 0;
         if (keys16)
             rc = radix_sort_pairs<uint16_t>((uint16_t *)ka, (uint16_t *)kb, va, vb, false, status + count_word,
-                                            status + DQO_ST_OVERFLOW, n, sort_bits, sort_temp, stream);
+                                            status + DQO_ST_OVERFLOW, n, sort_bits, sort_temp, stream, slot0, own_clear,
+                                            capacity);
         else
             rc = radix_sort_pairs<uint32_t>((uint32_t *)ka, (uint32_t *)kb, va, vb, false, status + count_word,
-                                            status + DQO_ST_OVERFLOW, n, sort_bits, sort_temp, stream);
+                                            status + DQO_ST_OVERFLOW, n, sort_bits, sort_temp, stream, slot0, own_clear,
+                                            capacity);
         if (rc) return rc;
         if (debug) DQO_CUDA_CHECK(cudaStreamSynchronize(stream));
         if (mode != 2) stage_mark(stream, ST_TILE_SORT);

@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(RS_THREADS, 3)
 
 template <typename KeyT>
 int radix_sort_pairs(KeyT *keys_a, KeyT *keys_b, uint32_t *vals_a, uint32_t *vals_b, bool implicit_vals, const int *count,
-                     const int *skip, int64_t capacity, int nbits, void *temp, cudaStream_t stream) {
+                     const int *skip, int64_t capacity, int nbits, void *temp, cudaStream_t stream, int pass_slot0, bool clear,
+                     int64_t temp_capacity) {
     if (capacity <= 0) return DQO_OK;
     if (capacity >= (1ll << 30)) {
         set_error("radix_sort_pairs: at most 2^30 - 1 items");
@@ -293,13 +294,22 @@ int radix_sort_pairs(KeyT *keys_a, KeyT *keys_b, uint32_t *vals_a, uint32_t *val
     }
     if (nbits < 1) nbits = 1;
     if (nbits > (int)sizeof(KeyT) * 8) nbits = (int)sizeof(KeyT) * 8;
-    SortTemp T;
-    make_sort_temp(capacity, nbits, &T);
+    if (temp_capacity < capacity) temp_capacity = capacity;
+    SortTemp T; // offsets (and the look-back stride) from the capacity the scratch was laid out for, grids from this sort's
+    make_sort_temp(temp_capacity, nbits, &T);
+    const int lb_stride = T.scan_blocks;
+    T.tiles = (int)((capacity + radix_tile(capacity) - 1) / radix_tile(capacity));
+    if (T.tiles < 1) T.tiles = 1;
+    T.scan_blocks = (int)(((int64_t)256 * T.tiles + 4095) / 4096);
     const int passes = radix_passes(nbits);
     char *tp = (char *)temp;
     uint32_t *counts = (uint32_t *)(tp + T.counts), *ticket = (uint32_t *)(tp + T.ticket);
     unsigned long long *lb = (unsigned long long *)(tp + T.lb);
-    DQO_CUDA_CHECK(cudaMemsetAsync(tp + T.ticket, 0, T.clear_bytes, stream)); // tickets + look-back words of every pass
+    if (pass_slot0 < 0 || pass_slot0 + passes > RS_MAX_PASSES) {
+        set_error("radix_sort_pairs: pass slots out of range");
+        return DQO_ERR_INVALID_ARG;
+    }
+    if (clear) DQO_CUDA_CHECK(cudaMemsetAsync(tp + T.ticket, 0, T.clear_bytes, stream)); // tickets + look-back words of every pass
     KeyT *kin = keys_a, *kout = keys_b;
     const uint32_t *vin = implicit_vals ? nullptr : vals_a;
     uint32_t *vout = vals_b;
@@ -309,14 +319,14 @@ int radix_sort_pairs(KeyT *keys_a, KeyT *keys_b, uint32_t *vals_a, uint32_t *val
             launch_pdl(radix_count_kernel<KeyT, 8>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, count, skip, capacity, 8 * p,
                        bits, T.tiles, counts);
             launch_pdl(radix_scan_kernel, dim3(T.scan_blocks), dim3(1024), 0, stream, counts, count, skip, capacity,
-                       RS_THREADS * 8, lb + (size_t)p * T.scan_blocks, ticket + p);
+                       RS_THREADS * 8, lb + (size_t)(pass_slot0 + p) * lb_stride, ticket + pass_slot0 + p);
             launch_pdl(radix_scatter_kernel<KeyT, 8>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, kout, vin, vout, count,
                        skip, capacity, 8 * p, bits, T.tiles, counts);
         } else {
             launch_pdl(radix_count_kernel<KeyT, 16>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, count, skip, capacity, 8 * p,
                        bits, T.tiles, counts);
             launch_pdl(radix_scan_kernel, dim3(T.scan_blocks), dim3(1024), 0, stream, counts, count, skip, capacity,
-                       RS_THREADS * 16, lb + (size_t)p * T.scan_blocks, ticket + p);
+                       RS_THREADS * 16, lb + (size_t)(pass_slot0 + p) * lb_stride, ticket + pass_slot0 + p);
             launch_pdl(radix_scatter_kernel<KeyT, 16>, dim3(T.tiles), dim3(RS_THREADS), 0, stream, kin, kout, vin, vout, count,
                        skip, capacity, 8 * p, bits, T.tiles, counts);
         }
@@ -332,9 +342,9 @@ int radix_sort_pairs(KeyT *keys_a, KeyT *keys_b, uint32_t *vals_a, uint32_t *val
 }
 
 template int radix_sort_pairs<uint16_t>(uint16_t *, uint16_t *, uint32_t *, uint32_t *, bool, const int *, const int *,
-                                        int64_t, int, void *, cudaStream_t);
+                                        int64_t, int, void *, cudaStream_t, int, bool, int64_t);
 template int radix_sort_pairs<uint32_t>(uint32_t *, uint32_t *, uint32_t *, uint32_t *, bool, const int *, const int *,
-                                        int64_t, int, void *, cudaStream_t);
+                                        int64_t, int, void *, cudaStream_t, int, bool, int64_t);
 
 } // namespace dqo
 

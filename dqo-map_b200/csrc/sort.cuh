@@ -25,29 +25,32 @@ inline int radix_items(int64_t capacity) { return capacity <= RS_SMALL_SORT ? 8 
 inline int radix_tile(int64_t capacity) { return RS_THREADS * radix_items(capacity); }
 
 struct SortTemp {
+    size_t ticket;  // u32[RS_MAX_PASSES] dynamic block ids of the scan kernel (+ padding)           } fixed position: sorts of
+    size_t lb;      // u64[RS_MAX_PASSES][scan_blocks] look-back words of the scan kernel            } different sizes can share
+    size_t clear_bytes; // ticket + lb: cleared once before the first sort that uses the scratch    } one scratch buffer
     size_t counts;  // u32[256][tiles] digit-major count matrix of the current pass, scanned in place
-    size_t ticket;  // u32[RS_MAX_PASSES] dynamic block ids of the scan kernel (+ padding)
-    size_t lb;      // u64[RS_MAX_PASSES][scan_blocks] look-back words of the scan kernel
-    size_t clear_bytes; // ticket + lb: cleared by ONE memset per sort
     size_t total;
     int tiles, scan_blocks;
 };
 
 inline int radix_passes(int nbits) { return nbits <= 0 ? 1 : (nbits + 7) / 8; }
 
+// Layout of the scratch for sorts of up to `capacity` items (the worst case over both tile sizes).
 inline void make_sort_temp(int64_t capacity, int nbits, SortTemp *T) {
     (void)nbits;
+    const int64_t tiles8 = (capacity + RS_THREADS * 8 - 1) / (RS_THREADS * 8);
     T->tiles = (int)((capacity + radix_tile(capacity) - 1) / radix_tile(capacity));
     if (T->tiles < 1) T->tiles = 1;
-    T->scan_blocks = (int)(((int64_t)256 * T->tiles + 4095) / 4096);
+    const int64_t max_tiles = tiles8 < 1 ? 1 : tiles8; // a smaller sort sharing this scratch may use 8-key tiles
+    T->scan_blocks = (int)(((int64_t)256 * max_tiles + 4095) / 4096);
     size_t cur = 0;
-    T->counts = cur;
-    cur += align_up((size_t)256 * T->tiles * 4, 256);
     T->ticket = cur;
     cur += 256;
     T->lb = cur;
     cur += align_up((size_t)RS_MAX_PASSES * T->scan_blocks * 8, 256);
     T->clear_bytes = cur - T->ticket;
+    T->counts = cur;
+    cur += align_up((size_t)256 * max_tiles * 4, 256);
     T->total = align_up(cur, 256);
 }
 
@@ -56,9 +59,20 @@ inline void make_sort_temp(int64_t capacity, int nbits, SortTemp *T) {
 // (keys_a, vals_a), with an odd number in (keys_b, vals_b) -- see radix_result_in_a().  vals_a == nullptr on input means
 // value = index (vals_b and, for an even number of passes, a scratch vals_a are still needed: pass it as vals_scratch).
 // `temp` must hold make_sort_temp(capacity, nbits).total bytes.  Enqueues 1 memset + 3 kernels per pass on `stream`.
+// `clear` = false: the caller has zeroed the scratch words itself (sort_clear_region) before the first sort that uses
+// `temp`; several sorts may then share one `temp` as long as their passes use disjoint slots [pass_slot0, pass_slot0 +
+// passes) of the RS_MAX_PASSES available -- no memset node between the kernels that produce the keys and the sort.
+// `temp_capacity` (0: = capacity) is the capacity the scratch was laid out for (make_sort_temp); it fixes the offsets.
 template <typename KeyT>
 int radix_sort_pairs(KeyT *keys_a, KeyT *keys_b, uint32_t *vals_a, uint32_t *vals_b, bool implicit_vals,
-                     const int *count, const int *skip, int64_t capacity, int nbits, void *temp, cudaStream_t stream);
+                     const int *count, const int *skip, int64_t capacity, int nbits, void *temp, cudaStream_t stream,
+                     int pass_slot0 = 0, bool clear = true, int64_t temp_capacity = 0);
+inline void sort_clear_region(void *temp, int64_t capacity, int nbits, void **ptr, size_t *bytes) {
+    SortTemp T;
+    make_sort_temp(capacity, nbits, &T);
+    *ptr = (char *)temp + T.ticket;
+    *bytes = T.clear_bytes;
+}
 
 inline bool radix_result_in_a(int nbits) { return radix_passes(nbits) % 2 == 0; }
 
