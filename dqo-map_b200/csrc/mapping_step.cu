@@ -679,7 +679,7 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
     int32_t *hit_depth = (int32_t *)(ws + L.hit_depth), *radii = (int32_t *)(ws + L.radii);
     int rc = rast_forward_impl(s, kf->background, xyz, f_dc, f_rest, nullptr, act_op, act_sc, act_rot, nullptr, kf->viewmatrix,
                                kf->projmatrix, kf->campos, kf->tile_mask, ws + L.geom, ws + L.binning, capacity,
-                               ws + L.image, (int32_t *)(ws + L.tile_indices), color, depth, hit_depth,
+                               ws + L.image, /* tile list: nobody reads it in the step */ nullptr, color, depth, hit_depth,
                                (int32_t *)(ws + L.hit_color), (float *)(ws + L.hit_cw), (float *)(ws + L.hit_dw),
                                (float *)(ws + L.T), radii, (int32_t *)(ws + L.n_touched), status, stream_, activate_hook,
                                &actx);

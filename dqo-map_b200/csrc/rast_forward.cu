@@ -1445,6 +1445,10 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
                                 float *out_depth, int32_t *out_hit_depth, int32_t *out_hit_color,
                                 float *out_hit_color_weight, float *out_hit_depth_weight, float *out_T, int32_t *radii,
                                 int32_t *n_touched, int32_t *status, void *stream_) {
+    if (!tile_indices) {
+        set_error("dqo_rast_forward: tile_indices is NULL");
+        return DQO_ERR_INVALID_ARG;
+    }
     return rast_forward_impl(s, background, means3D, shs, nullptr, colors_precomp, opacities, scales, rotations,
                              cov3D_precomp, viewmatrix, projmatrix, campos, tile_mask, geom_buffer, binning_buffer,
                              capacity, image_buffer, tile_indices, out_color, out_depth, out_hit_depth, out_hit_color,
@@ -1467,7 +1471,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         set_error("dqo_rast_forward: invalid settings");
         return DQO_ERR_INVALID_ARG;
     }
-    if (!background || !viewmatrix || !projmatrix || !campos || !tile_mask || !image_buffer || !tile_indices ||
+    if (!background || !viewmatrix || !projmatrix || !campos || !tile_mask || !image_buffer ||
         !out_color || !out_depth || !out_hit_depth || !out_hit_color || !out_hit_color_weight ||
         !out_hit_depth_weight || !out_T) {
         set_error("dqo_rast_forward: null pointer argument");
@@ -1773,6 +1777,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     // The list of non-empty tiles (rasterizer_impl.cu:348-365) is an output only -- the blend reads the ranges -- so
     // its single-block kernel runs on the side stream beside the final blend instead of in front of it.
     auto compact_fork = [&](const uint2 *rb) -> int {
+        if (!tile_indices) return DQO_OK; // internal callers that never read the tile list (the fused mapping step)
         cudaStream_t cs = stream;
         if (fj) {
             DQO_CUDA_CHECK(cudaEventRecord(fj->ev[2], stream));
@@ -1786,7 +1791,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         return DQO_OK;
     };
     auto compact_join = [&]() -> int {
-        if (fj) DQO_CUDA_CHECK(cudaStreamWaitEvent(stream, fj->ev[3], 0));
+        if (fj && tile_indices) DQO_CUDA_CHECK(cudaStreamWaitEvent(stream, fj->ev[3], 0));
         return DQO_OK;
     };
 

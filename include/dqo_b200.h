@@ -398,7 +398,8 @@ int dqo_mapping_step_workspace_init(int32_t P, int32_t M, int32_t W, int32_t H, 
 /* loss_out: device float[4] {total, colour, depth, attach}; counts_out: device int32[2]; status: device int32[DQO_ST_WORDS]
  * (check DQO_ST_OVERFLOW together with the loss read-back; on overflow the render is invalid and the Adam update is
  * skipped on the device -- parameters and moments are untouched, repeat the step with a larger capacity and the same
- * `step` number: see mapping.FusedMappingStep.check). */
+ * `step` number: see mapping.FusedMappingStep.check).  * The list of non-empty tiles is not produced by the step: status[DQO_ST_TILE_NUM] stays 0.
+ */
 int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params *p, const dqo_keyframe *kf, int32_t step,
                      double beta1, double beta2, double eps, void *workspace, int64_t instance_capacity,
                      float *loss_out, int32_t *counts_out, int32_t *status, void *stream);
