@@ -568,6 +568,8 @@ def run_ours(a, world, rank, local_rank):
     copy_stream = torch.cuda.Stream(device=dev)
     kf_slots = [[torch.empty_like(t, device=dev) for t in views[0]["host"]] for _ in range(2)]
     kf_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
 
     def prefetch(slot, view):
         with torch.cuda.stream(copy_stream):
@@ -613,8 +615,16 @@ def run_ours(a, world, rank, local_rank):
         else:
             g.replay()
             total = fstep.loss[0]
-        prefetch(cur ^ 1, views[(k + 1) % len(views)])  # the other slot was last read by the previous, completed step
-        return float(total)  # D2H read of the loss
+        # D2H read of the loss, every step, through a pinned two-slot buffer: the copy of step k is enqueued behind it and
+        # read by the host while step k + 1 is already running (the device never waits for the host)
+        loss_host[cur].copy_(total.detach().reshape(1), non_blocking=True)
+        loss_ready[cur].record()
+        prev = None
+        if k > 0:
+            loss_ready[cur ^ 1].synchronize()   # step k - 1 has finished: its keyframe slot is free again
+            prev = float(loss_host[cur ^ 1][0])
+        prefetch(cur ^ 1, views[(k + 1) % len(views)])
+        return prev
 
     # operator path (GaussianRasterizer autograd + torch activations + FusedAdam) and the ZERO-EDIT path (the drop-in
     # rasterizer inside the reference's own loop: torch activations, torch loss with boolean indexing, torch.optim.Adam)
@@ -717,7 +727,8 @@ def run_ours(a, world, rank, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": 4,
                     "what": "mapping iteration through the public API (mapping.FusedMappingStep%s): H2D keyframe, activations, "
-                            "fwd, masked L1 + attach loss, bwd, Adam, D2H loss; window of %d keyframes" % (
+                            "fwd, masked L1 + attach loss, bwd, Adam, D2H loss (pinned buffer, read one step behind so that the "
+                            "read overlaps the next step); window of %d keyframes" % (
                                 ".graph replay" if graphs else "", len(views))},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
