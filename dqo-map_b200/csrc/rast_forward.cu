@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
 struct ColorArgs {
     int P, D, phase;
     int64_t front;
-    const uint32_t *order, *offsets, *tiles, *tiles_rank;
+    const uint32_t *order, *offsets, *tiles, *tiles_rank; // tiles: tiles_touched in RANK order (rank_sums_kernel<0>)
     const float *means3D, *shs, *f_rest, *campos;
     float4 *rec;
     uint8_t *clamped;
@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(LC_THREADS) lazy_color_kernel(ColorArgs a) {
     uint32_t id = 0;
     if (r < a.P) {
         id = a.order[r];
-        need = (a.phase == 1) ? (a.tiles[id] != 0 && (int64_t)a.offsets[r] <= a.front) : (a.tiles_rank[r] != 0);
+        need = (a.phase == 1) ? (a.tiles[r] != 0 && (int64_t)a.offsets[r] <= a.front) : (a.tiles_rank[r] != 0);
     }
     const unsigned rows = __ballot_sync(0xFFFFFFFFu, need);
     if (!rows) return;
@@ -626,10 +626,11 @@ __global__ void mark_visible_kernel(int P, const float *__restrict__ means, cons
 template <int MODE>
 __device__ __forceinline__ uint32_t rank_count(int64_t i, uint32_t id, int64_t front, const uint32_t *__restrict__ tiles,
                                                const uint32_t *offsets, const uint2 *__restrict__ rect,
-                                               const uint32_t *__restrict__ sat_b, int grid_x) {
+                                               const uint32_t *__restrict__ sat_b, int grid_x,
+                                               const uint32_t *__restrict__ rank_tiles) {
     if (MODE != 2) return tiles[id];
     uint32_t n = 0;
-    if ((int64_t)offsets[i] > front && tiles[id]) {
+    if ((int64_t)offsets[i] > front && rank_tiles[i]) { // (tiles_touched in rank order: no second gather)
         const uint2 rc = rect[id];
         const uint32_t minx = rc.x & 0xFFFF, maxx = rc.x >> 16, miny = rc.y & 0xFFFF, maxy = rc.y >> 16;
         n = sat_count(sat_b, grid_x, minx, maxx, miny, maxy);
@@ -645,15 +646,16 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
     rank_sums_kernel(int P, int64_t front, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
                      const uint32_t *offsets, const uint2 *__restrict__ rect, const uint32_t *__restrict__ sat_b, int grid_x,
-                     uint32_t *tiles_rank, uint32_t *sums, uint32_t *group_sums) {
+                     uint32_t *tiles_rank, uint32_t *rank_tiles, uint32_t *sums, uint32_t *group_sums) {
     pdl_enter();
     __shared__ uint32_t s_w[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t i = (int64_t)blockIdx.x * 256 + tid;
     uint32_t n = 0;
     if (i < P) {
-        n = rank_count<MODE>(i, order[i], front, tiles, offsets, rect, sat_b, grid_x);
+        n = rank_count<MODE>(i, order[i], front, tiles, offsets, rect, sat_b, grid_x, rank_tiles);
         if (MODE == 2) tiles_rank[i] = n;
+        else rank_tiles[i] = n; // tiles_touched in depth-rank order: the emission and the back phase read it coalesced
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
@@ -684,7 +686,8 @@ __global__ void __launch_bounds__(256)
 template <typename KeyT, int MODE>
 __global__ void __launch_bounds__(256)
     emit_kernel(int P, int64_t capacity, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles,
-                const uint32_t *__restrict__ tiles_rank, uint32_t *offsets, const uint2 *__restrict__ rect,
+                const uint32_t *__restrict__ tiles_rank, const uint32_t *__restrict__ rank_tiles, uint32_t *offsets,
+                const uint2 *__restrict__ rect,
                 const uint32_t *__restrict__ mask_bits, const uint32_t *__restrict__ row_any, int mask_words, int grid_x,
                 KeyT *__restrict__ keys, uint32_t *__restrict__ vals, const uint32_t *__restrict__ sums,
                 const uint32_t *__restrict__ group_sums, int *status) {
@@ -705,11 +708,11 @@ __global__ void __launch_bounds__(256)
     uint2 rc = make_uint2(0, 0);
     if (i < P) {
         id = order[i];
-        n = (MODE == 2) ? tiles_rank[i] : tiles[id];
+        n = (MODE == 2) ? tiles_rank[i] : rank_tiles[i];
         if (n) rc = rect[id];
     }
     s_n[tid] = n;
-    if (MODE == 1 && tid == 255) s_n[256] = (i + 1 < P) ? tiles[order[i + 1]] : 0u;
+    if (MODE == 1 && tid == 255) s_n[256] = (i + 1 < P) ? rank_tiles[i + 1] : 0u;
     // block-wide inclusive scan of n, block-wide sum of pre
     uint32_t incl = n;
 #pragma unroll
@@ -1542,7 +1545,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     const uint32_t *d_order = nullptr, *d_tiles = nullptr, *d_mask_bits = nullptr;
     uint32_t *d_offsets = nullptr;
     const uint2 *d_rect = nullptr;
-    uint32_t *d_sums = nullptr, *d_tiles_b = nullptr;
+    uint32_t *d_sums = nullptr, *d_tiles_b = nullptr, *d_rank_tiles = nullptr;
     size_t sums_stride = 0;
     int emit_blocks = 0;
     ForkJoin *fj = debug ? nullptr : fork_join(stream); // side stream + events owned by (device, caller stream)
@@ -1660,10 +1663,11 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         d_mask_bits = mask_bits;
         d_sums = (uint32_t *)(geom + GL.sums);
         d_tiles_b = (uint32_t *)(geom + GL.tiles_b);
+        d_rank_tiles = (uint32_t *)(geom + GL.depth_key2); // the depth sort's ping-pong buffer is free once it has joined
         sums_stride = GL.sums_stride / 4;
         emit_blocks = GL.emit_blocks;
         ca.P = P; ca.D = s->D; ca.front = front;
-        ca.order = d_order; ca.offsets = d_offsets; ca.tiles = d_tiles; ca.tiles_rank = d_tiles_b;
+        ca.order = d_order; ca.offsets = d_offsets; ca.tiles = d_rank_tiles; ca.tiles_rank = d_tiles_b;
         ca.means3D = means3D; ca.shs = shs; ca.f_rest = f_rest; ca.campos = campos;
         ca.rec = pa.rec; ca.clamped = pa.clamped;
     }
@@ -1721,17 +1725,17 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
         uint32_t *sums = d_sums + (mode == 2 ? sums_stride : 0), *group_sums = sums + emit_blocks;
         if (mode == 2)
             launch_pdl(rank_sums_kernel<2>, dim3(emit_blocks), dim3(256), 0, stream, P, front, d_order, d_tiles, d_offsets, d_rect,
-                       (const uint32_t *)(img + IL.sat_b), IL.tiles_x, d_tiles_b, sums, group_sums);
+                       (const uint32_t *)(img + IL.sat_b), IL.tiles_x, d_tiles_b, d_rank_tiles, sums, group_sums);
         else
             launch_pdl(rank_sums_kernel<0>, dim3(emit_blocks), dim3(256), 0, stream, P, front, d_order, d_tiles, d_offsets, d_rect,
-                       (const uint32_t *)nullptr, IL.tiles_x, (uint32_t *)nullptr, sums, group_sums);
+                       (const uint32_t *)nullptr, IL.tiles_x, (uint32_t *)nullptr, d_rank_tiles, sums, group_sums);
         DQO_LAUNCH_CHECK("rank sums", debug, stream);
         if (mode == 2) {
             const int rcc = color_fork(2);
             if (rcc) return rcc;
         }
 #define DQO_EMIT(KT, MODE)                                                                                             \
-    launch_pdl(emit_kernel<KT, MODE>, dim3(emit_blocks), dim3(256), 0, stream, P, n, d_order, d_tiles, d_tiles_b, d_offsets, d_rect, bits,  \
+    launch_pdl(emit_kernel<KT, MODE>, dim3(emit_blocks), dim3(256), 0, stream, P, n, d_order, d_tiles, d_tiles_b, d_rank_tiles, d_offsets, d_rect, bits,  \
                                                           row_any_b, IL.mask_words, IL.tiles_x, (KT *)ka, va, sums,    \
                                                           group_sums, status)
         if (keys16) {
