@@ -24,6 +24,10 @@ struct LossArgs {
     float *dimg, *ddepth, *loss_out;
     int *counts_out;
     double *partial; // [LOSS_BLOCKS][4]: colour sum, colour pixel count, depth sum, depth count
+    // optional (fused step): the tile mask of the render.  The backward blend reads the gradient images only in tiles that
+    // were rendered, so the zero gradients of masked-out tiles need not be written.
+    const int *tile_mask;
+    int tiles_x;
 };
 
 __device__ __forceinline__ bool depth_valid(const LossArgs &a, size_t p, bool m, float *err) {
@@ -41,7 +45,10 @@ struct LossPix4 {
     int hit[4];
     bool m[4];
 };
-__device__ __forceinline__ void load_pix4(const LossArgs &a, size_t N, size_t q, bool need_depth, LossPix4 &x) {
+__device__ __forceinline__ uchar4 load_mask4(const LossArgs &a, size_t q) {
+    return a.mask ? reinterpret_cast<const uchar4 *>(a.mask)[q] : make_uchar4(1, 1, 1, 1);
+}
+__device__ __forceinline__ void load_pix4(const LossArgs &a, size_t N, size_t q, bool need_depth, uchar4 mk, LossPix4 &x) {
     const float4 i0 = reinterpret_cast<const float4 *>(a.image)[q];
     const float4 i1 = reinterpret_cast<const float4 *>(a.image + N)[q];
     const float4 i2 = reinterpret_cast<const float4 *>(a.image + 2 * N)[q];
@@ -50,8 +57,6 @@ __device__ __forceinline__ void load_pix4(const LossArgs &a, size_t N, size_t q,
     const float4 g2 = reinterpret_cast<const float4 *>(a.gt_color)[3 * q + 2];
     const float iv[3][4] = {{i0.x, i0.y, i0.z, i0.w}, {i1.x, i1.y, i1.z, i1.w}, {i2.x, i2.y, i2.z, i2.w}};
     const float gf[12] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w};
-    uchar4 mk = make_uchar4(1, 1, 1, 1);
-    if (a.mask) mk = reinterpret_cast<const uchar4 *>(a.mask)[q];
     const uint8_t mv[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -80,8 +85,11 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_partial_kernel(LossArgs a, 
     if (vec) {
         const bool need_depth = a.depth_w > 0.f;
         for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N / 4; q += (size_t)gridDim.x * blockDim.x) {
+            const uchar4 mk = load_mask4(a, q);
+            if (!(mk.x | mk.y | mk.z | mk.w)) continue; // no masked-in pixel: contributes to neither term (object masks
+                                                        // cover a small part of the image: most quads stop here)
             LossPix4 x;
-            load_pix4(a, N, q, need_depth, x);
+            load_pix4(a, N, q, need_depth, mk, x);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 if (x.m[k]) {
@@ -166,8 +174,22 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_grad_kernel(LossArgs a, int
     if (vec) {
         const bool need_depth = a.depth_w > 0.f;
         for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < N / 4; q += (size_t)gridDim.x * blockDim.x) {
+            const uchar4 mk = load_mask4(a, q);
+            if (!(mk.x | mk.y | mk.z | mk.w)) { // all four gradients are zero; nothing else has to be read
+                if (a.tile_mask && (a.W & 3) == 0) { // ... and in a tile that is not rendered nobody reads them either
+                    const size_t p = 4 * q;
+                    const int py = (int)(p / a.W), px = (int)(p - (size_t)py * a.W);
+                    if (a.tile_mask[(py >> 4) * a.tiles_x + (px >> 4)] == 0) continue;
+                }
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                reinterpret_cast<float4 *>(a.dimg)[q] = z;
+                reinterpret_cast<float4 *>(a.dimg + N)[q] = z;
+                reinterpret_cast<float4 *>(a.dimg + 2 * N)[q] = z;
+                reinterpret_cast<float4 *>(a.ddepth)[q] = z;
+                continue;
+            }
             LossPix4 x;
-            load_pix4(a, N, q, need_depth, x);
+            load_pix4(a, N, q, need_depth, mk, x);
             float g[3][4], gdp[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -345,11 +367,11 @@ extern "C" size_t dqo_loss_workspace_bytes(int32_t W, int32_t H) {
     return (size_t)LOSS_BLOCKS * 4 * sizeof(double);
 }
 
-extern "C" int dqo_masked_l1_loss(int32_t W, int32_t H, const float *image, const float *depth,
-                                  const int32_t *hit_depth, const float *gt_color, const float *gt_depth,
-                                  const uint8_t *render_mask, float color_weight, float depth_weight,
-                                  float depth_err_thres, float *dL_dimage, float *dL_ddepth, float *loss_out,
-                                  int32_t *counts_out, void *workspace, void *stream_) {
+namespace dqo {
+int masked_l1_loss_impl(int32_t W, int32_t H, const float *image, const float *depth, const int32_t *hit_depth,
+                        const float *gt_color, const float *gt_depth, const uint8_t *render_mask, float color_weight,
+                        float depth_weight, float depth_err_thres, float *dL_dimage, float *dL_ddepth, float *loss_out,
+                        int32_t *counts_out, void *workspace, const int32_t *tile_mask, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (W <= 0 || H <= 0 || !image || !depth || !hit_depth || !gt_color || !gt_depth || !dL_dimage || !dL_ddepth ||
         !loss_out || !counts_out || !workspace) {
@@ -361,6 +383,7 @@ extern "C" int dqo_masked_l1_loss(int32_t W, int32_t H, const float *image, cons
     a.hit = hit_depth; a.mask = render_mask; a.color_w = color_weight; a.depth_w = depth_weight;
     a.depth_thr = depth_err_thres; a.dimg = dL_dimage; a.ddepth = dL_ddepth; a.loss_out = loss_out;
     a.counts_out = counts_out; a.partial = (double *)workspace;
+    a.tile_mask = tile_mask; a.tiles_x = (W + 15) / 16;
     const size_t N = (size_t)W * H;
     int blocks = (int)((N + LOSS_THREADS - 1) / LOSS_THREADS);
     if (blocks > LOSS_BLOCKS) blocks = LOSS_BLOCKS;
@@ -379,6 +402,16 @@ extern "C" int dqo_masked_l1_loss(int32_t W, int32_t H, const float *image, cons
     launch_pdl(loss_grad_kernel, dim3(blocks), dim3(LOSS_THREADS), 0, stream, a, blocks, vec);
     DQO_LAUNCH_CHECK("masked l1 loss", 0, stream);
     return DQO_OK;
+}
+} // namespace dqo
+
+extern "C" int dqo_masked_l1_loss(int32_t W, int32_t H, const float *image, const float *depth,
+                                  const int32_t *hit_depth, const float *gt_color, const float *gt_depth,
+                                  const uint8_t *render_mask, float color_weight, float depth_weight,
+                                  float depth_err_thres, float *dL_dimage, float *dL_ddepth, float *loss_out,
+                                  int32_t *counts_out, void *workspace, void *stream_) {
+    return masked_l1_loss_impl(W, H, image, depth, hit_depth, gt_color, gt_depth, render_mask, color_weight, depth_weight,
+                               depth_err_thres, dL_dimage, dL_ddepth, loss_out, counts_out, workspace, nullptr, stream_);
 }
 
 extern "C" int dqo_adam_step(const dqo_adam_tensor *tensors, int32_t n_tensors, int32_t step, double beta1, double beta2,

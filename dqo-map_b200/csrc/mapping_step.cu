@@ -23,6 +23,10 @@ int rast_forward_impl(const dqo_rast_settings *s, const float *background, const
                       float *out_depth, int32_t *out_hit_depth, int32_t *out_hit_color, float *out_hit_color_weight,
                       float *out_hit_depth_weight, float *out_T, int32_t *radii, int32_t *n_touched, int32_t *status,
                       void *stream_, void (*pre_hook)(void *, void *), void *hook_ctx);
+int masked_l1_loss_impl(int32_t W, int32_t H, const float *image, const float *depth, const int32_t *hit_depth,
+                        const float *gt_color, const float *gt_depth, const uint8_t *render_mask, float color_weight,
+                        float depth_weight, float depth_err_thres, float *dL_dimage, float *dL_ddepth, float *loss_out,
+                        int32_t *counts_out, void *workspace, const int32_t *tile_mask, void *stream_);
 int rast_backward_impl(const dqo_rast_settings *s, const float *background, const float *means3D, const float *shs,
                        const float *f_rest, const float *colors_precomp, const float *scales, const float *rotations,
                        const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix, const float *campos,
@@ -685,9 +689,9 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
                                &actx);
     if (rc) return rc;
     float *g_img = (float *)(ws + L.g_img), *g_depth = (float *)(ws + L.g_depth);
-    rc = dqo_masked_l1_loss(W, H, color, depth, hit_depth, kf->gt_color, kf->gt_depth, kf->render_mask, kf->color_weight,
-                            kf->depth_weight, kf->depth_err_thres, g_img, g_depth, loss_out, counts_out, ws + L.loss_ws,
-                            stream_);
+    rc = masked_l1_loss_impl(W, H, color, depth, hit_depth, kf->gt_color, kf->gt_depth, kf->render_mask, kf->color_weight,
+                             kf->depth_weight, kf->depth_err_thres, g_img, g_depth, loss_out, counts_out, ws + L.loss_ws,
+                             kf->tile_mask, stream_);
     if (rc) return rc;
     float *g_means3D = (float *)(ws + L.g_means3D), *g_sh = (float *)(ws + L.g_sh), *g_op = (float *)(ws + L.g_opacity);
     float *g_sc = (float *)(ws + L.g_scales), *g_rot = (float *)(ws + L.g_rot);
