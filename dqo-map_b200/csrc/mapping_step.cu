@@ -22,7 +22,7 @@ int rast_forward_impl(const dqo_rast_settings *s, const float *background, const
                       void *binning_buffer, int64_t capacity, void *image_buffer, int32_t *tile_indices, float *out_color,
                       float *out_depth, int32_t *out_hit_depth, int32_t *out_hit_color, float *out_hit_color_weight,
                       float *out_hit_depth_weight, float *out_T, int32_t *radii, int32_t *n_touched, int32_t *status,
-                      void *stream_, void (*pre_hook)(void *, void *), void *hook_ctx);
+                      void *stream_, void (*pre_hook)(void *, void *), void *hook_ctx, uint8_t *tile_filled);
 int masked_l1_loss_impl(int32_t W, int32_t H, const float *image, const float *depth, const int32_t *hit_depth,
                         const float *gt_color, const float *gt_depth, const uint8_t *render_mask, float color_weight,
                         float depth_weight, float depth_err_thres, float *dL_dimage, float *dL_ddepth, float *loss_out,
@@ -636,6 +636,8 @@ extern "C" int dqo_mapping_step_workspace_init(int32_t P, int32_t M, int32_t W, 
         set_error("dqo_mapping_step_workspace_init: invalid argument");
         return DQO_ERR_INVALID_ARG;
     }
+    const size_t tiles = (size_t)((W + 15) / 16) * ((H + 15) / 16);
+    DQO_CUDA_CHECK(cudaMemsetAsync((char *)workspace + L.tile_indices, 0, tiles * 4, (cudaStream_t)stream));
     return dqo_rast_geom_init(P, (char *)workspace + L.geom, stream);
 }
 
@@ -686,7 +688,7 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
                                ws + L.image, /* tile list: nobody reads it in the step */ nullptr, color, depth, hit_depth,
                                (int32_t *)(ws + L.hit_color), (float *)(ws + L.hit_cw), (float *)(ws + L.hit_dw),
                                (float *)(ws + L.T), radii, (int32_t *)(ws + L.n_touched), status, stream_, activate_hook,
-                               &actx);
+                               &actx, (uint8_t *)(ws + L.tile_indices) /* per-tile "holds fill values" flags */);
     if (rc) return rc;
     float *g_img = (float *)(ws + L.g_img), *g_depth = (float *)(ws + L.g_depth);
     rc = masked_l1_loss_impl(W, H, color, depth, hit_depth, kf->gt_color, kf->gt_depth, kf->render_mask, kf->color_weight,

@@ -921,6 +921,9 @@ struct RenderArgs {
     size_t plane; // T*256
     float *out_color, *out_depth, *out_hit_cw, *out_hit_dw, *out_T;
     int *out_hit_depth, *out_hit_color, *n_touched;
+    // optional (persistent outputs, single-phase): tile_filled[t] != 0 <=> the output pixels of tile t currently hold the
+    // fill values of a tile that is not rendered; such a tile is not written again until it is rendered
+    uint8_t *tile_filled;
     // two-phase binning (PHASE 1 / 2)
     const uint2 *ranges_b;
     const uint32_t *point_list_b;
@@ -990,6 +993,12 @@ __global__ void __launch_bounds__(256, PHASE == 2 ? 2 : 4) render_forward_kernel
 
     if (PHASE != 2 && range.x == range.y) { // tile not rendered: reference fill values (rasterize_points.cu:79-86)
         if (PHASE == 1 && tid == 0) a.unfinished[tile] = 1; // nothing in front: the back phase may still reach it
+        if (PHASE == 0 && a.tile_filled) { // object steps render a few tiles of a 1080p image: the rest stays as it is
+            const bool filled = a.tile_filled[tile] != 0;
+            __syncthreads();
+            if (filled) return;
+            if (tid == 0) a.tile_filled[tile] = 1;
+        }
         if (inside) {
             a.out_color[pix_id] = 0.f;
             a.out_color[HW + pix_id] = 0.f;
@@ -1007,6 +1016,7 @@ __global__ void __launch_bounds__(256, PHASE == 2 ? 2 : 4) render_forward_kernel
     const float tile_px = (float)(tile_x * DQO_TILE), tile_py = (float)(tile_y * DQO_TILE);
     const int total = (int)(range.y - range.x);
     const int rounds = (total + 255) / 256;
+    if (PHASE == 0 && a.tile_filled && tid == 0) a.tile_filled[tile] = 0;
     if (tid == 0) s_sp[256].r0 = s_sp[256].r1 = s_sp[256].c = make_float4(0.f, 0.f, 0.f, 0.f); // opacity 0: alpha = 0
 
     // Per-pixel state.  Two of the reference's flags live inside other values so that the walk needs no predicate <->
@@ -1436,7 +1446,7 @@ int rast_forward_impl(const dqo_rast_settings *s, const float *background, const
                       void *binning_buffer, int64_t capacity, void *image_buffer, int32_t *tile_indices, float *out_color,
                       float *out_depth, int32_t *out_hit_depth, int32_t *out_hit_color, float *out_hit_color_weight,
                       float *out_hit_depth_weight, float *out_T, int32_t *radii, int32_t *n_touched, int32_t *status,
-                      void *stream_, void (*pre_hook)(void *, void *), void *hook_ctx);
+                      void *stream_, void (*pre_hook)(void *, void *), void *hook_ctx, uint8_t *tile_filled);
 }
 
 extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *background, const float *means3D,
@@ -1456,7 +1466,7 @@ extern "C" int dqo_rast_forward(const dqo_rast_settings *s, const float *backgro
                              cov3D_precomp, viewmatrix, projmatrix, campos, tile_mask, geom_buffer, binning_buffer,
                              capacity, image_buffer, tile_indices, out_color, out_depth, out_hit_depth, out_hit_color,
                              out_hit_color_weight, out_hit_depth_weight, out_T, radii, n_touched, status, stream_, nullptr,
-                             nullptr);
+                             nullptr, nullptr);
 }
 
 int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, const float *means3D,
@@ -1468,7 +1478,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
                                 float *out_depth, int32_t *out_hit_depth, int32_t *out_hit_color,
                                 float *out_hit_color_weight, float *out_hit_depth_weight, float *out_T, int32_t *radii,
                                 int32_t *n_touched, int32_t *status, void *stream_, void (*pre_hook)(void *, void *),
-                                void *hook_ctx) {
+                                void *hook_ctx, uint8_t *tile_filled) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!s || s->P < 0 || s->W <= 0 || s->H <= 0 || !status) {
         set_error("dqo_rast_forward: invalid settings");
@@ -1540,6 +1550,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     }
     uint2 *ranges_b = two_phase ? (uint2 *)(img + IL.ranges_b) : nullptr;
     if (two_phase) clear_add(ranges_b, (size_t)T * sizeof(uint2));
+    if (two_phase && tile_filled) clear_add(tile_filled, ((size_t)T + 3) / 4 * 4); // the two-phase blends do not keep the flags
     uint32_t *vals_a = nullptr, *vals_b = nullptr;
     char *keys_a = nullptr, *keys_b = nullptr, *sort_temp = nullptr;
     const uint32_t *d_order = nullptr, *d_tiles = nullptr, *d_mask_bits = nullptr;
@@ -1711,6 +1722,7 @@ int dqo::rast_forward_impl(const dqo_rast_settings *s, const float *background, 
     ra.out_hit_dw = out_hit_depth_weight; ra.out_T = out_T; ra.out_hit_depth = out_hit_depth;
     ra.out_hit_color = out_hit_color; ra.n_touched = s->need_n_touched ? n_touched : nullptr;
     ra.ranges_b = ranges_b; ra.point_list_b = point_list ? point_list + front : nullptr;
+    ra.tile_filled = two_phase ? nullptr : tile_filled;
     ra.unfinished = (int *)(img + IL.unfinished);
     ra.state = (float *)(img + IL.state);
     ra.status = status;

@@ -601,3 +601,33 @@ def test_fused_step_graph_replay_is_bit_identical_at_config2_size():
     assert la[-1] < la[0]
     for k in pa:
         assert torch.equal(pa[k], pb[k]), k
+
+
+def test_fused_step_outputs_outside_a_changing_tile_mask_are_fill_values():
+    """The fused step keeps its output images across calls and does not rewrite the fill values of tiles that stay
+    unrendered (object steps render a few tiles of a large image).  With a tile mask that changes from call to call --
+    tiles rendered before, masked out now -- `rendered()` must still equal what a step with a FRESH workspace returns for
+    the same parameters and mask: fill values (rasterize_points.cu:79-89) outside the mask, never stale content."""
+    gt, cam, settings, raw, gt_color, gt_depth, render_mask = _scene(P=6000, deg=3)
+    H, W = cam.image_height, cam.image_width
+    th, tw = (H + 15) // 16, (W + 15) // 16
+    frozen = dict(LRS, xyz=0.0, f_dc=0.0, f_rest=0.0, scaling=0.0, rotation=0.0)  # parameters stay put
+    params = {k: v.clone().contiguous() for k, v in raw.items()}
+    st = mapping.FusedMappingStep(params, frozen, W, H, 0.8, 1.0, 0.1)
+    rs = settings()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    masks = [torch.ones((th, tw), dtype=torch.int32, device=DEV)]
+    for _ in range(3):
+        masks.append((torch.rand((th, tw), generator=g) < 0.4).to(torch.int32).to(DEV))
+    masks.append(torch.ones((th, tw), dtype=torch.int32, device=DEV))
+    for k, tm in enumerate(masks):
+        tm = tm.contiguous()
+        st(rs, tm, gt_color, gt_depth, render_mask)
+        st.check()
+        fresh = mapping.FusedMappingStep({n: v.clone().contiguous() for n, v in raw.items()}, frozen, W, H, 0.8, 1.0, 0.1)
+        fresh.ws.fill_(0x5A)  # poison, then initialise as the constructor does
+        fresh._alloc()
+        fresh(rs, tm, gt_color, gt_depth, render_mask)
+        fresh.check()
+        for name, a, b in zip(("color", "depth", "hit_depth", "T"), st.rendered(), fresh.rendered()):
+            assert torch.equal(a, b), (k, name)
