@@ -289,10 +289,33 @@ __device__ __forceinline__ uint32_t mask_row_count(const uint32_t *__restrict__ 
 // The number of masked tiles in a rectangle is then four loads, whatever its size (the row-by-row popcount it replaces
 // was a chain of dependent loads per Gaussian: 15 % of the preprocess).  Built by ONE block: row prefixes from the
 // bitmap words, then a running sum down every column.
+#define SAT_SMEM_ENTRIES 9216 // 36 KB of shared memory: images up to 1920x1080 (121 x 68 entries); larger ones take the slow path
 __device__ __forceinline__ void build_sat(int gx, int gy, int words, const uint32_t *bits, uint32_t *sat) {
+    __shared__ uint32_t s_pre[SAT_SMEM_ENTRIES];
+    const int stride = gx + 1;
+    if (gy * stride <= SAT_SMEM_ENTRIES) {
+        // all (row, column) prefixes in parallel from the bitmap words, then one thread per column sums down the rows
+        for (int e = threadIdx.x; e < gy * stride; e += blockDim.x) {
+            const int y = e / stride, x = e - y * stride; // bits of row y in columns [0, x)
+            const uint32_t *row = bits + y * words;
+            uint32_t c = 0;
+            for (int w = 0; w < (x >> 5); w++) c += __popc(row[w]);
+            if (x & 31) c += __popc(row[x >> 5] & ((1u << (x & 31)) - 1u));
+            s_pre[e] = c;
+        }
+        __syncthreads();
+        for (int x = threadIdx.x; x < stride; x += blockDim.x) {
+            uint32_t run = 0;
+            sat[x] = 0;
+            for (int y = 0; y < gy; y++) {
+                run += s_pre[y * stride + x];
+                sat[(y + 1) * stride + x] = run;
+            }
+        }
+        return;
+    }
     // one thread per column x: running sum over the rows of "set bits of row y in columns [0, x)", read straight from
     // the bitmap words (a few hundred bytes, cache-resident); the table is only ever written, never read back
-    const int stride = gx + 1;
     for (int x = threadIdx.x; x < stride; x += blockDim.x) {
         const int full = x >> 5;
         const uint32_t part = (x & 31) ? ((1u << (x & 31)) - 1u) : 0u;
