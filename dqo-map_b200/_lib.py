@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # DQO_B200_LIB: another build of the same library (kernel A/B experiments, tests/dev_*.py); there is still no fallback
 LIB_PATH = os.environ.get("DQO_B200_LIB") or os.path.join(_HERE, "csrc", "libdqomap_b200.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_R_FRONT, ST_R_BACK, ST_WALKED, ST_UNFINISHED = range(8)
 ST_WORDS = 8
@@ -41,13 +41,16 @@ class MapParams(C.Structure):
                 ("confidence", c_p), ("ever", c_p), ("ever_list", c_p), ("ever_count", c_p),
                 ("init_xyz", c_p), ("init_scaling", c_p), ("init_rotation", c_p), ("init_opacity", c_p),
                 ("attach_count", c_p), ("attach_weight", C.c_float), ("attach_opacity_thres", C.c_float),
-                ("step_state", c_p)]
+                ("step_state", c_p),
+                ("semantics", c_p), ("semantics_exp_avg", c_p), ("semantics_exp_avg_sq", c_p),
+                ("lr_semantics", C.c_double)]
 
 
 class Keyframe(C.Structure):
     _fields_ = [("gt_color", c_p), ("gt_depth", c_p), ("render_mask", c_p), ("tile_mask", c_p), ("viewmatrix", c_p),
                 ("projmatrix", c_p), ("campos", c_p), ("background", c_p), ("color_weight", C.c_float),
-                ("depth_weight", C.c_float), ("depth_err_thres", C.c_float)]
+                ("depth_weight", C.c_float), ("depth_err_thres", C.c_float), ("ssim_weight", C.c_float),
+                ("semantic_weight", C.c_float), ("gt_semantic", c_p)]
 
 
 # name -> (restype, argtypes); mirrors include/dqo_b200.h declaration by declaration
@@ -96,6 +99,9 @@ PROTOTYPES = {
     "dqo_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "dqo_masked_l1_loss": (C.c_int, [C.c_int32, C.c_int32] + [c_p] * 6 + [C.c_float, C.c_float, C.c_float]
                            + [c_p] * 5 + [c_p]),
+    "dqo_ssim_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "dqo_ssim_window": (None, [C.POINTER(C.c_float)]),
+    "dqo_ssim_loss": (C.c_int, [C.c_int32, C.c_int32, c_p, c_p, C.c_float, c_p, C.c_int32, c_p, c_p, c_p]),
     "dqo_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                                 c_p, C.c_int32, c_p]),
     "dqo_mapping_step_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64]),

@@ -13,7 +13,7 @@
 
 #define DQO_TILE 16
 #define DQO_TILE_PIX 256
-#define DQO_ABI_VERSION 12
+#define DQO_ABI_VERSION 13
 
 namespace dqo {
 
@@ -200,6 +200,14 @@ __host__ __device__ inline uint32_t higher_msb(uint32_t n) { // rasterizer_impl.
 
 // ---- private workspace layouts ------------------------------------------------------------------
 // geometry buffer: per-Gaussian splat records + depth-sort scratch
+// A second colour set blended over the lists of the main render (semantic image of loss_update): inputs and outputs of
+// its backward pass (rast_backward_impl)
+struct ExtraBlendGrad {
+    const float *colors;  // [P,3]
+    const float *dL_dpix; // [3,H,W] gradient of the loss w.r.t. the extra image
+    double *cacc;         // f64[4P] colour-gradient accumulators, zero on entry, left zero
+    float *dL_dcolors;    // [P,3] out
+};
 struct GeomLayout {
     size_t rec;        // float4[3P]: {x,y,conic.x,conic.y} {conic.z,opacity,power_reject,extent.y} {r,g,b,extent.x}
     size_t depth;      // f32[P] view-space depth (forward.cu:339)

@@ -1,7 +1,8 @@
 // Fused mapping iteration: one C-ABI call enqueues the whole step of the reference's hot loop
-// (SLAM/multiprocess/mapper.py:568-599 + loss_update :799-928: masked L1 colour + depth loss and the attach term
-// :810-829; the SSIM / normal / semantic / instance terms are not part of the fused step) on one stream, with no host
-// synchronisation and no intermediate tensor owned by the host:
+// (SLAM/multiprocess/mapper.py:568-599 + loss_update :799-928: masked L1 colour + depth loss, the attach term :810-829,
+// the SSIM term of the mask-less global pass :839-841 and the semantic colour term :877-880; not the normal term, whose
+// weight is 0 in every shipped config, nor the gradient-free instance term) on one stream, with no host synchronisation
+// and no intermediate tensor owned by the host:
 //
 //   raw parameters --activate--> rasterize forward --> masked L1 colour/depth loss + image gradients
 //                  <-- Adam on the raw parameters <-- activation backward <-- rasterize backward
@@ -35,7 +36,9 @@ int rast_backward_impl(const dqo_rast_settings *s, const float *background, cons
                        const float *dL_dout_depth, const int32_t *hit_image, float *dL_dmeans2D, float *dL_dconic,
                        float *dL_dopacity, float *dL_dcolors, float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh,
                        float *dL_dscales, float *dL_drotations, uint8_t *ever, uint32_t *ever_list, int32_t *ever_count,
-                       void *stream_);
+                       void *stream_, const ExtraBlendGrad *extra);
+int ssim_loss_impl(int32_t W, int32_t H, const float *image, const float *gt_color, float weight, float *dL_dimage,
+                   int32_t accumulate, float *loss_out, void *workspace, void *stream_);
 
 struct StepLayout {
     size_t act_opacity, act_scales, act_rot;                    // activated copies [P], [P,3], [P,4]
@@ -44,6 +47,9 @@ struct StepLayout {
     size_t g_img, g_depth, loss_ws;                             // loss gradients + reduction scratch
     size_t g_means3D, g_sh, g_opacity, g_scales, g_rot;         // activated-space parameter gradients
     size_t adam;                                                // AdamScalars of this step, written on the device
+    // optional loss terms: SSIM scratch; semantic image, its gradient image, a dummy depth-gradient image, loss scratch,
+    // f64[4] colour-gradient accumulators per Gaussian (kept zero between steps) and the semantic colour gradient [P,3]
+    size_t ssim_ws, extra_loss, sem_img, g_sem, g_sem_depth, sem_loss_ws, cacc, g_semantics;
     size_t total;
 };
 static size_t sbump(size_t &cur, size_t bytes) {
@@ -82,6 +88,14 @@ static int make_step_layout(int P, int M, int W, int H, int64_t capacity, StepLa
     L->g_scales = sbump(cur, n * 12);
     L->g_rot = sbump(cur, n * 16);
     L->adam = sbump(cur, 256);
+    L->ssim_ws = sbump(cur, dqo_ssim_workspace_bytes(W, H));
+    L->extra_loss = sbump(cur, 256);
+    L->sem_img = sbump(cur, N * 12);
+    L->g_sem = sbump(cur, N * 12);
+    L->g_sem_depth = sbump(cur, N * 4);
+    L->sem_loss_ws = sbump(cur, dqo_loss_workspace_bytes(W, H));
+    L->cacc = sbump(cur, n * 32);
+    L->g_semantics = sbump(cur, n * 12);
     L->total = align_up(cur, 256);
     return 0;
 }
@@ -112,6 +126,7 @@ struct AdamScalars {
     float attach_grad[3], attach_val[3];
     float attach_logit_thr; // a Gaussian is anchored when sigmoid(init_opacity) < thr
     int skip;               // the forward flagged an instance overflow: gradients are invalid, no update
+    float step_size_sem;    // semantic colours
 };
 __device__ __forceinline__ void adam_update(float &p, float g, float &m, float &v, const AdamScalars &k, float step_size) {
     m = m + k.omb1 * (g - m);
@@ -132,6 +147,11 @@ struct PrepareArgs {
     float attach_thr;
     const int *attach_count; // NULL: no attach term
     AdamScalars *out;
+    // optional loss terms computed into scratch by their own kernels: folded into the report here
+    float *loss_out;          // float[8] of the step
+    const float *ssim_val;    // {1 - ssim, weight * (1 - ssim)} or NULL
+    const float *sem_val;     // {weight * L1, L1} or NULL
+    double lr_semantics;
 };
 __global__ void adam_prepare_kernel(PrepareArgs a) {
     pdl_enter();
@@ -161,7 +181,15 @@ __global__ void adam_prepare_kernel(PrepareArgs a) {
     }
     k.attach_logit_thr = a.attach_thr;
     k.skip = overflow;
+    k.step_size_sem = (float)(a.lr_semantics / bc1);
     *a.out = k;
+    float total = a.loss_out[0];
+    a.loss_out[4] = a.ssim_val ? a.ssim_val[0] : 0.f;
+    if (a.ssim_val) total += a.ssim_val[1];
+    a.loss_out[5] = a.sem_val ? a.sem_val[1] : 0.f;
+    if (a.sem_val) total += a.sem_val[0];
+    a.loss_out[0] = total;
+    a.loss_out[6] = a.loss_out[7] = 0.f;
 }
 // number of Gaussians whose initial opacity is below the attach threshold (mapper.py:810-812)
 __global__ void __launch_bounds__(256) attach_count_kernel(int P, const float *__restrict__ init_opacity, float thr, int *count) {
@@ -618,6 +646,37 @@ __global__ void adam_rest_tail_kernel(long long begin, long long end, RestAdamAr
     a.f_rest[e] = p; a.m_rest[e] = m; a.v_rest[e] = v;
 }
 
+// Adam for the semantic colours [P,3] (parameter group "semantics_color", gaussian_pointcloud.py:371-378): over the
+// compact list of ever-touched Gaussians when there is one, else over the cloud with the flag byte
+struct SemAdamArgs {
+    int P;
+    float *p, *m, *v;
+    const float *g;
+    const uint8_t *ever;
+    const uint32_t *list;
+    const int *count;
+    const AdamScalars *kd;
+};
+__global__ void __launch_bounds__(256) adam_semantics_kernel(SemAdamArgs a) {
+    pdl_enter();
+    const AdamScalars k = *a.kd;
+    if (k.skip) return;
+    const long long n = a.list ? 3ll * (*a.count) : 3ll * a.P;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < n; w += (long long)gridDim.x * blockDim.x) {
+        const long long l = w / 3;
+        const int c = (int)(w - 3 * l);
+        const long long i = a.list ? (long long)a.list[l] : l;
+        if (!a.list && a.ever && !a.ever[i]) continue;
+        const long long e = 3 * i + c;
+        const float g = a.g[e];
+        float m = a.m[e], v = a.v[e];
+        if (g == 0.f && m == 0.f && v == 0.f) continue;
+        float p = a.p[e];
+        adam_update(p, g, m, v, k, k.step_size_sem);
+        a.p[e] = p; a.m[e] = m; a.v[e] = v;
+    }
+}
+
 } // namespace dqo
 
 using namespace dqo;
@@ -638,6 +697,7 @@ extern "C" int dqo_mapping_step_workspace_init(int32_t P, int32_t M, int32_t W, 
     }
     const size_t tiles = (size_t)((W + 15) / 16) * ((H + 15) / 16);
     DQO_CUDA_CHECK(cudaMemsetAsync((char *)workspace + L.tile_indices, 0, tiles * 4, (cudaStream_t)stream));
+    DQO_CUDA_CHECK(cudaMemsetAsync((char *)workspace + L.cacc, 0, (size_t)(P > 0 ? P : 1) * 32, (cudaStream_t)stream));
     return dqo_rast_geom_init(P, (char *)workspace + L.geom, stream);
 }
 
@@ -695,12 +755,39 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
                              kf->depth_weight, kf->depth_err_thres, g_img, g_depth, loss_out, counts_out, ws + L.loss_ws,
                              kf->tile_mask, stream_);
     if (rc) return rc;
+    // optional terms.  SSIM: like the reference only in the mask-less pass (mapper.py:839-841); its gradient is added to
+    // the colour-gradient image the backward blend reads.
+    float *extra_loss = (float *)(ws + L.extra_loss);
+    const bool use_ssim = kf->ssim_weight > 0.f && !kf->render_mask;
+    if (use_ssim) {
+        rc = ssim_loss_impl(W, H, color, kf->gt_color, kf->ssim_weight, g_img, 1, extra_loss, ws + L.ssim_ws, stream_);
+        if (rc) return rc;
+    }
+    // semantic term (mapper.py:877-880): the semantic image is one more blend over the lists of the main render
+    const bool use_sem = kf->gt_semantic != nullptr && kf->semantic_weight > 0.f;
+    ExtraBlendGrad xg;
+    if (use_sem) {
+        if (!p->semantics || !p->semantics_exp_avg || !p->semantics_exp_avg_sq) {
+            set_error("dqo_mapping_step: the semantic term needs dqo_map_params.semantics and its Adam state");
+            return DQO_ERR_INVALID_ARG;
+        }
+        float *sem_img = (float *)(ws + L.sem_img), *g_sem = (float *)(ws + L.g_sem);
+        rc = dqo_rast_blend_extra(s, kf->background, p->semantics, ws + L.geom, ws + L.binning, capacity, ws + L.image, status,
+                                  sem_img, stream_);
+        if (rc) return rc;
+        rc = masked_l1_loss_impl(W, H, sem_img, depth, hit_depth, kf->gt_semantic, kf->gt_depth, kf->render_mask,
+                                 kf->semantic_weight, 0.f, kf->depth_err_thres, g_sem, (float *)(ws + L.g_sem_depth),
+                                 extra_loss + 4, (int32_t *)(extra_loss + 8), ws + L.sem_loss_ws, kf->tile_mask, stream_);
+        if (rc) return rc;
+        xg.colors = p->semantics; xg.dL_dpix = g_sem; xg.cacc = (double *)(ws + L.cacc);
+        xg.dL_dcolors = (float *)(ws + L.g_semantics);
+    }
     float *g_means3D = (float *)(ws + L.g_means3D), *g_sh = (float *)(ws + L.g_sh), *g_op = (float *)(ws + L.g_opacity);
     float *g_sc = (float *)(ws + L.g_scales), *g_rot = (float *)(ws + L.g_rot);
     rc = rast_backward_impl(s, kf->background, xyz, f_dc, f_rest, nullptr, act_sc, act_rot, nullptr, kf->viewmatrix,
                             kf->projmatrix, kf->campos, radii, ws + L.geom, ws + L.binning, capacity, ws + L.image, status,
                             g_img, g_depth, hit_depth, nullptr, nullptr, g_op, nullptr, g_means3D, nullptr, g_sh, g_sc,
-                            g_rot, p->ever, p->ever_list, p->ever_count, stream_);
+                            g_rot, p->ever, p->ever_list, p->ever_count, stream_, use_sem ? &xg : nullptr);
     if (rc) return rc;
 
     // step number, bias corrections, attach scales and the overflow decision: one thread on the device
@@ -719,6 +806,10 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
         pa.attach_thr = p->attach_opacity_thres;
         pa.attach_count = attach ? p->attach_count : nullptr;
         pa.out = kd;
+        pa.loss_out = loss_out;
+        pa.ssim_val = use_ssim ? extra_loss : nullptr;
+        pa.sem_val = use_sem ? extra_loss + 4 : nullptr;
+        pa.lr_semantics = use_sem ? p->lr_semantics : 0.0;
         launch_pdl(adam_prepare_kernel, dim3(1), dim3(32), 0, stream, pa);
         DQO_LAUNCH_CHECK("adam prepare", s->debug, stream);
     }
@@ -741,6 +832,14 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
         aligned &= ((uintptr_t)p->ever % 4 == 0);
     }
     const bool use_list = p->ever && p->ever_list && p->ever_count && (long long)P * 45 < (1ll << 32);
+    if (use_sem) {
+        SemAdamArgs se;
+        se.P = P; se.p = p->semantics; se.m = p->semantics_exp_avg; se.v = p->semantics_exp_avg_sq;
+        se.g = (const float *)(ws + L.g_semantics); se.ever = p->ever;
+        se.list = use_list ? p->ever_list : nullptr; se.count = p->ever_count; se.kd = kd;
+        launch_pdl(adam_semantics_kernel, dim3(148 * 4), dim3(256), 0, stream, se);
+        DQO_LAUNCH_CHECK("adam (semantic colours)", s->debug, stream);
+    }
     if (use_list) {
         ListArgs la;
         la.s = sa; la.list = p->ever_list; la.count = p->ever_count;

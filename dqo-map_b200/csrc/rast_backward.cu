@@ -32,6 +32,11 @@ struct RenderBwdArgs {
     const int *hit_image;
     double *gacc;
     uint8_t *touched; // touched[id] = 1 whenever a record receives a contribution (plain store, every writer stores 1)
+    // EXTRA instantiation (a second colour set blended over the same lists, e.g. the semantic image of loss_update): the
+    // colours come from extra_colors [P,3] instead of the splat record, their gradient goes to cacc (f64[4] per Gaussian),
+    // the geometry gradients into the same records as the main pass (gradients of the two images add), no depth path
+    const float *extra_colors;
+    double *cacc;
 };
 
 // Sum 9 per-lane values over the warp; on return lanes with (lane & 1) == 0 whose slot index < 9 hold the
@@ -189,6 +194,7 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c
 __device__ __forceinline__ f2 dup(float v) { return make_float2(v, v); }
 __device__ __forceinline__ f2 lo_hi(float4 q, int h) { return h ? make_float2(q.z, q.w) : make_float2(q.x, q.y); }
 
+template <bool EXTRA>
 __global__ void __launch_bounds__(RB_THREADS, RB_OCC) render_backward_kernel(RenderBwdArgs a) {
     pdl_enter();
     // RB_BATCH entries are staged per round; most tiles need a single round (max n_contrib is a few hundred): the four
@@ -274,7 +280,12 @@ __global__ void __launch_bounds__(RB_THREADS, RB_OCC) render_backward_kernel(Ren
                 const int id = (int)(pos < len_a ? a.point_list[range.x + pos] : a.point_list_b[start_b + (pos - len_a)]);
                 const float4 r0 = __ldg(&a.rec[3 * (size_t)id]);
                 const float4 r1 = __ldg(&a.rec[3 * (size_t)id + 1]);
-                const float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
+                float4 r2 = __ldg(&a.rec[3 * (size_t)id + 2]);
+                if constexpr (EXTRA) {
+                    r2.x = __ldg(&a.extra_colors[3 * (size_t)id]);
+                    r2.y = __ldg(&a.extra_colors[3 * (size_t)id + 1]);
+                    r2.z = __ldg(&a.extra_colors[3 * (size_t)id + 2]);
+                }
                 float4 *dst = reinterpret_cast<float4 *>(&s_sp[slot]);
                 dst[0] = make_float4(r0.x, r0.x, r0.y, r0.y);
                 dst[1] = make_float4(r0.z, r0.z, -r0.w, -r0.w);
@@ -357,20 +368,28 @@ __global__ void __launch_bounds__(RB_THREADS, RB_OCC) render_backward_kernel(Ren
             float v[9] = {p0.x + p0.y, p1.x + p1.y, p2.x + p2.y, p3.x + p3.y, p4.x + p4.y,
                           p5.x + p5.y, p6.x + p6.y, p7.x + p7.y, p8.x + p8.y};
             const float total = warp_reduce9(v, lane);
-            if (my_slot >= 0) atomicAdd(&a.gacc[(size_t)__float_as_int(q4.z) * DQO_GACC_FLOATS + my_slot], (double)total);
+            if constexpr (EXTRA) {
+                if (my_slot >= 6) atomicAdd(&a.cacc[(size_t)__float_as_int(q4.z) * 4 + (my_slot - 6)], (double)total);
+                else if (my_slot >= 0) atomicAdd(&a.gacc[(size_t)__float_as_int(q4.z) * DQO_GACC_FLOATS + my_slot], (double)total);
+            } else {
+                if (my_slot >= 0) atomicAdd(&a.gacc[(size_t)__float_as_int(q4.z) * DQO_GACC_FLOATS + my_slot], (double)total);
+            }
             if (lane == 0) a.touched[__float_as_int(q4.z)] = 1;
         }
     }
+    if constexpr (!EXTRA) { // (the extra image carries no depth output)
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int ly = ly0 + 4 * h;
-        const uint32_t py = tile_y * DQO_TILE + ly;
-        if (!(pix_x < (uint32_t)a.W && py < (uint32_t)a.H)) continue;
-        const size_t pid = (size_t)a.W * py + pix_x;
-        const int gid = a.hit_image[pid];
-        if (gid >= 0)
-            bwd_depth_path(a.scales, a.rotations, a.means3D, a.view, a.hit_geo, a.plane, (size_t)tile * 256 + ly * 16 + lx,
-                           a.gacc, a.touched, gid, a.dL_ddepth[pid], pix_x, py, a.fx, a.fy, a.cx, a.cy, a.depth_thr, a.normal_thr);
+        for (int h = 0; h < 2; h++) {
+            const int ly = ly0 + 4 * h;
+            const uint32_t py = tile_y * DQO_TILE + ly;
+            if (!(pix_x < (uint32_t)a.W && py < (uint32_t)a.H)) continue;
+            const size_t pid = (size_t)a.W * py + pix_x;
+            const int gid = a.hit_image[pid];
+            if (gid >= 0)
+                bwd_depth_path(a.scales, a.rotations, a.means3D, a.view, a.hit_geo, a.plane, (size_t)tile * 256 + ly * 16 + lx,
+                               a.gacc, a.touched, gid, a.dL_ddepth[pid], pix_x, py, a.fx, a.fy, a.cx, a.cy, a.depth_thr,
+                               a.normal_thr);
+        }
     }
 }
 
@@ -394,6 +413,10 @@ struct GaussBwdArgs {
     // dqo_rast_settings.geom_clean == 2 (nullptr otherwise): out_nz[i] != 0 where the previous call wrote a non-zero row
     // into the caller's gradient tensors; rows that were zero and stay zero are not written again.
     uint8_t *out_nz;
+    // extra colour set (see RenderBwdArgs): accumulators f64[4] per Gaussian, consumed and cleared like gacc; the gradient
+    // w.r.t. the extra colours [P,3] is written under the same rules as the other rows (nullptr: none)
+    double *cacc;
+    float *dL_dextra;
 };
 
 __device__ __constant__ float B_SH_C0 = 0.28209479177387814f;
@@ -443,6 +466,17 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
     bool nz = false;
 #pragma unroll
     for (int k = 0; k < DQO_GACC_FLOATS; k++) nz |= (g[k] != 0.f);
+    float ex[3] = {0.f, 0.f, 0.f};
+    if (a.cacc && active) {
+        double2 *cp = reinterpret_cast<double2 *>(a.cacc + (size_t)idx * 4);
+        const double2 c0 = cp[0], c1 = cp[1];
+        ex[0] = (float)c0.x; ex[1] = (float)c0.y; ex[2] = (float)c1.x;
+        if (ex[0] != 0.f || ex[1] != 0.f || ex[2] != 0.f) {
+            nz = true;
+            cp[0] = make_double2(0.0, 0.0);
+            cp[1] = make_double2(0.0, 0.0);
+        }
+    }
     const bool need = active && nz;
     if (active) a.touched[idx] = 0;
     if (need) { // leave the accumulator clean for the next backward pass
@@ -780,6 +814,11 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
     }
     if (!write_out) return;
 
+    if (a.dL_dextra) {
+        a.dL_dextra[3 * idx] = ex[0];
+        a.dL_dextra[3 * idx + 1] = ex[1];
+        a.dL_dextra[3 * idx + 2] = ex[2];
+    }
     if (a.dL_dmeans2D) {
         a.dL_dmeans2D[3 * idx] = g[0];
         a.dL_dmeans2D[3 * idx + 1] = g[1];
@@ -820,7 +859,7 @@ int rast_backward_impl(const dqo_rast_settings *s, const float *background, cons
                        const float *dL_dout_depth, const int32_t *hit_image, float *dL_dmeans2D, float *dL_dconic,
                        float *dL_dopacity, float *dL_dcolors, float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh,
                        float *dL_dscales, float *dL_drotations, uint8_t *ever, uint32_t *ever_list,
-                       int32_t *ever_count, void *stream_);
+                       int32_t *ever_count, void *stream_, const ExtraBlendGrad *extra);
 }
 
 extern "C" int dqo_rast_geom_init(int32_t P, void *geom_buffer, void *stream_) {
@@ -852,7 +891,7 @@ extern "C" int dqo_rast_backward(const dqo_rast_settings *s, const float *backgr
                               viewmatrix, projmatrix, campos, radii, geom_buffer, binning_buffer, capacity, image_buffer,
                               status, dL_dout_color, dL_dout_depth, hit_image, dL_dmeans2D, dL_dconic, dL_dopacity,
                               dL_dcolors, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, nullptr, nullptr, nullptr,
-                              stream_);
+                              stream_, nullptr);
 }
 
 int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background, const float *means3D,
@@ -864,7 +903,8 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
                                  const float *dL_dout_depth, const int32_t *hit_image, float *dL_dmeans2D,
                                  float *dL_dconic, float *dL_dopacity, float *dL_dcolors, float *dL_dmeans3D,
                                  float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
-                                 uint8_t *ever, uint32_t *ever_list, int32_t *ever_count, void *stream_) {
+                                 uint8_t *ever, uint32_t *ever_list, int32_t *ever_count, void *stream_,
+                                 const ExtraBlendGrad *extra) {
     cudaStream_t stream = (cudaStream_t)stream_;
     pdl_scope(s ? s->P : 0);
     if (!s || s->P < 0) {
@@ -918,8 +958,19 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     ra.plane = (size_t)IL.T * 256;
     ra.dL_dpix = dL_dout_color; ra.dL_ddepth = dL_dout_depth; ra.hit_image = hit_image; ra.gacc = gacc;
     ra.touched = (uint8_t *)(geom + GL.touched);
-    launch_pdl(render_backward_kernel, dim3(IL.T), dim3(RB_THREADS), 0, stream, ra);
+    ra.extra_colors = nullptr; ra.cacc = nullptr;
+    launch_pdl(render_backward_kernel<false>, dim3(IL.T), dim3(RB_THREADS), 0, stream, ra);
     DQO_LAUNCH_CHECK("render backward", s->debug, stream);
+    if (extra) { // second colour set over the same lists: its image gradient, its colours, its own colour accumulators
+        if (!extra->colors || !extra->dL_dpix || !extra->cacc || !extra->dL_dcolors) {
+            set_error("dqo_rast_backward: incomplete extra colour set");
+            return DQO_ERR_INVALID_ARG;
+        }
+        RenderBwdArgs rx = ra;
+        rx.dL_dpix = extra->dL_dpix; rx.extra_colors = extra->colors; rx.cacc = extra->cacc;
+        launch_pdl(render_backward_kernel<true>, dim3(IL.T), dim3(RB_THREADS), 0, stream, rx);
+        DQO_LAUNCH_CHECK("render backward (extra colours)", s->debug, stream);
+    }
     stage_mark(stream, ST_RENDER_BWD);
 
     GaussBwdArgs ga;
@@ -934,6 +985,8 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     ga.dL_dmeans2D = dL_dmeans2D; ga.dL_dconic = dL_dconic; ga.dL_dopacity = dL_dopacity; ga.dL_dcolors = dL_dcolors;
     ga.dL_dmeans3D = dL_dmeans3D; ga.dL_dcov3D = dL_dcov3D; ga.dL_dsh = (s->M > 0) ? dL_dsh : nullptr;
     ga.dL_dscales = dL_dscales; ga.dL_drot = dL_drotations;
+    ga.cacc = extra ? extra->cacc : nullptr;
+    ga.dL_dextra = extra ? extra->dL_dcolors : nullptr;
     ga.ever = ever;
     ga.out_nz = (s->geom_clean == 2 && !ever) ? (uint8_t *)(geom + GL.out_nz) : nullptr;
     ga.ever_list = (ever && ever_list && ever_count) ? ever_list : nullptr;

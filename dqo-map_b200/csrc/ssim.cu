@@ -1,0 +1,247 @@
+// SSIM term of Mapping.loss_update: in the mask-less (global) pass the reference adds
+//   ssim_weight * (1 - ssim(image, gt))                      SLAM/multiprocess/mapper.py:839-841, :874
+// with ssim = utils/loss_utils.py:61-99: 11x11 Gaussian window (sigma 1.5, the outer product of a normalised 1-D
+// window, loss_utils.py:42-58), zero padding, per channel (groups = 3), C1 = 0.01^2, C2 = 0.03^2, mean over 3*H*W.
+// The window is applied separably (11 + 11 taps instead of 121): the reference rounds the outer product to float32
+// before convolving, which this form does not reproduce -- measured effect on a smooth 1200x680 pair (the sensitive
+// case, see ssim_window): 4e-7 on the loss, 5e-6 of the largest gradient element (tests/test_gpu_ssim.py).
+// The reference spends 5 depthwise conv2d + ~15 elementwise kernels forward and their autograd twins backward; here
+// the value and the gradient image d(weight * (1 - mean ssim)) / d image take two launches:
+//
+//   ssim_stats_kernel  per 16x16 tile and channel: the five windowed moments (separable: 11 + 11 taps through shared
+//                      memory), the SSIM value (fp64 block partial, fixed-order final sum: deterministic) and its three
+//                      partial derivatives w.r.t. the windowed moments mu1, E[x^2], E[xy] -> three maps
+//   ssim_grad_kernel   the same window applied to the three maps (the adjoint of a symmetric zero-padded convolution is
+//                      the convolution itself): dL/dx = scale * (w * dmu1 + 2 x (w * dsxx) + y (w * dsxy)), written or
+//                      accumulated into the colour-gradient image the backward blend reads
+#include "common.cuh"
+#include <math.h>
+#include <string.h>
+
+namespace dqo {
+
+#define SS_T 16
+#define SS_R 5
+#define SS_IN (SS_T + 2 * SS_R) // 26
+#define SS_PITCH (SS_IN + 1)
+
+struct SsimArgs {
+    int W, H;
+    const float *img; // [3,H,W]
+    const float *gt;  // [H,W,3]
+    float w[11];
+    float *maps;      // [3 maps][3 channels][H][W]
+    double *partial;  // one per block of ssim_stats_kernel
+    int nparts;
+    float *dimg;      // [3,H,W]
+    float scale;      // -weight / (3 H W)
+    int accumulate;
+    float weight;
+    float *loss_out;  // {1 - mean ssim, weight * (1 - mean ssim)}
+};
+
+__global__ void __launch_bounds__(SS_T * SS_T) ssim_stats_kernel(SsimArgs a) {
+    pdl_enter();
+    __shared__ float s_x[SS_IN][SS_PITCH], s_y[SS_IN][SS_PITCH];
+    __shared__ float s_h[5][SS_IN][SS_T];
+    __shared__ double s_red[SS_T * SS_T / 32];
+    const int c = blockIdx.z;
+    const int x0 = blockIdx.x * SS_T - SS_R, y0 = blockIdx.y * SS_T - SS_R;
+    const int tid = threadIdx.y * SS_T + threadIdx.x;
+    const size_t HW = (size_t)a.W * a.H;
+    for (int i = tid; i < SS_IN * SS_IN; i += SS_T * SS_T) {
+        const int r = i / SS_IN, q = i - r * SS_IN;
+        const int gx = x0 + q, gy = y0 + r;
+        float vx = 0.f, vy = 0.f;
+        if (gx >= 0 && gx < a.W && gy >= 0 && gy < a.H) {
+            const size_t p = (size_t)gy * a.W + gx;
+            vx = a.img[c * HW + p];
+            vy = __ldg(&a.gt[3 * p + c]);
+        }
+        s_x[r][q] = vx;
+        s_y[r][q] = vy;
+    }
+    __syncthreads();
+    for (int i = tid; i < SS_IN * SS_T; i += SS_T * SS_T) {
+        const int r = i / SS_T, q = i - r * SS_T;
+        float m1 = 0.f, m2 = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const float wk = a.w[k], vx = s_x[r][q + k], vy = s_y[r][q + k];
+            m1 = fmaf(wk, vx, m1);
+            m2 = fmaf(wk, vy, m2);
+            xx = fmaf(wk, vx * vx, xx);
+            yy = fmaf(wk, vy * vy, yy);
+            xy = fmaf(wk, vx * vy, xy);
+        }
+        s_h[0][r][q] = m1; s_h[1][r][q] = m2; s_h[2][r][q] = xx; s_h[3][r][q] = yy; s_h[4][r][q] = xy;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int gx = blockIdx.x * SS_T + tx, gy = blockIdx.y * SS_T + ty;
+    const bool inside = gx < a.W && gy < a.H;
+    float mu1 = 0.f, mu2 = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; k++) {
+        const float wk = a.w[k];
+        mu1 = fmaf(wk, s_h[0][ty + k][tx], mu1);
+        mu2 = fmaf(wk, s_h[1][ty + k][tx], mu2);
+        sxx = fmaf(wk, s_h[2][ty + k][tx], sxx);
+        syy = fmaf(wk, s_h[3][ty + k][tx], syy);
+        sxy = fmaf(wk, s_h[4][ty + k][tx], sxy);
+    }
+    double s_val = 0.0;
+    if (inside) {
+        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+        const float sig1 = sxx - mu1_sq, sig2 = syy - mu2_sq, sig12 = sxy - mu12;
+        const float A = 2.f * mu12 + C1, B = 2.f * sig12 + C2;
+        const float Cc = mu1_sq + mu2_sq + C1, D = sig1 + sig2 + C2;
+        const float inv = 1.0f / (Cc * D);
+        const float S = (A * B) * inv;
+        s_val = (double)S;
+        // partial derivatives of S w.r.t. the windowed moments mu1, E[x^2] (sxx), E[xy] (sxy)
+        const float dmu1 = (2.f * mu2 * (B - A) - 2.f * mu1 * S * (D - Cc)) * inv;
+        const float dsxx = -S / D;
+        const float dsxy = 2.f * A * inv;
+        const size_t p = (size_t)gy * a.W + gx;
+        a.maps[(0 * 3 + c) * HW + p] = dmu1;
+        a.maps[(1 * 3 + c) * HW + p] = dsxx;
+        a.maps[(2 * 3 + c) * HW + p] = dsxy;
+    }
+    for (int o = 16; o > 0; o >>= 1) s_val += __shfl_xor_sync(0xFFFFFFFFu, s_val, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = s_val;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int k = 0; k < SS_T * SS_T / 32; k++) t += s_red[k];
+        a.partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(SS_T * SS_T) ssim_grad_kernel(SsimArgs a) {
+    pdl_enter();
+    __shared__ float s_m[3][SS_IN][SS_PITCH];
+    __shared__ float s_h[3][SS_IN][SS_T];
+    __shared__ double s_red[SS_T * SS_T / 32];
+    const int c = blockIdx.z;
+    const int x0 = blockIdx.x * SS_T - SS_R, y0 = blockIdx.y * SS_T - SS_R;
+    const int tid = threadIdx.y * SS_T + threadIdx.x;
+    const size_t HW = (size_t)a.W * a.H;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { // the value: fixed-order sum of the block partials
+        double t = 0.0;
+        for (int b = tid; b < a.nparts; b += SS_T * SS_T) t += a.partial[b];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+        if ((tid & 31) == 0) s_red[tid >> 5] = t;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int k = 0; k < SS_T * SS_T / 32; k++) s += s_red[k];
+            const float loss = (float)(1.0 - s / (3.0 * (double)HW));
+            a.loss_out[0] = loss;
+            a.loss_out[1] = a.weight * loss;
+        }
+    }
+    for (int i = tid; i < SS_IN * SS_IN; i += SS_T * SS_T) {
+        const int r = i / SS_IN, q = i - r * SS_IN;
+        const int gx = x0 + q, gy = y0 + r;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        if (gx >= 0 && gx < a.W && gy >= 0 && gy < a.H) {
+            const size_t p = (size_t)gy * a.W + gx;
+            v0 = a.maps[(0 * 3 + c) * HW + p];
+            v1 = a.maps[(1 * 3 + c) * HW + p];
+            v2 = a.maps[(2 * 3 + c) * HW + p];
+        }
+        s_m[0][r][q] = v0; s_m[1][r][q] = v1; s_m[2][r][q] = v2;
+    }
+    __syncthreads();
+    for (int i = tid; i < SS_IN * SS_T; i += SS_T * SS_T) {
+        const int r = i / SS_T, q = i - r * SS_T;
+        float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const float wk = a.w[k];
+            h0 = fmaf(wk, s_m[0][r][q + k], h0);
+            h1 = fmaf(wk, s_m[1][r][q + k], h1);
+            h2 = fmaf(wk, s_m[2][r][q + k], h2);
+        }
+        s_h[0][r][q] = h0; s_h[1][r][q] = h1; s_h[2][r][q] = h2;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int gx = blockIdx.x * SS_T + tx, gy = blockIdx.y * SS_T + ty;
+    if (!(gx < a.W && gy < a.H)) return;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; k++) {
+        const float wk = a.w[k];
+        c0 = fmaf(wk, s_h[0][ty + k][tx], c0);
+        c1 = fmaf(wk, s_h[1][ty + k][tx], c1);
+        c2 = fmaf(wk, s_h[2][ty + k][tx], c2);
+    }
+    const size_t p = (size_t)gy * a.W + gx;
+    const float x = a.img[c * HW + p], y = __ldg(&a.gt[3 * p + c]);
+    const float g = a.scale * (c0 + 2.f * x * c1 + y * c2);
+    float *dst = a.dimg + c * HW + p;
+    *dst = a.accumulate ? (*dst + g) : g;
+}
+
+// loss_utils.py:42-49: torch.Tensor([exp(-(x - 5)^2 / (2 * 1.5^2))]) / its float32 sum.  The value of SSIM on smooth images is
+// extremely sensitive to the normalisation of the window (E[x^2] - mu^2 in flat regions is the deviation of the window
+// sum from 1, times x^2, against C2 = 9e-4: one float32 ulp in the sum moves the loss by 1e-5), so the taps are the exact
+// bits torch produces (its vectorised float32 sum differs from a sequential one by one ulp); tests/test_ssim_oracle.py
+// checks them against torch through dqo_ssim_window.
+static void ssim_window(float *w) {
+    static const uint32_t bits[11] = {0x3a86cab6u, 0x3bf8ff01u, 0x3d13758cu, 0x3ddff87fu, 0x3e5a1e1fu, 0x3e8832b0u,
+                                      0x3e5a1e1fu, 0x3ddff87fu, 0x3d13758cu, 0x3bf8ff01u, 0x3a86cab6u};
+    memcpy(w, bits, sizeof(bits));
+}
+
+static size_t ssim_partial_bytes(int W, int H) {
+    const size_t blocks = (size_t)((W + SS_T - 1) / SS_T) * ((H + SS_T - 1) / SS_T) * 3;
+    return align_up(blocks * sizeof(double), 256);
+}
+
+int ssim_loss_impl(int32_t W, int32_t H, const float *image, const float *gt_color, float weight, float *dL_dimage,
+                   int32_t accumulate, float *loss_out, void *workspace, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (W <= 0 || H <= 0 || !image || !gt_color || !dL_dimage || !loss_out || !workspace) {
+        set_error("dqo_ssim_loss: invalid argument");
+        return DQO_ERR_INVALID_ARG;
+    }
+    SsimArgs a;
+    a.W = W; a.H = H; a.img = image; a.gt = gt_color;
+    ssim_window(a.w);
+    const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, 3), block(SS_T, SS_T);
+    a.partial = (double *)workspace;
+    a.maps = (float *)((char *)workspace + ssim_partial_bytes(W, H));
+    a.nparts = (int)(grid.x * grid.y * grid.z);
+    a.dimg = dL_dimage;
+    a.scale = (float)(-(double)weight / (3.0 * (double)W * (double)H));
+    a.accumulate = accumulate;
+    a.weight = weight;
+    a.loss_out = loss_out;
+    launch_pdl(ssim_stats_kernel, grid, block, 0, stream, a);
+    launch_pdl(ssim_grad_kernel, grid, block, 0, stream, a);
+    DQO_LAUNCH_CHECK("ssim loss", 0, stream);
+    note_launch();
+    return DQO_OK;
+}
+
+} // namespace dqo
+
+using namespace dqo;
+
+extern "C" size_t dqo_ssim_workspace_bytes(int32_t W, int32_t H) {
+    if (W <= 0 || H <= 0) return 0;
+    return ssim_partial_bytes(W, H) + (size_t)9 * W * H * sizeof(float);
+}
+
+extern "C" void dqo_ssim_window(float *window11) {
+    if (window11) ssim_window(window11);
+}
+
+extern "C" int dqo_ssim_loss(int32_t W, int32_t H, const float *image, const float *gt_color, float weight,
+                             float *dL_dimage, int32_t accumulate, float *loss_out, void *workspace, void *stream) {
+    return ssim_loss_impl(W, H, image, gt_color, weight, dL_dimage, accumulate, loss_out, workspace, stream);
+}

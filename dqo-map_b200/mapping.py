@@ -63,6 +63,37 @@ def masked_l1_loss(image, depth, hit_depth, gt_color, gt_depth, render_mask=None
                            depth_err_thres)
 
 
+class _SSIMLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, gt_color):
+        L = lib()
+        dev = image.device
+        H, W = image.shape[1], image.shape[2]
+        image_c = image.contiguous()
+        d_img = torch.empty_like(image_c)
+        out = torch.empty((2,), dtype=torch.float32, device=dev)
+        ws = torch.empty((L.dqo_ssim_workspace_bytes(W, H),), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(L.dqo_ssim_loss(W, H, ptr(image_c), ptr(gt_color.contiguous()), 1.0, ptr(d_img), 0, ptr(out), ptr(ws),
+                                  _stream()), "dqo_ssim_loss")
+        ctx.save_for_backward(d_img)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_img,) = ctx.saved_tensors
+        return d_img * g, None
+
+
+def ssim_loss(image, gt_color):
+    """1 - ssim(image, gt) as `Mapping.loss_update` adds it in the mask-less global pass (mapper.py:839-841;
+    utils/loss_utils.py:61-99: 11x11 Gaussian window, zero padding, mean over 3*H*W), value and image gradient in two
+    launches.  image [3,H,W] (differentiable), gt_color [H,W,3] float32 CUDA tensors.  Returns a device scalar."""
+    if image.dim() != 3 or image.shape[0] != 3 or tuple(gt_color.shape) != (image.shape[1], image.shape[2], 3):
+        raise ValueError("ssim_loss expects image [3,H,W] and gt_color [H,W,3]")
+    return _SSIMLoss.apply(image, gt_color)
+
+
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam semantics (amsgrad=False, weight_decay=0, maximize=False) in ONE launch over all groups."""
 
@@ -164,14 +195,18 @@ class FusedMappingStep:
     backward, activation backward, the attach term and Adam all run inside the library on the raw parameter tensors,
     which are updated in place (opt-in).
 
-    Loss terms: masked L1 colour, masked L1 depth and -- after `begin_window(attach=True)` -- the attach term
-    (mapper.py:810-829).  NOT covered: the SSIM term of the mask-less final global pass (:841), the normal term (weight 0
-    in every shipped config) and the semantic / instance colour terms (:876-903); use `MappingStep` (operator path,
-    differentiable torch tensors) for those configurations.
+    Loss terms: masked L1 colour, masked L1 depth, after `begin_window(attach=True)` the attach term (mapper.py:810-829),
+    with `ssim_weight` > 0 the SSIM term -- like the reference only for calls without a render_mask (:839-841, the final
+    global pass) -- and, when `params` holds "semantics" and the call passes `gt_semantic`, the semantic colour term
+    `semantic_weight` * masked L1 of the semantic image (:877-880), whose gradient updates the semantic colours (group
+    "semantics_color", lrs["semantics"]) and the geometry.  NOT covered: the normal term (weight 0 in every shipped
+    config).  The instance term (:881-902, Method 2) is an L1 on T_map, whose gradient the rasterizer's backward drops
+    (diff_gaussian_rasterization_depth/__init__.py:184): it never changes a parameter and is not evaluated here.
+    `loss` holds {total, colour, depth, attach, 1 - ssim, semantic L1, 0, 0}.
 
     params: dict of raw contiguous float32 CUDA tensors xyz [P,3], f_dc [P,1,3], f_rest [P,M-1,3], opacity [P,1],
-    scaling [P,3], rotation [P,4] (the tensors of GaussianPointCloud.parametrize); lrs: dict name -> lr (re-read on
-    every call).  `__call__` returns device tensors (total, colour, depth loss); reading them is the only
+    scaling [P,3], rotation [P,4] and optionally semantics [P,3] (the tensors of GaussianPointCloud.parametrize); lrs:
+    dict name -> lr (re-read on every call).  `__call__` returns device tensors (total, colour, depth loss); reading them is the only
     synchronisation.  The Adam step number lives on the device; `check()` reports how many steps the device skipped
     since the last check (instance overflow) -- the counter is sticky, so checking once after a window is enough.
     `graph(...)` captures the step of one keyframe into a CUDA graph (one launch per iteration instead of ~45)."""
@@ -180,9 +215,11 @@ class FusedMappingStep:
 
     def __init__(self, params, lrs, width, height, color_weight=0.8, depth_weight=1.0, depth_err_thres=0.1,
                  confidence=None, betas=(0.9, 0.999), eps=1e-15, capacity=None, need_n_touched=True,
-                 front_instances=0, back_instances=0):
+                 front_instances=0, back_instances=0, ssim_weight=0.0, semantic_weight=0.1):
         L = lib()
         self.p = params
+        self.ssim_w, self.sem_w = float(ssim_weight), float(semantic_weight)
+        self.has_sem = params.get("semantics") is not None and params["semantics"].numel() > 1
         self.front, self.back = int(front_instances), int(back_instances)
         for k in self.ORDER:
             t = params[k]
@@ -200,6 +237,11 @@ class FusedMappingStep:
         self.confidence = confidence
         self.need_n_touched = need_n_touched
         self.state = {k: (torch.zeros_like(params[k]), torch.zeros_like(params[k])) for k in self.ORDER}
+        if self.has_sem:
+            t = params["semantics"]
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (self.P, 3)):
+                raise ValueError("FusedMappingStep expects semantics as a contiguous float32 CUDA tensor [P,3]")
+            self.state["semantics"] = (torch.zeros_like(t), torch.zeros_like(t))
         # one byte per Gaussian: has it ever received a non-zero gradient?  (zero-initialised with the moments; Gaussians
         # that never have are skipped by the backward's gradient writes and by the optimiser, see dqo_map_params.ever)
         self.ever = torch.zeros(self.P, dtype=torch.uint8, device=self.dev)
@@ -214,7 +256,7 @@ class FusedMappingStep:
         self._kf_cache = {}
         self.capacity = int(capacity) if capacity else max(8 * self.P, 1 << 16)
         self._alloc()
-        self.loss = torch.zeros(4, dtype=torch.float32, device=self.dev)
+        self.loss = torch.zeros(8, dtype=torch.float32, device=self.dev)
         self._loss_views = (self.loss[0], self.loss[1], self.loss[2])
         self.counts = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.status = torch.zeros(_lib.ST_WORDS, dtype=torch.int32, device=self.dev)
@@ -252,6 +294,8 @@ class FusedMappingStep:
     def _map_params(self):
         """ctypes view of the parameter / moment tensors; rebuilt when a tensor was replaced or a learning rate changed."""
         lrs = tuple(float(self.lrs[k]) for k in self.ORDER)
+        if self.has_sem:
+            lrs = lrs + (float(self.lrs["semantics"]), self.p["semantics"].data_ptr())
         key = tuple(self.p[k].data_ptr() for k in self.ORDER) + lrs + (
             self.confidence.data_ptr() if self.confidence is not None else 0,
             self.init["xyz"].data_ptr() if self.init is not None else 0, self.attach_weight, self.attach_thres)
@@ -274,6 +318,10 @@ class FusedMappingStep:
                 mp.attach_count = ptr(self.attach_count)
             mp.attach_weight, mp.attach_opacity_thres = self.attach_weight, self.attach_thres
             mp.step_state = ptr(self.step_state)
+            if self.has_sem:
+                mp.semantics = ptr(self.p["semantics"])
+                mp.semantics_exp_avg, mp.semantics_exp_avg_sq = (ptr(t) for t in self.state["semantics"])
+                mp.lr_semantics = float(self.lrs["semantics"])
             self._mp, self._mp_key = mp, key
         return self._mp
 
@@ -287,27 +335,31 @@ class FusedMappingStep:
             check(lib().dqo_mapping_step_workspace_init(self.P, self.M, self.W, self.H, self.capacity, ptr(self.ws), _stream()),
                   "dqo_mapping_step_workspace_init")
 
-    def _keyframe(self, rs, tile_mask, gt_color, gt_depth, render_mask):
+    def _keyframe(self, rs, tile_mask, gt_color, gt_depth, render_mask, gt_semantic=None):
         from .rasterizer import _make_settings
         # the ctypes views of a keyframe (settings + pointers) are cached per keyframe: a mapping window revisits the
         # same few keyframes, and building the structs costs more host time than launching the step.  Inputs must be
         # contiguous (no hidden copies that an in-place update of the source would miss).
         key = (id(rs), tile_mask.data_ptr(), gt_color.data_ptr(), gt_depth.data_ptr(),
                render_mask.data_ptr() if render_mask is not None else 0, self.front, self.back, self.need_n_touched,
-               self.cw, self.dw, self.thr)
+               self.cw, self.dw, self.thr, self.ssim_w, self.sem_w, gt_semantic.data_ptr() if gt_semantic is not None else 0)
         hit = self._kf_cache.get(key)
         if hit is None:
             mask = render_mask
             if mask is not None and mask.dtype == torch.bool:
                 mask = mask.view(torch.uint8)
-            for name, t in (("gt_color", gt_color), ("gt_depth", gt_depth), ("render_mask", mask), ("tile_mask", tile_mask)):
+            if gt_semantic is not None and not self.has_sem:
+                raise ValueError("gt_semantic given but params has no 'semantics' tensor")
+            for name, t in (("gt_color", gt_color), ("gt_depth", gt_depth), ("render_mask", mask), ("tile_mask", tile_mask),
+                            ("gt_semantic", gt_semantic)):
                 if t is not None and not t.is_contiguous():
                     raise ValueError("FusedMappingStep expects a contiguous %s" % name)
             if mask is not None and mask.dtype != torch.uint8:
                 raise TypeError("render_mask must be a bool or uint8 tensor")
-            tensors = (gt_color, gt_depth, mask, tile_mask, rs)  # kept alive with the cache entry
+            tensors = (gt_color, gt_depth, mask, tile_mask, rs, gt_semantic)  # kept alive with the cache entry
             kf = _lib.Keyframe(ptr(gt_color), ptr(gt_depth), ptr(mask), ptr(tile_mask), ptr(rs.viewmatrix),
-                               ptr(rs.projmatrix), ptr(rs.campos), ptr(rs.bg), self.cw, self.dw, self.thr)
+                               ptr(rs.projmatrix), ptr(rs.campos), ptr(rs.bg), self.cw, self.dw, self.thr, self.ssim_w,
+                               self.sem_w if gt_semantic is not None else 0.0, ptr(gt_semantic))
             s = _make_settings(self.P, int(rs.sh_degree), self.M, self.W, self.H, rs.tanfovx, rs.tanfovy, rs.cx, rs.cy,
                                rs.scale_modifier, rs.color_sigma, rs.opaque_threshold, rs.depth_threshold,
                                rs.normal_threshold, rs.T_threshold, rs.prefiltered, rs.debug, self.need_n_touched,
@@ -317,10 +369,11 @@ class FusedMappingStep:
             hit = self._kf_cache[key] = (s, kf, tensors)
         return hit[0], hit[1]
 
-    def __call__(self, rs, tile_mask, gt_color, gt_depth, render_mask=None):
-        """rs: GaussianRasterizationSettings of the keyframe (as built by SLAM/render.py:142-162)."""
+    def __call__(self, rs, tile_mask, gt_color, gt_depth, render_mask=None, gt_semantic=None):
+        """rs: GaussianRasterizationSettings of the keyframe (as built by SLAM/render.py:142-162); gt_semantic: [H,W,3]
+        image_input["semantics_color"] (enables the semantic term) or None."""
         mp = self._map_params()
-        s, kf = self._keyframe(rs, tile_mask, gt_color, gt_depth, render_mask)
+        s, kf = self._keyframe(rs, tile_mask, gt_color, gt_depth, render_mask, gt_semantic)
         args = (s, mp, kf, 0, float(self.betas[0]), float(self.betas[1]), float(self.eps), ptr(self.ws),
                 self.capacity, ptr(self.loss), ptr(self.counts), ptr(self.status))
         if torch.cuda.current_device() == self.dev.index:  # the common case: no device switch on the hot path
@@ -330,18 +383,18 @@ class FusedMappingStep:
                 check(lib().dqo_mapping_step(*args, _stream()), "dqo_mapping_step")
         return self._loss_views
 
-    def graph(self, rs, tile_mask, gt_color, gt_depth, render_mask=None, warmup=True):
+    def graph(self, rs, tile_mask, gt_color, gt_depth, render_mask=None, warmup=True, gt_semantic=None):
         """CUDA graph of this keyframe's step: `g = step.graph(...); g.replay()` runs one iteration with a single launch.
         Possible because nothing in the step depends on a host value that changes between iterations (the Adam step
         number is a device counter).  The tensors of the keyframe and the parameters must stay where they are; learning
         rates and loss weights are frozen into the graph (re-capture after changing them).  With warmup=True one real
         step is taken first (on the current stream) so that lazily created resources exist before the capture."""
         if warmup:
-            self(rs, tile_mask, gt_color, gt_depth, render_mask)
+            self(rs, tile_mask, gt_color, gt_depth, render_mask, gt_semantic)
             torch.cuda.current_stream().synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, capture_error_mode="relaxed"):
-            self(rs, tile_mask, gt_color, gt_depth, render_mask)
+            self(rs, tile_mask, gt_color, gt_depth, render_mask, gt_semantic)
         return g
 
     def check(self, auto_resize=False):

@@ -338,15 +338,29 @@ typedef struct dqo_adam_tensor {
 } dqo_adam_tensor;
 #define DQO_ADAM_MAX_TENSORS 16
 /* betas / eps / lr are doubles like the Python floats torch receives ((float)(1 - beta2) != 1 - (float)beta2). */
+/* SSIM term of the mask-less global pass of loss_update: ssim_weight * (1 - ssim(image, gt)) (mapper.py:839-841, :874;
+ * ssim = utils/loss_utils.py:61-99: 11x11 Gaussian window, sigma 1.5, zero padding, per channel, C1 = 0.01^2,
+ * C2 = 0.03^2, mean over 3*H*W).  Two launches produce the value and d(weight * (1 - ssim)) / d image, which is written
+ * to (accumulate = 0) or added to (accumulate = 1) `dL_dimage`, e.g. on top of dqo_masked_l1_loss's colour gradient.
+ * loss_out: device float[2] = {1 - ssim, weight * (1 - ssim)}; deterministic (fixed-order fp64 reduction). */
+size_t dqo_ssim_workspace_bytes(int32_t W, int32_t H);
+/* The 11 taps of the 1-D window (host call, no GPU): the bits torch produces for loss_utils.py:42-49. */
+void dqo_ssim_window(float *window11);
+int dqo_ssim_loss(int32_t W, int32_t H, const float *image /* [3,H,W] */, const float *gt_color /* [H,W,3] */,
+                  float weight, float *dL_dimage /* [3,H,W] */, int32_t accumulate, float *loss_out, void *workspace,
+                  void *stream);
+
 int dqo_adam_step(const dqo_adam_tensor *tensors /* host array */, int32_t n_tensors, int32_t step, double beta1,
                   double beta2, double eps, float *confidence /* [P] or NULL */, int32_t conf_tensor, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused mapping iteration (opt-in).  One call enqueues, on one stream and without any host
  * synchronisation, what one iteration of Mapping.local_optimize does (SLAM/multiprocess/mapper.py:568-599 and
- * loss_update :799-928: masked L1 colour + depth loss and the attach term; NOT the SSIM term of the mask-less final global
- * pass :841, the normal term (weight 0 in every shipped config) or the semantic / instance colour terms :876-903 -- callers
- * that need those use the operator path, whose outputs are differentiable torch tensors): activations of the RAW parameters (exp / sigmoid / normalize,
+ * loss_update :799-928: masked L1 colour + depth loss, the attach term, the SSIM term of the mask-less final global pass
+ * :841 and the semantic colour term :877-880 -- see dqo_keyframe; NOT the normal term (weight 0 in every shipped config);
+ * the instance term :881-902 (Method 2) is an L1 on T_map, whose gradient the rasterizer's backward drops
+ * (diff_gaussian_rasterization_depth/__init__.py:184), i.e. a reported number without any effect on the parameters):
+ * activations of the RAW parameters (exp / sigmoid / normalize,
  * SLAM/gaussian_pointcloud.py:20-30, 724-826; the torch.cat of f_dc / f_rest is never materialised), rasterize
  * forward, masked L1 colour + depth loss, rasterize backward, activation backward and Adam (eps / betas / lrs as in
  * GaussianPointCloud.parametrize :331-378) on the raw parameters in place, plus the confidence bump (:909-910).
@@ -382,6 +396,11 @@ typedef struct dqo_map_params {
      * argument (CUDA-graph replayable) and a skipped step can neither be missed (sticky until the caller clears [1]) nor
      * advance the bias correction.  NULL: the `step` argument is used and nothing is counted. */
     int32_t *step_state;
+    /* Semantic colours [P,3] (GaussianPointCloud._semantics, parameter group "semantics_color" with lr semantic_lr,
+     * gaussian_pointcloud.py:371-378), their Adam moments and learning rate.  Used when the keyframe carries a semantic
+     * target (dqo_keyframe.gt_semantic); NULL otherwise. */
+    float *semantics, *semantics_exp_avg, *semantics_exp_avg_sq;
+    double lr_semantics;
 } dqo_map_params;
 typedef struct dqo_keyframe {
     const float *gt_color;      /* [H,W,3] */
@@ -390,12 +409,23 @@ typedef struct dqo_keyframe {
     const int32_t *tile_mask;   /* [ceil(H/16), ceil(W/16)] */
     const float *viewmatrix, *projmatrix, *campos, *background;
     float color_weight, depth_weight, depth_err_thres;
+    /* Optional terms of loss_update (0 / NULL = off).
+     * ssim_weight: adds ssim_weight * (1 - ssim(image, gt_color)); like the reference only when render_mask == NULL
+     *   (mapper.py:839-841, the final global pass); ignored for masked keyframes.
+     * gt_semantic + semantic_weight: adds semantic_weight * mean |semantic_seg - gt_semantic| over the render_mask pixels
+     *   (mapper.py:877-880).  The semantic image is the blend of dqo_map_params.semantics over the lists of the main render
+     *   (the reference runs the whole rasterizer a second time with colors_precomp, SLAM/render.py:227-246); its gradient
+     *   reaches the semantic colours and, through alpha and the 2-D geometry, every geometric parameter. */
+    float ssim_weight;
+    float semantic_weight;
+    const float *gt_semantic;   /* [H,W,3] or NULL */
 } dqo_keyframe;
 size_t dqo_mapping_step_workspace_bytes(int32_t P, int32_t M, int32_t W, int32_t H, int64_t instance_capacity);
 /* One-time initialisation of a freshly allocated step workspace: lets the step run with dqo_rast_settings.geom_clean = 1. */
 int dqo_mapping_step_workspace_init(int32_t P, int32_t M, int32_t W, int32_t H, int64_t instance_capacity, void *workspace,
                                     void *stream);
-/* loss_out: device float[4] {total, colour, depth, attach}; counts_out: device int32[2]; status: device int32[DQO_ST_WORDS]
+/* loss_out: device float[8] {total, colour, depth, attach, ssim (1 - ssim), semantic, 0, 0} -- `total` is the reference's
+ * `loss` (mapper.py:870-880, :904: every weighted term except the attach term); counts_out: device int32[2]; status: device int32[DQO_ST_WORDS]
  * (check DQO_ST_OVERFLOW together with the loss read-back; on overflow the render is invalid and the Adam update is
  * skipped on the device -- parameters and moments are untouched, repeat the step with a larger capacity and the same
  * `step` number: see mapping.FusedMappingStep.check).  * The list of non-empty tiles is not produced by the step: status[DQO_ST_TILE_NUM] stays 0.
