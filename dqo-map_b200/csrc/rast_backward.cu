@@ -417,6 +417,10 @@ struct GaussBwdArgs {
     // w.r.t. the extra colours [P,3] is written under the same rules as the other rows (nullptr: none)
     double *cacc;
     float *dL_dextra;
+    // 1: every block takes the thread-per-Gaussian branch (callers without persistent outputs: every row is written, zeros
+    // included, through the coalesced staged stores)
+    int force_dense;
+    int chunks; // 128-Gaussian chunks per block, 1 .. GB_MAX_CHUNKS
 };
 
 __device__ __constant__ float B_SH_C0 = 0.28209479177387814f;
@@ -433,20 +437,23 @@ __device__ __constant__ float B_SH_C3[7] = {-0.5900435899266435f, 2.890611442640
 // STAGED (M == 16, 16-byte aligned shs / dL_dsh): each warp moves its 32 x 192 B of SH coefficients in and its
 // 32 x 192 B of SH gradients out with coalesced 128-bit accesses through a padded shared-memory tile.
 // SHMODE 1: staged merged SH, 2: staged split f_dc / f_rest inputs (gradients are still written merged), 0: plain.
+//
+// One Gaussian per thread.  COMPACT = false: thread t of the warp owns Gaussian base_g + t (consecutive rows: the staged
+// paths can move whole 32-row blocks).  COMPACT = true: the warp's lanes own arbitrary (touched) Gaussians handed in through
+// `idx`, live lanes first; `nrow` live lanes; the staged paths then move single rows, addressed through a shuffle of idx.
+// Inlined at exactly ONE call site of the one kernel every caller launches (operator path, RasterPipeline, fused step), so a
+// Gaussian's gradients do not depend on which form processed it: separately inlined copies were optimised separately and
+// differed in FMA contraction (last-ulp differences between the pipeline and the operator path), and a non-inlined
+// function reads the kernel arguments through generic loads (-15 % on the small clouds of the object workload).
 template <int SHMODE>
-__global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussBwdArgs a) {
-    pdl_enter();
-    extern __shared__ float4 s_row[];
+__device__ __forceinline__ void gaussian_backward_body(const GaussBwdArgs &a, const int idx, const bool live, const int base_g,
+                                                    const int nrow, float4 *s_row, const bool COMPACT) {
     constexpr bool STAGED = SHMODE != 0;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 *wbuf = s_row + warp * 32 * GB_ROW_Q;
     float *wrest = reinterpret_cast<float *>(wbuf), *wdc = wrest + 1440;
-    const int base_g = blockIdx.x * blockDim.x + warp * 32;
-    const int nrow = min(32, a.P - base_g);
-    const bool live = idx < a.P;
     // only Gaussians the blend added to (a visible Gaussian that no pixel with a gradient saw has an all-zero record)
-    const bool active = live && a.touched[idx] != 0;
+    const bool active = live && (COMPACT || a.touched[idx] != 0);
     const int M = a.M;
     float g[DQO_GACC_FLOATS];
     if (active) {
@@ -485,7 +492,7 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
         for (int k = 0; k < 8; k++) gz[k] = make_double2(0.0, 0.0);
     }
     const unsigned need_rows = __ballot_sync(0xFFFFFFFFu, need);
-    const bool whole_block = nrow == 32 && __popc(need_rows) >= 12; // dense: the warp's block in 12 coalesced 128-bit loads
+    const bool whole_block = !COMPACT && nrow == 32 && __popc(need_rows) >= 12; // dense: the warp's block in 12 coalesced 128-bit loads
     if (SHMODE == 2 && need_rows) {
         if (whole_block) {
             const float4 *g4 = reinterpret_cast<const float4 *>(a.f_rest + (size_t)base_g * 45);
@@ -496,29 +503,44 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
             }
             const float4 *gd4 = reinterpret_cast<const float4 *>(a.shs + (size_t)base_g * 3);
             if (lane < 24) reinterpret_cast<float4 *>(wdc)[lane] = __ldg(gd4 + lane);
+        } else if (COMPACT) { // scattered rows: every lane fetches its own (48 independent loads in flight per lane; a
+            if (need) {       // row-by-row loop pays one memory latency per row)
+                const float *src = a.f_rest + (size_t)idx * 45;
+#pragma unroll
+                for (int k = 0; k < 45; k++) wrest[lane * 45 + k] = __ldg(src + k);
+#pragma unroll
+                for (int c = 0; c < 3; c++) wdc[lane * 3 + c] = __ldg(a.shs + (size_t)idx * 3 + c);
+            }
         } else { // sparse: only the needed rows, 180 + 12 contiguous bytes each
             for (unsigned m = need_rows; m; m &= m - 1) {
                 const int r = __ffs(m) - 1;
-                const float *src = a.f_rest + (size_t)(base_g + r) * 45;
+                const size_t row = (size_t)(base_g + r);
+                const float *src = a.f_rest + row * 45;
                 wrest[r * 45 + lane] = __ldg(src + lane);
                 if (lane < 13) wrest[r * 45 + 32 + lane] = __ldg(src + 32 + lane);
-                else if (lane < 16) wdc[r * 3 + (lane - 13)] = __ldg(a.shs + (size_t)(base_g + r) * 3 + (lane - 13));
+                else if (lane < 16) wdc[r * 3 + (lane - 13)] = __ldg(a.shs + row * 3 + (lane - 13));
             }
         }
         __syncwarp();
     }
     if (SHMODE == 1 && need_rows) {
-        const float4 *gsh = reinterpret_cast<const float4 *>(a.shs) + (size_t)base_g * 12;
+        const float4 *gsh = reinterpret_cast<const float4 *>(a.shs) + (size_t)(COMPACT ? 0 : base_g) * 12;
         if (whole_block) {
 #pragma unroll
             for (int i = 0; i < 12; i++) {
                 const int q = i * 32 + lane;
                 wbuf[(q / 12) * GB_ROW_Q + (q % 12)] = __ldg(gsh + q);
             }
+        } else if (COMPACT) {
+            if (need) {
+#pragma unroll
+                for (int i = 0; i < 12; i++) wbuf[lane * GB_ROW_Q + i] = __ldg(gsh + (size_t)idx * 12 + i);
+            }
         } else {
             for (unsigned m = need_rows; m; m &= m - 1) {
                 const int r = __ffs(m) - 1;
-                if (lane < 12) wbuf[r * GB_ROW_Q + lane] = __ldg(gsh + r * 12 + lane);
+                const size_t row = (size_t)r;
+                if (lane < 12) wbuf[r * GB_ROW_Q + lane] = __ldg(gsh + row * 12 + lane);
             }
         }
         __syncwarp();
@@ -795,7 +817,13 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
     if (!STAGED && need && !a.shs && dsh) {
         for (int k = 0; k < 3 * M; k++) dsh[k] = 0.f;
     }
-    if (STAGED) { // own row -> shared -> coalesced 128-bit stores of the warp's contiguous 32 x 192 B block
+    if (STAGED && COMPACT) { // scattered rows: every lane stores its own 192 B
+        if (write_out) {
+            float4 *d = reinterpret_cast<float4 *>(a.dL_dsh) + (size_t)idx * 12;
+#pragma unroll
+            for (int i = 0; i < 12; i++) d[i] = make_float4(shg[4 * i], shg[4 * i + 1], shg[4 * i + 2], shg[4 * i + 3]);
+        }
+    } else if (STAGED) { // own row -> shared -> coalesced 128-bit stores of the warp's contiguous 32 x 192 B block
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 12; i++)
@@ -844,6 +872,115 @@ __global__ void __launch_bounds__(GB_THREADS, 5) gaussian_backward_kernel(GaussB
         a.dL_dscales[3 * idx + 2] = dscale[2];
     }
     if (a.dL_drot) reinterpret_cast<float4 *>(a.dL_drot)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+}
+
+// A Gaussian the blend did not touch: all-zero gradients.  With the persistent-output rules (out_nz / ever, see
+// GaussBwdArgs) its rows are rewritten -- with zeros -- only if they held something.
+template <int SHMODE>
+__device__ __forceinline__ void gaussian_backward_untouched(const GaussBwdArgs &a, const int idx) {
+    bool write_out = true;
+    if (a.out_nz) {
+        write_out = a.out_nz[idx] != 0;
+        if (write_out) a.out_nz[idx] = 0;
+    }
+    if (a.ever) write_out = a.ever[idx] != 0;
+    if (!write_out) return;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.dL_dsh) {
+        if (SHMODE != 0) { // M == 16, 16-byte aligned rows
+            float4 *d = reinterpret_cast<float4 *>(a.dL_dsh) + (size_t)idx * 12;
+#pragma unroll
+            for (int i = 0; i < 12; i++) d[i] = z4;
+        } else {
+            float *d = a.dL_dsh + (size_t)idx * a.M * 3;
+            for (int k = 0; k < 3 * a.M; k++) d[k] = 0.f;
+        }
+    }
+    if (a.dL_dextra) a.dL_dextra[3 * idx] = a.dL_dextra[3 * idx + 1] = a.dL_dextra[3 * idx + 2] = 0.f;
+    if (a.dL_dmeans2D) a.dL_dmeans2D[3 * idx] = a.dL_dmeans2D[3 * idx + 1] = a.dL_dmeans2D[3 * idx + 2] = 0.f;
+    if (a.dL_dconic) reinterpret_cast<float4 *>(a.dL_dconic)[idx] = z4;
+    if (a.dL_dopacity) a.dL_dopacity[idx] = 0.f;
+    if (a.dL_dcolors) a.dL_dcolors[3 * idx] = a.dL_dcolors[3 * idx + 1] = a.dL_dcolors[3 * idx + 2] = 0.f;
+    a.dL_dmeans3D[3 * idx] = a.dL_dmeans3D[3 * idx + 1] = a.dL_dmeans3D[3 * idx + 2] = 0.f;
+    if (a.dL_dcov3D) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * idx + k] = 0.f;
+    }
+    if (a.dL_dscales) a.dL_dscales[3 * idx] = a.dL_dscales[3 * idx + 1] = a.dL_dscales[3 * idx + 2] = 0.f;
+    if (a.dL_drot) reinterpret_cast<float4 *>(a.dL_drot)[idx] = z4;
+}
+
+// The per-Gaussian pass.  One view touches about 1 % of a 1 M-Gaussian map: with a thread per Gaussian a third of all warps
+// ran the whole chain for one or two live lanes.  A block owns `chunks` x 128 consecutive Gaussians, collects the touched
+// ones in shared memory and runs the chain on the compacted list (one warp-chain per 32 touched Gaussians); the untouched
+// ones cost their flag bytes.  Blocks in which most Gaussians are touched (small object clouds) and callers without
+// persistent outputs (force_dense) keep the thread-per-Gaussian form with its whole-block staged SH loads and stores.
+#define GB_MAX_CHUNKS 16
+template <int SHMODE>
+__global__ void __launch_bounds__(GB_THREADS, 4) gaussian_backward_kernel(const GaussBwdArgs a) {
+    pdl_enter();
+    extern __shared__ float4 s_row[];
+    __shared__ int s_ids[GB_THREADS * GB_MAX_CHUNKS];
+    __shared__ int s_n;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int chunks = a.chunks; // 128-Gaussian chunks per block (host: sized so that the grid is about one wave)
+    const int first = blockIdx.x * (GB_THREADS * chunks);
+    if (tid == 0) s_n = 0;
+    __shared__ int s_total;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    unsigned tmask = 0;
+#pragma unroll 4
+    for (int c = 0; c < chunks; c++) { // independent loads: all in flight together
+        const int i = first + c * GB_THREADS + tid;
+        const bool t = i < a.P && a.touched[i] != 0;
+        tmask |= (t ? 1u : 0u) << c;
+    }
+    {
+        int cnt = __popc(tmask);
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        if ((tid & 31) == 0 && cnt) atomicAdd(&s_total, cnt);
+    }
+    __syncthreads();
+    const int total = s_total;
+    if (total == 0 && !a.force_dense) { // nothing touched: flags only
+        for (int c = 0; c < chunks; c++) {
+            const int i = first + c * GB_THREADS + tid;
+            if (i < a.P) gaussian_backward_untouched<SHMODE>(a, i);
+        }
+        return;
+    }
+    const bool dense = a.force_dense || 2 * total >= GB_THREADS * chunks;
+    int n = GB_THREADS * chunks;
+    if (!dense) {
+        for (int c = 0; c < chunks; c++) {
+            const int i = first + c * GB_THREADS + tid;
+            if ((tmask >> c) & 1u) s_ids[atomicAdd(&s_n, 1)] = i;
+            else if (i < a.P) gaussian_backward_untouched<SHMODE>(a, i);
+        }
+        __syncthreads();
+        n = s_n;
+    }
+    // one loop, one inlined copy of the chain: over the block's chunks (dense) or over the compacted list (sparse)
+#pragma unroll 1
+    for (int base = 0; base < n; base += GB_THREADS) {
+        int idx, base_g, nrow;
+        bool live;
+        if (dense) {
+            idx = first + base + tid;
+            live = idx < a.P;
+            base_g = first + base + warp * 32;
+            nrow = min(32, a.P - base_g);
+        } else {
+            const int j = base + tid;
+            live = j < n;
+            idx = live ? s_ids[j] : 0;
+            base_g = 0;
+            nrow = max(0, min(32, n - (base + warp * 32)));
+        }
+        gaussian_backward_body<SHMODE>(a, idx, live, base_g, nrow, s_row, !dense);
+        __syncwarp();
+    }
 }
 
 } // namespace dqo
@@ -992,7 +1129,17 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     ga.ever_list = (ever && ever_list && ever_count) ? ever_list : nullptr;
     ga.ever_count = ever_count;
     const bool staged = shs && !f_rest && dL_dsh && s->M == 16 && ((uintptr_t)shs % 16 == 0) && ((uintptr_t)dL_dsh % 16 == 0);
-    const int gb_blocks = (P + GB_THREADS - 1) / GB_THREADS;
+    // persistent outputs (rows that stay zero are not rewritten): blocks compact their touched Gaussians; otherwise every
+    // row is written anyway and the blocks keep the thread-per-Gaussian form
+    ga.force_dense = (ga.ever != nullptr || ga.out_nz != nullptr) ? 0 : 1;
+    // chunks per block: about one wave of blocks (148 SMs x 4) on large maps, where a block finds a few touched Gaussians
+    // per chunk and its latency is one chain; one chunk per block on small clouds, where the chains should run side by side
+    int chunks = (P + GB_THREADS * 592 - 1) / (GB_THREADS * 592);
+    chunks = chunks < 1 ? 1 : (chunks > GB_MAX_CHUNKS ? GB_MAX_CHUNKS : chunks);
+    if (ga.force_dense) chunks = 1;
+    ga.chunks = chunks;
+    const int per_block = GB_THREADS * chunks;
+    const int gb_blocks = (P + per_block - 1) / per_block;
     const size_t gb_smem = (size_t)(GB_THREADS / 32) * 32 * GB_ROW_Q * sizeof(float4);
     if (f_rest) {
         if (s->M != 16 || !dL_dsh || (uintptr_t)shs % 16 || (uintptr_t)f_rest % 16 || (uintptr_t)dL_dsh % 16) {

@@ -631,6 +631,13 @@ def test_raster_pipeline_matches_operator_path_over_a_window(cfg, binning):
                         dL_drotations=pipe.g_rot)
             for name, t in zip(GRADS, bw):
                 if name in mine and t.numel():
-                    assert torch.equal(mine[name].reshape(t.shape), t), (k, name)
+                    m = mine[name].reshape(t.shape)
+                    if not torch.equal(m, t):
+                        d = (m - t).abs()
+                        rows = (d.reshape(d.shape[0], -1) > 0).any(dim=1)
+                        raise AssertionError((k, name, "rows differing", int(rows.sum()), "max abs", float(d.max()),
+                                              "max |ref|", float(t.abs().max()), "worst rel",
+                                              float((d / (t.abs() + 1e-30))[d > 0].max()),
+                                              "rows zero in mine", int(((m.reshape(m.shape[0], -1) == 0).all(1) & rows).sum())))
     finally:
         rasterizer.set_binning_mode("single")
