@@ -9,11 +9,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # DQO_B200_LIB: another build of the same library (kernel A/B experiments, tests/dev_*.py); there is still no fallback
 LIB_PATH = os.environ.get("DQO_B200_LIB") or os.path.join(_HERE, "csrc", "libdqomap_b200.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 ST_NUM_RENDERED, ST_TILE_NUM, ST_OVERFLOW, ST_NUM_VISIBLE, ST_R_FRONT, ST_R_BACK, ST_WALKED, ST_UNFINISHED = range(8)
 ST_WORDS = 8
 ADAM_MAX_TENSORS = 16
+STEP_TERM_SSIM, STEP_TERM_SEMANTIC = 1, 2
 
 c_p = C.c_void_p
 
@@ -43,7 +44,7 @@ class MapParams(C.Structure):
                 ("attach_count", c_p), ("attach_weight", C.c_float), ("attach_opacity_thres", C.c_float),
                 ("step_state", c_p),
                 ("semantics", c_p), ("semantics_exp_avg", c_p), ("semantics_exp_avg_sq", c_p),
-                ("lr_semantics", C.c_double)]
+                ("lr_semantics", C.c_double), ("workspace_terms", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Keyframe(C.Structure):
@@ -104,8 +105,8 @@ PROTOTYPES = {
     "dqo_ssim_loss": (C.c_int, [C.c_int32, C.c_int32, c_p, c_p, C.c_float, c_p, C.c_int32, c_p, c_p, c_p]),
     "dqo_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                                 c_p, C.c_int32, c_p]),
-    "dqo_mapping_step_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
-    "dqo_mapping_step_workspace_init": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, c_p, c_p]),
+    "dqo_mapping_step_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
+    "dqo_mapping_step_workspace_init": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, c_p, c_p]),
     "dqo_mapping_step": (C.c_int, [C.POINTER(RastSettings), C.POINTER(MapParams), C.POINTER(Keyframe), C.c_int32,
                                    C.c_double, C.c_double, C.c_double, c_p, C.c_int64, c_p, c_p, c_p, c_p]),
     "dqo_attach_count": (C.c_int, [C.c_int32, c_p, C.c_float, c_p, c_p]),

@@ -13,7 +13,7 @@
 
 #define DQO_TILE 16
 #define DQO_TILE_PIX 256
-#define DQO_ABI_VERSION 13
+#define DQO_ABI_VERSION 14
 
 namespace dqo {
 

@@ -57,7 +57,7 @@ static size_t sbump(size_t &cur, size_t bytes) {
     cur = off + bytes;
     return off;
 }
-static int make_step_layout(int P, int M, int W, int H, int64_t capacity, StepLayout *L) {
+static int make_step_layout(int P, int M, int W, int H, int64_t capacity, int terms, StepLayout *L) {
     const size_t n = (size_t)(P > 0 ? P : 1), N = (size_t)W * H;
     const size_t tiles = (size_t)((W + 15) / 16) * ((H + 15) / 16);
     size_t cur = 0;
@@ -88,14 +88,16 @@ static int make_step_layout(int P, int M, int W, int H, int64_t capacity, StepLa
     L->g_scales = sbump(cur, n * 12);
     L->g_rot = sbump(cur, n * 16);
     L->adam = sbump(cur, 256);
-    L->ssim_ws = sbump(cur, dqo_ssim_workspace_bytes(W, H));
+    // the optional terms' regions exist only in workspaces sized for them (DQO_STEP_TERM_*)
+    const bool t_ssim = terms & DQO_STEP_TERM_SSIM, t_sem = terms & DQO_STEP_TERM_SEMANTIC;
     L->extra_loss = sbump(cur, 256);
-    L->sem_img = sbump(cur, N * 12);
-    L->g_sem = sbump(cur, N * 12);
-    L->g_sem_depth = sbump(cur, N * 4);
-    L->sem_loss_ws = sbump(cur, dqo_loss_workspace_bytes(W, H));
-    L->cacc = sbump(cur, n * 32);
-    L->g_semantics = sbump(cur, n * 12);
+    L->ssim_ws = sbump(cur, t_ssim ? dqo_ssim_workspace_bytes(W, H) : 0);
+    L->sem_img = sbump(cur, t_sem ? N * 12 : 0);
+    L->g_sem = sbump(cur, t_sem ? N * 12 : 0);
+    L->g_sem_depth = sbump(cur, t_sem ? N * 4 : 0);
+    L->sem_loss_ws = sbump(cur, t_sem ? dqo_loss_workspace_bytes(W, H) : 0);
+    L->cacc = sbump(cur, t_sem ? n * 32 : 0);
+    L->g_semantics = sbump(cur, t_sem ? n * 12 : 0);
     L->total = align_up(cur, 256);
     return 0;
 }
@@ -681,23 +683,25 @@ __global__ void __launch_bounds__(256) adam_semantics_kernel(SemAdamArgs a) {
 
 using namespace dqo;
 
-extern "C" size_t dqo_mapping_step_workspace_bytes(int32_t P, int32_t M, int32_t W, int32_t H, int64_t capacity) {
+extern "C" size_t dqo_mapping_step_workspace_bytes(int32_t P, int32_t M, int32_t W, int32_t H, int64_t capacity,
+                                                   int32_t terms) {
     StepLayout L;
-    if (make_step_layout(P, M, W, H, capacity, &L)) return 0;
+    if (make_step_layout(P, M, W, H, capacity, terms, &L)) return 0;
     return L.total;
 }
 
 extern "C" int dqo_rast_geom_init(int32_t P, void *geom_buffer, void *stream);
-extern "C" int dqo_mapping_step_workspace_init(int32_t P, int32_t M, int32_t W, int32_t H, int64_t capacity, void *workspace,
-                                               void *stream) {
+extern "C" int dqo_mapping_step_workspace_init(int32_t P, int32_t M, int32_t W, int32_t H, int64_t capacity, int32_t terms,
+                                               void *workspace, void *stream) {
     StepLayout L;
-    if (!workspace || make_step_layout(P, M, W, H, capacity, &L)) {
+    if (!workspace || make_step_layout(P, M, W, H, capacity, terms, &L)) {
         set_error("dqo_mapping_step_workspace_init: invalid argument");
         return DQO_ERR_INVALID_ARG;
     }
     const size_t tiles = (size_t)((W + 15) / 16) * ((H + 15) / 16);
     DQO_CUDA_CHECK(cudaMemsetAsync((char *)workspace + L.tile_indices, 0, tiles * 4, (cudaStream_t)stream));
-    DQO_CUDA_CHECK(cudaMemsetAsync((char *)workspace + L.cacc, 0, (size_t)(P > 0 ? P : 1) * 32, (cudaStream_t)stream));
+    if (terms & DQO_STEP_TERM_SEMANTIC)
+        DQO_CUDA_CHECK(cudaMemsetAsync((char *)workspace + L.cacc, 0, (size_t)(P > 0 ? P : 1) * 32, (cudaStream_t)stream));
     return dqo_rast_geom_init(P, (char *)workspace + L.geom, stream);
 }
 
@@ -723,7 +727,7 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
         }
     const int P = s->P, M = s->M, W = s->W, H = s->H;
     StepLayout L;
-    if (make_step_layout(P, M, W, H, capacity, &L)) return DQO_ERR_WORKSPACE;
+    if (make_step_layout(P, M, W, H, capacity, p->workspace_terms, &L)) return DQO_ERR_WORKSPACE;
     char *ws = (char *)workspace;
     float *act_op = (float *)(ws + L.act_opacity), *act_sc = (float *)(ws + L.act_scales), *act_rot = (float *)(ws + L.act_rot);
     float *xyz = p->param[0], *f_dc = p->param[1], *f_rest = (M == 16) ? p->param[2] : nullptr;
@@ -759,6 +763,10 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
     // the colour-gradient image the backward blend reads.
     float *extra_loss = (float *)(ws + L.extra_loss);
     const bool use_ssim = kf->ssim_weight > 0.f && !kf->render_mask;
+    if (use_ssim && !(p->workspace_terms & DQO_STEP_TERM_SSIM)) {
+        set_error("dqo_mapping_step: the workspace was not sized for the SSIM term (dqo_map_params.workspace_terms)");
+        return DQO_ERR_WORKSPACE;
+    }
     if (use_ssim) {
         rc = ssim_loss_impl(W, H, color, kf->gt_color, kf->ssim_weight, g_img, 1, extra_loss, ws + L.ssim_ws, stream_);
         if (rc) return rc;
@@ -766,6 +774,10 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
     // semantic term (mapper.py:877-880): the semantic image is one more blend over the lists of the main render
     const bool use_sem = kf->gt_semantic != nullptr && kf->semantic_weight > 0.f;
     ExtraBlendGrad xg;
+    if (use_sem && !(p->workspace_terms & DQO_STEP_TERM_SEMANTIC)) {
+        set_error("dqo_mapping_step: the workspace was not sized for the semantic term (dqo_map_params.workspace_terms)");
+        return DQO_ERR_WORKSPACE;
+    }
     if (use_sem) {
         if (!p->semantics || !p->semantics_exp_avg || !p->semantics_exp_avg_sq) {
             set_error("dqo_mapping_step: the semantic term needs dqo_map_params.semantics and its Adam state");
@@ -900,8 +912,8 @@ extern "C" int dqo_attach_count(int32_t P, const float *init_opacity, float opac
 // Read-only views into the step workspace for callers that want the rendered images of the last step
 extern "C" int dqo_mapping_step_outputs(int32_t P, int32_t M, int32_t W, int32_t H, int64_t capacity, void *workspace,
                                         float **color, float **depth, int32_t **hit_depth, float **T_map) {
-    StepLayout L;
-    if (!workspace || make_step_layout(P, M, W, H, capacity, &L)) return DQO_ERR_WORKSPACE;
+    StepLayout L; // (the optional regions lie behind everything this returns)
+    if (!workspace || make_step_layout(P, M, W, H, capacity, 0, &L)) return DQO_ERR_WORKSPACE;
     char *ws = (char *)workspace;
     if (color) *color = (float *)(ws + L.color);
     if (depth) *depth = (float *)(ws + L.depth);

@@ -209,6 +209,15 @@ int ssim_loss_impl(int32_t W, int32_t H, const float *image, const float *gt_col
         set_error("dqo_ssim_loss: invalid argument");
         return DQO_ERR_INVALID_ARG;
     }
+    // When this is the first runtime call of the process into this library, let the runtime load the kernels through its
+    // regular path before the extended launch (the launch otherwise probes an unloaded kernel first, which
+    // compute-sanitizer reports as an (internally handled) CUDA_ERROR_INVALID_HANDLE)
+    static const bool loaded = [] {
+        cudaFuncAttributes fa;
+        return cudaFuncGetAttributes(&fa, ssim_stats_kernel) == cudaSuccess &&
+               cudaFuncGetAttributes(&fa, ssim_grad_kernel) == cudaSuccess;
+    }();
+    (void)loaded;
     SsimArgs a;
     a.W = W; a.H = H; a.img = image; a.gt = gt_color;
     ssim_window(a.w);

@@ -220,6 +220,8 @@ class FusedMappingStep:
         self.p = params
         self.ssim_w, self.sem_w = float(ssim_weight), float(semantic_weight)
         self.has_sem = params.get("semantics") is not None and params["semantics"].numel() > 1
+        # the step workspace carries the scratch of the optional terms only when they can occur
+        self.terms = (_lib.STEP_TERM_SSIM if self.ssim_w > 0 else 0) | (_lib.STEP_TERM_SEMANTIC if self.has_sem else 0)
         self.front, self.back = int(front_instances), int(back_instances)
         for k in self.ORDER:
             t = params[k]
@@ -318,6 +320,7 @@ class FusedMappingStep:
                 mp.attach_count = ptr(self.attach_count)
             mp.attach_weight, mp.attach_opacity_thres = self.attach_weight, self.attach_thres
             mp.step_state = ptr(self.step_state)
+            mp.workspace_terms = self.terms
             if self.has_sem:
                 mp.semantics = ptr(self.p["semantics"])
                 mp.semantics_exp_avg, mp.semantics_exp_avg_sq = (ptr(t) for t in self.state["semantics"])
@@ -326,13 +329,14 @@ class FusedMappingStep:
         return self._mp
 
     def _alloc(self):
-        n = lib().dqo_mapping_step_workspace_bytes(self.P, self.M, self.W, self.H, self.capacity)
+        n = lib().dqo_mapping_step_workspace_bytes(self.P, self.M, self.W, self.H, self.capacity, self.terms)
         if n == 0:
             raise _lib.DqoError("workspace size query failed: %s" % lib().dqo_last_error().decode())
         self.ws = torch.empty((n,), dtype=torch.uint8, device=self.dev)
         # persistent workspace: gradient accumulators cleared once, kept clean by every step (settings.geom_clean)
         with torch.cuda.device(self.dev):
-            check(lib().dqo_mapping_step_workspace_init(self.P, self.M, self.W, self.H, self.capacity, ptr(self.ws), _stream()),
+            check(lib().dqo_mapping_step_workspace_init(self.P, self.M, self.W, self.H, self.capacity, self.terms, ptr(self.ws),
+                                                        _stream()),
                   "dqo_mapping_step_workspace_init")
 
     def _keyframe(self, rs, tile_mask, gt_color, gt_depth, render_mask, gt_semantic=None):

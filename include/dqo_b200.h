@@ -401,6 +401,10 @@ typedef struct dqo_map_params {
      * target (dqo_keyframe.gt_semantic); NULL otherwise. */
     float *semantics, *semantics_exp_avg, *semantics_exp_avg_sq;
     double lr_semantics;
+    /* The DQO_STEP_TERM_* mask the step workspace was sized and initialised with: a keyframe that asks for a term the
+     * workspace has no room for is refused (DQO_ERR_WORKSPACE). */
+    int32_t workspace_terms;
+    int32_t reserved;
 } dqo_map_params;
 typedef struct dqo_keyframe {
     const float *gt_color;      /* [H,W,3] */
@@ -420,10 +424,15 @@ typedef struct dqo_keyframe {
     float semantic_weight;
     const float *gt_semantic;   /* [H,W,3] or NULL */
 } dqo_keyframe;
-size_t dqo_mapping_step_workspace_bytes(int32_t P, int32_t M, int32_t W, int32_t H, int64_t instance_capacity);
+/* Optional loss terms a step workspace has room for (their scratch is 36 B per pixel for SSIM, 28 B per pixel + 44 B per
+ * Gaussian for the semantic term: not carried by workspaces that never use them). */
+#define DQO_STEP_TERM_SSIM 1
+#define DQO_STEP_TERM_SEMANTIC 2
+size_t dqo_mapping_step_workspace_bytes(int32_t P, int32_t M, int32_t W, int32_t H, int64_t instance_capacity,
+                                        int32_t terms /* DQO_STEP_TERM_* mask */);
 /* One-time initialisation of a freshly allocated step workspace: lets the step run with dqo_rast_settings.geom_clean = 1. */
-int dqo_mapping_step_workspace_init(int32_t P, int32_t M, int32_t W, int32_t H, int64_t instance_capacity, void *workspace,
-                                    void *stream);
+int dqo_mapping_step_workspace_init(int32_t P, int32_t M, int32_t W, int32_t H, int64_t instance_capacity, int32_t terms,
+                                    void *workspace, void *stream);
 /* loss_out: device float[8] {total, colour, depth, attach, ssim (1 - ssim), semantic, 0, 0} -- `total` is the reference's
  * `loss` (mapper.py:870-880, :904: every weighted term except the attach term); counts_out: device int32[2]; status: device int32[DQO_ST_WORDS]
  * (check DQO_ST_OVERFLOW together with the loss read-back; on overflow the render is invalid and the Adam update is
