@@ -71,6 +71,8 @@ PROTOTYPES = {
     "dqo_mark_visible": (C.c_int, [C.c_int32, c_p, c_p, c_p, c_p, c_p]),
     "dqo_rast_export_state": (C.c_int, [C.POINTER(RastSettings), c_p, c_p, C.c_int64, c_p, c_p] + [c_p] * 10 + [c_p]),
     "dqo_rast_blend_extra": (C.c_int, [C.POINTER(RastSettings), c_p, c_p, c_p, c_p, C.c_int64, c_p, c_p, c_p, c_p]),
+    "dqo_rast_blend_extra_backward": (C.c_int, [C.POINTER(RastSettings)] + [c_p] * 10 + [c_p, c_p, C.c_int64, c_p, c_p]
+                                      + [c_p, c_p] + [c_p] * 8 + [c_p]),
     "dqo_sort_pairs_temp_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "dqo_sort_pairs_u32": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int32, c_p, c_p, C.c_int64, C.c_int32, c_p, c_p]),
     "dqo_sort_pairs_u16": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int32, c_p, c_p, C.c_int64, C.c_int32, c_p, c_p]),

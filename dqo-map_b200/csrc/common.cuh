@@ -207,6 +207,7 @@ struct ExtraBlendGrad {
     const float *dL_dpix; // [3,H,W] gradient of the loss w.r.t. the extra image
     double *cacc;         // f64[4P] colour-gradient accumulators, zero on entry, left zero
     float *dL_dcolors;    // [P,3] out
+    int only;             // 1: the backward of the extra image alone (no main image, no depth, no SH gradients)
 };
 struct GeomLayout {
     size_t rec;        // float4[3P]: {x,y,conic.x,conic.y} {conic.z,opacity,power_reject,extent.y} {r,g,b,extent.x}

@@ -793,6 +793,7 @@ extern "C" int dqo_mapping_step(const dqo_rast_settings *s, const dqo_map_params
         if (rc) return rc;
         xg.colors = p->semantics; xg.dL_dpix = g_sem; xg.cacc = (double *)(ws + L.cacc);
         xg.dL_dcolors = (float *)(ws + L.g_semantics);
+        xg.only = 0;
     }
     float *g_means3D = (float *)(ws + L.g_means3D), *g_sh = (float *)(ws + L.g_sh), *g_op = (float *)(ws + L.g_opacity);
     float *g_sc = (float *)(ws + L.g_scales), *g_rot = (float *)(ws + L.g_rot);

@@ -1096,8 +1096,10 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     ra.dL_dpix = dL_dout_color; ra.dL_ddepth = dL_dout_depth; ra.hit_image = hit_image; ra.gacc = gacc;
     ra.touched = (uint8_t *)(geom + GL.touched);
     ra.extra_colors = nullptr; ra.cacc = nullptr;
-    launch_pdl(render_backward_kernel<false>, dim3(IL.T), dim3(RB_THREADS), 0, stream, ra);
-    DQO_LAUNCH_CHECK("render backward", s->debug, stream);
+    if (!(extra && extra->only)) {
+        launch_pdl(render_backward_kernel<false>, dim3(IL.T), dim3(RB_THREADS), 0, stream, ra);
+        DQO_LAUNCH_CHECK("render backward", s->debug, stream);
+    }
     if (extra) { // second colour set over the same lists: its image gradient, its colours, its own colour accumulators
         if (!extra->colors || !extra->dL_dpix || !extra->cacc || !extra->dL_dcolors) {
             set_error("dqo_rast_backward: incomplete extra colour set");
@@ -1154,4 +1156,30 @@ int dqo::rast_backward_impl(const dqo_rast_settings *s, const float *background,
     DQO_LAUNCH_CHECK("gaussian backward", s->debug, stream);
     stage_mark(stream, ST_GAUSS_BWD);
     return DQO_OK;
+}
+
+// Backward of dqo_rast_blend_extra: the gradient of a loss on the extra image w.r.t. its colours and -- through alpha and the
+// 2-D geometry -- w.r.t. the geometric inputs of the view held by the workspaces, which autograd adds to the main render's.
+extern "C" int dqo_rast_blend_extra_backward(const dqo_rast_settings *s, const float *background, const float *colors,
+                                             const float *means3D, const float *scales, const float *rotations,
+                                             const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix,
+                                             const float *campos, const int32_t *radii, void *geom_buffer,
+                                             const void *binning_buffer, int64_t capacity, const void *image_buffer,
+                                             const int32_t *status, const float *dL_dextra_image, void *color_acc,
+                                             float *dL_dcolors, float *dL_dmeans2D, float *dL_dconic, float *dL_dopacity,
+                                             float *dL_dmeans3D, float *dL_dcov3D, float *dL_dscales, float *dL_drotations,
+                                             void *stream_) {
+    if (!s || !colors || !dL_dextra_image || !color_acc || !dL_dcolors || !status) {
+        set_error("dqo_rast_blend_extra_backward: null pointer argument");
+        return DQO_ERR_INVALID_ARG;
+    }
+    ExtraBlendGrad xg;
+    xg.colors = colors; xg.dL_dpix = dL_dextra_image; xg.cacc = (double *)color_acc; xg.dL_dcolors = dL_dcolors;
+    xg.only = 1;
+    // (the main image's gradient, the depth gradient and the hit image are not read in this mode: placeholders)
+    return rast_backward_impl(s, background, means3D, nullptr, nullptr, nullptr, scales, rotations, cov3D_precomp, viewmatrix,
+                              projmatrix, campos, radii, geom_buffer, binning_buffer, capacity, image_buffer, status,
+                              dL_dextra_image, dL_dextra_image, status, dL_dmeans2D, dL_dconic, dL_dopacity, nullptr,
+                              dL_dmeans3D, dL_dcov3D, nullptr, dL_dscales, dL_drotations, nullptr, nullptr, nullptr,
+                              stream_, &xg);
 }

@@ -90,7 +90,7 @@ def _make_settings(P, D, M, W, H, tanfovx, tanfovy, cx, cy, scale_modifier, colo
 class ForwardState:
     """Everything the backward needs; plays the role of (geomBuffer, binningBuffer, imgBuffer, tile_indices,
     num_rendered, num_tile) in the reference."""
-    __slots__ = ("settings", "geom", "binning", "image", "tile_indices", "status", "capacity", "status_host")
+    __slots__ = ("settings", "geom", "binning", "image", "tile_indices", "status", "capacity", "status_host", "radii")
 
 
 def _forward_impl(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
@@ -187,6 +187,7 @@ def _forward_impl(background, means3D, colors, opacity, scales, rotations, scale
             _capacity_hint[key] = capacity if retry else max(_capacity_hint.get(key, 0), capacity)
         if not retry:
             break
+    st.radii = radii
     outs = (out_color, out_depth, out_hit_color, out_hit_depth, out_hit_cw, out_hit_dw, out_T, radii, n_touched)
     return st, outs
 
@@ -368,6 +369,50 @@ def blend_extra_colors(state, colors_precomp, background):
                                          ptr(state.binning), state.capacity, ptr(state.image), ptr(state.status),
                                          ptr(out), _stream()), "dqo_rast_blend_extra")
     return out
+
+
+class _BlendExtraColors(torch.autograd.Function):
+    """Differentiable form of `blend_extra_colors`: forward = one blend pass over the lists of the main render, backward =
+    one reverse blend + the per-Gaussian chain (`dqo_rast_blend_extra_backward`).  The geometric inputs are arguments only
+    so that autograd routes the extra image's share of their gradients to them."""
+
+    @staticmethod
+    def forward(ctx, colors, means3D, opacities, scales, rotations, state, rs):
+        ctx.state, ctx.rs, ctx.opacity_shape = state, rs, tuple(opacities.shape)
+        ctx.save_for_backward(colors, means3D, scales, rotations)
+        return blend_extra_colors(state, colors, rs.bg)
+
+    @staticmethod
+    def backward(ctx, grad_image):
+        st, rs = ctx.state, ctx.rs
+        colors, means3D, scales, rotations = ctx.saved_tensors
+        s = st.settings
+        P, dev = s.P, means3D.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        g_colors, g_means2D = torch.empty((P, 3), **f32), torch.empty((P, 3), **f32)
+        g_conic, g_opacity = torch.empty((P, 2, 2), **f32), torch.empty((P, 1), **f32)
+        g_means3D, g_cov3D = torch.empty((P, 3), **f32), torch.empty((P, 6), **f32)
+        g_scales, g_rot = torch.empty((P, 3), **f32), torch.empty((P, 4), **f32)
+        acc = torch.zeros((4 * P,), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().dqo_rast_blend_extra_backward(
+                s, ptr(_f32c(rs.bg)), ptr(_f32c(colors)), ptr(_f32c(means3D)), ptr(_f32c(scales)), ptr(_f32c(rotations)),
+                None, ptr(_f32c(rs.viewmatrix)), ptr(_f32c(rs.projmatrix)), ptr(_f32c(rs.campos)), ptr(st.radii),
+                ptr(st.geom), ptr(st.binning), st.capacity, ptr(st.image), ptr(st.status), ptr(_f32c(grad_image)),
+                ptr(acc), ptr(g_colors), ptr(g_means2D), ptr(g_conic), ptr(g_opacity), ptr(g_means3D), ptr(g_cov3D),
+                ptr(g_scales), ptr(g_rot), _stream()), "dqo_rast_blend_extra_backward")
+        return g_colors, g_means3D, g_opacity.reshape(ctx.opacity_shape), g_scales, g_rot, None, None
+
+
+def blend_extra_colors_grad(state, raster_settings, colors_precomp, means3D, opacities, scales, rotations):
+    """`blend_extra_colors` with gradients: what the reference obtains by running the whole rasterizer a second time with
+    colors_precomp and back-propagating through it (SLAM/render.py:227-262) -- the image is identical, the gradients reach
+    colors_precomp and, through alpha and the projected geometry, means3D / opacities / scales / rotations -- for one extra
+    blend forward and one reverse blend instead of a second preprocess + binning + sort + render.  `state` must be the
+    ForwardState of a forward pass over exactly these geometric inputs (scale/rotation form, not cov3D_precomp)."""
+    if state.settings.P == 0:
+        return blend_extra_colors(state, colors_precomp, raster_settings.bg)
+    return _BlendExtraColors.apply(colors_precomp, means3D, opacities, scales, rotations, state, raster_settings)
 
 
 def mark_visible(means3D, viewmatrix, projmatrix):

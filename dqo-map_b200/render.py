@@ -4,12 +4,12 @@ normal / index / transmission maps and, when the Gaussians carry them, the seman
 The reference obtains the two extra images by running the complete rasterizer two more times with colors_precomp
 (render.py:227-262); those calls are differentiable: with the default configuration (use_semantics, semantic_color_weight
 0.1) the L1 on "semantic_seg" back-propagates into the trainable `_semantics` group (gaussian_pointcloud.py:372-378) and
-into the geometry.  So:
-  * while autograd is recording and any input of an extra image requires grad, that image comes from a second full,
-    differentiable GaussianRasterizer call -- exactly the reference's graph;
-  * otherwise (evaluation renders: evaluate_render_range, error_gaussians_remove, get_render_output) the view is
-    preprocessed, binned and sorted once and each extra image is one additional blend pass over the same lists
-    (`dqo_rast_blend_extra`), bit-identical to what the extra full call returns."""
+into the geometry.  Here
+the view is preprocessed, binned and sorted ONCE and each extra image is one additional blend pass over the same lists
+(`dqo_rast_blend_extra`), bit-identical to what the extra full call returns; while autograd is recording and any input of
+an extra image requires grad, that pass is differentiable (`rasterizer.blend_extra_colors_grad`: one reverse blend + the
+per-Gaussian chain, `dqo_rast_blend_extra_backward`), its gradients reach the colour tensor and the geometry like those
+of the reference's second full call and are added to the main render's by autograd."""
 import torch
 
 from . import rasterizer
@@ -18,7 +18,7 @@ from . import rasterizer
 def render(raster_settings, gaussian_data, tile_mask=None):
     """gaussian_data: dict with xyz, opacity, scales, rotations, shs, normal and optional semantics_color / instance
     ([P,3] each), already activated, as `Renderer.render` receives it (render.py:180-186).  Returns the reference's result
-    dict (render.py:218-266).  Gradients flow through "render", "depth" and -- via the full differentiable path, see the
+    dict (render.py:218-266).  Gradients flow through "render", "depth" and -- via the differentiable extra blend, see the
     module docstring -- "semantic_seg" / "instance", as in the reference."""
     rs = raster_settings
     means3D = gaussian_data["xyz"]
@@ -47,9 +47,8 @@ def render(raster_settings, gaussian_data, tile_mask=None):
                 t is not None and t.requires_grad
                 for t in (c, means3D, gaussian_data["opacity"], gaussian_data["scales"], gaussian_data["rotations"]))
             if needs_grad:
-                results[name] = rast(means3D=means3D, opacities=gaussian_data["opacity"], shs=None, colors_precomp=c,
-                                     scales=gaussian_data["scales"], rotations=gaussian_data["rotations"],
-                                     cov3D_precomp=None, normal_w=gaussian_data.get("normal"), tile_mask=tile_mask)[0]
+                results[name] = rasterizer.blend_extra_colors_grad(state, rs, c, means3D, gaussian_data["opacity"],
+                                                                   gaussian_data["scales"], gaussian_data["rotations"])
             else:
                 with torch.no_grad():
                     results[name] = rasterizer.blend_extra_colors(state, c, rs.bg)

@@ -168,6 +168,19 @@ int dqo_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, c
 int dqo_rast_blend_extra(const dqo_rast_settings *s, const float *background, const float *colors,
                          const void *geom_buffer, const void *binning_buffer, int64_t instance_capacity,
                          const void *image_buffer, const int32_t *status, float *out_color, void *stream);
+/* Backward of dqo_rast_blend_extra (the reference back-propagates through its second full rasterizer call, SLAM/render.py:227-262
+ * + rasterizer_impl.cu:445-564): given dL/d(extra image) [3,H,W], writes the gradient w.r.t. the extra colours [P,3] and the
+ * extra image's contribution to the gradients of the geometric inputs of the view the workspaces hold (same tensors and
+ * meaning as dqo_rast_backward; autograd adds them to the main render's).  `color_acc`: f64[4P] device scratch, zero on entry
+ * (left zero).  Uses the per-Gaussian accumulators inside geom_buffer like dqo_rast_backward does. */
+int dqo_rast_blend_extra_backward(const dqo_rast_settings *s, const float *background, const float *colors /* [P,3] */,
+                                  const float *means3D, const float *scales, const float *rotations,
+                                  const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix,
+                                  const float *campos, const int32_t *radii, void *geom_buffer, const void *binning_buffer,
+                                  int64_t instance_capacity, const void *image_buffer, const int32_t *status,
+                                  const float *dL_dextra_image, void *color_acc, float *dL_dcolors, float *dL_dmeans2D,
+                                  float *dL_dconic, float *dL_dopacity, float *dL_dmeans3D, float *dL_dcov3D,
+                                  float *dL_dscales, float *dL_drotations, void *stream);
 
 /* Introspection for parity tests: re-materialises the reference's binning artefacts from the
  * private workspace in the reference's own formats (rasterizer_impl.h:29-66): 64-bit sorted keys

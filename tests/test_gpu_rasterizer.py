@@ -525,6 +525,63 @@ def test_render_semantic_image_is_differentiable_like_the_reference():
     assert torch.equal(res_ng["semantic_seg"], full.detach())
 
 
+@pytest.mark.parametrize("two_phase", [False, True])
+def test_differentiable_extra_blend_gradients_for_every_input(two_phase):
+    """f3 with gradients (`rasterizer.blend_extra_colors_grad`, `dqo_rast_blend_extra_backward`): a loss on the main image,
+    the depth AND the semantic image; the gradients of every leaf (semantic colours, positions, opacities, scales,
+    rotations) equal those of the reference's graph -- main call plus a second full rasterizer call with colors_precomp
+    (SLAM/render.py:187-246) -- for single-phase and two-phase binning."""
+    from dqo_map_b200 import render as render_mod
+    inp = rh.make_inputs("small", torch.device(DEV), mask="half")
+    cam = inp["cam"]
+    P, H, W = inp["xyz"].shape[0], cam.image_height, cam.image_width
+    g = torch.Generator().manual_seed(8)
+    rd = synthetic.RENDER_DEFAULTS
+    rs = rasterizer.GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        bg=torch.tensor([0.05, 0.1, 0.0], device=DEV), scale_modifier=1.0, viewmatrix=cam.world_view_transform,
+        projmatrix=cam.full_proj_transform, sh_degree=inp["sh_degree"], campos=cam.camera_center,
+        opaque_threshold=rd["opaque_threshold"], normal_threshold=rd["normal_threshold"],
+        depth_threshold=rd["depth_threshold"], prefiltered=False, debug=False, cx=cam.cx, cy=cam.cy)
+    w_img, w_sem = torch.randn(3, H, W, generator=g).to(DEV), torch.randn(3, H, W, generator=g).to(DEV)
+    w_dep = (0.1 * torch.randn(1, H, W, generator=g)).to(DEV)
+    sem0 = torch.rand(P, 3, generator=g).to(DEV)
+    names = ("sem", "xyz", "opacity", "scales", "rotations")
+
+    def leaves():
+        return {"sem": sem0.clone().requires_grad_(True), "xyz": inp["xyz"].clone().requires_grad_(True),
+                "opacity": inp["opacity"].clone().requires_grad_(True), "scales": inp["scales"].clone().requires_grad_(True),
+                "rotations": inp["rotations"].clone().requires_grad_(True)}
+
+    binning = ("single",)
+    if two_phase:
+        rasterizer.set_binning_mode("single")
+        R = rasterizer.rasterize_gaussians(*rh.raster_args(inp))[0]
+        binning = ("fixed", max(256, (R // 6) // 256 * 256), R + 1024)
+    rasterizer.set_binning_mode(*binning)
+    try:
+        a = leaves()
+        res = render_mod.render(rs, dict(xyz=a["xyz"], opacity=a["opacity"], scales=a["scales"], rotations=a["rotations"],
+                                         shs=inp["shs"], normal=None, semantics_color=a["sem"], instance=None),
+                                inp["tile_mask"])
+        ((res["render"] * w_img).sum() + (res["depth"] * w_dep).sum() + (res["semantic_seg"] * w_sem).sum()).backward()
+        b = leaves()
+        rast = rasterizer.GaussianRasterizer(rs)
+        kw = dict(means3D=b["xyz"], opacities=b["opacity"], scales=b["scales"], rotations=b["rotations"],
+                  tile_mask=inp["tile_mask"])
+        main = rast(shs=inp["shs"], **kw)
+        sem_img = rast(colors_precomp=b["sem"], **kw)[0]
+        ((main[0] * w_img).sum() + (main[1] * w_dep).sum() + (sem_img * w_sem).sum()).backward()
+    finally:
+        rasterizer.set_binning_mode("single")
+    assert torch.equal(res["semantic_seg"].detach(), sem_img.detach()) and torch.equal(res["render"].detach(), main[0].detach())
+    for n in names:
+        ga, gb = a[n].grad, b[n].grad
+        assert ga is not None and float(gb.abs().sum()) > 0, n
+        rel = float((ga - gb).norm() / gb.norm())
+        assert rel <= 1e-5, (n, rel)      # the same kernels and the same fp64 accumulation on both sides
+
+
 def _arbiter_inputs(inp, o, ex):
     cam = inp["cam"]
     rd = synthetic.RENDER_DEFAULTS
