@@ -683,7 +683,12 @@ def run_ours(a, world, rank, local_rank):
     ms_e2e_zero = timed(e2e_zero_edit_step, a.steps, a.warmup, dist_on, sampler)
     value = world * a.steps / (ms / 1000.0)
     e2e_value = world * a.steps / (ms_e2e / 1000.0)
-    optional = optional_terms(inp, views[0], dev, P, W, H, front, back, two_phase, R_max) if inp["sh_degree"] == 3 else None
+    optional = None
+    if inp["sh_degree"] == 3:
+        try:  # auxiliary numbers: never let them take the headline line down
+            optional = optional_terms(inp, views[0], dev, P, W, H, front, back, two_phase, R_max)
+        except Exception as e:
+            optional = {"error": "%s: %s" % (type(e).__name__, e)}
 
     # per-stage CUDA-event timing on the launching stream (separate short run, not part of `value`)
     L.dqo_profile_enable(1)
