@@ -148,14 +148,21 @@ class FusedAdam(torch.optim.Optimizer):
 class MappingStep:
     """One iteration of the reference's mapping hot loop (mapper.py:568-599 + loss_update :799-928) with the
     B200 operators plugged in: activations (torch) -> rasterize (C-ABI) -> masked L1 loss (C-ABI) -> backward
-    (C-ABI + torch activations) -> fused Adam (C-ABI) with the confidence bump."""
+    (C-ABI + torch activations) -> fused Adam (C-ABI) with the confidence bump.  Optional terms as in loss_update: with
+    `ssim_weight` > 0 calls without a render mask add ssim_weight * (1 - ssim) (mapper.py:839-841, `ssim_loss`); when
+    `params` holds "semantics" [P,3] and the call passes `gt_semantic`, semantic_weight * masked L1 of the semantic image
+    (mapper.py:877-880), rendered and back-propagated over the lists of the main render (`blend_extra_colors_grad`)."""
 
     def __init__(self, params, lrs, settings_fn, color_weight=0.8, depth_weight=1.0, depth_err_thres=0.1,
-                 confidence=None, optimizer="fused"):
+                 confidence=None, optimizer="fused", ssim_weight=0.0, semantic_weight=0.1):
         # params: dict with raw leaf tensors xyz[P,3], f_dc[P,1,3], f_rest[P,M-1,3], opacity[P,1], scaling[P,3], rotation[P,4]
+        # and optionally semantics[P,3] (parameter group "semantics_color", gaussian_pointcloud.py:371-378)
         self.p = params
+        self.ssim_w, self.sem_w = float(ssim_weight), float(semantic_weight)
         groups = [{"params": [params[k]], "lr": lrs[k], "name": k}
                   for k in ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")]
+        if params.get("semantics") is not None:
+            groups.append({"params": [params["semantics"]], "lr": lrs["semantics"], "name": "semantics_color"})
         if optimizer == "fused":
             self.opt = FusedAdam(groups, lr=0.0, eps=1e-15, confidence=confidence, confidence_param=params["f_dc"])
         else:
@@ -171,15 +178,26 @@ class MappingStep:
                     rotations=torch.nn.functional.normalize(p["rotation"]),
                     shs=torch.cat((p["f_dc"], p["f_rest"]), dim=1))
 
-    def __call__(self, frame, tile_mask, gt_color, gt_depth, render_mask):
-        from .rasterizer import GaussianRasterizer
+    def __call__(self, frame, tile_mask, gt_color, gt_depth, render_mask, gt_semantic=None):
+        from .rasterizer import GaussianRasterizer, _RasterizeGaussians, blend_extra_colors_grad
         a = self.activated()
-        rast = GaussianRasterizer(self.settings_fn(frame))
+        rs = self.settings_fn(frame)
+        rast = GaussianRasterizer(rs)
         color, depth, hit_color, hit_depth, hcw, hdw, T_map, n_touched, radii = rast(
             means3D=a["xyz"], opacities=a["opacity"], shs=a["shs"], scales=a["scales"], rotations=a["rotations"],
             tile_mask=tile_mask)
         total, lc, ld, counts = masked_l1_loss(color, depth, hit_depth, gt_color, gt_depth, render_mask, self.cw,
                                                self.dw, self.thr)
+        self.ssim_value = self.semantic_value = None
+        if render_mask is None and self.ssim_w > 0:
+            self.ssim_value = ssim_loss(color, gt_color)
+            total = total + self.ssim_w * self.ssim_value
+        if gt_semantic is not None and self.p.get("semantics") is not None:
+            sem = blend_extra_colors_grad(_RasterizeGaussians.last_state, rs, self.p["semantics"], a["xyz"], a["opacity"],
+                                          a["scales"], a["rotations"]).permute(1, 2, 0)
+            m = render_mask.bool() if render_mask is not None else torch.ones(sem.shape[:2], dtype=torch.bool, device=sem.device)
+            self.semantic_value = torch.abs(sem[m] - gt_semantic[m]).mean()
+            total = total + self.sem_w * self.semantic_value
         total.backward()
         self.opt.step()
         if not self.fused and self.confidence is not None:

@@ -130,7 +130,7 @@ def _torch_loop(raw, settings, tile_mask, gt_color, gt_depth, render_mask, iters
         total.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
-        rows.append((float(total), float(ssim_l), float(sem_l)))
+        rows.append((float(total.detach()), float(ssim_l.detach()), float(sem_l.detach())))
     return params, rows
 
 
@@ -241,3 +241,26 @@ def test_fused_step_semantic_term_graph_replay_and_clean_accumulators():
     for a, b in zip(eager, replay):
         assert abs(a - b) <= 2e-4 * abs(a), (eager, replay)
     assert _close_after_adam(p_e["semantics"], p_g["semantics"], 5e-4)
+
+
+def test_operator_path_mapping_step_with_optional_terms_matches_the_literal_loop():
+    """`MappingStep` (autograd operator path) with the SSIM and semantic terms: per-step losses follow the literal torch
+    loop of loss_update, whose semantic image is a second full rasterizer call."""
+    gt, cam, settings, raw, gt_color, gt_depth, render_mask, gt_sem = _semantic_scene(P=4000)
+    iters = 4
+    lrs = dict(LRS_OP, semantics=5e-4)
+    for mask, ssim_w in ((render_mask, 0.0), (None, 0.2)):
+        _, rows = _torch_loop(raw, settings, gt["tile_mask"], gt_color, gt_depth, mask, iters, ssim_weight=ssim_w,
+                              gt_semantic=gt_sem)
+        params = {k: torch.nn.Parameter(v.clone()) for k, v in raw.items()}
+        ms = mapping.MappingStep(params, lrs, lambda _f: settings(), 0.8, 1.0, 0.1, optimizer="torch", ssim_weight=ssim_w,
+                                 semantic_weight=0.1)
+        for i in range(iters):
+            total, _, _ = ms(None, gt["tile_mask"], gt_color, gt_depth, mask, gt_semantic=gt_sem)
+            assert abs(float(total) - rows[i][0]) <= 3e-4 * abs(rows[i][0]), (i, float(total), rows[i])
+            assert abs(float(ms.semantic_value) - rows[i][2]) <= 3e-4 * abs(rows[i][2])
+            if mask is None:
+                assert abs(float(ms.ssim_value) - rows[i][1]) <= 3e-4 * abs(rows[i][1]) + 1e-6
+            else:
+                assert ms.ssim_value is None
+        assert float((params["semantics"].detach() - raw["semantics"]).abs().max()) > 1e-3
