@@ -38,6 +38,35 @@ def test_struct_layouts():
     assert ctypes.sizeof(_lib.AdamTensor) == 4 * 8 + 8 + 8 + 4 + 4
 
 
+def test_struct_layouts_match_the_header_as_a_c_compiler_sees_it(tmp_path):
+    """Every struct that crosses the boundary: size and the offset of every field, from a C program compiled against
+    include/dqo_b200.h (gcc, plain C: the header must stay C-compatible), against the ctypes mirrors in _lib.py."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {"dqo_rast_settings": _lib.RastSettings, "dqo_adam_tensor": _lib.AdamTensor, "dqo_map_params": _lib.MapParams,
+             "dqo_keyframe": _lib.Keyframe}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dqo_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = {}
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        cname, fname, value = line.split()
+        got[(cname, fname)] = int(value)
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_invalid_arguments_are_reported_without_a_gpu():
     L = _lib.lib()
     assert L.dqo_mark_visible(-1, None, None, None, None, None) == -1
