@@ -23,6 +23,29 @@ def test_header_and_binding_agree():
     assert sorted(_lib.PROTOTYPES) == declared
 
 
+def _declared_parameter_counts():
+    """name -> number of parameters of every prototype in the header (comments stripped; `(void)` = 0)."""
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    counts = {}
+    for m in re.finditer(r"\b(dqo_[a-z0-9_]+)\s*\(", text):
+        depth, i = 1, m.end()
+        while depth:
+            depth += {"(": 1, ")": -1}.get(text[i], 0)
+            i += 1
+        params = text[m.end():i - 1].strip()
+        if text[i:].lstrip()[:1] != ";":
+            continue  # not a prototype
+        counts[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    return counts
+
+
+def test_binding_argument_counts_match_the_header():
+    counts = _declared_parameter_counts()
+    assert sorted(counts) == sorted(_lib.PROTOTYPES)
+    for name, (_res, args) in _lib.PROTOTYPES.items():
+        assert len(args) == counts[name], (name, len(args), counts[name])
+
+
 def test_library_exports_every_symbol():
     assert os.path.exists(_lib.LIB_PATH), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
     h = ctypes.CDLL(_lib.LIB_PATH)
