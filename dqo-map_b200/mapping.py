@@ -405,6 +405,37 @@ class FusedMappingStep:
                 check(lib().dqo_mapping_step(*args, _stream()), "dqo_mapping_step")
         return self._loss_views
 
+    def optimize_window(self, keyframes, iters, rng=None, attach=True):
+        """The iteration loop of `Mapping.local_optimize` (mapper.py:531-599) on this step: `begin_window` (fresh Adam,
+        attach anchors), then `iters` iterations, each on a randomly chosen keyframe of the window during the first half
+        and on the newest keyframe afterwards (:573-575).  keyframes: sequence of dicts with rs, tile_mask, gt_color,
+        gt_depth and optionally render_mask / gt_semantic (the tensors of `processed_frames` / `processed_map` and the masks
+        of `evaluate_render_range`).  Nothing synchronises inside the loop; the overflow counter is read once at its end:
+        steps the device skipped because a keyframe outgrew the instance buffers are repeated (on the newest keyframe, like
+        the second half of the window) after the workspace has been re-sized for what the device reported.  Returns the
+        keyframe index of every iteration that was enqueued."""
+        import random
+        rng = rng or random
+        self.begin_window(attach=attach)
+        used = []
+
+        def run(n, first):
+            for it in range(first, first + n):
+                idx = rng.randint(0, len(keyframes) - 1)
+                if it > iters / 2:
+                    idx = len(keyframes) - 1
+                kf = keyframes[idx]
+                self(kf["rs"], kf["tile_mask"], kf["gt_color"], kf["gt_depth"], kf.get("render_mask"), kf.get("gt_semantic"))
+                used.append(idx)
+
+        run(iters, 0)
+        for _ in range(6):
+            skipped = self.check(auto_resize=True)
+            if not isinstance(skipped, int):    # the status words: nothing was skipped
+                return used
+            run(skipped, iters)
+        raise _lib.DqoError("optimize_window: instance buffers still overflow after six re-sizes")
+
     def graph(self, rs, tile_mask, gt_color, gt_depth, render_mask=None, warmup=True, gt_semantic=None):
         """CUDA graph of this keyframe's step: `g = step.graph(...); g.replay()` runs one iteration with a single launch.
         Possible because nothing in the step depends on a host value that changes between iterations (the Adam step

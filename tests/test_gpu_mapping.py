@@ -631,3 +631,43 @@ def test_fused_step_outputs_outside_a_changing_tile_mask_are_fill_values():
         fresh.check()
         for name, a, b in zip(("color", "depth", "hit_depth", "T"), st.rendered(), fresh.rendered()):
             assert torch.equal(a, b), (k, name)
+
+
+def test_optimize_window_follows_local_optimize_and_recovers_from_overflow():
+    """`FusedMappingStep.optimize_window` = the loop of Mapping.local_optimize (mapper.py:531-599): random keyframe in the
+    first half, the newest one afterwards; bit-identical to the same calls issued by hand.  With instance buffers that are
+    too small for the window the skipped steps are repeated after an automatic re-size: the Adam step count still equals
+    the number of iterations and the result stays finite."""
+    import random
+    gt, cam, settings, raw, gt_color, gt_depth, render_mask = _scene(P=20000, deg=3)
+    H, W = cam.image_height, cam.image_width
+    kfs = [dict(rs=settings(), tile_mask=gt["tile_mask"], gt_color=gt_color, gt_depth=gt_depth, render_mask=render_mask),
+           dict(rs=settings(), tile_mask=gt["tile_mask"], gt_color=gt_color.clone(), gt_depth=gt_depth.clone(), render_mask=None)]
+    iters = 8
+
+    p_a = {k: v.clone().contiguous() for k, v in raw.items()}
+    st_a = mapping.FusedMappingStep(p_a, LRS_OP, W, H, 0.8, 1.0, 0.1)
+    used = st_a.optimize_window(kfs, iters, rng=random.Random(3))
+    assert len(used) == iters and all(u == 1 for u in used[iters // 2 + 1:]) and st_a.step == iters
+
+    p_b = {k: v.clone().contiguous() for k, v in raw.items()}
+    st_b = mapping.FusedMappingStep(p_b, LRS_OP, W, H, 0.8, 1.0, 0.1)
+    st_b.begin_window(attach=True)
+    for idx in used:
+        kf = kfs[idx]
+        st_b(kf["rs"], kf["tile_mask"], kf["gt_color"], kf["gt_depth"], kf["render_mask"])
+    st_b.check()
+    for k in p_a:
+        assert torch.equal(p_a[k], p_b[k]), k
+
+    # two-phase binning with a back region that cannot hold the window: every step overflows at first
+    R = st_a.check()[_lib.ST_NUM_RENDERED]
+    front = max(256, (R // 10) // 256 * 256)
+    p_c = {k: v.clone().contiguous() for k, v in raw.items()}
+    st_c = mapping.FusedMappingStep(p_c, LRS_OP, W, H, 0.8, 1.0, 0.1, capacity=front + 256, front_instances=front,
+                                    back_instances=256)
+    used_c = st_c.optimize_window(kfs, iters, rng=random.Random(3))
+    assert st_c.step == iters and len(used_c) >= 2 * iters - 1 and st_c.back > 256
+    for k in p_c:
+        assert bool(torch.isfinite(p_c[k]).all()), k
+        assert float((p_c[k] - raw[k]).abs().max()) > 0 or LRS_OP[k] == 0
