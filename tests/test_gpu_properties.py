@@ -5,7 +5,6 @@ padding, SSIM against its float64 oracle on arbitrary small shapes."""
 import os
 import sys
 
-import numpy as np
 import pytest
 import torch
 from hypothesis import given, settings, strategies as st
@@ -14,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import refharness as rh  # noqa: E402
 from oracle import ssim_oracle as so  # noqa: E402
-from dqo_map_b200 import _lib, mapping, rasterizer  # noqa: E402
+from dqo_map_b200 import mapping, rasterizer  # noqa: E402
 from test_gpu_sort import reference_sort, run_sort  # noqa: E402
 
 pytestmark = pytest.mark.gpu

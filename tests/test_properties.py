@@ -3,7 +3,6 @@ to the example-based tests.  No GPU, no compute call into the library."""
 import os
 import sys
 
-import numpy as np
 import torch
 from hypothesis import given, settings, strategies as st
 
