@@ -106,3 +106,22 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libdqomap_b200.so")
     with pytest.raises(_lib.DqoError, match="no CPU fallback"):
         _lib.lib()
+
+
+def test_workspace_size_queries_without_a_gpu():
+    """Host-only size queries: the optional loss terms enlarge the step workspace by exactly their scratch, and only when
+    asked for (DQO_STEP_TERM_*)."""
+    L = _lib.lib()
+    P, M, W, H, cap = 100_000, 16, 640, 480, 1 << 20
+    N = W * H
+    base = L.dqo_mapping_step_workspace_bytes(P, M, W, H, cap, 0)
+    with_ssim = L.dqo_mapping_step_workspace_bytes(P, M, W, H, cap, _lib.STEP_TERM_SSIM)
+    with_sem = L.dqo_mapping_step_workspace_bytes(P, M, W, H, cap, _lib.STEP_TERM_SEMANTIC)
+    both = L.dqo_mapping_step_workspace_bytes(P, M, W, H, cap, _lib.STEP_TERM_SSIM | _lib.STEP_TERM_SEMANTIC)
+    assert 0 < base < with_ssim < both and base < with_sem < both
+    ssim_ws = L.dqo_ssim_workspace_bytes(W, H)
+    assert ssim_ws >= 9 * N * 4 and abs((with_ssim - base) - ssim_ws) <= 512          # 256-byte alignment slack
+    sem_scratch = 28 * N + 44 * P + L.dqo_loss_workspace_bytes(W, H)
+    assert abs((with_sem - base) - sem_scratch) <= 6 * 256
+    assert abs((both - base) - (ssim_ws + sem_scratch)) <= 8 * 256
+    assert L.dqo_ssim_workspace_bytes(0, H) == 0
